@@ -1,0 +1,271 @@
+/*
+ * uvs.h — C ABI of libuvs_b200.so: the B200-native replacement for the sliding-window
+ * backend solve of UV-SLAM (vins_estimator).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / POD structs and returns an
+ * int status (0 = ok, negative = UvsStatus error).  No C++ or torch types cross this boundary.
+ * All host buffers are caller-owned; all device memory lives behind the opaque UvsHandle.
+ *
+ * Reference interfaces replaced (paths relative to the UV-SLAM checkout):
+ *   void Estimator::optimization()                           vins_estimator/src/estimator.h:52,
+ *                                                            estimator.cpp:761-1233
+ *   bool ceres::CostFunction::Evaluate(double const* const*, double*, double**) const
+ *        IMUFactor                                           factor/imu_factor.h:12,19
+ *        ProjectionFactor                                    factor/projection_factor.h:12,17
+ *        ProjectionTdFactor                                  factor/projection_td_factor.h:10
+ *        AutoDiffCostFunction<LineProjectionFactor,2,7,4>    estimator.cpp:916-918
+ *        AutoDiffCostFunction<VPProjectionFactor,1,7,4>      estimator.cpp:923-925
+ *        MarginalizationFactor                               factor/marginalization_factor.h:74-81
+ *   MarginalizationInfo::{preMarginalize,marginalize}        factor/marginalization_factor.cpp:110-297
+ *   ceres::Solve (SPARSE_SCHUR + LEVENBERG_MARQUARDT)        estimator.cpp:982-994
+ *
+ * Layout conventions (identical to the reference's parameter blocks, estimator.cpp:526-594):
+ *   pose block        [px,py,pz,qx,qy,qz,qw]            7 doubles, tangent size 6
+ *   speed-bias block  [v(3), ba(3), bg(3)]              9 doubles
+ *   inverse depth     [lambda]                          1 double
+ *   line block        [psi_x, psi_y, psi_z, phi]        4 doubles (orthonormal Pluecker)
+ * Jacobians in "Ceres layout" are row-major num_residuals x global_block_size, blocks of one
+ * factor concatenated in parameter-block order; "local layout" keeps only the tangent columns
+ * (first 6 of every 7-wide pose block, pose_local_parameterization.cpp:20-27).
+ */
+#ifndef UVS_H_
+#define UVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVS_ABI_VERSION 1
+
+typedef enum UvsStatus {
+  UVS_OK = 0,
+  UVS_ERR_INVALID_ARG = -1,
+  UVS_ERR_CUDA = -2,
+  UVS_ERR_CAPACITY = -3,
+  UVS_ERR_NOT_FINITE = -4,      /* non-finite cost / step */
+  UVS_ERR_NOT_PD = -5,          /* reduced camera system not positive definite */
+  UVS_ERR_NO_WINDOW = -6,       /* call needs an uploaded window */
+  UVS_ERR_COMM = -7,            /* multi-GPU exchange failed */
+  UVS_ERR_UNSUPPORTED = -8
+} UvsStatus;
+
+/* kinds of parameter block a marginalization prior can refer to */
+typedef enum UvsBlockKind {
+  UVS_BLOCK_POSE = 0,       /* id = frame index, global 7 / local 6 */
+  UVS_BLOCK_SPEEDBIAS = 1,  /* id = frame index, 9 */
+  UVS_BLOCK_EXPOSE = 2,     /* id = 0, global 7 / local 6 */
+  UVS_BLOCK_TD = 3          /* id = 0, 1 */
+} UvsBlockKind;
+
+/* marginalization_flag of the reference (estimator.h:26-30) */
+typedef enum UvsMarginFlag { UVS_MARGIN_OLD = 0, UVS_MARGIN_SECOND_NEW = 1 } UvsMarginFlag;
+
+/*
+ * One sliding window ("uvs_window v1").  Pointers address caller-owned host memory.
+ * State arrays are read by uvs_upload_windows and written by uvs_download_state.
+ */
+typedef struct UvsWindow {
+  int32_t n_frames;           /* WINDOW_SIZE + 1 (11 in the reference, parameters.h:12) */
+  int32_t n_points;           /* eligible point features  (estimator.cpp:826-829) */
+  int32_t n_lines;            /* eligible line features   (estimator.cpp:873-878) */
+  int32_t n_proj;             /* point reprojection factors */
+  int32_t n_line_obs;         /* line reprojection factors */
+  int32_t n_vp_obs;           /* vanishing-point factors */
+  int32_t n_imu;              /* IMU factors */
+  int32_t prior_n;            /* residual dimension of the marginalization prior, 0 = none */
+  int32_t prior_n_blocks;     /* number of kept parameter blocks of the prior */
+  int32_t estimate_extrinsic; /* 0: ex_pose constant (estimator.cpp:786-790) */
+  int32_t estimate_td;        /* 0: ProjectionFactor, 1: ProjectionTdFactor (estimator.cpp:846-863) */
+  int32_t reserved0;
+
+  /* ---- state (parameter blocks) ---- */
+  double *pose;        /* [n_frames][7] */
+  double *speed_bias;  /* [n_frames][9] */
+  double *ex_pose;     /* [7] */
+  double *td;          /* [1] */
+  double *inv_depth;   /* [n_points] */
+  double *ortho;       /* [n_lines][4] */
+
+  /* ---- point reprojection factors (projection_factor.h:12) ---- */
+  const int32_t *proj_frame_i; /* [n_proj] start frame of the feature */
+  const int32_t *proj_frame_j; /* [n_proj] observing frame, != frame_i */
+  const int32_t *proj_point;   /* [n_proj] index into inv_depth */
+  const double *proj_pts_i;    /* [n_proj][3] normalised image point in frame i (z = 1) */
+  const double *proj_pts_j;    /* [n_proj][3] */
+  /* time-offset variant only (projection_td_factor.h:10); may be NULL when !estimate_td */
+  const double *proj_vel_i;    /* [n_proj][2] */
+  const double *proj_vel_j;    /* [n_proj][2] */
+  const double *proj_td_i;     /* [n_proj] td at which pts_i was taken */
+  const double *proj_td_j;     /* [n_proj] */
+  const double *proj_row_i;    /* [n_proj] raw image row uv.y (ROW/2 is subtracted inside) */
+  const double *proj_row_j;    /* [n_proj] */
+
+  /* ---- line reprojection factors (line_projection_factor.h:11-68) ---- */
+  const int32_t *line_frame;   /* [n_line_obs] observing frame */
+  const int32_t *line_idx;     /* [n_line_obs] index into ortho */
+  const double *line_sp;       /* [n_line_obs][2] start point, z = 1 implied */
+  const double *line_ep;       /* [n_line_obs][2] end point */
+  /* ---- vanishing-point factors (vp_projection_factor.h:14-73) ---- */
+  const int32_t *vp_frame;     /* [n_vp_obs] */
+  const int32_t *vp_line;      /* [n_vp_obs] */
+  const double *vp_dir;        /* [n_vp_obs][3] vp = (x/z, y/z, 1) */
+  /* extrinsics frozen into the line / VP functors at construction (estimator.cpp:917,924) */
+  const double *line_ric;      /* [9] row-major 3x3 */
+  const double *line_tic;      /* [3] */
+
+  /* ---- IMU factors: constants of IntegrationBase (integration_base.h:188-207) ---- */
+  const int32_t *imu_frame_i;  /* [n_imu] factor links frame_i and frame_i + 1 */
+  const double *imu_delta_p;   /* [n_imu][3] */
+  const double *imu_delta_q;   /* [n_imu][4]  x,y,z,w */
+  const double *imu_delta_v;   /* [n_imu][3] */
+  const double *imu_sum_dt;    /* [n_imu] */
+  const double *imu_lin_ba;    /* [n_imu][3] linearized_ba */
+  const double *imu_lin_bg;    /* [n_imu][3] linearized_bg */
+  const double *imu_jacobian;  /* [n_imu][15*15] row-major */
+  const double *imu_covariance;/* [n_imu][15*15] row-major */
+
+  /* ---- marginalization prior (marginalization_factor.h:52-71) ---- */
+  const double *prior_J;           /* [prior_n][prior_n] row-major linearized_jacobians */
+  const double *prior_r;           /* [prior_n] linearized_residuals */
+  const int32_t *prior_block_kind; /* [prior_n_blocks] UvsBlockKind, in column order */
+  const int32_t *prior_block_id;   /* [prior_n_blocks] */
+  const double *prior_x0;          /* global-size linearisation points, concatenated */
+} UvsWindow;
+
+/* Globals of parameters.h:11-47 that the hot path reads, plus Ceres' trust-region defaults. */
+typedef struct UvsOptions {
+  double focal_length;       /* FOCAL_LENGTH; sqrt_info = focal/1.6 * I2 (estimator.cpp:17) */
+  double gravity[3];         /* G */
+  double line_factor;        /* LINE_FACTOR */
+  double vp_factor;          /* VP_FACTOR */
+  double cauchy_point;       /* CauchyLoss scale a for points (estimator.cpp:765) */
+  double cauchy_line;        /* (estimator.cpp:768) */
+  double cauchy_vp;          /* (estimator.cpp:772) */
+  double tr;                 /* TR rolling-shutter read-out time */
+  double row;                /* ROW image height */
+  /* ceres::Solver::Options, defaults unless the reference sets them (estimator.cpp:982-991) */
+  int32_t max_num_iterations;    /* NUM_ITERATIONS */
+  int32_t fixed_iterations;      /* 1: disable convergence exits (benchmark mode) */
+  double max_solver_time;        /* seconds; <= 0 disables the wall-clock cap */
+  double initial_radius;         /* 1e4 */
+  double max_radius;             /* 1e16 */
+  double min_radius;             /* 1e-32 */
+  double min_relative_decrease;  /* 1e-3 */
+  double min_lm_diagonal;        /* 1e-6 */
+  double max_lm_diagonal;        /* 1e32 */
+  double function_tolerance;     /* 1e-6 */
+  double gradient_tolerance;     /* 1e-10 */
+  double parameter_tolerance;    /* 1e-8 */
+} UvsOptions;
+
+#define UVS_MAX_ITER_LOG 64
+
+typedef enum UvsTermination {
+  UVS_TERM_NO_CONVERGENCE = 0,   /* iteration cap */
+  UVS_TERM_FUNCTION_TOL = 1,
+  UVS_TERM_PARAMETER_TOL = 2,
+  UVS_TERM_GRADIENT_TOL = 3,
+  UVS_TERM_MIN_RADIUS = 4,
+  UVS_TERM_FAILURE = 5,
+  UVS_TERM_TIME = 6
+} UvsTermination;
+
+/* Counterpart of ceres::Solver::Summary for one window. */
+typedef struct UvsSummary {
+  int32_t num_iterations;          /* summary.iterations.size(): includes iteration 0 */
+  int32_t num_successful_steps;
+  int32_t termination;             /* UvsTermination */
+  int32_t status;                  /* UvsStatus of this window */
+  double initial_cost;
+  double final_cost;
+  double cost[UVS_MAX_ITER_LOG];             /* cost after each iteration */
+  double radius[UVS_MAX_ITER_LOG];           /* trust-region radius after each iteration */
+  double relative_decrease[UVS_MAX_ITER_LOG];
+  double step_norm[UVS_MAX_ITER_LOG];
+  double gradient_max_norm[UVS_MAX_ITER_LOG];
+  int32_t step_accepted[UVS_MAX_ITER_LOG];
+} UvsSummary;
+
+/* Next marginalization prior, caller-allocated (see uvs_marginalize_size). */
+typedef struct UvsPrior {
+  int32_t n;                 /* out: residual dimension */
+  int32_t n_blocks;          /* out */
+  int32_t m;                 /* out: marginalised dimension */
+  int32_t reserved0;
+  double *J;                 /* [cap_n][cap_n] row-major, first n*n used */
+  double *r;                 /* [cap_n] */
+  int32_t *block_kind;       /* [cap_blocks] */
+  int32_t *block_id;         /* [cap_blocks] ids AFTER the window shift (estimator.cpp:1139-1153) */
+  double *x0;                /* [7*cap_blocks] */
+  double *A;                 /* optional [cap_n][cap_n]: Schur complement A' (nullable) */
+  double *b;                 /* optional [cap_n]: b' (nullable) */
+  int32_t cap_n;
+  int32_t cap_blocks;
+} UvsPrior;
+
+/* uvs_eval_* flags */
+#define UVS_EVAL_CERES_LAYOUT 0x0  /* raw Evaluate() output, global-size Jacobian blocks */
+#define UVS_EVAL_LOCAL_LAYOUT 0x1  /* tangent columns only, loss-corrected (what the solver eats) */
+#define UVS_EVAL_DEVICE_OUT   0x2  /* output pointers are device pointers */
+
+typedef struct UvsHandle UvsHandle;
+
+int uvs_abi_version(void);
+void uvs_default_options(UvsOptions *opts);
+const char *uvs_status_string(int status);
+
+/* Create a solver bound to CUDA device `device` with its own stream.  Fails (UVS_ERR_CUDA) when no
+ * GPU is present: there is no CPU fallback. */
+int uvs_create(int device, UvsHandle **out);
+int uvs_destroy(UvsHandle *h);
+const char *uvs_last_error(const UvsHandle *h);
+
+/* Copy `n_windows` windows (H2D) into the handle's device batch; replaces any previous batch. */
+int uvs_upload_windows(UvsHandle *h, int32_t n_windows, const UvsWindow *windows,
+                       const UvsOptions *opts);
+/* Copy the current state of every window back into the caller's state arrays (D2H). */
+int uvs_download_state(UvsHandle *h, int32_t n_windows, UvsWindow *windows);
+
+/* Batched factor sweeps over the uploaded batch, factors concatenated in window order.
+ * residuals: [n_total][nres]; jacobians (nullable): per factor, layout per flags. */
+int uvs_eval_proj(UvsHandle *h, double *residuals, double *jacobians, int32_t flags);
+int uvs_eval_line(UvsHandle *h, double *residuals, double *jacobians, int32_t flags);
+int uvs_eval_vp(UvsHandle *h, double *residuals, double *jacobians, int32_t flags);
+int uvs_eval_imu(UvsHandle *h, double *residuals, double *jacobians, int32_t flags);
+int uvs_eval_prior(UvsHandle *h, double *residuals, double *jacobians, int32_t flags);
+/* cost = 1/2 sum rho(|r|^2) per window, [n_windows] */
+int uvs_eval_cost(UvsHandle *h, double *cost);
+
+/* Levenberg-Marquardt + Schur solve of every uploaded window (ceres::Solve replacement). */
+int uvs_solve(UvsHandle *h, UvsSummary *summaries /* [n_windows], nullable */);
+
+/* Convenience for the optimization() shim: upload + solve + download for one batch. */
+int uvs_batch_solve(UvsHandle *h, int32_t n_windows, UvsWindow *windows, const UvsOptions *opts,
+                    UvsSummary *summaries);
+
+/* Build the next prior of window `window_index` from its current state
+ * (MarginalizationInfo::preMarginalize + marginalize, estimator.cpp:1003-1228). */
+int uvs_marginalize(UvsHandle *h, int32_t window_index, int32_t flag, UvsPrior *out);
+
+/* Sum of the sweep's algorithmic bytes for the uploaded batch */
+int uvs_sweep_bytes(UvsHandle *h, int64_t *jacobian_sweep_bytes, int64_t *residual_sweep_bytes);
+/* Number of kernel launches issued through this handle since creation. */
+int64_t uvs_launch_count(const UvsHandle *h);
+/* Device time of the last uvs_solve (CUDA events on the handle's stream), milliseconds. */
+int uvs_last_solve_ms(const UvsHandle *h, float *ms);
+/* Device time [ms] of the Jacobian-sweep kernels accumulated over the last uvs_solve. */
+int uvs_last_sweep_ms(const UvsHandle *h, float *ms, int32_t *n_sweeps);
+
+/* Factor-parallel multi-GPU mode: this rank owns the landmarks with (index % nranks == rank);
+ * IMU factors and the prior belong to rank 0.  `reduce` is called once per LM iteration with the
+ * device buffer holding the rank's partial reduced camera system (count doubles) and must sum it
+ * over ranks in place (e.g. ncclAllReduce on `stream`). */
+typedef int (*UvsAllReduceFn)(void *user, void *device_buf, int64_t count, void *cuda_stream);
+int uvs_comm_init(UvsHandle *h, int32_t rank, int32_t nranks, UvsAllReduceFn reduce, void *user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVS_H_ */

@@ -1,0 +1,229 @@
+"""ctypes binding of libuvs_b200.so — the same C ABI a cgo/JNI/C++ caller would bind
+(include/uvs.h).  There is NO CPU fallback: if the CUDA library is missing or no GPU is present,
+every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .window import (EVAL_CERES_LAYOUT, EVAL_DEVICE_OUT, EVAL_LOCAL_LAYOUT, UvsOptionsStruct, UvsPriorStruct,
+                     UvsSummaryStruct, UvsWindowStruct, Window, c_double_p, c_int32_p, default_options,
+                     window_array)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libuvs_b200.so"
+_lib = None
+
+EXPORTS = (
+    "uvs_abi_version", "uvs_default_options", "uvs_status_string", "uvs_create", "uvs_destroy", "uvs_last_error",
+    "uvs_upload_windows", "uvs_download_state", "uvs_eval_proj", "uvs_eval_line", "uvs_eval_vp", "uvs_eval_imu",
+    "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
+    "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init",
+)
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+class UvsError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        super().__init__("%s failed with status %d%s" % (where, status, (": " + detail) if detail else ""))
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "csrc", _LIB_NAME)
+
+
+def load_library():
+    """Load the CUDA library; raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    H = C.c_void_p
+    lib.uvs_abi_version.restype = C.c_int
+    lib.uvs_default_options.argtypes = [C.POINTER(UvsOptionsStruct)]
+    lib.uvs_status_string.restype = C.c_char_p
+    lib.uvs_status_string.argtypes = [C.c_int]
+    lib.uvs_create.argtypes = [C.c_int, C.POINTER(H)]
+    lib.uvs_destroy.argtypes = [H]
+    lib.uvs_last_error.restype = C.c_char_p
+    lib.uvs_last_error.argtypes = [H]
+    lib.uvs_upload_windows.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct), C.POINTER(UvsOptionsStruct)]
+    lib.uvs_download_state.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct)]
+    for n in ("uvs_eval_proj", "uvs_eval_line", "uvs_eval_vp", "uvs_eval_imu", "uvs_eval_prior"):
+        getattr(lib, n).argtypes = [H, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.uvs_eval_cost.argtypes = [H, c_double_p]
+    lib.uvs_solve.argtypes = [H, C.POINTER(UvsSummaryStruct)]
+    lib.uvs_batch_solve.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct), C.POINTER(UvsOptionsStruct),
+                                    C.POINTER(UvsSummaryStruct)]
+    lib.uvs_marginalize.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(UvsPriorStruct)]
+    lib.uvs_sweep_bytes.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.uvs_launch_count.restype = C.c_int64
+    lib.uvs_launch_count.argtypes = [H]
+    lib.uvs_last_solve_ms.argtypes = [H, C.POINTER(C.c_float)]
+    lib.uvs_last_sweep_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    lib.uvs_comm_init.argtypes = [H, C.c_int32, C.c_int32, ALLREDUCE_FN, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+_JDIM = {  # doubles per factor: (nres, ceres-layout jac, local-layout jac)
+    "proj": (2, 44, 38), "line": (2, 22, 20), "vp": (1, 11, 10), "imu": (15, 480, 450),
+}
+
+
+class Solver:
+    """Thin object wrapper over one UvsHandle (one CUDA stream, not re-entrant)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.uvs_create(device, C.byref(self.h))
+        if rc != 0:
+            raise UvsError(rc, "uvs_create", self.lib.uvs_status_string(rc).decode())
+        self.windows = []
+        self._arr = None
+        self._cb = None
+
+    def close(self):
+        if self.h:
+            self.lib.uvs_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, where):
+        if rc != 0:
+            raise UvsError(rc, where, self.lib.uvs_last_error(self.h).decode())
+
+    # -- data movement -------------------------------------------------------------------------
+    def upload(self, windows, opts: UvsOptionsStruct | None = None):
+        if isinstance(windows, Window):
+            windows = [windows]
+        self.windows = list(windows)
+        self.opts = opts if opts is not None else default_options()
+        self._arr = window_array(self.windows)
+        self._check(self.lib.uvs_upload_windows(self.h, len(self.windows), self._arr, C.byref(self.opts)), "uvs_upload_windows")
+
+    def download(self):
+        """Writes the device state back into the Window objects given to upload()."""
+        self._check(self.lib.uvs_download_state(self.h, len(self.windows), self._arr), "uvs_download_state")
+        return self.windows
+
+    # -- factor sweeps -------------------------------------------------------------------------
+    def _count(self, kind):
+        return sum({"proj": w.n_proj, "line": w.n_line_obs, "vp": w.n_vp_obs, "imu": w.n_imu}[kind] for w in self.windows)
+
+    def eval(self, kind: str, local: bool = False, want_jac: bool = True):
+        """-> (residuals [n, nr], jacobians [n, jd] or None) on the host."""
+        if kind == "prior":
+            return self.eval_prior(local, want_jac)
+        nr, jc, jl = _JDIM[kind]
+        if kind == "proj" and self.windows and self.windows[0].estimate_td:
+            jc, jl = jc + 2, jl + 2
+        n = self._count(kind)
+        r = np.zeros((n, nr))
+        J = np.zeros((n, jl if local else jc)) if want_jac else None
+        fn = getattr(self.lib, "uvs_eval_" + kind)
+        flags = EVAL_LOCAL_LAYOUT if local else EVAL_CERES_LAYOUT
+        self._check(fn(self.h, r.ctypes.data, J.ctypes.data if want_jac else None, flags), "uvs_eval_" + kind)
+        return r, J
+
+    def eval_prior(self, local=False, want_jac=True):
+        """Per-window lists: residual [n], jacobian [n, cols]."""
+        tot_r, tot_j, shapes = 0, 0, []
+        for w in self.windows:
+            n = w.prior_n
+            cols = sum((6 if local else 7) if k in (0, 2) else (9 if k == 1 else 1) for k in w.prior_block_kind)
+            shapes.append((n, cols))
+            tot_r += n
+            tot_j += n * cols
+        r = np.zeros(max(tot_r, 1)); J = np.zeros(max(tot_j, 1))
+        flags = EVAL_LOCAL_LAYOUT if local else EVAL_CERES_LAYOUT
+        self._check(self.lib.uvs_eval_prior(self.h, r.ctypes.data, J.ctypes.data if want_jac else None, flags), "uvs_eval_prior")
+        rs, Js, ro, jo = [], [], 0, 0
+        for n, cols in shapes:
+            rs.append(r[ro:ro + n].copy()); ro += n
+            Js.append(J[jo:jo + n * cols].copy()); jo += n * cols
+        return rs, (Js if want_jac else None)
+
+    def cost(self):
+        c = np.zeros(len(self.windows))
+        self._check(self.lib.uvs_eval_cost(self.h, c.ctypes.data_as(c_double_p)), "uvs_eval_cost")
+        return c
+
+    # -- solve ---------------------------------------------------------------------------------
+    def solve(self):
+        sums = (UvsSummaryStruct * len(self.windows))()
+        self._check(self.lib.uvs_solve(self.h, sums), "uvs_solve")
+        return sums
+
+    def batch_solve(self, windows, opts=None):
+        """upload + solve + download through the single reference-facing call (host buffers)."""
+        if isinstance(windows, Window):
+            windows = [windows]
+        self.windows = list(windows)
+        self.opts = opts if opts is not None else default_options()
+        self._arr = window_array(self.windows)
+        sums = (UvsSummaryStruct * len(self.windows))()
+        self._check(self.lib.uvs_batch_solve(self.h, len(self.windows), self._arr, C.byref(self.opts), sums), "uvs_batch_solve")
+        return sums
+
+    def marginalize(self, window_index=0, flag=0):
+        w = self.windows[window_index]
+        cap_n, cap_b = 16 * w.n_frames + 16, 2 * w.n_frames + 8
+        J = np.zeros((cap_n, cap_n)); r = np.zeros(cap_n); A = np.zeros((cap_n, cap_n)); b = np.zeros(cap_n)
+        kind = np.zeros(cap_b, np.int32); bid = np.zeros(cap_b, np.int32); x0 = np.zeros(9 * cap_b)
+        p = UvsPriorStruct()
+        p.J, p.r, p.A, p.b, p.x0 = (a.ctypes.data_as(c_double_p) for a in (J, r, A, b, x0))
+        p.block_kind, p.block_id = kind.ctypes.data_as(c_int32_p), bid.ctypes.data_as(c_int32_p)
+        p.cap_n, p.cap_blocks = cap_n, cap_b
+        self._check(self.lib.uvs_marginalize(self.h, window_index, flag, C.byref(p)), "uvs_marginalize")
+        n, nb = p.n, p.n_blocks
+        if n == 0:
+            return None
+        kinds = kind[:nb].copy(); ids = bid[:nb].copy()
+        gs = np.array([7 if k in (0, 2) else (9 if k == 1 else 1) for k in kinds])
+        return dict(n=n, m=p.m, J=J.ravel()[:n * n].reshape(n, n).copy(), r=r[:n].copy(),
+                    A=A.ravel()[:n * n].reshape(n, n).copy(), b=b[:n].copy(), kinds=kinds, ids=ids,
+                    x0=x0[:gs.sum()].copy())
+
+    # -- introspection -------------------------------------------------------------------------
+    def sweep_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.uvs_sweep_bytes(self.h, C.byref(a), C.byref(b)), "uvs_sweep_bytes")
+        return a.value, b.value
+
+    def launch_count(self):
+        return int(self.lib.uvs_launch_count(self.h))
+
+    def last_solve_ms(self):
+        ms = C.c_float()
+        self._check(self.lib.uvs_last_solve_ms(self.h, C.byref(ms)), "uvs_last_solve_ms")
+        return ms.value
+
+    def last_sweep_ms(self):
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self.lib.uvs_last_sweep_ms(self.h, C.byref(ms), C.byref(n)), "uvs_last_sweep_ms")
+        return ms.value, n.value
+
+    def comm_init(self, rank, nranks, reduce_fn):
+        """reduce_fn(device_ptr:int, count:int, stream:int) -> int, summing in place over ranks."""
+        def _tramp(user, buf, count, stream):
+            try:
+                return int(reduce_fn(buf, count, stream) or 0)
+            except Exception:  # never let an exception cross the C ABI
+                return -7
+        self._cb = ALLREDUCE_FN(_tramp)
+        self._check(self.lib.uvs_comm_init(self.h, rank, nranks, self._cb, None), "uvs_comm_init")
