@@ -1,0 +1,246 @@
+"""GPU parity tests: libuvs_b200.so (through its C ABI) against the CPU oracle on the same seeded
+windows.  Tolerances are the ones BASELINE.json's north_star states: 1e-6 relative on residuals
+(and, our addition, on Jacobian blocks), 1e-4 on the solved pose delta."""
+import numpy as np
+import pytest
+
+import uvs_b200
+from tests import orc
+from tools import gen_window as gw
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6          # residuals / Jacobians, relative to the largest magnitude of the block
+STEP_TOL = 1e-4      # solved pose delta
+
+KINDS = (("proj", orc.F_PROJ), ("line", orc.F_LINE), ("vp", orc.F_VP), ("imu", orc.F_IMU))
+
+
+@pytest.fixture(scope="module")
+def solver():
+    s = uvs_b200.Solver(0)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def windows():
+    return {k: gw.make_window(k) for k in ("tiny", "C1", "C2")}
+
+
+def rel_err(a, b):
+    scale = max(1.0, float(np.abs(b).max())) if b.size else 1.0
+    return float(np.abs(a - b).max()) / scale if b.size else 0.0
+
+
+def rel_err_rows(a, b):
+    """max over factors of |a-b|_inf / max(|b|_inf of that factor, 1e-300) - the 1e-6 *relative* bar"""
+    if b.size == 0:
+        return 0.0
+    scale = np.maximum(np.abs(b).max(axis=1, keepdims=True), 1e-12)
+    return float((np.abs(a - b) / scale).max())
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "C1", "C2"])
+@pytest.mark.parametrize("local", [False, True])
+def test_factor_sweep_parity(solver, windows, opts, cfg, local):
+    w = windows[cfg]
+    solver.upload([w], opts)
+    for kind, ft in KINDS:
+        r, J = solver.eval(kind, local=local)
+        r0, J0, _ = orc.eval_factors(w, opts, ft, local=local)
+        assert r.shape == r0.shape and J.shape == J0.shape, kind
+        assert rel_err_rows(r, r0) < RTOL, (kind, "residual", rel_err_rows(r, r0))
+        assert rel_err_rows(J, J0) < RTOL, (kind, "jacobian", rel_err_rows(J, J0))
+
+
+@pytest.mark.parametrize("local", [False, True])
+def test_prior_parity(solver, windows, opts, local):
+    w = windows["C1"]
+    solver.upload([w], opts)
+    rs, Js = solver.eval_prior(local=local)
+    r0, J0, _ = orc.eval_factors(w, opts, orc.F_PRIOR, local=local)
+    assert rel_err(rs[0], r0.ravel()) < RTOL
+    assert rel_err(Js[0], J0.ravel()) < 1e-12   # the prior Jacobian is a copy of J0's columns
+
+
+def test_extrinsic_and_cost(solver, opts):
+    w = gw.make_window("C1", estimate_extrinsic=1)
+    solver.upload([w], opts)
+    r, J = solver.eval("proj", local=True)
+    r0, J0, _ = orc.eval_factors(w, opts, orc.F_PROJ, local=True)
+    assert rel_err_rows(J, J0) < RTOL
+    c = solver.cost()[0]
+    c0 = orc.total_cost(w, opts)
+    assert abs(c - c0) <= 1e-9 * abs(c0)
+
+
+def test_td_factor_parity(solver, opts):
+    rng = np.random.default_rng(5)
+    w = gw.make_window("C1", with_prior=False)
+    n = w.n_proj
+    w.estimate_td = 1
+    w.td = np.array([0.013])
+    w.proj_vel_i = rng.normal(0, 0.3, (n, 2)); w.proj_vel_j = rng.normal(0, 0.3, (n, 2))
+    w.proj_td_i = rng.normal(0, 0.005, n); w.proj_td_j = rng.normal(0, 0.005, n)
+    w.proj_row_i = rng.uniform(0, 480, n); w.proj_row_j = rng.uniform(0, 480, n)
+    w.normalize()
+    o = uvs_b200.default_options(tr=0.03, row=480.0)
+    solver.upload([w], o)
+    for local in (False, True):
+        r, J = solver.eval("proj", local=local)
+        r0, J0, _ = orc.eval_factors(w, o, orc.F_PROJ, local=local)
+        assert J.shape == J0.shape
+        assert rel_err_rows(r, r0) < RTOL and rel_err_rows(J, J0) < RTOL
+    ref = w.copy()
+    sm0 = orc.solve(ref, o)
+    sm = solver.solve()[0]
+    solver.download()
+    assert abs(sm.final_cost - sm0.final_cost) <= 1e-6 * abs(sm0.final_cost)
+    assert abs(w.td[0] - ref.td[0]) < STEP_TOL
+
+
+def _tangent_delta(w0, w1):
+    """pose delta between two windows: positions and the quaternion difference (as the north_star's
+    'solved pose delta')"""
+    dp = np.abs(w1.pose[:, :3] - w0.pose[:, :3]).max()
+    dq = np.abs(np.abs((w1.pose[:, 3:] * w0.pose[:, 3:]).sum(axis=1)) - 1.0).max()
+    return dp, dq
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "C1", "C2"])
+def test_first_step_parity(solver, windows, opts, cfg):
+    """one LM iteration (fixed radius 1e4): the GPU candidate equals Plus(x, oracle delta)"""
+    w = windows[cfg].copy()
+    fs = orc.first_step(w, opts, radius=1e4)
+    o = uvs_b200.default_options(max_num_iterations=1, fixed_iterations=1)
+    solver.upload([w], o)
+    sm = solver.solve()[0]
+    assert abs(sm.initial_cost - fs["cost"]) <= 1e-9 * abs(fs["cost"])
+    assert sm.step_accepted[1] == 1
+    x0 = windows[cfg]
+    solver.download()
+    d = w.cam_dim
+    delta = fs["delta"]
+    for f in range(w.n_frames):
+        ref = orc.pose_plus(x0.pose[f], delta[15 * f:15 * f + 6])
+        assert np.abs(w.pose[f] - ref).max() < STEP_TOL
+        assert np.abs(w.speed_bias[f] - (x0.speed_bias[f] + delta[15 * f + 6:15 * f + 15])).max() < STEP_TOL
+    scale = np.maximum(np.abs(delta[d:d + w.n_points]), 1e-3)
+    assert (np.abs((w.inv_depth - x0.inv_depth) - delta[d:d + w.n_points]) / scale).max() < 1e-4
+    dl = delta[d + w.n_points:].reshape(-1, 4)
+    assert np.abs((w.ortho - x0.ortho) - dl).max() < 1e-4 * max(1.0, np.abs(dl).max())
+    # model cost change through the summary: relative_decrease = (cost - cost+) / model_change
+    rel = (sm.initial_cost - sm.cost[1]) / fs["model_change"]
+    assert abs(sm.relative_decrease[1] - rel) < 1e-6 * max(1.0, abs(rel))
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "C1", "C2"])
+def test_full_solve_parity(solver, windows, opts, cfg):
+    w = windows[cfg].copy()
+    ref = windows[cfg].copy()
+    sm0 = orc.solve(ref, opts)
+    solver.upload([w], opts)
+    sm = solver.solve()[0]
+    solver.download()
+    assert sm.num_iterations == sm0.num_iterations
+    assert sm.termination == sm0.termination
+    n = sm.num_iterations
+    acc = [sm.step_accepted[i] for i in range(n)]
+    acc0 = [sm0.step_accepted[i] for i in range(n)]
+    assert acc == acc0
+    for i in range(n):
+        assert abs(sm.cost[i] - sm0.cost[i]) <= 1e-6 * abs(sm0.cost[i]) + 1e-9, (i, sm.cost[i], sm0.cost[i])
+        assert abs(sm.radius[i] - sm0.radius[i]) <= 1e-5 * abs(sm0.radius[i])
+    dp, dq = _tangent_delta(ref, w)
+    assert dp < STEP_TOL and dq < STEP_TOL
+    assert np.abs(w.speed_bias - ref.speed_bias).max() < STEP_TOL
+    assert np.abs(w.inv_depth - ref.inv_depth).max() < STEP_TOL
+    assert np.abs(w.ortho - ref.ortho).max() < STEP_TOL
+
+
+def test_solve_with_extrinsic(solver, opts):
+    w = gw.make_window("C1", estimate_extrinsic=1)
+    ref = w.copy()
+    sm0 = orc.solve(ref, opts)
+    solver.upload([w], opts)
+    sm = solver.solve()[0]
+    solver.download()
+    assert abs(sm.final_cost - sm0.final_cost) <= 1e-6 * abs(sm0.final_cost)
+    assert np.abs(w.ex_pose - ref.ex_pose).max() < STEP_TOL
+    assert np.abs(w.pose - ref.pose).max() < STEP_TOL
+
+
+def test_batch_equals_individual(solver, opts):
+    """windows of different shapes solved in one batch give the same result as one by one"""
+    ws = [gw.make_window("tiny", seed=s) for s in (11, 12)] + [gw.make_window("C1", seed=13), gw.make_window("tiny", seed=14, with_prior=False)]
+    single = []
+    for w in ws:
+        c = w.copy()
+        solver.upload([c], opts)
+        sm = solver.solve()[0]
+        solver.download()
+        single.append((c, sm.final_cost, sm.num_iterations))
+    batch = [w.copy() for w in ws]
+    sums = solver.batch_solve(batch, opts)
+    for k, (c, cost, iters) in enumerate(single):
+        assert sums[k].num_iterations == iters
+        assert abs(sums[k].final_cost - cost) <= 1e-9 * abs(cost)
+        assert np.abs(batch[k].pose - c.pose).max() < 1e-8
+        assert np.abs(batch[k].ortho - c.ortho).max() < 1e-8
+
+
+def test_converges_from_perturbed_truth(solver, opts):
+    """noise-free window perturbed from the truth converges back (SURVEY 8c pin #5)"""
+    w, truth = gw.make_window("C1", with_prior=False, return_truth=True)
+    solver.upload([w], uvs_b200.default_options(max_num_iterations=30))
+    sm = solver.solve()[0]
+    assert sm.final_cost < 1e-6 * sm.initial_cost
+    n = sm.num_iterations
+    costs = [sm.cost[i] for i in range(n)]
+    assert all(costs[i + 1] <= costs[i] * (1 + 1e-12) for i in range(n - 1))   # monotone under accepted steps
+
+
+def test_edge_cases(solver, opts):
+    # IMU + prior only (no visual factors)
+    w = gw.make_window("tiny")
+    bare = uvs_b200.Window(pose=w.pose, speed_bias=w.speed_bias, ex_pose=w.ex_pose, imu_frame_i=w.imu_frame_i,
+                           imu_delta_p=w.imu_delta_p, imu_delta_q=w.imu_delta_q, imu_delta_v=w.imu_delta_v,
+                           imu_sum_dt=w.imu_sum_dt, imu_lin_ba=w.imu_lin_ba, imu_lin_bg=w.imu_lin_bg,
+                           imu_jacobian=w.imu_jacobian, imu_covariance=w.imu_covariance)
+    bare.set_prior(w.prior_J, w.prior_r, w.prior_block_kind, w.prior_block_id, w.prior_x0)
+    ref = bare.copy()
+    sm0 = orc.solve(ref, opts)
+    solver.upload([bare], opts)
+    sm = solver.solve()[0]
+    solver.download()
+    assert abs(sm.final_cost - sm0.final_cost) <= 1e-6 * abs(sm0.final_cost) + 1e-9
+    assert np.abs(bare.pose - ref.pose).max() < STEP_TOL
+    # a landmark without observations keeps its value
+    w2 = gw.make_window("tiny")
+    w2.inv_depth = np.append(w2.inv_depth, 0.37)
+    w2.ortho = np.vstack([w2.ortho, [0.1, 0.2, 0.3, 0.4]])
+    w2.normalize()
+    solver.upload([w2], opts)
+    solver.solve()
+    solver.download()
+    assert w2.inv_depth[-1] == 0.37 and np.all(w2.ortho[-1] == [0.1, 0.2, 0.3, 0.4])
+    # malformed input is rejected, not computed on
+    bad = gw.make_window("tiny")
+    bad.proj_frame_j = bad.proj_frame_j.copy(); bad.proj_frame_j[0] = 99
+    with pytest.raises(uvs_b200.UvsError):
+        solver.upload([bad], opts)
+    with pytest.raises(uvs_b200.UvsError):
+        uvs_b200.Solver(0).solve()   # no window uploaded
+
+
+def test_stress_window_global_cholesky(solver, opts):
+    """C5 (31 frames, d = 465): reduced system too large for shared memory -> in-place global path"""
+    w = gw.make_window("C5")
+    ref = w.copy()
+    sm0 = orc.solve(ref, opts)
+    solver.upload([w], opts)
+    sm = solver.solve()[0]
+    solver.download()
+    assert abs(sm.final_cost - sm0.final_cost) <= 1e-6 * abs(sm0.final_cost)
+    assert np.abs(w.pose - ref.pose).max() < STEP_TOL

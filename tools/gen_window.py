@@ -449,6 +449,27 @@ def drop_first_frame(w: Window, truth, rng) -> tuple:
     return out, t2
 
 
+def truncate_landmarks(w: Window, n_points, n_lines, truth=None) -> Window:
+    """Keep the first n_points points / n_lines lines (the generator over-produces because features
+    anchored in the dropped frame can fall out of the window)."""
+    if w.n_points <= n_points and w.n_lines <= n_lines:
+        return w
+    n_points, n_lines = min(n_points, w.n_points), min(n_lines, w.n_lines)
+    pk, lk, vk = w.proj_point < n_points, w.line_idx < n_lines, w.vp_line < n_lines
+    out = w.copy()
+    out.inv_depth, out.ortho = w.inv_depth[:n_points].copy(), w.ortho[:n_lines].copy()
+    for n in ("proj_frame_i", "proj_frame_j", "proj_point", "proj_pts_i", "proj_pts_j"):
+        setattr(out, n, getattr(w, n)[pk].copy())
+    for n in ("line_frame", "line_idx", "line_sp", "line_ep"):
+        setattr(out, n, getattr(w, n)[lk].copy())
+    for n in ("vp_frame", "vp_line", "vp_dir"):
+        setattr(out, n, getattr(w, n)[vk].copy())
+    if truth is not None:
+        truth["inv_depth"] = truth["inv_depth"][:n_points]
+        truth["ortho"] = truth["ortho"][:n_lines]
+    return out.normalize()
+
+
 def make_window(config="C2", seed=None, with_prior=True, estimate_extrinsic=0, return_truth=False, **over):
     """Generate one window.  `config` is a key of CONFIGS or a dict with the same keys."""
     cfg = dict(CONFIGS[config]) if isinstance(config, str) else dict(config)
@@ -480,7 +501,7 @@ def make_window(config="C2", seed=None, with_prior=True, estimate_extrinsic=0, r
             w2.speed_bias[f, 6:9] = truth["bg"] + noise_rng.normal(0, 0.001, 3)
         if prior is not None:
             w2.set_prior(prior["J"], prior["r"], prior["kinds"], prior["ids"], prior["x0"])
-        w = w2
+        w = truncate_landmarks(w2, cfg["n_points"], cfg["n_lines"], truth)
     w.normalize()
     return (w, truth) if return_truth else w
 

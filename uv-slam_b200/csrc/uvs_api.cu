@@ -1,0 +1,683 @@
+// uvs_api.cu — the C ABI of libuvs_b200.so (include/uvs.h): host-side packing of the caller's
+// windows into one flat HBM batch, launch sequencing of the sm_100a kernels, and the LM loop.
+//
+// Replaces the body of Estimator::optimization() between vector2double() and double2vector()
+// (vins_estimator/src/estimator.cpp:800-999): problem assembly + ceres::Solve.  There is no CPU
+// fallback: every entry point fails with UVS_ERR_CUDA when no device is available.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/uvs.h"
+#include "uvs_device.cuh"
+#include "uvs_handle.h"
+#include "uvs_kernels.h"
+
+using namespace uvs;
+
+namespace {
+
+int fail(UvsHandle *h, int status, const std::string &msg) {
+  if (h) h->err = msg;
+  return status;
+}
+int cuda_fail(UvsHandle *h, cudaError_t e, const char *where) {
+  return fail(h, UVS_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                       \
+  do {                                                                 \
+    cudaError_t e_ = (call);                                           \
+    if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);             \
+  } while (0)
+
+void fill_params(const UvsOptions &o, Params &P) {
+  P.S = o.focal_length / 1.6;   // ProjectionFactor::sqrt_info = FOCAL_LENGTH / 1.6 * I2 (estimator.cpp:17)
+  for (int k = 0; k < 3; k++) P.g[k] = o.gravity[k];
+  P.line_factor = o.line_factor; P.vp_factor = o.vp_factor;
+  P.cauchy_point = o.cauchy_point; P.cauchy_line = o.cauchy_line; P.cauchy_vp = o.cauchy_vp;
+  P.tr_over_row = o.row != 0.0 ? o.tr / o.row : 0.0;
+  P.half_row = o.row / 2.0;
+  P.min_lm_diag = o.min_lm_diagonal; P.max_lm_diag = o.max_lm_diagonal;
+  P.min_relative_decrease = o.min_relative_decrease;
+  P.max_radius = o.max_radius; P.min_radius = o.min_radius; P.initial_radius = o.initial_radius;
+  P.function_tolerance = o.function_tolerance; P.gradient_tolerance = o.gradient_tolerance;
+  P.parameter_tolerance = o.parameter_tolerance;
+  P.fixed_iterations = o.fixed_iterations;
+  P.max_num_iterations = o.max_num_iterations;
+}
+
+template <class T>
+void prefix(std::vector<T> &off, int B, const UvsWindow *w, T (*get)(const UvsWindow &)) {
+  off.assign(B + 1, 0);
+  for (int i = 0; i < B; i++) off[i + 1] = off[i] + get(w[i]);
+}
+
+int prior_local(int kind) { return (kind == UVS_BLOCK_POSE || kind == UVS_BLOCK_EXPOSE) ? 6 : (kind == UVS_BLOCK_SPEEDBIAS ? 9 : 1); }
+int prior_global(int kind) { return (kind == UVS_BLOCK_POSE || kind == UVS_BLOCK_EXPOSE) ? 7 : (kind == UVS_BLOCK_SPEEDBIAS ? 9 : 1); }
+
+int post_launch(UvsHandle *h, const char *where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, where);
+  return UVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uvs_abi_version(void) { return UVS_ABI_VERSION; }
+
+void uvs_default_options(UvsOptions *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  // config/euroc/euroc_config.yaml:20,55-56,64,85-87 and Ceres' trust-region defaults
+  o->focal_length = 461.6;
+  o->gravity[0] = 0.0; o->gravity[1] = 0.0; o->gravity[2] = 9.81007;
+  o->line_factor = 300.0; o->vp_factor = 10.0;
+  o->cauchy_point = 1.0; o->cauchy_line = 0.1; o->cauchy_vp = 1.0;
+  o->tr = 0.0; o->row = 480.0;
+  o->max_num_iterations = 10; o->fixed_iterations = 0; o->max_solver_time = 0.0;
+  o->initial_radius = 1e4; o->max_radius = 1e16; o->min_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+}
+
+const char *uvs_status_string(int s) {
+  switch (s) {
+    case UVS_OK: return "ok";
+    case UVS_ERR_INVALID_ARG: return "invalid argument";
+    case UVS_ERR_CUDA: return "CUDA error (no device, or a runtime failure; there is no CPU fallback)";
+    case UVS_ERR_CAPACITY: return "capacity exceeded";
+    case UVS_ERR_NOT_FINITE: return "non-finite cost or step";
+    case UVS_ERR_NOT_PD: return "reduced camera system not positive definite";
+    case UVS_ERR_NO_WINDOW: return "no window uploaded";
+    case UVS_ERR_COMM: return "multi-GPU exchange failed";
+    case UVS_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+  }
+}
+
+int uvs_create(int device, UvsHandle **out) {
+  if (!out) return UVS_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return UVS_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) return UVS_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return UVS_ERR_CUDA;
+  if (prop.major < 10) return UVS_ERR_CUDA;   // built for sm_100a only
+  UvsHandle *h = new UvsHandle();
+  h->device = device;
+  h->stage.pinned_host = true;
+  h->hscratch.pinned_host = true;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return UVS_ERR_CUDA; }
+  cudaEventCreate(&h->ev_a); cudaEventCreate(&h->ev_b); cudaEventCreate(&h->ev_c); cudaEventCreate(&h->ev_d);
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  h->packed_limit = chol_packed_limit(max_smem - 1024);
+  set_chol_smem(max_smem - 1024);
+  cudaMalloc((void **)&h->d_active, sizeof(int));
+  cudaMallocHost((void **)&h->h_active, sizeof(int));
+  uvs_default_options(&h->opts);
+  *out = h;
+  return UVS_OK;
+}
+
+int uvs_destroy(UvsHandle *h) {
+  if (!h) return UVS_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->dev.release(); h->stage.release(); h->scratch.release(); h->hscratch.release();
+  if (h->d_active) cudaFree(h->d_active);
+  if (h->h_active) cudaFreeHost(h->h_active);
+  cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b); cudaEventDestroy(h->ev_c); cudaEventDestroy(h->ev_d);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return UVS_OK;
+}
+
+const char *uvs_last_error(const UvsHandle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts) {
+  if (!h || B <= 0 || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_windows: bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (opts) h->opts = *opts;
+  fill_params(h->opts, h->P);
+  h->have_window = false;
+  const int td = w[0].estimate_td ? 1 : 0;
+  int max_d = 0, max_prior_n = 0;
+  for (int i = 0; i < B; i++) {
+    const UvsWindow &x = w[i];
+    if (x.n_frames < 1 || x.n_points < 0 || x.n_lines < 0 || x.n_proj < 0 || x.n_line_obs < 0 || x.n_vp_obs < 0 ||
+        x.n_imu < 0 || x.prior_n < 0 || x.prior_n_blocks < 0)
+      return fail(h, UVS_ERR_INVALID_ARG, "negative size in window " + std::to_string(i));
+    if ((x.estimate_td ? 1 : 0) != td) return fail(h, UVS_ERR_UNSUPPORTED, "estimate_td must be uniform over the batch");
+    if (!x.pose || !x.speed_bias || !x.ex_pose || (x.n_points && !x.inv_depth) || (x.n_lines && !x.ortho))
+      return fail(h, UVS_ERR_INVALID_ARG, "null state pointer in window " + std::to_string(i));
+    if (x.n_proj && (!x.proj_frame_i || !x.proj_frame_j || !x.proj_point || !x.proj_pts_i || !x.proj_pts_j))
+      return fail(h, UVS_ERR_INVALID_ARG, "null projection-factor array");
+    if (td && x.n_proj && (!x.proj_vel_i || !x.proj_vel_j || !x.proj_td_i || !x.proj_td_j || !x.proj_row_i || !x.proj_row_j || !x.td))
+      return fail(h, UVS_ERR_INVALID_ARG, "estimate_td needs the td arrays");
+    if (x.n_line_obs && (!x.line_frame || !x.line_idx || !x.line_sp || !x.line_ep)) return fail(h, UVS_ERR_INVALID_ARG, "null line-factor array");
+    if (x.n_vp_obs && (!x.vp_frame || !x.vp_line || !x.vp_dir)) return fail(h, UVS_ERR_INVALID_ARG, "null VP-factor array");
+    if ((x.n_line_obs || x.n_vp_obs) && (!x.line_ric || !x.line_tic)) return fail(h, UVS_ERR_INVALID_ARG, "line_ric / line_tic missing");
+    if (x.n_imu && (!x.imu_frame_i || !x.imu_delta_p || !x.imu_delta_q || !x.imu_delta_v || !x.imu_sum_dt || !x.imu_lin_ba ||
+                    !x.imu_lin_bg || !x.imu_jacobian || !x.imu_covariance))
+      return fail(h, UVS_ERR_INVALID_ARG, "null IMU array");
+    if (x.prior_n && (!x.prior_J || !x.prior_r || !x.prior_block_kind || !x.prior_block_id || !x.prior_x0 || !x.prior_n_blocks))
+      return fail(h, UVS_ERR_INVALID_ARG, "null prior array");
+    if (x.n_frames > 32) return fail(h, UVS_ERR_CAPACITY, "more than 32 frames per window (a landmark's factors must fit one warp)");
+    const int d = 15 * x.n_frames + (x.estimate_extrinsic ? 6 : 0) + (td ? 1 : 0);
+    max_d = std::max(max_d, d);
+    max_prior_n = std::max(max_prior_n, (int)x.prior_n);
+  }
+  h->B = B; h->max_d = max_d; h->max_prior_n = max_prior_n;
+  prefix<int>(h->frame_off, B, w, [](const UvsWindow &x) { return (int)x.n_frames; });
+  prefix<int>(h->point_off, B, w, [](const UvsWindow &x) { return (int)x.n_points; });
+  prefix<int>(h->line_off, B, w, [](const UvsWindow &x) { return (int)x.n_lines; });
+  prefix<int>(h->proj_off, B, w, [](const UvsWindow &x) { return (int)x.n_proj; });
+  prefix<int>(h->lobs_off, B, w, [](const UvsWindow &x) { return (int)x.n_line_obs; });
+  prefix<int>(h->vobs_off, B, w, [](const UvsWindow &x) { return (int)x.n_vp_obs; });
+  prefix<int>(h->imu_off, B, w, [](const UvsWindow &x) { return (int)x.n_imu; });
+  prefix<int>(h->prior_off, B, w, [](const UvsWindow &x) { return (int)x.prior_n; });
+  prefix<int>(h->pblk_off, B, w, [](const UvsWindow &x) { return x.prior_n > 0 ? (int)x.prior_n_blocks : 0; });
+  h->cam_off.assign(B + 1, 0); h->S_off.assign(B + 1, 0); h->priorJ_off.assign(B + 1, 0); h->win_flags.assign(B, 0);
+  for (int i = 0; i < B; i++) {
+    const int d = 15 * w[i].n_frames + (w[i].estimate_extrinsic ? 6 : 0) + (td ? 1 : 0);
+    h->cam_off[i + 1] = h->cam_off[i] + d;
+    h->S_off[i + 1] = h->S_off[i] + (long long)d * d;
+    h->priorJ_off[i + 1] = h->priorJ_off[i] + (long long)w[i].prior_n * w[i].prior_n;
+    h->win_flags[i] = (w[i].estimate_extrinsic ? WF_EXTRINSIC : 0) | (td ? WF_TD : 0);
+  }
+  const int nF = h->frame_off[B], nP = h->point_off[B], nL = h->line_off[B], nProj = h->proj_off[B], nLobs = h->lobs_off[B],
+            nVobs = h->vobs_off[B], nImu = h->imu_off[B], nCam = h->cam_off[B], nPriorR = h->prior_off[B], nBlk = h->pblk_off[B];
+  const long long nS = h->S_off[B], nPJ = h->priorJ_off[B];
+
+  // ---- input region: identical offsets in the pinned staging buffer and in the device arena
+  Layout in;
+  const size_t I = sizeof(int), Dd = sizeof(double);
+  const size_t o_frame_off = in.take((B + 1) * I), o_point_off = in.take((B + 1) * I), o_line_off = in.take((B + 1) * I),
+               o_proj_off = in.take((B + 1) * I), o_lobs_off = in.take((B + 1) * I), o_vobs_off = in.take((B + 1) * I),
+               o_imu_off = in.take((B + 1) * I), o_cam_off = in.take((B + 1) * I), o_prior_off = in.take((B + 1) * I),
+               o_pblk_off = in.take((B + 1) * I), o_S_off = in.take((B + 1) * 8), o_pJ_off = in.take((B + 1) * 8),
+               o_flags = in.take(B * I);
+  const size_t o_pose = in.take(nF * 7 * Dd), o_sb = in.take(nF * 9 * Dd), o_ex = in.take(B * 7 * Dd), o_td = in.take(B * Dd),
+               o_inv = in.take(nP * Dd), o_ortho = in.take(nL * 4 * Dd);
+  const size_t o_state_end = in.total;
+  const size_t o_pfi = in.take(nProj * I), o_pfj = in.take(nProj * I), o_ppt = in.take(nProj * I),
+               o_ppi = in.take(nProj * 3 * Dd), o_ppj = in.take(nProj * 3 * Dd);
+  const size_t o_pvi = in.take(td ? nProj * 2 * Dd : 0), o_pvj = in.take(td ? nProj * 2 * Dd : 0),
+               o_ptdi = in.take(td ? nProj * Dd : 0), o_ptdj = in.take(td ? nProj * Dd : 0),
+               o_prwi = in.take(td ? nProj * Dd : 0), o_prwj = in.take(td ? nProj * Dd : 0);
+  const size_t o_lf = in.take(nLobs * I), o_li = in.take(nLobs * I), o_lsp = in.take(nLobs * 2 * Dd), o_lep = in.take(nLobs * 2 * Dd);
+  const size_t o_vf = in.take(nVobs * I), o_vl = in.take(nVobs * I), o_vd = in.take(nVobs * 3 * Dd);
+  const size_t o_ric = in.take(B * 9 * Dd), o_tic = in.take(B * 3 * Dd);
+  const size_t o_if = in.take(nImu * I), o_idp = in.take(nImu * 3 * Dd), o_idq = in.take(nImu * 4 * Dd), o_idv = in.take(nImu * 3 * Dd),
+               o_idt = in.take(nImu * Dd), o_iba = in.take(nImu * 3 * Dd), o_ibg = in.take(nImu * 3 * Dd),
+               o_ijac = in.take((size_t)nImu * 225 * Dd), o_icov = in.take((size_t)nImu * 225 * Dd);
+  const size_t o_prJ = in.take((size_t)nPJ * Dd), o_prr = in.take(nPriorR * Dd), o_prx = in.take((size_t)nBlk * 9 * Dd),
+               o_bk = in.take(nBlk * I), o_bi = in.take(nBlk * I), o_bcol = in.take(nBlk * I), o_bcam = in.take(nBlk * I),
+               o_brow = in.take(nBlk * I);
+  h->input_bytes = in.total;
+
+  // ---- work region
+  Layout wk;
+  wk.total = in.total;
+  const size_t w_pose = wk.take(nF * 7 * Dd), w_sb = wk.take(nF * 9 * Dd), w_ex = wk.take(B * 7 * Dd), w_td = wk.take(B * Dd),
+               w_inv = wk.take(nP * Dd), w_ortho = wk.take(nL * 4 * Dd);
+  const size_t w_cur = wk.take(B * I), w_ctl = wk.take(B * sizeof(WinCtl)), w_acc = wk.take((size_t)B * ACC_STRIDE * Dd),
+               w_sum = wk.take((size_t)B * sizeof(UvsSummary));
+  const size_t w_pidx = wk.take(nProj * sizeof(int4)), w_lidx = wk.take(nLobs * sizeof(int4)), w_vidx = wk.take(nVobs * sizeof(int4)),
+               w_iidx = wk.take(nImu * sizeof(int2));
+  const size_t w_ptb = wk.take(nP * I), w_lnb = wk.take(nL * I);            // begin arrays (memset 0x7f together)
+  const size_t w_pte = wk.take(nP * I), w_lne = wk.take(nL * I), w_ptw = wk.take(nP * I), w_lnw = wk.take(nL * I);
+  const size_t w_sqi = wk.take((size_t)nImu * 225 * Dd), w_prH = wk.take((size_t)nPJ * Dd), w_err = wk.take(I);
+  const size_t w_rp = wk.take((size_t)nProj * 48 * Dd), w_rl = wk.take((size_t)nLobs * 24 * Dd), w_rv = wk.take((size_t)nVobs * 12 * Dd),
+               w_ri = wk.take((size_t)nImu * REC_IMU * Dd), w_rpr = wk.take(nPriorR * Dd);
+  const size_t w_scc = wk.take(nCam * Dd), w_scp = wk.take(nP * Dd), w_scl = wk.take(nL * 4 * Dd);
+  const size_t w_S = wk.take((size_t)nS * Dd), w_gS = wk.take(nCam * Dd), w_gf = wk.take(nCam * Dd), w_csq = wk.take(nCam * Dd);
+  const size_t w_reduce_end = wk.total;
+  const size_t w_dc = wk.take(nCam * Dd), w_dp = wk.take(nP * Dd), w_dl = wk.take(nL * 4 * Dd);
+
+  CK(h->stage.reserve(in.total));
+  CK(h->dev.reserve(wk.total));
+  char *S = h->stage.base;
+  auto cpI = [&](size_t off, const std::vector<int> &v) { std::memcpy(S + off, v.data(), v.size() * sizeof(int)); };
+  cpI(o_frame_off, h->frame_off); cpI(o_point_off, h->point_off); cpI(o_line_off, h->line_off); cpI(o_proj_off, h->proj_off);
+  cpI(o_lobs_off, h->lobs_off); cpI(o_vobs_off, h->vobs_off); cpI(o_imu_off, h->imu_off); cpI(o_cam_off, h->cam_off);
+  cpI(o_prior_off, h->prior_off); cpI(o_pblk_off, h->pblk_off); cpI(o_flags, h->win_flags);
+  std::memcpy(S + o_S_off, h->S_off.data(), (B + 1) * 8);
+  std::memcpy(S + o_pJ_off, h->priorJ_off.data(), (B + 1) * 8);
+  auto put = [&](size_t off, size_t elem_off, const void *src, size_t bytes) { if (bytes) std::memcpy(S + off + elem_off, src, bytes); };
+  for (int i = 0; i < B; i++) {
+    const UvsWindow &x = w[i];
+    const size_t f0 = h->frame_off[i], p0 = h->point_off[i], l0 = h->line_off[i], j0 = h->proj_off[i], a0 = h->lobs_off[i],
+                 v0 = h->vobs_off[i], m0 = h->imu_off[i], b0 = h->pblk_off[i];
+    put(o_pose, f0 * 7 * Dd, x.pose, x.n_frames * 7 * Dd);
+    put(o_sb, f0 * 9 * Dd, x.speed_bias, x.n_frames * 9 * Dd);
+    put(o_ex, (size_t)i * 7 * Dd, x.ex_pose, 7 * Dd);
+    { const double tdv = x.td ? x.td[0] : 0.0; put(o_td, (size_t)i * Dd, &tdv, Dd); }
+    put(o_inv, p0 * Dd, x.inv_depth, x.n_points * Dd);
+    put(o_ortho, l0 * 4 * Dd, x.ortho, x.n_lines * 4 * Dd);
+    put(o_pfi, j0 * I, x.proj_frame_i, x.n_proj * I); put(o_pfj, j0 * I, x.proj_frame_j, x.n_proj * I);
+    put(o_ppt, j0 * I, x.proj_point, x.n_proj * I);
+    put(o_ppi, j0 * 3 * Dd, x.proj_pts_i, x.n_proj * 3 * Dd); put(o_ppj, j0 * 3 * Dd, x.proj_pts_j, x.n_proj * 3 * Dd);
+    if (td) {
+      put(o_pvi, j0 * 2 * Dd, x.proj_vel_i, x.n_proj * 2 * Dd); put(o_pvj, j0 * 2 * Dd, x.proj_vel_j, x.n_proj * 2 * Dd);
+      put(o_ptdi, j0 * Dd, x.proj_td_i, x.n_proj * Dd); put(o_ptdj, j0 * Dd, x.proj_td_j, x.n_proj * Dd);
+      put(o_prwi, j0 * Dd, x.proj_row_i, x.n_proj * Dd); put(o_prwj, j0 * Dd, x.proj_row_j, x.n_proj * Dd);
+    }
+    put(o_lf, a0 * I, x.line_frame, x.n_line_obs * I); put(o_li, a0 * I, x.line_idx, x.n_line_obs * I);
+    put(o_lsp, a0 * 2 * Dd, x.line_sp, x.n_line_obs * 2 * Dd); put(o_lep, a0 * 2 * Dd, x.line_ep, x.n_line_obs * 2 * Dd);
+    put(o_vf, v0 * I, x.vp_frame, x.n_vp_obs * I); put(o_vl, v0 * I, x.vp_line, x.n_vp_obs * I);
+    put(o_vd, v0 * 3 * Dd, x.vp_dir, x.n_vp_obs * 3 * Dd);
+    if (x.line_ric) put(o_ric, (size_t)i * 9 * Dd, x.line_ric, 9 * Dd); else std::memset(S + o_ric + (size_t)i * 9 * Dd, 0, 9 * Dd);
+    if (x.line_tic) put(o_tic, (size_t)i * 3 * Dd, x.line_tic, 3 * Dd); else std::memset(S + o_tic + (size_t)i * 3 * Dd, 0, 3 * Dd);
+    put(o_if, m0 * I, x.imu_frame_i, x.n_imu * I);
+    put(o_idp, m0 * 3 * Dd, x.imu_delta_p, x.n_imu * 3 * Dd); put(o_idq, m0 * 4 * Dd, x.imu_delta_q, x.n_imu * 4 * Dd);
+    put(o_idv, m0 * 3 * Dd, x.imu_delta_v, x.n_imu * 3 * Dd); put(o_idt, m0 * Dd, x.imu_sum_dt, x.n_imu * Dd);
+    put(o_iba, m0 * 3 * Dd, x.imu_lin_ba, x.n_imu * 3 * Dd); put(o_ibg, m0 * 3 * Dd, x.imu_lin_bg, x.n_imu * 3 * Dd);
+    put(o_ijac, m0 * 225 * Dd, x.imu_jacobian, (size_t)x.n_imu * 225 * Dd);
+    put(o_icov, m0 * 225 * Dd, x.imu_covariance, (size_t)x.n_imu * 225 * Dd);
+    if (x.prior_n > 0) {
+      put(o_prJ, (size_t)h->priorJ_off[i] * Dd, x.prior_J, (size_t)x.prior_n * x.prior_n * Dd);
+      put(o_prr, (size_t)h->prior_off[i] * Dd, x.prior_r, x.prior_n * Dd);
+      int col = 0; size_t xo = 0;
+      int *bk = (int *)(S + o_bk) + b0, *bi = (int *)(S + o_bi) + b0, *bcol = (int *)(S + o_bcol) + b0,
+          *bcam = (int *)(S + o_bcam) + b0, *brow = (int *)(S + o_brow) + b0;
+      double *bx = (double *)(S + o_prx) + 9 * b0;
+      for (int b = 0; b < x.prior_n_blocks; b++) {
+        const int kind = x.prior_block_kind[b], id = x.prior_block_id[b];
+        if (kind < 0 || kind > 3) return fail(h, UVS_ERR_INVALID_ARG, "bad prior block kind");
+        if ((kind <= 1) && (id < 0 || id >= x.n_frames)) return fail(h, UVS_ERR_INVALID_ARG, "prior block id out of range");
+        bk[b] = kind; bi[b] = id; bcol[b] = col;
+        int cam = -1, row = i;
+        if (kind == UVS_BLOCK_POSE) { cam = 15 * id; row = (int)f0 + id; }
+        else if (kind == UVS_BLOCK_SPEEDBIAS) { cam = 15 * id + 6; row = (int)f0 + id; }
+        else if (kind == UVS_BLOCK_EXPOSE) cam = x.estimate_extrinsic ? 15 * x.n_frames : -1;
+        else cam = td ? 15 * x.n_frames + (x.estimate_extrinsic ? 6 : 0) : -1;
+        bcam[b] = cam; brow[b] = row;
+        const int gs = prior_global(kind);
+        for (int k = 0; k < 9; k++) bx[9 * b + k] = k < gs ? x.prior_x0[xo + k] : 0.0;
+        xo += gs; col += prior_local(kind);
+      }
+      if (col != x.prior_n) return fail(h, UVS_ERR_INVALID_ARG, "prior blocks do not add up to prior_n in window " + std::to_string(i));
+    }
+  }
+  char *Dv = h->dev.base;
+  CK(cudaMemcpyAsync(Dv, S, in.total, cudaMemcpyHostToDevice, h->stream));
+  // zero / preset the derived region that needs it
+  CK(cudaMemsetAsync(Dv + w_cur, 0, w_pidx - w_cur, h->stream));          // cur, ctl, acc, summary
+  CK(cudaMemsetAsync(Dv + w_ptb, 0x7f, w_pte - w_ptb, h->stream));        // pt_begin, ln_begin
+  CK(cudaMemsetAsync(Dv + w_pte, 0, w_sqi - w_pte, h->stream));           // pt_end .. ln_win
+  CK(cudaMemsetAsync(Dv + w_err, 0, ALIGN, h->stream));
+  CK(cudaMemsetAsync(Dv + w_scc, 0, wk.total - w_scc, h->stream));        // scales, system, deltas
+  CK(cudaMemcpyAsync(Dv + w_pose, Dv + o_pose, o_state_end - o_pose, cudaMemcpyDeviceToDevice, h->stream));  // candidate buffer = copy
+
+  Dev &D = h->D;
+  std::memset(&D, 0, sizeof(D));
+  D.B = B; D.nF = nF; D.nP = nP; D.nL = nL; D.nProj = nProj; D.nLobs = nLobs; D.nVobs = nVobs; D.nImu = nImu; D.nCam = nCam;
+  D.nPriorR = nPriorR; D.nPriorBlk = nBlk; D.estimate_td = td; D.rank = h->rank; D.nranks = h->nranks;
+#define PI(o) ((const int *)(Dv + (o)))
+#define PD(o) ((const double *)(Dv + (o)))
+#define WD(o) ((double *)(Dv + (o)))
+#define WI(o) ((int *)(Dv + (o)))
+  D.frame_off = PI(o_frame_off); D.point_off = PI(o_point_off); D.line_off = PI(o_line_off); D.proj_off = PI(o_proj_off);
+  D.lobs_off = PI(o_lobs_off); D.vobs_off = PI(o_vobs_off); D.imu_off = PI(o_imu_off); D.cam_off = PI(o_cam_off);
+  D.prior_off = PI(o_prior_off); D.pblk_off = PI(o_pblk_off);
+  D.S_off = (const long long *)(Dv + o_S_off); D.priorJ_off = (const long long *)(Dv + o_pJ_off); D.win_flags = PI(o_flags);
+  D.pose[0] = WD(o_pose); D.sb[0] = WD(o_sb); D.ex[0] = WD(o_ex); D.td[0] = WD(o_td); D.inv_depth[0] = WD(o_inv); D.ortho[0] = WD(o_ortho);
+  D.pose[1] = WD(w_pose); D.sb[1] = WD(w_sb); D.ex[1] = WD(w_ex); D.td[1] = WD(w_td); D.inv_depth[1] = WD(w_inv); D.ortho[1] = WD(w_ortho);
+  D.cur = WI(w_cur); D.ctl = (WinCtl *)(Dv + w_ctl); D.acc = WD(w_acc); D.summary = (UvsSummary *)(Dv + w_sum);
+  D.proj_fi = PI(o_pfi); D.proj_fj = PI(o_pfj); D.proj_pt = PI(o_ppt); D.proj_pts_i = PD(o_ppi); D.proj_pts_j = PD(o_ppj);
+  D.proj_vel_i = PD(o_pvi); D.proj_vel_j = PD(o_pvj); D.proj_td_i = PD(o_ptdi); D.proj_td_j = PD(o_ptdj);
+  D.proj_row_i = PD(o_prwi); D.proj_row_j = PD(o_prwj);
+  D.line_frame = PI(o_lf); D.line_idx = PI(o_li); D.line_sp = PD(o_lsp); D.line_ep = PD(o_lep);
+  D.vp_frame = PI(o_vf); D.vp_line = PI(o_vl); D.vp_dir = PD(o_vd); D.ric = PD(o_ric); D.tic = PD(o_tic);
+  D.imu_frame = PI(o_if); D.imu_dp = PD(o_idp); D.imu_dq = PD(o_idq); D.imu_dv = PD(o_idv); D.imu_sum_dt = PD(o_idt);
+  D.imu_lin_ba = PD(o_iba); D.imu_lin_bg = PD(o_ibg); D.imu_jac = PD(o_ijac); D.imu_cov = PD(o_icov);
+  D.prior_J = PD(o_prJ); D.prior_r0 = PD(o_prr); D.prior_x0 = PD(o_prx); D.pblk_kind = PI(o_bk); D.pblk_id = PI(o_bi);
+  D.pblk_col = WI(o_bcol); D.pblk_cam = WI(o_bcam); D.pblk_row = WI(o_brow);
+  D.proj_idx = (int4 *)(Dv + w_pidx); D.line_idx4 = (int4 *)(Dv + w_lidx); D.vp_idx4 = (int4 *)(Dv + w_vidx); D.imu_idx = (int2 *)(Dv + w_iidx);
+  D.pt_begin = WI(w_ptb); D.ln_begin = WI(w_lnb); D.pt_end = WI(w_pte); D.ln_end = WI(w_lne); D.pt_win = WI(w_ptw); D.ln_win = WI(w_lnw);
+  D.imu_sqrt_info = WD(w_sqi); D.prior_H = WD(w_prH); D.err = WI(w_err);
+  D.rec_proj = WD(w_rp); D.rec_line = WD(w_rl); D.rec_vp = WD(w_rv); D.rec_imu = WD(w_ri); D.rec_prior = WD(w_rpr);
+  D.scale_cam = WD(w_scc); D.scale_pt = WD(w_scp); D.scale_ln = WD(w_scl);
+  D.Smat = WD(w_S); D.gS = WD(w_gS); D.gfull = WD(w_gf); D.colsq_cam = WD(w_csq);
+  D.colsq_pt = nullptr; D.colsq_ln = nullptr;
+  D.delta_cam = WD(w_dc); D.delta_pt = WD(w_dp); D.delta_ln = WD(w_dl);
+#undef PI
+#undef PD
+#undef WD
+#undef WI
+  h->o_pose0 = o_pose; h->o_state_bytes = o_state_end - o_pose;
+  h->o_reduce = w_S; h->reduce_doubles = (w_reduce_end - w_S) / Dd;
+
+  h->launches += launch_prep(D, h->stream);
+  int rc = post_launch(h, "prep kernels");
+  if (rc) return rc;
+  int err = 0;
+  CK(cudaMemcpyAsync(h->h_active, D.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  err = *h->h_active;
+  if (err) {
+    static const char *msg[] = {"", "projection factor index out of range", "projection factors of one point are not contiguous",
+                                "projection factors of one point have different anchor frames", "line factor index out of range",
+                                "line factors of one line are not contiguous", "VP factor index out of range",
+                                "VP factor without the line factor of the same observation", "two VP factors on one line observation",
+                                "IMU factor frame out of range", "IMU covariance not invertible / not positive definite"};
+    return fail(h, err == 10 ? UVS_ERR_NOT_PD : (err == 2 || err == 3 || err == 5 || err == 7 || err == 8 ? UVS_ERR_UNSUPPORTED : UVS_ERR_INVALID_ARG),
+                std::string("uvs_upload_windows: ") + msg[err < 11 ? err : 0]);
+  }
+  h->have_window = true;
+  return UVS_OK;
+}
+
+}  // extern "C"
+
+namespace uvs {
+int handle_fail(UvsHandle *h, int status, const std::string &msg) { return fail(h, status, msg); }
+int handle_ensure_scratch(UvsHandle *h, size_t bytes) {
+  if (h->scratch.reserve(bytes) != cudaSuccess) return fail(h, UVS_ERR_CUDA, "scratch allocation failed");
+  return UVS_OK;
+}
+int handle_ensure_hscratch(UvsHandle *h, size_t bytes) {
+  if (h->hscratch.reserve(bytes) != cudaSuccess) return fail(h, UVS_ERR_CUDA, "pinned scratch allocation failed");
+  return UVS_OK;
+}
+}  // namespace uvs
+namespace {
+int ensure_scratch(UvsHandle *h, size_t bytes) { return handle_ensure_scratch(h, bytes); }
+int ensure_hscratch(UvsHandle *h, size_t bytes) { return handle_ensure_hscratch(h, bytes); }
+int all_reduce(UvsHandle *h, double *buf, size_t count) {
+  if (h->nranks <= 1) return UVS_OK;
+  if (!h->reduce) return fail(h, UVS_ERR_COMM, "multi-rank mode without a reduce callback");
+  const int rc = h->reduce(h->reduce_user, buf, (int64_t)count, (void *)h->stream);
+  if (rc != 0) return fail(h, UVS_ERR_COMM, "reduce callback failed with " + std::to_string(rc));
+  return UVS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int uvs_download_state(UvsHandle *h, int32_t B, UvsWindow *w) {
+  if (!h || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_download_state: bad arguments");
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_download_state: no window uploaded");
+  if (B != h->B) return fail(h, UVS_ERR_INVALID_ARG, "uvs_download_state: batch size differs from the upload");
+  CK(cudaSetDevice(h->device));
+  const Dev &D = h->D;
+  const size_t Dd = sizeof(double);
+  // same section layout as the input state region
+  Layout L;
+  const size_t o_pose = L.take(D.nF * 7 * Dd), o_sb = L.take(D.nF * 9 * Dd), o_ex = L.take(D.B * 7 * Dd), o_td = L.take(D.B * Dd),
+               o_inv = L.take(D.nP * Dd), o_ortho = L.take(D.nL * 4 * Dd);
+  int rc = ensure_scratch(h, L.total); if (rc) return rc;
+  rc = ensure_hscratch(h, L.total); if (rc) return rc;
+  char *ds = h->scratch.base;
+  CK(cudaMemsetAsync(ds, 0, L.total, h->stream));
+  h->launches += launch_gather_state(D, (double *)(ds + o_pose), (double *)(ds + o_sb), (double *)(ds + o_ex), (double *)(ds + o_td),
+                                     (double *)(ds + o_inv), (double *)(ds + o_ortho), h->stream);
+  rc = post_launch(h, "gather_state"); if (rc) return rc;
+  rc = all_reduce(h, (double *)ds, L.total / Dd); if (rc) return rc;
+  CK(cudaMemcpyAsync(h->hscratch.base, ds, L.total, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const char *S = h->hscratch.base;
+  for (int i = 0; i < B; i++) {
+    UvsWindow &x = w[i];
+    if (x.n_frames != h->frame_off[i + 1] - h->frame_off[i] || x.n_points != h->point_off[i + 1] - h->point_off[i] ||
+        x.n_lines != h->line_off[i + 1] - h->line_off[i])
+      return fail(h, UVS_ERR_INVALID_ARG, "uvs_download_state: window sizes differ from the upload");
+    std::memcpy(x.pose, S + o_pose + (size_t)h->frame_off[i] * 7 * Dd, x.n_frames * 7 * Dd);
+    std::memcpy(x.speed_bias, S + o_sb + (size_t)h->frame_off[i] * 9 * Dd, x.n_frames * 9 * Dd);
+    std::memcpy(x.ex_pose, S + o_ex + (size_t)i * 7 * Dd, 7 * Dd);
+    if (x.td) std::memcpy(x.td, S + o_td + (size_t)i * Dd, Dd);
+    if (x.n_points) std::memcpy(x.inv_depth, S + o_inv + (size_t)h->point_off[i] * Dd, x.n_points * Dd);
+    if (x.n_lines) std::memcpy(x.ortho, S + o_ortho + (size_t)h->line_off[i] * 4 * Dd, x.n_lines * 4 * Dd);
+  }
+  return UVS_OK;
+}
+
+// ---- factor sweeps through the ABI ---------------------------------------------------------------
+static int eval_common(UvsHandle *h, int type, double *residuals, double *jacobians, int32_t flags) {
+  if (!h) return UVS_ERR_INVALID_ARG;
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_eval_*: no window uploaded");
+  CK(cudaSetDevice(h->device));
+  const Dev &D = h->D;
+  const bool local = (flags & UVS_EVAL_LOCAL_LAYOUT) != 0, dev_out = (flags & UVS_EVAL_DEVICE_OUT) != 0;
+  const bool ceres = !local;
+  const int td = D.estimate_td;
+  long long n = 0; int NR = 0, JD = 0, REC = 0;
+  double *rec = nullptr;
+  cudaStream_t st = h->stream;
+  switch (type) {
+    case 0: n = D.nProj; NR = 2; REC = ceres ? (td ? CREC_PROJ_TD : CREC_PROJ) : (td ? REC_PROJ_TD : REC_PROJ); rec = D.rec_proj;
+      h->launches += launch_proj(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st); break;
+    case 1: n = D.nLobs; NR = 2; REC = ceres ? CREC_LINE : REC_LINE; rec = D.rec_line;
+      h->launches += launch_line(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st); break;
+    case 2: n = D.nVobs; NR = 1; REC = ceres ? CREC_VP : REC_VP; rec = D.rec_vp;
+      h->launches += launch_vp(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st); break;
+    case 3: n = D.nImu; NR = 15; REC = 15 + 15 * (2 * (ceres ? 7 : 6) + 18); rec = D.rec_imu;
+      h->launches += launch_imu(D, h->P, true, 0, 0, rec, nullptr, nullptr, 0, st); break;
+    default: return UVS_ERR_INVALID_ARG;
+  }
+  int rc = post_launch(h, "uvs_eval sweep"); if (rc) return rc;
+  if (n == 0) return UVS_OK;
+  JD = REC - NR;
+  double *dr = residuals, *dj = jacobians;
+  if (!dev_out) {
+    rc = ensure_scratch(h, (size_t)n * REC * sizeof(double) + 2 * ALIGN); if (rc) return rc;
+    dr = (double *)h->scratch.base;
+    dj = (double *)(h->scratch.base + align_up((size_t)n * NR * sizeof(double)));
+  }
+  if (type == 3) h->launches += launch_export_imu(rec, (int)n, ceres ? 7 : 6, residuals ? dr : nullptr, jacobians ? dj : nullptr, st);
+  else h->launches += launch_split(rec, n, REC, NR, residuals ? dr : nullptr, jacobians ? dj : nullptr, st);
+  rc = post_launch(h, "uvs_eval export"); if (rc) return rc;
+  if (!dev_out) {
+    if (residuals) CK(cudaMemcpyAsync(residuals, dr, (size_t)n * NR * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (jacobians) CK(cudaMemcpyAsync(jacobians, dj, (size_t)n * JD * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return UVS_OK;
+}
+
+int uvs_eval_proj(UvsHandle *h, double *r, double *J, int32_t flags) { return eval_common(h, 0, r, J, flags); }
+int uvs_eval_line(UvsHandle *h, double *r, double *J, int32_t flags) { return eval_common(h, 1, r, J, flags); }
+int uvs_eval_vp(UvsHandle *h, double *r, double *J, int32_t flags) { return eval_common(h, 2, r, J, flags); }
+int uvs_eval_imu(UvsHandle *h, double *r, double *J, int32_t flags) { return eval_common(h, 3, r, J, flags); }
+
+int uvs_eval_prior(UvsHandle *h, double *residuals, double *jacobians, int32_t flags) {
+  if (!h) return UVS_ERR_INVALID_ARG;
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_eval_prior: no window uploaded");
+  CK(cudaSetDevice(h->device));
+  const Dev &D = h->D;
+  if (D.nPriorR == 0) return UVS_OK;
+  const bool local = (flags & UVS_EVAL_LOCAL_LAYOUT) != 0, dev_out = (flags & UVS_EVAL_DEVICE_OUT) != 0;
+  cudaStream_t st = h->stream;
+  h->launches += launch_prior(D, h->max_prior_n, false, 0, 0, D.rec_prior, nullptr, 0, st);
+  int rc = post_launch(h, "uvs_eval_prior"); if (rc) return rc;
+  if (residuals) CK(cudaMemcpyAsync(residuals, D.rec_prior, (size_t)D.nPriorR * sizeof(double), dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (jacobians) {
+    // per window: n x sum(widths)
+    std::vector<long long> off(h->B + 1, 0);
+    for (int i = 0; i < h->B; i++) {
+      long long cols = 0;
+      const int n = h->prior_off[i + 1] - h->prior_off[i];
+      // widths come from the staging copy of the block kinds
+      const int *bk = nullptr; (void)bk;
+      off[i + 1] = off[i];
+      if (n > 0) {
+        // block kinds live in the pinned staging buffer at the same offset as on the device
+        const int *kinds = (const int *)(h->stage.base + ((const char *)D.pblk_kind - h->dev.base));
+        for (int b = h->pblk_off[i]; b < h->pblk_off[i + 1]; b++) cols += local ? prior_local(kinds[b]) : prior_global(kinds[b]);
+        off[i + 1] += (long long)n * cols;
+      }
+    }
+    const size_t jbytes = (size_t)off[h->B] * sizeof(double), obytes = align_up((h->B + 1) * sizeof(long long));
+    rc = ensure_scratch(h, obytes + jbytes + ALIGN); if (rc) return rc;
+    CK(cudaMemcpyAsync(h->scratch.base, off.data(), (h->B + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    double *dj = dev_out ? jacobians : (double *)(h->scratch.base + obytes);
+    h->launches += launch_export_prior(D, local ? 6 : 7, dj, (const long long *)h->scratch.base, st);
+    rc = post_launch(h, "uvs_eval_prior export"); if (rc) return rc;
+    if (!dev_out) CK(cudaMemcpyAsync(jacobians, dj, jbytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // `off` must outlive the H2D copy
+  }
+  CK(cudaStreamSynchronize(st));
+  return UVS_OK;
+}
+
+static int launch_resid_sweep(UvsHandle *h, int mode, int cand, int slot) {
+  const Dev &D = h->D;
+  double *cost = D.acc + slot;
+  cudaStream_t st = h->stream;
+  h->launches += launch_proj(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_line(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_vp(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_imu(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_prior(D, h->max_prior_n, false, mode, cand, D.rec_prior, cost, ACC_STRIDE, st);
+  return post_launch(h, "residual sweep");
+}
+
+static int launch_jac_sweep(UvsHandle *h, int mode) {
+  const Dev &D = h->D;
+  double *cost = D.acc + ACC_COST0;
+  cudaStream_t st = h->stream;
+  h->launches += launch_proj(D, h->P, true, false, mode, 0, D.rec_proj, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_line(D, h->P, true, false, mode, 0, D.rec_line, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_vp(D, h->P, true, false, mode, 0, D.rec_vp, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_imu(D, h->P, true, mode, 0, D.rec_imu, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_prior(D, h->max_prior_n, true, mode, 0, D.rec_prior, cost, ACC_STRIDE, st);
+  return post_launch(h, "Jacobian sweep");
+}
+
+int uvs_eval_cost(UvsHandle *h, double *cost) {
+  if (!h || !cost) return fail(h, UVS_ERR_INVALID_ARG, "uvs_eval_cost: bad arguments");
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_eval_cost: no window uploaded");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_scratch(h, h->B * sizeof(double)); if (rc) return rc;
+  h->launches += launch_copy_acc(h->D, ACC_CAND_COST, (double *)h->scratch.base, 1, h->stream);   // clear
+  rc = launch_resid_sweep(h, 0, 0, ACC_CAND_COST); if (rc) return rc;
+  h->launches += launch_copy_acc(h->D, ACC_CAND_COST, (double *)h->scratch.base, 1, h->stream);
+  CK(cudaMemcpyAsync(cost, h->scratch.base, h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return UVS_OK;
+}
+
+// ---- Levenberg-Marquardt + Schur solve (ceres::Solve replacement, estimator.cpp:982-994) ---------
+int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
+  if (!h) return UVS_ERR_INVALID_ARG;
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_solve: no window uploaded");
+  CK(cudaSetDevice(h->device));
+  const Dev &D = h->D;
+  const Params &P = h->P;
+  cudaStream_t st = h->stream;
+  if (h->opts.max_num_iterations + 1 > UVS_MAX_ITER_LOG) return fail(h, UVS_ERR_CAPACITY, "max_num_iterations exceeds the iteration log");
+  const auto t0 = std::chrono::steady_clock::now();
+  CK(cudaEventRecord(h->ev_a, st));
+  h->launches += launch_solve_init(D, P, st);
+  float sweep_ms = 0.f; int n_sweeps = 0;
+  const bool time_sweeps = true;
+  const bool check_exit = !h->opts.fixed_iterations;
+  int rc = UVS_OK;
+  for (int it = 0; it < h->opts.max_num_iterations; it++) {
+    if (time_sweeps) CK(cudaEventRecord(h->ev_c, st));
+    rc = launch_jac_sweep(h, 1); if (rc) return rc;
+    if (time_sweeps) CK(cudaEventRecord(h->ev_d, st));
+    h->launches += launch_build(D, P, h->max_prior_n, st);
+    rc = post_launch(h, "build"); if (rc) return rc;
+    if (h->nranks > 1) {
+      rc = all_reduce(h, (double *)(h->dev.base + h->o_reduce), h->reduce_doubles); if (rc) return rc;
+      rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc;
+    }
+    h->launches += launch_chol(D, P, h->max_d, h->packed_limit, st);
+    rc = post_launch(h, "chol"); if (rc) return rc;
+    h->launches += launch_backsub(D, P, st);
+    rc = post_launch(h, "backsub"); if (rc) return rc;
+    rc = launch_resid_sweep(h, 1, 1, ACC_CAND_COST); if (rc) return rc;
+    if (h->nranks > 1) { rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc; }
+    h->launches += launch_step(D, P, st);
+    rc = post_launch(h, "step"); if (rc) return rc;
+    if (time_sweeps) {
+      // the events are on this stream; reading them needs the iteration to have finished
+      CK(cudaEventSynchronize(h->ev_d));
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev_c, h->ev_d) == cudaSuccess) { sweep_ms += ms; n_sweeps++; }
+    }
+    if (check_exit || h->opts.max_solver_time > 0.0) {
+      h->launches += launch_count_active(D, h->d_active, st);
+      CK(cudaMemcpyAsync(h->h_active, h->d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (*h->h_active == 0) break;
+      if (h->opts.max_solver_time > 0.0 && !h->opts.fixed_iterations) {
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (el >= h->opts.max_solver_time) break;   // remaining windows report UVS_TERM_NO_CONVERGENCE / time
+      }
+    }
+  }
+  h->launches += launch_finish(D, st);
+  CK(cudaEventRecord(h->ev_b, st));
+  if (summaries) CK(cudaMemcpyAsync(summaries, D.summary, (size_t)D.B * sizeof(UvsSummary), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&h->last_solve_ms, h->ev_a, h->ev_b);
+  h->last_sweep_ms = sweep_ms; h->n_sweeps = n_sweeps;
+  if (summaries && h->opts.max_solver_time > 0.0 && !h->opts.fixed_iterations) {
+    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (el >= h->opts.max_solver_time)
+      for (int i = 0; i < D.B; i++) if (summaries[i].termination == UVS_TERM_NO_CONVERGENCE && summaries[i].num_iterations <= h->opts.max_num_iterations) summaries[i].termination = UVS_TERM_TIME;
+  }
+  return UVS_OK;
+}
+
+int uvs_batch_solve(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOptions *opts, UvsSummary *summaries) {
+  int rc = uvs_upload_windows(h, B, w, opts); if (rc) return rc;
+  rc = uvs_solve(h, summaries); if (rc) return rc;
+  return uvs_download_state(h, B, w);
+}
+
+int uvs_marginalize(UvsHandle *h, int32_t window_index, int32_t flag, UvsPrior *out) {
+  if (!h || !out) return fail(h, UVS_ERR_INVALID_ARG, "uvs_marginalize: bad arguments");
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_marginalize: no window uploaded");
+  return uvs_marginalize_impl(h, window_index, flag, out);
+}
+
+int uvs_sweep_bytes(UvsHandle *h, int64_t *jac, int64_t *res) {
+  if (!h) return UVS_ERR_INVALID_ARG;
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_sweep_bytes: no window uploaded");
+  // algorithmic bytes per factor (reads of observations + indices, writes of r and local J)
+  const Dev &D = h->D;
+  long long pr = 0;
+  for (int i = 0; i < h->B; i++) { const long long n = h->prior_off[i + 1] - h->prior_off[i]; pr += 8 * (n * n + 3 * n); }
+  const long long state = 8LL * (16LL * D.nF + 8LL * D.B + D.nP + 4LL * D.nL);
+  if (jac) *jac = 384LL * D.nProj + 232LL * D.nLobs + 120LL * D.nVobs + 6024LL * D.nImu + pr + state;
+  if (res) *res = 80LL * D.nProj + 72LL * D.nLobs + 40LL * D.nVobs + 2424LL * D.nImu + pr + state;
+  return UVS_OK;
+}
+
+int64_t uvs_launch_count(const UvsHandle *h) { return h ? h->launches : 0; }
+
+int uvs_last_solve_ms(const UvsHandle *h, float *ms) {
+  if (!h || !ms) return UVS_ERR_INVALID_ARG;
+  *ms = h->last_solve_ms;
+  return UVS_OK;
+}
+
+int uvs_last_sweep_ms(const UvsHandle *h, float *ms, int32_t *n) {
+  if (!h || !ms) return UVS_ERR_INVALID_ARG;
+  *ms = h->last_sweep_ms;
+  if (n) *n = h->n_sweeps;
+  return UVS_OK;
+}
+
+int uvs_comm_init(UvsHandle *h, int32_t rank, int32_t nranks, UvsAllReduceFn reduce, void *user) {
+  if (!h || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(h, UVS_ERR_INVALID_ARG, "uvs_comm_init: bad arguments");
+  if (nranks > 1 && !reduce) return fail(h, UVS_ERR_INVALID_ARG, "uvs_comm_init: reduce callback missing");
+  h->rank = rank; h->nranks = nranks; h->reduce = reduce; h->reduce_user = user;
+  h->D.rank = rank; h->D.nranks = nranks;
+  return UVS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// uvs_handle.h — the opaque UvsHandle behind the C ABI (internal to libuvs_b200).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/uvs.h"
+#include "uvs_device.cuh"
+
+namespace uvs {
+
+constexpr size_t ALIGN = 256;
+inline size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
+
+// bump allocator over one growable device arena (and a mirrored pinned staging buffer)
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  bool pinned_host = false;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    release();
+    const size_t want = bytes + bytes / 4 + (1 << 20);
+    cudaError_t e = pinned_host ? cudaMallocHost((void **)&base, want) : cudaMalloc((void **)&base, want);
+    if (e != cudaSuccess) { base = nullptr; cap = 0; return e; }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (base) { if (pinned_host) cudaFreeHost(base); else cudaFree(base); }
+    base = nullptr; cap = 0;
+  }
+};
+
+struct Layout {   // byte offsets of one section list; computed twice (input region, work region)
+  size_t total = 0;
+  size_t take(size_t bytes) { const size_t o = total; total = align_up(total + std::max<size_t>(bytes, 8)); return o; }
+};
+
+}  // namespace uvs
+
+struct UvsHandle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+  std::string err;
+  uvs::Arena dev, stage, scratch, hscratch;
+  uvs::Dev D{};
+  uvs::Params P{};
+  UvsOptions opts{};
+  bool have_window = false;
+  int B = 0, max_d = 0, max_prior_n = 0, packed_limit = 0;
+  size_t input_bytes = 0;
+  // host copies of the per-window tables
+  std::vector<int> frame_off, point_off, line_off, proj_off, lobs_off, vobs_off, imu_off, cam_off, prior_off, pblk_off;
+  std::vector<long long> S_off, priorJ_off;
+  std::vector<int> win_flags;
+  // offsets of the state sections inside the device arena (buffer 0) for download
+  size_t o_pose0 = 0, o_state_bytes = 0;
+  size_t o_reduce = 0, reduce_doubles = 0;   // [Smat | gS | gfull | colsq] block for the multi-GPU exchange
+  int64_t launches = 0;
+  float last_solve_ms = 0.f, last_sweep_ms = 0.f;
+  int n_sweeps = 0;
+  int rank = 0, nranks = 1;
+  UvsAllReduceFn reduce = nullptr;
+  void *reduce_user = nullptr;
+  int *d_active = nullptr;
+  int *h_active = nullptr;
+};
+
+
+namespace uvs {
+int handle_fail(UvsHandle *h, int status, const std::string &msg);
+int handle_ensure_scratch(UvsHandle *h, size_t bytes);
+int handle_ensure_hscratch(UvsHandle *h, size_t bytes);
+}  // namespace uvs

@@ -1,0 +1,49 @@
+// uvs_kernels.h — host-callable launch wrappers of the sm_100a kernels (internal to libuvs_b200).
+// Every wrapper returns the number of kernel launches it issued.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "uvs_device.cuh"
+
+namespace uvs {
+
+// uvs_prep.cu
+int launch_prep(const Dev &D, cudaStream_t st);
+int launch_split(const double *rec, long long n, int REC, int NR, double *r_out, double *J_out, cudaStream_t st);
+int launch_export_imu(const double *rec, int n, int PW, double *r_out, double *J_out, cudaStream_t st);
+int launch_export_prior(const Dev &D, int PW, double *J_out, const long long *out_off, cudaStream_t st);
+
+// uvs_sweep.cu — mode 0: API evaluation of every factor; mode 1: solver (per-window state gates)
+int launch_proj(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
+                double *cost, int cost_stride, cudaStream_t st);
+int launch_line(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
+                double *cost, int cost_stride, cudaStream_t st);
+int launch_vp(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
+              double *cost, int cost_stride, cudaStream_t st);
+int launch_imu(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out, double *res_out, double *cost,
+               int cost_stride, cudaStream_t st);
+int launch_prior(const Dev &D, int max_prior_n, bool jac_phase, int mode, int cand, double *res_out, double *cost,
+                 int cost_stride, cudaStream_t st);
+
+// uvs_build.cu
+int launch_build(const Dev &D, const Params &P, int max_prior_n, cudaStream_t st);
+int launch_backsub(const Dev &D, const Params &P, cudaStream_t st);
+
+// uvs_solve.cu
+int chol_packed_limit(size_t max_smem);
+int set_chol_smem(size_t bytes);
+int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st);
+int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, cudaStream_t st);
+int launch_step(const Dev &D, const Params &P, cudaStream_t st);
+int launch_finish(const Dev &D, cudaStream_t st);
+int launch_count_active(const Dev &D, int *out, cudaStream_t st);
+int launch_copy_acc(const Dev &D, int slot, double *out, int zero, cudaStream_t st);
+
+int launch_gather_state(const Dev &D, double *out_pose, double *out_sb, double *out_ex, double *out_td, double *out_inv,
+                        double *out_ortho, cudaStream_t st);
+
+}  // namespace uvs
+
+// uvs_marg.cu
+struct UvsHandle;
+int uvs_marginalize_impl(UvsHandle *h, int window_index, int flag, UvsPrior *out);

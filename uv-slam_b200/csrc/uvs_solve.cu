@@ -1,0 +1,406 @@
+// uvs_solve.cu — reduced-camera-system solve and Levenberg-Marquardt step control, all on device.
+//
+// Restates what ceres::Solve does with the options of Estimator::optimization()
+// (vins_estimator/src/estimator.cpp:982-994: SPARSE_SCHUR, LEVENBERG_MARQUARDT, defaults otherwise)
+// after the landmark blocks have been eliminated (uvs_build.cu):
+//   k_solve_init  trust-region state of every window
+//   k_chol        Jacobi scaling (fixed from the first Jacobian), LM diagonal, dense Cholesky of the
+//                 reduced camera system, camera step, x+ = Plus(x, delta) for poses / speed-biases /
+//                 extrinsic / td (pose_local_parameterization.cpp:3-19), model cost change of the
+//                 camera-only factors
+//   k_step        step quality, accept / reject, radius update, termination tests, iteration log
+// One CTA per window; windows of a batch advance in lock-step but accept / reject independently.
+#include "uvs_device.cuh"
+#include "uvs_math.cuh"
+#include "uvs_kernels.h"
+
+namespace uvs {
+
+constexpr int CT = 256;
+
+__device__ __forceinline__ double clampd2(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__device__ __forceinline__ void zero_window_system(const Dev &D, int w) {
+  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+  double *S = D.Smat + D.S_off[w];
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) S[e] = 0.0;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) { D.gS[co + e] = 0.0; D.gfull[co + e] = 0.0; D.colsq_cam[co + e] = 0.0; }
+}
+
+__global__ void __launch_bounds__(CT) k_solve_init(Dev D, Params P) {
+  const int w = blockIdx.x;
+  if (threadIdx.x == 0) {
+    WinCtl &c = D.ctl[w];
+    c.cost = 0.0; c.radius = P.initial_radius; c.decrease_factor = 2.0; c.x_norm = 0.0;
+    c.state = WS_ACTIVE | WS_NEED_JAC | WS_STEP_OK;
+    c.iter = 0; c.n_success = 0; c.n_invalid = 0; c.termination = UVS_TERM_NO_CONVERGENCE; c.status = UVS_OK;
+    c.have_scale = 0;
+  }
+  for (int e = threadIdx.x; e < ACC_STRIDE; e += blockDim.x) D.acc[(size_t)w * ACC_STRIDE + e] = 0.0;
+  unsigned char *sm = reinterpret_cast<unsigned char *>(D.summary + w);
+  for (int e = threadIdx.x; e < (int)sizeof(UvsSummary); e += blockDim.x) sm[e] = 0;
+  zero_window_system(D, w);
+}
+
+__device__ __forceinline__ double block_max(double v, double *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double m = red[0];
+  for (int k = 1; k < CT / 32; k++) m = fmax(m, red[k]);
+  __syncthreads();
+  return m;
+}
+__device__ __forceinline__ double block_sum(double v, double *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double m = 0.0;
+  for (int k = 0; k < CT / 32; k++) m += red[k];
+  __syncthreads();
+  return m;
+}
+
+// Packed lower-triangular storage (row i holds columns 0..i) in shared memory, or the window's own
+// d x d block of Smat reused as a full row-major matrix when it does not fit.
+template <bool kPacked>
+struct LowerMat {
+  double *a; int ld;
+  __device__ __forceinline__ double &at(int i, int k) const { return kPacked ? a[(size_t)i * (i + 1) / 2 + k] : a[(size_t)i * ld + k]; }
+};
+
+template <bool kPacked>
+__device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) {
+  __shared__ double red[CT / 32];
+  __shared__ int s_flag;
+  WinCtl &ctl = D.ctl[w];
+  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+  const int F = D.frame_off[w + 1] - D.frame_off[w];
+  const int fl = D.win_flags[w];
+  double *acc = D.acc + (size_t)w * ACC_STRIDE;
+  const int tid = threadIdx.x;
+  const double *gfull = D.gfull + co, *gS = D.gS + co, *colsq = D.colsq_cam + co;
+  double *scale = D.scale_cam + co;
+  double *Sg = D.Smat + D.S_off[w];
+
+  // ---- gradient max norm of the current iterate, iteration-0 bookkeeping, gradient tolerance
+  double gm = 0.0;
+  for (int c = tid; c < d; c += CT) gm = fmax(gm, fabs(gfull[c]));
+  if (tid < MAX_RANKS) gm = fmax(gm, acc[ACC_GMAX + tid]);
+  gm = block_max(gm, red);
+  if (tid == 0) {
+    UvsSummary &sm = D.summary[w];
+    if (ctl.iter == 0) {
+      ctl.cost = acc[ACC_COST0];
+      sm.initial_cost = ctl.cost;
+      sm.cost[0] = ctl.cost; sm.radius[0] = ctl.radius; sm.gradient_max_norm[0] = gm; sm.step_accepted[0] = 1;
+      ctl.iter = 1;
+    } else if ((ctl.state & WS_NEED_JAC) && ctl.iter - 1 < UVS_MAX_ITER_LOG) {
+      sm.gradient_max_norm[ctl.iter - 1] = gm;
+    }
+    int stop = 0;
+    if (!P.fixed_iterations && (ctl.state & WS_NEED_JAC) && gm <= P.gradient_tolerance) {
+      ctl.termination = UVS_TERM_GRADIENT_TOL; ctl.state &= ~WS_ACTIVE; stop = 1;
+    }
+    if (!isfinite(ctl.cost)) { ctl.termination = UVS_TERM_FAILURE; ctl.status = UVS_ERR_NOT_FINITE; ctl.state &= ~WS_ACTIVE; stop = 1; }
+    s_flag = stop;
+  }
+  __syncthreads();
+  if (s_flag) return;
+
+  // ---- Jacobi scaling, fixed from the first Jacobian: s = 1 / (1 + ||J[:,c]||)
+  if (!ctl.have_scale) for (int c = tid; c < d; c += CT) scale[c] = 1.0 / (1.0 + sqrt(colsq[c]));
+  __syncthreads();
+
+  // ---- assemble  A = D_s V D_s + D^2  (lower), last row = -D_s g  (augmented system)
+  LowerMat<kPacked> A;
+  A.a = kPacked ? smem : Sg;
+  A.ld = d;
+  double *vec = kPacked ? smem + (size_t)(d + 1) * (d + 2) / 2 : D.delta_cam + co;  // solution vector (d doubles)
+  const double radius = ctl.radius;
+  if (kPacked) {
+    for (int e = tid; e < d * d; e += CT) {
+      const int j = e / d, i = e - j * d;   // upper entry (j, i), j <= i
+      if (j > i) continue;
+      double v = scale[i] * scale[j] * Sg[e];
+      if (i == j) { const double h = scale[i] * scale[i] * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+      A.at(i, j) = v;
+    }
+    for (int c = tid; c < d; c += CT) A.at(d, c) = -scale[c] * gS[c];
+    if (tid == 0) A.at(d, d) = 0.0;
+  } else {
+    // in place in global memory: mirror the upper triangle into the lower one
+    for (int e = tid; e < d * d; e += CT) {
+      const int i = e / d, j = e - i * d;   // lower entry (i, j), j <= i
+      if (j > i) continue;
+      double v = scale[i] * scale[j] * Sg[(size_t)j * d + i];
+      if (i == j) { const double h = scale[i] * scale[i] * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+      Sg[e] = v;
+    }
+    for (int c = tid; c < d; c += CT) vec[c] = -scale[c] * gS[c];
+  }
+  __syncthreads();
+
+  // ---- right-looking Cholesky; the appended row turns into z = L^-1 (-g)
+  const int rows = kPacked ? d + 1 : d;
+  const int ti = tid >> 4, tk = tid & 15;
+  bool fail = false;
+  for (int j = 0; j < d; j++) {
+    const double piv = A.at(j, j);
+    if (!(piv > 0.0) || !isfinite(piv)) { fail = true; break; }
+    const double inv = 1.0 / sqrt(piv);
+    __syncthreads();
+    for (int i = j + 1 + tid; i < rows; i += CT) A.at(i, j) *= inv;
+    if (!kPacked && tid == 0) vec[j] *= inv;
+    if (tid == 0) A.at(j, j) = piv * inv;
+    __syncthreads();
+    if (!kPacked) {
+      const double zj = vec[j];
+      for (int i = j + 1 + tid; i < d; i += CT) vec[i] -= A.at(i, j) * zj;
+    }
+    for (int i = j + 1 + ti; i < rows; i += 16) {
+      const double lij = A.at(i, j);
+      const int kmax = i < d ? i : d - 1;   // the appended row has no diagonal entry
+      for (int k = j + 1 + tk; k <= kmax; k += 16) A.at(i, k) -= lij * A.at(k, j);
+    }
+    __syncthreads();
+  }
+  if (fail) {
+    if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
+    return;
+  }
+  // ---- back-solve L^T y = z with one warp
+  if (kPacked) { for (int c = tid; c < d; c += CT) vec[c] = A.at(d, c); }
+  __syncthreads();
+  if (tid < 32) {
+    for (int j = d - 1; j >= 0; j--) {
+      const double yj = vec[j] / A.at(j, j);
+      __syncwarp();
+      for (int i = tid; i < j; i += 32) vec[i] -= A.at(j, i) * yj;
+      if (tid == 0) vec[j] = yj;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- delta = s .* y, candidate camera state, step / state norms
+  const int cur = D.cur[w];
+  const int fo = D.frame_off[w];
+  double step2 = 0.0, x2 = 0.0;
+  for (int c = tid; c < d; c += CT) { const double dl = scale[c] * vec[c]; D.delta_cam[co + c] = dl; }
+  __syncthreads();
+  const double *dl = D.delta_cam + co;
+  const bool lead = D.nranks <= 1 || D.rank == 0;
+  for (int f = tid; f < F; f += CT) {
+    const double *x = D.pose[cur] + 7 * (size_t)(fo + f);
+    double *y = D.pose[cur ^ 1] + 7 * (size_t)(fo + f);
+    const double *t = dl + 15 * f;
+    for (int k = 0; k < 3; k++) y[k] = x[k] + t[k];
+    q4 q = qmul(mkq(x[3], x[4], x[5], x[6]), mkq(t[3] / 2.0, t[4] / 2.0, t[5] / 2.0, 1.0));
+    const double nq = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    y[3] = q.x / nq; y[4] = q.y / nq; y[5] = q.z / nq; y[6] = q.w / nq;
+    for (int k = 0; k < 7; k++) { step2 += (y[k] - x[k]) * (y[k] - x[k]); x2 += x[k] * x[k]; }
+    const double *xs = D.sb[cur] + 9 * (size_t)(fo + f);
+    double *ys = D.sb[cur ^ 1] + 9 * (size_t)(fo + f);
+    for (int k = 0; k < 9; k++) { ys[k] = xs[k] + t[6 + k]; step2 += t[6 + k] * t[6 + k]; x2 += xs[k] * xs[k]; }
+  }
+  if (tid == 0) {
+    const double *x = D.ex[cur] + 7 * (size_t)w;
+    double *y = D.ex[cur ^ 1] + 7 * (size_t)w;
+    if (fl & WF_EXTRINSIC) {
+      const double *t = dl + 15 * F;
+      for (int k = 0; k < 3; k++) y[k] = x[k] + t[k];
+      q4 q = qmul(mkq(x[3], x[4], x[5], x[6]), mkq(t[3] / 2.0, t[4] / 2.0, t[5] / 2.0, 1.0));
+      const double nq = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+      y[3] = q.x / nq; y[4] = q.y / nq; y[5] = q.z / nq; y[6] = q.w / nq;
+      for (int k = 0; k < 7; k++) { step2 += (y[k] - x[k]) * (y[k] - x[k]); x2 += x[k] * x[k]; }
+    } else {
+      for (int k = 0; k < 7; k++) y[k] = x[k];
+    }
+    const double tdx = D.td[cur][w];
+    if (fl & WF_TD) {
+      const double t = dl[15 * F + ((fl & WF_EXTRINSIC) ? 6 : 0)];
+      D.td[cur ^ 1][w] = tdx + t; step2 += t * t; x2 += tdx * tdx;
+    } else {
+      D.td[cur ^ 1][w] = tdx;
+    }
+  }
+  step2 = block_sum(step2, red);
+  x2 = block_sum(x2, red);
+
+  // ---- model cost change of the camera-only factors: sum (J delta) . (r + J delta / 2)
+  double mc = 0.0;
+  if (lead) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int f = D.imu_off[w] + warp; f < D.imu_off[w + 1]; f += CT / 32) {
+      const double *R = D.rec_imu + (size_t)f * REC_IMU;
+      const int c0 = 15 * (D.imu_idx[f].x - fo);
+      if (lane < 15) {
+        double jd = 0.0;
+        for (int c = 0; c < 30; c++) jd += R[15 + lane * 30 + c] * dl[c0 + c];
+        mc += jd * (R[lane] + 0.5 * jd);
+      }
+    }
+    const int n = D.prior_off[w + 1] - D.prior_off[w];
+    if (n > 0) {
+      const double *J0 = D.prior_J + D.priorJ_off[w];
+      const double *r = D.rec_prior + D.prior_off[w];
+      for (int i = warp; i < n; i += CT / 32) {
+        double jd = 0.0;
+        for (int b = D.pblk_off[w]; b < D.pblk_off[w + 1]; b++) {
+          const int kind = D.pblk_kind[b], cam = D.pblk_cam[b], col = D.pblk_col[b];
+          if (cam < 0) continue;
+          const int ls = (kind == 0 || kind == 2) ? 6 : (kind == 1 ? 9 : 1);
+          if (lane < ls) jd += J0[(size_t)i * n + col + lane] * dl[cam + lane];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) jd += __shfl_xor_sync(0xffffffffu, jd, o);
+        if (lane == 0) mc += jd * (r[i] + 0.5 * jd);
+      }
+    }
+  }
+  mc = block_sum(mc, red);
+  if (tid == 0) {
+    if (lead) { atomicAdd(acc + ACC_MODEL, -mc); atomicAdd(acc + ACC_STEP2, step2); atomicAdd(acc + ACC_XNORM2, x2); }
+    ctl.state |= WS_STEP_OK;
+    ctl.have_scale = 1;
+  }
+}
+
+__global__ void __launch_bounds__(CT) k_chol(Dev D, Params P, int packed_limit) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  if (D.acc[(size_t)w * ACC_STRIDE + ACC_FAIL] != 0.0) {   // a landmark block was not positive definite
+    if (threadIdx.x == 0) { D.ctl[w].state &= ~WS_STEP_OK; D.ctl[w].have_scale = 1; if (D.ctl[w].iter == 0) { D.ctl[w].cost = D.acc[(size_t)w * ACC_STRIDE + ACC_COST0]; D.ctl[w].iter = 1; D.summary[w].initial_cost = D.ctl[w].cost; D.summary[w].cost[0] = D.ctl[w].cost; } }
+    return;
+  }
+  const int d = D.cam_off[w + 1] - D.cam_off[w];
+  if (d <= packed_limit) chol_window<true>(D, P, w, smem);
+  else chol_window<false>(D, P, w, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CT) k_step(Dev D, Params P) {
+  const int w = blockIdx.x;
+  WinCtl &c = D.ctl[w];
+  if (!(c.state & WS_ACTIVE)) return;
+  double *acc = D.acc + (size_t)w * ACC_STRIDE;
+  if (threadIdx.x == 0) {
+    UvsSummary &sm = D.summary[w];
+    const bool fixed = P.fixed_iterations != 0;
+    const double mc = acc[ACC_MODEL], step_norm = sqrt(acc[ACC_STEP2]), cand_cost = acc[ACC_CAND_COST];
+    const bool step_ok = (c.state & WS_STEP_OK) && acc[ACC_FAIL] == 0.0;
+    const bool valid = step_ok && mc > 0.0 && isfinite(step_norm) && isfinite(mc);
+    const int it = c.iter;   // index of the log entry written now
+    double log_rel = 0.0, log_step = 0.0;
+    int accepted = 0, done = 0;
+    const double gprev = it - 1 < UVS_MAX_ITER_LOG ? sm.gradient_max_norm[it - 1] : 0.0;
+    c.state &= ~WS_NEED_JAC;
+    if (!valid) {   // invalid step: the LM strategy treats it as a rejected step
+      c.radius /= c.decrease_factor; c.decrease_factor *= 2.0;
+      if (++c.n_invalid >= 5 && !fixed) { c.termination = UVS_TERM_FAILURE; done = 1; }
+      else if (!fixed && c.radius < P.min_radius) { c.termination = UVS_TERM_MIN_RADIUS; done = 1; }
+    } else {
+      c.n_invalid = 0;
+      c.x_norm = sqrt(acc[ACC_XNORM2]);
+      log_step = step_norm;
+      const double cost_change = c.cost - cand_cost;
+      if (!fixed && step_norm <= P.parameter_tolerance * (c.x_norm + P.parameter_tolerance)) {
+        c.termination = UVS_TERM_PARAMETER_TOL; done = 1;
+      } else if (!fixed && fabs(cost_change) <= P.function_tolerance * c.cost) {
+        c.termination = UVS_TERM_FUNCTION_TOL; done = 1;
+      } else {
+        const double rel = cost_change / mc;
+        log_rel = rel;
+        accepted = isfinite(cand_cost) && rel > P.min_relative_decrease;
+        if (accepted) {
+          D.cur[w] ^= 1;
+          c.cost = cand_cost;
+          const double t = 2.0 * rel - 1.0;
+          c.radius = fmin(P.max_radius, c.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+          c.decrease_factor = 2.0;
+          c.n_success++;
+          c.state |= WS_NEED_JAC;
+        } else {
+          c.radius /= c.decrease_factor; c.decrease_factor *= 2.0;
+        }
+        if (!fixed && c.radius < P.min_radius) { c.termination = UVS_TERM_MIN_RADIUS; done = 1; }
+      }
+    }
+    if (it < UVS_MAX_ITER_LOG) {
+      sm.cost[it] = c.cost; sm.radius[it] = c.radius; sm.relative_decrease[it] = log_rel; sm.step_norm[it] = log_step;
+      sm.gradient_max_norm[it] = accepted ? -1.0 : gprev;   // filled by the next linearisation when accepted
+      sm.step_accepted[it] = accepted;
+    }
+    c.iter = it + 1;
+    if (!done && c.iter - 1 >= P.max_num_iterations) { c.termination = UVS_TERM_NO_CONVERGENCE; done = 1; }
+    if (done) c.state &= ~WS_ACTIVE;
+    for (int e = 0; e < ACC_STRIDE; e++) acc[e] = 0.0;
+  }
+  zero_window_system(D, w);
+}
+
+// final bookkeeping: summaries (device copy), number of active windows
+__global__ void k_finish(Dev D) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= D.B) return;
+  const WinCtl &c = D.ctl[w];
+  UvsSummary &sm = D.summary[w];
+  sm.num_iterations = c.iter;
+  sm.num_successful_steps = c.n_success;
+  sm.termination = c.termination;
+  sm.status = isfinite(c.cost) ? c.status : UVS_ERR_NOT_FINITE;
+  sm.final_cost = c.cost;
+}
+
+__global__ void k_count_active(Dev D, int *out) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= D.B) return;
+  if (D.ctl[w].state & WS_ACTIVE) atomicAdd(out, 1);
+}
+
+// per-window cost at the current iterate for uvs_eval_cost: acc[ACC_CAND_COST] -> out
+__global__ void k_copy_acc(Dev D, int slot, double *out, int zero) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= D.B) return;
+  out[w] = D.acc[(size_t)w * ACC_STRIDE + slot];
+  if (zero) D.acc[(size_t)w * ACC_STRIDE + slot] = 0.0;
+}
+
+int chol_packed_limit(size_t max_smem) {
+  // (d+1)(d+2)/2 + d doubles must fit
+  int d = 0;
+  while (((size_t)(d + 2) * (d + 3) / 2 + (d + 1)) * sizeof(double) <= max_smem) d++;
+  return d;
+}
+
+int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st) { k_solve_init<<<D.B, CT, 0, st>>>(D, P); return 1; }
+
+int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, cudaStream_t st) {
+  const int dd = max_d <= packed_limit ? max_d : packed_limit;
+  const size_t smem = ((size_t)(dd + 1) * (dd + 2) / 2 + dd) * sizeof(double);
+  k_chol<<<D.B, CT, smem, st>>>(D, P, packed_limit);
+  return 1;
+}
+int set_chol_smem(size_t bytes) {
+  return (int)cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int launch_step(const Dev &D, const Params &P, cudaStream_t st) { k_step<<<D.B, CT, 0, st>>>(D, P); return 1; }
+int launch_finish(const Dev &D, cudaStream_t st) { k_finish<<<(D.B + 127) / 128, 128, 0, st>>>(D); return 1; }
+int launch_count_active(const Dev &D, int *out, cudaStream_t st) {
+  cudaMemsetAsync(out, 0, sizeof(int), st);
+  k_count_active<<<(D.B + 127) / 128, 128, 0, st>>>(D, out);
+  return 1;
+}
+int launch_copy_acc(const Dev &D, int slot, double *out, int zero, cudaStream_t st) {
+  k_copy_acc<<<(D.B + 127) / 128, 128, 0, st>>>(D, slot, out, zero);
+  return 1;
+}
+
+}  // namespace uvs

@@ -1,0 +1,397 @@
+// uvs_sweep.cu — the factor sweep: one fused kernel per factor type evaluates every residual of
+// the batch and (Jacobian mode) its tangent-space Jacobian blocks, loss-corrected, into the
+// per-factor record arrays.  sm_100a, FP64.
+//
+// Reference functions replaced (per call, on the CPU, inside ceres::Solve):
+//   ProjectionFactor::Evaluate / ProjectionTdFactor::Evaluate   factor/projection_factor.cpp:22-175,
+//                                                                factor/projection_td_factor.cpp:34-145
+//   AutoDiffCostFunction<LineProjectionFactor,2,7,4>::Evaluate   factor/line_projection_factor.h:16-60
+//   AutoDiffCostFunction<VPProjectionFactor,1,7,4>::Evaluate     factor/vp_projection_factor.h:19-66
+//   IMUFactor::Evaluate                                          factor/imu_factor.h:19-182
+//   MarginalizationFactor::Evaluate                              factor/marginalization_factor.cpp:333-381
+//   Ceres' loss corrector (restated at marginalization_factor.cpp:37-68)
+//
+// Memory behaviour: a thread owns one factor (a warp for IMU factors); index records and
+// observations are read once; state blocks (a few KB per window) come through L1/L2; every CTA
+// stages its tile of records in shared memory and writes it back as one contiguous, fully
+// coalesced chunk.
+#include "uvs_device.cuh"
+#include "uvs_factors.cuh"
+#include "uvs_imu.cuh"
+#include "uvs_kernels.h"
+
+namespace uvs {
+
+constexpr int NT = 128;  // threads per CTA of the per-factor kernels
+
+// does window state `st` want this factor evaluated?
+//   mode 0: API evaluation (everything);  mode 1: solver
+template <bool kJac>
+__device__ __forceinline__ bool wants(int st, int mode) {
+  if (mode == 0) return true;
+  if (!(st & WS_ACTIVE)) return false;
+  return kJac ? (st & WS_NEED_JAC) != 0 : (st & WS_STEP_OK) != 0;
+}
+
+// warp-aggregated accumulation of a per-window scalar
+__device__ __forceinline__ void add_window_scalar(double *arr, int stride_doubles, int win, double v, bool valid) {
+  const unsigned full = 0xffffffffu;
+  const int w0 = __shfl_sync(full, win, 0);
+  const bool uniform = __all_sync(full, !valid || win == w0) && __shfl_sync(full, (int)valid, 0);
+  if (uniform) {
+    double s = valid ? v : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(full, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(arr + (size_t)w0 * stride_doubles, s);
+  } else if (valid) {
+    atomicAdd(arr + (size_t)win * stride_doubles, v);
+  }
+}
+
+// loss: returns sqrt(rho') and the cost 1/2 rho(s); a <= 0 means no loss function
+__device__ __forceinline__ double corrector(double a, double s, double &half_rho) {
+  if (a <= 0.0) { half_rho = 0.5 * s; return 1.0; }
+  double rho0, rho1;
+  cauchy(a, s, rho0, rho1);
+  half_rho = 0.5 * rho0;
+  return sqrt(rho1);
+}
+
+// contiguous, coalesced write-back of a CTA's tile of records staged in shared memory
+template <int REC>
+__device__ __forceinline__ void flush_tile(const double *tile, const unsigned char *ok, double *__restrict__ out,
+                                           int first, int count) {
+  double *dst = out + (size_t)first * REC;
+  const int total = count * REC;
+  for (int e = threadIdx.x; e < total; e += NT) {
+    const int f = e / REC, c = e - f * REC;
+    if (ok[f]) dst[e] = tile[f * (REC + 1) + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool kJac, bool kTd, bool kCeres>
+__global__ void __launch_bounds__(NT) k_proj(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+                                             double *__restrict__ res_out, double *cost, int cost_stride) {
+  constexpr int REC = kCeres ? (kTd ? CREC_PROJ_TD : CREC_PROJ) : (kTd ? REC_PROJ_TD : REC_PROJ);
+  constexpr int PW = kCeres ? 7 : 6;
+  extern __shared__ double smem[];
+  double *tile = smem;
+  unsigned char *ok = reinterpret_cast<unsigned char *>(smem + NT * (REC + 1));
+  const int first = blockIdx.x * NT;
+  const int f = first + threadIdx.x;
+  bool valid = f < D.nProj;
+  int4 ix = make_int4(0, 0, 0, 0);
+  int wflags = 0;
+  if (valid) {
+    ix = D.proj_idx[f];
+    valid = wants<kJac>(D.ctl[ix.w].state, mode) && (D.nranks <= 1 || mode == 0 || (ix.z % D.nranks) == D.rank);
+    wflags = D.win_flags[ix.w];
+  }
+  double half_rho = 0.0;
+  if (valid) {
+    const int buf = D.cur[ix.w] ^ cand;
+    const double *pi = D.pose[buf] + 7 * (size_t)ix.x, *pj = D.pose[buf] + 7 * (size_t)ix.y;
+    const double *ex = D.ex[buf] + 7 * (size_t)ix.w;
+    const double lam = __ldg(D.inv_depth[buf] + ix.z);
+    const double *oi = D.proj_pts_i + 3 * (size_t)f, *oj = D.proj_pts_j + 3 * (size_t)f;
+    const d3 pts_i = mk3(__ldg(oi), __ldg(oi + 1), __ldg(oi + 2)), pts_j = mk3(__ldg(oj), __ldg(oj + 1), __ldg(oj + 2));
+    ProjTd tdp;
+    if (kTd) {
+      tdp.td = __ldg(D.td[buf] + ix.w);
+      tdp.td_i = __ldg(D.proj_td_i + f); tdp.td_j = __ldg(D.proj_td_j + f);
+      tdp.row_i = __ldg(D.proj_row_i + f); tdp.row_j = __ldg(D.proj_row_j + f);
+      tdp.vix = __ldg(D.proj_vel_i + 2 * (size_t)f); tdp.viy = __ldg(D.proj_vel_i + 2 * (size_t)f + 1);
+      tdp.vjx = __ldg(D.proj_vel_j + 2 * (size_t)f); tdp.vjy = __ldg(D.proj_vel_j + 2 * (size_t)f + 1);
+      tdp.tr_over_row = P.tr_over_row; tdp.half_row = P.half_row;
+    }
+    double r[2], Ji[12], Jj[12], Jex[12], Jl[2], Jtd[2];
+    const bool want_ex = mode == 0 || (wflags & WF_EXTRINSIC);
+    proj_eval<kJac, kTd>(pi, pj, ex, lam, pts_i, pts_j, P.S, &tdp, want_ex, r, Ji, Jj, Jex, Jl, Jtd);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    double sq = 1.0;
+    if (kCeres) half_rho = 0.5 * s; else sq = corrector(P.cauchy_point, s, half_rho);
+    r[0] *= sq; r[1] *= sq;
+    if (kJac) {
+      double *t = tile + threadIdx.x * (REC + 1);
+      t[0] = r[0]; t[1] = r[1];
+#pragma unroll
+      for (int row = 0; row < 2; row++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          t[2 + row * PW + c] = sq * Ji[row * 6 + c];
+          t[2 + 2 * PW + row * PW + c] = sq * Jj[row * 6 + c];
+          t[2 + 4 * PW + row * PW + c] = sq * Jex[row * 6 + c];
+        }
+        if (kCeres) { t[2 + row * 7 + 6] = 0.0; t[2 + 14 + row * 7 + 6] = 0.0; t[2 + 28 + row * 7 + 6] = 0.0; }
+      }
+      t[2 + 6 * PW] = sq * Jl[0]; t[2 + 6 * PW + 1] = sq * Jl[1];
+      if (kTd) { t[2 + 6 * PW + 2] = sq * Jtd[0]; t[2 + 6 * PW + 3] = sq * Jtd[1]; }
+    } else if (res_out) {
+      res_out[2 * (size_t)f] = r[0]; res_out[2 * (size_t)f + 1] = r[1];
+    }
+  }
+  if (cost) add_window_scalar(cost, cost_stride, ix.w, half_rho, valid);
+  if (kJac) {
+    ok[threadIdx.x] = valid;
+    __syncthreads();
+    flush_tile<REC>(tile, ok, out, first, min(NT, D.nProj - first));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool kJac, bool kCeres>
+__global__ void __launch_bounds__(NT) k_line(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+                                             double *__restrict__ res_out, double *cost, int cost_stride) {
+  constexpr int REC = kCeres ? CREC_LINE : REC_LINE;
+  constexpr int NP = kCeres ? 11 : 10;
+  constexpr int PW = kCeres ? 7 : 6;
+  extern __shared__ double smem[];
+  double *tile = smem;
+  unsigned char *ok = reinterpret_cast<unsigned char *>(smem + NT * (REC + 1));
+  const int first = blockIdx.x * NT;
+  const int f = first + threadIdx.x;
+  bool valid = f < D.nLobs;
+  int4 ix = make_int4(0, 0, 0, 0);
+  if (valid) {
+    ix = D.line_idx4[f];
+    valid = wants<kJac>(D.ctl[ix.z].state, mode) && (D.nranks <= 1 || mode == 0 || (ix.y % D.nranks) == D.rank);
+  }
+  double half_rho = 0.0;
+  if (valid) {
+    const int buf = D.cur[ix.z] ^ cand;
+    const double *sp = D.line_sp + 2 * (size_t)f, *ep = D.line_ep + 2 * (size_t)f;
+    double r[2], J[2 * NP];
+    line_eval<kJac, kCeres>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
+                            D.tic + 3 * (size_t)ix.z, __ldg(sp), __ldg(sp + 1), __ldg(ep), __ldg(ep + 1), P.line_factor, r, J);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    double sq = 1.0;
+    if (kCeres) half_rho = 0.5 * s; else sq = corrector(P.cauchy_line, s, half_rho);
+    r[0] *= sq; r[1] *= sq;
+    if (kJac) {
+      double *t = tile + threadIdx.x * (REC + 1);
+      t[0] = r[0]; t[1] = r[1];
+#pragma unroll
+      for (int row = 0; row < 2; row++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) t[2 + row * PW + c] = sq * J[row * NP + c];
+        if (kCeres) t[2 + row * 7 + 6] = J[row * NP + 10];
+#pragma unroll
+        for (int c = 0; c < 4; c++) t[2 + 2 * PW + row * 4 + c] = sq * J[row * NP + 6 + c];
+      }
+    } else if (res_out) {
+      res_out[2 * (size_t)f] = r[0]; res_out[2 * (size_t)f + 1] = r[1];
+    }
+  }
+  if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
+  if (kJac) {
+    ok[threadIdx.x] = valid;
+    __syncthreads();
+    flush_tile<REC>(tile, ok, out, first, min(NT, D.nLobs - first));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool kJac, bool kCeres>
+__global__ void __launch_bounds__(NT) k_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+                                           double *__restrict__ res_out, double *cost, int cost_stride) {
+  constexpr int REC = kCeres ? CREC_VP : REC_VP;
+  constexpr int NP = kCeres ? 11 : 10;
+  constexpr int PW = kCeres ? 7 : 6;
+  extern __shared__ double smem[];
+  double *tile = smem;
+  unsigned char *ok = reinterpret_cast<unsigned char *>(smem + NT * (REC + 1));
+  const int first = blockIdx.x * NT;
+  const int f = first + threadIdx.x;
+  bool valid = f < D.nVobs;
+  int4 ix = make_int4(0, 0, 0, 0);
+  if (valid) {
+    ix = D.vp_idx4[f];
+    valid = wants<kJac>(D.ctl[ix.z].state, mode) && (D.nranks <= 1 || mode == 0 || (ix.y % D.nranks) == D.rank);
+  }
+  double half_rho = 0.0;
+  if (valid) {
+    const int buf = D.cur[ix.z] ^ cand;
+    const double *vp = D.vp_dir + 3 * (size_t)f;
+    double r[1], J[NP];
+    vp_eval<kJac, kCeres>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
+                          D.tic + 3 * (size_t)ix.z, mk3(__ldg(vp), __ldg(vp + 1), __ldg(vp + 2)), P.vp_factor, r, J);
+    const double s = r[0] * r[0];
+    double sq = 1.0;
+    if (kCeres) half_rho = 0.5 * s; else sq = corrector(P.cauchy_vp, s, half_rho);
+    r[0] *= sq;
+    if (kJac) {
+      double *t = tile + threadIdx.x * (REC + 1);
+      t[0] = r[0];
+#pragma unroll
+      for (int c = 0; c < 6; c++) t[1 + c] = sq * J[c];
+      if (kCeres) t[1 + 6] = J[10];
+#pragma unroll
+      for (int c = 0; c < 4; c++) t[1 + PW + c] = sq * J[6 + c];
+    } else if (res_out) {
+      res_out[f] = r[0];
+    }
+  }
+  if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
+  if (kJac) {
+    ok[threadIdx.x] = valid;
+    __syncthreads();
+    flush_tile<REC>(tile, ok, out, first, min(NT, D.nVobs - first));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// IMU: one warp per factor, 4 warps per CTA.  Record = [r(15) | sqrt_info * J (15x30 row-major)].
+template <bool kJac>
+__global__ void __launch_bounds__(NT) k_imu(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+                                            double *__restrict__ res_out, double *cost, int cost_stride) {
+  __shared__ double Jraw_all[NT / 32][450];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (NT / 32) + warp;
+  if (f >= D.nImu) return;
+  const int2 ix = D.imu_idx[f];
+  if (!wants<kJac>(D.ctl[ix.y].state, mode)) return;
+  if (D.nranks > 1 && mode != 0 && D.rank != 0) return;
+  const int buf = D.cur[ix.y] ^ cand;
+  ImuIn in;
+  in.pose_i = D.pose[buf] + 7 * (size_t)ix.x; in.pose_j = in.pose_i + 7;
+  in.sb_i = D.sb[buf] + 9 * (size_t)ix.x; in.sb_j = in.sb_i + 9;
+  in.dp = D.imu_dp + 3 * (size_t)f; in.dq = D.imu_dq + 4 * (size_t)f; in.dv = D.imu_dv + 3 * (size_t)f;
+  in.lin_ba = D.imu_lin_ba + 3 * (size_t)f; in.lin_bg = D.imu_lin_bg + 3 * (size_t)f;
+  in.sum_dt = __ldg(D.imu_sum_dt + f);
+  in.jac = D.imu_jac + 225 * (size_t)f;
+  in.sqrt_info = D.imu_sqrt_info + 225 * (size_t)f;
+  double *Jraw = Jraw_all[warp];
+  const double res = imu_eval_warp<kJac>(in, P.g, lane, Jraw);
+  double s = res * res;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0 && cost) atomicAdd(cost + (size_t)ix.y * cost_stride, 0.5 * s);
+  if (kJac) {
+    double *rec = out + (size_t)f * REC_IMU;
+    if (lane < 15) rec[lane] = res;
+    const double *SI = in.sqrt_info;
+    for (int e = lane; e < 450; e += 32) {
+      const int i = e / 30, c = e - i * 30;
+      double acc = 0.0;
+      for (int k = i; k < 15; k++) acc += __ldg(SI + i * 15 + k) * Jraw[k * 30 + c];
+      rec[15 + e] = acc;
+    }
+  } else if (res_out && lane < 15) {
+    res_out[15 * (size_t)f + lane] = res;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prior residual r = r0 + J0 dx (its Jacobian is J0 itself).  One CTA per window, a warp per row.
+__global__ void __launch_bounds__(NT) k_prior(Dev D, int jac_phase, int mode, int cand, double *__restrict__ res_out,
+                                              double *cost, int cost_stride) {
+  extern __shared__ double dx[];
+  const int w = blockIdx.x;
+  const int n = D.prior_off[w + 1] - D.prior_off[w];
+  if (n <= 0) return;
+  if (jac_phase ? !wants<true>(D.ctl[w].state, mode) : !wants<false>(D.ctl[w].state, mode)) return;
+  if (D.nranks > 1 && D.rank != 0) return;
+  const int buf = D.cur[w] ^ cand;
+  const int b0 = D.pblk_off[w], b1 = D.pblk_off[w + 1];
+  for (int b = b0 + threadIdx.x; b < b1; b += NT) {
+    const int kind = D.pblk_kind[b], row = D.pblk_row[b], col = D.pblk_col[b];
+    const double *x0 = D.prior_x0 + 9 * (size_t)b;
+    if (kind == 0 || kind == 2) {   // pose / ex-pose: [dp ; 2 vec(q0^-1 q)] with sign fix
+      const double *x = (kind == 0 ? D.pose[buf] : D.ex[buf]) + 7 * (size_t)row;
+      for (int k = 0; k < 3; k++) dx[col + k] = x[k] - x0[k];
+      const q4 dq = qmul(qinv(mkq(x0[3], x0[4], x0[5], x0[6])), mkq(x[3], x[4], x[5], x[6]));
+      const double sgn = (dq.w >= 0.0) ? 2.0 : -2.0;
+      dx[col + 3] = sgn * dq.x; dx[col + 4] = sgn * dq.y; dx[col + 5] = sgn * dq.z;
+    } else if (kind == 1) {
+      const double *x = D.sb[buf] + 9 * (size_t)row;
+      for (int k = 0; k < 9; k++) dx[col + k] = x[k] - x0[k];
+    } else {
+      dx[col] = D.td[buf][row] - x0[0];
+    }
+  }
+  __syncthreads();
+  const double *J0 = D.prior_J + D.priorJ_off[w];
+  const double *r0 = D.prior_r0 + D.prior_off[w];
+  double *rout = res_out + D.prior_off[w];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double csum = 0.0;
+  for (int i = warp; i < n; i += NT / 32) {
+    double acc = 0.0;
+    for (int k = lane; k < n; k += 32) acc += __ldg(J0 + (size_t)i * n + k) * dx[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const double r = __ldg(r0 + i) + acc;
+      rout[i] = r;
+      csum += r * r;
+    }
+  }
+  if (lane == 0 && cost) atomicAdd(cost + (size_t)w * cost_stride, 0.5 * csum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+template <int REC>
+static size_t tile_bytes() { return (size_t)NT * (REC + 1) * sizeof(double) + NT; }
+
+#define PICK_PROJ(JAC, TD, CE) k_proj<JAC, TD, CE>
+int launch_proj(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
+                double *cost, int cost_stride, cudaStream_t st) {
+  if (D.nProj == 0) return 0;
+  const int grid = cdiv(D.nProj, NT);
+  const bool td = D.estimate_td != 0;
+  if (!jac) {
+    if (td) k_proj<false, true, false><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+    else k_proj<false, false, false><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+    return 1;
+  }
+  if (ceres) {
+    if (td) k_proj<true, true, true><<<grid, NT, tile_bytes<CREC_PROJ_TD>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+    else k_proj<true, false, true><<<grid, NT, tile_bytes<CREC_PROJ>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  } else {
+    if (td) k_proj<true, true, false><<<grid, NT, tile_bytes<REC_PROJ_TD>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+    else k_proj<true, false, false><<<grid, NT, tile_bytes<REC_PROJ>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  }
+  return 1;
+}
+
+int launch_line(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
+                double *cost, int cost_stride, cudaStream_t st) {
+  if (D.nLobs == 0) return 0;
+  const int grid = cdiv(D.nLobs, NT);
+  if (!jac) k_line<false, false><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  else if (ceres) k_line<true, true><<<grid, NT, tile_bytes<CREC_LINE>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  else k_line<true, false><<<grid, NT, tile_bytes<REC_LINE>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  return 1;
+}
+
+int launch_vp(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
+              double *cost, int cost_stride, cudaStream_t st) {
+  if (D.nVobs == 0) return 0;
+  const int grid = cdiv(D.nVobs, NT);
+  if (!jac) k_vp<false, false><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  else if (ceres) k_vp<true, true><<<grid, NT, tile_bytes<CREC_VP>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  else k_vp<true, false><<<grid, NT, tile_bytes<REC_VP>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  return 1;
+}
+
+int launch_imu(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out, double *res_out, double *cost,
+               int cost_stride, cudaStream_t st) {
+  if (D.nImu == 0) return 0;
+  const int grid = cdiv(D.nImu, NT / 32);
+  if (jac) k_imu<true><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  else k_imu<false><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  return 1;
+}
+
+int launch_prior(const Dev &D, int max_prior_n, bool jac_phase, int mode, int cand, double *res_out, double *cost,
+                 int cost_stride, cudaStream_t st) {
+  if (D.nPriorR == 0) return 0;
+  k_prior<<<D.B, NT, (size_t)max_prior_n * sizeof(double), st>>>(D, jac_phase ? 1 : 0, mode, cand, res_out, cost, cost_stride);
+  return 1;
+}
+
+}  // namespace uvs
