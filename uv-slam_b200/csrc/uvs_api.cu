@@ -538,7 +538,8 @@ static int launch_resid_sweep(UvsHandle *h, int mode, int cand, int slot) {
   h->launches += launch_line(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
   h->launches += launch_vp(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
   h->launches += launch_imu(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_prior(D, h->max_prior_n, false, mode, cand, D.rec_prior, cost, ACC_STRIDE, st);
+  // residual-only: the prior residual of the CURRENT iterate (rec_prior) must survive a rejected step
+  h->launches += launch_prior(D, h->max_prior_n, false, mode, cand, nullptr, cost, ACC_STRIDE, st);
   return post_launch(h, "residual sweep");
 }
 

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(NT) k_prior(Dev D, int jac_phase, int mode, in
   __syncthreads();
   const double *J0 = D.prior_J + D.priorJ_off[w];
   const double *r0 = D.prior_r0 + D.prior_off[w];
-  double *rout = res_out + D.prior_off[w];
+  double *rout = res_out ? res_out + D.prior_off[w] : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double csum = 0.0;
   for (int i = warp; i < n; i += NT / 32) {
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(NT) k_prior(Dev D, int jac_phase, int mode, in
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if (lane == 0) {
       const double r = __ldg(r0 + i) + acc;
-      rout[i] = r;
+      if (rout) rout[i] = r;
       csum += r * r;
     }
   }
@@ -337,10 +337,21 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 template <int REC>
 static size_t tile_bytes() { return (size_t)NT * (REC + 1) * sizeof(double) + NT; }
 
-#define PICK_PROJ(JAC, TD, CE) k_proj<JAC, TD, CE>
+// tiles of the widest records exceed the 48 KB default of dynamic shared memory
+static void raise_smem_limits() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncSetAttribute(k_proj<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<CREC_PROJ_TD>());
+  cudaFuncSetAttribute(k_proj<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<CREC_PROJ>());
+  cudaFuncSetAttribute(k_proj<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<REC_PROJ_TD>());
+  cudaFuncSetAttribute(k_proj<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<REC_PROJ>());
+}
+
 int launch_proj(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
                 double *cost, int cost_stride, cudaStream_t st) {
   if (D.nProj == 0) return 0;
+  raise_smem_limits();
   const int grid = cdiv(D.nProj, NT);
   const bool td = D.estimate_td != 0;
   if (!jac) {
