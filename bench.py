@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — solver iterations/sec of the sliding-window backend solve (BASELINE.json's metric).
+
+One "step" = one pass of the hot path over one batch: uvs_solve on B independent 11-frame / 200-point /
+80-line / 3-VP windows ("C2", BASELINE.json configs[1]/[2]) per GPU, K_LM = 10 Levenberg-Marquardt
+iterations each (config/euroc/euroc_config.yaml:56), convergence exits disabled so that every step
+does exactly B x 10 iterations.  value = LM iterations per second over all windows and GPUs.
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [...]                   the CPU path on the host cores
+The reference (ROS + Ceres + Eigen) cannot be built in this image, so the reference arm times the
+Ceres-semantics CPU restatement in oracle/ (cpu_baseline.kind = "port"), all host threads.
+"""
+import argparse
+import ctypes as C
+import glob
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+K_LM = 10
+METRIC = "solver iterations/sec (10-KF window)"
+UNIT = "LM iterations/s"
+
+
+def load_workload(n_windows, rank=0):
+    """B windows: the committed C2 fixtures, replicated with a seeded perturbation of the initial
+    guess so that every window is a different problem."""
+    from uvs_b200 import Window
+    paths = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "window_C2_s*.uvsw")))
+    if not paths:
+        raise SystemExit("fixtures missing: run python tools/make_fixtures.py")
+    base = [Window.load(p) for p in paths]
+    rng = np.random.default_rng(77 + 1000 * rank)
+    out = []
+    for i in range(n_windows):
+        w = base[i % len(base)].copy()
+        if i >= len(base):
+            w.pose[:, :3] += rng.normal(0, 0.01, w.pose[:, :3].shape)
+            dq = rng.normal(0, 0.002, (w.n_frames, 3))
+            q = w.pose[:, 3:]
+            # q <- q * (dq/2, 1), normalised
+            x, y, z, s = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+            a, b, c = dq[:, 0] / 2, dq[:, 1] / 2, dq[:, 2] / 2
+            qn = np.stack([s * a + x + y * c - z * b, s * b + y + z * a - x * c, s * c + z + x * b - y * a,
+                           s - x * a - y * b - z * c], axis=1)
+            w.pose[:, 3:] = qn / np.linalg.norm(qn, axis=1, keepdims=True)
+            w.speed_bias[:, :3] += rng.normal(0, 0.01, (w.n_frames, 3))
+            w.inv_depth *= 1.0 + rng.normal(0, 0.02, w.n_points)
+            w.ortho += rng.normal(0, 0.005, w.ortho.shape)
+        out.append(w)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    def __init__(self, gpu=0):
+        self.rows, self.proc, self.gpu = [], None, gpu
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, n in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def run_cpu_sample(n_windows, threads, budget_s, k_lm=K_LM):
+    """times the CPU oracle (test infrastructure) on a bounded sample of the same workload"""
+    import uvs_b200
+    from tests import orc
+    ws = load_workload(n_windows)
+    o = uvs_b200.default_options(max_num_iterations=k_lm, fixed_iterations=1)
+    t0 = time.perf_counter()
+    orc.solve_batch([w.copy() for w in ws[:max(1, threads)]], o, threads)   # warm-up
+    warm = time.perf_counter() - t0
+    reps = max(1, int(budget_s / max(warm * n_windows / max(1, threads), 1e-3)))
+    reps = min(reps, 50)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.solve_batch([w.copy() for w in ws], o, threads)
+    dt = time.perf_counter() - t0
+    return n_windows * k_lm * reps / dt, reps, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = max(threads * 2, 16)
+    # each "step" = one bounded sample: n windows x 10 LM iterations on all host threads
+    import uvs_b200
+    from tests import orc
+    ws = load_workload(n)
+    o = uvs_b200.default_options(max_num_iterations=K_LM, fixed_iterations=1)
+    for _ in range(args.warmup):
+        orc.solve_batch([w.copy() for w in ws], o, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.solve_batch([w.copy() for w in ws], o, threads)
+    dt = time.perf_counter() - t0
+    value = n * K_LM * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 window (11 frames / 200 points / 80 lines / 3 VP), %d LM iterations per window" % K_LM,
+                   "windows_per_step": n, "note": "reference = CPU restatement of the Ceres path (oracle/); Ceres itself cannot be built here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d C2 windows x %d LM iterations per step, %d host threads (window-parallel)" % (n, K_LM, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--windows", type=int, default=1024, help="windows per GPU and step")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import uvs_b200
+    rank, world, local, dist = dist_setup(args.gpus)
+    B = args.windows
+    ws = load_workload(B, rank)
+    opts = uvs_b200.default_options(max_num_iterations=K_LM, fixed_iterations=1)
+    s = uvs_b200.Solver(local)
+    s.upload(ws, opts)
+    jac_bytes, res_bytes = s.sweep_bytes()
+    s.set_profiling(1)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing: inputs already in HBM, state rewound on the device between steps
+    for _ in range(max(3, args.warmup)):
+        s.reset_state(); s.solve()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = s.launch_count()
+    dev_ms, stage_tot, iters_tot = 0.0, {}, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.reset_state()
+        s.solve()
+        dev_ms += s.last_solve_ms()
+        st, n_it = s.last_stage_ms()
+        iters_tot += n_it
+        for k, v in st.items():
+            stage_tot[k] = stage_tot.get(k, 0.0) + v
+    wall = time.perf_counter() - t0
+    barrier()
+    launches = s.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = dev_ms / args.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    value = world * B * K_LM / (step_ms * 1e-3)
+
+    # ---- end to end through the reference-facing call: host buffers, H2D + solve + D2H per step
+    host_sets = [[w.copy() for w in ws] for _ in range(2)]
+    for k in range(2):
+        s.batch_solve(host_sets[k % 2], opts)
+    n_e2e = max(2, min(args.steps, 5))
+    fresh_sets = [[w.copy() for w in ws] for _ in range(n_e2e)]   # host copies made outside the timer
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        s.batch_solve(fresh_sets[k], opts)
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * K_LM / e2e_s
+    h2d = sum(len(w.to_bytes()) for w in ws[:4]) // 4 * B
+    d2h = sum(w.state_vector().nbytes for w in ws) + B * C.sizeof(uvs_b200.UvsSummaryStruct)
+
+    # ---- single-window latency (the reference's own use: one window per frame)
+    s1 = uvs_b200.Solver(local)
+    s1.upload([ws[0]], opts)
+    for _ in range(5):
+        s1.reset_state(); s1.solve()
+    lat = []
+    for _ in range(20):
+        s1.reset_state(); s1.solve(); lat.append(s1.last_solve_ms())
+    lat_ms = float(np.median(lat))
+    s1.close()
+
+    if rank != 0:
+        return
+    # ---- roofline of the Jacobian sweep (SURVEY.md 8d bytes) against the measured HBM peak
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (of fallback)"
+    sweep_ms = sum(stage_tot[k] for k in ("sweep_proj", "sweep_line", "sweep_vp", "sweep_imu", "sweep_prior")) / max(1, iters_tot)
+    achieved = jac_bytes / (sweep_ms * 1e-3) / 1e9
+    total_stage = sum(stage_tot.values())
+    shares = {k: round(v / total_stage, 4) for k, v in stage_tot.items()}
+    nproj, nline, nvp = sum(w.n_proj for w in ws), sum(w.n_line_obs for w in ws), sum(w.n_vp_obs for w in ws)
+    per_kernel = {}
+    for k, nb in (("sweep_proj", 384 * nproj), ("sweep_line", 232 * nline), ("sweep_vp", 120 * nvp), ("sweep_imu", 6024 * 10 * B)):
+        ms = stage_tot[k] / max(1, iters_tot)
+        per_kernel[k] = {"ms": round(ms, 4), "GB/s": round(nb / (ms * 1e-3) / 1e9, 1), "frac": round(nb / (ms * 1e-3) / 1e9 / peak, 4)}
+
+    cpu = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, reps, dt = run_cpu_sample(max(2 * threads, 16), threads, args.cpu_budget)
+        v1, reps1, dt1 = run_cpu_sample(4, 1, min(4.0, args.cpu_budget / 3))
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d C2 windows x %d LM iterations x %d repetitions in %.1f s, %d host threads (window-parallel oracle)" % (
+                   max(2 * threads, 16), K_LM, reps, dt, threads),
+               "single_thread_value": v1}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2 window (11 frames / 200 points / 80 lines / 3 VP; BASELINE.json configs[1-2]) x %d independent "
+                               "windows per GPU, %d LM iterations per window per step" % (B, K_LM),
+                   "windows_per_gpu": B, "lm_iterations": K_LM, "parallelism": "window-parallel x%d (no data-path collective)" % world,
+                   "l2": "inputs larger than L2: %.0f MB of factor records per sweep" % (jac_bytes / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "Jacobian sweep (k_proj + k_line + k_vp + k_imu + k_prior, Jacobian mode)", "bytes_per_launch": int(jac_bytes),
+                     "ms_per_launch": sweep_ms, "peak_source": peak_src, "per_kernel": per_kernel},
+        "cpu_baseline": cpu,
+        "stage_share": shares,
+        "latency": {"single_window_ms_per_solve": lat_ms, "single_window_iterations_per_s": K_LM / (lat_ms * 1e-3)},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

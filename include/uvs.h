@@ -258,6 +258,19 @@ int uvs_last_solve_ms(const UvsHandle *h, float *ms);
 /* Device time [ms] of the Jacobian-sweep kernels accumulated over the last uvs_solve. */
 int uvs_last_sweep_ms(const UvsHandle *h, float *ms, int32_t *n_sweeps);
 
+/* Put every window back to the state it was uploaded with (device-to-device; no host traffic), so
+ * that the same batch can be solved again - used to time solves with the inputs resident in HBM. */
+int uvs_reset_state(UvsHandle *h);
+
+/* Stage timing with CUDA events on the handle's stream.  level 0: whole solve only; level 1: one
+ * event per pipeline stage and LM iteration, read back (no extra synchronisation) when the solve ends. */
+#define UVS_N_STAGES 10
+/* stage order: sweep_proj, sweep_line, sweep_vp, sweep_imu, sweep_prior, build, chol, backsub,
+ * resid_sweep, step */
+int uvs_set_profiling(UvsHandle *h, int32_t level);
+/* accumulated device time [ms] of every stage over the last uvs_solve and the number of iterations run */
+int uvs_last_stage_ms(const UvsHandle *h, float ms[UVS_N_STAGES], int32_t *n_iterations);
+
 /* Factor-parallel multi-GPU mode: this rank owns the landmarks with (index % nranks == rank);
  * IMU factors and the prior belong to rank 0.  `reduce` is called once per LM iteration with the
  * device buffer holding the rank's partial reduced camera system (count doubles) and must sum it

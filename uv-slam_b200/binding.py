@@ -20,9 +20,13 @@ EXPORTS = (
     "uvs_abi_version", "uvs_default_options", "uvs_status_string", "uvs_create", "uvs_destroy", "uvs_last_error",
     "uvs_upload_windows", "uvs_download_state", "uvs_eval_proj", "uvs_eval_line", "uvs_eval_vp", "uvs_eval_imu",
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
-    "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init",
+    "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
+    "uvs_set_profiling", "uvs_last_stage_ms",
 )
 
+N_STAGES = 10
+STAGE_NAMES = ("sweep_proj", "sweep_line", "sweep_vp", "sweep_imu", "sweep_prior", "build", "chol", "backsub",
+               "resid_sweep", "step")
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
@@ -70,6 +74,9 @@ def load_library():
     lib.uvs_last_solve_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.uvs_last_sweep_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.uvs_comm_init.argtypes = [H, C.c_int32, C.c_int32, ALLREDUCE_FN, C.c_void_p]
+    lib.uvs_reset_state.argtypes = [H]
+    lib.uvs_set_profiling.argtypes = [H, C.c_int32]
+    lib.uvs_last_stage_ms.argtypes = [H, C.POINTER(C.c_float * N_STAGES), C.POINTER(C.c_int32)]
     _lib = lib
     return lib
 
@@ -217,6 +224,18 @@ class Solver:
         ms, n = C.c_float(), C.c_int32()
         self._check(self.lib.uvs_last_sweep_ms(self.h, C.byref(ms), C.byref(n)), "uvs_last_sweep_ms")
         return ms.value, n.value
+
+    def reset_state(self):
+        self._check(self.lib.uvs_reset_state(self.h), "uvs_reset_state")
+
+    def set_profiling(self, level: int):
+        self._check(self.lib.uvs_set_profiling(self.h, level), "uvs_set_profiling")
+
+    def last_stage_ms(self):
+        """-> ({stage: ms accumulated over the last solve}, iterations run)"""
+        ms, n = (C.c_float * N_STAGES)(), C.c_int32()
+        self._check(self.lib.uvs_last_stage_ms(self.h, C.byref(ms), C.byref(n)), "uvs_last_stage_ms")
+        return {k: ms[i] for i, k in enumerate(STAGE_NAMES)}, n.value
 
     def comm_init(self, rank, nranks, reduce_fn):
         """reduce_fn(device_ptr:int, count:int, stream:int) -> int, summing in place over ranks."""

@@ -136,6 +136,7 @@ int uvs_destroy(UvsHandle *h) {
   if (h->d_active) cudaFree(h->d_active);
   if (h->h_active) cudaFreeHost(h->h_active);
   cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b); cudaEventDestroy(h->ev_c); cudaEventDestroy(h->ev_d);
+  for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
   delete h;
   return UVS_OK;
@@ -150,7 +151,8 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   fill_params(h->opts, h->P);
   h->have_window = false;
   const int td = w[0].estimate_td ? 1 : 0;
-  int max_d = 0, max_prior_n = 0;
+  int max_d = 0, max_prior_n = 0, max_frames = 0;
+  bool any_ex = false;
   for (int i = 0; i < B; i++) {
     const UvsWindow &x = w[i];
     if (x.n_frames < 1 || x.n_points < 0 || x.n_lines < 0 || x.n_proj < 0 || x.n_line_obs < 0 || x.n_vp_obs < 0 ||
@@ -174,9 +176,25 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
     if (x.n_frames > 32) return fail(h, UVS_ERR_CAPACITY, "more than 32 frames per window (a landmark's factors must fit one warp)");
     const int d = 15 * x.n_frames + (x.estimate_extrinsic ? 6 : 0) + (td ? 1 : 0);
     max_d = std::max(max_d, d);
+    max_frames = std::max(max_frames, (int)x.n_frames);
+    any_ex = any_ex || x.estimate_extrinsic;
     max_prior_n = std::max(max_prior_n, (int)x.prior_n);
   }
   h->B = B; h->max_d = max_d; h->max_prior_n = max_prior_n;
+  h->max_frames = max_frames; h->any_ex = any_ex;
+  // landmark path: shared-memory private accumulation when the pose-pose system is small enough
+  h->use_build2 = !td && (max_frames + (any_ex ? 1 : 0)) <= 12 && max_frames >= 2;
+  if (h->use_build2) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    int NW = 8;
+    while (NW > 1 && build2_smem_bytes(max_frames, any_ex, NW, false) > prop.sharedMemPerBlockOptin - 1024) NW--;
+    if (build2_smem_bytes(max_frames, any_ex, NW, false) > prop.sharedMemPerBlockOptin - 1024) h->use_build2 = false;
+    h->b2_NW = NW;
+    const int sms = prop.multiProcessorCount;
+    h->b2_G = std::max(1, std::min(16, (2 * sms + B - 1) / B));
+    if (B >= sms) h->b2_G = 1;
+  }
   prefix<int>(h->frame_off, B, w, [](const UvsWindow &x) { return (int)x.n_frames; });
   prefix<int>(h->point_off, B, w, [](const UvsWindow &x) { return (int)x.n_points; });
   prefix<int>(h->line_off, B, w, [](const UvsWindow &x) { return (int)x.n_lines; });
@@ -230,6 +248,7 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   wk.total = in.total;
   const size_t w_pose = wk.take(nF * 7 * Dd), w_sb = wk.take(nF * 9 * Dd), w_ex = wk.take(B * 7 * Dd), w_td = wk.take(B * Dd),
                w_inv = wk.take(nP * Dd), w_ortho = wk.take(nL * 4 * Dd);
+  const size_t w_pristine = wk.take(o_state_end - o_pose);
   const size_t w_cur = wk.take(B * I), w_ctl = wk.take(B * sizeof(WinCtl)), w_acc = wk.take((size_t)B * ACC_STRIDE * Dd),
                w_sum = wk.take((size_t)B * sizeof(UvsSummary));
   const size_t w_pidx = wk.take(nProj * sizeof(int4)), w_lidx = wk.take(nLobs * sizeof(int4)), w_vidx = wk.take(nVobs * sizeof(int4)),
@@ -318,6 +337,7 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   CK(cudaMemsetAsync(Dv + w_err, 0, ALIGN, h->stream));
   CK(cudaMemsetAsync(Dv + w_scc, 0, wk.total - w_scc, h->stream));        // scales, system, deltas
   CK(cudaMemcpyAsync(Dv + w_pose, Dv + o_pose, o_state_end - o_pose, cudaMemcpyDeviceToDevice, h->stream));  // candidate buffer = copy
+  CK(cudaMemcpyAsync(Dv + w_pristine, Dv + o_pose, o_state_end - o_pose, cudaMemcpyDeviceToDevice, h->stream));
 
   Dev &D = h->D;
   std::memset(&D, 0, sizeof(D));
@@ -356,6 +376,7 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
 #undef WD
 #undef WI
   h->o_pose0 = o_pose; h->o_state_bytes = o_state_end - o_pose;
+  h->o_pristine = w_pristine; h->o_cur = w_cur; h->cur_bytes = B * I;
   h->o_reduce = w_S; h->reduce_doubles = (w_reduce_end - w_S) / Dd;
 
   h->launches += launch_prep(D, h->stream);
@@ -580,34 +601,49 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
   const auto t0 = std::chrono::steady_clock::now();
   CK(cudaEventRecord(h->ev_a, st));
   h->launches += launch_solve_init(D, P, st);
-  float sweep_ms = 0.f; int n_sweeps = 0;
-  const bool time_sweeps = true;
+  const bool prof = h->profiling > 0;
+  const int NE = UVS_N_STAGES + 1;
+  if (prof) {
+    const size_t need = (size_t)NE * h->opts.max_num_iterations;
+    while (h->stage_ev.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->stage_ev.push_back(e); }
+  }
   const bool check_exit = !h->opts.fixed_iterations;
-  int rc = UVS_OK;
+  int rc = UVS_OK, iters_run = 0;
+  double *cost0 = D.acc + ACC_COST0, *costc = D.acc + ACC_CAND_COST;
+#define STAGE(k) do { if (prof) CK(cudaEventRecord(h->stage_ev[(size_t)it * NE + (k)], st)); } while (0)
   for (int it = 0; it < h->opts.max_num_iterations; it++) {
-    if (time_sweeps) CK(cudaEventRecord(h->ev_c, st));
-    rc = launch_jac_sweep(h, 1); if (rc) return rc;
-    if (time_sweeps) CK(cudaEventRecord(h->ev_d, st));
-    h->launches += launch_build(D, P, h->max_prior_n, st);
+    STAGE(0);
+    h->launches += launch_proj(D, P, true, false, 1, 0, D.rec_proj, nullptr, cost0, ACC_STRIDE, st); STAGE(1);
+    h->launches += launch_line(D, P, true, false, 1, 0, D.rec_line, nullptr, cost0, ACC_STRIDE, st); STAGE(2);
+    h->launches += launch_vp(D, P, true, false, 1, 0, D.rec_vp, nullptr, cost0, ACC_STRIDE, st); STAGE(3);
+    h->launches += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, st); STAGE(4);
+    h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, st); STAGE(5);
+    rc = post_launch(h, "Jacobian sweep"); if (rc) return rc;
+    if (h->use_build2) {
+      h->launches += launch_build2(D, P, h->b2_G, h->b2_NW, h->max_frames, h->any_ex, false, st);
+      h->launches += launch_build_cam(D, h->max_prior_n, st);
+    } else {
+      h->launches += launch_build(D, P, h->max_prior_n, st);
+    }
     rc = post_launch(h, "build"); if (rc) return rc;
     if (h->nranks > 1) {
       rc = all_reduce(h, (double *)(h->dev.base + h->o_reduce), h->reduce_doubles); if (rc) return rc;
       rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc;
     }
-    h->launches += launch_chol(D, P, h->max_d, h->packed_limit, st);
+    STAGE(6);
+    h->launches += launch_chol(D, P, h->max_d, h->packed_limit, st); STAGE(7);
     rc = post_launch(h, "chol"); if (rc) return rc;
-    h->launches += launch_backsub(D, P, st);
+    if (h->use_build2) h->launches += launch_build2(D, P, h->b2_G, h->b2_NW, h->max_frames, h->any_ex, true, st);
+    else h->launches += launch_backsub(D, P, st);
+    STAGE(8);
     rc = post_launch(h, "backsub"); if (rc) return rc;
     rc = launch_resid_sweep(h, 1, 1, ACC_CAND_COST); if (rc) return rc;
+    (void)costc;
     if (h->nranks > 1) { rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc; }
-    h->launches += launch_step(D, P, st);
+    STAGE(9);
+    h->launches += launch_step(D, P, st); STAGE(10);
     rc = post_launch(h, "step"); if (rc) return rc;
-    if (time_sweeps) {
-      // the events are on this stream; reading them needs the iteration to have finished
-      CK(cudaEventSynchronize(h->ev_d));
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, h->ev_c, h->ev_d) == cudaSuccess) { sweep_ms += ms; n_sweeps++; }
-    }
+    iters_run++;
     if (check_exit || h->opts.max_solver_time > 0.0) {
       h->launches += launch_count_active(D, h->d_active, st);
       CK(cudaMemcpyAsync(h->h_active, h->d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -619,12 +655,22 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
       }
     }
   }
+#undef STAGE
   h->launches += launch_finish(D, st);
   CK(cudaEventRecord(h->ev_b, st));
   if (summaries) CK(cudaMemcpyAsync(summaries, D.summary, (size_t)D.B * sizeof(UvsSummary), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   cudaEventElapsedTime(&h->last_solve_ms, h->ev_a, h->ev_b);
-  h->last_sweep_ms = sweep_ms; h->n_sweeps = n_sweeps;
+  for (int k = 0; k < UVS_N_STAGES; k++) h->stage_ms[k] = 0.f;
+  h->stage_iters = prof ? iters_run : 0;
+  if (prof)
+    for (int it = 0; it < iters_run; it++)
+      for (int k = 0; k < UVS_N_STAGES; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->stage_ev[(size_t)it * NE + k], h->stage_ev[(size_t)it * NE + k + 1]) == cudaSuccess) h->stage_ms[k] += ms;
+      }
+  h->last_sweep_ms = h->stage_ms[0] + h->stage_ms[1] + h->stage_ms[2] + h->stage_ms[3] + h->stage_ms[4];
+  h->n_sweeps = h->stage_iters;
   if (summaries && h->opts.max_solver_time > 0.0 && !h->opts.fixed_iterations) {
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (el >= h->opts.max_solver_time)
@@ -655,6 +701,29 @@ int uvs_sweep_bytes(UvsHandle *h, int64_t *jac, int64_t *res) {
   const long long state = 8LL * (16LL * D.nF + 8LL * D.B + D.nP + 4LL * D.nL);
   if (jac) *jac = 384LL * D.nProj + 232LL * D.nLobs + 120LL * D.nVobs + 6024LL * D.nImu + pr + state;
   if (res) *res = 80LL * D.nProj + 72LL * D.nLobs + 40LL * D.nVobs + 2424LL * D.nImu + pr + state;
+  return UVS_OK;
+}
+
+int uvs_reset_state(UvsHandle *h) {
+  if (!h) return UVS_ERR_INVALID_ARG;
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_reset_state: no window uploaded");
+  CK(cudaSetDevice(h->device));
+  char *Dv = h->dev.base;
+  CK(cudaMemcpyAsync(Dv + h->o_pose0, Dv + h->o_pristine, h->o_state_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemsetAsync(Dv + h->o_cur, 0, h->cur_bytes, h->stream));
+  return UVS_OK;
+}
+
+int uvs_set_profiling(UvsHandle *h, int32_t level) {
+  if (!h) return UVS_ERR_INVALID_ARG;
+  h->profiling = level;
+  return UVS_OK;
+}
+
+int uvs_last_stage_ms(const UvsHandle *h, float ms[UVS_N_STAGES], int32_t *n_iterations) {
+  if (!h || !ms) return UVS_ERR_INVALID_ARG;
+  for (int k = 0; k < UVS_N_STAGES; k++) ms[k] = h->stage_ms[k];
+  if (n_iterations) *n_iterations = h->stage_iters;
   return UVS_OK;
 }
 

@@ -604,6 +604,14 @@ int launch_build(const Dev &D, const Params &P, int max_prior_n, cudaStream_t st
   return n;
 }
 
+// camera-only factors (IMU, prior) of the normal equations
+int launch_build_cam(const Dev &D, int max_prior_n, cudaStream_t st) {
+  int n = 0;
+  if (D.nImu) { k_build_imu<<<cdiv(D.nImu, 4), 128, 0, st>>>(D); n++; }
+  if (D.nPriorR) { k_build_prior<<<D.B, 256, (size_t)max_prior_n * sizeof(int), st>>>(D); n++; }
+  return n;
+}
+
 int launch_backsub(const Dev &D, const Params &P, cudaStream_t st) {
   int n = 0;
   if (D.nP) { k_points<true><<<cdiv(D.nP, 4), 128, 0, st>>>(D, P); n++; }

@@ -68,6 +68,14 @@ struct UvsHandle {
   void *reduce_user = nullptr;
   int *d_active = nullptr;
   int *h_active = nullptr;
+  size_t o_pristine = 0;                      // pristine copy of the uploaded state (uvs_reset_state)
+  size_t o_cur = 0, cur_bytes = 0;
+  int profiling = 0;
+  int max_frames = 0; bool any_ex = false;
+  bool use_build2 = false; int b2_G = 1, b2_NW = 8;   // atomics-free landmark path (uvs_build2.cu)
+  std::vector<cudaEvent_t> stage_ev;          // (UVS_N_STAGES + 1) events per LM iteration
+  float stage_ms[UVS_N_STAGES] = {0};
+  int stage_iters = 0;
 };
 
 

@@ -29,6 +29,11 @@ int launch_prior(const Dev &D, int max_prior_n, bool jac_phase, int mode, int ca
 int launch_build(const Dev &D, const Params &P, int max_prior_n, cudaStream_t st);
 int launch_backsub(const Dev &D, const Params &P, cudaStream_t st);
 
+// uvs_build2.cu — atomics-free path for windows of <= 12 six-wide camera blocks without td
+size_t build2_smem_bytes(int max_frames, bool any_ex, int NW, bool back);
+int launch_build2(const Dev &D, const Params &P, int G, int NW, int max_frames, bool any_ex, bool back, cudaStream_t st);
+int launch_build_cam(const Dev &D, int max_prior_n, cudaStream_t st);
+
 // uvs_solve.cu
 int chol_packed_limit(size_t max_smem);
 int set_chol_smem(size_t bytes);

@@ -65,18 +65,22 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
   return m;
 }
 
-// Packed lower-triangular storage (row i holds columns 0..i) in shared memory, or the window's own
-// d x d block of Smat reused as a full row-major matrix when it does not fit.
-template <bool kPacked>
-struct LowerMat {
-  double *a; int ld;
-  __device__ __forceinline__ double &at(int i, int k) const { return kPacked ? a[(size_t)i * (i + 1) / 2 + k] : a[(size_t)i * ld + k]; }
-};
+constexpr int NB = 8;   // block size of the shared-memory Cholesky
+constexpr int MAX_PRIOR_COLS = 512;   // prior dimension bound (15 x 32 frames + extrinsic + td = 487)
+
+// linear index of the row-major lower triangle -> (I, J), J <= I
+__device__ __forceinline__ void unrank_lower(int t, int &I, int &J) {
+  int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (i * (i + 1) / 2 > t) i--;
+  while ((i + 1) * (i + 2) / 2 <= t) i++;
+  I = i; J = t - i * (i + 1) / 2;
+}
 
 template <bool kPacked>
 __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) {
   __shared__ double red[CT / 32];
   __shared__ int s_flag;
+  __shared__ int s_cmap[MAX_PRIOR_COLS];
   WinCtl &ctl = D.ctl[w];
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   const int F = D.frame_off[w + 1] - D.frame_off[w];
@@ -116,24 +120,159 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
   if (!ctl.have_scale) for (int c = tid; c < d; c += CT) scale[c] = 1.0 / (1.0 + sqrt(colsq[c]));
   __syncthreads();
 
-  // ---- assemble  A = D_s V D_s + D^2  (lower), last row = -D_s g  (augmented system)
-  LowerMat<kPacked> A;
-  A.a = kPacked ? smem : Sg;
-  A.ld = d;
-  double *vec = kPacked ? smem + (size_t)(d + 1) * (d + 2) / 2 : D.delta_cam + co;  // solution vector (d doubles)
+  double *vec;   // solution vector y (d doubles)
   const double radius = ctl.radius;
   if (kPacked) {
-    for (int e = tid; e < d * d; e += CT) {
-      const int j = e / d, i = e - j * d;   // upper entry (j, i), j <= i
-      if (j > i) continue;
-      double v = scale[i] * scale[j] * Sg[e];
-      if (i == j) { const double h = scale[i] * scale[i] * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
-      A.at(i, j) = v;
+    // ---- blocked path: 8x8 blocks of the lower triangle packed in shared memory
+    //      block (I,J), J <= I, at ((I(I+1)/2 + J) * 64), row-major inside; rhs as a separate vector.
+    const int K = (d + NB - 1) / NB;
+    double *A = smem;
+    double *bz = smem + (size_t)K * (K + 1) / 2 * 64;   // rhs / z / y   [8K]
+    double *invd = bz + (size_t)K * NB;                 // reciprocal diagonal of the current panel [8]
+    vec = bz;
+    for (int e = tid; e < K * (K + 1) / 2 * 64; e += CT) {
+      const int blk = e >> 6, jj = (e >> 3) & 7, ii = e & 7;   // ii fastest: coalesced reads of the upper triangle
+      int I, J;
+      unrank_lower(blk, I, J);
+      const int i = I * NB + ii, j = J * NB + jj;
+      double v = 0.0;
+      if (i < d && j < d) {
+        if (j <= i) {
+          v = scale[i] * scale[j] * Sg[(size_t)j * d + i];
+          if (i == j) { const double h = scale[i] * scale[i] * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+        }
+      } else if (i == j) {
+        v = 1.0;   // padding
+      }
+      A[(size_t)blk * 64 + ii * 8 + jj] = v;
     }
-    for (int c = tid; c < d; c += CT) A.at(d, c) = -scale[c] * gS[c];
-    if (tid == 0) A.at(d, d) = 0.0;
+    for (int c = tid; c < K * NB; c += CT) bz[c] = c < d ? -scale[c] * gS[c] : 0.0;
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k = 0; k < K; k++) {
+      double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * 64;
+      if (warp == 0) {
+        // factor the diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot
+        // chain is rsqrt -> scale -> rank-1 update, operands exchanged with shuffles
+        double a[NB];
+        const int r = lane & 7;
+#pragma unroll
+        for (int c = 0; c < NB; c++) a[c] = Akk[r * 8 + c];
+        int bad = 0;
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          const double piv = __shfl_sync(0xffffffffu, a[p], p);
+          if (!(piv > 0.0) || !isfinite(piv)) bad = 1;
+          const double inv = rsqrt(piv);
+          a[p] = r == p ? piv * inv : a[p] * inv;          // rows r < p are finished (their a[p] is unused)
+          if (r == p && lane < NB) invd[p] = inv;
+#pragma unroll
+          for (int q = p + 1; q < NB; q++) {
+            const double lq = __shfl_sync(0xffffffffu, a[p], q);
+            a[q] -= a[p] * lq;                             // only meaningful for r >= q
+          }
+        }
+        if (lane < NB) {
+#pragma unroll
+          for (int c = 0; c < NB; c++) if (c <= r) Akk[r * 8 + c] = a[c];
+        }
+        if (lane == 0) s_flag = bad;
+      }
+      __syncthreads();
+      if (s_flag) break;
+      // panel: L_Ik = A_Ik L_kk^-T for the rows below, z_k = L_kk^-1 b_k
+      const int nrows = NB * (K - 1 - k);
+      for (int t = tid; t <= nrows; t += CT) {
+        double *row;
+        if (t < nrows) { const int i = NB * (k + 1) + t, I = i >> 3; row = A + ((size_t)I * (I + 1) / 2 + k) * 64 + (i & 7) * 8; }
+        else row = bz + k * NB;
+        double x[NB];
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          double v = row[p];
+#pragma unroll
+          for (int q = 0; q < p; q++) v -= x[q] * Akk[p * 8 + q];
+          x[p] = v * invd[p];
+        }
+#pragma unroll
+        for (int p = 0; p < NB; p++) row[p] = x[p];
+      }
+      __syncthreads();
+      // trailing update A_IJ -= L_Ik L_Jk^T with 4x4 register tiles, b_I -= L_Ik z_k
+      const int nt = K - 1 - k;
+      const int ntiles = 4 * (nt * (nt + 1) / 2);
+      for (int tile = tid; tile < ntiles; tile += CT) {
+        int Ip, Jp;
+        unrank_lower(tile >> 2, Ip, Jp);
+        const int ti = (tile >> 1) & 1, tj = tile & 1;
+        if (Ip == Jp && tj > ti) continue;   // strictly-upper tile of a diagonal block
+        const int I = k + 1 + Ip, J = k + 1 + Jp;
+        const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * 64 + ti * 32;
+        const double *LJ = A + ((size_t)J * (J + 1) / 2 + k) * 64 + tj * 32;
+        double *C = A + ((size_t)I * (I + 1) / 2 + J) * 64 + ti * 32 + tj * 4;
+        double c[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b2 = 0; b2 < 4; b2++) c[a][b2] = C[a * 8 + b2];
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          double li[4], lj[4];
+#pragma unroll
+          for (int a = 0; a < 4; a++) { li[a] = LI[a * 8 + p]; lj[a] = LJ[a * 8 + p]; }
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b2 = 0; b2 < 4; b2++) c[a][b2] -= li[a] * lj[b2];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b2 = 0; b2 < 4; b2++) C[a * 8 + b2] = c[a][b2];
+      }
+      for (int t = tid; t < nrows; t += CT) {
+        const int i = NB * (k + 1) + t, I = i >> 3;
+        const double *row = A + ((size_t)I * (I + 1) / 2 + k) * 64 + (i & 7) * 8;
+        double v = bz[i];
+#pragma unroll
+        for (int p = 0; p < NB; p++) v -= row[p] * bz[k * NB + p];
+        bz[i] = v;
+      }
+      __syncthreads();
+    }
+    if (s_flag) {
+      if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
+      return;
+    }
+    // back-substitution L^T y = z, block row by block row, one warp
+    if (warp == 0) {
+      for (int k = K - 1; k >= 0; k--) {
+        const double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * 64;
+        double y[NB];
+#pragma unroll
+        for (int p = NB - 1; p >= 0; p--) {
+          double v = bz[k * NB + p];
+#pragma unroll
+          for (int q = p + 1; q < NB; q++) v -= Akk[q * 8 + p] * y[q];
+          y[p] = v / Akk[p * 8 + p];
+        }
+        __syncwarp();
+        for (int c = lane; c < k * NB; c += 32) {
+          const double *col = A + ((size_t)k * (k + 1) / 2 + (c >> 3)) * 64 + (c & 7);
+          double v = bz[c];
+#pragma unroll
+          for (int p = 0; p < NB; p++) v -= col[p * 8] * y[p];
+          bz[c] = v;
+        }
+        if (lane < NB) bz[k * NB + lane] = y[lane];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
   } else {
-    // in place in global memory: mirror the upper triangle into the lower one
+    // ---- large windows: in place in global memory (mirror the upper triangle into the lower one),
+    //      unblocked right-looking Cholesky
+    vec = D.delta_cam + co;
     for (int e = tid; e < d * d; e += CT) {
       const int i = e / d, j = e - i * d;   // lower entry (i, j), j <= i
       if (j > i) continue;
@@ -142,50 +281,40 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
       Sg[e] = v;
     }
     for (int c = tid; c < d; c += CT) vec[c] = -scale[c] * gS[c];
-  }
-  __syncthreads();
-
-  // ---- right-looking Cholesky; the appended row turns into z = L^-1 (-g)
-  const int rows = kPacked ? d + 1 : d;
-  const int ti = tid >> 4, tk = tid & 15;
-  bool fail = false;
-  for (int j = 0; j < d; j++) {
-    const double piv = A.at(j, j);
-    if (!(piv > 0.0) || !isfinite(piv)) { fail = true; break; }
-    const double inv = 1.0 / sqrt(piv);
     __syncthreads();
-    for (int i = j + 1 + tid; i < rows; i += CT) A.at(i, j) *= inv;
-    if (!kPacked && tid == 0) vec[j] *= inv;
-    if (tid == 0) A.at(j, j) = piv * inv;
-    __syncthreads();
-    if (!kPacked) {
+    const int ti = tid >> 4, tk = tid & 15;
+    bool fail = false;
+    for (int j = 0; j < d; j++) {
+      const double piv = Sg[(size_t)j * d + j];
+      if (!(piv > 0.0) || !isfinite(piv)) { fail = true; break; }
+      const double inv = 1.0 / sqrt(piv);
+      __syncthreads();
+      for (int i = j + 1 + tid; i < d; i += CT) Sg[(size_t)i * d + j] *= inv;
+      if (tid == 0) { vec[j] *= inv; Sg[(size_t)j * d + j] = piv * inv; }
+      __syncthreads();
       const double zj = vec[j];
-      for (int i = j + 1 + tid; i < d; i += CT) vec[i] -= A.at(i, j) * zj;
+      for (int i = j + 1 + tid; i < d; i += CT) vec[i] -= Sg[(size_t)i * d + j] * zj;
+      for (int i = j + 1 + ti; i < d; i += 16) {
+        const double lij = Sg[(size_t)i * d + j];
+        for (int k = j + 1 + tk; k <= i; k += 16) Sg[(size_t)i * d + k] -= lij * Sg[(size_t)k * d + j];
+      }
+      __syncthreads();
     }
-    for (int i = j + 1 + ti; i < rows; i += 16) {
-      const double lij = A.at(i, j);
-      const int kmax = i < d ? i : d - 1;   // the appended row has no diagonal entry
-      for (int k = j + 1 + tk; k <= kmax; k += 16) A.at(i, k) -= lij * A.at(k, j);
+    if (fail) {
+      if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
+      return;
+    }
+    if (tid < 32) {
+      for (int j = d - 1; j >= 0; j--) {
+        const double yj = vec[j] / Sg[(size_t)j * d + j];
+        __syncwarp();
+        for (int i = tid; i < j; i += 32) vec[i] -= Sg[(size_t)j * d + i] * yj;
+        if (tid == 0) vec[j] = yj;
+        __syncwarp();
+      }
     }
     __syncthreads();
   }
-  if (fail) {
-    if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
-    return;
-  }
-  // ---- back-solve L^T y = z with one warp
-  if (kPacked) { for (int c = tid; c < d; c += CT) vec[c] = A.at(d, c); }
-  __syncthreads();
-  if (tid < 32) {
-    for (int j = d - 1; j >= 0; j--) {
-      const double yj = vec[j] / A.at(j, j);
-      __syncwarp();
-      for (int i = tid; i < j; i += 32) vec[i] -= A.at(j, i) * yj;
-      if (tid == 0) vec[j] = yj;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
 
   // ---- delta = s .* y, candidate camera state, step / state norms
   const int cur = D.cur[w];
@@ -233,6 +362,17 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
   x2 = block_sum(x2, red);
 
   // ---- model cost change of the camera-only factors: sum (J delta) . (r + J delta / 2)
+  {   // prior column -> camera offset (-1: constant block)
+    const int n = D.prior_off[w + 1] - D.prior_off[w];
+    for (int c = tid; c < n && c < MAX_PRIOR_COLS; c += CT) s_cmap[c] = -1;
+    __syncthreads();
+    for (int b = D.pblk_off[w] + tid; b < D.pblk_off[w + 1]; b += CT) {
+      const int kind = D.pblk_kind[b], cam = D.pblk_cam[b], col = D.pblk_col[b];
+      const int ls = (kind == 0 || kind == 2) ? 6 : (kind == 1 ? 9 : 1);
+      if (cam >= 0) for (int c = 0; c < ls; c++) s_cmap[col + c] = cam + c;
+    }
+    __syncthreads();
+  }
   double mc = 0.0;
   if (lead) {
     const int warp = tid >> 5, lane = tid & 31;
@@ -251,12 +391,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
       const double *r = D.rec_prior + D.prior_off[w];
       for (int i = warp; i < n; i += CT / 32) {
         double jd = 0.0;
-        for (int b = D.pblk_off[w]; b < D.pblk_off[w + 1]; b++) {
-          const int kind = D.pblk_kind[b], cam = D.pblk_cam[b], col = D.pblk_col[b];
-          if (cam < 0) continue;
-          const int ls = (kind == 0 || kind == 2) ? 6 : (kind == 1 ? 9 : 1);
-          if (lane < ls) jd += J0[(size_t)i * n + col + lane] * dl[cam + lane];
-        }
+        for (int c = lane; c < n; c += 32) { const int cam = s_cmap[c]; if (cam >= 0) jd += J0[(size_t)i * n + c] * dl[cam]; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) jd += __shfl_xor_sync(0xffffffffu, jd, o);
         if (lane == 0) mc += jd * (r[i] + 0.5 * jd);
@@ -372,10 +507,13 @@ __global__ void k_copy_acc(Dev D, int slot, double *out, int zero) {
   if (zero) D.acc[(size_t)w * ACC_STRIDE + slot] = 0.0;
 }
 
+static size_t chol_smem_bytes(int d) {
+  const size_t K = (d + NB - 1) / NB;
+  return (K * (K + 1) / 2 * 64 + K * NB + NB) * sizeof(double);
+}
 int chol_packed_limit(size_t max_smem) {
-  // (d+1)(d+2)/2 + d doubles must fit
-  int d = 0;
-  while (((size_t)(d + 2) * (d + 3) / 2 + (d + 1)) * sizeof(double) <= max_smem) d++;
+  int d = NB;
+  while (chol_smem_bytes(d + NB) <= max_smem) d += NB;
   return d;
 }
 
@@ -383,7 +521,7 @@ int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st) { k_solve_
 
 int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, cudaStream_t st) {
   const int dd = max_d <= packed_limit ? max_d : packed_limit;
-  const size_t smem = ((size_t)(dd + 1) * (dd + 2) / 2 + dd) * sizeof(double);
+  const size_t smem = chol_smem_bytes(dd);
   k_chol<<<D.B, CT, smem, st>>>(D, P, packed_limit);
   return 1;
 }
