@@ -247,3 +247,61 @@ def test_stress_window_global_cholesky(solver, opts):
     solver.download()
     assert abs(sm.final_cost - sm0.final_cost) <= 1e-6 * abs(sm0.final_cost)
     assert np.abs(w.pose - ref.pose).max() < STEP_TOL
+
+
+@pytest.mark.parametrize("cfg,flag", [("C1", 0), ("C2", 0), ("tiny", 0), ("tiny", 1)])
+def test_marginalization_parity(solver, opts, cfg, flag):
+    """next prior built on the GPU (after the solve, as estimator.cpp:994-1003) vs the oracle: same kept
+    blocks / linearisation points, A' and b' equal, and the identities J0^T J0 = A', J0^T r0 = b'
+    (marginalization_factor.cpp:295-296).  J0 itself is only defined up to an orthogonal transform."""
+    w = gw.make_window(cfg)
+    solver.upload([w], opts)
+    solver.solve()
+    solver.download()
+    g = solver.marginalize(0, flag)
+    m = orc.marginalize(w, opts, flag)      # oracle on the SAME (GPU-solved) state
+    assert (g is None) == (m is None)
+    if m is None:
+        return
+    assert g["n"] == m["n"] and g["m"] == m["m"]
+    assert np.array_equal(g["kinds"], m["kinds"]) and np.array_equal(g["ids"], m["ids"])
+    assert np.allclose(g["x0"], m["x0"], atol=1e-12)
+    sA, sb = np.abs(m["A"]).max(), max(1.0, np.abs(m["b"]).max())
+    # A' = Arr - Arm Amm^+ Amr with eigenvalues <= 1e-8 zeroed: |Amm| reaches 1e10 (IMU information), so
+    # eigenvalues near the cut-off are resolved only to ~1e-6 absolute by ANY FP64 eigensolver and the
+    # weakly observed landmark directions amplify that; the oracle's own A' is asymmetric at 5e-4
+    # relative in such cases (tests/test_oracle.py).  Prior-only marginalization (flag 1) has no such
+    # directions and must agree to 1e-6; MARGIN_OLD is held to 2e-3 here and to the 1e-4 pose-delta bar
+    # through the next solve below.
+    tolA = 1e-6 if flag == 1 else 2e-3
+    assert np.abs(g["A"] - m["A"]).max() < tolA * sA, np.abs(g["A"] - m["A"]).max() / sA
+    assert np.abs(g["b"] - m["b"]).max() < tolA * sb, np.abs(g["b"] - m["b"]).max() / sb
+    J, r = g["J"], g["r"]
+    As = np.tril(g["A"]) + np.tril(g["A"], -1).T
+    assert np.abs(J.T @ J - As).max() < 1e-7 * sA
+    assert np.abs(J.T @ r - g["b"]).max() < 1e-6 * sb
+    # the prior is usable: a window carrying it evaluates to the same prior residual on GPU and oracle
+    if flag == 0:
+        w2, _ = gw.drop_first_frame(w, dict(Rs=[None] * w.n_frames, Ps=[None] * w.n_frames, Vs=[None] * w.n_frames, ba=0, bg=0,
+                                            inv_depth=w.inv_depth.copy(), ortho=w.ortho.copy(),
+                                            Rwc=[np.eye(3)] * w.n_frames, twc=[np.zeros(3)] * w.n_frames), np.random.default_rng(0))
+        w2.set_prior(J, r, g["kinds"], g["ids"], g["x0"])
+        w2_init = w2.copy()
+        solver.upload([w2], opts)
+        rs, _ = solver.eval_prior(local=True)
+        r0, _, _ = orc.eval_factors(w2, opts, orc.F_PRIOR, local=True)
+        assert np.abs(rs[0] - r0.ravel()).max() < 1e-6 * max(1.0, np.abs(r0).max())
+        sm = solver.solve()[0]
+        solver.download()
+        assert sm.final_cost <= sm.initial_cost
+        # functional parity: the same next window solved by the oracle with the ORACLE's prior
+        w3 = w2.copy()
+        w3.pose, w3.speed_bias, w3.inv_depth, w3.ortho = (a.copy() for a in (w2_init.pose, w2_init.speed_bias, w2_init.inv_depth, w2_init.ortho))
+        w3.set_prior(m["J"], m["r"], m["kinds"], m["ids"], m["x0"])
+        sm3 = orc.solve(w3, opts)
+        if cfg == "tiny":
+            # 4 frames / a dozen points after the slide: the gauge directions are held by the prior's
+            # weakest eigenvalues only, so compare what is observable - the cost - instead of the poses
+            assert abs(sm.final_cost - sm3.final_cost) < 1e-3 * abs(sm3.final_cost)
+        else:
+            assert np.abs(w2.pose - w3.pose).max() < STEP_TOL, np.abs(w2.pose - w3.pose).max()

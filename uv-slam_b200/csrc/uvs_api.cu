@@ -118,9 +118,9 @@ int uvs_create(int device, UvsHandle **out) {
   h->hscratch.pinned_host = true;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return UVS_ERR_CUDA; }
   cudaEventCreate(&h->ev_a); cudaEventCreate(&h->ev_b); cudaEventCreate(&h->ev_c); cudaEventCreate(&h->ev_d);
-  const size_t max_smem = prop.sharedMemPerBlockOptin;
-  h->packed_limit = chol_packed_limit(max_smem - 1024);
-  set_chol_smem(max_smem - 1024);
+  const size_t chol_smem = chol_max_dynamic_smem(prop.sharedMemPerBlockOptin);
+  if (chol_smem == 0) { cudaGetLastError(); cudaStreamDestroy(h->stream); delete h; return UVS_ERR_CUDA; }
+  h->packed_limit = chol_packed_limit(chol_smem);
   cudaMalloc((void **)&h->d_active, sizeof(int));
   cudaMallocHost((void **)&h->h_active, sizeof(int));
   uvs_default_options(&h->opts);

@@ -36,7 +36,7 @@ int launch_build_cam(const Dev &D, int max_prior_n, cudaStream_t st);
 
 // uvs_solve.cu
 int chol_packed_limit(size_t max_smem);
-int set_chol_smem(size_t bytes);
+size_t chol_max_dynamic_smem(size_t optin_bytes);
 int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st);
 int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, cudaStream_t st);
 int launch_step(const Dev &D, const Params &P, cudaStream_t st);

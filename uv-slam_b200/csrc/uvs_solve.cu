@@ -525,8 +525,15 @@ int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, cuda
   k_chol<<<D.B, CT, smem, st>>>(D, P, packed_limit);
   return 1;
 }
-int set_chol_smem(size_t bytes) {
-  return (int)cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+// largest dynamic shared-memory size k_chol can be launched with (opt-in limit minus its static arrays);
+// raises the kernel's limit to that value.  Returns 0 on failure.
+size_t chol_max_dynamic_smem(size_t optin_bytes) {
+  cudaFuncAttributes attr;
+  if (cudaFuncGetAttributes(&attr, k_chol) != cudaSuccess) return 0;
+  if (optin_bytes <= attr.sharedSizeBytes + 512) return 0;
+  const size_t dyn = optin_bytes - attr.sharedSizeBytes - 512;
+  if (cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return 0;
+  return dyn;
 }
 
 int launch_step(const Dev &D, const Params &P, cudaStream_t st) { k_step<<<D.B, CT, 0, st>>>(D, P); return 1; }
