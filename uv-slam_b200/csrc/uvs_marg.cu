@@ -9,7 +9,7 @@
 //   3. A_mm^+ by symmetric eigendecomposition with eigenvalues <= 1e-8 zeroed (:266-272),
 //      A' = A_rr - A_rm A_mm^+ A_mr, b' likewise (:274-281);
 //   4. second eigendecomposition: J0 = sqrt(S) V^T, r0 = S^-1/2 V^T b' (:283-291).
-// Deliberate difference (same as oracle/marg.h): blocks are identified by (kind, id), not by host
+// Deliberate difference (the CPU checker makes the same choice): blocks are identified by (kind, id), not by host
 // addresses, and their order is fixed (dropped: pose, speed-bias, points, lines; kept: pose_f,
 // speedbias_f by frame, extrinsic, td), so that results are reproducible.
 #include <cstring>

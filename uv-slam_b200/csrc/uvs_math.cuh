@@ -1,6 +1,6 @@
 // uvs_math.cuh — fixed-size FP64 algebra for the sm_100a factor kernels.
 //
-// Product code: written independently of oracle/ (which is test infrastructure).  Formulas follow
+// Product code: written independently of the CPU checker (test infrastructure).  Formulas follow
 // the reference's Eigen usage: R(q) = I + 2w[u]x + 2[u]x^2 is NOT
 // normalised, q^-1 = conj(q)/|q|^2, deltaQ(theta) = (theta/2, 1) (utility/utility.h:11-24).
 #pragma once
