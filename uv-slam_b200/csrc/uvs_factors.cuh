@@ -18,11 +18,16 @@ struct ProjTd {
   double td, td_i, td_j, row_i, row_j, vix, viy, vjx, vjy, tr_over_row, half_row;
 };
 
+// Writes r[2] and the Jacobian blocks through the given pointers (row stride `ld` inside a pose block:
+// 6 in the tangent layout, 7 in the Ceres layout; 7th column is the caller's business).  When
+// loss_a > 0 the Cauchy corrector (sqrt(rho') scaling, marginalization_factor.cpp:37-68) is folded
+// into the outputs; *half_rho returns 1/2 rho(|r|^2).  Outputs may live in shared memory: every value
+// is written once, as soon as it is known, so nothing stays live in registers.
 template <bool kJac, bool kTd>
 __device__ __forceinline__ void proj_eval(const double *__restrict__ pose_i, const double *__restrict__ pose_j,
                                           const double *__restrict__ ex, double inv_dep, d3 pts_i, d3 pts_j, double S,
-                                          const ProjTd *tdp, bool want_ex, double r[2], double *Ji, double *Jj,
-                                          double *Jex, double *Jl, double *Jtd) {
+                                          const ProjTd *tdp, bool want_ex, double loss_a, bool correct, int ld, double *r,
+                                          double *Ji, double *Jj, double *Jex, double *Jl, double *Jtd, double *half_rho) {
   d3 Pi, Pj, tic; q4 Qi, Qj, qic;
   load_pose(pose_i, Pi, Qi);
   load_pose(pose_j, Pj, Qj);
@@ -35,63 +40,74 @@ __device__ __forceinline__ void proj_eval(const double *__restrict__ pose_i, con
     pts_i = pts_i - si * vel_i;
     pts_j = pts_j - sj * mk3(tdp->vjx, tdp->vjy, 0.0);
   }
-  const d3 pci = mk3(pts_i.x / inv_dep, pts_i.y / inv_dep, pts_i.z / inv_dep);
+  const double depth = 1.0 / inv_dep;
+  const d3 pci = depth * pts_i;
   const d3 pbi = qrot(qic, pci) + tic;
   const d3 pw = qrot(Qi, pbi) + Pi;
   const d3 pbj = qrot(qinv(Qj), pw - Pj);
   const d3 pcj = qrot(qinv(qic), pbj - tic);
-  const double dep_j = pcj.z;
-  r[0] = S * (pcj.x / dep_j - pts_j.x);
-  r[1] = S * (pcj.y / dep_j - pts_j.y);
+  const double iz = 1.0 / pcj.z;
+  double r0 = S * (pcj.x * iz - pts_j.x), r1 = S * (pcj.y * iz - pts_j.y);
+  const double s = r0 * r0 + r1 * r1;
+  double sq = 1.0;
+  if (correct && loss_a > 0.0) {
+    double rho0, rho1;
+    cauchy(loss_a, s, rho0, rho1);
+    *half_rho = 0.5 * rho0;
+    sq = sqrt(rho1);
+  } else {
+    *half_rho = 0.5 * s;
+  }
+  r[0] = sq * r0; r[1] = sq * r1;
   if (!kJac) return;
 
   const m33 Ri = qmat(Qi), Rj = qmat(Qj), Ric = qmat(qic);
-  const double iz = 1.0 / dep_j;
-  const double r00 = S * iz, r02 = S * (-pcj.x / (dep_j * dep_j)), r12 = S * (-pcj.y / (dep_j * dep_j));
+  const double Ss = S * sq;
+  const double r00 = Ss * iz, r02 = -Ss * pcj.x * iz * iz, r12 = -Ss * pcj.y * iz * iz;
   // out[2x3] = reduce * M
-  auto red = [&](const m33 &M, double *o, int stride, double sgn) {
+  auto red = [&](const m33 &M, double *o, double sgn) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       o[c] = sgn * (r00 * M.a[c] + r02 * M.a[6 + c]);
-      o[stride + c] = sgn * (r00 * M.a[3 + c] + r12 * M.a[6 + c]);
+      o[ld + c] = sgn * (r00 * M.a[3 + c] + r12 * M.a[6 + c]);
     }
   };
   const m33 A = mtmul(Ric, mtrans(Rj));  // ric^T Rj^T
   const m33 B = mmul(A, Ri);             // ric^T Rj^T Ri
-  red(A, Ji, 6, 1.0);
-  red(mmul(B, skew(pbi)), Ji + 3, 6, -1.0);
-  red(A, Jj, 6, -1.0);
-  red(mtmul(Ric, skew(pbj)), Jj + 3, 6, 1.0);
+  red(A, Ji, 1.0);
+  red(mmul(B, skew(pbi)), Ji + 3, -1.0);
+  red(A, Jj, -1.0);
+  red(mtmul(Ric, skew(pbj)), Jj + 3, 1.0);
   const m33 T = mmul(B, Ric);  // tmp_r
   if (!want_ex) {
 #pragma unroll
-    for (int k = 0; k < 12; k++) Jex[k] = 0.0;
+    for (int k = 0; k < 6; k++) { Jex[k] = 0.0; Jex[ld + k] = 0.0; }
   } else {
     m33 L = B;  // ric^T (Rj^T Ri - I) = B - ric^T
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
       for (int j = 0; j < 3; j++) L.a[3 * i + j] -= Ric.a[3 * j + i];
-    red(L, Jex, 6, 1.0);
+    red(L, Jex, 1.0);
     const d3 tp = mvec(T, pci);
     const d3 e = mtvec(Ric, mtvec(Rj, mvec(Ri, tic) + Pi - Pj) - tic);
     m33 Rr = mmul(T, skew(pci));
     const m33 s1 = skew(tp + e);
 #pragma unroll
     for (int k = 0; k < 9; k++) Rr.a[k] = s1.a[k] - Rr.a[k];
-    red(Rr, Jex + 3, 6, 1.0);
+    red(Rr, Jex + 3, 1.0);
   }
   {
-    const double f = -1.0 / (inv_dep * inv_dep);
+    const double f = -depth * depth;
     const d3 v = mvec(T, pts_i);
     Jl[0] = (r00 * v.x + r02 * v.z) * f;
     Jl[1] = (r00 * v.y + r12 * v.z) * f;
   }
   if (kTd) {
-    const double f = -1.0 / inv_dep;
+    const double f = -depth;
     const d3 v = mvec(T, vel_i);
-    Jtd[0] = (r00 * v.x + r02 * v.z) * f + S * tdp->vjx;
-    Jtd[1] = (r00 * v.y + r12 * v.z) * f + S * tdp->vjy;
+    Jtd[0] = (r00 * v.x + r02 * v.z) * f + Ss * tdp->vjx;
+    Jtd[1] = (r00 * v.y + r12 * v.z) * f + Ss * tdp->vjy;
   }
 }
 

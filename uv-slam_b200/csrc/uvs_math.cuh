@@ -31,8 +31,8 @@ __device__ __forceinline__ q4 qmul(q4 a, q4 b) {
              a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z);
 }
 __device__ __forceinline__ q4 qinv(q4 q) {
-  const double n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
-  return mkq(-q.x / n2, -q.y / n2, -q.z / n2, q.w / n2);
+  const double in2 = 1.0 / (q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  return mkq(-q.x * in2, -q.y * in2, -q.z * in2, q.w * in2);
 }
 __device__ __forceinline__ d3 qvec(q4 q) { return mk3(q.x, q.y, q.z); }
 // v + w (2 u x v) + u x (2 u x v)

@@ -66,6 +66,7 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 }
 
 constexpr int NB = 8;   // block size of the shared-memory Cholesky
+constexpr int RS = 9, BS = 72;   // row / block stride in doubles (padded against bank conflicts)
 constexpr int MAX_PRIOR_COLS = 512;   // prior dimension bound (15 x 32 frames + extrinsic + td = 487)
 
 // linear index of the row-major lower triangle -> (I, J), J <= I
@@ -124,40 +125,44 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
   const double radius = ctl.radius;
   if (kPacked) {
     // ---- blocked path: 8x8 blocks of the lower triangle packed in shared memory
-    //      block (I,J), J <= I, at ((I(I+1)/2 + J) * 64), row-major inside; rhs as a separate vector.
+    //      block (I,J), J <= I, at ((I(I+1)/2 + J) * BS), rows RS = 9 doubles apart (the odd stride
+    //      spreads the rows of different blocks over the banks); rhs as a separate vector.
     const int K = (d + NB - 1) / NB;
     double *A = smem;
-    double *bz = smem + (size_t)K * (K + 1) / 2 * 64;   // rhs / z / y   [8K]
+    double *bz = smem + (size_t)K * (K + 1) / 2 * BS;   // rhs / z / y   [8K]
     double *invd = bz + (size_t)K * NB;                 // reciprocal diagonal of the current panel [8]
     vec = bz;
-    for (int e = tid; e < K * (K + 1) / 2 * 64; e += CT) {
-      const int blk = e >> 6, jj = (e >> 3) & 7, ii = e & 7;   // ii fastest: coalesced reads of the upper triangle
-      int I, J;
-      unrank_lower(blk, I, J);
-      const int i = I * NB + ii, j = J * NB + jj;
-      double v = 0.0;
-      if (i < d && j < d) {
-        if (j <= i) {
-          v = scale[i] * scale[j] * Sg[(size_t)j * d + i];
-          if (i == j) { const double h = scale[i] * scale[i] * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+    const int warp = tid >> 5, lane = tid & 31;
+    {
+      // rows j of the upper triangle of Sg, coalesced over i; element (i,j), j <= i, of the lower matrix
+      const int dp = K * NB;
+      for (int j = warp; j < dp; j += CT / 32) {
+        const double sj = j < d ? scale[j] : 0.0;
+        for (int i = j + lane; i < dp; i += 32) {
+          double v = 0.0;
+          if (i < d && j < d) {
+            v = scale[i] * sj * Sg[(size_t)j * d + i];
+            if (i == j) { const double h = sj * sj * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+          } else if (i == j) {
+            v = 1.0;   // padding
+          }
+          const int I = i >> 3, J = j >> 3;
+          A[((size_t)I * (I + 1) / 2 + J) * BS + (i & 7) * RS + (j & 7)] = v;
         }
-      } else if (i == j) {
-        v = 1.0;   // padding
       }
-      A[(size_t)blk * 64 + ii * 8 + jj] = v;
+      // strictly-upper parts of the diagonal blocks are never read
     }
     for (int c = tid; c < K * NB; c += CT) bz[c] = c < d ? -scale[c] * gS[c] : 0.0;
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
     for (int k = 0; k < K; k++) {
-      double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * 64;
+      double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
       if (warp == 0) {
         // factor the diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot
         // chain is rsqrt -> scale -> rank-1 update, operands exchanged with shuffles
         double a[NB];
         const int r = lane & 7;
 #pragma unroll
-        for (int c = 0; c < NB; c++) a[c] = Akk[r * 8 + c];
+        for (int c = 0; c < NB; c++) a[c] = c <= r ? Akk[r * RS + c] : 0.0;
         int bad = 0;
 #pragma unroll
         for (int p = 0; p < NB; p++) {
@@ -174,7 +179,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
         }
         if (lane < NB) {
 #pragma unroll
-          for (int c = 0; c < NB; c++) if (c <= r) Akk[r * 8 + c] = a[c];
+          for (int c = 0; c < NB; c++) if (c <= r) Akk[r * RS + c] = a[c];
         }
         if (lane == 0) s_flag = bad;
       }
@@ -184,14 +189,16 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
       const int nrows = NB * (K - 1 - k);
       for (int t = tid; t <= nrows; t += CT) {
         double *row;
-        if (t < nrows) { const int i = NB * (k + 1) + t, I = i >> 3; row = A + ((size_t)I * (I + 1) / 2 + k) * 64 + (i & 7) * 8; }
+        if (t < nrows) { const int i = NB * (k + 1) + t, I = i >> 3; row = A + ((size_t)I * (I + 1) / 2 + k) * BS + (i & 7) * RS; }
         else row = bz + k * NB;
         double x[NB];
 #pragma unroll
-        for (int p = 0; p < NB; p++) {
-          double v = row[p];
+        for (int p = 0; p < NB; p++) x[p] = row[p];
 #pragma unroll
-          for (int q = 0; q < p; q++) v -= x[q] * Akk[p * 8 + q];
+        for (int p = 0; p < NB; p++) {
+          double v = x[p];
+#pragma unroll
+          for (int q = 0; q < p; q++) v -= x[q] * Akk[p * RS + q];
           x[p] = v * invd[p];
         }
 #pragma unroll
@@ -207,19 +214,19 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
         const int ti = (tile >> 1) & 1, tj = tile & 1;
         if (Ip == Jp && tj > ti) continue;   // strictly-upper tile of a diagonal block
         const int I = k + 1 + Ip, J = k + 1 + Jp;
-        const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * 64 + ti * 32;
-        const double *LJ = A + ((size_t)J * (J + 1) / 2 + k) * 64 + tj * 32;
-        double *C = A + ((size_t)I * (I + 1) / 2 + J) * 64 + ti * 32 + tj * 4;
+        const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * BS + ti * 4 * RS;
+        const double *LJ = A + ((size_t)J * (J + 1) / 2 + k) * BS + tj * 4 * RS;
+        double *C = A + ((size_t)I * (I + 1) / 2 + J) * BS + ti * 4 * RS + tj * 4;
         double c[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int b2 = 0; b2 < 4; b2++) c[a][b2] = C[a * 8 + b2];
+          for (int b2 = 0; b2 < 4; b2++) c[a][b2] = C[a * RS + b2];
 #pragma unroll
         for (int p = 0; p < NB; p++) {
           double li[4], lj[4];
 #pragma unroll
-          for (int a = 0; a < 4; a++) { li[a] = LI[a * 8 + p]; lj[a] = LJ[a * 8 + p]; }
+          for (int a = 0; a < 4; a++) { li[a] = LI[a * RS + p]; lj[a] = LJ[a * RS + p]; }
 #pragma unroll
           for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -228,11 +235,11 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int b2 = 0; b2 < 4; b2++) C[a * 8 + b2] = c[a][b2];
+          for (int b2 = 0; b2 < 4; b2++) C[a * RS + b2] = c[a][b2];
       }
       for (int t = tid; t < nrows; t += CT) {
         const int i = NB * (k + 1) + t, I = i >> 3;
-        const double *row = A + ((size_t)I * (I + 1) / 2 + k) * 64 + (i & 7) * 8;
+        const double *row = A + ((size_t)I * (I + 1) / 2 + k) * BS + (i & 7) * RS;
         double v = bz[i];
 #pragma unroll
         for (int p = 0; p < NB; p++) v -= row[p] * bz[k * NB + p];
@@ -247,21 +254,21 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
     // back-substitution L^T y = z, block row by block row, one warp
     if (warp == 0) {
       for (int k = K - 1; k >= 0; k--) {
-        const double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * 64;
+        const double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
         double y[NB];
 #pragma unroll
         for (int p = NB - 1; p >= 0; p--) {
           double v = bz[k * NB + p];
 #pragma unroll
-          for (int q = p + 1; q < NB; q++) v -= Akk[q * 8 + p] * y[q];
-          y[p] = v / Akk[p * 8 + p];
+          for (int q = p + 1; q < NB; q++) v -= Akk[q * RS + p] * y[q];
+          y[p] = v / Akk[p * RS + p];
         }
         __syncwarp();
         for (int c = lane; c < k * NB; c += 32) {
-          const double *col = A + ((size_t)k * (k + 1) / 2 + (c >> 3)) * 64 + (c & 7);
+          const double *col = A + ((size_t)k * (k + 1) / 2 + (c >> 3)) * BS + (c & 7);
           double v = bz[c];
 #pragma unroll
-          for (int p = 0; p < NB; p++) v -= col[p * 8] * y[p];
+          for (int p = 0; p < NB; p++) v -= col[p * RS] * y[p];
           bz[c] = v;
         }
         if (lane < NB) bz[k * NB + lane] = y[lane];
@@ -509,7 +516,7 @@ __global__ void k_copy_acc(Dev D, int slot, double *out, int zero) {
 
 static size_t chol_smem_bytes(int d) {
   const size_t K = (d + NB - 1) / NB;
-  return (K * (K + 1) / 2 * 64 + K * NB + NB) * sizeof(double);
+  return (K * (K + 1) / 2 * BS + K * NB + NB) * sizeof(double);
 }
 int chol_packed_limit(size_t max_smem) {
   int d = NB;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void flush_tile(const double *tile, const unsigned ch
 
 // ------------------------------------------------------------------------------------------------
 template <bool kJac, bool kTd, bool kCeres>
-__global__ void __launch_bounds__(NT) k_proj(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+__global__ void __launch_bounds__(NT, 4) k_proj(Dev D, Params P, int mode, int cand, double *__restrict__ out,
                                              double *__restrict__ res_out, double *cost, int cost_stride) {
   constexpr int REC = kCeres ? (kTd ? CREC_PROJ_TD : CREC_PROJ) : (kTd ? REC_PROJ_TD : REC_PROJ);
   constexpr int PW = kCeres ? 7 : 6;
@@ -105,30 +105,20 @@ __global__ void __launch_bounds__(NT) k_proj(Dev D, Params P, int mode, int cand
       tdp.vjx = __ldg(D.proj_vel_j + 2 * (size_t)f); tdp.vjy = __ldg(D.proj_vel_j + 2 * (size_t)f + 1);
       tdp.tr_over_row = P.tr_over_row; tdp.half_row = P.half_row;
     }
-    double r[2], Ji[12], Jj[12], Jex[12], Jl[2], Jtd[2];
     const bool want_ex = mode == 0 || (wflags & WF_EXTRINSIC);
-    proj_eval<kJac, kTd>(pi, pj, ex, lam, pts_i, pts_j, P.S, &tdp, want_ex, r, Ji, Jj, Jex, Jl, Jtd);
-    const double s = r[0] * r[0] + r[1] * r[1];
-    double sq = 1.0;
-    if (kCeres) half_rho = 0.5 * s; else sq = corrector(P.cauchy_point, s, half_rho);
-    r[0] *= sq; r[1] *= sq;
     if (kJac) {
       double *t = tile + threadIdx.x * (REC + 1);
-      t[0] = r[0]; t[1] = r[1];
+      proj_eval<true, kTd>(pi, pj, ex, lam, pts_i, pts_j, P.S, &tdp, want_ex, P.cauchy_point, !kCeres, PW, t, t + 2, t + 2 + 2 * PW,
+                           t + 2 + 4 * PW, t + 2 + 6 * PW, t + 2 + 6 * PW + 2, &half_rho);
+      if (kCeres) {
 #pragma unroll
-      for (int row = 0; row < 2; row++) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-          t[2 + row * PW + c] = sq * Ji[row * 6 + c];
-          t[2 + 2 * PW + row * PW + c] = sq * Jj[row * 6 + c];
-          t[2 + 4 * PW + row * PW + c] = sq * Jex[row * 6 + c];
-        }
-        if (kCeres) { t[2 + row * 7 + 6] = 0.0; t[2 + 14 + row * 7 + 6] = 0.0; t[2 + 28 + row * 7 + 6] = 0.0; }
+        for (int row = 0; row < 2; row++) { t[2 + row * 7 + 6] = 0.0; t[2 + 14 + row * 7 + 6] = 0.0; t[2 + 28 + row * 7 + 6] = 0.0; }
       }
-      t[2 + 6 * PW] = sq * Jl[0]; t[2 + 6 * PW + 1] = sq * Jl[1];
-      if (kTd) { t[2 + 6 * PW + 2] = sq * Jtd[0]; t[2 + 6 * PW + 3] = sq * Jtd[1]; }
-    } else if (res_out) {
-      res_out[2 * (size_t)f] = r[0]; res_out[2 * (size_t)f + 1] = r[1];
+    } else {
+      double r[2];
+      proj_eval<false, kTd>(pi, pj, ex, lam, pts_i, pts_j, P.S, &tdp, want_ex, P.cauchy_point, true, 6, r, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, &half_rho);
+      if (res_out) { res_out[2 * (size_t)f] = r[0]; res_out[2 * (size_t)f + 1] = r[1]; }
     }
   }
   if (cost) add_window_scalar(cost, cost_stride, ix.w, half_rho, valid);
@@ -141,7 +131,7 @@ __global__ void __launch_bounds__(NT) k_proj(Dev D, Params P, int mode, int cand
 
 // ------------------------------------------------------------------------------------------------
 template <bool kJac, bool kCeres>
-__global__ void __launch_bounds__(NT) k_line(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+__global__ void __launch_bounds__(NT, 4) k_line(Dev D, Params P, int mode, int cand, double *__restrict__ out,
                                              double *__restrict__ res_out, double *cost, int cost_stride) {
   constexpr int REC = kCeres ? CREC_LINE : REC_LINE;
   constexpr int NP = kCeres ? 11 : 10;
@@ -193,7 +183,7 @@ __global__ void __launch_bounds__(NT) k_line(Dev D, Params P, int mode, int cand
 
 // ------------------------------------------------------------------------------------------------
 template <bool kJac, bool kCeres>
-__global__ void __launch_bounds__(NT) k_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+__global__ void __launch_bounds__(NT, 4) k_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out,
                                            double *__restrict__ res_out, double *cost, int cost_stride) {
   constexpr int REC = kCeres ? CREC_VP : REC_VP;
   constexpr int NP = kCeres ? 11 : 10;
