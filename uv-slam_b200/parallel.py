@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: one process per GPU, `torch.distributed` for rendezvous and the exchange.
+
+Two ways the path shards:
+  * window-parallel - independent windows are split over the ranks, no data-path collective;
+  * factor-parallel - ONE window's landmarks are split over the ranks (landmark k -> rank k % N, IMU factors
+    and the prior on rank 0); every LM iteration the ranks sum their partial reduced camera systems
+    (one all-reduce of d^2 + 3d doubles) and a 16-double accumulator per window.  The C library takes the
+    reduction as a callback (`uvs_comm_init`), implemented here with `torch.distributed.all_reduce` on the
+    library's own CUDA stream (NCCL over NVLink on GPUs; the same code path runs over gloo on host buffers
+    in the CPU tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def shard_windows(windows, rank: int, world: int):
+    """contiguous, balanced split of a list of windows (window-parallel mode)"""
+    n = len(windows)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return windows[lo:hi]
+
+
+def landmark_owner(index, world: int):
+    """rank that owns global landmark `index` in the factor-parallel mode (mirrors the device code)"""
+    return np.asarray(index) % world
+
+
+def make_allreduce(dist, device: str = "cuda"):
+    """reduce_fn(ptr, count, stream) -> 0 for Solver.comm_init: sums `count` doubles at `ptr` over all ranks,
+    in place, ordered on `stream` (a CUDA stream handle; ignored for host buffers)."""
+    import torch
+
+    if device == "cuda":
+        class _DevPtr:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        def reduce_fn(ptr, count, stream):
+            t = torch.as_tensor(_DevPtr(ptr, count), device="cuda")
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return 0
+    else:
+        def reduce_fn(ptr, count, stream):
+            buf = (C.c_double * count).from_address(ptr)
+            t = torch.frombuffer(buf, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return 0
+    return reduce_fn
