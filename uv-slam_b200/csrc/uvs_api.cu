@@ -182,19 +182,9 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   }
   h->B = B; h->max_d = max_d; h->max_prior_n = max_prior_n;
   h->max_frames = max_frames; h->any_ex = any_ex;
-  // landmark path: shared-memory private accumulation when the pose-pose system is small enough
-  h->use_build2 = !td && (max_frames + (any_ex ? 1 : 0)) <= 12 && max_frames >= 2;
-  if (h->use_build2) {
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, h->device));
-    int NW = 8;
-    while (NW > 1 && build2_smem_bytes(max_frames, any_ex, NW, false) > prop.sharedMemPerBlockOptin - 1024) NW--;
-    if (build2_smem_bytes(max_frames, any_ex, NW, false) > prop.sharedMemPerBlockOptin - 1024) h->use_build2 = false;
-    h->b2_NW = NW;
-    const int sms = prop.multiProcessorCount;
-    h->b2_G = std::max(1, std::min(16, (2 * sms + B - 1) / B));
-    if (B >= sms) h->b2_G = 1;
-  }
+  // landmark path: thread-per-landmark elimination + per-window dense rank update when the pose-pose system
+  // fits shared memory (the reference's window size); otherwise the general warp-per-landmark path
+  h->use_build3 = !td && (max_frames + (any_ex ? 1 : 0)) <= 12 && max_frames >= 2;
   prefix<int>(h->frame_off, B, w, [](const UvsWindow &x) { return (int)x.n_frames; });
   prefix<int>(h->point_off, B, w, [](const UvsWindow &x) { return (int)x.n_points; });
   prefix<int>(h->line_off, B, w, [](const UvsWindow &x) { return (int)x.n_lines; });
@@ -262,6 +252,14 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   const size_t w_S = wk.take((size_t)nS * Dd), w_gS = wk.take(nCam * Dd), w_gf = wk.take(nCam * Dd), w_csq = wk.take(nCam * Dd);
   const size_t w_reduce_end = wk.total;
   const size_t w_dc = wk.take(nCam * Dd), w_dp = wk.take(nP * Dd), w_dl = wk.take(nL * 4 * Dd);
+  size_t w_b3 = 0;
+  if (h->use_build3) {
+    Dev tmp{}; tmp.B = B; tmp.nP = nP; tmp.nL = nL; tmp.nProj = nProj; tmp.nLobs = nLobs; tmp.nVobs = nVobs;
+    w_b3 = wk.take(build3_bytes(tmp, max_frames, any_ex, &h->b3));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    if (build3_smem(max_frames, any_ex, max_prior_n) > prop.sharedMemPerBlockOptin - 1024) h->use_build3 = false;
+  }
 
   CK(h->stage.reserve(in.total));
   CK(h->dev.reserve(wk.total));
@@ -378,8 +376,10 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   h->o_pose0 = o_pose; h->o_state_bytes = o_state_end - o_pose;
   h->o_pristine = w_pristine; h->o_cur = w_cur; h->cur_bytes = B * I;
   h->o_reduce = w_S; h->reduce_doubles = (w_reduce_end - w_S) / Dd;
+  h->o_b3 = w_b3;
 
   h->launches += launch_prep(D, h->stream);
+  if (h->use_build3) h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->stream);
   int rc = post_launch(h, "prep kernels");
   if (rc) return rc;
   int err = 0;
@@ -619,9 +619,8 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
     h->launches += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, st); STAGE(4);
     h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, st); STAGE(5);
     rc = post_launch(h, "Jacobian sweep"); if (rc) return rc;
-    if (h->use_build2) {
-      h->launches += launch_build2(D, P, h->b2_G, h->b2_NW, h->max_frames, h->any_ex, false, st);
-      h->launches += launch_build_cam(D, h->max_prior_n, st);
+    if (h->use_build3) {
+      h->launches += launch_build3(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->any_ex, h->max_prior_n, st);
     } else {
       h->launches += launch_build(D, P, h->max_prior_n, st);
     }
@@ -631,9 +630,9 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
       rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc;
     }
     STAGE(6);
-    h->launches += launch_chol(D, P, h->max_d, h->packed_limit, st); STAGE(7);
+    h->launches += launch_chol(D, P, h->max_d, h->packed_limit, h->use_build3, st); STAGE(7);
     rc = post_launch(h, "chol"); if (rc) return rc;
-    if (h->use_build2) h->launches += launch_build2(D, P, h->b2_G, h->b2_NW, h->max_frames, h->any_ex, true, st);
+    if (h->use_build3) h->launches += launch_back3(D, h->dev.base + h->o_b3, h->b3, st);
     else h->launches += launch_backsub(D, P, st);
     STAGE(8);
     rc = post_launch(h, "backsub"); if (rc) return rc;

@@ -1,0 +1,716 @@
+// uvs_build3.cu — normal equations + Schur complement + back-substitution for the reference's window
+// size (<= 12 six-wide camera blocks: 11 poses + extrinsic, no td): the production path.
+//
+// Same algebra as uvs_build.cu (Ceres SPARSE_SCHUR restated), organised so that no lane is idle and no
+// atomics touch the Hessian:
+//
+//   k_core_points / k_core_lines   one THREAD per landmark: eliminates the landmark block and writes a compact
+//        "stash": Y = W (E + D^2)^-1/2 (6 values per camera block of the landmark; 6x4 per line observation),
+//        z = (E + D^2)^-1/2 g, Jacobi scale, LM diagonal.   W (E+D^2)^-1 W^T = Y Y^T,  W (E+D^2)^-1 g = Y z.
+//   k_window_system                one CTA per window:
+//        (1) direct terms  sum_f J_a^T J_b  per camera-block pair from lists sorted by block pair at upload
+//            (k_prep_direct): a warp owns a pair, lanes own the 6x6 entries, the records are gathered from L2;
+//        (2) Schur terms as a dense rank update  V -= Y Y^T  over all landmark columns, 6x6 register tiles,
+//            Y columns expanded chunk by chunk into shared memory (double buffered);
+//        (3) IMU blocks and the prior, then ONE write of the window's reduced system.
+//   k_back_points / k_back_lines   one thread per landmark: delta_k = -(E+D^2)^-1/2 (z + Y^T delta_c).
+// The model cost change uses  -(g^T y + y^T H y / 2) = (y^T D^2 y - g^T y) / 2  (y solves (H + D^2) y = -g),
+// which needs no Jacobians; k_chol adds the camera part.
+#include "uvs_device.cuh"
+#include "uvs_kernels.h"
+
+namespace uvs {
+
+__device__ __forceinline__ double clamp4(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+__device__ __forceinline__ void atomic_max_nn3(double *addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ int pair_key(int a, int b) { return a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b; }
+__device__ __forceinline__ void unrank_key(int t, int &a, int &b) {
+  int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (i * (i + 1) / 2 > t) i--;
+  while ((i + 1) * (i + 2) / 2 <= t) i++;
+  b = i; a = t - i * (i + 1) / 2;
+}
+
+// warp-aggregated per-window accumulation (threads of a warp usually share the window)
+__device__ __forceinline__ void add_win3(double *acc, int win, bool valid, double v0, double v1, double v2) {
+  const unsigned full = 0xffffffffu;
+  const int w0 = __shfl_sync(full, win, 0);
+  const bool v00 = __shfl_sync(full, (int)valid, 0) != 0;
+  const bool uniform = __all_sync(full, !valid || win == w0) && v00;
+  if (uniform) {
+    double a = valid ? v0 : 0.0, b = valid ? v1 : 0.0, c = valid ? v2 : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(full, a, o); b += __shfl_down_sync(full, b, o); c += __shfl_down_sync(full, c, o); }
+    if ((threadIdx.x & 31) == 0) {
+      double *p = acc + (size_t)w0 * ACC_STRIDE;
+      atomicAdd(p + ACC_MODEL, a); atomicAdd(p + ACC_STEP2, b); atomicAdd(p + ACC_XNORM2, c);
+    }
+  } else if (valid) {
+    double *p = acc + (size_t)win * ACC_STRIDE;
+    atomicAdd(p + ACC_MODEL, v0); atomicAdd(p + ACC_STEP2, v1); atomicAdd(p + ACC_XNORM2, v2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stash layout (B3): points  d[PS]: z, sk, sh, D2, pad(4), Y[blk][6];   i[PI]: nblk, blk[...]
+//                    lines   d[LS]: z(4) s(4) D2(4) Linv(16) pad(4), Y[obs][6][4];  i[LI]: n, blk[...]
+struct Stash {
+  double *pd, *ld;
+  int *pi, *li;
+  int PS, PI, LS, LI;
+};
+
+__global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
+  const int gp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= D.nP) return;
+  if (D.nranks > 1 && (gp % D.nranks) != D.rank) return;
+  const int w = D.pt_win[gp];
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int f0 = D.pt_begin[gp], n = D.pt_end[gp] - f0;
+  int *hi = S.pi + (size_t)gp * S.PI;
+  double *hd = S.pd + (size_t)gp * S.PS;
+  if (n <= 0) { hi[0] = 0; return; }
+  const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
+  const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
+  const double *R = D.rec_proj + (size_t)f0 * REC_PROJ;
+  double colsq = 0.0, gk = 0.0;
+  for (int f = 0; f < n; f++) {
+    const double j0 = R[f * REC_PROJ + 38], j1 = R[f * REC_PROJ + 39];
+    colsq += j0 * j0 + j1 * j1;
+    gk += j0 * R[f * REC_PROJ] + j1 * R[f * REC_PROJ + 1];
+  }
+  double sk;
+  if (!D.ctl[w].have_scale) { sk = 1.0 / (1.0 + sqrt(colsq)); D.scale_pt[gp] = sk; }
+  else sk = D.scale_pt[gp];
+  const double Et = sk * sk * colsq;
+  const double D2 = clamp4(Et, P.min_lm_diag, P.max_lm_diag) / D.ctl[w].radius;
+  const double sh = rsqrt(Et + D2);
+  const double ysc = sk * sh;
+  double wa[6] = {0, 0, 0, 0, 0, 0}, we[6] = {0, 0, 0, 0, 0, 0};
+  double *Y = hd + 8;
+  for (int f = 0; f < n; f++) {
+    const double *r = R + f * REC_PROJ;
+    const double j0 = r[38], j1 = r[39];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      wa[c] += r[2 + c] * j0 + r[8 + c] * j1;
+      Y[6 * (1 + f) + c] = ysc * (r[14 + c] * j0 + r[20 + c] * j1);
+      if (ex) we[c] += r[26 + c] * j0 + r[32 + c] * j1;
+    }
+    hi[2 + f] = D.proj_idx[f0 + f].y - fo;
+  }
+#pragma unroll
+  for (int c = 0; c < 6; c++) Y[c] = ysc * wa[c];
+  hi[1] = D.proj_idx[f0].x - fo;
+  int nblk = n + 1;
+  if (ex) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) Y[6 * nblk + c] = ysc * we[c];
+    hi[1 + nblk] = F;
+    nblk++;
+  }
+  hi[0] = nblk;
+  hd[0] = sk * gk * sh; hd[1] = sk; hd[2] = sh; hd[3] = D2;
+  atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fabs(gk));
+}
+
+__global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
+  const int gl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gl >= D.nL) return;
+  if (D.nranks > 1 && (gl % D.nranks) != D.rank) return;
+  const int w = D.ln_win[gl];
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int f0 = D.ln_begin[gl], n = D.ln_end[gl] - f0;
+  int *hi = S.li + (size_t)gl * S.LI;
+  double *hd = S.ld + (size_t)gl * S.LS;
+  if (n <= 0) { hi[0] = 0; return; }
+  const int fo = D.frame_off[w];
+  double E[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
+  for (int f = 0; f < n; f++) {
+    const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
+#pragma unroll
+    for (int row = 0; row < 2; row++) {
+      const double a0 = r[14 + 4 * row], a1 = r[15 + 4 * row], a2 = r[16 + 4 * row], a3 = r[17 + 4 * row], rr = r[row];
+      E[0] += a0 * a0; E[1] += a0 * a1; E[2] += a0 * a2; E[3] += a0 * a3; E[4] += a1 * a1; E[5] += a1 * a2; E[6] += a1 * a3;
+      E[7] += a2 * a2; E[8] += a2 * a3; E[9] += a3 * a3;
+      g[0] += a0 * rr; g[1] += a1 * rr; g[2] += a2 * rr; g[3] += a3 * rr;
+    }
+    const int vi = D.line_idx4[f0 + f].w;
+    if (vi >= 0) {
+      const double *q = D.rec_vp + (size_t)vi * REC_VP;
+      const double a0 = q[7], a1 = q[8], a2 = q[9], a3 = q[10], rr = q[0];
+      E[0] += a0 * a0; E[1] += a0 * a1; E[2] += a0 * a2; E[3] += a0 * a3; E[4] += a1 * a1; E[5] += a1 * a2; E[6] += a1 * a3;
+      E[7] += a2 * a2; E[8] += a2 * a3; E[9] += a3 * a3;
+      g[0] += a0 * rr; g[1] += a1 * rr; g[2] += a2 * rr; g[3] += a3 * rr;
+    }
+  }
+  double s[4];
+  const double Ed[4] = {E[0], E[4], E[7], E[9]};
+  if (!D.ctl[w].have_scale) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) { s[c] = 1.0 / (1.0 + sqrt(Ed[c])); D.scale_ln[4 * (size_t)gl + c] = s[c]; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; c++) s[c] = D.scale_ln[4 * (size_t)gl + c];
+  }
+  // M = D_s E D_s + D^2 (lower), Cholesky, inverse of the factor
+  const double radius = D.ctl[w].radius;
+  double M[4][4], D2[4];
+  M[0][0] = s[0] * s[0] * E[0]; M[1][0] = s[1] * s[0] * E[1]; M[2][0] = s[2] * s[0] * E[2]; M[3][0] = s[3] * s[0] * E[3];
+  M[1][1] = s[1] * s[1] * E[4]; M[2][1] = s[2] * s[1] * E[5]; M[3][1] = s[3] * s[1] * E[6];
+  M[2][2] = s[2] * s[2] * E[7]; M[3][2] = s[3] * s[2] * E[8]; M[3][3] = s[3] * s[3] * E[9];
+#pragma unroll
+  for (int c = 0; c < 4; c++) { D2[c] = clamp4(M[c][c], P.min_lm_diag, P.max_lm_diag) / radius; M[c][c] += D2[c]; }
+  double L[4][4], Li[4][4];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    double dj = M[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) dj -= L[j][k] * L[j][k];
+    if (!(dj > 0.0)) ok = false;
+    const double id = rsqrt(dj);
+    L[j][j] = dj * id;
+#pragma unroll
+    for (int i = j + 1; i < 4; i++) {
+      double t = M[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+      L[i][j] = t * id;
+    }
+  }
+  if (!ok) { atomicAdd(D.acc + (size_t)w * ACC_STRIDE + ACC_FAIL, 1.0); hi[0] = 0; return; }
+#pragma unroll
+  for (int col = 0; col < 4; col++)
+#pragma unroll
+    for (int i = col; i < 4; i++) {
+      double t = (i == col) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = col; k < i; k++) t -= L[i][k] * Li[k][col];
+      Li[i][col] = t / L[i][i];
+    }
+  // z = L^-1 (D_s g)
+  double z[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k <= c; k++) t += Li[c][k] * s[k] * g[k];
+    z[c] = t;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) { hd[c] = z[c]; hd[4 + c] = s[c]; hd[8 + c] = D2[c]; }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) hd[12 + 4 * i + k] = k <= i ? Li[i][k] : 0.0;
+  // Y_f = (Jp^T Jl D_s) L^-T
+  double *Y = hd + 32;
+  for (int f = 0; f < n; f++) {
+    const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
+    const int4 ix = D.line_idx4[f0 + f];
+    const double *q = ix.w >= 0 ? D.rec_vp + (size_t)ix.w * REC_VP : nullptr;
+    double jl[3][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { jl[0][c] = r[14 + c] * s[c]; jl[1][c] = r[18 + c] * s[c]; jl[2][c] = q ? q[7 + c] * s[c] : 0.0; }
+#pragma unroll
+    for (int p = 0; p < 6; p++) {
+      const double a0 = r[2 + p], a1 = r[8 + p], a2 = q ? q[1 + p] : 0.0;
+      double W4[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k <= c; k++) t += W4[k] * Li[c][k];
+        Y[f * 24 + p * 4 + c] = t;
+      }
+    }
+    hi[1 + f] = ix.x - fo;
+  }
+  hi[0] = n;
+  atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3]))));
+}
+
+// ------------------------------------------------------------------------------------------------
+// back-substitution, one thread per landmark
+__global__ void __launch_bounds__(128) k_back_points(Dev D, Stash S) {
+  const int gp = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = gp < D.nP && (D.nranks <= 1 || (gp % D.nranks) == D.rank);
+  int w = 0;
+  if (valid) {
+    w = D.pt_win[gp];
+    valid = (D.ctl[w].state & WS_ACTIVE) && D.acc[(size_t)w * ACC_STRIDE + ACC_FAIL] == 0.0;
+  }
+  double mc = 0.0, s2 = 0.0, x2 = 0.0;
+  if (valid) {
+    const int *hi = S.pi + (size_t)gp * S.PI;
+    const double *hd = S.pd + (size_t)gp * S.PS;
+    const int nblk = hi[0], cur = D.cur[w];
+    const double lam = D.inv_depth[cur][gp];
+    double dk = 0.0;
+    if (nblk > 0) {
+      const double *dl = D.delta_cam + D.cam_off[w];
+      double u = 0.0;
+      for (int b = 0; b < nblk; b++) {
+        const double *y = hd + 8 + 6 * b, *d = dl + 15 * hi[1 + b];
+#pragma unroll
+        for (int c = 0; c < 6; c++) u += y[c] * d[c];
+      }
+      const double z = hd[0], sk = hd[1], sh = hd[2], D2 = hd[3];
+      const double yk = -sh * (z + u);
+      dk = sk * yk;
+      mc = 0.5 * (D2 * yk * yk - (z / sh) * yk);
+    }
+    D.delta_pt[gp] = dk;
+    D.inv_depth[cur ^ 1][gp] = lam + dk;
+    s2 = dk * dk; x2 = lam * lam;
+  }
+  add_win3(D.acc, w, valid, mc, s2, x2);
+}
+
+__global__ void __launch_bounds__(128) k_back_lines(Dev D, Stash S) {
+  const int gl = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = gl < D.nL && (D.nranks <= 1 || (gl % D.nranks) == D.rank);
+  int w = 0;
+  if (valid) {
+    w = D.ln_win[gl];
+    valid = (D.ctl[w].state & WS_ACTIVE) && D.acc[(size_t)w * ACC_STRIDE + ACC_FAIL] == 0.0;
+  }
+  double mc = 0.0, s2 = 0.0, x2 = 0.0;
+  if (valid) {
+    const int *hi = S.li + (size_t)gl * S.LI;
+    const double *hd = S.ld + (size_t)gl * S.LS;
+    const int n = hi[0], cur = D.cur[w];
+    double dk[4] = {0, 0, 0, 0};
+    if (n > 0) {
+      const double *dl = D.delta_cam + D.cam_off[w];
+      double u[4] = {0, 0, 0, 0};
+      for (int f = 0; f < n; f++) {
+        const double *y = hd + 32 + 24 * f, *d = dl + 15 * hi[1 + f];
+#pragma unroll
+        for (int p = 0; p < 6; p++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) u[c] += y[p * 4 + c] * d[p];
+      }
+      // y_k = -L^-T (z + u)
+      double t[4], yk[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) t[c] = hd[c] + u[c];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = c; k < 4; k++) a += hd[12 + 4 * k + c] * t[k];
+        yk[c] = -a;
+      }
+      // g~^T y_k = (L z)^T y_k = -z^T (z + u)
+      double gy = 0.0, dy = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) { gy -= hd[c] * t[c]; dy += hd[8 + c] * yk[c] * yk[c]; dk[c] = hd[4 + c] * yk[c]; }
+      mc = 0.5 * (dy - gy);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double x = D.ortho[cur][4 * (size_t)gl + c];
+      D.delta_ln[4 * (size_t)gl + c] = dk[c];
+      D.ortho[cur ^ 1][4 * (size_t)gl + c] = x + dk[c];
+      s2 += dk[c] * dk[c]; x2 += x * x;
+    }
+  }
+  add_win3(D.acc, w, valid, mc, s2, x2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct-term lists: per window, items {factor, kind} sorted (stable) by camera-block pair.
+//   kinds: 0 proj (i,i)  1 proj (j,j)  2 proj (i,j) i<j  3 proj (j,i) j<i  4 proj (i,ex)  5 proj (j,ex)  6 proj (ex,ex)
+//          7 line (j,j)  8 vp (j,j)
+constexpr int KMAX = 80;   // >= 12 * 13 / 2 + 1 keys per window
+
+struct DirectLists {
+  int2 *items;      // [6 nProj + nLobs + nVobs]
+  int *off;         // [B][KMAX]  start of every key's list (exclusive scan; off[key+1] is its end)
+};
+
+__device__ __forceinline__ long long direct_base(const Dev &D, int w) {
+  return 6LL * D.proj_off[w] + D.lobs_off[w] + D.vobs_off[w];
+}
+
+__global__ void __launch_bounds__(128) k_prep_direct(Dev D, DirectLists L) {
+  __shared__ int cnt_all[4][KMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 4 + warp;
+  if (w >= D.B) return;
+  int *cnt = cnt_all[warp];
+  const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
+  const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
+  const int j0 = D.proj_off[w], j1 = D.proj_off[w + 1], a0 = D.lobs_off[w], a1 = D.lobs_off[w + 1], v0 = D.vobs_off[w], v1 = D.vobs_off[w + 1];
+  int2 *items = L.items + direct_base(D, w);
+  int *off = L.off + (size_t)w * KMAX;
+  const unsigned full = 0xffffffffu;
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 0) { for (int k = lane; k < KMAX; k += 32) cnt[k] = 0; }
+    else {
+      // exclusive scan of the counts -> cursors
+      if (lane == 0) { int run = 0; for (int k = 0; k < KMAX; k++) { const int c = cnt[k]; cnt[k] = run; off[k] = run; run += c; } }
+    }
+    __syncwarp();
+    // emit(key, factor, kind): pass 0 counts, pass 1 scatters stably in (slot, factor) order
+    auto emit = [&](bool active, int key, int fidx, int kind) {
+      if (pass == 0) { if (active) atomicAdd(&cnt[key], 1); return; }
+      const unsigned act = __ballot_sync(full, active);
+      if (active) {
+        const unsigned same = __match_any_sync(act, key);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        const int pos = cnt[key] + rank;
+        items[pos] = make_int2(fidx, kind);
+      }
+      __syncwarp();
+      if (active) {
+        const unsigned same = __match_any_sync(act, key);
+        if ((same & ((1u << lane) - 1u)) == 0) cnt[key] += __popc(same);
+      }
+      __syncwarp();
+    };
+    for (int slot = 0; slot < (ex ? 6 : 3); slot++) {
+      for (int base = j0; base < j1; base += 32) {
+        const int f = base + lane;
+        const bool act = f < j1;
+        int key = 0, kind = 0;
+        if (act) {
+          const int4 ix = D.proj_idx[f];
+          const int i = ix.x - fo, j = ix.y - fo;
+          if (slot == 0) { key = pair_key(i, i); kind = 0; }
+          else if (slot == 1) { key = pair_key(j, j); kind = 1; }
+          else if (slot == 2) { key = pair_key(i, j); kind = i < j ? 2 : 3; }
+          else if (slot == 3) { key = pair_key(i, F); kind = 4; }
+          else if (slot == 4) { key = pair_key(j, F); kind = 5; }
+          else { key = pair_key(F, F); kind = 6; }
+        }
+        emit(act, key, f, kind);
+      }
+    }
+    for (int base = a0; base < a1; base += 32) {
+      const int f = base + lane;
+      const bool act = f < a1;
+      int key = 0;
+      if (act) { const int j = D.line_idx4[f].x - fo; key = pair_key(j, j); }
+      emit(act, key, f, 7);
+    }
+    for (int base = v0; base < v1; base += 32) {
+      const int f = base + lane;
+      const bool act = f < v1;
+      int key = 0;
+      if (act) { const int j = D.vp_idx4[f].x - fo; key = pair_key(j, j); }
+      emit(act, key, f, 8);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int WT = 256;       // threads of k_window_system
+constexpr int CH = 32;        // landmark columns per chunk
+constexpr int GEMM_WARPS = 3; // warps 0..2 run the rank update (up to 78 pair tiles + 12 gradient tiles <= 96 threads)
+
+// upper-triangle unranking of a 6x6 symmetric block: e in [0,21) -> (p <= q)
+__constant__ unsigned char c_sym_p[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__constant__ unsigned char c_sym_q[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+__global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectLists L, int max_prior_n) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.x;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
+  const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
+  const int nb = F + (ex ? 1 : 0), m = 6 * nb, mp = m + 2;   // Y column stride: m values + z + pad
+  const int nkeys = nb * (nb + 1) / 2;
+  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+  const bool lead = D.nranks <= 1 || D.rank == 0;
+  // shared layout: V[m*m] gdir[m] gsch[m] csq[m] Ych[2][CH][mp] cmap(int)[max_prior_n]
+  double *V = sm, *gdir = V + (size_t)m * m, *gsch = gdir + m, *csq = gsch + m, *Ych = csq + m;
+  int *cmap = reinterpret_cast<int *>(Ych + (size_t)2 * CH * mp);
+  for (int e = tid; e < m * m + 3 * m; e += WT) V[e] = 0.0;
+  __syncthreads();
+
+  // ---- (1) direct terms: a warp owns a block pair, lanes own entries
+  {
+    const int2 *items = L.items + direct_base(D, w);
+    const int *off = L.off + (size_t)w * KMAX;
+    const bool td42 = D.estimate_td != 0;
+    (void)td42;
+    for (int key = warp; key < nkeys; key += WT / 32) {
+      int a, b;
+      unrank_key(key, a, b);
+      const int i0 = off[key], i1 = off[key + 1];
+      if (a == b) {
+        // 21 symmetric entries + 6 gradient entries
+        int p = 0, q = 0;
+        const bool isg = lane >= 21;
+        if (lane < 21) { p = c_sym_p[lane]; q = c_sym_q[lane]; } else if (lane < 27) { p = lane - 21; }
+        double acc = 0.0;
+        if (lane < 27) {
+          for (int it = i0; it < i1; it++) {
+            const int2 item = items[it];
+            const double *rec; int baseA, nrows, stride;
+            if (item.y <= 6) { rec = D.rec_proj + (size_t)item.x * REC_PROJ; nrows = 2; stride = 6; baseA = item.y == 0 ? 2 : (item.y == 1 ? 14 : 26); }
+            else if (item.y == 7) { rec = D.rec_line + (size_t)item.x * REC_LINE; nrows = 2; stride = 6; baseA = 2; }
+            else { rec = D.rec_vp + (size_t)item.x * REC_VP; nrows = 1; stride = 0; baseA = 1; }
+            double t = rec[baseA + p] * (isg ? rec[0] : rec[baseA + q]);
+            if (nrows == 2) t += rec[baseA + stride + p] * (isg ? rec[1] : rec[baseA + stride + q]);
+            acc += t;
+          }
+          if (!isg) { V[(6 * a + p) * m + 6 * a + q] = acc; V[(6 * a + q) * m + 6 * a + p] = acc; if (p == q) csq[6 * a + p] = acc; }
+          else gdir[6 * a + p] = acc;
+        }
+      } else {
+        // off-diagonal pair: 36 entries, lanes 0..31 + a second entry on lanes 0..3
+        const int p0 = lane / 6, q0 = lane - 6 * p0, q1 = 2 + lane;   // second entry: (5, 2 + lane)
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int it = i0; it < i1; it++) {
+          const int2 item = items[it];
+          const double *rec = D.rec_proj + (size_t)item.x * REC_PROJ;
+          int baseA, baseB;
+          if (item.y == 2) { baseA = 2; baseB = 14; } else if (item.y == 3) { baseA = 14; baseB = 2; }
+          else if (item.y == 4) { baseA = 2; baseB = 26; } else { baseA = 14; baseB = 26; }
+          acc0 += rec[baseA + p0] * rec[baseB + q0] + rec[baseA + 6 + p0] * rec[baseB + 6 + q0];
+          if (lane < 4) acc1 += rec[baseA + 5] * rec[baseB + q1] + rec[baseA + 11] * rec[baseB + 6 + q1];
+        }
+        V[(6 * a + p0) * m + 6 * b + q0] = acc0;
+        if (lane < 4) V[(6 * a + 5) * m + 6 * b + q1] = acc1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- (2) Schur terms: V -= Y Y^T, gsch = Y z, over all landmark columns
+  {
+    const int p0 = D.point_off[w], np = D.point_off[w + 1] - p0, l0 = D.line_off[w], nl = D.line_off[w + 1] - l0;
+    const int ncols = np + 4 * nl, nchunks = (ncols + CH - 1) / CH;
+    // GEMM tile of this thread
+    int ta = -1, tb = -1;      // block pair (ta <= tb), or gradient tile (ta, -2)
+    if (tid < nkeys) unrank_key(tid, ta, tb);
+    else if (tid < nkeys + nb) { ta = tid - nkeys; tb = -2; }
+    double acc[6][6];
+#pragma unroll
+    for (int p = 0; p < 6; p++)
+#pragma unroll
+      for (int q = 0; q < 6; q++) acc[p][q] = 0.0;
+    // expansion of chunk c into buffer buf by the threads [t0, t0 + nt)
+    auto expand = [&](int c, int buf, int t0, int nt) {
+      double *Yb = Ych + (size_t)buf * CH * mp;
+      const int c0 = c * CH, c1 = min(ncols, c0 + CH);
+      const int t = tid - t0;
+      for (int e = t; e < (c1 - c0) * mp; e += nt) Yb[e] = 0.0;
+      // the zero fill and the scatter below touch the same entries: order them inside the expanding group
+      if (nt == WT) __syncthreads(); else asm volatile("bar.sync 1, %0;" ::"r"(nt));
+      for (int e = t; e < (c1 - c0) * 12; e += nt) {     // (column, block slot)
+        const int cc = e / 12, slot = e - 12 * cc, col = c0 + cc;
+        double *y = Yb + (size_t)cc * mp;
+        if (col < np) {
+          const int gp = p0 + col;
+          if (D.nranks > 1 && (gp % D.nranks) != D.rank) continue;
+          const int *hi = S.pi + (size_t)gp * S.PI;
+          const double *hd = S.pd + (size_t)gp * S.PS;
+          const int nblk = hi[0];
+          if (slot < nblk) {
+            const int blk = hi[1 + slot];
+#pragma unroll
+            for (int k = 0; k < 6; k++) y[6 * blk + k] = hd[8 + 6 * slot + k];
+          }
+          if (slot == 0 && nblk > 0) y[m] = hd[0];
+        } else {
+          const int li = (col - np) >> 2, sub = (col - np) & 3, gl = l0 + li;
+          if (D.nranks > 1 && (gl % D.nranks) != D.rank) continue;
+          const int *hi = S.li + (size_t)gl * S.LI;
+          const double *hd = S.ld + (size_t)gl * S.LS;
+          const int n = hi[0];
+          if (slot < n) {
+            const int blk = hi[1 + slot];
+#pragma unroll
+            for (int k = 0; k < 6; k++) y[6 * blk + k] = hd[32 + 24 * slot + 4 * k + sub];
+          }
+          if (slot == 0 && n > 0) y[m] = hd[sub];
+        }
+      }
+    };
+    expand(0, 0, 0, WT);
+    __syncthreads();
+    for (int c = 0; c < nchunks; c++) {
+      if (warp >= GEMM_WARPS) {
+        if (c + 1 < nchunks) expand(c + 1, (c + 1) & 1, GEMM_WARPS * 32, WT - GEMM_WARPS * 32);
+      } else if (ta >= 0) {
+        const double *Yb = Ych + (size_t)(c & 1) * CH * mp;
+        const int c1 = min(ncols, (c + 1) * CH) - c * CH;
+        if (tb >= 0) {
+          for (int cc = 0; cc < c1; cc++) {
+            const double *y = Yb + (size_t)cc * mp;
+            double ya[6], yb[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { ya[k] = y[6 * ta + k]; yb[k] = y[6 * tb + k]; }
+#pragma unroll
+            for (int p = 0; p < 6; p++)
+#pragma unroll
+              for (int q = 0; q < 6; q++) acc[p][q] += ya[p] * yb[q];
+          }
+        } else {
+          for (int cc = 0; cc < c1; cc++) {
+            const double *y = Yb + (size_t)cc * mp;
+            const double zz = y[m];
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc[0][k] += y[6 * ta + k] * zz;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (ta >= 0 && tb >= 0) {
+#pragma unroll
+      for (int p = 0; p < 6; p++)
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          V[(6 * ta + p) * m + 6 * tb + q] -= acc[p][q];
+        }
+    } else if (ta >= 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) gsch[6 * ta + k] = acc[0][k];
+    }
+  }
+  __syncthreads();
+
+  // ---- (3) write the window's system (cleared by k_step / k_solve_init): pose blocks from V, then IMU, then prior
+  double *Sg = D.Smat + D.S_off[w];
+  for (int e = tid; e < m * m; e += WT) {
+    const int r = e / m, c = e - r * m;
+    if (r > c) continue;
+    const int a = r / 6, b = c / 6;
+    const int row = (a < F ? 15 * a : 15 * F) + (r - 6 * a), col = (b < F ? 15 * b : 15 * F) + (c - 6 * b);
+    if (D.nranks > 1) atomicAdd(Sg + (size_t)row * d + col, V[e]); else Sg[(size_t)row * d + col] += V[e];
+  }
+  for (int e = tid; e < m; e += WT) {
+    const int a = e / 6;
+    const int idx = co + (a < F ? 15 * a : 15 * F) + (e - 6 * a);
+    if (D.nranks > 1) { atomicAdd(D.gS + idx, gdir[e] - gsch[e]); atomicAdd(D.gfull + idx, gdir[e]); atomicAdd(D.colsq_cam + idx, csq[e]); }
+    else { D.gS[idx] += gdir[e] - gsch[e]; D.gfull[idx] += gdir[e]; D.colsq_cam[idx] += csq[e]; }
+  }
+  if (!lead) return;
+  __syncthreads();
+  // IMU factors: 30x30 blocks; factors of even / odd frame index do not overlap
+  for (int parity = 0; parity < 2; parity++) {
+    for (int f = D.imu_off[w]; f < D.imu_off[w + 1]; f++) {
+      const int fi = D.imu_idx[f].x - fo;
+      if ((fi & 1) != parity) continue;
+      const int c0 = 15 * fi;
+      const double *R = D.rec_imu + (size_t)f * REC_IMU, *J = R + 15;
+      for (int e = tid; e < 900; e += WT) {
+        const int p = e / 30, q = e - 30 * p;
+        if (p > q) continue;
+        double h = 0.0;
+#pragma unroll
+        for (int i = 0; i < 15; i++) h += J[i * 30 + p] * J[i * 30 + q];
+        Sg[(size_t)(c0 + p) * d + c0 + q] += h;
+      }
+      if (tid < 30) {
+        double g = 0.0, q2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 15; i++) { const double j = J[i * 30 + tid]; g += j * R[i]; q2 += j * j; }
+        D.gfull[co + c0 + tid] += g; D.gS[co + c0 + tid] += g; D.colsq_cam[co + c0 + tid] += q2;
+      }
+    }
+    __syncthreads();
+  }
+  // prior: H += J0^T J0 (precomputed), g += J0^T r
+  const int n = D.prior_off[w + 1] - D.prior_off[w];
+  if (n > 0) {
+    for (int c = tid; c < n; c += WT) cmap[c] = -1;
+    __syncthreads();
+    for (int b = D.pblk_off[w] + tid; b < D.pblk_off[w + 1]; b += WT) {
+      const int kind = D.pblk_kind[b], cam = D.pblk_cam[b], col = D.pblk_col[b];
+      const int ls = (kind == 0 || kind == 2) ? 6 : (kind == 1 ? 9 : 1);
+      if (cam >= 0) for (int c = 0; c < ls; c++) cmap[col + c] = cam + c;
+    }
+    __syncthreads();
+    const double *H = D.prior_H + D.priorJ_off[w], *J0 = D.prior_J + D.priorJ_off[w], *r = D.rec_prior + D.prior_off[w];
+    for (int e = tid; e < n * n; e += WT) {
+      const int p = e / n, q = e - p * n;
+      const int cp = cmap[p], cq = cmap[q];
+      if (cp < 0 || cq < 0 || cp > cq) continue;
+      Sg[(size_t)cp * d + cq] += H[e];
+    }
+    // g += J0^T r: warp per column group, coalesced over columns
+    for (int p = tid; p < n; p += WT) {
+      const int cp = cmap[p];
+      if (cp < 0) continue;
+      double g = 0.0;
+      for (int i = 0; i < n; i++) g += J0[(size_t)i * n + p] * r[i];
+      D.gfull[co + cp] += g; D.gS[co + cp] += g; D.colsq_cam[co + cp] += H[(size_t)p * n + p];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Build3Ctx {
+  Stash S;
+  DirectLists L;
+};
+
+size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay) {
+  const int nbmax = max_frames + (any_ex ? 1 : 0);
+  lay->PS = 8 + 6 * (nbmax + 1); lay->PI = nbmax + 4; lay->LS = 32 + 24 * max_frames; lay->LI = max_frames + 2;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t o = 0;
+  lay->o_pd = o; o += al((size_t)D.nP * lay->PS * sizeof(double));
+  lay->o_ld = o; o += al((size_t)D.nL * lay->LS * sizeof(double));
+  lay->o_pi = o; o += al((size_t)D.nP * lay->PI * sizeof(int));
+  lay->o_li = o; o += al((size_t)D.nL * lay->LI * sizeof(int));
+  lay->o_items = o; o += al(((size_t)6 * D.nProj + D.nLobs + D.nVobs + 1) * sizeof(int2));
+  lay->o_off = o; o += al((size_t)D.B * KMAX * sizeof(int));
+  return o;
+}
+
+static void make_ctx(char *base, const Build3Layout &lay, Build3Ctx &c) {
+  c.S.pd = (double *)(base + lay.o_pd); c.S.ld = (double *)(base + lay.o_ld);
+  c.S.pi = (int *)(base + lay.o_pi); c.S.li = (int *)(base + lay.o_li);
+  c.S.PS = lay.PS; c.S.PI = lay.PI; c.S.LS = lay.LS; c.S.LI = lay.LI;
+  c.L.items = (int2 *)(base + lay.o_items); c.L.off = (int *)(base + lay.o_off);
+}
+
+static inline int cdiv3(int a, int b) { return (a + b - 1) / b; }
+
+int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st) {
+  Build3Ctx c; make_ctx(base, lay, c);
+  k_prep_direct<<<cdiv3(D.B, 4), 128, 0, st>>>(D, c.L);
+  return 1;
+}
+
+size_t build3_smem(int max_frames, bool any_ex, int max_prior_n) {
+  const int nb = max_frames + (any_ex ? 1 : 0), m = 6 * nb, mp = m + 2;
+  return ((size_t)m * m + 3 * m + (size_t)2 * CH * mp) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
+}
+
+int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
+                  cudaStream_t st) {
+  Build3Ctx c; make_ctx(base, lay, c);
+  int n = 0;
+  if (D.nP) { k_core_points<<<cdiv3(D.nP, 128), 128, 0, st>>>(D, P, c.S); n++; }
+  if (D.nL) { k_core_lines<<<cdiv3(D.nL, 128), 128, 0, st>>>(D, P, c.S); n++; }
+  const size_t smem = build3_smem(max_frames, any_ex, max_prior_n);
+  static size_t raised = 0;
+  if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
+  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, c.L, max_prior_n);
+  return n + 1;
+}
+
+int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st) {
+  Build3Ctx c; make_ctx(base, lay, c);
+  int n = 0;
+  if (D.nP) { k_back_points<<<cdiv3(D.nP, 128), 128, 0, st>>>(D, c.S); n++; }
+  if (D.nL) { k_back_lines<<<cdiv3(D.nL, 128), 128, 0, st>>>(D, c.S); n++; }
+  return n;
+}
+
+}  // namespace uvs

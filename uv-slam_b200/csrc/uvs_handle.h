@@ -8,6 +8,7 @@
 
 #include "../../include/uvs.h"
 #include "uvs_device.cuh"
+#include "uvs_kernels.h"
 
 namespace uvs {
 
@@ -72,7 +73,9 @@ struct UvsHandle {
   size_t o_cur = 0, cur_bytes = 0;
   int profiling = 0;
   int max_frames = 0; bool any_ex = false;
-  bool use_build2 = false; int b2_G = 1, b2_NW = 8;   // atomics-free landmark path (uvs_build2.cu)
+  bool use_build3 = false;                    // atomics-free landmark path (uvs_build3.cu)
+  uvs::Build3Layout b3{};
+  size_t o_b3 = 0;
   std::vector<cudaEvent_t> stage_ev;          // (UVS_N_STAGES + 1) events per LM iteration
   float stage_ms[UVS_N_STAGES] = {0};
   int stage_iters = 0;

@@ -29,16 +29,24 @@ int launch_prior(const Dev &D, int max_prior_n, bool jac_phase, int mode, int ca
 int launch_build(const Dev &D, const Params &P, int max_prior_n, cudaStream_t st);
 int launch_backsub(const Dev &D, const Params &P, cudaStream_t st);
 
-// uvs_build2.cu — atomics-free path for windows of <= 12 six-wide camera blocks without td
-size_t build2_smem_bytes(int max_frames, bool any_ex, int NW, bool back);
-int launch_build2(const Dev &D, const Params &P, int G, int NW, int max_frames, bool any_ex, bool back, cudaStream_t st);
+// uvs_build3.cu — atomics-free landmark path for windows of <= 12 six-wide camera blocks without td
+struct Build3Layout {
+  int PS, PI, LS, LI;
+  size_t o_pd, o_ld, o_pi, o_li, o_items, o_off;
+};
+size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay);
+size_t build3_smem(int max_frames, bool any_ex, int max_prior_n);
+int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st);
+int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
+                  cudaStream_t st);
+int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st);
 int launch_build_cam(const Dev &D, int max_prior_n, cudaStream_t st);
 
 // uvs_solve.cu
 int chol_packed_limit(size_t max_smem);
 size_t chol_max_dynamic_smem(size_t optin_bytes);
 int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st);
-int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, cudaStream_t st);
+int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool mc_identity, cudaStream_t st);
 int launch_step(const Dev &D, const Params &P, cudaStream_t st);
 int launch_finish(const Dev &D, cudaStream_t st);
 int launch_count_active(const Dev &D, int *out, cudaStream_t st);

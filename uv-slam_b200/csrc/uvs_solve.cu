@@ -78,10 +78,11 @@ __device__ __forceinline__ void unrank_lower(int t, int &I, int &J) {
 }
 
 template <bool kPacked>
-__device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) {
+__device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, bool mc_identity) {
   __shared__ double red[CT / 32];
   __shared__ int s_flag;
   __shared__ int s_cmap[MAX_PRIOR_COLS];
+  double *vec_y = D.gS + D.cam_off[w];   // y (scaled step) parked in the consumed reduced-gradient buffer
   WinCtl &ctl = D.ctl[w];
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   const int F = D.frame_off[w + 1] - D.frame_off[w];
@@ -327,7 +328,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
   const int cur = D.cur[w];
   const int fo = D.frame_off[w];
   double step2 = 0.0, x2 = 0.0;
-  for (int c = tid; c < d; c += CT) { const double dl = scale[c] * vec[c]; D.delta_cam[co + c] = dl; }
+  for (int c = tid; c < d; c += CT) { const double yv = vec[c]; vec_y[c] = yv; D.delta_cam[co + c] = scale[c] * yv; }
   __syncthreads();
   const double *dl = D.delta_cam + co;
   const bool lead = D.nranks <= 1 || D.rank == 0;
@@ -381,7 +382,15 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
     __syncthreads();
   }
   double mc = 0.0;
-  if (lead) {
+  if (lead && mc_identity) {
+    // -(g^T y + y^T H y / 2) = (y^T D^2 y - g^T y) / 2 for the solution of (H + D^2) y = -g: camera part
+    for (int c = tid; c < d; c += CT) {
+      const double y = vec_y[c];
+      const double h = scale[c] * scale[c] * colsq[c];
+      mc += 0.5 * (clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius * y * y - scale[c] * gfull[c] * y);
+    }
+    mc = -mc;   // accumulated below as -mc
+  } else if (lead) {
     const int warp = tid >> 5, lane = tid & 31;
     for (int f = D.imu_off[w] + warp; f < D.imu_off[w + 1]; f += CT / 32) {
       const double *R = D.rec_imu + (size_t)f * REC_IMU;
@@ -413,7 +422,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem) 
   }
 }
 
-__global__ void __launch_bounds__(CT) k_chol(Dev D, Params P, int packed_limit) {
+__global__ void __launch_bounds__(CT) k_chol(Dev D, Params P, int packed_limit, int mc_identity) {
   extern __shared__ double smem[];
   const int w = blockIdx.x;
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
@@ -422,8 +431,8 @@ __global__ void __launch_bounds__(CT) k_chol(Dev D, Params P, int packed_limit) 
     return;
   }
   const int d = D.cam_off[w + 1] - D.cam_off[w];
-  if (d <= packed_limit) chol_window<true>(D, P, w, smem);
-  else chol_window<false>(D, P, w, smem);
+  if (d <= packed_limit) chol_window<true>(D, P, w, smem, mc_identity != 0);
+  else chol_window<false>(D, P, w, smem, mc_identity != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -526,10 +535,10 @@ int chol_packed_limit(size_t max_smem) {
 
 int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st) { k_solve_init<<<D.B, CT, 0, st>>>(D, P); return 1; }
 
-int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, cudaStream_t st) {
+int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool mc_identity, cudaStream_t st) {
   const int dd = max_d <= packed_limit ? max_d : packed_limit;
   const size_t smem = chol_smem_bytes(dd);
-  k_chol<<<D.B, CT, smem, st>>>(D, P, packed_limit);
+  k_chol<<<D.B, CT, smem, st>>>(D, P, packed_limit, mc_identity ? 1 : 0);
   return 1;
 }
 // largest dynamic shared-memory size k_chol can be launched with (opt-in limit minus its static arrays);
