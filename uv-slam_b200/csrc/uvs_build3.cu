@@ -420,6 +420,90 @@ constexpr int GEMM_WARPS = 3; // warps 0..2 run the rank update (up to 78 pair t
 __constant__ unsigned char c_sym_p[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
 __constant__ unsigned char c_sym_q[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
 
+// Direct terms sum_f J_a^T J_b per camera-block pair, gradient J^T r and squared column norms: one WARP per
+// (window, block pair[, segment of a diagonal pair's list]) so that thousands of warps hide the gather latency;
+// lanes own the entries of the 6x6 block.  Results go straight into the window's (zeroed) system.
+constexpr int SEGS = 8;   // diagonal pairs see ~40x more factors than off-diagonal ones: split their lists
+
+__global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max) {
+  const int lane = threadIdx.x & 31;
+  const int U = nb_max * SEGS + nb_max * (nb_max - 1) / 2;
+  const long long unit = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int w = (int)(unit / U), local = (int)(unit - (long long)w * U);
+  if (w >= D.B) return;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
+  const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
+  const int nb = F + (ex ? 1 : 0);
+  int a, b, seg = 0;
+  if (local < nb_max * SEGS) { a = b = local / SEGS; seg = local - a * SEGS; }
+  else {
+    const int o = local - nb_max * SEGS;          // strictly upper pair: o = b (b - 1) / 2 + a, a < b
+    int i = (int)((sqrtf(8.0f * (float)o + 1.0f) + 1.0f) * 0.5f);
+    while (i * (i - 1) / 2 > o) i--;
+    while ((i + 1) * i / 2 <= o) i++;
+    b = i; a = o - i * (i - 1) / 2;
+  }
+  if (b >= nb) return;
+  const int key = pair_key(a, b);
+  const int2 *items = L.items + direct_base(D, w);
+  const int *off = L.off + (size_t)w * KMAX;
+  int i0 = off[key], i1 = off[key + 1];
+  if (a == b) {
+    const int len = i1 - i0, per = (len + SEGS - 1) / SEGS;
+    i0 += seg * per; i1 = min(i1, i0 + per);
+  }
+  if (i0 >= i1) return;
+  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+  double *Sg = D.Smat + D.S_off[w];
+  const int ra = a < F ? 15 * a : 15 * F, rb = b < F ? 15 * b : 15 * F;
+  if (a == b) {
+    // 21 symmetric entries + 6 gradient entries
+    if (lane >= 27) return;
+    int p, q = 0;
+    const bool isg = lane >= 21;
+    if (!isg) { p = c_sym_p[lane]; q = c_sym_q[lane]; } else p = lane - 21;
+    double acc = 0.0;
+    for (int it = i0; it < i1; it++) {
+      const int2 item = items[it];
+      if (D.nranks > 1) {   // factor-parallel mode: only the records of this rank's landmarks are current
+        const int lm = item.y <= 6 ? D.proj_idx[item.x].z : (item.y == 7 ? D.line_idx4[item.x].y : D.vp_idx4[item.x].y);
+        if ((lm % D.nranks) != D.rank) continue;
+      }
+      const double *rec; int baseA, nrows;
+      if (item.y <= 6) { rec = D.rec_proj + (size_t)item.x * REC_PROJ; nrows = 2; baseA = item.y == 0 ? 2 : (item.y == 1 ? 14 : 26); }
+      else if (item.y == 7) { rec = D.rec_line + (size_t)item.x * REC_LINE; nrows = 2; baseA = 2; }
+      else { rec = D.rec_vp + (size_t)item.x * REC_VP; nrows = 1; baseA = 1; }
+      double t = rec[baseA + p] * (isg ? rec[0] : rec[baseA + q]);
+      if (nrows == 2) t += rec[baseA + 6 + p] * (isg ? rec[1] : rec[baseA + 6 + q]);
+      acc += t;
+    }
+    if (!isg) {
+      atomicAdd(Sg + (size_t)(ra + p) * d + ra + q, acc);
+      if (p == q) atomicAdd(D.colsq_cam + co + ra + p, acc);
+    } else {
+      atomicAdd(D.gS + co + ra + p, acc);
+      atomicAdd(D.gfull + co + ra + p, acc);
+    }
+  } else {
+    // off-diagonal pair (a < b): 36 entries, lanes 0..31 + a second entry on lanes 0..3; one warp owns the block
+    const int p0 = lane / 6, q0 = lane - 6 * p0, q1 = 2 + lane;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int it = i0; it < i1; it++) {
+      const int2 item = items[it];
+      if (D.nranks > 1 && (D.proj_idx[item.x].z % D.nranks) != D.rank) continue;
+      const double *rec = D.rec_proj + (size_t)item.x * REC_PROJ;
+      int baseA, baseB;
+      if (item.y == 2) { baseA = 2; baseB = 14; } else if (item.y == 3) { baseA = 14; baseB = 2; }
+      else if (item.y == 4) { baseA = 2; baseB = 26; } else { baseA = 14; baseB = 26; }
+      acc0 += rec[baseA + p0] * rec[baseB + q0] + rec[baseA + 6 + p0] * rec[baseB + 6 + q0];
+      if (lane < 4) acc1 += rec[baseA + 5] * rec[baseB + q1] + rec[baseA + 11] * rec[baseB + 6 + q1];
+    }
+    Sg[(size_t)(ra + p0) * d + rb + q0] += acc0;
+    if (lane < 4) Sg[(size_t)(ra + 5) * d + rb + q1] += acc1;
+  }
+}
+
 __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectLists L, int max_prior_n) {
   extern __shared__ double sm[];
   const int w = blockIdx.x;
@@ -431,60 +515,11 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectList
   const int nkeys = nb * (nb + 1) / 2;
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   const bool lead = D.nranks <= 1 || D.rank == 0;
-  // shared layout: V[m*m] gdir[m] gsch[m] csq[m] Ych[2][CH][mp] cmap(int)[max_prior_n]
-  double *V = sm, *gdir = V + (size_t)m * m, *gsch = gdir + m, *csq = gsch + m, *Ych = csq + m;
+  // shared layout: V[m*m] gsch[m] Ych[2][CH][mp] cmap(int)[max_prior_n]
+  double *V = sm, *gsch = V + (size_t)m * m, *Ych = gsch + m;
+  (void)L; (void)nkeys;
   int *cmap = reinterpret_cast<int *>(Ych + (size_t)2 * CH * mp);
-  for (int e = tid; e < m * m + 3 * m; e += WT) V[e] = 0.0;
-  __syncthreads();
-
-  // ---- (1) direct terms: a warp owns a block pair, lanes own entries
-  {
-    const int2 *items = L.items + direct_base(D, w);
-    const int *off = L.off + (size_t)w * KMAX;
-    const bool td42 = D.estimate_td != 0;
-    (void)td42;
-    for (int key = warp; key < nkeys; key += WT / 32) {
-      int a, b;
-      unrank_key(key, a, b);
-      const int i0 = off[key], i1 = off[key + 1];
-      if (a == b) {
-        // 21 symmetric entries + 6 gradient entries
-        int p = 0, q = 0;
-        const bool isg = lane >= 21;
-        if (lane < 21) { p = c_sym_p[lane]; q = c_sym_q[lane]; } else if (lane < 27) { p = lane - 21; }
-        double acc = 0.0;
-        if (lane < 27) {
-          for (int it = i0; it < i1; it++) {
-            const int2 item = items[it];
-            const double *rec; int baseA, nrows, stride;
-            if (item.y <= 6) { rec = D.rec_proj + (size_t)item.x * REC_PROJ; nrows = 2; stride = 6; baseA = item.y == 0 ? 2 : (item.y == 1 ? 14 : 26); }
-            else if (item.y == 7) { rec = D.rec_line + (size_t)item.x * REC_LINE; nrows = 2; stride = 6; baseA = 2; }
-            else { rec = D.rec_vp + (size_t)item.x * REC_VP; nrows = 1; stride = 0; baseA = 1; }
-            double t = rec[baseA + p] * (isg ? rec[0] : rec[baseA + q]);
-            if (nrows == 2) t += rec[baseA + stride + p] * (isg ? rec[1] : rec[baseA + stride + q]);
-            acc += t;
-          }
-          if (!isg) { V[(6 * a + p) * m + 6 * a + q] = acc; V[(6 * a + q) * m + 6 * a + p] = acc; if (p == q) csq[6 * a + p] = acc; }
-          else gdir[6 * a + p] = acc;
-        }
-      } else {
-        // off-diagonal pair: 36 entries, lanes 0..31 + a second entry on lanes 0..3
-        const int p0 = lane / 6, q0 = lane - 6 * p0, q1 = 2 + lane;   // second entry: (5, 2 + lane)
-        double acc0 = 0.0, acc1 = 0.0;
-        for (int it = i0; it < i1; it++) {
-          const int2 item = items[it];
-          const double *rec = D.rec_proj + (size_t)item.x * REC_PROJ;
-          int baseA, baseB;
-          if (item.y == 2) { baseA = 2; baseB = 14; } else if (item.y == 3) { baseA = 14; baseB = 2; }
-          else if (item.y == 4) { baseA = 2; baseB = 26; } else { baseA = 14; baseB = 26; }
-          acc0 += rec[baseA + p0] * rec[baseB + q0] + rec[baseA + 6 + p0] * rec[baseB + 6 + q0];
-          if (lane < 4) acc1 += rec[baseA + 5] * rec[baseB + q1] + rec[baseA + 11] * rec[baseB + 6 + q1];
-        }
-        V[(6 * a + p0) * m + 6 * b + q0] = acc0;
-        if (lane < 4) V[(6 * a + 5) * m + 6 * b + q1] = acc1;
-      }
-    }
-  }
+  for (int e = tid; e < m * m + m; e += WT) V[e] = 0.0;
   __syncthreads();
 
   // ---- (2) Schur terms: V -= Y Y^T, gsch = Y z, over all landmark columns
@@ -589,13 +624,12 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectList
     if (r > c) continue;
     const int a = r / 6, b = c / 6;
     const int row = (a < F ? 15 * a : 15 * F) + (r - 6 * a), col = (b < F ? 15 * b : 15 * F) + (c - 6 * b);
-    if (D.nranks > 1) atomicAdd(Sg + (size_t)row * d + col, V[e]); else Sg[(size_t)row * d + col] += V[e];
+    Sg[(size_t)row * d + col] += V[e];
   }
   for (int e = tid; e < m; e += WT) {
     const int a = e / 6;
     const int idx = co + (a < F ? 15 * a : 15 * F) + (e - 6 * a);
-    if (D.nranks > 1) { atomicAdd(D.gS + idx, gdir[e] - gsch[e]); atomicAdd(D.gfull + idx, gdir[e]); atomicAdd(D.colsq_cam + idx, csq[e]); }
-    else { D.gS[idx] += gdir[e] - gsch[e]; D.gfull[idx] += gdir[e]; D.colsq_cam[idx] += csq[e]; }
+    D.gS[idx] -= gsch[e];
   }
   if (!lead) return;
   __syncthreads();
@@ -689,7 +723,7 @@ int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, cudaSt
 
 size_t build3_smem(int max_frames, bool any_ex, int max_prior_n) {
   const int nb = max_frames + (any_ex ? 1 : 0), m = 6 * nb, mp = m + 2;
-  return ((size_t)m * m + 3 * m + (size_t)2 * CH * mp) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
+  return ((size_t)m * m + m + (size_t)2 * CH * mp) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
 }
 
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
@@ -701,8 +735,13 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
   const size_t smem = build3_smem(max_frames, any_ex, max_prior_n);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
+  {
+    const int nb_max = max_frames + (any_ex ? 1 : 0);
+    const long long units = (long long)D.B * (nb_max * SEGS + nb_max * (nb_max - 1) / 2);
+    k_direct<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(D, c.L, nb_max);
+  }
   k_window_system<<<D.B, WT, smem, st>>>(D, c.S, c.L, max_prior_n);
-  return n + 1;
+  return n + 2;
 }
 
 int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st) {
