@@ -379,7 +379,10 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   h->o_b3 = w_b3;
 
   h->launches += launch_prep(D, h->stream);
-  if (h->use_build3) h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->stream);
+  if (h->use_build3) {
+    CK(cudaMemsetAsync(Dv + w_b3 + h->b3.o_Y, 0, h->b3.o_ph - h->b3.o_Y, h->stream));   // dense landmark columns start as zeros
+    h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->stream);
+  }
   int rc = post_launch(h, "prep kernels");
   if (rc) return rc;
   int err = 0;

@@ -54,24 +54,28 @@ __device__ __forceinline__ void add_win3(double *acc, int win, bool valid, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// stash layout (B3): points  d[PS]: z, sk, sh, D2, pad(4), Y[blk][6];   i[PI]: nblk, blk[...]
-//                    lines   d[LS]: z(4) s(4) D2(4) Linv(16) pad(4), Y[obs][6][4];  i[LI]: n, blk[...]
+// stash (B3): dense landmark columns  Y[col][mp]:  entries [6 blk + k] = Y of camera block blk, [mp-2] = z,
+//             col = colbase(w) + point  |  colbase(w) + np_w + 4 line + sub, colbase(w) = point_off[w] + 4 line_off[w]
+//             (the window kernel streams whole chunks of columns with TMA bulk copies);
+//             headers for the back-substitution: points ph[4] = sk, sh, D2, -;  lines lh[24] = s(4) D2(4) Linv(16)
 struct Stash {
-  double *pd, *ld;
-  int *pi, *li;
-  int PS, PI, LS, LI;
+  double *Y, *ph, *lh;
+  int mp;
 };
+__device__ __forceinline__ long long colbase(const Dev &D, int w) { return (long long)D.point_off[w] + 4LL * D.line_off[w]; }
 
 __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
   const int gp = blockIdx.x * blockDim.x + threadIdx.x;
   if (gp >= D.nP) return;
-  if (D.nranks > 1 && (gp % D.nranks) != D.rank) return;
   const int w = D.pt_win[gp];
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int mp = S.mp;
+  double *Y = S.Y + (colbase(D, w) + (gp - D.point_off[w])) * mp;
+  double *ph = S.ph + 4 * (size_t)gp;
   const int f0 = D.pt_begin[gp], n = D.pt_end[gp] - f0;
-  int *hi = S.pi + (size_t)gp * S.PI;
-  double *hd = S.pd + (size_t)gp * S.PS;
-  if (n <= 0) { hi[0] = 0; return; }
+  const bool mine = D.nranks <= 1 || (gp % D.nranks) == D.rank;
+  // the column was zero-filled at upload and its sparsity pattern never changes: only the blocks are rewritten
+  if (n <= 0 || !mine) { ph[1] = 0.0; return; }
   const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
   const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
   const double *R = D.rec_proj + (size_t)f0 * REC_PROJ;
@@ -89,43 +93,37 @@ __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
   const double sh = rsqrt(Et + D2);
   const double ysc = sk * sh;
   double wa[6] = {0, 0, 0, 0, 0, 0}, we[6] = {0, 0, 0, 0, 0, 0};
-  double *Y = hd + 8;
   for (int f = 0; f < n; f++) {
     const double *r = R + f * REC_PROJ;
     const double j0 = r[38], j1 = r[39];
+    const int bj = D.proj_idx[f0 + f].y - fo;
 #pragma unroll
     for (int c = 0; c < 6; c++) {
       wa[c] += r[2 + c] * j0 + r[8 + c] * j1;
-      Y[6 * (1 + f) + c] = ysc * (r[14 + c] * j0 + r[20 + c] * j1);
+      Y[6 * bj + c] = ysc * (r[14 + c] * j0 + r[20 + c] * j1);
       if (ex) we[c] += r[26 + c] * j0 + r[32 + c] * j1;
     }
-    hi[2 + f] = D.proj_idx[f0 + f].y - fo;
   }
+  const int bi = D.proj_idx[f0].x - fo;
 #pragma unroll
-  for (int c = 0; c < 6; c++) Y[c] = ysc * wa[c];
-  hi[1] = D.proj_idx[f0].x - fo;
-  int nblk = n + 1;
-  if (ex) {
-#pragma unroll
-    for (int c = 0; c < 6; c++) Y[6 * nblk + c] = ysc * we[c];
-    hi[1 + nblk] = F;
-    nblk++;
-  }
-  hi[0] = nblk;
-  hd[0] = sk * gk * sh; hd[1] = sk; hd[2] = sh; hd[3] = D2;
+  for (int c = 0; c < 6; c++) { Y[6 * bi + c] = ysc * wa[c]; if (ex) Y[6 * F + c] = ysc * we[c]; }
+  Y[mp - 2] = sk * gk * sh;
+  ph[0] = sk; ph[1] = sh; ph[2] = D2;
   atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fabs(gk));
 }
 
 __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
   const int gl = blockIdx.x * blockDim.x + threadIdx.x;
   if (gl >= D.nL) return;
-  if (D.nranks > 1 && (gl % D.nranks) != D.rank) return;
   const int w = D.ln_win[gl];
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
   const int f0 = D.ln_begin[gl], n = D.ln_end[gl] - f0;
-  int *hi = S.li + (size_t)gl * S.LI;
-  double *hd = S.ld + (size_t)gl * S.LS;
-  if (n <= 0) { hi[0] = 0; return; }
+  const int mp = S.mp;
+  double *Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp;   // 4 columns
+  double *hd = S.lh + 24 * (size_t)gl;
+  const bool mine = D.nranks <= 1 || (gl % D.nranks) == D.rank;
+  hd[8] = 0.0;   // Linv[0][0] = 0 marks "no step" for the back-substitution
+  if (n <= 0 || !mine) return;
   const int fo = D.frame_off[w];
   double E[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
   for (int f = 0; f < n; f++) {
@@ -181,7 +179,7 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
       L[i][j] = t * id;
     }
   }
-  if (!ok) { atomicAdd(D.acc + (size_t)w * ACC_STRIDE + ACC_FAIL, 1.0); hi[0] = 0; return; }
+  if (!ok) { atomicAdd(D.acc + (size_t)w * ACC_STRIDE + ACC_FAIL, 1.0); return; }
 #pragma unroll
   for (int col = 0; col < 4; col++)
 #pragma unroll
@@ -201,13 +199,12 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
     z[c] = t;
   }
 #pragma unroll
-  for (int c = 0; c < 4; c++) { hd[c] = z[c]; hd[4 + c] = s[c]; hd[8 + c] = D2[c]; }
+  for (int c = 0; c < 4; c++) { Y[c * mp + mp - 2] = z[c]; hd[c] = s[c]; hd[4 + c] = D2[c]; }
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int k = 0; k < 4; k++) hd[12 + 4 * i + k] = k <= i ? Li[i][k] : 0.0;
+    for (int k = 0; k < 4; k++) hd[8 + 4 * i + k] = k <= i ? Li[i][k] : 0.0;
   // Y_f = (Jp^T Jl D_s) L^-T
-  double *Y = hd + 32;
   for (int f = 0; f < n; f++) {
     const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
     const int4 ix = D.line_idx4[f0 + f];
@@ -226,12 +223,10 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k <= c; k++) t += W4[k] * Li[c][k];
-        Y[f * 24 + p * 4 + c] = t;
+        Y[c * mp + 6 * (ix.x - fo) + p] = t;
       }
     }
-    hi[1 + f] = ix.x - fo;
   }
-  hi[0] = n;
   atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3]))));
 }
 
@@ -247,20 +242,23 @@ __global__ void __launch_bounds__(128) k_back_points(Dev D, Stash S) {
   }
   double mc = 0.0, s2 = 0.0, x2 = 0.0;
   if (valid) {
-    const int *hi = S.pi + (size_t)gp * S.PI;
-    const double *hd = S.pd + (size_t)gp * S.PS;
-    const int nblk = hi[0], cur = D.cur[w];
+    const int mp = S.mp, cur = D.cur[w];
+    const double *Y = S.Y + (colbase(D, w) + (gp - D.point_off[w])) * mp;
+    const double *ph = S.ph + 4 * (size_t)gp;
     const double lam = D.inv_depth[cur][gp];
+    const double sk = ph[0], sh = ph[1], D2 = ph[2];
     double dk = 0.0;
-    if (nblk > 0) {
+    if (sh != 0.0) {
+      const int F = D.frame_off[w + 1] - D.frame_off[w];
+      const int nb = F + ((D.win_flags[w] & WF_EXTRINSIC) ? 1 : 0);
       const double *dl = D.delta_cam + D.cam_off[w];
       double u = 0.0;
-      for (int b = 0; b < nblk; b++) {
-        const double *y = hd + 8 + 6 * b, *d = dl + 15 * hi[1 + b];
+      for (int b = 0; b < nb; b++) {
+        const double *y = Y + 6 * b, *d = dl + 15 * b;   // the extrinsic block (b == F) sits at 15 F as well
 #pragma unroll
         for (int c = 0; c < 6; c++) u += y[c] * d[c];
       }
-      const double z = hd[0], sk = hd[1], sh = hd[2], D2 = hd[3];
+      const double z = Y[mp - 2];
       const double yk = -sh * (z + u);
       dk = sk * yk;
       mc = 0.5 * (D2 * yk * yk - (z / sh) * yk);
@@ -282,35 +280,36 @@ __global__ void __launch_bounds__(128) k_back_lines(Dev D, Stash S) {
   }
   double mc = 0.0, s2 = 0.0, x2 = 0.0;
   if (valid) {
-    const int *hi = S.li + (size_t)gl * S.LI;
-    const double *hd = S.ld + (size_t)gl * S.LS;
-    const int n = hi[0], cur = D.cur[w];
+    const int mp = S.mp, cur = D.cur[w];
+    const double *Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp;
+    const double *hd = S.lh + 24 * (size_t)gl;
     double dk[4] = {0, 0, 0, 0};
-    if (n > 0) {
+    if (hd[8] != 0.0) {
+      const int F = D.frame_off[w + 1] - D.frame_off[w];
       const double *dl = D.delta_cam + D.cam_off[w];
-      double u[4] = {0, 0, 0, 0};
-      for (int f = 0; f < n; f++) {
-        const double *y = hd + 32 + 24 * f, *d = dl + 15 * hi[1 + f];
-#pragma unroll
-        for (int p = 0; p < 6; p++)
-#pragma unroll
-          for (int c = 0; c < 4; c++) u[c] += y[p * 4 + c] * d[p];
-      }
-      // y_k = -L^-T (z + u)
       double t[4], yk[4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) t[c] = hd[c] + u[c];
+      for (int c = 0; c < 4; c++) {
+        const double *y = Y + c * mp;
+        double u = 0.0;
+        for (int b = 0; b < F; b++) {
+#pragma unroll
+          for (int p = 0; p < 6; p++) u += y[6 * b + p] * dl[15 * b + p];
+        }
+        t[c] = y[mp - 2] + u;   // z + u
+      }
+      // y_k = -L^-T (z + u)
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         double a = 0.0;
 #pragma unroll
-        for (int k = c; k < 4; k++) a += hd[12 + 4 * k + c] * t[k];
+        for (int k = c; k < 4; k++) a += hd[8 + 4 * k + c] * t[k];
         yk[c] = -a;
       }
       // g~^T y_k = (L z)^T y_k = -z^T (z + u)
       double gy = 0.0, dy = 0.0;
 #pragma unroll
-      for (int c = 0; c < 4; c++) { gy -= hd[c] * t[c]; dy += hd[8 + c] * yk[c] * yk[c]; dk[c] = hd[4 + c] * yk[c]; }
+      for (int c = 0; c < 4; c++) { gy -= Y[c * mp + mp - 2] * t[c]; dy += hd[4 + c] * yk[c] * yk[c]; dk[c] = hd[c] * yk[c]; }
       mc = 0.5 * (dy - gy);
     }
 #pragma unroll
@@ -413,12 +412,36 @@ __global__ void __launch_bounds__(128) k_prep_direct(Dev D, DirectLists L) {
 
 // ------------------------------------------------------------------------------------------------
 constexpr int WT = 256;       // threads of k_window_system
-constexpr int CH = 32;        // landmark columns per chunk
-constexpr int GEMM_WARPS = 3; // warps 0..2 run the rank update (up to 78 pair tiles + 12 gradient tiles <= 96 threads)
+constexpr int CH = 32;        // landmark columns per chunk (one TMA bulk copy)
+constexpr int GT = 96;        // threads of one GEMM group (<= 78 pair tiles + 12 gradient tiles)
+constexpr int NGROUPS = 2;    // groups split the columns of a chunk
 
 // upper-triangle unranking of a 6x6 symmetric block: e in [0,21) -> (p <= q)
 __constant__ unsigned char c_sym_p[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
 __constant__ unsigned char c_sym_q[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+ PTX)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // Direct terms sum_f J_a^T J_b per camera-block pair, gradient J^T r and squared column norms: one WARP per
 // (window, block pair[, segment of a diagonal pair's list]) so that thousands of warps hide the gather latency;
@@ -504,85 +527,60 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
   }
 }
 
-__global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectLists L, int max_prior_n) {
-  extern __shared__ double sm[];
+// Schur terms of one window as a dense rank update over its landmark columns, then IMU blocks and the prior.
+//   V -= Y Y^T (6x6 register tiles, one per camera-block pair), gsch = Y z.
+// The dense columns are streamed chunk by chunk with TMA bulk copies (cp.async.bulk + mbarrier), double buffered.
+__global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_prior_n) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) unsigned long long bar[2];
   const int w = blockIdx.x;
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
   const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
-  const int nb = F + (ex ? 1 : 0), m = 6 * nb, mp = m + 2;   // Y column stride: m values + z + pad
+  const int nb = F + (ex ? 1 : 0), m = 6 * nb, mp = S.mp;
   const int nkeys = nb * (nb + 1) / 2;
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   const bool lead = D.nranks <= 1 || D.rank == 0;
-  // shared layout: V[m*m] gsch[m] Ych[2][CH][mp] cmap(int)[max_prior_n]
-  double *V = sm, *gsch = V + (size_t)m * m, *Ych = gsch + m;
-  (void)L; (void)nkeys;
-  int *cmap = reinterpret_cast<int *>(Ych + (size_t)2 * CH * mp);
+  // shared layout: Ych[2][CH][mp] (TMA destination, 16-byte aligned) V[m*m] gsch[m] cmap(int)[max_prior_n]
+  double *Ych = sm, *V = Ych + (size_t)2 * CH * mp, *gsch = V + (size_t)m * m;
+  int *cmap = reinterpret_cast<int *>(gsch + m);
   for (int e = tid; e < m * m + m; e += WT) V[e] = 0.0;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
 
-  // ---- (2) Schur terms: V -= Y Y^T, gsch = Y z, over all landmark columns
   {
-    const int p0 = D.point_off[w], np = D.point_off[w + 1] - p0, l0 = D.line_off[w], nl = D.line_off[w + 1] - l0;
+    const int np = D.point_off[w + 1] - D.point_off[w], nl = D.line_off[w + 1] - D.line_off[w];
     const int ncols = np + 4 * nl, nchunks = (ncols + CH - 1) / CH;
-    // GEMM tile of this thread
+    const double *Yw = S.Y + colbase(D, w) * mp;
+    auto issue = [&](int c) {   // one elected thread: arm the barrier with the byte count, start the bulk copy
+      const int c0 = c * CH, c1 = min(ncols, c0 + CH);
+      const unsigned bytes = (unsigned)((c1 - c0) * mp * sizeof(double));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bar[c & 1], bytes);
+      tma_bulk_g2s(Ych + (size_t)(c & 1) * CH * mp, Yw + (size_t)c0 * mp, bytes, &bar[c & 1]);
+    };
+    // GEMM tile of this thread: group g takes the columns cc = g (mod NGROUPS) of every chunk
+    const int g = tid / GT, t = tid - g * GT;
     int ta = -1, tb = -1;      // block pair (ta <= tb), or gradient tile (ta, -2)
-    if (tid < nkeys) unrank_key(tid, ta, tb);
-    else if (tid < nkeys + nb) { ta = tid - nkeys; tb = -2; }
+    if (g < NGROUPS) {
+      if (t < nkeys) unrank_key(t, ta, tb);
+      else if (t < nkeys + nb) { ta = t - nkeys; tb = -2; }
+    }
     double acc[6][6];
 #pragma unroll
     for (int p = 0; p < 6; p++)
 #pragma unroll
       for (int q = 0; q < 6; q++) acc[p][q] = 0.0;
-    // expansion of chunk c into buffer buf by the threads [t0, t0 + nt)
-    auto expand = [&](int c, int buf, int t0, int nt) {
-      double *Yb = Ych + (size_t)buf * CH * mp;
-      const int c0 = c * CH, c1 = min(ncols, c0 + CH);
-      const int t = tid - t0;
-      for (int e = t; e < (c1 - c0) * mp; e += nt) Yb[e] = 0.0;
-      // the zero fill and the scatter below touch the same entries: order them inside the expanding group
-      if (nt == WT) __syncthreads(); else asm volatile("bar.sync 1, %0;" ::"r"(nt));
-      for (int e = t; e < (c1 - c0) * 12; e += nt) {     // (column, block slot)
-        const int cc = e / 12, slot = e - 12 * cc, col = c0 + cc;
-        double *y = Yb + (size_t)cc * mp;
-        if (col < np) {
-          const int gp = p0 + col;
-          if (D.nranks > 1 && (gp % D.nranks) != D.rank) continue;
-          const int *hi = S.pi + (size_t)gp * S.PI;
-          const double *hd = S.pd + (size_t)gp * S.PS;
-          const int nblk = hi[0];
-          if (slot < nblk) {
-            const int blk = hi[1 + slot];
-#pragma unroll
-            for (int k = 0; k < 6; k++) y[6 * blk + k] = hd[8 + 6 * slot + k];
-          }
-          if (slot == 0 && nblk > 0) y[m] = hd[0];
-        } else {
-          const int li = (col - np) >> 2, sub = (col - np) & 3, gl = l0 + li;
-          if (D.nranks > 1 && (gl % D.nranks) != D.rank) continue;
-          const int *hi = S.li + (size_t)gl * S.LI;
-          const double *hd = S.ld + (size_t)gl * S.LS;
-          const int n = hi[0];
-          if (slot < n) {
-            const int blk = hi[1 + slot];
-#pragma unroll
-            for (int k = 0; k < 6; k++) y[6 * blk + k] = hd[32 + 24 * slot + 4 * k + sub];
-          }
-          if (slot == 0 && n > 0) y[m] = hd[sub];
-        }
-      }
-    };
-    expand(0, 0, 0, WT);
-    __syncthreads();
+    if (tid == 0 && nchunks > 0) issue(0);
     for (int c = 0; c < nchunks; c++) {
-      if (warp >= GEMM_WARPS) {
-        if (c + 1 < nchunks) expand(c + 1, (c + 1) & 1, GEMM_WARPS * 32, WT - GEMM_WARPS * 32);
-      } else if (ta >= 0) {
+      if (tid == 0 && c + 1 < nchunks) issue(c + 1);      // buffer (c+1)&1 was released by the barrier below
+      mbar_wait(&bar[c & 1], (unsigned)((c >> 1) & 1));
+      if (ta >= 0) {
         const double *Yb = Ych + (size_t)(c & 1) * CH * mp;
         const int c1 = min(ncols, (c + 1) * CH) - c * CH;
         if (tb >= 0) {
-          for (int cc = 0; cc < c1; cc++) {
+          for (int cc = g; cc < c1; cc += NGROUPS) {
             const double *y = Yb + (size_t)cc * mp;
             double ya[6], yb[6];
 #pragma unroll
@@ -593,9 +591,9 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectList
               for (int q = 0; q < 6; q++) acc[p][q] += ya[p] * yb[q];
           }
         } else {
-          for (int cc = 0; cc < c1; cc++) {
+          for (int cc = g; cc < c1; cc += NGROUPS) {
             const double *y = Yb + (size_t)cc * mp;
-            const double zz = y[m];
+            const double zz = y[mp - 2];
 #pragma unroll
             for (int k = 0; k < 6; k++) acc[0][k] += y[6 * ta + k] * zz;
           }
@@ -603,21 +601,23 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectList
       }
       __syncthreads();
     }
-    if (ta >= 0 && tb >= 0) {
+    for (int gg = 0; gg < NGROUPS; gg++) {
+      if (g == gg && ta >= 0) {
+        if (tb >= 0) {
 #pragma unroll
-      for (int p = 0; p < 6; p++)
+          for (int p = 0; p < 6; p++)
 #pragma unroll
-        for (int q = 0; q < 6; q++) {
-          V[(6 * ta + p) * m + 6 * tb + q] -= acc[p][q];
+            for (int q = 0; q < 6; q++) V[(6 * ta + p) * m + 6 * tb + q] -= acc[p][q];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) gsch[6 * ta + k] += acc[0][k];
         }
-    } else if (ta >= 0) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) gsch[6 * ta + k] = acc[0][k];
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
 
-  // ---- (3) write the window's system (cleared by k_step / k_solve_init): pose blocks from V, then IMU, then prior
+  // ---- write the window's system (cleared by k_step / k_solve_init, direct terms already added by k_direct)
   double *Sg = D.Smat + D.S_off[w];
   for (int e = tid; e < m * m; e += WT) {
     const int r = e / m, c = e - r * m;
@@ -628,32 +628,31 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectList
   }
   for (int e = tid; e < m; e += WT) {
     const int a = e / 6;
-    const int idx = co + (a < F ? 15 * a : 15 * F) + (e - 6 * a);
-    D.gS[idx] -= gsch[e];
+    D.gS[co + (a < F ? 15 * a : 15 * F) + (e - 6 * a)] -= gsch[e];
   }
   if (!lead) return;
   __syncthreads();
-  // IMU factors: 30x30 blocks; factors of even / odd frame index do not overlap
-  for (int parity = 0; parity < 2; parity++) {
-    for (int f = D.imu_off[w]; f < D.imu_off[w + 1]; f++) {
-      const int fi = D.imu_idx[f].x - fo;
-      if ((fi & 1) != parity) continue;
-      const int c0 = 15 * fi;
-      const double *R = D.rec_imu + (size_t)f * REC_IMU, *J = R + 15;
-      for (int e = tid; e < 900; e += WT) {
-        const int p = e / 30, q = e - 30 * p;
-        if (p > q) continue;
-        double h = 0.0;
+  // IMU factors: 30x30 blocks, record staged in shared memory (the chunk buffers are free now)
+  double *Js = Ych;
+  for (int f = D.imu_off[w]; f < D.imu_off[w + 1]; f++) {
+    const double *R = D.rec_imu + (size_t)f * REC_IMU;
+    for (int e = tid; e < REC_IMU; e += WT) Js[e] = R[e];
+    __syncthreads();
+    const int c0 = 15 * (D.imu_idx[f].x - fo);
+    const double *J = Js + 15;
+    for (int e = tid; e < 900; e += WT) {
+      const int p = e / 30, q = e - 30 * p;
+      if (p > q) continue;
+      double h = 0.0;
 #pragma unroll
-        for (int i = 0; i < 15; i++) h += J[i * 30 + p] * J[i * 30 + q];
-        Sg[(size_t)(c0 + p) * d + c0 + q] += h;
-      }
-      if (tid < 30) {
-        double g = 0.0, q2 = 0.0;
+      for (int i = 0; i < 15; i++) h += J[i * 30 + p] * J[i * 30 + q];
+      Sg[(size_t)(c0 + p) * d + c0 + q] += h;
+    }
+    if (tid < 30) {
+      double gg = 0.0, q2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 15; i++) { const double j = J[i * 30 + tid]; g += j * R[i]; q2 += j * j; }
-        D.gfull[co + c0 + tid] += g; D.gS[co + c0 + tid] += g; D.colsq_cam[co + c0 + tid] += q2;
-      }
+      for (int i = 0; i < 15; i++) { const double j = J[i * 30 + tid]; gg += j * Js[i]; q2 += j * j; }
+      D.gfull[co + c0 + tid] += gg; D.gS[co + c0 + tid] += gg; D.colsq_cam[co + c0 + tid] += q2;
     }
     __syncthreads();
   }
@@ -675,13 +674,12 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, DirectList
       if (cp < 0 || cq < 0 || cp > cq) continue;
       Sg[(size_t)cp * d + cq] += H[e];
     }
-    // g += J0^T r: warp per column group, coalesced over columns
     for (int p = tid; p < n; p += WT) {
       const int cp = cmap[p];
       if (cp < 0) continue;
-      double g = 0.0;
-      for (int i = 0; i < n; i++) g += J0[(size_t)i * n + p] * r[i];
-      D.gfull[co + cp] += g; D.gS[co + cp] += g; D.colsq_cam[co + cp] += H[(size_t)p * n + p];
+      double gg = 0.0;
+      for (int i = 0; i < n; i++) gg += J0[(size_t)i * n + p] * r[i];
+      D.gfull[co + cp] += gg; D.gS[co + cp] += gg; D.colsq_cam[co + cp] += H[(size_t)p * n + p];
     }
   }
 }
@@ -694,22 +692,20 @@ struct Build3Ctx {
 
 size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay) {
   const int nbmax = max_frames + (any_ex ? 1 : 0);
-  lay->PS = 8 + 6 * (nbmax + 1); lay->PI = nbmax + 4; lay->LS = 32 + 24 * max_frames; lay->LI = max_frames + 2;
+  lay->mp = 6 * nbmax + 2;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o = 0;
-  lay->o_pd = o; o += al((size_t)D.nP * lay->PS * sizeof(double));
-  lay->o_ld = o; o += al((size_t)D.nL * lay->LS * sizeof(double));
-  lay->o_pi = o; o += al((size_t)D.nP * lay->PI * sizeof(int));
-  lay->o_li = o; o += al((size_t)D.nL * lay->LI * sizeof(int));
+  lay->o_Y = o; o += al(((size_t)D.nP + 4 * (size_t)D.nL) * lay->mp * sizeof(double));
+  lay->o_ph = o; o += al((size_t)D.nP * 4 * sizeof(double));
+  lay->o_lh = o; o += al((size_t)D.nL * 24 * sizeof(double));
   lay->o_items = o; o += al(((size_t)6 * D.nProj + D.nLobs + D.nVobs + 1) * sizeof(int2));
   lay->o_off = o; o += al((size_t)D.B * KMAX * sizeof(int));
   return o;
 }
 
 static void make_ctx(char *base, const Build3Layout &lay, Build3Ctx &c) {
-  c.S.pd = (double *)(base + lay.o_pd); c.S.ld = (double *)(base + lay.o_ld);
-  c.S.pi = (int *)(base + lay.o_pi); c.S.li = (int *)(base + lay.o_li);
-  c.S.PS = lay.PS; c.S.PI = lay.PI; c.S.LS = lay.LS; c.S.LI = lay.LI;
+  c.S.Y = (double *)(base + lay.o_Y); c.S.ph = (double *)(base + lay.o_ph); c.S.lh = (double *)(base + lay.o_lh);
+  c.S.mp = lay.mp;
   c.L.items = (int2 *)(base + lay.o_items); c.L.off = (int *)(base + lay.o_off);
 }
 
@@ -740,7 +736,7 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
     const long long units = (long long)D.B * (nb_max * SEGS + nb_max * (nb_max - 1) / 2);
     k_direct<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(D, c.L, nb_max);
   }
-  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, c.L, max_prior_n);
+  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
   return n + 2;
 }
 

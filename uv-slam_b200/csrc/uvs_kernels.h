@@ -31,8 +31,8 @@ int launch_backsub(const Dev &D, const Params &P, cudaStream_t st);
 
 // uvs_build3.cu — atomics-free landmark path for windows of <= 12 six-wide camera blocks without td
 struct Build3Layout {
-  int PS, PI, LS, LI;
-  size_t o_pd, o_ld, o_pi, o_li, o_items, o_off;
+  int mp;                                        // doubles per dense landmark column (6 blocks + z + pad)
+  size_t o_Y, o_ph, o_lh, o_items, o_off;
 };
 size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay);
 size_t build3_smem(int max_frames, bool any_ex, int max_prior_n);

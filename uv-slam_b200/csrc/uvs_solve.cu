@@ -135,20 +135,31 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     vec = bz;
     const int warp = tid >> 5, lane = tid & 31;
     {
-      // rows j of the upper triangle of Sg, coalesced over i; element (i,j), j <= i, of the lower matrix
+      // rows j of the upper triangle of Sg, coalesced over i; element (i,j), j <= i, of the lower matrix.
+      // All loads of a row are issued before they are used (up to MAXL per lane in flight).
       const int dp = K * NB;
+      constexpr int MAXL = 8;   // 8 x 32 = 256 >= padded dimension of the blocked path
       for (int j = warp; j < dp; j += CT / 32) {
         const double sj = j < d ? scale[j] : 0.0;
-        for (int i = j + lane; i < dp; i += 32) {
-          double v = 0.0;
+        double v[MAXL];
+#pragma unroll
+        for (int k = 0; k < MAXL; k++) {
+          const int i = j + lane + 32 * k;
+          v[k] = (i < d && j < d) ? Sg[(size_t)j * d + i] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < MAXL; k++) {
+          const int i = j + lane + 32 * k;
+          if (i >= dp) continue;
+          double x = 0.0;
           if (i < d && j < d) {
-            v = scale[i] * sj * Sg[(size_t)j * d + i];
-            if (i == j) { const double h = sj * sj * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+            x = scale[i] * sj * v[k];
+            if (i == j) { const double h = sj * sj * colsq[i]; x += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
           } else if (i == j) {
-            v = 1.0;   // padding
+            x = 1.0;   // padding
           }
           const int I = i >> 3, J = j >> 3;
-          A[((size_t)I * (I + 1) / 2 + J) * BS + (i & 7) * RS + (j & 7)] = v;
+          A[((size_t)I * (I + 1) / 2 + J) * BS + (i & 7) * RS + (j & 7)] = x;
         }
       }
       // strictly-upper parts of the diagonal blocks are never read
