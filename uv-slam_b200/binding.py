@@ -176,13 +176,14 @@ class Solver:
         self._check(self.lib.uvs_solve(self.h, sums), "uvs_solve")
         return sums
 
-    def batch_solve(self, windows, opts=None):
-        """upload + solve + download through the single reference-facing call (host buffers)."""
+    def batch_solve(self, windows, opts=None, prepared=None):
+        """upload + solve + download through the single reference-facing call (host buffers).
+        `prepared` = window_array(windows) built beforehand (the ctypes view of the same host arrays)."""
         if isinstance(windows, Window):
             windows = [windows]
         self.windows = list(windows)
         self.opts = opts if opts is not None else default_options()
-        self._arr = window_array(self.windows)
+        self._arr = prepared if prepared is not None else window_array(self.windows)
         sums = (UvsSummaryStruct * len(self.windows))()
         self._check(self.lib.uvs_batch_solve(self.h, len(self.windows), self._arr, C.byref(self.opts), sums), "uvs_batch_solve")
         return sums

@@ -7,11 +7,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/uvs.h"
@@ -271,7 +273,9 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   std::memcpy(S + o_S_off, h->S_off.data(), (B + 1) * 8);
   std::memcpy(S + o_pJ_off, h->priorJ_off.data(), (B + 1) * 8);
   auto put = [&](size_t off, size_t elem_off, const void *src, size_t bytes) { if (bytes) std::memcpy(S + off + elem_off, src, bytes); };
-  for (int i = 0; i < B; i++) {
+  std::atomic<int> pack_err(0);
+  auto pack_range = [&](int lo, int hi) {
+  for (int i = lo; i < hi; i++) {
     const UvsWindow &x = w[i];
     const size_t f0 = h->frame_off[i], p0 = h->point_off[i], l0 = h->line_off[i], j0 = h->proj_off[i], a0 = h->lobs_off[i],
                  v0 = h->vobs_off[i], m0 = h->imu_off[i], b0 = h->pblk_off[i];
@@ -310,8 +314,8 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
       double *bx = (double *)(S + o_prx) + 9 * b0;
       for (int b = 0; b < x.prior_n_blocks; b++) {
         const int kind = x.prior_block_kind[b], id = x.prior_block_id[b];
-        if (kind < 0 || kind > 3) return fail(h, UVS_ERR_INVALID_ARG, "bad prior block kind");
-        if ((kind <= 1) && (id < 0 || id >= x.n_frames)) return fail(h, UVS_ERR_INVALID_ARG, "prior block id out of range");
+        if (kind < 0 || kind > 3) { pack_err = 1; return; }
+        if ((kind <= 1) && (id < 0 || id >= x.n_frames)) { pack_err = 2; return; }
         bk[b] = kind; bi[b] = id; bcol[b] = col;
         int cam = -1, row = i;
         if (kind == UVS_BLOCK_POSE) { cam = 15 * id; row = (int)f0 + id; }
@@ -323,8 +327,23 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
         for (int k = 0; k < 9; k++) bx[9 * b + k] = k < gs ? x.prior_x0[xo + k] : 0.0;
         xo += gs; col += prior_local(kind);
       }
-      if (col != x.prior_n) return fail(h, UVS_ERR_INVALID_ARG, "prior blocks do not add up to prior_n in window " + std::to_string(i));
+      if (col != x.prior_n) { pack_err = 3; return; }
     }
+  }
+  };
+  {
+    // the copies are independent per window: spread them over host threads for large batches
+    int nt = 1;
+    if (B >= 64) nt = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (nt <= 1) pack_range(0, B);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; t++) th.emplace_back(pack_range, (int)((long long)B * t / nt), (int)((long long)B * (t + 1) / nt));
+      for (auto &t : th) t.join();
+    }
+    if (pack_err == 1) return fail(h, UVS_ERR_INVALID_ARG, "bad prior block kind");
+    if (pack_err == 2) return fail(h, UVS_ERR_INVALID_ARG, "prior block id out of range");
+    if (pack_err == 3) return fail(h, UVS_ERR_INVALID_ARG, "prior blocks do not add up to prior_n");
   }
   char *Dv = h->dev.base;
   CK(cudaMemcpyAsync(Dv, S, in.total, cudaMemcpyHostToDevice, h->stream));

@@ -131,7 +131,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     const int K = (d + NB - 1) / NB;
     double *A = smem;
     double *bz = smem + (size_t)K * (K + 1) / 2 * BS;   // rhs / z / y   [8K]
-    double *invd = bz + (size_t)K * NB;                 // reciprocal diagonal of the current panel [8]
+    double *invd_all = bz + (size_t)K * NB;             // reciprocal diagonal of L, all rows [8K]
     vec = bz;
     const int warp = tid >> 5, lane = tid & 31;
     {
@@ -168,6 +168,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     __syncthreads();
     for (int k = 0; k < K; k++) {
       double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
+      double *invd = invd_all + k * NB;
       if (warp == 0) {
         // factor the diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot
         // chain is rsqrt -> scale -> rank-1 update, operands exchanged with shuffles
@@ -273,7 +274,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
           double v = bz[k * NB + p];
 #pragma unroll
           for (int q = p + 1; q < NB; q++) v -= Akk[q * RS + p] * y[q];
-          y[p] = v / Akk[p * RS + p];
+          y[p] = v * invd_all[k * NB + p];
         }
         __syncwarp();
         for (int c = lane; c < k * NB; c += 32) {
@@ -536,7 +537,7 @@ __global__ void k_copy_acc(Dev D, int slot, double *out, int zero) {
 
 static size_t chol_smem_bytes(int d) {
   const size_t K = (d + NB - 1) / NB;
-  return (K * (K + 1) / 2 * BS + K * NB + NB) * sizeof(double);
+  return (K * (K + 1) / 2 * BS + 2 * K * NB) * sizeof(double);
 }
 int chol_packed_limit(size_t max_smem) {
   int d = NB;
