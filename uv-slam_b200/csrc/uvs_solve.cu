@@ -16,7 +16,10 @@
 
 namespace uvs {
 
-constexpr int CT = 256;
+#ifndef UVS_CHOL_THREADS
+#define UVS_CHOL_THREADS 512
+#endif
+constexpr int CT = UVS_CHOL_THREADS;
 
 __device__ __forceinline__ double clampd2(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
@@ -166,38 +169,40 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     }
     for (int c = tid; c < K * NB; c += CT) bz[c] = c < d ? -scale[c] * gS[c] : 0.0;
     __syncthreads();
-    for (int k = 0; k < K; k++) {
+    // factor of a diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot chain is
+    // rsqrt -> scale -> rank-1 update, operands exchanged with shuffles
+    auto potrf_block = [&](int k) {
       double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
       double *invd = invd_all + k * NB;
-      if (warp == 0) {
-        // factor the diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot
-        // chain is rsqrt -> scale -> rank-1 update, operands exchanged with shuffles
-        double a[NB];
-        const int r = lane & 7;
+      double a[NB];
+      const int r = lane & 7;
 #pragma unroll
-        for (int c = 0; c < NB; c++) a[c] = c <= r ? Akk[r * RS + c] : 0.0;
-        int bad = 0;
+      for (int c = 0; c < NB; c++) a[c] = c <= r ? Akk[r * RS + c] : 0.0;
+      int bad = 0;
 #pragma unroll
-        for (int p = 0; p < NB; p++) {
-          const double piv = __shfl_sync(0xffffffffu, a[p], p);
-          if (!(piv > 0.0) || !isfinite(piv)) bad = 1;
-          const double inv = rsqrt(piv);
-          a[p] = r == p ? piv * inv : a[p] * inv;          // rows r < p are finished (their a[p] is unused)
-          if (r == p && lane < NB) invd[p] = inv;
+      for (int p = 0; p < NB; p++) {
+        const double piv = __shfl_sync(0xffffffffu, a[p], p);
+        if (!(piv > 0.0) || !isfinite(piv)) bad = 1;
+        const double inv = rsqrt(piv);
+        a[p] = r == p ? piv * inv : a[p] * inv;          // rows r < p are finished (their a[p] is unused)
+        if (r == p && lane < NB) invd[p] = inv;
 #pragma unroll
-          for (int q = p + 1; q < NB; q++) {
-            const double lq = __shfl_sync(0xffffffffu, a[p], q);
-            a[q] -= a[p] * lq;                             // only meaningful for r >= q
-          }
+        for (int q = p + 1; q < NB; q++) {
+          const double lq = __shfl_sync(0xffffffffu, a[p], q);
+          a[q] -= a[p] * lq;                             // only meaningful for r >= q
         }
-        if (lane < NB) {
-#pragma unroll
-          for (int c = 0; c < NB; c++) if (c <= r) Akk[r * RS + c] = a[c];
-        }
-        if (lane == 0) s_flag = bad;
       }
-      __syncthreads();
-      if (s_flag) break;
+      if (lane < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; c++) if (c <= r) Akk[r * RS + c] = a[c];
+      }
+      if (lane == 0 && bad) s_flag = 1;
+    };
+    if (warp == 0) potrf_block(0);
+    __syncthreads();
+    for (int k = 0; k < K && !s_flag; k++) {
+      const double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
+      const double *invd = invd_all + k * NB;
       // panel: L_Ik = A_Ik L_kk^-T for the rows below, z_k = L_kk^-1 b_k
       const int nrows = NB * (K - 1 - k);
       for (int t = tid; t <= nrows; t += CT) {
@@ -218,45 +223,65 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
         for (int p = 0; p < NB; p++) row[p] = x[p];
       }
       __syncthreads();
-      // trailing update A_IJ -= L_Ik L_Jk^T with 4x4 register tiles, b_I -= L_Ik z_k
+      // trailing update A_IJ -= L_Ik L_Jk^T (4x4 register tiles), b_I -= L_Ik z_k.  Look-ahead: warp 0 updates
+      // the next diagonal block first and factors it while the other warps update the rest.
       const int nt = K - 1 - k;
-      const int ntiles = 4 * (nt * (nt + 1) / 2);
-      for (int tile = tid; tile < ntiles; tile += CT) {
-        int Ip, Jp;
-        unrank_lower(tile >> 2, Ip, Jp);
-        const int ti = (tile >> 1) & 1, tj = tile & 1;
-        if (Ip == Jp && tj > ti) continue;   // strictly-upper tile of a diagonal block
-        const int I = k + 1 + Ip, J = k + 1 + Jp;
-        const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * BS + ti * 4 * RS;
-        const double *LJ = A + ((size_t)J * (J + 1) / 2 + k) * BS + tj * 4 * RS;
-        double *C = A + ((size_t)I * (I + 1) / 2 + J) * BS + ti * 4 * RS + tj * 4;
-        double c[4][4];
+      if (warp == 0) {
+        if (nt > 0) {
+          const int I = k + 1;
+          const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * BS;
+          double *C = A + ((size_t)I * (I + 1) / 2 + I) * BS;
+          for (int e = lane; e < 64; e += 32) {
+            const int r = e >> 3, q = e & 7;
+            if (q > r) continue;
+            double v = C[r * RS + q];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b2 = 0; b2 < 4; b2++) c[a][b2] = C[a * RS + b2];
-#pragma unroll
-        for (int p = 0; p < NB; p++) {
-          double li[4], lj[4];
-#pragma unroll
-          for (int a = 0; a < 4; a++) { li[a] = LI[a * RS + p]; lj[a] = LJ[a * RS + p]; }
+            for (int p = 0; p < NB; p++) v -= LI[r * RS + p] * LI[q * RS + p];
+            C[r * RS + q] = v;
+          }
+          __syncwarp();
+          potrf_block(k + 1);
+        }
+      } else {
+        const int ntiles = 4 * (nt * (nt + 1) / 2);
+        for (int tile = tid - 32; tile < ntiles; tile += CT - 32) {
+          if (tile < 4) continue;              // block (k+1, k+1): done by warp 0
+          int Ip, Jp;
+          unrank_lower(tile >> 2, Ip, Jp);
+          const int ti = (tile >> 1) & 1, tj = tile & 1;
+          if (Ip == Jp && tj > ti) continue;   // strictly-upper tile of a diagonal block
+          const int I = k + 1 + Ip, J = k + 1 + Jp;
+          const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * BS + ti * 4 * RS;
+          const double *LJ = A + ((size_t)J * (J + 1) / 2 + k) * BS + tj * 4 * RS;
+          double *C = A + ((size_t)I * (I + 1) / 2 + J) * BS + ti * 4 * RS + tj * 4;
+          double c[4][4];
 #pragma unroll
           for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b2 = 0; b2 < 4; b2++) c[a][b2] -= li[a] * lj[b2];
+            for (int b2 = 0; b2 < 4; b2++) c[a][b2] = C[a * RS + b2];
+#pragma unroll
+          for (int p = 0; p < NB; p++) {
+            double li[4], lj[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) { li[a] = LI[a * RS + p]; lj[a] = LJ[a * RS + p]; }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+              for (int b2 = 0; b2 < 4; b2++) c[a][b2] -= li[a] * lj[b2];
+          }
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b2 = 0; b2 < 4; b2++) C[a * RS + b2] = c[a][b2];
         }
+        for (int t = tid - 32; t < nrows; t += CT - 32) {
+          const int i = NB * (k + 1) + t, I = i >> 3;
+          const double *row = A + ((size_t)I * (I + 1) / 2 + k) * BS + (i & 7) * RS;
+          double v = bz[i];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b2 = 0; b2 < 4; b2++) C[a * RS + b2] = c[a][b2];
-      }
-      for (int t = tid; t < nrows; t += CT) {
-        const int i = NB * (k + 1) + t, I = i >> 3;
-        const double *row = A + ((size_t)I * (I + 1) / 2 + k) * BS + (i & 7) * RS;
-        double v = bz[i];
-#pragma unroll
-        for (int p = 0; p < NB; p++) v -= row[p] * bz[k * NB + p];
-        bz[i] = v;
+          for (int p = 0; p < NB; p++) v -= row[p] * bz[k * NB + p];
+          bz[i] = v;
+        }
       }
       __syncthreads();
     }
