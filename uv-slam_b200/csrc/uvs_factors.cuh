@@ -114,16 +114,14 @@ __device__ __forceinline__ void proj_eval(const double *__restrict__ pose_i, con
 // ---------------------------------------------------------------------------------------------
 // Shared transform of LineProjectionFactor / VPProjectionFactor (line_projection_factor.h:21-53).
 // Produces n_c, d_c and their 10 partials: columns 0-2 = p, 3-5 = raw (qx,qy,qz), 6-8 = psi, 9 = phi.
-struct LineCam {
-  d3 n, d;        // n_c, d_c
-  d3 dn[11];      // d n_c / d theta_k      (k = 10: raw qw, only when kQw)
-  d3 dd[11];      // d d_c / d theta_k   (zero for k < 3)
-};
-
-template <bool kJac, bool kNeedN, bool kQw>
+// The transform is written as a producer: `sink.base(n_c, d_c)` is called once, then
+// `sink.partial(k, dn_c/dtheta_k, dd_c/dtheta_k)` for k = 0-2 (p), 3-5 (raw qx,qy,qz), 6-8 (psi), 9 (phi) and, when kQw,
+// 10 (raw qw).  The consumer turns every partial into its Jacobian entries immediately, so no array of partials
+// stays live in registers.
+template <bool kJac, bool kNeedN, bool kQw, class Sink>
 __device__ __forceinline__ void line_to_camera(const double *__restrict__ pose, const double *__restrict__ line,
                                                const double *__restrict__ ric_rm, const double *__restrict__ tic3,
-                                               LineCam &o) {
+                                               Sink &sink) {
   d3 p; q4 q;
   load_pose(pose, p, q);
   m33 ric;
@@ -142,115 +140,121 @@ __device__ __forceinline__ void line_to_camera(const double *__restrict__ pose, 
   const d3 twc = mvec(R, tic) + p;
   const d3 av = mvec(A, twc);           // -t_cw
   const d3 u = mvec(A, dw);             // d_c
-  o.d = u;
-  if (kNeedN) o.n = mvec(A, nw) - cross(av, u);
+  const d3 zero = mk3(0, 0, 0);
+  sink.base(kNeedN ? mvec(A, nw) - cross(av, u) : zero, u);
   if (!kJac) return;
   // translation
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    o.dd[k] = mk3(0, 0, 0);
-    if (kNeedN) o.dn[k] = -cross(mcol(A, k), u);
-  }
-  // raw quaternion coordinates: G_m = dR/dq_m
+  for (int k = 0; k < 3; k++) sink.partial(k, kNeedN ? -cross(mcol(A, k), u) : zero, zero);
+  // raw quaternion coordinates: G_m = dR/dq_m, applied as G^T v (m = 0,1,2: x,y,z; 3: w)
   {
     const double x2 = 2 * q.x, y2 = 2 * q.y, z2 = 2 * q.z, w2 = 2 * q.w;
-    m33 G[4];
-    G[0].a[0] = 0;        G[0].a[1] = y2;       G[0].a[2] = z2;
-    G[0].a[3] = y2;       G[0].a[4] = -2 * x2;  G[0].a[5] = -w2;
-    G[0].a[6] = z2;       G[0].a[7] = w2;       G[0].a[8] = -2 * x2;
-    G[1].a[0] = -2 * y2;  G[1].a[1] = x2;       G[1].a[2] = w2;
-    G[1].a[3] = x2;       G[1].a[4] = 0;        G[1].a[5] = z2;
-    G[1].a[6] = -w2;      G[1].a[7] = z2;       G[1].a[8] = -2 * y2;
-    G[2].a[0] = -2 * z2;  G[2].a[1] = -w2;      G[2].a[2] = x2;
-    G[2].a[3] = w2;       G[2].a[4] = -2 * z2;  G[2].a[5] = y2;
-    G[2].a[6] = x2;       G[2].a[7] = y2;       G[2].a[8] = 0;
-    // dR/dqw = 2 [u]x
-    G[3].a[0] = 0;        G[3].a[1] = -z2;      G[3].a[2] = y2;
-    G[3].a[3] = z2;       G[3].a[4] = 0;        G[3].a[5] = -x2;
-    G[3].a[6] = -y2;      G[3].a[7] = x2;       G[3].a[8] = 0;
+    auto GT = [&](int m, d3 v) -> d3 {   // G_m^T v
+      if (m == 0) return mk3(y2 * v.y + z2 * v.z, y2 * v.x - 2 * x2 * v.y + w2 * v.z, z2 * v.x - w2 * v.y - 2 * x2 * v.z);
+      if (m == 1) return mk3(-2 * y2 * v.x + x2 * v.y - w2 * v.z, x2 * v.x + z2 * v.z, w2 * v.x + z2 * v.y - 2 * y2 * v.z);
+      if (m == 2) return mk3(-2 * z2 * v.x + w2 * v.y + x2 * v.z, -w2 * v.x - 2 * z2 * v.y + y2 * v.z, x2 * v.x + y2 * v.y);
+      return mk3(z2 * v.y - y2 * v.z, -z2 * v.x + x2 * v.z, y2 * v.x - x2 * v.y);
+    };
+    auto G = [&](int m, d3 v) -> d3 {    // G_m v
+      if (m == 0) return mk3(y2 * v.y + z2 * v.z, y2 * v.x - 2 * x2 * v.y - w2 * v.z, z2 * v.x + w2 * v.y - 2 * x2 * v.z);
+      if (m == 1) return mk3(-2 * y2 * v.x + x2 * v.y + w2 * v.z, x2 * v.x + z2 * v.z, -w2 * v.x + z2 * v.y - 2 * y2 * v.z);
+      if (m == 2) return mk3(-2 * z2 * v.x - w2 * v.y + x2 * v.z, w2 * v.x - 2 * z2 * v.y + y2 * v.z, x2 * v.x + y2 * v.y);
+      return mk3(-z2 * v.y + y2 * v.z, z2 * v.x - x2 * v.z, -y2 * v.x + x2 * v.y);
+    };
 #pragma unroll
     for (int m = 0; m < (kQw ? 4 : 3); m++) {
       const int slot = m < 3 ? 3 + m : 10;
       // A' v = ric^T (G^T v)
-      const d3 du = mtvec(ric, mtvec(G[m], dw));
-      o.dd[slot] = du;
+      const d3 du = mtvec(ric, GT(m, dw));
+      d3 dn = zero;
       if (kNeedN) {
-        const d3 dm = mtvec(ric, mtvec(G[m], nw));
-        const d3 da = mtvec(ric, mtvec(G[m], twc)) + mvec(A, mvec(G[m], tic));
-        o.dn[slot] = dm - cross(da, u) - cross(av, du);
+        const d3 dm = mtvec(ric, GT(m, nw));
+        const d3 da = mtvec(ric, GT(m, twc)) + mvec(A, G(m, tic));
+        dn = dm - cross(da, u) - cross(av, du);
       }
+      sink.partial(slot, dn, du);
     }
   }
   // line parameters
   {
-    d3 du0[3], du1[3];
-    du0[0] = mk3(0.0, -sa * sc + ca * sb * cc, ca * sc + sa * sb * cc);
-    du0[1] = mk3(-sb * cc, sa * cb * cc, -ca * cb * cc);
-    du0[2] = u1;
-    du1[0] = mk3(0.0, -sa * cc - ca * sb * sc, ca * cc - sa * sb * sc);
-    du1[1] = mk3(sb * sc, -sa * cb * sc, ca * cb * sc);
-    du1[2] = -u0;
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-      const d3 du = mvec(A, sp * du1[m]);
-      o.dd[6 + m] = du;
-      if (kNeedN) o.dn[6 + m] = mvec(A, cp * du0[m]) - cross(av, du);
+    const d3 du0a = mk3(0.0, -sa * sc + ca * sb * cc, ca * sc + sa * sb * cc), du1a = mk3(0.0, -sa * cc - ca * sb * sc, ca * cc - sa * sb * sc);
+    const d3 du0b = mk3(-sb * cc, sa * cb * cc, -ca * cb * cc), du1b = mk3(sb * sc, -sa * cb * sc, ca * cb * sc);
+    { const d3 du = mvec(A, sp * du1a); sink.partial(6, kNeedN ? mvec(A, cp * du0a) - cross(av, du) : zero, du); }
+    { const d3 du = mvec(A, sp * du1b); sink.partial(7, kNeedN ? mvec(A, cp * du0b) - cross(av, du) : zero, du); }
+    { const d3 du = mvec(A, (-sp) * u0); sink.partial(8, kNeedN ? mvec(A, cp * u1) - cross(av, du) : zero, du); }
+    { const d3 du = mvec(A, cp * u1); sink.partial(9, kNeedN ? mvec(A, (-sp) * u0) - cross(av, du) : zero, du); }
+  }
+}
+
+// LineProjectionFactor: residual r[2] -> out_r, Jacobian entries -> out_jp (2 x PW pose block, row stride PW; the raw qw
+// derivative goes to column 6 when kQw) and out_jl (2 x 4).  When `correct`, the Cauchy corrector is folded in.
+template <bool kJac, bool kQw>
+struct LineSink {
+  double spx, spy, epx, epy, lf, loss_a;
+  bool correct;
+  int PW;
+  double *out_r, *out_jp, *out_jl;
+  double half_rho;
+  // state between base() and partial()
+  double nx, ny, irho, irho3, ds, de, sq;
+  __device__ __forceinline__ void base(d3 n, d3) {
+    const double rho2 = n.x * n.x + n.y * n.y;
+    irho = rsqrt(rho2);
+    irho3 = irho * irho * irho;
+    nx = n.x; ny = n.y;
+    ds = spx * n.x + spy * n.y + n.z;
+    de = epx * n.x + epy * n.y + n.z;
+    const double r0 = lf * ds * irho, r1 = lf * de * irho;
+    const double s = r0 * r0 + r1 * r1;
+    sq = 1.0;
+    if (correct && loss_a > 0.0) { double rho0, rho1; cauchy(loss_a, s, rho0, rho1); half_rho = 0.5 * rho0; sq = sqrt(rho1); }
+    else half_rho = 0.5 * s;
+    out_r[0] = sq * r0; out_r[1] = sq * r1;
+  }
+  __device__ __forceinline__ void partial(int k, d3 dn, d3) {
+    const double drho = (nx * dn.x + ny * dn.y) * irho3;
+    const double f = lf * sq;
+    const double j0 = f * ((spx * dn.x + spy * dn.y + dn.z) * irho - ds * drho);
+    const double j1 = f * ((epx * dn.x + epy * dn.y + dn.z) * irho - de * drho);
+    if (k < 6) { out_jp[k] = j0; out_jp[PW + k] = j1; }
+    else if (k < 10) { out_jl[k - 6] = j0; out_jl[4 + k - 6] = j1; }
+    else { out_jp[6] = j0; out_jp[PW + 6] = j1; }
+  }
+};
+
+template <bool kJac, bool kQw>
+struct VpSink {
+  d3 vp;
+  double vf, loss_a;
+  bool correct;
+  double *out_r, *out_jp, *out_jl;
+  double half_rho;
+  d3 dvec;
+  double g, i1, i3;
+  __device__ __forceinline__ void base(d3, d3 d) {
+    dvec = d;
+    const double un2 = dot(d, d), vn2 = dot(vp, vp);
+    const double iuv = rsqrt(un2 * vn2);
+    const double uv = dot(d, vp);
+    const double c = uv * iuv;
+    const double ac = fabs(c);
+    const double r0 = vf * acos(ac);
+    const double s = r0 * r0;
+    double sq = 1.0;
+    if (correct && loss_a > 0.0) { double rho0, rho1; cauchy(loss_a, s, rho0, rho1); half_rho = 0.5 * rho0; sq = sqrt(rho1); }
+    else half_rho = 0.5 * s;
+    out_r[0] = sq * r0;
+    if (kJac) {
+      g = sq * vf * (c < 0.0 ? 1.0 : -1.0) * rsqrt(1.0 - ac * ac);
+      i1 = iuv; i3 = uv * iuv / un2;
     }
-    const d3 du = mvec(A, cp * u1);
-    o.dd[9] = du;
-    if (kNeedN) o.dn[9] = mvec(A, (-sp) * u0) - cross(av, du);
   }
-}
-
-// LineProjectionFactor residual + Jacobian [2 x NP]: cols 0-5 pose tangent, 6-9 line (10: raw qw).
-template <bool kJac, bool kQw>
-__device__ __forceinline__ void line_eval(const double *__restrict__ pose, const double *__restrict__ line,
-                                          const double *__restrict__ ric, const double *__restrict__ tic, double spx,
-                                          double spy, double epx, double epy, double line_factor, double r[2],
-                                          double *J /*[2][NP]*/) {
-  constexpr int NP = kQw ? 11 : 10;
-  LineCam lc;
-  line_to_camera<kJac, true, kQw>(pose, line, ric, tic, lc);
-  const double rho2 = lc.n.x * lc.n.x + lc.n.y * lc.n.y;
-  const double rho = sqrt(rho2);
-  const double ds = spx * lc.n.x + spy * lc.n.y + lc.n.z;
-  const double de = epx * lc.n.x + epy * lc.n.y + lc.n.z;
-  r[0] = line_factor * ds / rho;
-  r[1] = line_factor * de / rho;
-  if (!kJac) return;
-  const double irho = 1.0 / rho, irho3 = irho / rho2;
-#pragma unroll
-  for (int k = 0; k < NP; k++) {
-    const d3 dn = lc.dn[k];
-    const double drho = (lc.n.x * dn.x + lc.n.y * dn.y) * irho3;
-    J[k] = line_factor * ((spx * dn.x + spy * dn.y + dn.z) * irho - ds * drho);
-    J[NP + k] = line_factor * ((epx * dn.x + epy * dn.y + dn.z) * irho - de * drho);
+  __device__ __forceinline__ void partial(int k, d3, d3 du) {
+    const double j = k < 3 ? 0.0 : g * (dot(vp, du) * i1 - dot(dvec, du) * i3);
+    if (k < 6) out_jp[k] = j;
+    else if (k < 10) out_jl[k - 6] = j;
+    else out_jp[6] = j;
   }
-}
-
-// VPProjectionFactor residual + Jacobian [1 x NP]
-template <bool kJac, bool kQw>
-__device__ __forceinline__ void vp_eval(const double *__restrict__ pose, const double *__restrict__ line,
-                                        const double *__restrict__ ric, const double *__restrict__ tic, d3 vp,
-                                        double vp_factor, double r[1], double *J /*[NP]*/) {
-  constexpr int NP = kQw ? 11 : 10;
-  LineCam lc;
-  line_to_camera<kJac, false, kQw>(pose, line, ric, tic, lc);
-  const double un = sqrt(dot(lc.d, lc.d)), vn = sqrt(dot(vp, vp));
-  const double uv = dot(lc.d, vp);
-  const double c = uv / (un * vn);
-  const double ac = fabs(c);
-  r[0] = vp_factor * acos(ac);
-  if (!kJac) return;
-  const double sgn = c < 0.0 ? -1.0 : 1.0;
-  const double g = vp_factor * sgn * (-1.0 / sqrt(1.0 - ac * ac));
-  const double i1 = 1.0 / (un * vn), i3 = uv / (un * un * un * vn);
-#pragma unroll
-  for (int k = 0; k < NP; k++) {
-    if (k < 3) { J[k] = 0.0; continue; }
-    const d3 du = lc.dd[k];
-    J[k] = g * (dot(vp, du) * i1 - dot(lc.d, du) * i3);
-  }
-}
+};
 
 }  // namespace uvs

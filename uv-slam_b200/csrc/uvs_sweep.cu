@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NT, 4) k_proj(Dev D, Params P, int mode, int c
 
 // ------------------------------------------------------------------------------------------------
 template <bool kJac, bool kCeres>
-__global__ void __launch_bounds__(NT, 4) k_line(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+__global__ void __launch_bounds__(NT, 3) k_line(Dev D, Params P, int mode, int cand, double *__restrict__ out,
                                              double *__restrict__ res_out, double *cost, int cost_stride) {
   constexpr int REC = kCeres ? CREC_LINE : REC_LINE;
   constexpr int NP = kCeres ? 11 : 10;
@@ -151,27 +151,16 @@ __global__ void __launch_bounds__(NT, 4) k_line(Dev D, Params P, int mode, int c
   if (valid) {
     const int buf = D.cur[ix.z] ^ cand;
     const double *sp = D.line_sp + 2 * (size_t)f, *ep = D.line_ep + 2 * (size_t)f;
-    double r[2], J[2 * NP];
-    line_eval<kJac, kCeres>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
-                            D.tic + 3 * (size_t)ix.z, __ldg(sp), __ldg(sp + 1), __ldg(ep), __ldg(ep + 1), P.line_factor, r, J);
-    const double s = r[0] * r[0] + r[1] * r[1];
-    double sq = 1.0;
-    if (kCeres) half_rho = 0.5 * s; else sq = corrector(P.cauchy_line, s, half_rho);
-    r[0] *= sq; r[1] *= sq;
-    if (kJac) {
-      double *t = tile + threadIdx.x * (REC + 1);
-      t[0] = r[0]; t[1] = r[1];
-#pragma unroll
-      for (int row = 0; row < 2; row++) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) t[2 + row * PW + c] = sq * J[row * NP + c];
-        if (kCeres) t[2 + row * 7 + 6] = J[row * NP + 10];
-#pragma unroll
-        for (int c = 0; c < 4; c++) t[2 + 2 * PW + row * 4 + c] = sq * J[row * NP + 6 + c];
-      }
-    } else if (res_out) {
-      res_out[2 * (size_t)f] = r[0]; res_out[2 * (size_t)f + 1] = r[1];
-    }
+    LineSink<kJac, kCeres> sink;
+    sink.spx = __ldg(sp); sink.spy = __ldg(sp + 1); sink.epx = __ldg(ep); sink.epy = __ldg(ep + 1);
+    sink.lf = P.line_factor; sink.loss_a = P.cauchy_line; sink.correct = !kCeres; sink.PW = PW;
+    double rloc[2];
+    if (kJac) { double *t = tile + threadIdx.x * (REC + 1); sink.out_r = t; sink.out_jp = t + 2; sink.out_jl = t + 2 + 2 * PW; }
+    else { sink.out_r = rloc; sink.out_jp = nullptr; sink.out_jl = nullptr; }
+    line_to_camera<kJac, true, kCeres>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
+                                       D.tic + 3 * (size_t)ix.z, sink);
+    half_rho = sink.half_rho;
+    if (!kJac && res_out) { res_out[2 * (size_t)f] = rloc[0]; res_out[2 * (size_t)f + 1] = rloc[1]; }
   }
   if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
   if (kJac) {
@@ -203,24 +192,16 @@ __global__ void __launch_bounds__(NT, 4) k_vp(Dev D, Params P, int mode, int can
   if (valid) {
     const int buf = D.cur[ix.z] ^ cand;
     const double *vp = D.vp_dir + 3 * (size_t)f;
-    double r[1], J[NP];
-    vp_eval<kJac, kCeres>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
-                          D.tic + 3 * (size_t)ix.z, mk3(__ldg(vp), __ldg(vp + 1), __ldg(vp + 2)), P.vp_factor, r, J);
-    const double s = r[0] * r[0];
-    double sq = 1.0;
-    if (kCeres) half_rho = 0.5 * s; else sq = corrector(P.cauchy_vp, s, half_rho);
-    r[0] *= sq;
-    if (kJac) {
-      double *t = tile + threadIdx.x * (REC + 1);
-      t[0] = r[0];
-#pragma unroll
-      for (int c = 0; c < 6; c++) t[1 + c] = sq * J[c];
-      if (kCeres) t[1 + 6] = J[10];
-#pragma unroll
-      for (int c = 0; c < 4; c++) t[1 + PW + c] = sq * J[6 + c];
-    } else if (res_out) {
-      res_out[f] = r[0];
-    }
+    VpSink<kJac, kCeres> sink;
+    sink.vp = mk3(__ldg(vp), __ldg(vp + 1), __ldg(vp + 2));
+    sink.vf = P.vp_factor; sink.loss_a = P.cauchy_vp; sink.correct = !kCeres;
+    double rloc[1];
+    if (kJac) { double *t = tile + threadIdx.x * (REC + 1); sink.out_r = t; sink.out_jp = t + 1; sink.out_jl = t + 1 + PW; }
+    else { sink.out_r = rloc; sink.out_jp = nullptr; sink.out_jl = nullptr; }
+    line_to_camera<kJac, false, kCeres>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
+                                        D.tic + 3 * (size_t)ix.z, sink);
+    half_rho = sink.half_rho;
+    if (!kJac && res_out) res_out[f] = rloc[0];
   }
   if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
   if (kJac) {
