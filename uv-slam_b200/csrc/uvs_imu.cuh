@@ -1,10 +1,10 @@
-// uvs_imu.cuh — warp-cooperative IMU preintegration factor and the prior residual.
+// uvs_imu.cuh — IMU preintegration factor.
 //
 // IMUFactor::Evaluate (factor/imu_factor.h:19-182) + IntegrationBase::evaluate
-// (factor/integration_base.h:160-186).  One warp per factor: every lane computes the (cheap) frame
-// geometry redundantly, the 15x30 raw Jacobian is assembled in shared memory and the
-// sqrt_info (15x15 upper-triangular) left-multiply is spread over the lanes so that consecutive
-// lanes write consecutive doubles of the record.
+// (factor/integration_base.h:160-186).  Two phases (see k_imu in uvs_sweep.cu): one THREAD per factor computes
+// the frame geometry (a long dependent chain of quaternion algebra - doing it once per lane instead of once
+// per warp cuts the issued instructions 3x), then one WARP per factor applies the sqrt_info (15x15
+// upper-triangular) left-multiply so that consecutive lanes write consecutive doubles of the record.
 #pragma once
 #include "uvs_math.cuh"
 
@@ -41,10 +41,15 @@ struct ImuIn {
   const double *sqrt_info;  // 15x15 upper
 };
 
-// Computes the weighted residual (returned for row `lane` < 15, 0 otherwise) and, when kJac, fills
-// Jraw (15x30 row-major, shared memory, this warp's slice) with the UNWEIGHTED Jacobian.
+// Geometry of one factor by ONE thread: unweighted residual raw[15] and, when kJac, the twelve 3x3 blocks the
+// unweighted Jacobian is made of (compact form, 9 doubles each, IMU_NBLK blocks):
+//   0 RiT   1 [a]x   2 -(Qleft(qj^-1 qi) Qright(dq^))_br   3 [b]x   4 RiT*T   5 dp_dba   6 dp_dbg
+//   7 -Qleft(qj^-1 qi dq)_br dq_dbg   8 dv_dba   9 dv_dbg   10 Qleft(dq^^-1 qi^-1 qj)_br   11 I
+constexpr int IMU_NBLK = 12;
+constexpr int IMU_COMP = 9 * IMU_NBLK;
+
 template <bool kJac>
-__device__ __forceinline__ double imu_eval_warp(const ImuIn &in, const double g[3], int lane, double *Jraw) {
+__device__ __forceinline__ void imu_geometry(const ImuIn &in, const double g[3], double raw[15], double *comp) {
   d3 Pi, Pj; q4 Qi, Qj;
   load_pose(in.pose_i, Pi, Qi);
   load_pose(in.pose_j, Pj, Qj);
@@ -56,7 +61,6 @@ __device__ __forceinline__ double imu_eval_warp(const ImuIn &in, const double g[
   const d3 Bgj = mk3(__ldg(in.sb_j + 6), __ldg(in.sb_j + 7), __ldg(in.sb_j + 8));
   const d3 G = mk3(g[0], g[1], g[2]);
   const double T = in.sum_dt;
-
   const m33 dp_dba = ld33(in.jac, 0, 9), dp_dbg = ld33(in.jac, 0, 12), dq_dbg = ld33(in.jac, 3, 12);
   const m33 dv_dba = ld33(in.jac, 6, 9), dv_dbg = ld33(in.jac, 6, 12);
   const d3 dba = Bai - mk3(__ldg(in.lin_ba), __ldg(in.lin_ba + 1), __ldg(in.lin_ba + 2));
@@ -66,75 +70,68 @@ __device__ __forceinline__ double imu_eval_warp(const ImuIn &in, const double g[
   const q4 cdq = qmul(delta_q, mkq(th.x / 2.0, th.y / 2.0, th.z / 2.0, 1.0));   // corrected_delta_q (not unit)
   const d3 cdv = mk3(__ldg(in.dv), __ldg(in.dv + 1), __ldg(in.dv + 2)) + mvec(dv_dba, dba) + mvec(dv_dbg, dbg);
   const d3 cdp = mk3(__ldg(in.dp), __ldg(in.dp + 1), __ldg(in.dp + 2)) + mvec(dp_dba, dba) + mvec(dp_dbg, dbg);
-
   const q4 Qi_inv = qinv(Qi);
   const d3 a = qrot(Qi_inv, (0.5 * T * T) * G + Pj - Pi - T * Vi);
   const d3 b = qrot(Qi_inv, T * G + Vj - Vi);
   const q4 qij = qmul(Qi_inv, Qj);
-  const d3 rq = 2.0 * qvec(qmul(qinv(cdq), qij));
-  double raw[15];
+  const q4 qlast = qmul(qinv(cdq), qij);
+  const d3 rq = 2.0 * qvec(qlast);
+  const d3 rp = a - cdp, rv = b - cdv, rba = Baj - Bai, rbg = Bgj - Bgi;
+  raw[0] = rp.x; raw[1] = rp.y; raw[2] = rp.z; raw[3] = rq.x; raw[4] = rq.y; raw[5] = rq.z;
+  raw[6] = rv.x; raw[7] = rv.y; raw[8] = rv.z; raw[9] = rba.x; raw[10] = rba.y; raw[11] = rba.z;
+  raw[12] = rbg.x; raw[13] = rbg.y; raw[14] = rbg.z;
+  if (!kJac) return;
+  auto store = [&](int blk, const m33 &M, double sgn) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) comp[9 * blk + k] = sgn * M.a[k];
+  };
+  const m33 RiT = qmat(Qi_inv);
+  const q4 qji = qmul(qinv(Qj), Qi);
+  store(0, RiT, 1.0);
+  store(1, skew(a), 1.0);
   {
-    const d3 rp = a - cdp, rv = b - cdv, rba = Baj - Bai, rbg = Bgj - Bgi;
-    raw[0] = rp.x; raw[1] = rp.y; raw[2] = rp.z;
-    raw[3] = rq.x; raw[4] = rq.y; raw[5] = rq.z;
-    raw[6] = rv.x; raw[7] = rv.y; raw[8] = rv.z;
-    raw[9] = rba.x; raw[10] = rba.y; raw[11] = rba.z;
-    raw[12] = rbg.x; raw[13] = rbg.y; raw[14] = rbg.z;
-  }
-  double res = 0.0;
-  if (lane < 15) {
+    // -(Qleft(Qj^-1 Qi) Qright(corrected_delta_q)).bottomRightCorner<3,3>()        imu_factor.h:100-101
+    const d3 u = qvec(qji), v = qvec(cdq);
+    const m33 Lbr = qleft_br(qji);
+    m33 Rbr = skew(v);
 #pragma unroll
-    for (int k = 0; k < 15; k++) res += __ldg(in.sqrt_info + lane * 15 + k) * raw[k];
+    for (int k = 0; k < 9; k++) Rbr.a[k] = -Rbr.a[k];
+    Rbr.a[0] += cdq.w; Rbr.a[4] += cdq.w; Rbr.a[8] += cdq.w;
+    m33 M = mmul(Lbr, Rbr);
+    M.a[0] += u.x * -v.x; M.a[1] += u.x * -v.y; M.a[2] += u.x * -v.z;
+    M.a[3] += u.y * -v.x; M.a[4] += u.y * -v.y; M.a[5] += u.y * -v.z;
+    M.a[6] += u.z * -v.x; M.a[7] += u.z * -v.y; M.a[8] += u.z * -v.z;
+    store(2, M, -1.0);
   }
-  if (kJac) {
-    for (int e = lane; e < 450; e += 32) Jraw[e] = 0.0;
-    __syncwarp();
-    const m33 RiT = qmat(Qi_inv);
-    const q4 qji = qmul(qinv(Qj), Qi);
-    switch (lane) {
-      // pose_i: columns 0-5
-      case 0: put33(Jraw, 30, 0, 0, RiT, -1.0); break;
-      case 1: put33(Jraw, 30, 0, 3, skew(a), 1.0); break;
-      case 2: {
-        // -(Qleft(Qj^-1 Qi) Qright(corrected_delta_q)).bottomRightCorner<3,3>()        imu_factor.h:100-101
-        // rows 1..3 of the 4x4 product restricted to columns 1..3 (order w,x,y,z)
-        const d3 u = qvec(qji), v = qvec(cdq);
-        const m33 Lbr = qleft_br(qji);
-        m33 Rbr = skew(v);
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rbr.a[k] = -Rbr.a[k];
-        Rbr.a[0] += cdq.w; Rbr.a[4] += cdq.w; Rbr.a[8] += cdq.w;
-        m33 M = mmul(Lbr, Rbr);
-        // + column 0 of L rows (= u) times row 0 of R columns 1..3 (= -v)
-        M.a[0] += u.x * -v.x; M.a[1] += u.x * -v.y; M.a[2] += u.x * -v.z;
-        M.a[3] += u.y * -v.x; M.a[4] += u.y * -v.y; M.a[5] += u.y * -v.z;
-        M.a[6] += u.z * -v.x; M.a[7] += u.z * -v.y; M.a[8] += u.z * -v.z;
-        put33(Jraw, 30, 3, 3, M, -1.0);
-      } break;
-      case 3: put33(Jraw, 30, 6, 3, skew(b), 1.0); break;
-      // speed-bias_i: columns 6-14
-      case 4: { m33 M = RiT; for (int k = 0; k < 9; k++) M.a[k] *= T; put33(Jraw, 30, 0, 6, M, -1.0); } break;
-      case 5: put33(Jraw, 30, 0, 9, dp_dba, -1.0); break;
-      case 6: put33(Jraw, 30, 0, 12, dp_dbg, -1.0); break;
-      // -Qleft(Qj^-1 Qi delta_q).bottomRightCorner<3,3>() dq_dbg   (delta_q, not corrected)   imu_factor.h:128
-      case 7: put33(Jraw, 30, 3, 12, mmul(qleft_br(qmul(qji, delta_q)), dq_dbg), -1.0); break;
-      case 8: put33(Jraw, 30, 6, 6, RiT, -1.0); break;
-      case 9: put33(Jraw, 30, 6, 9, dv_dba, -1.0); break;
-      case 10: put33(Jraw, 30, 6, 12, dv_dbg, -1.0); break;
-      case 11: Jraw[9 * 30 + 9] = Jraw[10 * 30 + 10] = Jraw[11 * 30 + 11] = -1.0; break;
-      case 12: Jraw[12 * 30 + 12] = Jraw[13 * 30 + 13] = Jraw[14 * 30 + 14] = -1.0; break;
-      // pose_j: columns 15-20
-      case 13: put33(Jraw, 30, 0, 15, RiT, 1.0); break;
-      case 14: put33(Jraw, 30, 3, 18, qleft_br(qmul(qinv(cdq), qij)), 1.0); break;
-      // speed-bias_j: columns 21-29
-      case 15: put33(Jraw, 30, 6, 21, RiT, 1.0); break;
-      case 16: Jraw[9 * 30 + 24] = Jraw[10 * 30 + 25] = Jraw[11 * 30 + 26] = 1.0; break;
-      case 17: Jraw[12 * 30 + 27] = Jraw[13 * 30 + 28] = Jraw[14 * 30 + 29] = 1.0; break;
-      default: break;
-    }
-    __syncwarp();
+  store(3, skew(b), 1.0);
+  { m33 M = RiT; for (int k = 0; k < 9; k++) M.a[k] *= T; store(4, M, 1.0); }
+  store(5, dp_dba, 1.0); store(6, dp_dbg, 1.0);
+  // -Qleft(Qj^-1 Qi delta_q).bottomRightCorner<3,3>() dq_dbg   (delta_q, not corrected)   imu_factor.h:128
+  store(7, mmul(qleft_br(qmul(qji, delta_q)), dq_dbg), -1.0);
+  store(8, dv_dba, 1.0); store(9, dv_dbg, 1.0);
+  store(10, qleft_br(qlast), 1.0);
+  { m33 I; for (int k = 0; k < 9; k++) I.a[k] = (k % 4 == 0) ? 1.0 : 0.0; store(11, I, 1.0); }
+}
+
+// where the compact blocks go in the 15 x 30 unweighted Jacobian: {row0, col0, block, sign}
+struct ImuPut { signed char r0, c0, blk, sgn; };
+__constant__ ImuPut c_imu_puts[18] = {
+    {0, 0, 0, -1}, {0, 3, 1, 1}, {3, 3, 2, 1}, {6, 3, 3, 1},                                   // pose_i
+    {0, 6, 4, -1}, {0, 9, 5, -1}, {0, 12, 6, -1}, {3, 12, 7, 1}, {6, 6, 0, -1}, {6, 9, 8, -1},  // speed-bias_i
+    {6, 12, 9, -1}, {9, 9, 11, -1}, {12, 12, 11, -1},
+    {0, 15, 0, 1}, {3, 18, 10, 1},                                                             // pose_j
+    {6, 21, 0, 1}, {9, 24, 11, 1}, {12, 27, 11, 1}};                                           // speed-bias_j
+
+// expands the compact blocks into the dense 15 x 30 Jacobian (one warp, shared memory)
+__device__ __forceinline__ void imu_expand_warp(const double *comp, double *Jraw, int lane) {
+  for (int e = lane; e < 450; e += 32) Jraw[e] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < 18 * 9; e += 32) {
+    const int b = e / 9, k = e - 9 * b;
+    const ImuPut p = c_imu_puts[b];
+    Jraw[(p.r0 + k / 3) * 30 + p.c0 + k % 3] = (double)p.sgn * comp[9 * p.blk + k];
   }
-  return res;
+  __syncwarp();
 }
 
 }  // namespace uvs

@@ -339,7 +339,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
       __syncthreads();
       const double zj = vec[j];
       for (int i = j + 1 + tid; i < d; i += CT) vec[i] -= Sg[(size_t)i * d + j] * zj;
-      for (int i = j + 1 + ti; i < d; i += 16) {
+      for (int i = j + 1 + ti; i < d; i += CT / 16) {
         const double lij = Sg[(size_t)i * d + j];
         for (int k = j + 1 + tk; k <= i; k += 16) Sg[(size_t)i * d + k] -= lij * Sg[(size_t)k * d + j];
       }

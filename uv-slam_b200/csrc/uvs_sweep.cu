@@ -212,44 +212,77 @@ __global__ void __launch_bounds__(NT, 4) k_vp(Dev D, Params P, int mode, int can
 }
 
 // ------------------------------------------------------------------------------------------------
-// IMU: one warp per factor, 4 warps per CTA.  Record = [r(15) | sqrt_info * J (15x30 row-major)].
+// IMU: 32 factors per CTA.  Phase 1: one thread per factor computes the frame geometry (unweighted residual and
+// the twelve 3x3 blocks of the unweighted Jacobian) and the weighted residual.  Phase 2 (Jacobian mode): the four
+// warps take eight factors each, expand the blocks to the dense 15x30 matrix in shared memory and spread the
+// sqrt_info (15x15 upper-triangular) left-multiply over the lanes, consecutive lanes writing consecutive doubles.
+// Record = [r(15) | sqrt_info * J (15x30 row-major)].
+constexpr int IMU_PER_CTA = 8;
+
 template <bool kJac>
-__global__ void __launch_bounds__(NT) k_imu(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+__global__ void __launch_bounds__(NT, 4) k_imu(Dev D, Params P, int mode, int cand, double *__restrict__ out,
                                             double *__restrict__ res_out, double *cost, int cost_stride) {
-  __shared__ double Jraw_all[NT / 32][450];
+  __shared__ double comp_all[kJac ? IMU_PER_CTA : 1][kJac ? IMU_COMP : 1];
+  __shared__ double res_all[IMU_PER_CTA][15];
+  __shared__ double Jraw_all[kJac ? NT / 32 : 1][kJac ? 450 : 1];
+  __shared__ unsigned char ok_all[IMU_PER_CTA];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * (NT / 32) + warp;
-  if (f >= D.nImu) return;
-  const int2 ix = D.imu_idx[f];
-  if (!wants<kJac>(D.ctl[ix.y].state, mode)) return;
-  if (D.nranks > 1 && mode != 0 && D.rank != 0) return;
-  const int buf = D.cur[ix.y] ^ cand;
-  ImuIn in;
-  in.pose_i = D.pose[buf] + 7 * (size_t)ix.x; in.pose_j = in.pose_i + 7;
-  in.sb_i = D.sb[buf] + 9 * (size_t)ix.x; in.sb_j = in.sb_i + 9;
-  in.dp = D.imu_dp + 3 * (size_t)f; in.dq = D.imu_dq + 4 * (size_t)f; in.dv = D.imu_dv + 3 * (size_t)f;
-  in.lin_ba = D.imu_lin_ba + 3 * (size_t)f; in.lin_bg = D.imu_lin_bg + 3 * (size_t)f;
-  in.sum_dt = __ldg(D.imu_sum_dt + f);
-  in.jac = D.imu_jac + 225 * (size_t)f;
-  in.sqrt_info = D.imu_sqrt_info + 225 * (size_t)f;
-  double *Jraw = Jraw_all[warp];
-  const double res = imu_eval_warp<kJac>(in, P.g, lane, Jraw);
-  double s = res * res;
+  const int first = blockIdx.x * IMU_PER_CTA;
+  if (warp == 0) {
+    const int f = first + threadIdx.x;
+    bool valid = lane < IMU_PER_CTA && f < D.nImu;
+    int2 ix = make_int2(0, 0);
+    if (valid) {
+      ix = D.imu_idx[f];
+      valid = wants<kJac>(D.ctl[ix.y].state, mode) && !(D.nranks > 1 && mode != 0 && D.rank != 0);
+    }
+    double half = 0.0;
+    if (valid) {
+      const int buf = D.cur[ix.y] ^ cand;
+      ImuIn in;
+      in.pose_i = D.pose[buf] + 7 * (size_t)ix.x; in.pose_j = in.pose_i + 7;
+      in.sb_i = D.sb[buf] + 9 * (size_t)ix.x; in.sb_j = in.sb_i + 9;
+      in.dp = D.imu_dp + 3 * (size_t)f; in.dq = D.imu_dq + 4 * (size_t)f; in.dv = D.imu_dv + 3 * (size_t)f;
+      in.lin_ba = D.imu_lin_ba + 3 * (size_t)f; in.lin_bg = D.imu_lin_bg + 3 * (size_t)f;
+      in.sum_dt = __ldg(D.imu_sum_dt + f);
+      in.jac = D.imu_jac + 225 * (size_t)f;
+      in.sqrt_info = D.imu_sqrt_info + 225 * (size_t)f;
+      double raw[15];
+      imu_geometry<kJac>(in, P.g, raw, comp_all[kJac ? lane : 0]);
+      const double *SI = in.sqrt_info;
+      double s = 0.0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0 && cost) atomicAdd(cost + (size_t)ix.y * cost_stride, 0.5 * s);
-  if (kJac) {
+      for (int i = 0; i < 15; i++) {
+        double r = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; k++) if (k >= i) r += __ldg(SI + i * 15 + k) * raw[k];
+        res_all[lane][i] = r;
+        s += r * r;
+        if (!kJac && res_out) res_out[15 * (size_t)f + i] = r;
+      }
+      half = 0.5 * s;
+    }
+    if (lane < IMU_PER_CTA) ok_all[lane] = valid;
+    if (cost) add_window_scalar(cost, cost_stride, ix.y, half, valid);
+  }
+  if (!kJac) return;
+  __syncthreads();
+  double *Jraw = Jraw_all[kJac ? warp : 0];
+  for (int k = 0; k < IMU_PER_CTA / (NT / 32); k++) {
+    const int slot = warp * (IMU_PER_CTA / (NT / 32)) + k;
+    if (!ok_all[slot]) continue;
+    const int f = first + slot;
+    imu_expand_warp(comp_all[kJac ? slot : 0], Jraw, lane);
     double *rec = out + (size_t)f * REC_IMU;
-    if (lane < 15) rec[lane] = res;
-    const double *SI = in.sqrt_info;
+    if (lane < 15) rec[lane] = res_all[slot][lane];
+    const double *SI = D.imu_sqrt_info + 225 * (size_t)f;
     for (int e = lane; e < 450; e += 32) {
       const int i = e / 30, c = e - i * 30;
       double acc = 0.0;
-      for (int k = i; k < 15; k++) acc += __ldg(SI + i * 15 + k) * Jraw[k * 30 + c];
+      for (int kk = i; kk < 15; kk++) acc += __ldg(SI + i * 15 + kk) * Jraw[kk * 30 + c];
       rec[15 + e] = acc;
     }
-  } else if (res_out && lane < 15) {
-    res_out[15 * (size_t)f + lane] = res;
+    __syncwarp();
   }
 }
 
@@ -287,15 +320,26 @@ __global__ void __launch_bounds__(NT) k_prior(Dev D, int jac_phase, int mode, in
   double *rout = res_out ? res_out + D.prior_off[w] : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double csum = 0.0;
-  for (int i = warp; i < n; i += NT / 32) {
-    double acc = 0.0;
-    for (int k = lane; k < n; k += 32) acc += __ldg(J0 + (size_t)i * n + k) * dx[k];
+  // a warp per row, four rows in flight per warp (independent accumulators keep the loads overlapped)
+  constexpr int NW = NT / 32, RB = 4;
+  for (int i0 = warp * RB; i0 < n; i0 += NW * RB) {
+    double acc[RB];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const double r = __ldg(r0 + i) + acc;
-      if (rout) rout[i] = r;
-      csum += r * r;
+    for (int u = 0; u < RB; u++) acc[u] = 0.0;
+    for (int k = lane; k < n; k += 32) {
+      const double x = dx[k];
+#pragma unroll
+      for (int u = 0; u < RB; u++) if (i0 + u < n) acc[u] += __ldg(J0 + (size_t)(i0 + u) * n + k) * x;
+    }
+#pragma unroll
+    for (int u = 0; u < RB; u++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_down_sync(0xffffffffu, acc[u], o);
+      if (lane == 0 && i0 + u < n) {
+        const double r = __ldg(r0 + i0 + u) + acc[u];
+        if (rout) rout[i0 + u] = r;
+        csum += r * r;
+      }
     }
   }
   if (lane == 0 && cost) atomicAdd(cost + (size_t)w * cost_stride, 0.5 * csum);
@@ -363,7 +407,7 @@ int launch_vp(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int
 int launch_imu(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out, double *res_out, double *cost,
                int cost_stride, cudaStream_t st) {
   if (D.nImu == 0) return 0;
-  const int grid = cdiv(D.nImu, NT / 32);
+  const int grid = cdiv(D.nImu, IMU_PER_CTA);
   if (jac) k_imu<true><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
   else k_imu<false><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
   return 1;
