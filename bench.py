@@ -284,6 +284,15 @@ def main():
                    max(2 * threads, 16), K_LM, reps, dt, threads),
                "single_thread_value": v1}
 
+    # DRAM traffic of the same five launches from the committed ncu --set full capture (profiles/r1_sweep_ncu.json)
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_sweep_ncu.json")
+    if os.path.exists(tp):
+        prof = json.load(open(tp))
+        if prof.get("windows") == B:
+            traffic = prof["jacobian_sweep_dram_bytes"]
+            traffic_note = "dram read+write of the 5 sweep launches, " + prof["note"]
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -295,7 +304,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                      "kernel": "Jacobian sweep (k_proj + k_line + k_vp + k_imu + k_prior, Jacobian mode)", "bytes_per_launch": int(jac_bytes),
                      "ms_per_launch": sweep_ms, "peak_source": peak_src, "per_kernel": per_kernel},
         "cpu_baseline": cpu,
