@@ -204,30 +204,47 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int k = 0; k < 4; k++) hd[8 + 4 * i + k] = k <= i ? Li[i][k] : 0.0;
-  // Y_f = (Jp^T Jl D_s) L^-T
-  for (int f = 0; f < n; f++) {
-    const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
-    const int4 ix = D.line_idx4[f0 + f];
-    const double *q = ix.w >= 0 ? D.rec_vp + (size_t)ix.w * REC_VP : nullptr;
-    double jl[3][4];
+  atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3]))));
+}
+
+// Y_f = (Jp^T Jl D_s) L^-T of one line observation (+ its VP factor): one thread per observation
+__global__ void __launch_bounds__(128) k_core_line_obs(Dev D, Stash S) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= D.nLobs) return;
+  const int4 ix = D.line_idx4[f];
+  const int gl = ix.y, w = ix.z;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  if (D.nranks > 1 && (gl % D.nranks) != D.rank) return;
+  const double *hd = S.lh + 24 * (size_t)gl;
+  if (hd[8] == 0.0) return;   // block not positive definite: the step is flagged invalid
+  const int mp = S.mp;
+  double *Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp + 6 * (ix.x - D.frame_off[w]);
+  const double *r = D.rec_line + (size_t)f * REC_LINE;
+  const double *q = ix.w >= 0 ? D.rec_vp + (size_t)ix.w * REC_VP : nullptr;
+  double s[4], Li[4][4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) { jl[0][c] = r[14 + c] * s[c]; jl[1][c] = r[18 + c] * s[c]; jl[2][c] = q ? q[7 + c] * s[c] : 0.0; }
+  for (int c = 0; c < 4; c++) s[c] = hd[c];
 #pragma unroll
-    for (int p = 0; p < 6; p++) {
-      const double a0 = r[2 + p], a1 = r[8 + p], a2 = q ? q[1 + p] : 0.0;
-      double W4[4];
+  for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
+    for (int k = 0; k < 4; k++) Li[i][k] = hd[8 + 4 * i + k];
+  double jl[3][4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        double t = 0.0;
+  for (int c = 0; c < 4; c++) { jl[0][c] = r[14 + c] * s[c]; jl[1][c] = r[18 + c] * s[c]; jl[2][c] = q ? q[7 + c] * s[c] : 0.0; }
 #pragma unroll
-        for (int k = 0; k <= c; k++) t += W4[k] * Li[c][k];
-        Y[c * mp + 6 * (ix.x - fo) + p] = t;
-      }
+  for (int p = 0; p < 6; p++) {
+    const double a0 = r[2 + p], a1 = r[8 + p], a2 = q ? q[1 + p] : 0.0;
+    double W4[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k <= c; k++) t += W4[k] * Li[c][k];
+      Y[c * mp + p] = t;
     }
   }
-  atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3]))));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -677,8 +694,14 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
     for (int p = tid; p < n; p += WT) {
       const int cp = cmap[p];
       if (cp < 0) continue;
-      double gg = 0.0;
-      for (int i = 0; i < n; i++) gg += J0[(size_t)i * n + p] * r[i];
+      double g8[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // eight independent partial sums keep eight loads in flight
+      int i = 0;
+      for (; i + 8 <= n; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) g8[u] += J0[(size_t)(i + u) * n + p] * r[i + u];
+      }
+      for (; i < n; i++) g8[0] += J0[(size_t)i * n + p] * r[i];
+      const double gg = ((g8[0] + g8[1]) + (g8[2] + g8[3])) + ((g8[4] + g8[5]) + (g8[6] + g8[7]));
       D.gfull[co + cp] += gg; D.gS[co + cp] += gg; D.colsq_cam[co + cp] += H[(size_t)p * n + p];
     }
   }
@@ -728,6 +751,7 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
   int n = 0;
   if (D.nP) { k_core_points<<<cdiv3(D.nP, 128), 128, 0, st>>>(D, P, c.S); n++; }
   if (D.nL) { k_core_lines<<<cdiv3(D.nL, 128), 128, 0, st>>>(D, P, c.S); n++; }
+  if (D.nLobs) { k_core_line_obs<<<cdiv3(D.nLobs, 128), 128, 0, st>>>(D, c.S); n++; }
   const size_t smem = build3_smem(max_frames, any_ex, max_prior_n);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
