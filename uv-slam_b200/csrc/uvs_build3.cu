@@ -432,6 +432,7 @@ constexpr int WT = 256;       // threads of k_window_system
 constexpr int CH = 32;        // landmark columns per chunk (one TMA bulk copy)
 constexpr int GT = 96;        // threads of one GEMM group (<= 78 pair tiles + 12 gradient tiles)
 constexpr int NGROUPS = 2;    // groups split the columns of a chunk
+constexpr int NSTAGE = 4;     // chunks in flight (TMA bulk copies)
 
 // upper-triangle unranking of a 6x6 symmetric block: e in [0,21) -> (p <= q)
 __constant__ unsigned char c_sym_p[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
 // The dense columns are streamed chunk by chunk with TMA bulk copies (cp.async.bulk + mbarrier), double buffered.
 __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_prior_n) {
   extern __shared__ __align__(16) double sm[];
-  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ __align__(8) unsigned long long bar[NSTAGE];
   const int w = blockIdx.x;
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
   const int tid = threadIdx.x;
@@ -559,11 +560,11 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
   const int nkeys = nb * (nb + 1) / 2;
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   const bool lead = D.nranks <= 1 || D.rank == 0;
-  // shared layout: Ych[2][CH][mp] (TMA destination, 16-byte aligned) V[m*m] gsch[m] cmap(int)[max_prior_n]
-  double *Ych = sm, *V = Ych + (size_t)2 * CH * mp, *gsch = V + (size_t)m * m;
+  // shared layout: Ych[NSTAGE][CH][mp] (TMA destination, 16-byte aligned) V[m*m] gsch[m] cmap(int)[max_prior_n]
+  double *Ych = sm, *V = Ych + (size_t)NSTAGE * CH * mp, *gsch = V + (size_t)m * m;
   int *cmap = reinterpret_cast<int *>(gsch + m);
   for (int e = tid; e < m * m + m; e += WT) V[e] = 0.0;
-  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { for (int k = 0; k < NSTAGE; k++) mbar_init(&bar[k], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
 
   {
@@ -574,8 +575,8 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
       const int c0 = c * CH, c1 = min(ncols, c0 + CH);
       const unsigned bytes = (unsigned)((c1 - c0) * mp * sizeof(double));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&bar[c & 1], bytes);
-      tma_bulk_g2s(Ych + (size_t)(c & 1) * CH * mp, Yw + (size_t)c0 * mp, bytes, &bar[c & 1]);
+      mbar_expect_tx(&bar[c % NSTAGE], bytes);
+      tma_bulk_g2s(Ych + (size_t)(c % NSTAGE) * CH * mp, Yw + (size_t)c0 * mp, bytes, &bar[c % NSTAGE]);
     };
     // GEMM tile of this thread: group g takes the columns cc = g (mod NGROUPS) of every chunk
     const int g = tid / GT, t = tid - g * GT;
@@ -589,12 +590,13 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
     for (int p = 0; p < 6; p++)
 #pragma unroll
       for (int q = 0; q < 6; q++) acc[p][q] = 0.0;
-    if (tid == 0 && nchunks > 0) issue(0);
+    if (tid == 0) for (int c = 0; c < NSTAGE - 1 && c < nchunks; c++) issue(c);
     for (int c = 0; c < nchunks; c++) {
-      if (tid == 0 && c + 1 < nchunks) issue(c + 1);      // buffer (c+1)&1 was released by the barrier below
-      mbar_wait(&bar[c & 1], (unsigned)((c >> 1) & 1));
+      // the stage of chunk c + NSTAGE - 1 held chunk c - 1, released by the barrier at the end of the last iteration
+      if (tid == 0 && c + NSTAGE - 1 < nchunks) issue(c + NSTAGE - 1);
+      mbar_wait(&bar[c % NSTAGE], (unsigned)((c / NSTAGE) & 1));
       if (ta >= 0) {
-        const double *Yb = Ych + (size_t)(c & 1) * CH * mp;
+        const double *Yb = Ych + (size_t)(c % NSTAGE) * CH * mp;
         const int c1 = min(ncols, (c + 1) * CH) - c * CH;
         if (tb >= 0) {
           for (int cc = g; cc < c1; cc += NGROUPS) {
@@ -634,18 +636,20 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
     }
   }
 
-  // ---- write the window's system (cleared by k_step / k_solve_init, direct terms already added by k_direct)
+  // ---- write the Schur part of the window's system: plain stores (the system was cleared by k_step / k_solve_init
+  //      and nothing else has touched these entries yet - k_direct runs after this kernel)
   double *Sg = D.Smat + D.S_off[w];
-  for (int e = tid; e < m * m; e += WT) {
-    const int r = e / m, c = e - r * m;
-    if (r > c) continue;
-    const int a = r / 6, b = c / 6;
-    const int row = (a < F ? 15 * a : 15 * F) + (r - 6 * a), col = (b < F ? 15 * b : 15 * F) + (c - 6 * b);
-    Sg[(size_t)row * d + col] += V[e];
+  for (int e = tid; e < nkeys * 36; e += WT) {
+    const int pr = e / 36, rq = e - 36 * pr, p = rq / 6, q = rq - 6 * p;
+    int a, b;
+    unrank_key(pr, a, b);
+    if (a == b && p > q) continue;
+    const int row = (a < F ? 15 * a : 15 * F) + p, col = (b < F ? 15 * b : 15 * F) + q;
+    Sg[(size_t)row * d + col] = V[(6 * a + p) * m + 6 * b + q];
   }
   for (int e = tid; e < m; e += WT) {
     const int a = e / 6;
-    D.gS[co + (a < F ? 15 * a : 15 * F) + (e - 6 * a)] -= gsch[e];
+    D.gS[co + (a < F ? 15 * a : 15 * F) + (e - 6 * a)] = -gsch[e];
   }
   if (!lead) return;
   __syncthreads();
@@ -742,7 +746,7 @@ int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, cudaSt
 
 size_t build3_smem(int max_frames, bool any_ex, int max_prior_n) {
   const int nb = max_frames + (any_ex ? 1 : 0), m = 6 * nb, mp = m + 2;
-  return ((size_t)m * m + m + (size_t)2 * CH * mp) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
+  return ((size_t)m * m + m + (size_t)NSTAGE * CH * mp) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
 }
 
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
@@ -755,12 +759,12 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
   const size_t smem = build3_smem(max_frames, any_ex, max_prior_n);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
+  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
   {
     const int nb_max = max_frames + (any_ex ? 1 : 0);
     const long long units = (long long)D.B * (nb_max * SEGS + nb_max * (nb_max - 1) / 2);
     k_direct<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(D, c.L, nb_max);
   }
-  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
   return n + 2;
 }
 
