@@ -271,6 +271,17 @@ int uvs_set_profiling(UvsHandle *h, int32_t level);
 /* accumulated device time [ms] of every stage over the last uvs_solve and the number of iterations run */
 int uvs_last_stage_ms(const UvsHandle *h, float ms[UVS_N_STAGES], int32_t *n_iterations);
 
+/* IMU mid-point preintegration of `n_intervals` keyframe intervals in one launch
+ * (IntegrationBase::{push_back,propagate,midPointIntegration,repropagate}, factor/integration_base.h:30-158; the step
+ * that produces the IMU-factor constants of UvsWindow).  Interval k owns samples [sample_off[k], sample_off[k+1]):
+ * dt[S], acc[S][3], gyr[S][3]; acc0/gyr0[n][3] = the measurement the interval starts from; lin_ba/lin_bg[n][3] =
+ * linearisation biases; noise = {ACC_N, GYR_N, ACC_W, GYR_W}.  Outputs are the arrays imu_delta_p ... imu_covariance
+ * of UvsWindow ([n][3], [n][4] xyzw, [n][3], [n], [n][225], [n][225]). */
+int uvs_preintegrate(UvsHandle *h, int32_t n_intervals, const int32_t *sample_off, const double *dt, const double *acc,
+                     const double *gyr, const double *acc0, const double *gyr0, const double *lin_ba, const double *lin_bg,
+                     const double *noise, double *delta_p, double *delta_q, double *delta_v, double *sum_dt, double *jacobian,
+                     double *covariance);
+
 /* Factor-parallel multi-GPU mode: this rank owns the landmarks with (index % nranks == rank);
  * IMU factors and the prior belong to rank 0.  `reduce` is called once per LM iteration with the
  * device buffer holding the rank's partial reduced camera system (count doubles) and must sum it

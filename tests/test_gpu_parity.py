@@ -306,3 +306,29 @@ def test_marginalization_parity(solver, opts, cfg, flag):
             assert sm.final_cost < sm.initial_cost and sm3.final_cost < sm3.initial_cost
         else:
             assert np.abs(w2.pose - w3.pose).max() < STEP_TOL, np.abs(w2.pose - w3.pose).max()
+
+
+def test_preintegration_on_device(solver):
+    """IntegrationBase mid-point preintegration (integration_base.h:30-158) for many intervals in one launch,
+    against the oracle's restatement and the independent numpy one of the generator"""
+    rng = np.random.default_rng(11)
+    n, per = 7, [20, 20, 13, 1, 40, 20, 5]
+    off = np.concatenate([[0], np.cumsum(per)]).astype(np.int32)
+    S = int(off[-1])
+    dt = rng.uniform(0.004, 0.006, S)
+    acc = rng.normal(0, 1.0, (S, 3)) + [0, 0, 9.8]
+    gyr = rng.normal(0, 0.3, (S, 3))
+    acc0 = rng.normal(0, 1.0, (n, 3)) + [0, 0, 9.8]; gyr0 = rng.normal(0, 0.3, (n, 3))
+    ba = rng.normal(0, 0.02, (n, 3)); bg = rng.normal(0, 0.002, (n, 3))
+    noise = [gw.ACC_N, gw.GYR_N, gw.ACC_W, gw.GYR_W]
+    out = solver.preintegrate(off, dt, acc, gyr, acc0, gyr0, ba, bg, noise)
+    for k in range(n):
+        sl = slice(off[k], off[k + 1])
+        ref = orc.preintegrate(dt[sl], acc[sl], gyr[sl], acc0[k], gyr0[k], ba[k], bg[k], noise)
+        for name in ("delta_p", "delta_q", "delta_v"):
+            assert np.allclose(out[name][k], ref[name], rtol=1e-12, atol=1e-14), (k, name)
+        assert abs(out["sum_dt"][k] - ref["sum_dt"]) < 1e-14
+        assert np.allclose(out["jacobian"][k].reshape(15, 15), ref["jacobian"], rtol=1e-10, atol=1e-16), k
+        assert np.allclose(out["covariance"][k].reshape(15, 15), ref["covariance"], rtol=1e-10, atol=1e-24), k
+    py = gw.preintegrate(dt[:20], acc[:20], gyr[:20], acc0[0], gyr0[0], ba[0], bg[0])
+    assert np.allclose(out["covariance"][0].reshape(15, 15), py["covariance"], rtol=1e-9, atol=1e-24)

@@ -21,7 +21,7 @@ EXPORTS = (
     "uvs_upload_windows", "uvs_download_state", "uvs_eval_proj", "uvs_eval_line", "uvs_eval_vp", "uvs_eval_imu",
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
-    "uvs_set_profiling", "uvs_last_stage_ms",
+    "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate",
 )
 
 N_STAGES = 10
@@ -75,6 +75,7 @@ def load_library():
     lib.uvs_last_sweep_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.uvs_comm_init.argtypes = [H, C.c_int32, C.c_int32, ALLREDUCE_FN, C.c_void_p]
     lib.uvs_reset_state.argtypes = [H]
+    lib.uvs_preintegrate.argtypes = [H, C.c_int32, c_int32_p] + [c_double_p] * 14
     lib.uvs_set_profiling.argtypes = [H, C.c_int32]
     lib.uvs_last_stage_ms.argtypes = [H, C.POINTER(C.c_float * N_STAGES), C.POINTER(C.c_int32)]
     _lib = lib
@@ -237,6 +238,20 @@ class Solver:
         ms, n = (C.c_float * N_STAGES)(), C.c_int32()
         self._check(self.lib.uvs_last_stage_ms(self.h, C.byref(ms), C.byref(n)), "uvs_last_stage_ms")
         return {k: ms[i] for i, k in enumerate(STAGE_NAMES)}, n.value
+
+    def preintegrate(self, sample_off, dt, acc, gyr, acc0, gyr0, lin_ba, lin_bg, noise):
+        """IMU mid-point preintegration of n intervals on the device -> dict of the UvsWindow imu_* arrays"""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        off = np.ascontiguousarray(sample_off, dtype=np.int32)
+        n = len(off) - 1
+        dt, acc, gyr, acc0, gyr0, lin_ba, lin_bg, noise = map(f, (dt, acc, gyr, acc0, gyr0, lin_ba, lin_bg, noise))
+        out = dict(delta_p=np.zeros((n, 3)), delta_q=np.zeros((n, 4)), delta_v=np.zeros((n, 3)), sum_dt=np.zeros(n),
+                   jacobian=np.zeros((n, 225)), covariance=np.zeros((n, 225)))
+        p = lambda a: a.ctypes.data_as(c_double_p)
+        self._check(self.lib.uvs_preintegrate(self.h, n, off.ctypes.data_as(c_int32_p), p(dt), p(acc), p(gyr), p(acc0), p(gyr0), p(lin_ba),
+                                              p(lin_bg), p(noise), p(out["delta_p"]), p(out["delta_q"]), p(out["delta_v"]), p(out["sum_dt"]),
+                                              p(out["jacobian"]), p(out["covariance"])), "uvs_preintegrate")
+        return out
 
     def comm_init(self, rank, nranks, reduce_fn):
         """reduce_fn(device_ptr:int, count:int, stream:int) -> int, summing in place over ranks."""

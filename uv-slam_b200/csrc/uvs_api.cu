@@ -149,6 +149,10 @@ const char *uvs_last_error(const UvsHandle *h) { return h ? h->err.c_str() : "nu
 int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts) {
   if (!h || B <= 0 || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_windows: bad arguments");
   CK(cudaSetDevice(h->device));
+  static const bool trace = std::getenv("UVS_TRACE") != nullptr;   // host-side phase timings on stderr (adds syncs)
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  auto t_phase = now();
   if (opts) h->opts = *opts;
   fill_params(h->opts, h->P);
   h->have_window = false;
@@ -265,6 +269,7 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
 
   CK(h->stage.reserve(in.total));
   CK(h->dev.reserve(wk.total));
+  if (trace) { std::fprintf(stderr, "[uvs] upload: layout %.3f ms (input %.1f MB, work %.1f MB)\n", ms_since(t_phase), in.total / 1e6, wk.total / 1e6); t_phase = now(); }
   char *S = h->stage.base;
   auto cpI = [&](size_t off, const std::vector<int> &v) { std::memcpy(S + off, v.data(), v.size() * sizeof(int)); };
   cpI(o_frame_off, h->frame_off); cpI(o_point_off, h->point_off); cpI(o_line_off, h->line_off); cpI(o_proj_off, h->proj_off);
@@ -346,7 +351,9 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
     if (pack_err == 3) return fail(h, UVS_ERR_INVALID_ARG, "prior blocks do not add up to prior_n");
   }
   char *Dv = h->dev.base;
+  if (trace) { std::fprintf(stderr, "[uvs] upload: pack %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
   CK(cudaMemcpyAsync(Dv, S, in.total, cudaMemcpyHostToDevice, h->stream));
+  if (trace) { cudaStreamSynchronize(h->stream); std::fprintf(stderr, "[uvs] upload: H2D %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
   // zero / preset the derived region that needs it
   CK(cudaMemsetAsync(Dv + w_cur, 0, w_pidx - w_cur, h->stream));          // cur, ctl, acc, summary
   CK(cudaMemsetAsync(Dv + w_ptb, 0x7f, w_pte - w_ptb, h->stream));        // pt_begin, ln_begin
@@ -397,6 +404,7 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   h->o_reduce = w_S; h->reduce_doubles = (w_reduce_end - w_S) / Dd;
   h->o_b3 = w_b3;
 
+  if (trace) { cudaStreamSynchronize(h->stream); std::fprintf(stderr, "[uvs] upload: memsets + state copies %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
   h->launches += launch_prep(D, h->stream);
   if (h->use_build3) {
     CK(cudaMemsetAsync(Dv + w_b3 + h->b3.o_Y, 0, h->b3.o_ph - h->b3.o_Y, h->stream));   // dense landmark columns start as zeros
@@ -407,6 +415,7 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   int err = 0;
   CK(cudaMemcpyAsync(h->h_active, D.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (trace) { std::fprintf(stderr, "[uvs] upload: prep kernels %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
   err = *h->h_active;
   if (err) {
     static const char *msg[] = {"", "projection factor index out of range", "projection factors of one point are not contiguous",
@@ -701,9 +710,21 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
 }
 
 int uvs_batch_solve(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOptions *opts, UvsSummary *summaries) {
+  static const bool trace = std::getenv("UVS_TRACE") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!trace) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[uvs] batch_solve: %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  };
   int rc = uvs_upload_windows(h, B, w, opts); if (rc) return rc;
+  lap("upload");
   rc = uvs_solve(h, summaries); if (rc) return rc;
-  return uvs_download_state(h, B, w);
+  lap("solve");
+  rc = uvs_download_state(h, B, w);
+  lap("download");
+  return rc;
 }
 
 int uvs_marginalize(UvsHandle *h, int32_t window_index, int32_t flag, UvsPrior *out) {
