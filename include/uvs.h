@@ -245,6 +245,13 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries /* [n_windows], nullable */);
 int uvs_batch_solve(UvsHandle *h, int32_t n_windows, UvsWindow *windows, const UvsOptions *opts,
                     UvsSummary *summaries);
 
+/* The same one-call service for LARGE batches, pipelined: the batch is cut into n_groups sub-batches (0 = choose),
+ * each with its own stream and arenas; sub-batch k+1 is packed and copied to the device while sub-batch k already
+ * iterates.  Results are identical to uvs_batch_solve (windows are independent).  One-shot: the handle keeps no
+ * batch afterwards (uvs_marginalize / uvs_eval_* need uvs_upload_windows or uvs_batch_solve). */
+int uvs_batch_solve_pipelined(UvsHandle *h, int32_t n_windows, UvsWindow *windows, const UvsOptions *opts,
+                              UvsSummary *summaries, int32_t n_groups);
+
 /* Build the next prior of window `window_index` from its current state
  * (MarginalizationInfo::preMarginalize + marginalize, estimator.cpp:1003-1228). */
 int uvs_marginalize(UvsHandle *h, int32_t window_index, int32_t flag, UvsPrior *out);

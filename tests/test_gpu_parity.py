@@ -332,3 +332,20 @@ def test_preintegration_on_device(solver):
         assert np.allclose(out["covariance"][k].reshape(15, 15), ref["covariance"], rtol=1e-10, atol=1e-24), k
     py = gw.preintegrate(dt[:20], acc[:20], gyr[:20], acc0[0], gyr0[0], ba[0], bg[0])
     assert np.allclose(out["covariance"][0].reshape(15, 15), py["covariance"], rtol=1e-9, atol=1e-24)
+
+
+def test_batch_solve_pipelined_matches_plain(solver, windows):
+    """uvs_batch_solve_pipelined cuts the batch into sub-batches on their own streams: same answer per window"""
+    base = [windows[k] for k in ("C1", "tiny", "C2")]
+    ws_a = [base[i % 3].copy() for i in range(9)]
+    ws_b = [w.copy() for w in ws_a]
+    opts = uvs_b200.default_options(max_num_iterations=6)
+    sa = solver.batch_solve(ws_a, opts)
+    sb = solver.batch_solve(ws_b, opts, groups=3)
+    for i, (a, b) in enumerate(zip(ws_a, ws_b)):
+        assert abs(sa[i].final_cost - sb[i].final_cost) <= 1e-9 * max(1.0, abs(sa[i].final_cost)), i
+        assert sa[i].num_iterations == sb[i].num_iterations
+        assert np.allclose(a.pose, b.pose, rtol=0, atol=1e-8), i
+    # one-shot: the handle keeps no batch afterwards
+    with pytest.raises(uvs_b200.UvsError):
+        solver.cost()

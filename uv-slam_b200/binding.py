@@ -21,7 +21,7 @@ EXPORTS = (
     "uvs_upload_windows", "uvs_download_state", "uvs_eval_proj", "uvs_eval_line", "uvs_eval_vp", "uvs_eval_imu",
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
-    "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate",
+    "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate", "uvs_batch_solve_pipelined",
 )
 
 N_STAGES = 10
@@ -67,6 +67,8 @@ def load_library():
     lib.uvs_solve.argtypes = [H, C.POINTER(UvsSummaryStruct)]
     lib.uvs_batch_solve.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct), C.POINTER(UvsOptionsStruct),
                                     C.POINTER(UvsSummaryStruct)]
+    lib.uvs_batch_solve_pipelined.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct), C.POINTER(UvsOptionsStruct),
+                                              C.POINTER(UvsSummaryStruct), C.c_int32]
     lib.uvs_marginalize.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(UvsPriorStruct)]
     lib.uvs_sweep_bytes.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.uvs_launch_count.restype = C.c_int64
@@ -177,7 +179,7 @@ class Solver:
         self._check(self.lib.uvs_solve(self.h, sums), "uvs_solve")
         return sums
 
-    def batch_solve(self, windows, opts=None, prepared=None):
+    def batch_solve(self, windows, opts=None, prepared=None, groups=None):
         """upload + solve + download through the single reference-facing call (host buffers).
         `prepared` = window_array(windows) built beforehand (the ctypes view of the same host arrays)."""
         if isinstance(windows, Window):
@@ -186,7 +188,11 @@ class Solver:
         self.opts = opts if opts is not None else default_options()
         self._arr = prepared if prepared is not None else window_array(self.windows)
         sums = (UvsSummaryStruct * len(self.windows))()
-        self._check(self.lib.uvs_batch_solve(self.h, len(self.windows), self._arr, C.byref(self.opts), sums), "uvs_batch_solve")
+        if groups is None:
+            self._check(self.lib.uvs_batch_solve(self.h, len(self.windows), self._arr, C.byref(self.opts), sums), "uvs_batch_solve")
+        else:   # pipelined over sub-batches (one-shot: the handle keeps no batch afterwards)
+            self._check(self.lib.uvs_batch_solve_pipelined(self.h, len(self.windows), self._arr, C.byref(self.opts), sums, int(groups)),
+                        "uvs_batch_solve_pipelined")
         return sums
 
     def marginalize(self, window_index=0, flag=0):

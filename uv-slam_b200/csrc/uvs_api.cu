@@ -123,6 +123,7 @@ int uvs_create(int device, UvsHandle **out) {
   const size_t chol_smem = chol_max_dynamic_smem(prop.sharedMemPerBlockOptin);
   if (chol_smem == 0) { cudaGetLastError(); cudaStreamDestroy(h->stream); delete h; return UVS_ERR_CUDA; }
   h->packed_limit = chol_packed_limit(chol_smem);
+  h->smem_optin = prop.sharedMemPerBlockOptin;
   cudaMalloc((void **)&h->d_active, sizeof(int));
   cudaMallocHost((void **)&h->h_active, sizeof(int));
   uvs_default_options(&h->opts);
@@ -132,6 +133,8 @@ int uvs_create(int device, UvsHandle **out) {
 
 int uvs_destroy(UvsHandle *h) {
   if (!h) return UVS_ERR_INVALID_ARG;
+  for (UvsHandle *c : h->children) uvs_destroy(c);
+  h->children.clear();
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->dev.release(); h->stage.release(); h->scratch.release(); h->hscratch.release();
@@ -146,7 +149,16 @@ int uvs_destroy(UvsHandle *h) {
 
 const char *uvs_last_error(const UvsHandle *h) { return h ? h->err.c_str() : "null handle"; }
 
+static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts);
+static int upload_finish(UvsHandle *h);
+
 int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts) {
+  const int rc = upload_enqueue(h, B, w, opts);
+  return rc ? rc : upload_finish(h);
+}
+
+// host packing + every device operation of an upload, enqueued on the handle's stream without waiting
+static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts) {
   if (!h || B <= 0 || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_windows: bad arguments");
   CK(cudaSetDevice(h->device));
   static const bool trace = std::getenv("UVS_TRACE") != nullptr;   // host-side phase timings on stderr (adds syncs)
@@ -262,9 +274,7 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   if (h->use_build3) {
     Dev tmp{}; tmp.B = B; tmp.nP = nP; tmp.nL = nL; tmp.nProj = nProj; tmp.nLobs = nLobs; tmp.nVobs = nVobs;
     w_b3 = wk.take(build3_bytes(tmp, max_frames, any_ex, &h->b3));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, h->device));
-    if (build3_smem(max_frames, any_ex, max_prior_n) > prop.sharedMemPerBlockOptin - 1024) h->use_build3 = false;
+    if (build3_smem(max_frames, any_ex, max_prior_n) > h->smem_optin - 1024) h->use_build3 = false;
   }
 
   CK(h->stage.reserve(in.total));
@@ -412,11 +422,16 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   }
   int rc = post_launch(h, "prep kernels");
   if (rc) return rc;
-  int err = 0;
   CK(cudaMemcpyAsync(h->h_active, D.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (trace) { cudaStreamSynchronize(h->stream); std::fprintf(stderr, "[uvs] upload: prep kernels %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
+  return UVS_OK;
+}
+
+// waits for the upload and reports what the device-side validation found
+static int upload_finish(UvsHandle *h) {
+  CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  if (trace) { std::fprintf(stderr, "[uvs] upload: prep kernels %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
-  err = *h->h_active;
+  const int err = *h->h_active;
   if (err) {
     static const char *msg[] = {"", "projection factor index out of range", "projection factors of one point are not contiguous",
                                 "projection factors of one point have different anchor frames", "line factor index out of range",
@@ -725,6 +740,51 @@ int uvs_batch_solve(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOptions *opt
   rc = uvs_download_state(h, B, w);
   lap("download");
   return rc;
+}
+
+int uvs_batch_solve_pipelined(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOptions *opts, UvsSummary *summaries, int32_t n_groups) {
+  if (!h || B <= 0 || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_batch_solve_pipelined: bad arguments");
+  if (h->nranks > 1) return fail(h, UVS_ERR_UNSUPPORTED, "uvs_batch_solve_pipelined: not available in factor-parallel mode");
+  int G = n_groups > 0 ? n_groups : (B >= 512 ? 4 : (B >= 128 ? 2 : 1));
+  G = std::min(G, B);
+  if (G <= 1) return uvs_batch_solve(h, B, w, opts, summaries);
+  while ((int)h->children.size() < G) {
+    UvsHandle *c = nullptr;
+    const int rc = uvs_create(h->device, &c);
+    if (rc) return fail(h, rc, "uvs_batch_solve_pipelined: cannot create a sub-batch handle");
+    h->children.push_back(c);
+  }
+  h->have_window = false;   // one-shot service call: the parent keeps no batch
+  std::vector<int> rcs(G, UVS_OK);
+  std::vector<std::thread> workers;
+  const UvsOptions o = opts ? *opts : h->opts;
+  for (int g = 0; g < G; g++) {
+    UvsHandle *c = h->children[g];
+    const int lo = (int)((long long)B * g / G), hi = (int)((long long)B * (g + 1) / G);
+    const int64_t l0 = c->launches;
+    // uploads go one after another (they share the host cores and the PCIe link); each sub-batch starts its LM loop
+    // on its own stream as soon as its data has landed, overlapping the next sub-batch's pack + H2D
+    rcs[g] = upload_enqueue(c, hi - lo, w + lo, &o);
+    if (rcs[g]) break;
+    workers.emplace_back([c, lo, hi, w, summaries, g, l0, &rcs] {
+      int rc = upload_finish(c);
+      if (!rc) rc = uvs_solve(c, summaries ? summaries + lo : nullptr);
+      if (!rc) rc = uvs_download_state(c, hi - lo, w + lo);
+      rcs[g] = rc;
+      (void)l0;
+    });
+  }
+  for (auto &t : workers) t.join();
+  float ms = 0.f;
+  for (int g = 0; g < G; g++) {
+    UvsHandle *c = h->children[g];
+    ms = std::max(ms, c->last_solve_ms);
+    h->launches += c->launches; c->launches = 0;
+  }
+  h->last_solve_ms = ms;
+  for (int g = 0; g < G; g++)
+    if (rcs[g]) return fail(h, rcs[g], "sub-batch " + std::to_string(g) + ": " + h->children[g]->err);
+  return UVS_OK;
 }
 
 int uvs_marginalize(UvsHandle *h, int32_t window_index, int32_t flag, UvsPrior *out) {

@@ -4,7 +4,8 @@
 // Same algebra as uvs_build.cu (Ceres SPARSE_SCHUR restated), organised so that no lane is idle and no
 // atomics touch the Hessian:
 //
-//   k_core_points / k_core_lines   one THREAD per landmark: eliminates the landmark block and writes a compact
+//   k_core_points / k_core_lines   one lane GROUP (4 / 8 lanes) per landmark: the lanes split the observations,
+//        merge by shuffles, eliminate the landmark block and write the
 //        "stash": Y = W (E + D^2)^-1/2 (6 values per camera block of the landmark; 6x4 per line observation),
 //        z = (E + D^2)^-1/2 g, Jacobi scale, LM diagonal.   W (E+D^2)^-1 W^T = Y Y^T,  W (E+D^2)^-1 g = Y z.
 //   k_window_system                one CTA per window:
@@ -13,7 +14,7 @@
 //        (2) Schur terms as a dense rank update  V -= Y Y^T  over all landmark columns, 6x6 register tiles,
 //            Y columns expanded chunk by chunk into shared memory (double buffered);
 //        (3) IMU blocks and the prior, then ONE write of the window's reduced system.
-//   k_back_points / k_back_lines   one thread per landmark: delta_k = -(E+D^2)^-1/2 (z + Y^T delta_c).
+//   k_back_points / k_back_lines   one thread per point / one lane group per line: delta_k = -(E+D^2)^-1/2 (z + Y^T delta_c).
 // The model cost change uses  -(g^T y + y^T H y / 2) = (y^T D^2 y - g^T y) / 2  (y solves (H + D^2) y = -g),
 // which needs no Jacobians; k_chol adds the camera part.
 #include "uvs_device.cuh"
@@ -64,9 +65,22 @@ struct Stash {
 };
 __device__ __forceinline__ long long colbase(const Dev &D, int w) { return (long long)D.point_off[w] + 4LL * D.line_off[w]; }
 
+// sum over the 2^k lanes of a landmark's lane group (all lanes end with the same bits)
+template <int kLanes>
+__device__ __forceinline__ double group_sum(unsigned gmask, double v) {
+#pragma unroll
+  for (int o = 1; o < kLanes; o <<= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+constexpr int LPP = 4;   // lanes per point: one observation each (a C2 point has ~4), partial sums merged by shuffles
+constexpr int LPL = 8;   // lanes per line  (a C2 line has ~7 observations)
+
 __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
-  const int gp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gp >= D.nP) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gp = t / LPP, sub = t - gp * LPP;
+  if (gp >= D.nP) return;   // every branch up to the shuffles is uniform over the lane group
+  const unsigned gmask = ((1u << LPP) - 1u) << ((threadIdx.x & 31) & ~(LPP - 1));
   const int w = D.pt_win[gp];
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
   const int mp = S.mp;
@@ -75,35 +89,44 @@ __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
   const int f0 = D.pt_begin[gp], n = D.pt_end[gp] - f0;
   const bool mine = D.nranks <= 1 || (gp % D.nranks) == D.rank;
   // the column was zero-filled at upload and its sparsity pattern never changes: only the blocks are rewritten
-  if (n <= 0 || !mine) { ph[1] = 0.0; return; }
+  if (n <= 0 || !mine) { if (sub == 0) ph[1] = 0.0; return; }
   const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
   const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
   const double *R = D.rec_proj + (size_t)f0 * REC_PROJ;
   double colsq = 0.0, gk = 0.0;
-  for (int f = 0; f < n; f++) {
-    const double j0 = R[f * REC_PROJ + 38], j1 = R[f * REC_PROJ + 39];
+  double wa[6] = {0, 0, 0, 0, 0, 0}, we[6] = {0, 0, 0, 0, 0, 0}, u0[6] = {0, 0, 0, 0, 0, 0};
+  for (int f = sub; f < n; f += LPP) {
+    const double *r = R + f * REC_PROJ;
+    const double j0 = r[38], j1 = r[39];
     colsq += j0 * j0 + j1 * j1;
-    gk += j0 * R[f * REC_PROJ] + j1 * R[f * REC_PROJ + 1];
+    gk += j0 * r[0] + j1 * r[1];
+    const bool first = f < LPP;
+    double *yj = Y + 6 * (D.proj_idx[f0 + f].y - fo);
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      wa[c] += r[2 + c] * j0 + r[8 + c] * j1;
+      const double u = r[14 + c] * j0 + r[20 + c] * j1;
+      if (first) u0[c] = u; else yj[c] = u;   // later observations of this lane: parked unscaled, rescaled below
+      if (ex) we[c] += r[26 + c] * j0 + r[32 + c] * j1;
+    }
   }
+  colsq = group_sum<LPP>(gmask, colsq);
+  gk = group_sum<LPP>(gmask, gk);
+#pragma unroll
+  for (int c = 0; c < 6; c++) { wa[c] = group_sum<LPP>(gmask, wa[c]); if (ex) we[c] = group_sum<LPP>(gmask, we[c]); }
   double sk;
-  if (!D.ctl[w].have_scale) { sk = 1.0 / (1.0 + sqrt(colsq)); D.scale_pt[gp] = sk; }
+  if (!D.ctl[w].have_scale) { sk = 1.0 / (1.0 + sqrt(colsq)); if (sub == 0) D.scale_pt[gp] = sk; }
   else sk = D.scale_pt[gp];
   const double Et = sk * sk * colsq;
   const double D2 = clamp4(Et, P.min_lm_diag, P.max_lm_diag) / D.ctl[w].radius;
   const double sh = rsqrt(Et + D2);
   const double ysc = sk * sh;
-  double wa[6] = {0, 0, 0, 0, 0, 0}, we[6] = {0, 0, 0, 0, 0, 0};
-  for (int f = 0; f < n; f++) {
-    const double *r = R + f * REC_PROJ;
-    const double j0 = r[38], j1 = r[39];
-    const int bj = D.proj_idx[f0 + f].y - fo;
+  for (int f = sub; f < n; f += LPP) {
+    double *yj = Y + 6 * (D.proj_idx[f0 + f].y - fo);
 #pragma unroll
-    for (int c = 0; c < 6; c++) {
-      wa[c] += r[2 + c] * j0 + r[8 + c] * j1;
-      Y[6 * bj + c] = ysc * (r[14 + c] * j0 + r[20 + c] * j1);
-      if (ex) we[c] += r[26 + c] * j0 + r[32 + c] * j1;
-    }
+    for (int c = 0; c < 6; c++) yj[c] = ysc * (f < LPP ? u0[c] : yj[c]);
   }
+  if (sub != 0) return;
   const int bi = D.proj_idx[f0].x - fo;
 #pragma unroll
   for (int c = 0; c < 6; c++) { Y[6 * bi + c] = ysc * wa[c]; if (ex) Y[6 * F + c] = ysc * we[c]; }
@@ -112,9 +135,13 @@ __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
   atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fabs(gk));
 }
 
+// One lane GROUP per line: the lanes split the line's observations (E = sum Jl^T Jl, g), merge by shuffles, every lane
+// factors the damped 4x4 block, then each lane writes  Y_f = (Jp^T Jl D_s) L^-T  of its own observations (+ VP factors).
 __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
-  const int gl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gl = t / LPL, sub = t - gl * LPL;
   if (gl >= D.nL) return;
+  const unsigned gmask = ((1u << LPL) - 1u) << ((threadIdx.x & 31) & ~(LPL - 1));
   const int w = D.ln_win[gl];
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
   const int f0 = D.ln_begin[gl], n = D.ln_end[gl] - f0;
@@ -122,11 +149,11 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
   double *Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp;   // 4 columns
   double *hd = S.lh + 24 * (size_t)gl;
   const bool mine = D.nranks <= 1 || (gl % D.nranks) == D.rank;
-  hd[8] = 0.0;   // Linv[0][0] = 0 marks "no step" for the back-substitution
-  if (n <= 0 || !mine) return;
+  // Linv[0][0] = 0 marks "no step" for the back-substitution
+  if (n <= 0 || !mine) { if (sub == 0) hd[8] = 0.0; return; }
   const int fo = D.frame_off[w];
   double E[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
-  for (int f = 0; f < n; f++) {
+  for (int f = sub; f < n; f += LPL) {
     const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
 #pragma unroll
     for (int row = 0; row < 2; row++) {
@@ -144,11 +171,15 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
       g[0] += a0 * rr; g[1] += a1 * rr; g[2] += a2 * rr; g[3] += a3 * rr;
     }
   }
+#pragma unroll
+  for (int k = 0; k < 10; k++) E[k] = group_sum<LPL>(gmask, E[k]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) g[k] = group_sum<LPL>(gmask, g[k]);
   double s[4];
   const double Ed[4] = {E[0], E[4], E[7], E[9]};
   if (!D.ctl[w].have_scale) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) { s[c] = 1.0 / (1.0 + sqrt(Ed[c])); D.scale_ln[4 * (size_t)gl + c] = s[c]; }
+    for (int c = 0; c < 4; c++) { s[c] = 1.0 / (1.0 + sqrt(Ed[c])); if (sub == 0) D.scale_ln[4 * (size_t)gl + c] = s[c]; }
   } else {
 #pragma unroll
     for (int c = 0; c < 4; c++) s[c] = D.scale_ln[4 * (size_t)gl + c];
@@ -173,76 +204,62 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
     L[j][j] = dj * id;
 #pragma unroll
     for (int i = j + 1; i < 4; i++) {
-      double t = M[i][j];
+      double tt = M[i][j];
 #pragma unroll
-      for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
-      L[i][j] = t * id;
+      for (int k = 0; k < j; k++) tt -= L[i][k] * L[j][k];
+      L[i][j] = tt * id;
     }
   }
-  if (!ok) { atomicAdd(D.acc + (size_t)w * ACC_STRIDE + ACC_FAIL, 1.0); return; }
+  if (!ok) {
+    if (sub == 0) { hd[8] = 0.0; atomicAdd(D.acc + (size_t)w * ACC_STRIDE + ACC_FAIL, 1.0); }
+    return;
+  }
 #pragma unroll
   for (int col = 0; col < 4; col++)
 #pragma unroll
     for (int i = col; i < 4; i++) {
-      double t = (i == col) ? 1.0 : 0.0;
+      double tt = (i == col) ? 1.0 : 0.0;
 #pragma unroll
-      for (int k = col; k < i; k++) t -= L[i][k] * Li[k][col];
-      Li[i][col] = t / L[i][i];
+      for (int k = col; k < i; k++) tt -= L[i][k] * Li[k][col];
+      Li[i][col] = tt / L[i][i];
     }
-  // z = L^-1 (D_s g)
-  double z[4];
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    double t = 0.0;
-#pragma unroll
-    for (int k = 0; k <= c; k++) t += Li[c][k] * s[k] * g[k];
-    z[c] = t;
-  }
-#pragma unroll
-  for (int c = 0; c < 4; c++) { Y[c * mp + mp - 2] = z[c]; hd[c] = s[c]; hd[4 + c] = D2[c]; }
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) hd[8 + 4 * i + k] = k <= i ? Li[i][k] : 0.0;
-  atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3]))));
-}
-
-// Y_f = (Jp^T Jl D_s) L^-T of one line observation (+ its VP factor): one thread per observation
-__global__ void __launch_bounds__(128) k_core_line_obs(Dev D, Stash S) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= D.nLobs) return;
-  const int4 ix = D.line_idx4[f];
-  const int gl = ix.y, w = ix.z;
-  if (!(D.ctl[w].state & WS_ACTIVE)) return;
-  if (D.nranks > 1 && (gl % D.nranks) != D.rank) return;
-  const double *hd = S.lh + 24 * (size_t)gl;
-  if (hd[8] == 0.0) return;   // block not positive definite: the step is flagged invalid
-  const int mp = S.mp;
-  double *Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp + 6 * (ix.x - D.frame_off[w]);
-  const double *r = D.rec_line + (size_t)f * REC_LINE;
-  const double *q = ix.w >= 0 ? D.rec_vp + (size_t)ix.w * REC_VP : nullptr;
-  double s[4], Li[4][4];
-#pragma unroll
-  for (int c = 0; c < 4; c++) s[c] = hd[c];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) Li[i][k] = hd[8 + 4 * i + k];
-  double jl[3][4];
-#pragma unroll
-  for (int c = 0; c < 4; c++) { jl[0][c] = r[14 + c] * s[c]; jl[1][c] = r[18 + c] * s[c]; jl[2][c] = q ? q[7 + c] * s[c] : 0.0; }
-#pragma unroll
-  for (int p = 0; p < 6; p++) {
-    const double a0 = r[2 + p], a1 = r[8 + p], a2 = q ? q[1 + p] : 0.0;
-    double W4[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
+  if (sub == 0) {
+    // z = L^-1 (D_s g)
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      double t = 0.0;
+      double tt = 0.0;
 #pragma unroll
-      for (int k = 0; k <= c; k++) t += W4[k] * Li[c][k];
-      Y[c * mp + p] = t;
+      for (int k = 0; k <= c; k++) tt += Li[c][k] * s[k] * g[k];
+      Y[c * mp + mp - 2] = tt; hd[c] = s[c]; hd[4 + c] = D2[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) hd[8 + 4 * i + k] = k <= i ? Li[i][k] : 0.0;
+    atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3]))));
+  }
+  // Y blocks of this lane's observations
+  for (int f = sub; f < n; f += LPL) {
+    const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
+    const int4 ix = D.line_idx4[f0 + f];
+    const double *q = ix.w >= 0 ? D.rec_vp + (size_t)ix.w * REC_VP : nullptr;
+    double *Yf = Y + 6 * (ix.x - fo);
+    double jl[3][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { jl[0][c] = r[14 + c] * s[c]; jl[1][c] = r[18 + c] * s[c]; jl[2][c] = q ? q[7 + c] * s[c] : 0.0; }
+#pragma unroll
+    for (int p = 0; p < 6; p++) {
+      const double a0 = r[2 + p], a1 = r[8 + p], a2 = q ? q[1 + p] : 0.0;
+      double W4[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        double tt = 0.0;
+#pragma unroll
+        for (int k = 0; k <= c; k++) tt += W4[k] * Li[c][k];
+        Yf[c * mp + p] = tt;
+      }
     }
   }
 }
@@ -288,7 +305,9 @@ __global__ void __launch_bounds__(128) k_back_points(Dev D, Stash S) {
 }
 
 __global__ void __launch_bounds__(128) k_back_lines(Dev D, Stash S) {
-  const int gl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gl = t / LPL, sub = t - gl * LPL;
+  const unsigned gmask = ((1u << LPL) - 1u) << ((threadIdx.x & 31) & ~(LPL - 1));
   bool valid = gl < D.nL && (D.nranks <= 1 || (gl % D.nranks) == D.rank);
   int w = 0;
   if (valid) {
@@ -296,7 +315,7 @@ __global__ void __launch_bounds__(128) k_back_lines(Dev D, Stash S) {
     valid = (D.ctl[w].state & WS_ACTIVE) && D.acc[(size_t)w * ACC_STRIDE + ACC_FAIL] == 0.0;
   }
   double mc = 0.0, s2 = 0.0, x2 = 0.0;
-  if (valid) {
+  if (valid) {   // uniform over the lane group
     const int mp = S.mp, cur = D.cur[w];
     const double *Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp;
     const double *hd = S.lh + 24 * (size_t)gl;
@@ -304,40 +323,43 @@ __global__ void __launch_bounds__(128) k_back_lines(Dev D, Stash S) {
     if (hd[8] != 0.0) {
       const int F = D.frame_off[w + 1] - D.frame_off[w];
       const double *dl = D.delta_cam + D.cam_off[w];
-      double t[4], yk[4];
+      double tz[4], yk[4];
+      // the lanes split the camera blocks of  u = Y^T delta_c
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const double *y = Y + c * mp;
         double u = 0.0;
-        for (int b = 0; b < F; b++) {
+        for (int b = sub; b < F; b += LPL) {
 #pragma unroll
           for (int p = 0; p < 6; p++) u += y[6 * b + p] * dl[15 * b + p];
         }
-        t[c] = y[mp - 2] + u;   // z + u
+        tz[c] = y[mp - 2] + group_sum<LPL>(gmask, u);   // z + u
       }
       // y_k = -L^-T (z + u)
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         double a = 0.0;
 #pragma unroll
-        for (int k = c; k < 4; k++) a += hd[8 + 4 * k + c] * t[k];
+        for (int k = c; k < 4; k++) a += hd[8 + 4 * k + c] * tz[k];
         yk[c] = -a;
       }
       // g~^T y_k = (L z)^T y_k = -z^T (z + u)
       double gy = 0.0, dy = 0.0;
 #pragma unroll
-      for (int c = 0; c < 4; c++) { gy -= Y[c * mp + mp - 2] * t[c]; dy += hd[4 + c] * yk[c] * yk[c]; dk[c] = hd[c] * yk[c]; }
+      for (int c = 0; c < 4; c++) { gy -= Y[c * mp + mp - 2] * tz[c]; dy += hd[4 + c] * yk[c] * yk[c]; dk[c] = hd[c] * yk[c]; }
       mc = 0.5 * (dy - gy);
     }
+    if (sub == 0) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const double x = D.ortho[cur][4 * (size_t)gl + c];
-      D.delta_ln[4 * (size_t)gl + c] = dk[c];
-      D.ortho[cur ^ 1][4 * (size_t)gl + c] = x + dk[c];
-      s2 += dk[c] * dk[c]; x2 += x * x;
+      for (int c = 0; c < 4; c++) {
+        const double x = D.ortho[cur][4 * (size_t)gl + c];
+        D.delta_ln[4 * (size_t)gl + c] = dk[c];
+        D.ortho[cur ^ 1][4 * (size_t)gl + c] = x + dk[c];
+        s2 += dk[c] * dk[c]; x2 += x * x;
+      }
     }
   }
-  add_win3(D.acc, w, valid, mc, s2, x2);
+  add_win3(D.acc, w, valid && sub == 0, mc, s2, x2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -753,9 +775,8 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
                   cudaStream_t st) {
   Build3Ctx c; make_ctx(base, lay, c);
   int n = 0;
-  if (D.nP) { k_core_points<<<cdiv3(D.nP, 128), 128, 0, st>>>(D, P, c.S); n++; }
-  if (D.nL) { k_core_lines<<<cdiv3(D.nL, 128), 128, 0, st>>>(D, P, c.S); n++; }
-  if (D.nLobs) { k_core_line_obs<<<cdiv3(D.nLobs, 128), 128, 0, st>>>(D, c.S); n++; }
+  if (D.nP) { k_core_points<<<cdiv3(D.nP, 128 / LPP), 128, 0, st>>>(D, P, c.S); n++; }
+  if (D.nL) { k_core_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, st>>>(D, P, c.S); n++; }
   const size_t smem = build3_smem(max_frames, any_ex, max_prior_n);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
@@ -772,7 +793,7 @@ int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t
   Build3Ctx c; make_ctx(base, lay, c);
   int n = 0;
   if (D.nP) { k_back_points<<<cdiv3(D.nP, 128), 128, 0, st>>>(D, c.S); n++; }
-  if (D.nL) { k_back_lines<<<cdiv3(D.nL, 128), 128, 0, st>>>(D, c.S); n++; }
+  if (D.nL) { k_back_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, st>>>(D, c.S); n++; }
   return n;
 }
 

@@ -79,6 +79,8 @@ struct UvsHandle {
   std::vector<cudaEvent_t> stage_ev;          // (UVS_N_STAGES + 1) events per LM iteration
   float stage_ms[UVS_N_STAGES] = {0};
   int stage_iters = 0;
+  size_t smem_optin = 0;                      // cudaDeviceProp::sharedMemPerBlockOptin (queried once)
+  std::vector<UvsHandle *> children;          // sub-batch handles of uvs_batch_solve_pipelined (own stream + arenas)
 };
 
 
