@@ -452,9 +452,8 @@ __global__ void __launch_bounds__(128) k_prep_direct(Dev D, DirectLists L) {
 // ------------------------------------------------------------------------------------------------
 constexpr int WT = 256;       // threads of k_window_system
 constexpr int CH = 32;        // landmark columns per chunk (one TMA bulk copy)
-constexpr int GT = 96;        // threads of one GEMM group (<= 78 pair tiles + 12 gradient tiles)
-constexpr int NGROUPS = 2;    // groups split the columns of a chunk
 constexpr int NSTAGE = 4;     // chunks in flight (TMA bulk copies)
+constexpr int YSLACK = 64;    // fragment rows of the last 8-row tiles run past mp into the next column / this slack
 
 // upper-triangle unranking of a 6x6 symmetric block: e in [0,21) -> (p <= q)
 __constant__ unsigned char c_sym_p[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
@@ -567,9 +566,17 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
   }
 }
 
+// FP64 tensor-core MMA  D(8x8) += A(8x4) B(4x8)  (mma.sync m8n8k4: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}])
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+constexpr int SUP = 3;        // a warp owns a SUP x SUP block of 8x8 tiles of the rank update
+constexpr int SUP_SETS = 2;   // and at most this many of them (8 warps x 2 covers the 10 blocks of 12 camera blocks)
+
 // Schur terms of one window as a dense rank update over its landmark columns, then IMU blocks and the prior.
-//   V -= Y Y^T (6x6 register tiles, one per camera-block pair), gsch = Y z.
-// The dense columns are streamed chunk by chunk with TMA bulk copies (cp.async.bulk + mbarrier), double buffered.
+//   [V | gsch] = Y [Y | z]^T  on the FP64 tensor cores: the columns (camera rows + the z row) are streamed chunk by
+//   chunk with TMA bulk copies (cp.async.bulk + mbarrier, NSTAGE in flight); warps own 24 x 24 blocks of the upper
+//   triangle and read the 8x4 / 4x8 fragments straight from the chunk (bank-conflict free for mp = 4 mod 16).
 __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_prior_n) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) unsigned long long bar[NSTAGE];
@@ -579,15 +586,15 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
   const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
   const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
   const int nb = F + (ex ? 1 : 0), m = 6 * nb, mp = S.mp;
-  const int nkeys = nb * (nb + 1) / 2;
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   const bool lead = D.nranks <= 1 || D.rank == 0;
-  // shared layout: Ych[NSTAGE][CH][mp] (TMA destination, 16-byte aligned) V[m*m] gsch[m] cmap(int)[max_prior_n]
-  double *Ych = sm, *V = Ych + (size_t)NSTAGE * CH * mp, *gsch = V + (size_t)m * m;
-  int *cmap = reinterpret_cast<int *>(gsch + m);
-  for (int e = tid; e < m * m + m; e += WT) V[e] = 0.0;
+  // shared layout: Ych[NSTAGE][CH][mp] (TMA destination, 16-byte aligned) + slack for fragment rows past mp, cmap(int)[max_prior_n]
+  double *Ych = sm;
+  int *cmap = reinterpret_cast<int *>(Ych + (size_t)NSTAGE * CH * mp + YSLACK);
   if (tid == 0) { for (int k = 0; k < NSTAGE; k++) mbar_init(&bar[k], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  for (int e = tid; e < YSLACK; e += WT) Ych[(size_t)NSTAGE * CH * mp + e] = 0.0;
   __syncthreads();
+  double *Sg = D.Smat + D.S_off[w];
 
   {
     const int np = D.point_off[w + 1] - D.point_off[w], nl = D.line_off[w + 1] - D.line_off[w];
@@ -600,78 +607,81 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
       mbar_expect_tx(&bar[c % NSTAGE], bytes);
       tma_bulk_g2s(Ych + (size_t)(c % NSTAGE) * CH * mp, Yw + (size_t)c0 * mp, bytes, &bar[c % NSTAGE]);
     };
-    // GEMM tile of this thread: group g takes the columns cc = g (mod NGROUPS) of every chunk
-    const int g = tid / GT, t = tid - g * GT;
-    int ta = -1, tb = -1;      // block pair (ta <= tb), or gradient tile (ta, -2)
-    if (g < NGROUPS) {
-      if (t < nkeys) unrank_key(t, ta, tb);
-      else if (t < nkeys + nb) { ta = t - nkeys; tb = -2; }
+    const int warp = tid >> 5, lane = tid & 31;
+    const int zr = mp - 2;                           // the z row of a column (rows m .. zr-1 are zero padding)
+    const int ntr = (zr + 1 + 7) / 8;                // 8-row tiles over the camera rows and the z row
+    const int nsr = (ntr + SUP - 1) / SUP, nsuper = nsr * (nsr + 1) / 2;
+    int sa[SUP_SETS], sb[SUP_SETS];
+    bool has[SUP_SETS];
+#pragma unroll
+    for (int i = 0; i < SUP_SETS; i++) {
+      const int idx = warp + i * (WT / 32);
+      has[i] = idx < nsuper;
+      sa[i] = sb[i] = 0;
+      if (has[i]) unrank_key(idx, sa[i], sb[i]);
     }
-    double acc[6][6];
+    double acc[SUP_SETS][SUP][SUP][2];
 #pragma unroll
-    for (int p = 0; p < 6; p++)
+    for (int i = 0; i < SUP_SETS; i++)
 #pragma unroll
-      for (int q = 0; q < 6; q++) acc[p][q] = 0.0;
+      for (int u = 0; u < SUP; u++)
+#pragma unroll
+        for (int v = 0; v < SUP; v++) acc[i][u][v][0] = acc[i][u][v][1] = 0.0;
     if (tid == 0) for (int c = 0; c < NSTAGE - 1 && c < nchunks; c++) issue(c);
     for (int c = 0; c < nchunks; c++) {
       // the stage of chunk c + NSTAGE - 1 held chunk c - 1, released by the barrier at the end of the last iteration
       if (tid == 0 && c + NSTAGE - 1 < nchunks) issue(c + NSTAGE - 1);
       mbar_wait(&bar[c % NSTAGE], (unsigned)((c / NSTAGE) & 1));
-      if (ta >= 0) {
-        const double *Yb = Ych + (size_t)(c % NSTAGE) * CH * mp;
-        const int c1 = min(ncols, (c + 1) * CH) - c * CH;
-        if (tb >= 0) {
-          for (int cc = g; cc < c1; cc += NGROUPS) {
-            const double *y = Yb + (size_t)cc * mp;
-            double ya[6], yb[6];
+      double *Yb = Ych + (size_t)(c % NSTAGE) * CH * mp;
+      const int c1 = min(ncols, (c + 1) * CH) - c * CH;
+      if (c1 & 3) {   // last chunk: zero columns up to the next multiple of the MMA depth
+        const int pad = ((c1 + 3) & ~3) - c1;
+        for (int e = tid; e < pad * mp; e += WT) Yb[(size_t)c1 * mp + e] = 0.0;
+        __syncthreads();
+      }
 #pragma unroll
-            for (int k = 0; k < 6; k++) { ya[k] = y[6 * ta + k]; yb[k] = y[6 * tb + k]; }
+      for (int i = 0; i < SUP_SETS; i++) {
+        if (!has[i]) continue;
+        const bool diag = sa[i] == sb[i];
+        const double *ya = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * SUP * sa[i];
+        const double *yb = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * SUP * sb[i];
+        for (int k0 = 0; k0 < c1; k0 += 4) {
+          double fa[SUP], fb[SUP];
 #pragma unroll
-            for (int p = 0; p < 6; p++)
+          for (int u = 0; u < SUP; u++) { fa[u] = ya[(size_t)k0 * mp + 8 * u]; fb[u] = yb[(size_t)k0 * mp + 8 * u]; }
 #pragma unroll
-              for (int q = 0; q < 6; q++) acc[p][q] += ya[p] * yb[q];
-          }
-        } else {
-          for (int cc = g; cc < c1; cc += NGROUPS) {
-            const double *y = Yb + (size_t)cc * mp;
-            const double zz = y[mp - 2];
+          for (int u = 0; u < SUP; u++)
 #pragma unroll
-            for (int k = 0; k < 6; k++) acc[0][k] += y[6 * ta + k] * zz;
-          }
+            for (int v = 0; v < SUP; v++) {
+              if (diag && v < u) continue;                                   // lower-triangle tile
+              if (SUP * sa[i] + u >= ntr || SUP * sb[i] + v >= ntr) continue;   // past the last row tile
+              dmma884(acc[i][u][v], fa[u], fb[v]);
+            }
         }
       }
       __syncthreads();
     }
-    for (int gg = 0; gg < NGROUPS; gg++) {
-      if (g == gg && ta >= 0) {
-        if (tb >= 0) {
+    // ---- write the Schur part of the window's system: plain stores (the system was cleared by k_step / k_solve_init
+    //      and nothing else has touched these entries yet - k_direct runs after this kernel)
+    auto grow = [&](int e) { const int a = e / 6; return (a < F ? 15 * a : 15 * F) + (e - 6 * a); };
 #pragma unroll
-          for (int p = 0; p < 6; p++)
+    for (int i = 0; i < SUP_SETS; i++) {
+      if (!has[i]) continue;
 #pragma unroll
-            for (int q = 0; q < 6; q++) V[(6 * ta + p) * m + 6 * tb + q] -= acc[p][q];
-        } else {
+      for (int u = 0; u < SUP; u++)
 #pragma unroll
-          for (int k = 0; k < 6; k++) gsch[6 * ta + k] += acc[0][k];
+        for (int v = 0; v < SUP; v++) {
+          if (sa[i] == sb[i] && v < u) continue;
+          const int row = 8 * (SUP * sa[i] + u) + (lane >> 2);
+          if (row >= m) continue;
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int col = 8 * (SUP * sb[i] + v) + 2 * (lane & 3) + e;
+            if (col < m) { if (row <= col) Sg[(size_t)grow(row) * d + grow(col)] = -acc[i][u][v][e]; }
+            else if (col == zr) D.gS[co + grow(row)] = -acc[i][u][v][e];
+          }
         }
-      }
-      __syncthreads();
     }
-  }
-
-  // ---- write the Schur part of the window's system: plain stores (the system was cleared by k_step / k_solve_init
-  //      and nothing else has touched these entries yet - k_direct runs after this kernel)
-  double *Sg = D.Smat + D.S_off[w];
-  for (int e = tid; e < nkeys * 36; e += WT) {
-    const int pr = e / 36, rq = e - 36 * pr, p = rq / 6, q = rq - 6 * p;
-    int a, b;
-    unrank_key(pr, a, b);
-    if (a == b && p > q) continue;
-    const int row = (a < F ? 15 * a : 15 * F) + p, col = (b < F ? 15 * b : 15 * F) + q;
-    Sg[(size_t)row * d + col] = V[(6 * a + p) * m + 6 * b + q];
-  }
-  for (int e = tid; e < m; e += WT) {
-    const int a = e / 6;
-    D.gS[co + (a < F ? 15 * a : 15 * F) + (e - 6 * a)] = -gsch[e];
   }
   if (!lead) return;
   __syncthreads();
@@ -742,6 +752,7 @@ struct Build3Ctx {
 size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay) {
   const int nbmax = max_frames + (any_ex ? 1 : 0);
   lay->mp = 6 * nbmax + 2;
+  while (lay->mp % 16 != 4) lay->mp++;   // fragment loads of the tensor-core rank update are bank-conflict free for mp = 4 (mod 16)
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o = 0;
   lay->o_Y = o; o += al(((size_t)D.nP + 4 * (size_t)D.nL) * lay->mp * sizeof(double));
@@ -767,8 +778,11 @@ int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, cudaSt
 }
 
 size_t build3_smem(int max_frames, bool any_ex, int max_prior_n) {
-  const int nb = max_frames + (any_ex ? 1 : 0), m = 6 * nb, mp = m + 2;
-  return ((size_t)m * m + m + (size_t)NSTAGE * CH * mp) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
+  const int nb = max_frames + (any_ex ? 1 : 0), m = 6 * nb;
+  int mp = m + 2;
+  while (mp % 16 != 4) mp++;
+  (void)m;
+  return ((size_t)NSTAGE * CH * mp + YSLACK) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
 }
 
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
