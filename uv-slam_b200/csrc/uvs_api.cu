@@ -263,6 +263,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
                w_iidx = wk.take(nImu * sizeof(int2));
   const size_t w_ptb = wk.take(nP * I), w_lnb = wk.take(nL * I);            // begin arrays (memset 0x7f together)
   const size_t w_pte = wk.take(nP * I), w_lne = wk.take(nL * I), w_ptw = wk.take(nP * I), w_lnw = wk.take(nL * I);
+  const size_t w_icomp = wk.take((size_t)nImu * 108 * Dd);
   const size_t w_sqi = wk.take((size_t)nImu * 225 * Dd), w_prH = wk.take((size_t)nPJ * Dd), w_err = wk.take(I);
   const size_t w_rp = wk.take((size_t)nProj * 48 * Dd), w_rl = wk.take((size_t)nLobs * 24 * Dd), w_rv = wk.take((size_t)nVobs * 12 * Dd),
                w_ri = wk.take((size_t)nImu * REC_IMU * Dd), w_rpr = wk.take(nPriorR * Dd);
@@ -399,7 +400,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   D.pblk_col = WI(o_bcol); D.pblk_cam = WI(o_bcam); D.pblk_row = WI(o_brow);
   D.proj_idx = (int4 *)(Dv + w_pidx); D.line_idx4 = (int4 *)(Dv + w_lidx); D.vp_idx4 = (int4 *)(Dv + w_vidx); D.imu_idx = (int2 *)(Dv + w_iidx);
   D.pt_begin = WI(w_ptb); D.ln_begin = WI(w_lnb); D.pt_end = WI(w_pte); D.ln_end = WI(w_lne); D.pt_win = WI(w_ptw); D.ln_win = WI(w_lnw);
-  D.imu_sqrt_info = WD(w_sqi); D.prior_H = WD(w_prH); D.err = WI(w_err);
+  D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.prior_H = WD(w_prH); D.err = WI(w_err);
   D.rec_proj = WD(w_rp); D.rec_line = WD(w_rl); D.rec_vp = WD(w_rv); D.rec_imu = WD(w_ri); D.rec_prior = WD(w_rpr);
   D.scale_cam = WD(w_scc); D.scale_pt = WD(w_scp); D.scale_ln = WD(w_scl);
   D.Smat = WD(w_S); D.gS = WD(w_gS); D.gfull = WD(w_gf); D.colsq_cam = WD(w_csq);
@@ -418,7 +419,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   h->launches += launch_prep(D, h->stream);
   if (h->use_build3) {
     CK(cudaMemsetAsync(Dv + w_b3 + h->b3.o_Y, 0, h->b3.o_ph - h->b3.o_Y, h->stream));   // dense landmark columns start as zeros
-    h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->stream);
+    h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->any_ex, h->stream);
   }
   int rc = post_launch(h, "prep kernels");
   if (rc) return rc;
@@ -602,8 +603,7 @@ static int launch_resid_sweep(UvsHandle *h, int mode, int cand, int slot) {
   double *cost = D.acc + slot;
   cudaStream_t st = h->stream;
   h->launches += launch_proj(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_line(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_vp(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_line_vp(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
   h->launches += launch_imu(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
   // residual-only: the prior residual of the CURRENT iterate (rec_prior) must survive a rejected step
   h->launches += launch_prior(D, h->max_prior_n, false, mode, cand, nullptr, cost, ACC_STRIDE, st);
@@ -660,8 +660,8 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
   for (int it = 0; it < h->opts.max_num_iterations; it++) {
     STAGE(0);
     h->launches += launch_proj(D, P, true, false, 1, 0, D.rec_proj, nullptr, cost0, ACC_STRIDE, st); STAGE(1);
-    h->launches += launch_line(D, P, true, false, 1, 0, D.rec_line, nullptr, cost0, ACC_STRIDE, st); STAGE(2);
-    h->launches += launch_vp(D, P, true, false, 1, 0, D.rec_vp, nullptr, cost0, ACC_STRIDE, st); STAGE(3);
+    h->launches += launch_line_vp(D, P, true, 1, 0, D.rec_line, D.rec_vp, cost0, ACC_STRIDE, st); STAGE(2);
+    STAGE(3);   // the VP factors ride in the line kernel
     h->launches += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, st); STAGE(4);
     h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, st); STAGE(5);
     rc = post_launch(h, "Jacobian sweep"); if (rc) return rc;

@@ -17,6 +17,8 @@
 //   k_back_points / k_back_lines   one thread per point / one lane group per line: delta_k = -(E+D^2)^-1/2 (z + Y^T delta_c).
 // The model cost change uses  -(g^T y + y^T H y / 2) = (y^T D^2 y - g^T y) / 2  (y solves (H + D^2) y = -g),
 // which needs no Jacobians; k_chol adds the camera part.
+#include <algorithm>
+
 #include "uvs_device.cuh"
 #include "uvs_kernels.h"
 
@@ -377,7 +379,9 @@ __device__ __forceinline__ long long direct_base(const Dev &D, int w) {
   return 6LL * D.proj_off[w] + D.lobs_off[w] + D.vobs_off[w];
 }
 
-__global__ void __launch_bounds__(128) k_prep_direct(Dev D, DirectLists L) {
+// `fused` (batches without a free extrinsic): a projection factor appears ONCE, under its off-diagonal pair (i, j) -
+// k_direct_fused derives the (i,i), (j,j) blocks and the gradient from the same read of the record.
+__global__ void __launch_bounds__(128) k_prep_direct(Dev D, DirectLists L, int fused) {
   __shared__ int cnt_all[4][KMAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * 4 + warp;
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(128) k_prep_direct(Dev D, DirectLists L) {
       }
       __syncwarp();
     };
-    for (int slot = 0; slot < (ex ? 6 : 3); slot++) {
+    for (int slot = fused ? 2 : 0; slot < (fused ? 3 : (ex ? 6 : 3)); slot++) {
       for (int base = j0; base < j1; base += 32) {
         const int f = base + lane;
         const bool act = f < j1;
@@ -566,6 +570,144 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
   }
 }
 
+
+// Fused variant for batches without a free extrinsic (the reference's EuRoC configuration): every factor record is
+// read exactly once.  Units per window: one warp per off-diagonal camera-block pair (a < b) takes the projection
+// factors of that pair and accumulates the (a,b) block (36 entries, owned by this warp), its share of the (a,a) and
+// (b,b) blocks (21 + 21) and of the gradient (6 + 6) - 90 outputs, three per lane; SEGS_D warps per diagonal block
+// take the line / VP factors.  The lists are read 32 items at a time (coalesced) and handed round by shuffles, so the
+// record loads of consecutive items are independent and stay in flight together.
+constexpr int SEGS_D = 4;
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int nb_max) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int npair = nb_max * (nb_max - 1) / 2;
+  const int U = npair + nb_max * SEGS_D;
+  const long long unit = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int w = (int)(unit / U), local = (int)(unit - (long long)w * U);
+  if (w >= D.B) return;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int fo = D.frame_off[w], nb = D.frame_off[w + 1] - fo;
+  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+  double *Sg = D.Smat + D.S_off[w];
+  const int2 *items = L.items + direct_base(D, w);
+  const int *off = L.off + (size_t)w * KMAX;
+  if (local < npair) {
+    int b = (int)((sqrtf(8.0f * (float)local + 1.0f) + 1.0f) * 0.5f);   // local = b (b - 1) / 2 + a, a < b
+    while (b * (b - 1) / 2 > local) b--;
+    while ((b + 1) * b / 2 <= local) b++;
+    const int a = local - b * (b - 1) / 2;
+    if (b >= nb) return;
+    const int key = pair_key(a, b);
+    const int i0 = off[key], i1 = off[key + 1];
+    if (i0 >= i1) return;
+    // output o = lane + 32 t:  [0,36) block (a,b)   [36,57) (a,a)   [57,78) (b,b)   [78,84) g_a   [84,90) g_b
+    // operand offsets inside the record for a kind-2 item (a = anchor frame i: A = Ji at 2, B = Jj at 14) and a
+    // kind-3 item (a = observing frame j: A = Jj, B = Ji);  second row: +6 for a Jacobian operand, +1 for the residual
+    int x2[3], y2[3], x3[3], y3[3], yd[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int o = lane + 32 * t;
+      int xs = 0, xp = 0, ys = 0, yq = 0;   // operand = block (0 = A, 1 = B, 2 = residual) + column
+      if (o < 36) { xs = 0; xp = o / 6; ys = 1; yq = o - 6 * xp; }
+      else if (o < 57) { xs = 0; xp = c_sym_p[o - 36]; ys = 0; yq = c_sym_q[o - 36]; }
+      else if (o < 78) { xs = 1; xp = c_sym_p[o - 57]; ys = 1; yq = c_sym_q[o - 57]; }
+      else if (o < 84) { xs = 0; xp = o - 78; ys = 2; }
+      else if (o < 90) { xs = 1; xp = o - 84; ys = 2; }
+      x2[t] = (xs == 0 ? 2 : 14) + xp; x3[t] = (xs == 0 ? 14 : 2) + xp;
+      y2[t] = ys == 2 ? 0 : (ys == 0 ? 2 : 14) + yq; y3[t] = ys == 2 ? 0 : (ys == 0 ? 14 : 2) + yq;
+      yd[t] = ys == 2 ? 1 : 6;
+    }
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int base = i0; base < i1; base += 32) {
+      int2 my = make_int2(0, -1);
+      if (base + lane < i1) {
+        my = items[base + lane];
+        if (D.nranks > 1 && (D.proj_idx[my.x].z % D.nranks) != D.rank) my.y = -1;   // factor-parallel: another rank's landmark
+        if (my.y >= 0) {   // every lane pulls the record of its own item towards L2 -> 32 records in flight per warp
+          const double *rec = D.rec_proj + (size_t)my.x * REC_PROJ;
+          prefetch_l2(rec); prefetch_l2(rec + 13); prefetch_l2(rec + 25);
+        }
+      }
+      const int cnt = min(32, i1 - base);
+#pragma unroll 4
+      for (int k = 0; k < cnt; k++) {
+        const int fidx = __shfl_sync(full, my.x, k), kd = __shfl_sync(full, my.y, k);
+        if (kd < 0) continue;
+        const double *rec = D.rec_proj + (size_t)fidx * REC_PROJ;
+        const bool swap = kd == 3;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const int xo = swap ? x3[t] : x2[t], yo = swap ? y3[t] : y2[t];
+          acc[t] += rec[xo] * rec[yo] + rec[xo + 6] * rec[yo + yd[t]];
+        }
+      }
+    }
+    const int ra = 15 * a, rb = 15 * b;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int o = lane + 32 * t;
+      if (o < 36) { const int p = o / 6, q = o - 6 * p; Sg[(size_t)(ra + p) * d + rb + q] += acc[t]; }   // sole owner of the block
+      else if (o < 78) {
+        const int e = o < 57 ? o - 36 : o - 57, r0 = o < 57 ? ra : rb;
+        const int p = c_sym_p[e], q = c_sym_q[e];
+        atomicAdd(Sg + (size_t)(r0 + p) * d + r0 + q, acc[t]);
+        if (p == q) atomicAdd(D.colsq_cam + co + r0 + p, acc[t]);
+      } else if (o < 90) {
+        const int r0 = (o < 84 ? ra : rb) + (o < 84 ? o - 78 : o - 84);
+        atomicAdd(D.gS + co + r0, acc[t]);
+        atomicAdd(D.gfull + co + r0, acc[t]);
+      }
+    }
+  } else {
+    // line / VP factors of diagonal block a, one segment of the list
+    const int a = (local - npair) / SEGS_D, seg = (local - npair) - a * SEGS_D;
+    if (a >= nb) return;
+    const int key = pair_key(a, a);
+    int i0 = off[key], i1 = off[key + 1];
+    const int per = (i1 - i0 + SEGS_D - 1) / SEGS_D;
+    i0 += seg * per; i1 = min(i1, i0 + per);
+    if (i0 >= i1) return;
+    const bool isg = lane >= 21;
+    const int p = lane < 21 ? c_sym_p[lane] : min(lane - 21, 5), q = lane < 21 ? c_sym_q[lane] : 0;
+    double acc = 0.0;
+    for (int base = i0; base < i1; base += 32) {
+      const double *myrec = nullptr;
+      int mybase = -1;   // offset of the pose block inside the record; -1 = skip
+      if (base + lane < i1) {
+        const int2 it = items[base + lane];
+        const bool line = it.y == 7;
+        bool mine = true;
+        if (D.nranks > 1) mine = ((line ? D.line_idx4[it.x].y : D.vp_idx4[it.x].y) % D.nranks) == D.rank;
+        if (mine) {
+          myrec = line ? D.rec_line + (size_t)it.x * REC_LINE : D.rec_vp + (size_t)it.x * REC_VP; mybase = line ? 2 : 1;
+          prefetch_l2(myrec); prefetch_l2(myrec + (line ? 13 : 6));
+        }
+      }
+      const int cnt = min(32, i1 - base);
+#pragma unroll 4
+      for (int k = 0; k < cnt; k++) {
+        const int bA = __shfl_sync(full, mybase, k);
+        const double *rec = reinterpret_cast<const double *>(__shfl_sync(full, reinterpret_cast<unsigned long long>(myrec), k));
+        if (bA < 0) continue;
+        double t = rec[bA + p] * (isg ? rec[0] : rec[bA + q]);
+        if (bA == 2) t += rec[bA + 6 + p] * (isg ? rec[1] : rec[bA + 6 + q]);   // line factors have two residual rows
+        acc += t;
+      }
+    }
+    const int ra = 15 * a;
+    if (lane < 21) {
+      atomicAdd(Sg + (size_t)(ra + p) * d + ra + q, acc);
+      if (p == q) atomicAdd(D.colsq_cam + co + ra + p, acc);
+    } else if (lane < 27) {
+      atomicAdd(D.gS + co + ra + p, acc);
+      atomicAdd(D.gfull + co + ra + p, acc);
+    }
+  }
+}
+
 // FP64 tensor-core MMA  D(8x8) += A(8x4) B(4x8)  (mma.sync m8n8k4: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}])
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -587,10 +729,8 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
   const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
   const int nb = F + (ex ? 1 : 0), m = 6 * nb, mp = S.mp;
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
-  const bool lead = D.nranks <= 1 || D.rank == 0;
-  // shared layout: Ych[NSTAGE][CH][mp] (TMA destination, 16-byte aligned) + slack for fragment rows past mp, cmap(int)[max_prior_n]
+  // shared layout: Ych[NSTAGE][CH][mp] (TMA destination, 16-byte aligned) + slack for fragment rows past mp
   double *Ych = sm;
-  int *cmap = reinterpret_cast<int *>(Ych + (size_t)NSTAGE * CH * mp + YSLACK);
   if (tid == 0) { for (int k = 0; k < NSTAGE; k++) mbar_init(&bar[k], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   for (int e = tid; e < YSLACK; e += WT) Ych[(size_t)NSTAGE * CH * mp + e] = 0.0;
   __syncthreads();
@@ -683,62 +823,90 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
         }
     }
   }
-  if (!lead) return;
-  __syncthreads();
-  // IMU factors: 30x30 blocks, record staged in shared memory (the chunk buffers are free now)
-  double *Js = Ych;
-  for (int f = D.imu_off[w]; f < D.imu_off[w + 1]; f++) {
-    const double *R = D.rec_imu + (size_t)f * REC_IMU;
-    for (int e = tid; e < REC_IMU; e += WT) Js[e] = R[e];
+}
+
+// IMU blocks and the prior of one window, added to the reduced system after k_window_system has stored the Schur part
+// (a kernel of its own: the work is a handful of L2 round trips per window, which the two resident CTAs per SM of the
+// rank-update kernel cannot hide, while here six to eight windows share an SM).  All additions are fire-and-forget
+// FP64 reductions, so the IMU factors of a window are processed in one pass.
+constexpr int TT = 256;       // threads of k_window_tail
+constexpr int IMU_G = 4;      // IMU records staged per pass (15 KB: ten or more CTAs per SM)
+
+__global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
+  extern __shared__ __align__(16) double sm[];
+  const int w = blockIdx.x;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int tid = threadIdx.x;
+  const int fo = D.frame_off[w];
+  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+  double *Sg = D.Smat + D.S_off[w];
+  const int f0 = D.imu_off[w], nf = blockIdx.y == 0 ? D.imu_off[w + 1] - f0 : 0;   // blockIdx.y: 0 = IMU factors, 1 = prior
+  for (int g0 = 0; g0 < nf; g0 += IMU_G) {
+    const int ng = min(IMU_G, nf - g0);
+    const double *R = D.rec_imu + (size_t)(f0 + g0) * REC_IMU;
+    for (int e = tid; e < ng * REC_IMU; e += TT) sm[e] = R[e];
     __syncthreads();
-    const int c0 = 15 * (D.imu_idx[f].x - fo);
-    const double *J = Js + 15;
-    for (int e = tid; e < 900; e += WT) {
-      const int p = e / 30, q = e - 30 * p;
-      if (p > q) continue;
+    // J^T J: the 465 upper-triangle entries of every 30x30 block
+    for (int e = tid; e < ng * 465; e += TT) {
+      const int k = e / 465, t = e - 465 * k;
+      int p = (int)((61.0f - sqrtf(3721.0f - 8.0f * (float)t)) * 0.5f);   // t = p (61 - p) / 2 + (q - p)
+      while (p * (61 - p) / 2 > t) p--;
+      while ((p + 1) * (60 - p) / 2 <= t) p++;
+      const int q = p + t - p * (61 - p) / 2;
+      const double *J = sm + k * REC_IMU + 15;
       double h = 0.0;
 #pragma unroll
       for (int i = 0; i < 15; i++) h += J[i * 30 + p] * J[i * 30 + q];
-      Sg[(size_t)(c0 + p) * d + c0 + q] += h;
+      const int c0 = 15 * (D.imu_idx[f0 + g0 + k].x - fo);
+      atomicAdd(Sg + (size_t)(c0 + p) * d + c0 + q, h);
+      if (p == q) atomicAdd(D.colsq_cam + co + c0 + p, h);
     }
-    if (tid < 30) {
-      double gg = 0.0, q2 = 0.0;
+    for (int e = tid; e < ng * 30; e += TT) {
+      const int k = e / 30, p = e - 30 * k;
+      const double *r = sm + k * REC_IMU, *J = r + 15;
+      double gg = 0.0;
 #pragma unroll
-      for (int i = 0; i < 15; i++) { const double j = J[i * 30 + tid]; gg += j * Js[i]; q2 += j * j; }
-      D.gfull[co + c0 + tid] += gg; D.gS[co + c0 + tid] += gg; D.colsq_cam[co + c0 + tid] += q2;
+      for (int i = 0; i < 15; i++) gg += J[i * 30 + p] * r[i];
+      const int c0 = 15 * (D.imu_idx[f0 + g0 + k].x - fo);
+      atomicAdd(D.gfull + co + c0 + p, gg); atomicAdd(D.gS + co + c0 + p, gg);
     }
     __syncthreads();
   }
-  // prior: H += J0^T J0 (precomputed), g += J0^T r
-  const int n = D.prior_off[w + 1] - D.prior_off[w];
+  // prior: H += J0^T J0 (precomputed at upload), g += J0^T r
+  const int n = blockIdx.y == 1 ? D.prior_off[w + 1] - D.prior_off[w] : 0;
   if (n > 0) {
-    for (int c = tid; c < n; c += WT) cmap[c] = -1;
+    int *cmap = reinterpret_cast<int *>(sm);
+    for (int c = tid; c < n; c += TT) cmap[c] = -1;
     __syncthreads();
-    for (int b = D.pblk_off[w] + tid; b < D.pblk_off[w + 1]; b += WT) {
+    for (int b = D.pblk_off[w] + tid; b < D.pblk_off[w + 1]; b += TT) {
       const int kind = D.pblk_kind[b], cam = D.pblk_cam[b], col = D.pblk_col[b];
       const int ls = (kind == 0 || kind == 2) ? 6 : (kind == 1 ? 9 : 1);
       if (cam >= 0) for (int c = 0; c < ls; c++) cmap[col + c] = cam + c;
     }
     __syncthreads();
     const double *H = D.prior_H + D.priorJ_off[w], *J0 = D.prior_J + D.priorJ_off[w], *r = D.rec_prior + D.prior_off[w];
-    for (int e = tid; e < n * n; e += WT) {
+#pragma unroll 4
+    for (int e = tid; e < n * n; e += TT) {
       const int p = e / n, q = e - p * n;
       const int cp = cmap[p], cq = cmap[q];
       if (cp < 0 || cq < 0 || cp > cq) continue;
-      Sg[(size_t)cp * d + cq] += H[e];
+      atomicAdd(Sg + (size_t)cp * d + cq, __ldg(H + e));
     }
-    for (int p = tid; p < n; p += WT) {
+    // gradient: thread (p, part) sums every fourth row of column p (coalesced over p), eight loads in flight
+    for (int u = tid; u < 4 * n; u += TT) {
+      const int part = u / n, p = u - part * n;
       const int cp = cmap[p];
       if (cp < 0) continue;
-      double g8[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // eight independent partial sums keep eight loads in flight
-      int i = 0;
-      for (; i + 8 <= n; i += 8) {
+      double g4[4] = {0, 0, 0, 0};
+      int i = part;
+      for (; i + 12 < n; i += 16) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) g8[u] += J0[(size_t)(i + u) * n + p] * r[i + u];
+        for (int v = 0; v < 4; v++) g4[v] += __ldg(J0 + (size_t)(i + 4 * v) * n + p) * r[i + 4 * v];
       }
-      for (; i < n; i++) g8[0] += J0[(size_t)i * n + p] * r[i];
-      const double gg = ((g8[0] + g8[1]) + (g8[2] + g8[3])) + ((g8[4] + g8[5]) + (g8[6] + g8[7]));
-      D.gfull[co + cp] += gg; D.gS[co + cp] += gg; D.colsq_cam[co + cp] += H[(size_t)p * n + p];
+      for (; i < n; i += 4) g4[0] += __ldg(J0 + (size_t)i * n + p) * r[i];
+      const double gg = (g4[0] + g4[1]) + (g4[2] + g4[3]);
+      atomicAdd(D.gfull + co + cp, gg); atomicAdd(D.gS + co + cp, gg);
+      if (part == 0) atomicAdd(D.colsq_cam + co + cp, __ldg(H + (size_t)p * n + p));
     }
   }
 }
@@ -771,9 +939,9 @@ static void make_ctx(char *base, const Build3Layout &lay, Build3Ctx &c) {
 
 static inline int cdiv3(int a, int b) { return (a + b - 1) / b; }
 
-int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st) {
+int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, bool any_ex, cudaStream_t st) {
   Build3Ctx c; make_ctx(base, lay, c);
-  k_prep_direct<<<cdiv3(D.B, 4), 128, 0, st>>>(D, c.L);
+  k_prep_direct<<<cdiv3(D.B, 4), 128, 0, st>>>(D, c.L, any_ex ? 0 : 1);
   return 1;
 }
 
@@ -795,12 +963,21 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
   k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
-  {
-    const int nb_max = max_frames + (any_ex ? 1 : 0);
+  int ntail = 0;
+  if (D.nranks <= 1 || D.rank == 0) {   // factor-parallel mode: IMU factors and the prior belong to rank 0
+    const size_t tsm = std::max((size_t)IMU_G * REC_IMU * sizeof(double), (size_t)(max_prior_n + 2) * sizeof(int));
+    k_window_tail<<<dim3(D.B, 2), TT, tsm, st>>>(D, max_prior_n);
+    ntail = 1;
+  }
+  if (any_ex) {
+    const int nb_max = max_frames + 1;
     const long long units = (long long)D.B * (nb_max * SEGS + nb_max * (nb_max - 1) / 2);
     k_direct<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(D, c.L, nb_max);
+  } else {
+    const long long units = (long long)D.B * (max_frames * SEGS_D + max_frames * (max_frames - 1) / 2);
+    k_direct_fused<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(D, c.L, max_frames);
   }
-  return n + 2;
+  return n + 2 + ntail;
 }
 
 int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st) {

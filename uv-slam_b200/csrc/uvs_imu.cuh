@@ -42,14 +42,14 @@ struct ImuIn {
 };
 
 // Geometry of one factor by ONE thread: unweighted residual raw[15] and, when kJac, the twelve 3x3 blocks the
-// unweighted Jacobian is made of (compact form, 9 doubles each, IMU_NBLK blocks):
+// unweighted Jacobian is made of (compact form, 9 doubles each, IMU_NBLK blocks; element e at comp[e * cstride]):
 //   0 RiT   1 [a]x   2 -(Qleft(qj^-1 qi) Qright(dq^))_br   3 [b]x   4 RiT*T   5 dp_dba   6 dp_dbg
 //   7 -Qleft(qj^-1 qi dq)_br dq_dbg   8 dv_dba   9 dv_dbg   10 Qleft(dq^^-1 qi^-1 qj)_br   11 I
 constexpr int IMU_NBLK = 12;
 constexpr int IMU_COMP = 9 * IMU_NBLK;
 
 template <bool kJac>
-__device__ __forceinline__ void imu_geometry(const ImuIn &in, const double g[3], double raw[15], double *comp) {
+__device__ __forceinline__ void imu_geometry(const ImuIn &in, const double g[3], double raw[15], double *comp, int cstride) {
   d3 Pi, Pj; q4 Qi, Qj;
   load_pose(in.pose_i, Pi, Qi);
   load_pose(in.pose_j, Pj, Qj);
@@ -83,7 +83,7 @@ __device__ __forceinline__ void imu_geometry(const ImuIn &in, const double g[3],
   if (!kJac) return;
   auto store = [&](int blk, const m33 &M, double sgn) {
 #pragma unroll
-    for (int k = 0; k < 9; k++) comp[9 * blk + k] = sgn * M.a[k];
+    for (int k = 0; k < 9; k++) comp[(size_t)(9 * blk + k) * cstride] = sgn * M.a[k];
   };
   const m33 RiT = qmat(Qi_inv);
   const q4 qji = qmul(qinv(Qj), Qi);
@@ -121,17 +121,5 @@ __constant__ ImuPut c_imu_puts[18] = {
     {6, 12, 9, -1}, {9, 9, 11, -1}, {12, 12, 11, -1},
     {0, 15, 0, 1}, {3, 18, 10, 1},                                                             // pose_j
     {6, 21, 0, 1}, {9, 24, 11, 1}, {12, 27, 11, 1}};                                           // speed-bias_j
-
-// expands the compact blocks into the dense 15 x 30 Jacobian (one warp, shared memory)
-__device__ __forceinline__ void imu_expand_warp(const double *comp, double *Jraw, int lane) {
-  for (int e = lane; e < 450; e += 32) Jraw[e] = 0.0;
-  __syncwarp();
-  for (int e = lane; e < 18 * 9; e += 32) {
-    const int b = e / 9, k = e - 9 * b;
-    const ImuPut p = c_imu_puts[b];
-    Jraw[(p.r0 + k / 3) * 30 + p.c0 + k % 3] = (double)p.sgn * comp[9 * p.blk + k];
-  }
-  __syncwarp();
-}
 
 }  // namespace uvs

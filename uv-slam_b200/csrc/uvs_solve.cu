@@ -10,6 +10,9 @@
 //                 camera-only factors
 //   k_step        step quality, accept / reject, radius update, termination tests, iteration log
 // One CTA per window; windows of a batch advance in lock-step but accept / reject independently.
+#include <algorithm>
+#include <cstdlib>
+
 #include "uvs_device.cuh"
 #include "uvs_math.cuh"
 #include "uvs_kernels.h"
@@ -52,7 +55,7 @@ __device__ __forceinline__ double block_max(double v, double *red) {
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   double m = red[0];
-  for (int k = 1; k < CT / 32; k++) m = fmax(m, red[k]);
+  for (int k = 1; k < (int)blockDim.x / 32; k++) m = fmax(m, red[k]);
   __syncthreads();
   return m;
 }
@@ -63,14 +66,30 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   double m = 0.0;
-  for (int k = 0; k < CT / 32; k++) m += red[k];
+  for (int k = 0; k < (int)blockDim.x / 32; k++) m += red[k];
   __syncthreads();
   return m;
 }
 
 constexpr int NB = 8;   // block size of the shared-memory Cholesky
-constexpr int RS = 9, BS = 72;   // row / block stride in doubles (padded against bank conflicts)
 constexpr int MAX_PRIOR_COLS = 512;   // prior dimension bound (15 x 32 frames + extrinsic + td = 487)
+
+// shared-memory layout of the blocked Cholesky (see chol_window): offsets in doubles
+struct CholLayout { int K, vr, dbase, vbase, total; };
+__host__ __device__ __forceinline__ CholLayout chol_layout(int d) {
+  CholLayout L;
+  L.K = (d + NB - 1) / NB;
+  L.vr = d - NB * (L.K - 1);                                   // rows of the last block row
+  L.dbase = L.K > 1 ? 32 * (L.K - 1) * (L.K - 2) + 2 * (L.K - 1) * 4 * L.vr : 0;   // after the off-diagonal fragments
+  L.vbase = L.dbase + 36 * L.K;                                // after the packed diagonal blocks
+  L.total = L.vbase + 2 * L.K * NB;
+  return L;
+}
+
+// FP64 tensor-core MMA  D(8x8) += A(8x4) B(4x8)  (mma.sync m8n8k4: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}])
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
 // linear index of the row-major lower triangle -> (I, J), J <= I
 __device__ __forceinline__ void unrank_lower(int t, int &I, int &J) {
@@ -82,9 +101,11 @@ __device__ __forceinline__ void unrank_lower(int t, int &I, int &J) {
 
 template <bool kPacked>
 __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, bool mc_identity) {
-  __shared__ double red[CT / 32];
+  __shared__ double red[CT / 32];   // CT = largest block size
   __shared__ int s_flag;
-  __shared__ int s_cmap[MAX_PRIOR_COLS];
+  __shared__ unsigned short s_pair[kPacked ? 528 : 1];   // (I, J) of the t-th block of a lower triangle, K <= 32
+  const int nthr = blockDim.x;   // 256 when two windows fit one SM, else 512
+  int *s_cmap = reinterpret_cast<int *>(smem);   // aliases the factor: only used after the back-substitution
   double *vec_y = D.gS + D.cam_off[w];   // y (scaled step) parked in the consumed reduced-gradient buffer
   WinCtl &ctl = D.ctl[w];
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
@@ -98,7 +119,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
 
   // ---- gradient max norm of the current iterate, iteration-0 bookkeeping, gradient tolerance
   double gm = 0.0;
-  for (int c = tid; c < d; c += CT) gm = fmax(gm, fabs(gfull[c]));
+  for (int c = tid; c < d; c += nthr) gm = fmax(gm, fabs(gfull[c]));
   if (tid < MAX_RANKS) gm = fmax(gm, acc[ACC_GMAX + tid]);
   gm = block_max(gm, red);
   if (tid == 0) {
@@ -122,62 +143,65 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
   if (s_flag) return;
 
   // ---- Jacobi scaling, fixed from the first Jacobian: s = 1 / (1 + ||J[:,c]||)
-  if (!ctl.have_scale) for (int c = tid; c < d; c += CT) scale[c] = 1.0 / (1.0 + sqrt(colsq[c]));
+  if (!ctl.have_scale) for (int c = tid; c < d; c += nthr) scale[c] = 1.0 / (1.0 + sqrt(colsq[c]));
   __syncthreads();
 
   double *vec;   // solution vector y (d doubles)
   const double radius = ctl.radius;
   if (kPacked) {
-    // ---- blocked path: 8x8 blocks of the lower triangle packed in shared memory
-    //      block (I,J), J <= I, at ((I(I+1)/2 + J) * BS), rows RS = 9 doubles apart (the odd stride
-    //      spreads the rows of different blocks over the banks); rhs as a separate vector.
-    const int K = (d + NB - 1) / NB;
+    // ---- blocked path: the lower triangle in shared memory, 8x8 blocks, stored in FP64 tensor-core FRAGMENT order:
+    //      block row I (rows 8I..8I+7), columns 0..8I-1, is a sequence of 8x4 fragments (32 consecutive doubles,
+    //      element (r, c) at 4r + c = the lane that holds it in mma.sync m8n8k4), so every operand load of the
+    //      trailing update is one contiguous, conflict-free 256-byte read; the diagonal blocks live apart as packed
+    //      lower triangles (36 doubles); the last block row keeps only the rows that exist.  112 KB at d = 165, i.e.
+    //      two windows per SM: while one sits in its pivot chain the other one's trailing update runs.
+    const CholLayout Lo = chol_layout(d);
+    const int K = Lo.K;
     double *A = smem;
-    double *bz = smem + (size_t)K * (K + 1) / 2 * BS;   // rhs / z / y   [8K]
+    double *Dg = smem + Lo.dbase;                       // diagonal blocks
+    double *bz = smem + Lo.vbase;                       // rhs / z / y   [8K]
     double *invd_all = bz + (size_t)K * NB;             // reciprocal diagonal of L, all rows [8K]
     vec = bz;
     const int warp = tid >> 5, lane = tid & 31;
+    auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
+    auto frag = [&](int I, int f) { return A + 32 * I * (I - 1) + f * 4 * rows_of(I); };   // fragment f of block row I
     {
       // rows j of the upper triangle of Sg, coalesced over i; element (i,j), j <= i, of the lower matrix.
       // All loads of a row are issued before they are used (up to MAXL per lane in flight).
-      const int dp = K * NB;
-      constexpr int MAXL = 8;   // 8 x 32 = 256 >= padded dimension of the blocked path
-      for (int j = warp; j < dp; j += CT / 32) {
-        const double sj = j < d ? scale[j] : 0.0;
+      constexpr int MAXL = 8;   // 8 x 32 = 256 >= dimension of the blocked path
+      for (int j = warp; j < d; j += nthr / 32) {
+        const double sj = scale[j];
         double v[MAXL];
 #pragma unroll
         for (int k = 0; k < MAXL; k++) {
           const int i = j + lane + 32 * k;
-          v[k] = (i < d && j < d) ? Sg[(size_t)j * d + i] : 0.0;
+          v[k] = i < d ? Sg[(size_t)j * d + i] : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < MAXL; k++) {
           const int i = j + lane + 32 * k;
-          if (i >= dp) continue;
-          double x = 0.0;
-          if (i < d && j < d) {
-            x = scale[i] * sj * v[k];
-            if (i == j) { const double h = sj * sj * colsq[i]; x += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
-          } else if (i == j) {
-            x = 1.0;   // padding
-          }
-          const int I = i >> 3, J = j >> 3;
-          A[((size_t)I * (I + 1) / 2 + J) * BS + (i & 7) * RS + (j & 7)] = x;
+          if (i >= d) continue;
+          double x = scale[i] * sj * v[k];
+          if (i == j) { const double h = sj * sj * colsq[i]; x += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+          const int I = i >> 3, r = i & 7;
+          if ((j >> 3) == I) Dg[36 * I + r * (r + 1) / 2 + (j & 7)] = x;
+          else frag(I, j >> 2)[4 * r + (j & 3)] = x;
         }
       }
-      // strictly-upper parts of the diagonal blocks are never read
     }
-    for (int c = tid; c < K * NB; c += CT) bz[c] = c < d ? -scale[c] * gS[c] : 0.0;
+    for (int c = tid; c < K * NB; c += nthr) { bz[c] = c < d ? -scale[c] * gS[c] : 0.0; invd_all[c] = 1.0; }
+    for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
     __syncthreads();
     // factor of a diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot chain is
-    // rsqrt -> scale -> rank-1 update, operands exchanged with shuffles
+    // rsqrt -> scale -> rank-1 update, operands exchanged with shuffles.  Missing rows act as identity rows.
     auto potrf_block = [&](int k) {
-      double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
       double *invd = invd_all + k * NB;
       double a[NB];
       const int r = lane & 7;
+      const bool have = r < rows_of(k);
+      double *row = Dg + 36 * k + r * (r + 1) / 2;
 #pragma unroll
-      for (int c = 0; c < NB; c++) a[c] = c <= r ? Akk[r * RS + c] : 0.0;
+      for (int c = 0; c < NB; c++) a[c] = have ? (c <= r ? row[c] : 0.0) : (c == r ? 1.0 : 0.0);
       int bad = 0;
 #pragma unroll
       for (int p = 0; p < NB; p++) {
@@ -192,94 +216,108 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
           a[q] -= a[p] * lq;                             // only meaningful for r >= q
         }
       }
-      if (lane < NB) {
+      if (lane < NB && have) {
 #pragma unroll
-        for (int c = 0; c < NB; c++) if (c <= r) Akk[r * RS + c] = a[c];
+        for (int c = 0; c < NB; c++) if (c <= r) row[c] = a[c];
       }
       if (lane == 0 && bad) s_flag = 1;
+    };
+    // C -= L_I L_J^T for one 8x8 block on the tensor cores: lane l holds L[l>>2][l&3] of both operands (the B operand
+    // of m8n8k4 is column-major, i.e. L_J itself), and C[l>>2][2(l&3) + {0,1}]
+    const int fr = lane >> 2, fc = lane & 3;
+    auto block_update = [&](int I, int J, int k) {
+      const int ra = min(fr, rows_of(I) - 1), rb = min(fr, rows_of(J) - 1);   // rows that do not exist: any finite value
+      const double a0 = -frag(I, 2 * k)[4 * ra + fc], a1 = -frag(I, 2 * k + 1)[4 * ra + fc];
+      const double b0 = frag(J, 2 * k)[4 * rb + fc], b1 = frag(J, 2 * k + 1)[4 * rb + fc];
+      double c[2];
+      if (J < I) {
+        double2 *C = reinterpret_cast<double2 *>(frag(I, 2 * J + (fc >> 1)) + 4 * ra + 2 * (fc & 1));
+        const double2 c2 = *C;
+        c[0] = c2.x; c[1] = c2.y;
+        dmma884(c, a0, b0); dmma884(c, a1, b1);
+        if (fr < rows_of(I)) *C = make_double2(c[0], c[1]);
+      } else {
+        double *C = Dg + 36 * I + fr * (fr + 1) / 2 + 2 * fc;   // row fr, columns 2 fc, 2 fc + 1 (lower part only)
+        const bool h0 = 2 * fc <= fr && fr < rows_of(I), h1 = 2 * fc + 1 <= fr && fr < rows_of(I);
+        c[0] = h0 ? C[0] : 0.0; c[1] = h1 ? C[1] : 0.0;
+        dmma884(c, a0, b0); dmma884(c, a1, b1);
+        if (h0) C[0] = c[0];
+        if (h1) C[1] = c[1];
+      }
     };
     if (warp == 0) potrf_block(0);
     __syncthreads();
     for (int k = 0; k < K && !s_flag; k++) {
-      const double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
       const double *invd = invd_all + k * NB;
+      const int vr = rows_of(k);                         // rows of block k that exist
       // panel: L_Ik = A_Ik L_kk^-T for the rows below, z_k = L_kk^-1 b_k
-      const int nrows = NB * (K - 1 - k);
-      for (int t = tid; t <= nrows; t += CT) {
-        double *row;
-        if (t < nrows) { const int i = NB * (k + 1) + t, I = i >> 3; row = A + ((size_t)I * (I + 1) / 2 + k) * BS + (i & 7) * RS; }
-        else row = bz + k * NB;
+      const int nrows = max(0, d - NB * (k + 1));
+      for (int t = tid; t <= nrows; t += nthr) {
         double x[NB];
-#pragma unroll
-        for (int p = 0; p < NB; p++) x[p] = row[p];
+        double2 *r0, *r1;   // columns 8k..8k+3 and 8k+4..8k+7 of the row
+        if (t < nrows) {
+          const int i = NB * (k + 1) + t, I = i >> 3, r = i & 7;
+          r0 = reinterpret_cast<double2 *>(frag(I, 2 * k) + 4 * r); r1 = reinterpret_cast<double2 *>(frag(I, 2 * k + 1) + 4 * r);
+        } else {
+          r0 = reinterpret_cast<double2 *>(bz + k * NB); r1 = r0 + 2;
+        }
+        { const double2 t0 = r0[0], t1 = r0[1], t2 = r1[0], t3 = r1[1];
+          x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; x[4] = t2.x; x[5] = t2.y; x[6] = t3.x; x[7] = t3.y; }
 #pragma unroll
         for (int p = 0; p < NB; p++) {
-          double v = x[p];
+          if (p < vr) {
+            const double *akk = Dg + 36 * k + p * (p + 1) / 2;   // row p of L_kk (broadcast reads)
+            double v = x[p];
 #pragma unroll
-          for (int q = 0; q < p; q++) v -= x[q] * Akk[p * RS + q];
-          x[p] = v * invd[p];
+            for (int q = 0; q < p; q++) v -= x[q] * akk[q];
+            x[p] = v * invd[p];
+          }
         }
-#pragma unroll
-        for (int p = 0; p < NB; p++) row[p] = x[p];
+        r0[0] = make_double2(x[0], x[1]); r0[1] = make_double2(x[2], x[3]);
+        r1[0] = make_double2(x[4], x[5]); r1[1] = make_double2(x[6], x[7]);
       }
       __syncthreads();
-      // trailing update A_IJ -= L_Ik L_Jk^T (4x4 register tiles), b_I -= L_Ik z_k.  Look-ahead: warp 0 updates
-      // the next diagonal block first and factors it while the other warps update the rest.
+      // trailing update A_IJ -= L_Ik L_Jk^T, one 8x8 block per warp and step (two DMMAs), b_I -= L_Ik z_k.
+      // Look-ahead: warp 0 updates the next diagonal block first and factors it while the other warps do the rest.
       const int nt = K - 1 - k;
       if (warp == 0) {
         if (nt > 0) {
-          const int I = k + 1;
-          const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * BS;
-          double *C = A + ((size_t)I * (I + 1) / 2 + I) * BS;
-          for (int e = lane; e < 64; e += 32) {
-            const int r = e >> 3, q = e & 7;
-            if (q > r) continue;
-            double v = C[r * RS + q];
-#pragma unroll
-            for (int p = 0; p < NB; p++) v -= LI[r * RS + p] * LI[q * RS + p];
-            C[r * RS + q] = v;
-          }
+          block_update(k + 1, k + 1, k);
           __syncwarp();
           potrf_block(k + 1);
         }
       } else {
-        const int ntiles = 4 * (nt * (nt + 1) / 2);
-        for (int tile = tid - 32; tile < ntiles; tile += CT - 32) {
-          if (tile < 4) continue;              // block (k+1, k+1): done by warp 0
-          int Ip, Jp;
-          unrank_lower(tile >> 2, Ip, Jp);
-          const int ti = (tile >> 1) & 1, tj = tile & 1;
-          if (Ip == Jp && tj > ti) continue;   // strictly-upper tile of a diagonal block
-          const int I = k + 1 + Ip, J = k + 1 + Jp;
-          const double *LI = A + ((size_t)I * (I + 1) / 2 + k) * BS + ti * 4 * RS;
-          const double *LJ = A + ((size_t)J * (J + 1) / 2 + k) * BS + tj * 4 * RS;
-          double *C = A + ((size_t)I * (I + 1) / 2 + J) * BS + ti * 4 * RS + tj * 4;
-          double c[4][4];
+        if (warp == 1) {
+          // L_kk is not read again before the back-substitution: replace it by its inverse (lane c: column c),
+          // which turns the 8-step dependent chain per block of the back-substitution into independent dot products
+          double *Dk = Dg + 36 * k;
+          double m[NB];
+          const int c = lane & 7;
 #pragma unroll
-          for (int a = 0; a < 4; a++)
+          for (int r = 0; r < NB; r++) {
+            double sacc = 0.0;
 #pragma unroll
-            for (int b2 = 0; b2 < 4; b2++) c[a][b2] = C[a * RS + b2];
-#pragma unroll
-          for (int p = 0; p < NB; p++) {
-            double li[4], lj[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) { li[a] = LI[a * RS + p]; lj[a] = LJ[a * RS + p]; }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-              for (int b2 = 0; b2 < 4; b2++) c[a][b2] -= li[a] * lj[b2];
+            for (int q = 0; q < r; q++) if (r < vr) sacc += Dk[r * (r + 1) / 2 + q] * m[q];
+            m[r] = r < c ? 0.0 : (r == c ? invd[r] : -sacc * invd[r]);
           }
+          __syncwarp();
+          if (lane < NB) {
 #pragma unroll
-          for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b2 = 0; b2 < 4; b2++) C[a * RS + b2] = c[a][b2];
+            for (int r = 0; r < NB; r++) if (r >= c && r < vr) Dk[r * (r + 1) / 2 + c] = m[r];
+          }
         }
-        for (int t = tid - 32; t < nrows; t += CT - 32) {
-          const int i = NB * (k + 1) + t, I = i >> 3;
-          const double *row = A + ((size_t)I * (I + 1) / 2 + k) * BS + (i & 7) * RS;
+        const int nblk = nt * (nt + 1) / 2;
+        for (int blk = warp; blk < nblk; blk += nthr / 32 - 1) {   // blk 0 = (k+1, k+1): warp 0
+          const int pr = s_pair[blk];
+          block_update(k + 1 + (pr >> 8), k + 1 + (pr & 255), k);
+        }
+        for (int t = tid - 32; t < nrows; t += nthr - 32) {
+          const int i = NB * (k + 1) + t, I = i >> 3, r = i & 7;
+          const double2 *r0 = reinterpret_cast<const double2 *>(frag(I, 2 * k) + 4 * r), *r1 = reinterpret_cast<const double2 *>(frag(I, 2 * k + 1) + 4 * r);
+          const double2 *z = reinterpret_cast<const double2 *>(bz + k * NB);
           double v = bz[i];
-#pragma unroll
-          for (int p = 0; p < NB; p++) v -= row[p] * bz[k * NB + p];
+          v -= r0[0].x * z[0].x; v -= r0[0].y * z[0].y; v -= r0[1].x * z[1].x; v -= r0[1].y * z[1].y;
+          v -= r1[0].x * z[2].x; v -= r1[0].y * z[2].y; v -= r1[1].x * z[3].x; v -= r1[1].y * z[3].y;
           bz[i] = v;
         }
       }
@@ -289,27 +327,46 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
       if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
       return;
     }
-    // back-substitution L^T y = z, block row by block row, one warp
+    // back-substitution L^T y = z, block row by block row, one warp: y_k = L_kk^-T z_k as eight independent dot
+    // products (the diagonal blocks hold their inverses by now), then z[0..8k) -= L_k^T y_k eight columns at a time as
+    // (y^T in row 0 of A) x (block of L_k as B) on the tensor cores
     if (warp == 0) {
       for (int k = K - 1; k >= 0; k--) {
-        const double *Akk = A + ((size_t)k * (k + 1) / 2 + k) * BS;
-        double y[NB];
+        const int vr = rows_of(k);
+        const double *Dk = Dg + 36 * k;
+        const int p = lane & 7;
+        double y = 0.0;
 #pragma unroll
-        for (int p = NB - 1; p >= 0; p--) {
-          double v = bz[k * NB + p];
-#pragma unroll
-          for (int q = p + 1; q < NB; q++) v -= Akk[q * RS + p] * y[q];
-          y[p] = v * invd_all[k * NB + p];
-        }
+        for (int q = 0; q < NB; q++) if (q >= p && q < vr) y += Dk[q * (q + 1) / 2 + p] * bz[k * NB + q];
+        // A fragments: row 0 = y[0..3] / y[4..7] (zero for rows that do not exist)
+        double ya = __shfl_sync(0xffffffffu, y, fc), yb = __shfl_sync(0xffffffffu, y, 4 + fc);
+        if (fr != 0 || fc >= vr) ya = 0.0;
+        if (fr != 0 || 4 + fc >= vr) yb = 0.0;
+        const int pa = min(fc, vr - 1), pb = min(4 + fc, vr - 1);   // B[p][n] = L[8k + p][8g + n]: lane holds p = fc (+4), n = fr
         __syncwarp();
-        for (int c = lane; c < k * NB; c += 32) {
-          const double *col = A + ((size_t)k * (k + 1) / 2 + (c >> 3)) * BS + (c & 7);
-          double v = bz[c];
+        if (lane < NB) bz[k * NB + lane] = y;
+        for (int g0 = 0; g0 < k; g0 += 4) {   // four independent column groups in flight
+          double c[4][2];
 #pragma unroll
-          for (int p = 0; p < NB; p++) v -= col[p * RS] * y[p];
-          bz[c] = v;
+          for (int u = 0; u < 4; u++) {
+            c[u][0] = c[u][1] = 0.0;
+            if (g0 + u < k) {
+              const double *f = frag(k, 2 * (g0 + u) + (fr >> 2)) + (fr & 3);
+              dmma884(c[u], ya, f[4 * pa]); dmma884(c[u], yb, f[4 * pb]);
+            }
+          }
+          if (lane < 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              if (g0 + u < k) {
+                double2 *zc = reinterpret_cast<double2 *>(bz + (g0 + u) * NB + 2 * lane);
+                double2 zz = *zc;
+                zz.x -= c[u][0]; zz.y -= c[u][1];
+                *zc = zz;
+              }
+            }
+          }
         }
-        if (lane < NB) bz[k * NB + lane] = y[lane];
         __syncwarp();
       }
     }
@@ -318,14 +375,14 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     // ---- large windows: in place in global memory (mirror the upper triangle into the lower one),
     //      unblocked right-looking Cholesky
     vec = D.delta_cam + co;
-    for (int e = tid; e < d * d; e += CT) {
+    for (int e = tid; e < d * d; e += nthr) {
       const int i = e / d, j = e - i * d;   // lower entry (i, j), j <= i
       if (j > i) continue;
       double v = scale[i] * scale[j] * Sg[(size_t)j * d + i];
       if (i == j) { const double h = scale[i] * scale[i] * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
       Sg[e] = v;
     }
-    for (int c = tid; c < d; c += CT) vec[c] = -scale[c] * gS[c];
+    for (int c = tid; c < d; c += nthr) vec[c] = -scale[c] * gS[c];
     __syncthreads();
     const int ti = tid >> 4, tk = tid & 15;
     bool fail = false;
@@ -334,12 +391,12 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
       if (!(piv > 0.0) || !isfinite(piv)) { fail = true; break; }
       const double inv = 1.0 / sqrt(piv);
       __syncthreads();
-      for (int i = j + 1 + tid; i < d; i += CT) Sg[(size_t)i * d + j] *= inv;
+      for (int i = j + 1 + tid; i < d; i += nthr) Sg[(size_t)i * d + j] *= inv;
       if (tid == 0) { vec[j] *= inv; Sg[(size_t)j * d + j] = piv * inv; }
       __syncthreads();
       const double zj = vec[j];
-      for (int i = j + 1 + tid; i < d; i += CT) vec[i] -= Sg[(size_t)i * d + j] * zj;
-      for (int i = j + 1 + ti; i < d; i += CT / 16) {
+      for (int i = j + 1 + tid; i < d; i += nthr) vec[i] -= Sg[(size_t)i * d + j] * zj;
+      for (int i = j + 1 + ti; i < d; i += nthr / 16) {
         const double lij = Sg[(size_t)i * d + j];
         for (int k = j + 1 + tk; k <= i; k += 16) Sg[(size_t)i * d + k] -= lij * Sg[(size_t)k * d + j];
       }
@@ -365,11 +422,11 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
   const int cur = D.cur[w];
   const int fo = D.frame_off[w];
   double step2 = 0.0, x2 = 0.0;
-  for (int c = tid; c < d; c += CT) { const double yv = vec[c]; vec_y[c] = yv; D.delta_cam[co + c] = scale[c] * yv; }
+  for (int c = tid; c < d; c += nthr) { const double yv = vec[c]; vec_y[c] = yv; D.delta_cam[co + c] = scale[c] * yv; }
   __syncthreads();
   const double *dl = D.delta_cam + co;
   const bool lead = D.nranks <= 1 || D.rank == 0;
-  for (int f = tid; f < F; f += CT) {
+  for (int f = tid; f < F; f += nthr) {
     const double *x = D.pose[cur] + 7 * (size_t)(fo + f);
     double *y = D.pose[cur ^ 1] + 7 * (size_t)(fo + f);
     const double *t = dl + 15 * f;
@@ -409,9 +466,9 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
   // ---- model cost change of the camera-only factors: sum (J delta) . (r + J delta / 2)
   {   // prior column -> camera offset (-1: constant block)
     const int n = D.prior_off[w + 1] - D.prior_off[w];
-    for (int c = tid; c < n && c < MAX_PRIOR_COLS; c += CT) s_cmap[c] = -1;
+    for (int c = tid; c < n && c < MAX_PRIOR_COLS; c += nthr) s_cmap[c] = -1;
     __syncthreads();
-    for (int b = D.pblk_off[w] + tid; b < D.pblk_off[w + 1]; b += CT) {
+    for (int b = D.pblk_off[w] + tid; b < D.pblk_off[w + 1]; b += nthr) {
       const int kind = D.pblk_kind[b], cam = D.pblk_cam[b], col = D.pblk_col[b];
       const int ls = (kind == 0 || kind == 2) ? 6 : (kind == 1 ? 9 : 1);
       if (cam >= 0) for (int c = 0; c < ls; c++) s_cmap[col + c] = cam + c;
@@ -421,7 +478,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
   double mc = 0.0;
   if (lead && mc_identity) {
     // -(g^T y + y^T H y / 2) = (y^T D^2 y - g^T y) / 2 for the solution of (H + D^2) y = -g: camera part
-    for (int c = tid; c < d; c += CT) {
+    for (int c = tid; c < d; c += nthr) {
       const double y = vec_y[c];
       const double h = scale[c] * scale[c] * colsq[c];
       mc += 0.5 * (clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius * y * y - scale[c] * gfull[c] * y);
@@ -429,7 +486,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     mc = -mc;   // accumulated below as -mc
   } else if (lead) {
     const int warp = tid >> 5, lane = tid & 31;
-    for (int f = D.imu_off[w] + warp; f < D.imu_off[w + 1]; f += CT / 32) {
+    for (int f = D.imu_off[w] + warp; f < D.imu_off[w + 1]; f += nthr / 32) {
       const double *R = D.rec_imu + (size_t)f * REC_IMU;
       const int c0 = 15 * (D.imu_idx[f].x - fo);
       if (lane < 15) {
@@ -442,7 +499,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     if (n > 0) {
       const double *J0 = D.prior_J + D.priorJ_off[w];
       const double *r = D.rec_prior + D.prior_off[w];
-      for (int i = warp; i < n; i += CT / 32) {
+      for (int i = warp; i < n; i += nthr / 32) {
         double jd = 0.0;
         for (int c = lane; c < n; c += 32) { const int cam = s_cmap[c]; if (cam >= 0) jd += J0[(size_t)i * n + c] * dl[cam]; }
 #pragma unroll
@@ -562,11 +619,12 @@ __global__ void k_copy_acc(Dev D, int slot, double *out, int zero) {
 
 static size_t chol_smem_bytes(int d) {
   const size_t K = (d + NB - 1) / NB;
-  return (K * (K + 1) / 2 * BS + 2 * K * NB) * sizeof(double);
+  (void)K;
+  return std::max((size_t)chol_layout(d).total * sizeof(double), (size_t)MAX_PRIOR_COLS * sizeof(int));
 }
 int chol_packed_limit(size_t max_smem) {
   int d = NB;
-  while (chol_smem_bytes(d + NB) <= max_smem) d += NB;
+  while (d < 256 && chol_smem_bytes(d + 1) <= max_smem) d++;   // 256: the load phase keeps 8 x 32 entries of a row in flight
   return d;
 }
 
@@ -575,7 +633,18 @@ int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st) { k_solve_
 int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool mc_identity, cudaStream_t st) {
   const int dd = max_d <= packed_limit ? max_d : packed_limit;
   const size_t smem = chol_smem_bytes(dd);
-  k_chol<<<D.B, CT, smem, st>>>(D, P, packed_limit, mc_identity ? 1 : 0);
+  // two windows per SM when two factors fit its shared memory (d <= 165): 256 threads each, else one window with 512
+  static int sm_smem = 0, static_smem = 0;
+  if (!sm_smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, k_chol) == cudaSuccess) static_smem = (int)attr.sharedSizeBytes;
+  }
+  const bool two = 2 * (smem + static_smem + 1024) <= (size_t)sm_smem && max_d <= packed_limit;
+  static const int t2 = std::getenv("UVS_CHOL_T2") ? std::atoi(std::getenv("UVS_CHOL_T2")) : CT;   // tuning knob (64 registers per thread: two 512-thread CTAs fit)
+  k_chol<<<D.B, two ? t2 : CT, smem, st>>>(D, P, packed_limit, mc_identity ? 1 : 0);
   return 1;
 }
 // largest dynamic shared-memory size k_chol can be launched with (opt-in limit minus its static arrays);
@@ -586,6 +655,7 @@ size_t chol_max_dynamic_smem(size_t optin_bytes) {
   if (optin_bytes <= attr.sharedSizeBytes + 512) return 0;
   const size_t dyn = optin_bytes - attr.sharedSizeBytes - 512;
   if (cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) return 0;
+  cudaFuncSetAttribute(k_chol, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   return dyn;
 }
 

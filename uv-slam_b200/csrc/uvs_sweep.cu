@@ -24,6 +24,11 @@ namespace uvs {
 
 constexpr int NT = 128;  // threads per CTA of the per-factor kernels
 
+// FP64 tensor-core MMA  D(8x8) += A(8x4) B(4x8)  (mma.sync m8n8k4: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}])
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
 // does window state `st` want this factor evaluated?
 //   mode 0: API evaluation (everything);  mode 1: solver
 template <bool kJac>
@@ -212,78 +217,187 @@ __global__ void __launch_bounds__(NT, 4) k_vp(Dev D, Params P, int mode, int can
 }
 
 // ------------------------------------------------------------------------------------------------
-// IMU: 32 factors per CTA.  Phase 1: one thread per factor computes the frame geometry (unweighted residual and
-// the twelve 3x3 blocks of the unweighted Jacobian) and the weighted residual.  Phase 2 (Jacobian mode): the four
-// warps take eight factors each, expand the blocks to the dense 15x30 matrix in shared memory and spread the
-// sqrt_info (15x15 upper-triangular) left-multiply over the lanes, consecutive lanes writing consecutive doubles.
-// Record = [r(15) | sqrt_info * J (15x30 row-major)].
-constexpr int IMU_PER_CTA = 8;
+// Solver path: line factor and the VP factor of the same (frame, line) observation in ONE pass - both are functions of
+// (n_c, d_c) and their ten partials, which cost ~10x more than either residual's own arithmetic.  A thread owns a line
+// observation; line_idx4[f].w names the paired VP observation (k_prep_vp) or -1.  The VP records of a tile are staged
+// in shared memory and written back record by record (the VP observations follow the order of the line observations,
+// so neighbouring records are adjacent in memory).
+template <bool kJac>
+struct LineVpSink {
+  LineSink<kJac, false> ln;
+  VpSink<kJac, false> vp;
+  bool has_vp;
+  __device__ __forceinline__ void base(d3 n, d3 d) { ln.base(n, d); if (has_vp) vp.base(n, d); }
+  __device__ __forceinline__ void partial(int k, d3 dn, d3 du) { ln.partial(k, dn, du); if (has_vp) vp.partial(k, dn, du); }
+};
 
 template <bool kJac>
-__global__ void __launch_bounds__(NT, 4) k_imu(Dev D, Params P, int mode, int cand, double *__restrict__ out,
-                                            double *__restrict__ res_out, double *cost, int cost_stride) {
-  __shared__ double comp_all[kJac ? IMU_PER_CTA : 1][kJac ? IMU_COMP : 1];
-  __shared__ double res_all[IMU_PER_CTA][15];
-  __shared__ double Jraw_all[kJac ? NT / 32 : 1][kJac ? 450 : 1];
-  __shared__ unsigned char ok_all[IMU_PER_CTA];
+__global__ void __launch_bounds__(NT, 3) k_line_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out_line,
+                                                double *__restrict__ out_vp, double *cost, int cost_stride) {
+  extern __shared__ double smem[];
+  double *tile = smem;                                        // [NT][REC_LINE + 1]
+  double *vtile = smem + NT * (REC_LINE + 1);                 // [NT][REC_VP + 1]
+  int *vslot = reinterpret_cast<int *>(vtile + NT * (REC_VP + 1));   // [NT] VP observation of the slot or -1
+  unsigned char *ok = reinterpret_cast<unsigned char *>(vslot + NT);
+  const int first = blockIdx.x * NT;
+  const int f = first + threadIdx.x;
+  bool valid = f < D.nLobs;
+  int4 ix = make_int4(0, 0, 0, -1);
+  if (valid) {
+    ix = D.line_idx4[f];
+    valid = wants<kJac>(D.ctl[ix.z].state, mode) && (D.nranks <= 1 || mode == 0 || (ix.y % D.nranks) == D.rank);
+  }
+  double half_rho = 0.0;
+  int vi = -1;
+  if (valid) {
+    const int buf = D.cur[ix.z] ^ cand;
+    const double *sp = D.line_sp + 2 * (size_t)f, *ep = D.line_ep + 2 * (size_t)f;
+    LineVpSink<kJac> sink;
+    sink.ln.spx = __ldg(sp); sink.ln.spy = __ldg(sp + 1); sink.ln.epx = __ldg(ep); sink.ln.epy = __ldg(ep + 1);
+    sink.ln.lf = P.line_factor; sink.ln.loss_a = P.cauchy_line; sink.ln.correct = true; sink.ln.PW = 6;
+    vi = ix.w;
+    sink.has_vp = vi >= 0;
+    sink.vp.half_rho = 0.0;
+    if (vi >= 0) {
+      const double *vp = D.vp_dir + 3 * (size_t)vi;
+      sink.vp.vp = mk3(__ldg(vp), __ldg(vp + 1), __ldg(vp + 2));
+      sink.vp.vf = P.vp_factor; sink.vp.loss_a = P.cauchy_vp; sink.vp.correct = true;
+    }
+    double rloc[3];
+    if (kJac) {
+      double *t = tile + threadIdx.x * (REC_LINE + 1), *v = vtile + threadIdx.x * (REC_VP + 1);
+      sink.ln.out_r = t; sink.ln.out_jp = t + 2; sink.ln.out_jl = t + 14;
+      sink.vp.out_r = v; sink.vp.out_jp = v + 1; sink.vp.out_jl = v + 7;
+    } else {
+      sink.ln.out_r = rloc; sink.ln.out_jp = nullptr; sink.ln.out_jl = nullptr;
+      sink.vp.out_r = rloc + 2; sink.vp.out_jp = nullptr; sink.vp.out_jl = nullptr;
+    }
+    line_to_camera<kJac, true, false>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
+                                      D.tic + 3 * (size_t)ix.z, sink);
+    half_rho = sink.ln.half_rho + sink.vp.half_rho;
+  }
+  if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
+  if (kJac) {
+    ok[threadIdx.x] = valid;
+    vslot[threadIdx.x] = valid ? vi : -1;
+    __syncthreads();
+    flush_tile<REC_LINE>(tile, ok, out_line, first, min(NT, D.nLobs - first));
+    for (int e = threadIdx.x; e < NT * REC_VP; e += NT) {
+      const int slot = e / REC_VP, c = e - slot * REC_VP;
+      const int v = vslot[slot];
+      if (v >= 0) out_vp[(size_t)v * REC_VP + c] = vtile[slot * (REC_VP + 1) + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// IMU, two kernels.
+//   k_imu_geom    one THREAD per factor: frame geometry (unweighted residual, the twelve 3x3 blocks the unweighted
+//                 Jacobian is made of -> D.imu_comp, struct-of-arrays so the stores coalesce), weighted residual, cost.
+//                 Every lane of a warp carries a factor (the dependent chain of quaternion algebra is ~1000
+//                 instructions long; it is latency, not work).
+//   k_imu_weight  one WARP per factor: [sqrt_info (15x15 upper) x J (15x30)] as a 16x16 by 16x32 product on the FP64
+//                 tensor cores (mma.sync m8n8k4, 24 DMMAs - the all-zero lower-left tiles are skipped); J is expanded
+//                 into shared memory with row stride 40 (= 8 mod 16: conflict-free B fragments), the product goes
+//                 back through shared memory so that consecutive lanes write consecutive doubles of the record.
+// Record = [r(15) | sqrt_info * J (15x30 row-major)].
+constexpr int GT_IMU = 64;      // threads (= factors) per CTA of k_imu_geom
+constexpr int IMU_WPC = 4;      // warps (= factors) per CTA of k_imu_weight
+constexpr int JS = 40;          // row stride of the staged unweighted Jacobian
+
+template <bool kJac>
+__global__ void __launch_bounds__(GT_IMU) k_imu_geom(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+                                                    double *__restrict__ res_out, double *cost, int cost_stride) {
+  const int f = blockIdx.x * GT_IMU + threadIdx.x;
+  bool valid = f < D.nImu;
+  int2 ix = make_int2(0, 0);
+  if (valid) {
+    ix = D.imu_idx[f];
+    valid = wants<kJac>(D.ctl[ix.y].state, mode) && !(D.nranks > 1 && mode != 0 && D.rank != 0);
+  }
+  double half = 0.0;
+  if (valid) {
+    const int buf = D.cur[ix.y] ^ cand;
+    ImuIn in;
+    in.pose_i = D.pose[buf] + 7 * (size_t)ix.x; in.pose_j = in.pose_i + 7;
+    in.sb_i = D.sb[buf] + 9 * (size_t)ix.x; in.sb_j = in.sb_i + 9;
+    in.dp = D.imu_dp + 3 * (size_t)f; in.dq = D.imu_dq + 4 * (size_t)f; in.dv = D.imu_dv + 3 * (size_t)f;
+    in.lin_ba = D.imu_lin_ba + 3 * (size_t)f; in.lin_bg = D.imu_lin_bg + 3 * (size_t)f;
+    in.sum_dt = __ldg(D.imu_sum_dt + f);
+    in.jac = D.imu_jac + 225 * (size_t)f;
+    in.sqrt_info = D.imu_sqrt_info + 225 * (size_t)f;
+    double raw[15];
+    imu_geometry<kJac>(in, P.g, raw, D.imu_comp + f, D.nImu);
+    const double *SI = in.sqrt_info;
+    double *rdst = kJac ? out + (size_t)f * REC_IMU : (res_out ? res_out + 15 * (size_t)f : nullptr);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 15; i++) {
+      double r = 0.0;
+#pragma unroll
+      for (int k = 0; k < 15; k++) if (k >= i) r += __ldg(SI + i * 15 + k) * raw[k];
+      if (rdst) rdst[i] = r;
+      s += r * r;
+    }
+    half = 0.5 * s;
+  }
+  if (cost) add_window_scalar(cost, cost_stride, ix.y, half, valid);
+}
+
+__global__ void __launch_bounds__(32 * IMU_WPC) k_imu_weight(Dev D, int mode, double *__restrict__ out) {
+  __shared__ __align__(16) double Jraw_all[IMU_WPC][16 * JS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int first = blockIdx.x * IMU_PER_CTA;
-  if (warp == 0) {
-    const int f = first + threadIdx.x;
-    bool valid = lane < IMU_PER_CTA && f < D.nImu;
-    int2 ix = make_int2(0, 0);
-    if (valid) {
-      ix = D.imu_idx[f];
-      valid = wants<kJac>(D.ctl[ix.y].state, mode) && !(D.nranks > 1 && mode != 0 && D.rank != 0);
+  const int f = blockIdx.x * IMU_WPC + warp;
+  if (f >= D.nImu) return;
+  const int2 ix = D.imu_idx[f];
+  if (!wants<true>(D.ctl[ix.y].state, mode) || (D.nranks > 1 && mode != 0 && D.rank != 0)) return;   // uniform over the warp
+  double *Jraw = Jraw_all[warp];
+  const int fr = lane >> 2, fc = lane & 3;
+  // A fragments: sqrt_info[8 mt + fr][4 ks + fc] (upper triangular, row / column 15 = padding)
+  const double *SI = D.imu_sqrt_info + 225 * (size_t)f;
+  double a[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int row = 8 * mt + fr, col = 4 * ks + fc;
+      a[mt][ks] = (row < 15 && col < 15 && col >= row) ? __ldg(SI + row * 15 + col) : 0.0;
     }
-    double half = 0.0;
-    if (valid) {
-      const int buf = D.cur[ix.y] ^ cand;
-      ImuIn in;
-      in.pose_i = D.pose[buf] + 7 * (size_t)ix.x; in.pose_j = in.pose_i + 7;
-      in.sb_i = D.sb[buf] + 9 * (size_t)ix.x; in.sb_j = in.sb_i + 9;
-      in.dp = D.imu_dp + 3 * (size_t)f; in.dq = D.imu_dq + 4 * (size_t)f; in.dv = D.imu_dv + 3 * (size_t)f;
-      in.lin_ba = D.imu_lin_ba + 3 * (size_t)f; in.lin_bg = D.imu_lin_bg + 3 * (size_t)f;
-      in.sum_dt = __ldg(D.imu_sum_dt + f);
-      in.jac = D.imu_jac + 225 * (size_t)f;
-      in.sqrt_info = D.imu_sqrt_info + 225 * (size_t)f;
-      double raw[15];
-      imu_geometry<kJac>(in, P.g, raw, comp_all[kJac ? lane : 0]);
-      const double *SI = in.sqrt_info;
-      double s = 0.0;
+  for (int e = lane; e < 16 * JS; e += 32) Jraw[e] = 0.0;
+  __syncwarp();
+  const double *comp = D.imu_comp + f;
+  for (int e = lane; e < 18 * 9; e += 32) {
+    const int b = e / 9, k = e - 9 * b;
+    const ImuPut p = c_imu_puts[b];
+    Jraw[(p.r0 + k / 3) * JS + p.c0 + k % 3] = (double)p.sgn * __ldg(comp + (size_t)(9 * p.blk + k) * D.nImu);
+  }
+  __syncwarp();
+  double acc[2][4][2];
 #pragma unroll
-      for (int i = 0; i < 15; i++) {
-        double r = 0.0;
+  for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int k = 0; k < 15; k++) if (k >= i) r += __ldg(SI + i * 15 + k) * raw[k];
-        res_all[lane][i] = r;
-        s += r * r;
-        if (!kJac && res_out) res_out[15 * (size_t)f + i] = r;
+    for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const double b = Jraw[(4 * ks + fc) * JS + 8 * nt + fr];   // B[k][n] = J[k][n]
+      dmma884(acc[0][nt], a[0][ks], b);
+      if (ks >= 2) dmma884(acc[1][nt], a[1][ks], b);               // rows 8..14 of sqrt_info start at column 8
+    }
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int row = 8 * mt + fr, col = 8 * nt + 2 * fc + e;
+        if (row < 15 && col < 30) Jraw[row * 30 + col] = acc[mt][nt][e];
       }
-      half = 0.5 * s;
-    }
-    if (lane < IMU_PER_CTA) ok_all[lane] = valid;
-    if (cost) add_window_scalar(cost, cost_stride, ix.y, half, valid);
-  }
-  if (!kJac) return;
-  __syncthreads();
-  double *Jraw = Jraw_all[kJac ? warp : 0];
-  for (int k = 0; k < IMU_PER_CTA / (NT / 32); k++) {
-    const int slot = warp * (IMU_PER_CTA / (NT / 32)) + k;
-    if (!ok_all[slot]) continue;
-    const int f = first + slot;
-    imu_expand_warp(comp_all[kJac ? slot : 0], Jraw, lane);
-    double *rec = out + (size_t)f * REC_IMU;
-    if (lane < 15) rec[lane] = res_all[slot][lane];
-    const double *SI = D.imu_sqrt_info + 225 * (size_t)f;
-    for (int e = lane; e < 450; e += 32) {
-      const int i = e / 30, c = e - i * 30;
-      double acc = 0.0;
-      for (int kk = i; kk < 15; kk++) acc += __ldg(SI + i * 15 + kk) * Jraw[kk * 30 + c];
-      rec[15 + e] = acc;
-    }
-    __syncwarp();
-  }
+  __syncwarp();
+  double *rec = out + (size_t)f * REC_IMU + 15;
+  for (int e = lane; e < 450; e += 32) rec[e] = Jraw[e];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,13 +518,24 @@ int launch_vp(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int
   return 1;
 }
 
+int launch_line_vp(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out_line, double *out_vp, double *cost,
+                   int cost_stride, cudaStream_t st) {
+  if (D.nLobs == 0) return 0;
+  const int grid = cdiv(D.nLobs, NT);
+  const size_t smem = (size_t)NT * (REC_LINE + 1 + REC_VP + 1) * sizeof(double) + NT * sizeof(int) + NT;
+  if (jac) k_line_vp<true><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  else k_line_vp<false><<<grid, NT, 0, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  return 1;
+}
+
 int launch_imu(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out, double *res_out, double *cost,
                int cost_stride, cudaStream_t st) {
   if (D.nImu == 0) return 0;
-  const int grid = cdiv(D.nImu, IMU_PER_CTA);
-  if (jac) k_imu<true><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
-  else k_imu<false><<<grid, NT, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
-  return 1;
+  const int grid = cdiv(D.nImu, GT_IMU);
+  if (!jac) { k_imu_geom<false><<<grid, GT_IMU, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride); return 1; }
+  k_imu_geom<true><<<grid, GT_IMU, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+  k_imu_weight<<<cdiv(D.nImu, IMU_WPC), 32 * IMU_WPC, 0, st>>>(D, mode, out);
+  return 2;
 }
 
 int launch_prior(const Dev &D, int max_prior_n, bool jac_phase, int mode, int cand, double *res_out, double *cost,
