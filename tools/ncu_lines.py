@@ -16,16 +16,19 @@ import sys
 import tempfile
 
 
-def sass_lines(so_path, kernel):
+def sass_lines(so_path, kernel, n_inst=None):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so_path)], cwd=tmp, stdout=subprocess.DEVNULL, check=True)
     for cub in sorted(glob.glob(os.path.join(tmp, "*.cubin"))):
         txt = subprocess.run(["nvdisasm", "-g", cub], capture_output=True, text=True).stdout
-        out, cur, inside = [], None, False
+        out, cur, inside, cands = [], None, False, []
         for ln in txt.splitlines():
             m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
             if m:
-                inside = kernel in m.group(1) and not out
+                if out:
+                    cands.append(out)
+                    out = []
+                inside = kernel in m.group(1)
                 continue
             if not inside:
                 continue
@@ -36,7 +39,13 @@ def sass_lines(so_path, kernel):
             if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
                 out.append(cur)
         if out:
-            return out
+            cands.append(out)
+        # several template instantiations may match the name: take the one with the report's instruction count
+        for c in cands:
+            if n_inst is None or len(c) == n_inst:
+                return c
+        if cands:
+            return cands[0]
     return []
 
 
@@ -46,8 +55,10 @@ def main():
     so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "uv-slam_b200", "csrc", "libuvs_b200.so")
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
-    # the report may hold several launches of the kernel: use the first block
-    hdr_i = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
+    # the report may hold several launches / instantiations of the kernel: --nth N picks the N-th block (default 0)
+    nth = int(sys.argv[sys.argv.index("--nth") + 1]) if "--nth" in sys.argv else 0
+    hdr_i = [i for i, r in enumerate(rows) if "Source" in r and "Address" in r][nth]
+    print(" ".join(rows[hdr_i - 1][:2]) if hdr_i > 0 else "")
     hdr = rows[hdr_i]
     ws, si = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Source")
     ie = hdr.index("Instructions Executed")
@@ -56,7 +67,7 @@ def main():
         if len(r) != len(hdr) or r[0] == "Address":
             break
         inst.append((int(r[ws] or 0), r[si].strip(), int(r[ie] or 0)))
-    lines = sass_lines(so, kernel)
+    lines = sass_lines(so, re.sub(r'[^A-Za-z0-9_].*', '', kernel), len(inst))
     if len(lines) != len(inst):
         print("warning: %d SASS instructions in the report, %d in the cubin (stale build?)" % (len(inst), len(lines)))
     per, ops = {}, {}

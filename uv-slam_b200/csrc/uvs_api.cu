@@ -120,6 +120,11 @@ int uvs_create(int device, UvsHandle **out) {
   h->hscratch.pinned_host = true;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return UVS_ERR_CUDA; }
   cudaEventCreate(&h->ev_a); cudaEventCreate(&h->ev_b); cudaEventCreate(&h->ev_c); cudaEventCreate(&h->ev_d);
+  for (int k = 0; k < 3; k++) {
+    if (cudaStreamCreateWithFlags(&h->fork.aux[k], cudaStreamNonBlocking) != cudaSuccess) { delete h; return UVS_ERR_CUDA; }
+    cudaEventCreateWithFlags(&h->fork.join[k], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&h->fork.fork, cudaEventDisableTiming);
   const size_t chol_smem = chol_max_dynamic_smem(prop.sharedMemPerBlockOptin);
   if (chol_smem == 0) { cudaGetLastError(); cudaStreamDestroy(h->stream); delete h; return UVS_ERR_CUDA; }
   h->packed_limit = chol_packed_limit(chol_smem);
@@ -141,6 +146,8 @@ int uvs_destroy(UvsHandle *h) {
   if (h->d_active) cudaFree(h->d_active);
   if (h->h_active) cudaFreeHost(h->h_active);
   cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b); cudaEventDestroy(h->ev_c); cudaEventDestroy(h->ev_d);
+  for (int k = 0; k < 3; k++) { cudaStreamDestroy(h->fork.aux[k]); cudaEventDestroy(h->fork.join[k]); }
+  cudaEventDestroy(h->fork.fork);
   for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -200,6 +207,10 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   }
   h->B = B; h->max_d = max_d; h->max_prior_n = max_prior_n;
   h->max_frames = max_frames; h->any_ex = any_ex;
+  // batches: independent kernels of a stage side by side on the auxiliary streams; a single window is launch-latency
+  // bound and keeps the plain in-order sequence (UVS_SERIAL=1 forces it, for profiling)
+  static const bool force_serial = std::getenv("UVS_SERIAL") != nullptr;
+  h->concurrent = B >= 32 && !force_serial;
   // landmark path: thread-per-landmark elimination + per-window dense rank update when the pose-pose system
   // fits shared memory (the reference's window size); otherwise the general warp-per-landmark path
   h->use_build3 = !td && (max_frames + (any_ex ? 1 : 0)) <= 12 && max_frames >= 2;
@@ -602,11 +613,14 @@ static int launch_resid_sweep(UvsHandle *h, int mode, int cand, int slot) {
   const Dev &D = h->D;
   double *cost = D.acc + slot;
   cudaStream_t st = h->stream;
+  const Fork *fk = h->concurrent ? &h->fork : nullptr;
+  if (fk) fork_from(fk, st, 3);
   h->launches += launch_proj(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_line_vp(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_imu(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_line_vp(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, fk ? fk->aux[0] : st);
+  h->launches += launch_imu(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, fk ? fk->aux[1] : st);
   // residual-only: the prior residual of the CURRENT iterate (rec_prior) must survive a rejected step
-  h->launches += launch_prior(D, h->max_prior_n, false, mode, cand, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_prior(D, h->max_prior_n, false, mode, cand, nullptr, cost, ACC_STRIDE, fk ? fk->aux[2] : st);
+  if (fk) for (int k = 0; k < 3; k++) join_to(fk, st, k);
   return post_launch(h, "residual sweep");
 }
 
@@ -654,19 +668,31 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
     while (h->stage_ev.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->stage_ev.push_back(e); }
   }
   const bool check_exit = !h->opts.fixed_iterations;
+  const Fork *fk = h->concurrent ? &h->fork : nullptr;
   int rc = UVS_OK, iters_run = 0;
   double *cost0 = D.acc + ACC_COST0, *costc = D.acc + ACC_CAND_COST;
 #define STAGE(k) do { if (prof) CK(cudaEventRecord(h->stage_ev[(size_t)it * NE + (k)], st)); } while (0)
   for (int it = 0; it < h->opts.max_num_iterations; it++) {
     STAGE(0);
-    h->launches += launch_proj(D, P, true, false, 1, 0, D.rec_proj, nullptr, cost0, ACC_STRIDE, st); STAGE(1);
-    h->launches += launch_line_vp(D, P, true, 1, 0, D.rec_line, D.rec_vp, cost0, ACC_STRIDE, st); STAGE(2);
-    STAGE(3);   // the VP factors ride in the line kernel
-    h->launches += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, st); STAGE(4);
-    h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, st); STAGE(5);
+    if (fk && h->profiling < 2) {
+      // the four factor-type kernels side by side; the stage events then see the sweep as one interval
+      fork_from(fk, st, 3);
+      h->launches += launch_proj(D, P, true, false, 1, 0, D.rec_proj, nullptr, cost0, ACC_STRIDE, st);
+      h->launches += launch_line_vp(D, P, true, 1, 0, D.rec_line, D.rec_vp, cost0, ACC_STRIDE, fk->aux[0]);
+      h->launches += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, fk->aux[1]);
+      h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, fk->aux[2]);
+      for (int k = 0; k < 3; k++) join_to(fk, st, k);
+      STAGE(1); STAGE(2); STAGE(3); STAGE(4); STAGE(5);
+    } else {
+      h->launches += launch_proj(D, P, true, false, 1, 0, D.rec_proj, nullptr, cost0, ACC_STRIDE, st); STAGE(1);
+      h->launches += launch_line_vp(D, P, true, 1, 0, D.rec_line, D.rec_vp, cost0, ACC_STRIDE, st); STAGE(2);
+      STAGE(3);   // the VP factors ride in the line kernel
+      h->launches += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, st); STAGE(4);
+      h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, st); STAGE(5);
+    }
     rc = post_launch(h, "Jacobian sweep"); if (rc) return rc;
     if (h->use_build3) {
-      h->launches += launch_build3(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->any_ex, h->max_prior_n, st);
+      h->launches += launch_build3(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->any_ex, h->max_prior_n, st, fk);
     } else {
       h->launches += launch_build(D, P, h->max_prior_n, st);
     }
@@ -678,7 +704,7 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
     STAGE(6);
     h->launches += launch_chol(D, P, h->max_d, h->packed_limit, h->use_build3, st); STAGE(7);
     rc = post_launch(h, "chol"); if (rc) return rc;
-    if (h->use_build3) h->launches += launch_back3(D, h->dev.base + h->o_b3, h->b3, st);
+    if (h->use_build3) h->launches += launch_back3(D, h->dev.base + h->o_b3, h->b3, st, fk);
     else h->launches += launch_backsub(D, P, st);
     STAGE(8);
     rc = post_launch(h, "backsub"); if (rc) return rc;

@@ -565,8 +565,8 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
       acc0 += rec[baseA + p0] * rec[baseB + q0] + rec[baseA + 6 + p0] * rec[baseB + 6 + q0];
       if (lane < 4) acc1 += rec[baseA + 5] * rec[baseB + q1] + rec[baseA + 11] * rec[baseB + 6 + q1];
     }
-    Sg[(size_t)(ra + p0) * d + rb + q0] += acc0;
-    if (lane < 4) Sg[(size_t)(ra + 5) * d + rb + q1] += acc1;
+    atomicAdd(Sg + (size_t)(ra + p0) * d + rb + q0, acc0);
+    if (lane < 4) atomicAdd(Sg + (size_t)(ra + 5) * d + rb + q1, acc1);
   }
 }
 
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
 #pragma unroll
     for (int t = 0; t < 3; t++) {
       const int o = lane + 32 * t;
-      if (o < 36) { const int p = o / 6, q = o - 6 * p; Sg[(size_t)(ra + p) * d + rb + q] += acc[t]; }   // sole owner of the block
+      if (o < 36) { const int p = o / 6, q = o - 6 * p; atomicAdd(Sg + (size_t)(ra + p) * d + rb + q, acc[t]); }
       else if (o < 78) {
         const int e = o < 57 ? o - 36 : o - 57, r0 = o < 57 ? ra : rb;
         const int p = c_sym_p[e], q = c_sym_q[e];
@@ -801,8 +801,8 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
       }
       __syncthreads();
     }
-    // ---- write the Schur part of the window's system: plain stores (the system was cleared by k_step / k_solve_init
-    //      and nothing else has touched these entries yet - k_direct runs after this kernel)
+    // ---- add the Schur part to the window's system (cleared by k_step / k_solve_init): fire-and-forget reductions,
+    //      because the direct-term and IMU / prior kernels run side by side with this one on other streams
     auto grow = [&](int e) { const int a = e / 6; return (a < F ? 15 * a : 15 * F) + (e - 6 * a); };
 #pragma unroll
     for (int i = 0; i < SUP_SETS; i++) {
@@ -817,8 +817,8 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             const int col = 8 * (SUP * sb[i] + v) + 2 * (lane & 3) + e;
-            if (col < m) { if (row <= col) Sg[(size_t)grow(row) * d + grow(col)] = -acc[i][u][v][e]; }
-            else if (col == zr) D.gS[co + grow(row)] = -acc[i][u][v][e];
+            if (col < m) { if (row <= col) atomicAdd(Sg + (size_t)grow(row) * d + grow(col), -acc[i][u][v][e]); }
+            else if (col == zr) atomicAdd(D.gS + co + grow(row), -acc[i][u][v][e]);
           }
         }
     }
@@ -954,37 +954,46 @@ size_t build3_smem(int max_frames, bool any_ex, int max_prior_n) {
 }
 
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
-                  cudaStream_t st) {
+                  cudaStream_t st, const Fork *fk) {
   Build3Ctx c; make_ctx(base, lay, c);
   int n = 0;
+  // four independent strands: point elimination | line elimination | direct terms | IMU + prior; the rank update needs
+  // the first two.  With auxiliary streams (fk) they run side by side, otherwise one after the other on st.
+  cudaStream_t s_lines = fk ? fk->aux[0] : st, s_direct = fk ? fk->aux[1] : st, s_tail = fk ? fk->aux[2] : st;
+  if (fk) fork_from(fk, st, 3);
   if (D.nP) { k_core_points<<<cdiv3(D.nP, 128 / LPP), 128, 0, st>>>(D, P, c.S); n++; }
-  if (D.nL) { k_core_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, st>>>(D, P, c.S); n++; }
+  if (D.nL) { k_core_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, s_lines>>>(D, P, c.S); n++; }
+  if (any_ex) {
+    const int nb_max = max_frames + 1;
+    const long long units = (long long)D.B * (nb_max * SEGS + nb_max * (nb_max - 1) / 2);
+    k_direct<<<(unsigned)((units + 3) / 4), 128, 0, s_direct>>>(D, c.L, nb_max);
+  } else {
+    const long long units = (long long)D.B * (max_frames * SEGS_D + max_frames * (max_frames - 1) / 2);
+    k_direct_fused<<<(unsigned)((units + 3) / 4), 128, 0, s_direct>>>(D, c.L, max_frames);
+  }
+  n++;
+  if (D.nranks <= 1 || D.rank == 0) {   // factor-parallel mode: IMU factors and the prior belong to rank 0
+    const size_t tsm = std::max((size_t)IMU_G * REC_IMU * sizeof(double), (size_t)(max_prior_n + 2) * sizeof(int));
+    k_window_tail<<<dim3(D.B, 2), TT, tsm, s_tail>>>(D, max_prior_n);
+    n++;
+  }
+  if (fk) join_to(fk, st, 0);
   const size_t smem = build3_smem(max_frames, any_ex, max_prior_n);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
   k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
-  int ntail = 0;
-  if (D.nranks <= 1 || D.rank == 0) {   // factor-parallel mode: IMU factors and the prior belong to rank 0
-    const size_t tsm = std::max((size_t)IMU_G * REC_IMU * sizeof(double), (size_t)(max_prior_n + 2) * sizeof(int));
-    k_window_tail<<<dim3(D.B, 2), TT, tsm, st>>>(D, max_prior_n);
-    ntail = 1;
-  }
-  if (any_ex) {
-    const int nb_max = max_frames + 1;
-    const long long units = (long long)D.B * (nb_max * SEGS + nb_max * (nb_max - 1) / 2);
-    k_direct<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(D, c.L, nb_max);
-  } else {
-    const long long units = (long long)D.B * (max_frames * SEGS_D + max_frames * (max_frames - 1) / 2);
-    k_direct_fused<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(D, c.L, max_frames);
-  }
-  return n + 2 + ntail;
+  n++;
+  if (fk) { join_to(fk, st, 1); join_to(fk, st, 2); }
+  return n;
 }
 
-int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st) {
+int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st, const Fork *fk) {
   Build3Ctx c; make_ctx(base, lay, c);
   int n = 0;
+  if (fk) fork_from(fk, st, 1);
   if (D.nP) { k_back_points<<<cdiv3(D.nP, 128), 128, 0, st>>>(D, c.S); n++; }
-  if (D.nL) { k_back_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, st>>>(D, c.S); n++; }
+  if (D.nL) { k_back_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, fk ? fk->aux[0] : st>>>(D, c.S); n++; }
+  if (fk) join_to(fk, st, 0);
   return n;
 }
 

@@ -46,6 +46,8 @@ struct UvsHandle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+  uvs::Fork fork{};                           // auxiliary streams + fork / join events (uvs_kernels.h)
+  bool concurrent = false;                    // this batch runs independent kernels of a stage side by side
   std::string err;
   uvs::Arena dev, stage, scratch, hscratch;
   uvs::Dev D{};

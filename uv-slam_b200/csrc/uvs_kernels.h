@@ -37,12 +37,27 @@ struct Build3Layout {
   int mp;                                        // doubles per dense landmark column (6 blocks + z + pad)
   size_t o_Y, o_ph, o_lh, o_items, o_off;
 };
+// Auxiliary streams of a handle: independent kernels of one solver stage run side by side (most of them are latency-
+// bound, so they overlap almost perfectly); every stage forks from and joins the handle's main stream with events.
+struct Fork {
+  cudaStream_t aux[3];
+  cudaEvent_t fork, join[3];
+};
+inline void fork_from(const Fork *fk, cudaStream_t main, int n) {
+  cudaEventRecord(fk->fork, main);
+  for (int k = 0; k < n; k++) cudaStreamWaitEvent(fk->aux[k], fk->fork, 0);
+}
+inline void join_to(const Fork *fk, cudaStream_t main, int k) {
+  cudaEventRecord(fk->join[k], fk->aux[k]);
+  cudaStreamWaitEvent(main, fk->join[k], 0);
+}
+
 size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay);
 size_t build3_smem(int max_frames, bool any_ex, int max_prior_n);
 int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, bool any_ex, cudaStream_t st);
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
-                  cudaStream_t st);
-int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st);
+                  cudaStream_t st, const Fork *fk);
+int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st, const Fork *fk);
 int launch_build_cam(const Dev &D, int max_prior_n, cudaStream_t st);
 
 // uvs_solve.cu

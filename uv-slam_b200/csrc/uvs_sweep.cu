@@ -62,15 +62,30 @@ __device__ __forceinline__ double corrector(double a, double s, double &half_rho
   return sqrt(rho1);
 }
 
-// contiguous, coalesced write-back of a CTA's tile of records staged in shared memory
+// contiguous, coalesced write-back of a CTA's tile of records staged in shared memory.  Call after a __syncthreads()
+// that follows the writes of `tile` and `ok`; `all_ok` (uniform over the CTA) skips the per-record test.
 template <int REC>
 __device__ __forceinline__ void flush_tile(const double *tile, const unsigned char *ok, double *__restrict__ out,
-                                           int first, int count) {
+                                           int first, int count, bool all_ok) {
   double *dst = out + (size_t)first * REC;
   const int total = count * REC;
-  for (int e = threadIdx.x; e < total; e += NT) {
-    const int f = e / REC, c = e - f * REC;
-    if (ok[f]) dst[e] = tile[f * (REC + 1) + c];
+  constexpr int DF = NT / REC, DC = NT % REC;   // element e + NT lies DF records and DC columns further
+  int e = threadIdx.x;
+  int f = e / REC, c = e - f * REC;
+  if (all_ok) {
+    // element (f, c) sits at tile[f (REC + 1) + c] = tile[e + f]
+#pragma unroll 4
+    for (; e < total; e += NT) {
+      dst[e] = tile[e + f];
+      f += DF; c += DC;
+      if (c >= REC) { c -= REC; f++; }
+    }
+  } else {
+    for (; e < total; e += NT) {
+      if (ok[f]) dst[e] = tile[e + f];
+      f += DF; c += DC;
+      if (c >= REC) { c -= REC; f++; }
+    }
   }
 }
 
@@ -129,8 +144,8 @@ __global__ void __launch_bounds__(NT, 4) k_proj(Dev D, Params P, int mode, int c
   if (cost) add_window_scalar(cost, cost_stride, ix.w, half_rho, valid);
   if (kJac) {
     ok[threadIdx.x] = valid;
-    __syncthreads();
-    flush_tile<REC>(tile, ok, out, first, min(NT, D.nProj - first));
+    const bool all_ok = __syncthreads_and(valid || f >= D.nProj) != 0;
+    flush_tile<REC>(tile, ok, out, first, min(NT, D.nProj - first), all_ok);
   }
 }
 
@@ -170,8 +185,8 @@ __global__ void __launch_bounds__(NT, 3) k_line(Dev D, Params P, int mode, int c
   if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
   if (kJac) {
     ok[threadIdx.x] = valid;
-    __syncthreads();
-    flush_tile<REC>(tile, ok, out, first, min(NT, D.nLobs - first));
+    const bool all_ok = __syncthreads_and(valid || f >= D.nLobs) != 0;
+    flush_tile<REC>(tile, ok, out, first, min(NT, D.nLobs - first), all_ok);
   }
 }
 
@@ -211,8 +226,8 @@ __global__ void __launch_bounds__(NT, 4) k_vp(Dev D, Params P, int mode, int can
   if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
   if (kJac) {
     ok[threadIdx.x] = valid;
-    __syncthreads();
-    flush_tile<REC>(tile, ok, out, first, min(NT, D.nVobs - first));
+    const bool all_ok = __syncthreads_and(valid || f >= D.nVobs) != 0;
+    flush_tile<REC>(tile, ok, out, first, min(NT, D.nVobs - first), all_ok);
   }
 }
 
@@ -280,12 +295,19 @@ __global__ void __launch_bounds__(NT, 3) k_line_vp(Dev D, Params P, int mode, in
   if (kJac) {
     ok[threadIdx.x] = valid;
     vslot[threadIdx.x] = valid ? vi : -1;
-    __syncthreads();
-    flush_tile<REC_LINE>(tile, ok, out_line, first, min(NT, D.nLobs - first));
-    for (int e = threadIdx.x; e < NT * REC_VP; e += NT) {
-      const int slot = e / REC_VP, c = e - slot * REC_VP;
-      const int v = vslot[slot];
-      if (v >= 0) out_vp[(size_t)v * REC_VP + c] = vtile[slot * (REC_VP + 1) + c];
+    const bool all_ok = __syncthreads_and(valid || f >= D.nLobs) != 0;
+    flush_tile<REC_LINE>(tile, ok, out_line, first, min(NT, D.nLobs - first), all_ok);
+    {
+      constexpr int DF = NT / REC_VP, DC = NT % REC_VP;
+      int e = threadIdx.x;
+      int slot = e / REC_VP, c = e - slot * REC_VP;
+#pragma unroll 4
+      for (; e < NT * REC_VP; e += NT) {
+        const int v = vslot[slot];
+        if (v >= 0) out_vp[(size_t)v * REC_VP + c] = vtile[e + slot];
+        slot += DF; c += DC;
+        if (c >= REC_VP) { c -= REC_VP; slot++; }
+      }
     }
   }
 }
