@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--windows", type=int, default=1024, help="windows per GPU and step")
+    ap.add_argument("--windows", type=int, default=1184, help="windows per GPU and step (1184 = 4 x 148 SMs x 2 resident window CTAs)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

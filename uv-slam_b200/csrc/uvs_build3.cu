@@ -578,11 +578,22 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
 // take the line / VP factors.  The lists are read 32 items at a time (coalesced) and handed round by shuffles, so the
 // record loads of consecutive items are independent and stay in flight together.
 constexpr int SEGS_D = 4;
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// asynchronous global -> shared copies (LDGSTS): the records of a whole list chunk are in flight at once without
+// holding registers
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+constexpr int DSTR = 26;   // doubles staged per item: [r | Ji | Jj] of a projection record; 14 of a line record, 7 of a VP record
 
 __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int nb_max) {
+  __shared__ __align__(16) double stage[4][32 * DSTR];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  double *buf = stage[threadIdx.x >> 5];
   const int npair = nb_max * (nb_max - 1) / 2;
   const int U = npair + nb_max * SEGS_D;
   const long long unit = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -622,21 +633,26 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
     }
     double acc[3] = {0.0, 0.0, 0.0};
     for (int base = i0; base < i1; base += 32) {
-      int2 my = make_int2(0, -1);
+      int kind = -1;
       if (base + lane < i1) {
-        my = items[base + lane];
-        if (D.nranks > 1 && (D.proj_idx[my.x].z % D.nranks) != D.rank) my.y = -1;   // factor-parallel: another rank's landmark
-        if (my.y >= 0) {   // every lane pulls the record of its own item towards L2 -> 32 records in flight per warp
+        const int2 my = items[base + lane];
+        kind = my.y;
+        if (D.nranks > 1 && (D.proj_idx[my.x].z % D.nranks) != D.rank) kind = -1;   // factor-parallel: another rank's landmark
+        if (kind >= 0) {   // every lane copies [r | Ji | Jj] of its own item's record: up to 32 records in flight per warp
           const double *rec = D.rec_proj + (size_t)my.x * REC_PROJ;
-          prefetch_l2(rec); prefetch_l2(rec + 13); prefetch_l2(rec + 25);
+          double *dst = buf + lane * DSTR;
+#pragma unroll
+          for (int c = 0; c < 13; c++) cp_async16(dst + 2 * c, rec + 2 * c);
         }
       }
+      cp_async_wait_all();
+      __syncwarp();
       const int cnt = min(32, i1 - base);
 #pragma unroll 4
       for (int k = 0; k < cnt; k++) {
-        const int fidx = __shfl_sync(full, my.x, k), kd = __shfl_sync(full, my.y, k);
+        const int kd = __shfl_sync(full, kind, k);
         if (kd < 0) continue;
-        const double *rec = D.rec_proj + (size_t)fidx * REC_PROJ;
+        const double *rec = buf + k * DSTR;
         const bool swap = kd == 3;
 #pragma unroll
         for (int t = 0; t < 3; t++) {
@@ -644,6 +660,7 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
           acc[t] += rec[xo] * rec[yo] + rec[xo + 6] * rec[yo + yd[t]];
         }
       }
+      __syncwarp();
     }
     const int ra = 15 * a, rb = 15 * b;
 #pragma unroll
@@ -674,28 +691,39 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
     const int p = lane < 21 ? c_sym_p[lane] : min(lane - 21, 5), q = lane < 21 ? c_sym_q[lane] : 0;
     double acc = 0.0;
     for (int base = i0; base < i1; base += 32) {
-      const double *myrec = nullptr;
-      int mybase = -1;   // offset of the pose block inside the record; -1 = skip
+      int mybase = -1;   // offset of the pose block inside the record (2: line, two rows; 1: VP, one row); -1 = skip
       if (base + lane < i1) {
         const int2 it = items[base + lane];
         const bool line = it.y == 7;
         bool mine = true;
         if (D.nranks > 1) mine = ((line ? D.line_idx4[it.x].y : D.vp_idx4[it.x].y) % D.nranks) == D.rank;
         if (mine) {
-          myrec = line ? D.rec_line + (size_t)it.x * REC_LINE : D.rec_vp + (size_t)it.x * REC_VP; mybase = line ? 2 : 1;
-          prefetch_l2(myrec); prefetch_l2(myrec + (line ? 13 : 6));
+          double *dst = buf + lane * DSTR;
+          if (line) {
+            const double *rec = D.rec_line + (size_t)it.x * REC_LINE;   // [r(2) | Jpose 2x6]: 14 doubles, 16-byte aligned
+#pragma unroll
+            for (int c = 0; c < 7; c++) cp_async16(dst + 2 * c, rec + 2 * c);
+          } else {
+            const double *rec = D.rec_vp + (size_t)it.x * REC_VP;       // [r | Jpose 6]: 7 doubles
+#pragma unroll
+            for (int c = 0; c < 7; c++) cp_async8(dst + c, rec + c);
+          }
+          mybase = line ? 2 : 1;
         }
       }
+      cp_async_wait_all();
+      __syncwarp();
       const int cnt = min(32, i1 - base);
 #pragma unroll 4
       for (int k = 0; k < cnt; k++) {
         const int bA = __shfl_sync(full, mybase, k);
-        const double *rec = reinterpret_cast<const double *>(__shfl_sync(full, reinterpret_cast<unsigned long long>(myrec), k));
         if (bA < 0) continue;
+        const double *rec = buf + k * DSTR;
         double t = rec[bA + p] * (isg ? rec[0] : rec[bA + q]);
         if (bA == 2) t += rec[bA + 6 + p] * (isg ? rec[1] : rec[bA + 6 + q]);   // line factors have two residual rows
         acc += t;
       }
+      __syncwarp();
     }
     const int ra = 15 * a;
     if (lane < 21) {

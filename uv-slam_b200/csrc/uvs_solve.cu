@@ -26,10 +26,16 @@ constexpr int CT = UVS_CHOL_THREADS;
 
 __device__ __forceinline__ double clampd2(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
+// clears the window's reduced system: only the upper triangle of S is ever written or read (k_window_system, k_direct*,
+// k_window_tail add into it, k_chol reads it), so only that half is cleared - a warp per row, from the diagonal on
 __device__ __forceinline__ void zero_window_system(const Dev &D, int w) {
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   double *S = D.Smat + D.S_off[w];
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) S[e] = 0.0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < d; r += nw) {
+    double *row = S + (size_t)r * d;
+    for (int c = (r & ~3) + lane; c < d; c += 32) row[c] = 0.0;   // from the 32-byte sector that holds the diagonal
+  }
   for (int e = threadIdx.x; e < d; e += blockDim.x) { D.gS[co + e] = 0.0; D.gfull[co + e] = 0.0; D.colsq_cam[co + e] = 0.0; }
 }
 
@@ -327,46 +333,63 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
       if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
       return;
     }
-    // back-substitution L^T y = z, block row by block row, one warp: y_k = L_kk^-T z_k as eight independent dot
-    // products (the diagonal blocks hold their inverses by now), then z[0..8k) -= L_k^T y_k eight columns at a time as
-    // (y^T in row 0 of A) x (block of L_k as B) on the tensor cores
+    // back-substitution L^T y = z by one warp, block by block from the bottom, "left-looking": for block k first
+    // s = sum_{I>k} L_Ik^T y_I on the tensor cores ((y_I^T in row 0 of A) x (block of L as B), four independent
+    // accumulator chains, nothing written back in between), then y_k = L_kk^-T (z_k - s) as eight independent dot
+    // products (the diagonal blocks hold their inverses by now).
     if (warp == 0) {
       for (int k = K - 1; k >= 0; k--) {
         const int vr = rows_of(k);
+        double c[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++) c[u][0] = c[u][1] = 0.0;
+        // one warp issues this whole chain: keep the instruction count per block low (pointer increments instead of
+        // address arithmetic; the ragged last block row is peeled off)
+        const double ymask = fr == 0 ? 1.0 : 0.0;
+        {
+          const int I = K - 1;   // last block row: rI rows
+          if (I > k) {
+            const int rI = rows_of(I);
+            const double ya = fc < rI ? ymask * bz[I * NB + fc] : 0.0;
+            const double yb = 4 + fc < rI ? ymask * bz[I * NB + 4 + fc] : 0.0;
+            const double *f = frag(I, 2 * k + (fr >> 2)) + (fr & 3);
+            dmma884(c[3], ya, f[4 * min(fc, rI - 1)]);
+            dmma884(c[3], yb, f[4 * min(4 + fc, rI - 1)]);
+          }
+        }
+        {
+          // full block rows I = k+1 .. K-2: fragment (I, 2k + (fr >> 2)) sits at 32 I (I-1) + 32 (2k + (fr >> 2)), i.e. 64 I further per row
+          int I = k + 1;
+          const double *f = A + 32 * I * (I - 1) + 32 * (2 * k + (fr >> 2)) + (fr & 3) + 4 * fc;
+          const double *yv = bz + I * NB + fc;
+          for (; I + 4 <= K - 1; I += 4) {
+            const double *f1 = f + 64 * I, *f2 = f1 + 64 * (I + 1), *f3 = f2 + 64 * (I + 2);
+            dmma884(c[0], ymask * yv[0], f[0]);   dmma884(c[0], ymask * yv[4], f[16]);
+            dmma884(c[1], ymask * yv[8], f1[0]);  dmma884(c[1], ymask * yv[12], f1[16]);
+            dmma884(c[2], ymask * yv[16], f2[0]); dmma884(c[2], ymask * yv[20], f2[16]);
+            dmma884(c[3], ymask * yv[24], f3[0]); dmma884(c[3], ymask * yv[28], f3[16]);
+            f = f3 + 64 * (I + 3); yv += 32;
+          }
+          for (; I < K - 1; I++) {
+            dmma884(c[0], ymask * yv[0], f[0]); dmma884(c[0], ymask * yv[4], f[16]);
+            f += 64 * I; yv += NB;
+          }
+        }
+        if (lane < 4) {   // row 0 of the accumulators: columns 2 lane, 2 lane + 1 of block k
+          double2 *zc = reinterpret_cast<double2 *>(bz + k * NB + 2 * lane);
+          double2 zz = *zc;
+          zz.x -= (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+          zz.y -= (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+          *zc = zz;
+        }
+        __syncwarp();
         const double *Dk = Dg + 36 * k;
         const int p = lane & 7;
         double y = 0.0;
 #pragma unroll
         for (int q = 0; q < NB; q++) if (q >= p && q < vr) y += Dk[q * (q + 1) / 2 + p] * bz[k * NB + q];
-        // A fragments: row 0 = y[0..3] / y[4..7] (zero for rows that do not exist)
-        double ya = __shfl_sync(0xffffffffu, y, fc), yb = __shfl_sync(0xffffffffu, y, 4 + fc);
-        if (fr != 0 || fc >= vr) ya = 0.0;
-        if (fr != 0 || 4 + fc >= vr) yb = 0.0;
-        const int pa = min(fc, vr - 1), pb = min(4 + fc, vr - 1);   // B[p][n] = L[8k + p][8g + n]: lane holds p = fc (+4), n = fr
         __syncwarp();
         if (lane < NB) bz[k * NB + lane] = y;
-        for (int g0 = 0; g0 < k; g0 += 4) {   // four independent column groups in flight
-          double c[4][2];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            c[u][0] = c[u][1] = 0.0;
-            if (g0 + u < k) {
-              const double *f = frag(k, 2 * (g0 + u) + (fr >> 2)) + (fr & 3);
-              dmma884(c[u], ya, f[4 * pa]); dmma884(c[u], yb, f[4 * pb]);
-            }
-          }
-          if (lane < 4) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              if (g0 + u < k) {
-                double2 *zc = reinterpret_cast<double2 *>(bz + (g0 + u) * NB + 2 * lane);
-                double2 zz = *zc;
-                zz.x -= c[u][0]; zz.y -= c[u][1];
-                *zc = zz;
-              }
-            }
-          }
-        }
         __syncwarp();
       }
     }
