@@ -289,6 +289,27 @@ int uvs_preintegrate(UvsHandle *h, int32_t n_intervals, const int32_t *sample_of
                      const double *noise, double *delta_p, double *delta_q, double *delta_v, double *sum_dt, double *jacobian,
                      double *covariance);
 
+/* Triangulation of the features that have no estimate yet - the step that seeds para_Feature / para_Ortho_plucker
+ * before optimization().  Rs[n_frames][9] (row-major) and Ps[n_frames][3] are Estimator::Rs / Ps,
+ * ric[9] (row-major) / tic[3] are ric[0] / tic[0].
+ *
+ * uvs_triangulate_points = FeatureManager::triangulate (feature_manager.cpp:427-481): track t starts at frame
+ * start_frame[t] and owns the observations [obs_off[t], obs_off[t+1]) of consecutive frames, obs_pts[.][3] =
+ * FeaturePerFrame::point; depth_out[t] = V(2)/V(3) of the smallest right singular vector of the 2n x 4 DLT system, or
+ * init_depth (INIT_DEPTH, parameters.h) when that is < 0.1.  The caller applies the reference's eligibility tests
+ * (used_num >= 2, start_frame < WINDOW_SIZE - 2, estimated_depth <= 0) when it builds the list.
+ *
+ * uvs_triangulate_lines = FeatureManager::triangulateLine (feature_manager.cpp:504-589, calcPluckerLine :827-902):
+ * line t is seen first in frame frame_first[t] with end points sp_first / ep_first and last in frame_last[t] with
+ * sp_last / ep_last ([n_lines][3], z = 1); ortho_out[t][4] = (eulerAngles(0,1,2) of [n_w d_w n_w x d_w] normalised,
+ * atan2(|d_w|, |n_w|)) - the orthonormal_vec of the feature. */
+int uvs_triangulate_points(UvsHandle *h, int32_t n_frames, const double *Rs, const double *Ps, const double *ric, const double *tic,
+                           int32_t n_tracks, const int32_t *start_frame, const int32_t *obs_off, const double *obs_pts,
+                           double init_depth, double *depth_out);
+int uvs_triangulate_lines(UvsHandle *h, int32_t n_frames, const double *Rs, const double *Ps, const double *ric, const double *tic,
+                          int32_t n_lines, const int32_t *frame_first, const int32_t *frame_last, const double *sp_first,
+                          const double *ep_first, const double *sp_last, const double *ep_last, double *ortho_out);
+
 /* Factor-parallel multi-GPU mode: this rank owns the landmarks with (index % nranks == rank);
  * IMU factors and the prior belong to rank 0.  `reduce` is called once per LM iteration with the
  * device buffer holding the rank's partial reduced camera system (count doubles) and must sum it

@@ -22,6 +22,7 @@ EXPORTS = (
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
     "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate", "uvs_batch_solve_pipelined",
+    "uvs_triangulate_points", "uvs_triangulate_lines",
 )
 
 N_STAGES = 10
@@ -78,6 +79,8 @@ def load_library():
     lib.uvs_comm_init.argtypes = [H, C.c_int32, C.c_int32, ALLREDUCE_FN, C.c_void_p]
     lib.uvs_reset_state.argtypes = [H]
     lib.uvs_preintegrate.argtypes = [H, C.c_int32, c_int32_p] + [c_double_p] * 14
+    lib.uvs_triangulate_points.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p, c_double_p, C.c_double, c_double_p]
+    lib.uvs_triangulate_lines.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p] + [c_double_p] * 5
     lib.uvs_set_profiling.argtypes = [H, C.c_int32]
     lib.uvs_last_stage_ms.argtypes = [H, C.POINTER(C.c_float * N_STAGES), C.POINTER(C.c_int32)]
     _lib = lib
@@ -257,6 +260,35 @@ class Solver:
         self._check(self.lib.uvs_preintegrate(self.h, n, off.ctypes.data_as(c_int32_p), p(dt), p(acc), p(gyr), p(acc0), p(gyr0), p(lin_ba),
                                               p(lin_bg), p(noise), p(out["delta_p"]), p(out["delta_q"]), p(out["delta_v"]), p(out["sum_dt"]),
                                               p(out["jacobian"]), p(out["covariance"])), "uvs_preintegrate")
+        return out
+
+    def triangulate_points(self, Rs, Ps, ric, tic, start_frame, obs_off, obs_pts, init_depth=5.0):
+        """FeatureManager::triangulate on the device: depth of every track (see include/uvs.h)."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        Rs, Ps, ric, tic, obs_pts = f64(Rs), f64(Ps), f64(ric), f64(tic), f64(obs_pts)
+        start_frame, obs_off = i32(start_frame), i32(obs_off)
+        n = len(start_frame)
+        out = np.zeros(n)
+        p = lambda a: a.ctypes.data_as(c_double_p)
+        self._check(self.lib.uvs_triangulate_points(self.h, len(Ps), p(Rs), p(Ps), p(ric), p(tic), n, start_frame.ctypes.data_as(c_int32_p),
+                                                    obs_off.ctypes.data_as(c_int32_p), p(obs_pts), float(init_depth), p(out)),
+                    "uvs_triangulate_points")
+        return out
+
+    def triangulate_lines(self, Rs, Ps, ric, tic, frame_first, frame_last, sp_first, ep_first, sp_last, ep_last):
+        """FeatureManager::triangulateLine on the device: orthonormal parameters [n][4] (see include/uvs.h)."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        Rs, Ps, ric, tic = f64(Rs), f64(Ps), f64(ric), f64(tic)
+        sp_first, ep_first, sp_last, ep_last = f64(sp_first), f64(ep_first), f64(sp_last), f64(ep_last)
+        frame_first, frame_last = i32(frame_first), i32(frame_last)
+        n = len(frame_first)
+        out = np.zeros((n, 4))
+        p = lambda a: a.ctypes.data_as(c_double_p)
+        self._check(self.lib.uvs_triangulate_lines(self.h, len(Ps), p(Rs), p(Ps), p(ric), p(tic), n, frame_first.ctypes.data_as(c_int32_p),
+                                                   frame_last.ctypes.data_as(c_int32_p), p(sp_first), p(ep_first), p(sp_last), p(ep_last),
+                                                   p(out)), "uvs_triangulate_lines")
         return out
 
     def comm_init(self, rank, nranks, reduce_fn):
