@@ -127,7 +127,7 @@ def run_cpu_sample(n_windows, threads, budget_s, k_lm=K_LM):
     orc.solve_batch([w.copy() for w in ws[:max(1, threads)]], o, threads)   # warm-up
     warm = time.perf_counter() - t0
     reps = max(1, int(budget_s / max(warm * n_windows / max(1, threads), 1e-3)))
-    reps = min(reps, 50)
+    reps = min(reps, 400)
     t0 = time.perf_counter()
     for _ in range(reps):
         orc.solve_batch([w.copy() for w in ws], o, threads)
