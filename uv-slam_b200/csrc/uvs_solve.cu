@@ -12,6 +12,7 @@
 // One CTA per window; windows of a batch advance in lock-step but accept / reject independently.
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 
 #include "uvs_device.cuh"
 #include "uvs_math.cuh"
@@ -105,12 +106,23 @@ __device__ __forceinline__ void unrank_lower(int t, int &I, int &J) {
   I = i; J = t - i * (i + 1) / 2;
 }
 
+// developer aid: -DUVS_CHOL_TIMING prints the cycle count of every phase of window 0 (one line per launch)
+#ifdef UVS_CHOL_TIMING
+#define CHOL_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) ts[i] = clock64(); } while (0)
+#else
+#define CHOL_TS(i) do { } while (0)
+#endif
+
 template <bool kPacked>
 __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, bool mc_identity) {
   __shared__ double red[CT / 32];   // CT = largest block size
   __shared__ int s_flag;
   __shared__ unsigned short s_pair[kPacked ? 528 : 1];   // (I, J) of the t-th block of a lower triangle, K <= 32
   const int nthr = blockDim.x;   // 256 when two windows fit one SM, else 512
+#ifdef UVS_CHOL_TIMING
+  long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_panel = 0, t_trail = 0, t_potrf = 0, t_bs_mma = 0, t_bs_rest = 0;
+#endif
+  CHOL_TS(0);
   int *s_cmap = reinterpret_cast<int *>(smem);   // aliases the factor: only used after the back-substitution
   double *vec_y = D.gS + D.cam_off[w];   // y (scaled step) parked in the consumed reduced-gradient buffer
   WinCtl &ctl = D.ctl[w];
@@ -154,6 +166,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
 
   double *vec;   // solution vector y (d doubles)
   const double radius = ctl.radius;
+  CHOL_TS(1);
   if (kPacked) {
     // ---- blocked path: the lower triangle in shared memory, 8x8 blocks, stored in FP64 tensor-core FRAGMENT order:
     //      block row I (rows 8I..8I+7), columns 0..8I-1, is a sequence of 8x4 fragments (32 consecutive doubles,
@@ -172,28 +185,44 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
     auto frag = [&](int I, int f) { return A + 32 * I * (I - 1) + f * 4 * rows_of(I); };   // fragment f of block row I
     {
-      // rows j of the upper triangle of Sg, coalesced over i; element (i,j), j <= i, of the lower matrix.
-      // All loads of a row are issued before they are used (up to MAXL per lane in flight).
-      constexpr int MAXL = 8;   // 8 x 32 = 256 >= dimension of the blocked path
+      // The upper triangle of Sg goes straight to its fragment slots with asynchronous 8-byte copies (LDGSTS): rows j by
+      // warp, columns i >= j by lane (coalesced), all ~27 copies of a thread in flight at once - one memory round trip
+      // for the whole matrix instead of one per row.  Scaling and the LM diagonal are applied in place afterwards.
+      auto slot = [&](int i, int j) -> double * {   // element (i, j), j <= i, of the lower matrix
+        const int I = i >> 3, r = i & 7;
+        return (j >> 3) == I ? Dg + 36 * I + r * (r + 1) / 2 + (j & 7) : frag(I, j >> 2) + 4 * r + (j & 3);
+      };
+      for (int j = warp; j < d; j += nthr / 32) {
+        const double *src = Sg + (size_t)j * d;
+        for (int i = j + lane; i < d; i += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(slot(i, j))), "l"(src + i) : "memory");
+      }
+#ifdef UVS_CHOL_TIMING
+      const long long tl0 = clock64();
+#endif
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+#ifdef UVS_CHOL_TIMING
+      const long long tl1 = clock64();
+      if (threadIdx.x == 0 && blockIdx.x == 0) printf("  load: issue %lld wait %lld", tl0 - ts[1], tl1 - tl0);
+#endif
       for (int j = warp; j < d; j += nthr / 32) {
         const double sj = scale[j];
-        double v[MAXL];
-#pragma unroll
-        for (int k = 0; k < MAXL; k++) {
-          const int i = j + lane + 32 * k;
-          v[k] = i < d ? Sg[(size_t)j * d + i] : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < MAXL; k++) {
-          const int i = j + lane + 32 * k;
-          if (i >= d) continue;
-          double x = scale[i] * sj * v[k];
-          if (i == j) { const double h = sj * sj * colsq[i]; x += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
-          const int I = i >> 3, r = i & 7;
-          if ((j >> 3) == I) Dg[36 * I + r * (r + 1) / 2 + (j & 7)] = x;
-          else frag(I, j >> 2)[4 * r + (j & 3)] = x;
+        for (int i = j + lane; i < d; i += 32) {
+          double *a = slot(i, j);
+          *a = scale[i] * sj * *a;
         }
       }
+      // LM diagonal, one thread per column (kept out of the row loop: a load and a division on one lane would stall
+      // the whole warp once per row); each diagonal slot was scaled by this very thread's warp-mates above -> barrier
+      __syncthreads();
+      for (int c = tid; c < d; c += nthr) {
+        const double sc = scale[c], h = sc * sc * colsq[c];
+        *slot(c, c) += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius;
+      }
+#ifdef UVS_CHOL_TIMING
+      if (threadIdx.x == 0 && blockIdx.x == 0) printf(" scale %lld\n", clock64() - tl1);
+#endif
     }
     for (int c = tid; c < K * NB; c += nthr) { bz[c] = c < d ? -scale[c] * gS[c] : 0.0; invd_all[c] = 1.0; }
     for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
@@ -251,9 +280,14 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
         if (h1) C[1] = c[1];
       }
     };
+    CHOL_TS(2);
     if (warp == 0) potrf_block(0);
     __syncthreads();
+    CHOL_TS(3);
     for (int k = 0; k < K && !s_flag; k++) {
+#ifdef UVS_CHOL_TIMING
+      const long long tk0 = clock64();
+#endif
       const double *invd = invd_all + k * NB;
       const int vr = rows_of(k);                         // rows of block k that exist
       // panel: L_Ik = A_Ik L_kk^-T for the rows below, z_k = L_kk^-1 b_k
@@ -283,14 +317,24 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
         r1[0] = make_double2(x[4], x[5]); r1[1] = make_double2(x[6], x[7]);
       }
       __syncthreads();
+#ifdef UVS_CHOL_TIMING
+      const long long tk1 = clock64();
+      t_panel += tk1 - tk0;
+#endif
       // trailing update A_IJ -= L_Ik L_Jk^T, one 8x8 block per warp and step (two DMMAs), b_I -= L_Ik z_k.
       // Look-ahead: warp 0 updates the next diagonal block first and factors it while the other warps do the rest.
       const int nt = K - 1 - k;
       if (warp == 0) {
         if (nt > 0) {
+#ifdef UVS_CHOL_TIMING
+          const long long tp0 = clock64();
+#endif
           block_update(k + 1, k + 1, k);
           __syncwarp();
           potrf_block(k + 1);
+#ifdef UVS_CHOL_TIMING
+          t_potrf += clock64() - tp0;
+#endif
         }
       } else {
         if (warp == 1) {
@@ -328,7 +372,11 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
         }
       }
       __syncthreads();
+#ifdef UVS_CHOL_TIMING
+      t_trail += clock64() - tk1;
+#endif
     }
+    CHOL_TS(4);
     if (s_flag) {
       if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
       return;
@@ -340,6 +388,9 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     if (warp == 0) {
       for (int k = K - 1; k >= 0; k--) {
         const int vr = rows_of(k);
+#ifdef UVS_CHOL_TIMING
+        const long long tb0 = clock64();
+#endif
         double c[4][2];
 #pragma unroll
         for (int u = 0; u < 4; u++) c[u][0] = c[u][1] = 0.0;
@@ -375,6 +426,10 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
             f += 64 * I; yv += NB;
           }
         }
+#ifdef UVS_CHOL_TIMING
+        const long long tb1 = clock64();
+        t_bs_mma += tb1 - tb0;
+#endif
         if (lane < 4) {   // row 0 of the accumulators: columns 2 lane, 2 lane + 1 of block k
           double2 *zc = reinterpret_cast<double2 *>(bz + k * NB + 2 * lane);
           double2 zz = *zc;
@@ -391,9 +446,13 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
         __syncwarp();
         if (lane < NB) bz[k * NB + lane] = y;
         __syncwarp();
+#ifdef UVS_CHOL_TIMING
+        t_bs_rest += clock64() - tb1;
+#endif
       }
     }
     __syncthreads();
+    CHOL_TS(5);
   } else {
     // ---- large windows: in place in global memory (mirror the upper triangle into the lower one),
     //      unblocked right-looking Cholesky
@@ -532,6 +591,13 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     }
   }
   mc = block_sum(mc, red);
+#ifdef UVS_CHOL_TIMING
+  if (kPacked && threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t6 = clock64();
+    printf("chol d=%d cycles: prologue %lld load %lld potrf0 %lld loop %lld (panel %lld trailing %lld of which diag update + potrf %lld) backsub %lld (mma %lld rest %lld) tail %lld total %lld\n", d,
+           ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], t_panel, t_trail, t_potrf, ts[5] - ts[4], t_bs_mma, t_bs_rest, t6 - ts[5], t6 - ts[0]);
+  }
+#endif
   if (tid == 0) {
     if (lead) { atomicAdd(acc + ACC_MODEL, -mc); atomicAdd(acc + ACC_STEP2, step2); atomicAdd(acc + ACC_XNORM2, x2); }
     ctl.state |= WS_STEP_OK;
