@@ -599,20 +599,32 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
   const long long unit = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int w = (int)(unit / U), local = (int)(unit - (long long)w * U);
   if (w >= D.B) return;
-  if (!(D.ctl[w].state & WS_ACTIVE)) return;
-  const int fo = D.frame_off[w], nb = D.frame_off[w + 1] - fo;
-  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
-  double *Sg = D.Smat + D.S_off[w];
-  const int2 *items = L.items + direct_base(D, w);
-  const int *off = L.off + (size_t)w * KMAX;
+  // which unit (pure arithmetic), then ALL the metadata loads at once, then the tests: the warp's life is a chain of
+  // dependent memory round trips (metadata -> list -> records), every one that can be merged is ~1 us saved
+  int a, b, seg = 0;
   if (local < npair) {
-    int b = (int)((sqrtf(8.0f * (float)local + 1.0f) + 1.0f) * 0.5f);   // local = b (b - 1) / 2 + a, a < b
+    b = (int)((sqrtf(8.0f * (float)local + 1.0f) + 1.0f) * 0.5f);   // local = b (b - 1) / 2 + a, a < b
     while (b * (b - 1) / 2 > local) b--;
     while ((b + 1) * b / 2 <= local) b++;
-    const int a = local - b * (b - 1) / 2;
+    a = local - b * (b - 1) / 2;
+  } else {
+    a = b = (local - npair) / SEGS_D;
+    seg = (local - npair) - a * SEGS_D;
+  }
+  const int key = pair_key(a, b);          // < KMAX for every unit of the grid
+  const int *off = L.off + (size_t)w * KMAX;
+  const int wstate = D.ctl[w].state;
+  const int fo = D.frame_off[w], nb = D.frame_off[w + 1] - fo;
+  const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+  const long long s_off = D.S_off[w];
+  const long long ibase = direct_base(D, w);
+  const int o0 = off[key], o1 = off[key + 1];
+  if (!(wstate & WS_ACTIVE)) return;
+  double *Sg = D.Smat + s_off;
+  const int2 *items = L.items + ibase;
+  if (local < npair) {
     if (b >= nb) return;
-    const int key = pair_key(a, b);
-    const int i0 = off[key], i1 = off[key + 1];
+    const int i0 = o0, i1 = o1;
     if (i0 >= i1) return;
     // output o = lane + 32 t:  [0,36) block (a,b)   [36,57) (a,a)   [57,78) (b,b)   [78,84) g_a   [84,90) g_b
     // operand offsets inside the record for a kind-2 item (a = anchor frame i: A = Ji at 2, B = Jj at 14) and a
@@ -680,10 +692,8 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
     }
   } else {
     // line / VP factors of diagonal block a, one segment of the list
-    const int a = (local - npair) / SEGS_D, seg = (local - npair) - a * SEGS_D;
     if (a >= nb) return;
-    const int key = pair_key(a, a);
-    int i0 = off[key], i1 = off[key + 1];
+    int i0 = o0, i1 = o1;
     const int per = (i1 - i0 + SEGS_D - 1) / SEGS_D;
     i0 += seg * per; i1 = min(i1, i0 + per);
     if (i0 >= i1) return;

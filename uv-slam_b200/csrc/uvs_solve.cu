@@ -415,10 +415,11 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
           const double *yv = bz + I * NB + fc;
           for (; I + 4 <= K - 1; I += 4) {
             const double *f1 = f + 64 * I, *f2 = f1 + 64 * (I + 1), *f3 = f2 + 64 * (I + 2);
-            dmma884(c[0], ymask * yv[0], f[0]);   dmma884(c[0], ymask * yv[4], f[16]);
-            dmma884(c[1], ymask * yv[8], f1[0]);  dmma884(c[1], ymask * yv[12], f1[16]);
-            dmma884(c[2], ymask * yv[16], f2[0]); dmma884(c[2], ymask * yv[20], f2[16]);
-            dmma884(c[3], ymask * yv[24], f3[0]); dmma884(c[3], ymask * yv[28], f3[16]);
+            // issue order: the two DMMAs of an accumulator are four apart, so none waits for its predecessor
+            dmma884(c[0], ymask * yv[0], f[0]);    dmma884(c[1], ymask * yv[8], f1[0]);
+            dmma884(c[2], ymask * yv[16], f2[0]);  dmma884(c[3], ymask * yv[24], f3[0]);
+            dmma884(c[0], ymask * yv[4], f[16]);   dmma884(c[1], ymask * yv[12], f1[16]);
+            dmma884(c[2], ymask * yv[20], f2[16]); dmma884(c[3], ymask * yv[28], f3[16]);
             f = f3 + 64 * (I + 3); yv += 32;
           }
           for (; I < K - 1; I++) {
