@@ -275,6 +275,10 @@ int uvs_reset_state(UvsHandle *h);
 /* stage order: sweep_proj, sweep_line, sweep_vp, sweep_imu, sweep_prior, build, chol, backsub,
  * resid_sweep, step */
 int uvs_set_profiling(UvsHandle *h, int32_t level);
+/* Replay the LM iteration of the uploaded batch from a CUDA graph (captured during the first solve after an upload)
+ * instead of launching its ~20 kernels one by one.  Off by default: building the graph costs more than one solve
+ * saves; enable it when the same upload is solved many times.  Ignored while stage profiling is on. */
+int uvs_set_graph_replay(UvsHandle *h, int32_t enable);
 /* accumulated device time [ms] of every stage over the last uvs_solve and the number of iterations run */
 int uvs_last_stage_ms(const UvsHandle *h, float ms[UVS_N_STAGES], int32_t *n_iterations);
 

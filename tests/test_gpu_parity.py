@@ -399,3 +399,22 @@ def test_rejected_steps_keep_the_system_complete(solver, windows):
         # any two solvers (measured: poses agree to 3e-8, the cost to 4e-6): the cost bar is 2e-5 here, the pose bar stays
         assert abs(sums[i].final_cost - sm0.final_cost) <= 2e-5 * abs(sm0.final_cost)
         assert np.abs(big[i].pose - r.pose).max() < STEP_TOL
+
+
+def test_graph_replay_gives_the_same_solve(windows, opts):
+    """uvs_set_graph_replay: the LM iteration replayed from a CUDA graph (captured at the first solve after an upload,
+    reused by later solves of the same upload) must give what the plain launches give."""
+    s = uvs_b200.Solver(0)
+    try:
+        batch = [windows["C2"].copy(), windows["C1"].copy(), windows["tiny"].copy()]
+        s.upload(batch, opts)
+        plain = s.solve()
+        s.set_graph_replay(True)
+        for _ in range(2):   # first solve captures, second one replays from iteration 0 on
+            s.reset_state()
+            g = s.solve()
+            for a, b in zip(plain, g):
+                assert a.num_iterations == b.num_iterations
+                assert abs(a.final_cost - b.final_cost) <= 1e-9 * abs(a.final_cost)
+    finally:
+        s.close()

@@ -22,7 +22,7 @@ EXPORTS = (
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
     "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate", "uvs_batch_solve_pipelined",
-    "uvs_triangulate_points", "uvs_triangulate_lines",
+    "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_set_graph_replay",
 )
 
 N_STAGES = 10
@@ -82,6 +82,7 @@ def load_library():
     lib.uvs_triangulate_points.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p, c_double_p, C.c_double, c_double_p]
     lib.uvs_triangulate_lines.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p] + [c_double_p] * 5
     lib.uvs_set_profiling.argtypes = [H, C.c_int32]
+    lib.uvs_set_graph_replay.argtypes = [H, C.c_int32]
     lib.uvs_last_stage_ms.argtypes = [H, C.POINTER(C.c_float * N_STAGES), C.POINTER(C.c_int32)]
     _lib = lib
     return lib
@@ -261,6 +262,9 @@ class Solver:
                                               p(lin_bg), p(noise), p(out["delta_p"]), p(out["delta_q"]), p(out["delta_v"]), p(out["sum_dt"]),
                                               p(out["jacobian"]), p(out["covariance"])), "uvs_preintegrate")
         return out
+
+    def set_graph_replay(self, enable=True):
+        self._check(self.lib.uvs_set_graph_replay(self.h, 1 if enable else 0), "uvs_set_graph_replay")
 
     def triangulate_points(self, Rs, Ps, ric, tic, start_frame, obs_off, obs_pts, init_depth=5.0):
         """FeatureManager::triangulate on the device: depth of every track (see include/uvs.h)."""

@@ -48,6 +48,9 @@ struct UvsHandle {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
   uvs::Fork fork{};                           // auxiliary streams + fork / join events (uvs_kernels.h)
   bool concurrent = false;                    // this batch runs independent kernels of a stage side by side
+  bool graph_replay = false;                  // uvs_set_graph_replay
+  cudaGraphExec_t iter_exec = nullptr;        // one LM iteration of the uploaded batch as a CUDA graph (uvs_solve)
+  int64_t iter_launches = 0;                  // kernel launches inside that graph
   std::string err;
   uvs::Arena dev, stage, scratch, hscratch;
   uvs::Dev D{};
