@@ -814,20 +814,26 @@ int uvs_batch_solve_pipelined(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOp
   std::vector<int> rcs(G, UVS_OK);
   std::vector<std::thread> workers;
   const UvsOptions o = opts ? *opts : h->opts;
+  static const bool trace = std::getenv("UVS_TRACE") != nullptr;
+  const auto t_call = std::chrono::steady_clock::now();
+  auto since = [t_call] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
   for (int g = 0; g < G; g++) {
     UvsHandle *c = h->children[g];
     const int lo = (int)((long long)B * g / G), hi = (int)((long long)B * (g + 1) / G);
-    const int64_t l0 = c->launches;
     // uploads go one after another (they share the host cores and the PCIe link); each sub-batch starts its LM loop
     // on its own stream as soon as its data has landed, overlapping the next sub-batch's pack + H2D
     rcs[g] = upload_enqueue(c, hi - lo, w + lo, &o);
+    if (trace) std::fprintf(stderr, "[uvs] pipelined: group %d upload enqueued at %.2f ms\n", g, since());
     if (rcs[g]) break;
-    workers.emplace_back([c, lo, hi, w, summaries, g, l0, &rcs] {
+    workers.emplace_back([c, lo, hi, w, summaries, g, since, &rcs] {
       int rc = upload_finish(c);
+      const double t_up = since();
       if (!rc) rc = uvs_solve(c, summaries ? summaries + lo : nullptr);
+      const double t_solve = since();
       if (!rc) rc = uvs_download_state(c, hi - lo, w + lo);
+      if (trace) std::fprintf(stderr, "[uvs] pipelined: group %d data on device at %.2f ms, solved at %.2f ms (device %.2f ms), downloaded at %.2f ms\n",
+                              g, t_up, t_solve, c->last_solve_ms, since());
       rcs[g] = rc;
-      (void)l0;
     });
   }
   for (auto &t : workers) t.join();
