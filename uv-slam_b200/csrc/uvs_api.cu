@@ -277,6 +277,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   const size_t w_ptb = wk.take(nP * I), w_lnb = wk.take(nL * I);            // begin arrays (memset 0x7f together)
   const size_t w_pte = wk.take(nP * I), w_lne = wk.take(nL * I), w_ptw = wk.take(nP * I), w_lnw = wk.take(nL * I);
   const size_t w_icomp = wk.take((size_t)nImu * 108 * Dd);
+  const size_t w_clw = wk.take(h->use_build3 ? (size_t)B * chol_chain_lw_doubles(max_frames) * Dd : 0);
   const size_t w_sqi = wk.take((size_t)nImu * 225 * Dd), w_prH = wk.take((size_t)nPJ * Dd), w_err = wk.take(I);
   const size_t w_rp = wk.take((size_t)nProj * 48 * Dd), w_rl = wk.take((size_t)nLobs * 24 * Dd), w_rv = wk.take((size_t)nVobs * 12 * Dd),
                w_ri = wk.take((size_t)nImu * REC_IMU * Dd), w_rpr = wk.take(nPriorR * Dd);
@@ -302,7 +303,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   std::memcpy(S + o_S_off, h->S_off.data(), (B + 1) * 8);
   std::memcpy(S + o_pJ_off, h->priorJ_off.data(), (B + 1) * 8);
   auto put = [&](size_t off, size_t elem_off, const void *src, size_t bytes) { if (bytes) std::memcpy(S + off + elem_off, src, bytes); };
-  std::atomic<int> pack_err(0);
+  std::atomic<int> pack_err(0), chain_bad(0);
   auto pack_range = [&](int lo, int hi) {
   for (int i = lo; i < hi; i++) {
     const UvsWindow &x = w[i];
@@ -338,6 +339,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
       put(o_prJ, (size_t)h->priorJ_off[i] * Dd, x.prior_J, (size_t)x.prior_n * x.prior_n * Dd);
       put(o_prr, (size_t)h->prior_off[i] * Dd, x.prior_r, x.prior_n * Dd);
       int col = 0; size_t xo = 0;
+      int sb_lo = 1 << 30, sb_hi = -1;   // frames whose speed-bias block the prior couples
       int *bk = (int *)(S + o_bk) + b0, *bi = (int *)(S + o_bi) + b0, *bcol = (int *)(S + o_bcol) + b0,
           *bcam = (int *)(S + o_bcam) + b0, *brow = (int *)(S + o_brow) + b0;
       double *bx = (double *)(S + o_prx) + 9 * b0;
@@ -346,6 +348,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
         if (kind < 0 || kind > 3) { pack_err = 1; return; }
         if ((kind <= 1) && (id < 0 || id >= x.n_frames)) { pack_err = 2; return; }
         bk[b] = kind; bi[b] = id; bcol[b] = col;
+        if (kind == UVS_BLOCK_SPEEDBIAS) { sb_lo = std::min(sb_lo, id); sb_hi = std::max(sb_hi, id); }
         int cam = -1, row = i;
         if (kind == UVS_BLOCK_POSE) { cam = 15 * id; row = (int)f0 + id; }
         else if (kind == UVS_BLOCK_SPEEDBIAS) { cam = 15 * id + 6; row = (int)f0 + id; }
@@ -357,6 +360,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
         xo += gs; col += prior_local(kind);
       }
       if (col != x.prior_n) { pack_err = 3; return; }
+      if (sb_hi - sb_lo > 1) chain_bad = 1;   // the prior ties speed-bias blocks of non-adjacent frames together
     }
   }
   };
@@ -369,6 +373,12 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
       std::vector<std::thread> th;
       for (int t = 0; t < nt; t++) th.emplace_back(pack_range, (int)((long long)B * t / nt), (int)((long long)B * (t + 1) / nt));
       for (auto &t : th) t.join();
+    }
+    {
+      static const bool no_chain = std::getenv("UVS_NO_CHAIN") != nullptr;
+      bool small = false;
+      for (int i = 0; i < B; i++) small = small || w[i].n_frames < 2;
+      h->chain_ok = h->use_build3 && !chain_bad && !small && !no_chain;
     }
     if (pack_err == 1) return fail(h, UVS_ERR_INVALID_ARG, "bad prior block kind");
     if (pack_err == 2) return fail(h, UVS_ERR_INVALID_ARG, "prior block id out of range");
@@ -413,7 +423,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   D.pblk_col = WI(o_bcol); D.pblk_cam = WI(o_bcam); D.pblk_row = WI(o_brow);
   D.proj_idx = (int4 *)(Dv + w_pidx); D.line_idx4 = (int4 *)(Dv + w_lidx); D.vp_idx4 = (int4 *)(Dv + w_vidx); D.imu_idx = (int2 *)(Dv + w_iidx);
   D.pt_begin = WI(w_ptb); D.ln_begin = WI(w_lnb); D.pt_end = WI(w_pte); D.ln_end = WI(w_lne); D.pt_win = WI(w_ptw); D.ln_win = WI(w_lnw);
-  D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.prior_H = WD(w_prH); D.err = WI(w_err);
+  D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.chain_lw = WD(w_clw); D.chain_lw_stride = chol_chain_lw_doubles(max_frames); D.prior_H = WD(w_prH); D.err = WI(w_err);
   D.rec_proj = WD(w_rp); D.rec_line = WD(w_rl); D.rec_vp = WD(w_rv); D.rec_imu = WD(w_ri); D.rec_prior = WD(w_rpr);
   D.scale_cam = WD(w_scc); D.scale_pt = WD(w_scp); D.scale_ln = WD(w_scl);
   D.Smat = WD(w_S); D.gS = WD(w_gS); D.gfull = WD(w_gf); D.colsq_cam = WD(w_csq);
@@ -709,7 +719,9 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
       rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc;
     }
     STAGE(6);
-    h->launches += launch_chol(D, P, h->max_d, h->packed_limit, h->use_build3, st); STAGE(7);
+    if (h->chain_ok) h->launches += launch_chol_chain(D, P, h->max_frames, h->any_ex, h->use_build3, st);
+    else h->launches += launch_chol(D, P, h->max_d, h->packed_limit, h->use_build3, st);
+    STAGE(7);
     rc = post_launch(h, "chol"); if (rc) return rc;
     if (h->use_build3) h->launches += launch_back3(D, h->dev.base + h->o_b3, h->b3, st, fk);
     else h->launches += launch_backsub(D, P, st);

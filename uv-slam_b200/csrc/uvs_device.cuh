@@ -100,6 +100,8 @@ struct Dev {
   int *pt_win, *ln_win;     // [nP], [nL]
   int *pblk_col, *pblk_cam, *pblk_row;   // column in J0, tangent offset in the window (-1 const), state row
   double *imu_sqrt_info;    // [nImu][225]
+  double *chain_lw;         // [B][chain_lw_stride] L_w blocks of the chain-mode reduced solve (k_chol_chain)
+  long long chain_lw_stride;
   double *imu_comp;         // [IMU_COMP = 108][nImu] compact blocks of the unweighted IMU Jacobians (k_imu_geom -> k_imu_weight)
   double *prior_H;          // [sum n^2]  J0^T J0 (constant during a solve)
   int *err;                 // [1] validation flag

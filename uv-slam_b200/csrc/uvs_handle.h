@@ -79,6 +79,7 @@ struct UvsHandle {
   int profiling = 0;
   int max_frames = 0; bool any_ex = false;
   bool use_build3 = false;                    // atomics-free landmark path (uvs_build3.cu)
+  bool chain_ok = false;                      // speed-bias blocks form a chain in every window: k_chol_chain
   uvs::Build3Layout b3{};
   size_t o_b3 = 0;
   std::vector<cudaEvent_t> stage_ev;          // (UVS_N_STAGES + 1) events per LM iteration

@@ -65,6 +65,10 @@ int chol_packed_limit(size_t max_smem);
 size_t chol_max_dynamic_smem(size_t optin_bytes);
 int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st);
 int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool mc_identity, cudaStream_t st);
+// chain mode (uvs_solve.cu): speed-bias blocks eliminated one by one, dense tensor-core Cholesky of the rest
+size_t chol_chain_smem(int max_frames, bool any_ex);
+int chol_chain_lw_doubles(int max_frames);
+int launch_chol_chain(const Dev &D, const Params &P, int max_frames, bool any_ex, bool mc_identity, cudaStream_t st);
 int launch_step(const Dev &D, const Params &P, cudaStream_t st);
 int launch_finish(const Dev &D, cudaStream_t st);
 int launch_count_active(const Dev &D, int *out, cudaStream_t st);

@@ -106,6 +106,498 @@ __device__ __forceinline__ void unrank_lower(int t, int &I, int &J) {
   I = i; J = t - i * (i + 1) / 2;
 }
 
+// Blocked right-looking Cholesky, forward and back substitution of a system that already sits in shared memory in
+// tensor-core fragment order (layout Lo at `A`; rhs in bz, solution returned in bz).  Called by every thread of the CTA.
+// Returns false when a pivot is not positive (s_flag set).
+__device__ bool blocked_chol_solve(double *A, const CholLayout &Lo, int nthr, unsigned short *s_pair, int &s_flag) {
+  const int tid = threadIdx.x;
+  const int K = Lo.K;
+  double *Dg = A + Lo.dbase;                          // diagonal blocks
+  double *bz = A + Lo.vbase;                          // rhs / z / y   [8K]
+  double *invd_all = bz + (size_t)K * NB;             // reciprocal diagonal of L, all rows [8K]
+  const int d = NB * (K - 1) + Lo.vr;
+  const int warp = tid >> 5, lane = tid & 31;
+  auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
+  auto frag = [&](int I, int f) { return A + 32 * I * (I - 1) + f * 4 * rows_of(I); };   // fragment f of block row I
+    for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
+    __syncthreads();
+    // factor of a diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot chain is
+    // rsqrt -> scale -> rank-1 update, operands exchanged with shuffles.  Missing rows act as identity rows.
+    auto potrf_block = [&](int k) {
+      double *invd = invd_all + k * NB;
+      double a[NB];
+      const int r = lane & 7;
+      const bool have = r < rows_of(k);
+      double *row = Dg + 36 * k + r * (r + 1) / 2;
+#pragma unroll
+      for (int c = 0; c < NB; c++) a[c] = have ? (c <= r ? row[c] : 0.0) : (c == r ? 1.0 : 0.0);
+      int bad = 0;
+#pragma unroll
+      for (int p = 0; p < NB; p++) {
+        const double piv = __shfl_sync(0xffffffffu, a[p], p);
+        if (!(piv > 0.0) || !isfinite(piv)) bad = 1;
+        const double inv = rsqrt(piv);
+        a[p] = r == p ? piv * inv : a[p] * inv;          // rows r < p are finished (their a[p] is unused)
+        if (r == p && lane < NB) invd[p] = inv;
+#pragma unroll
+        for (int q = p + 1; q < NB; q++) {
+          const double lq = __shfl_sync(0xffffffffu, a[p], q);
+          a[q] -= a[p] * lq;                             // only meaningful for r >= q
+        }
+      }
+      if (lane < NB && have) {
+#pragma unroll
+        for (int c = 0; c < NB; c++) if (c <= r) row[c] = a[c];
+      }
+      if (lane == 0 && bad) s_flag = 1;
+    };
+    // C -= L_I L_J^T for one 8x8 block on the tensor cores: lane l holds L[l>>2][l&3] of both operands (the B operand
+    // of m8n8k4 is column-major, i.e. L_J itself), and C[l>>2][2(l&3) + {0,1}]
+    const int fr = lane >> 2, fc = lane & 3;
+    auto block_update = [&](int I, int J, int k) {
+      const int ra = min(fr, rows_of(I) - 1), rb = min(fr, rows_of(J) - 1);   // rows that do not exist: any finite value
+      const double a0 = -frag(I, 2 * k)[4 * ra + fc], a1 = -frag(I, 2 * k + 1)[4 * ra + fc];
+      const double b0 = frag(J, 2 * k)[4 * rb + fc], b1 = frag(J, 2 * k + 1)[4 * rb + fc];
+      double c[2];
+      if (J < I) {
+        double2 *C = reinterpret_cast<double2 *>(frag(I, 2 * J + (fc >> 1)) + 4 * ra + 2 * (fc & 1));
+        const double2 c2 = *C;
+        c[0] = c2.x; c[1] = c2.y;
+        dmma884(c, a0, b0); dmma884(c, a1, b1);
+        if (fr < rows_of(I)) *C = make_double2(c[0], c[1]);
+      } else {
+        double *C = Dg + 36 * I + fr * (fr + 1) / 2 + 2 * fc;   // row fr, columns 2 fc, 2 fc + 1 (lower part only)
+        const bool h0 = 2 * fc <= fr && fr < rows_of(I), h1 = 2 * fc + 1 <= fr && fr < rows_of(I);
+        c[0] = h0 ? C[0] : 0.0; c[1] = h1 ? C[1] : 0.0;
+        dmma884(c, a0, b0); dmma884(c, a1, b1);
+        if (h0) C[0] = c[0];
+        if (h1) C[1] = c[1];
+      }
+    };
+    if (warp == 0) potrf_block(0);
+    __syncthreads();
+    for (int k = 0; k < K && !s_flag; k++) {
+      const double *invd = invd_all + k * NB;
+      const int vr = rows_of(k);                         // rows of block k that exist
+      // panel: L_Ik = A_Ik L_kk^-T for the rows below, z_k = L_kk^-1 b_k
+      const int nrows = max(0, d - NB * (k + 1));
+      for (int t = tid; t <= nrows; t += nthr) {
+        double x[NB];
+        double2 *r0, *r1;   // columns 8k..8k+3 and 8k+4..8k+7 of the row
+        if (t < nrows) {
+          const int i = NB * (k + 1) + t, I = i >> 3, r = i & 7;
+          r0 = reinterpret_cast<double2 *>(frag(I, 2 * k) + 4 * r); r1 = reinterpret_cast<double2 *>(frag(I, 2 * k + 1) + 4 * r);
+        } else {
+          r0 = reinterpret_cast<double2 *>(bz + k * NB); r1 = r0 + 2;
+        }
+        { const double2 t0 = r0[0], t1 = r0[1], t2 = r1[0], t3 = r1[1];
+          x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; x[4] = t2.x; x[5] = t2.y; x[6] = t3.x; x[7] = t3.y; }
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          if (p < vr) {
+            const double *akk = Dg + 36 * k + p * (p + 1) / 2;   // row p of L_kk (broadcast reads)
+            double v = x[p];
+#pragma unroll
+            for (int q = 0; q < p; q++) v -= x[q] * akk[q];
+            x[p] = v * invd[p];
+          }
+        }
+        r0[0] = make_double2(x[0], x[1]); r0[1] = make_double2(x[2], x[3]);
+        r1[0] = make_double2(x[4], x[5]); r1[1] = make_double2(x[6], x[7]);
+      }
+      __syncthreads();
+      // trailing update A_IJ -= L_Ik L_Jk^T, one 8x8 block per warp and step (two DMMAs), b_I -= L_Ik z_k.
+      // Look-ahead: warp 0 updates the next diagonal block first and factors it while the other warps do the rest.
+      const int nt = K - 1 - k;
+      if (warp == 0) {
+        if (nt > 0) {
+          block_update(k + 1, k + 1, k);
+          __syncwarp();
+          potrf_block(k + 1);
+        }
+      } else {
+        if (warp == 1) {
+          // L_kk is not read again before the back-substitution: replace it by its inverse (lane c: column c),
+          // which turns the 8-step dependent chain per block of the back-substitution into independent dot products
+          double *Dk = Dg + 36 * k;
+          double m[NB];
+          const int c = lane & 7;
+#pragma unroll
+          for (int r = 0; r < NB; r++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int q = 0; q < r; q++) if (r < vr) sacc += Dk[r * (r + 1) / 2 + q] * m[q];
+            m[r] = r < c ? 0.0 : (r == c ? invd[r] : -sacc * invd[r]);
+          }
+          __syncwarp();
+          if (lane < NB) {
+#pragma unroll
+            for (int r = 0; r < NB; r++) if (r >= c && r < vr) Dk[r * (r + 1) / 2 + c] = m[r];
+          }
+        }
+        const int nblk = nt * (nt + 1) / 2;
+        for (int blk = warp; blk < nblk; blk += nthr / 32 - 1) {   // blk 0 = (k+1, k+1): warp 0
+          const int pr = s_pair[blk];
+          block_update(k + 1 + (pr >> 8), k + 1 + (pr & 255), k);
+        }
+        for (int t = tid - 32; t < nrows; t += nthr - 32) {
+          const int i = NB * (k + 1) + t, I = i >> 3, r = i & 7;
+          const double2 *r0 = reinterpret_cast<const double2 *>(frag(I, 2 * k) + 4 * r), *r1 = reinterpret_cast<const double2 *>(frag(I, 2 * k + 1) + 4 * r);
+          const double2 *z = reinterpret_cast<const double2 *>(bz + k * NB);
+          double v = bz[i];
+          v -= r0[0].x * z[0].x; v -= r0[0].y * z[0].y; v -= r0[1].x * z[1].x; v -= r0[1].y * z[1].y;
+          v -= r1[0].x * z[2].x; v -= r1[0].y * z[2].y; v -= r1[1].x * z[3].x; v -= r1[1].y * z[3].y;
+          bz[i] = v;
+        }
+      }
+      __syncthreads();
+    }
+    if (s_flag) return false;
+    // back-substitution L^T y = z by one warp, block by block from the bottom, "left-looking": for block k first
+    // s = sum_{I>k} L_Ik^T y_I on the tensor cores ((y_I^T in row 0 of A) x (block of L as B), four independent
+    // accumulator chains, nothing written back in between), then y_k = L_kk^-T (z_k - s) as eight independent dot
+    // products (the diagonal blocks hold their inverses by now).
+    if (warp == 0) {
+      for (int k = K - 1; k >= 0; k--) {
+        const int vr = rows_of(k);
+        double c[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++) c[u][0] = c[u][1] = 0.0;
+        // one warp issues this whole chain: keep the instruction count per block low (pointer increments instead of
+        // address arithmetic; the ragged last block row is peeled off)
+        const double ymask = fr == 0 ? 1.0 : 0.0;
+        {
+          const int I = K - 1;   // last block row: rI rows
+          if (I > k) {
+            const int rI = rows_of(I);
+            const double ya = fc < rI ? ymask * bz[I * NB + fc] : 0.0;
+            const double yb = 4 + fc < rI ? ymask * bz[I * NB + 4 + fc] : 0.0;
+            const double *f = frag(I, 2 * k + (fr >> 2)) + (fr & 3);
+            dmma884(c[3], ya, f[4 * min(fc, rI - 1)]);
+            dmma884(c[3], yb, f[4 * min(4 + fc, rI - 1)]);
+          }
+        }
+        {
+          // full block rows I = k+1 .. K-2: fragment (I, 2k + (fr >> 2)) sits at 32 I (I-1) + 32 (2k + (fr >> 2)), i.e. 64 I further per row
+          int I = k + 1;
+          const double *f = A + 32 * I * (I - 1) + 32 * (2 * k + (fr >> 2)) + (fr & 3) + 4 * fc;
+          const double *yv = bz + I * NB + fc;
+          for (; I + 4 <= K - 1; I += 4) {
+            const double *f1 = f + 64 * I, *f2 = f1 + 64 * (I + 1), *f3 = f2 + 64 * (I + 2);
+            // issue order: the two DMMAs of an accumulator are four apart, so none waits for its predecessor
+            dmma884(c[0], ymask * yv[0], f[0]);    dmma884(c[1], ymask * yv[8], f1[0]);
+            dmma884(c[2], ymask * yv[16], f2[0]);  dmma884(c[3], ymask * yv[24], f3[0]);
+            dmma884(c[0], ymask * yv[4], f[16]);   dmma884(c[1], ymask * yv[12], f1[16]);
+            dmma884(c[2], ymask * yv[20], f2[16]); dmma884(c[3], ymask * yv[28], f3[16]);
+            f = f3 + 64 * (I + 3); yv += 32;
+          }
+          for (; I < K - 1; I++) {
+            dmma884(c[0], ymask * yv[0], f[0]); dmma884(c[0], ymask * yv[4], f[16]);
+            f += 64 * I; yv += NB;
+          }
+        }
+        if (lane < 4) {   // row 0 of the accumulators: columns 2 lane, 2 lane + 1 of block k
+          double2 *zc = reinterpret_cast<double2 *>(bz + k * NB + 2 * lane);
+          double2 zz = *zc;
+          zz.x -= (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+          zz.y -= (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+          *zc = zz;
+        }
+        __syncwarp();
+        const double *Dk = Dg + 36 * k;
+        const int p = lane & 7;
+        double y = 0.0;
+#pragma unroll
+        for (int q = 0; q < NB; q++) if (q >= p && q < vr) y += Dk[q * (q + 1) / 2 + p] * bz[k * NB + q];
+        __syncwarp();
+        if (lane < NB) bz[k * NB + lane] = y;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    return true;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Structure-exploiting reduced solve ("chain" mode).  The speed-bias blocks B_f (9 columns each) of the reduced camera
+// system couple only to their chain neighbours B_f-1, B_f+1 (IMU factors) and to the dense set D = {poses, extrinsic}
+// (IMU factors, prior); they never see each other across more than one frame unless a prior says so (checked at
+// upload).  Eliminating B_F-1, ..., B_0 in this order therefore needs, per block, a 9x9 Cholesky, the coupling blocks to
+// B_f-1 (9x9) and to D (nd x 9), and a rank-9 update of the dense nd x nd part - after which D is a 66..79-column dense
+// system for the blocked tensor-core Cholesky above.  Same arithmetic as a Cholesky of the whole matrix in that order,
+// but 35..50 KB of shared memory per window instead of 112 KB (four windows per SM instead of two) and ~2.3x fewer
+// FLOPs.  L_w (nd x 9 per block) goes to a global scratch for the back-substitution; everything else stays on chip.
+constexpr int CH_LWG = 720;      // doubles of global scratch per chain block (L_w, nd x 9)
+
+struct ChainLayout { int o_C[2], o_W[2], o_X, o_bb, o_LL, o_z, o_LwF, o_t, total; };
+__host__ __device__ __forceinline__ ChainLayout chain_layout(int nd, int F) {
+  const CholLayout Lo = chol_layout(nd);
+  ChainLayout c;
+  int o = (Lo.total + 1) & ~1;
+  c.o_C[0] = o; o += 82; c.o_C[1] = o; o += 82;
+  const int wsz = (9 * nd + 1) & ~1;          // a W buffer: nd x 9
+  c.o_W[0] = o; o += wsz; c.o_W[1] = o; o += wsz;
+  c.o_X = o; o += 82;
+  c.o_bb = o; o += 9 * F + (F & 1);          // rhs of every chain block
+  c.o_LL = o; o += 164 * F;                   // per block: L_c^-1 (81, lower) | L_x (81) | 2 pad
+  c.o_z = o; o += 10 * F;                     // z_f, later y_f
+  c.o_LwF = o; o += Lo.K * 96;                // L_w as tensor-core A fragments: [block row][k-step 0..2][32]
+  c.o_t = o; o += 10 * F;
+  c.total = o;
+  return c;
+}
+
+// C(I,J) -= sum_s a_s b_s^T for one 8x8 block of the fragment-layout matrix (nk k-steps of 4; lane holds the operands)
+__device__ __forceinline__ void frag_block_sub(double *A, double *Dg, int K, int vr, int I, int J, int lane, const double *a,
+                                               const double *b, int nk) {
+  const int fr = lane >> 2, fc = lane & 3;
+  const int rows = I == K - 1 ? vr : NB;
+  double c[2];
+  if (J < I) {
+    const int ra = min(fr, rows - 1);
+    double2 *C = reinterpret_cast<double2 *>(A + 32 * I * (I - 1) + (2 * J + (fc >> 1)) * 4 * rows + 4 * ra + 2 * (fc & 1));
+    const double2 c2 = *C;
+    c[0] = c2.x; c[1] = c2.y;
+    for (int s = 0; s < nk; s++) dmma884(c, -a[s], b[s]);
+    if (fr < rows) *C = make_double2(c[0], c[1]);
+  } else {
+    double *C = Dg + 36 * I + fr * (fr + 1) / 2 + 2 * fc;
+    const bool h0 = 2 * fc <= fr && fr < rows, h1 = 2 * fc + 1 <= fr && fr < rows;
+    c[0] = h0 ? C[0] : 0.0; c[1] = h1 ? C[1] : 0.0;
+    for (int s = 0; s < nk; s++) dmma884(c, -a[s], b[s]);
+    if (h0) C[0] = c[0];
+    if (h1) C[1] = c[1];
+  }
+}
+
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+// Solves (D_s S D_s + D^2) y = -D_s g for one window; y (in the order of S) -> yout (global).  All threads of the CTA.
+__device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int &s_flag, const Params &P, const double *Sg, int d, int F,
+                            const double *scale, const double *colsq, const double *gS, double radius, double *yout, double *lwg) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+  const int nd = d - 9 * F;
+  const CholLayout Lo = chol_layout(nd);
+  const ChainLayout Ch = chain_layout(nd, F);
+  const int K = Lo.K;
+  double *A = smem, *Dg = smem + Lo.dbase, *bz = smem + Lo.vbase, *invd_all = bz + K * NB;
+  double *Cb[2] = {smem + Ch.o_C[0], smem + Ch.o_C[1]}, *Wb[2] = {smem + Ch.o_W[0], smem + Ch.o_W[1]};
+  double *Xb = smem + Ch.o_X, *bb = smem + Ch.o_bb, *LL = smem + Ch.o_LL, *zb = smem + Ch.o_z, *LwF = smem + Ch.o_LwF, *tb = smem + Ch.o_t;
+  auto sidx = [&](int q) { return q < 6 * F ? 15 * (q / 6) + q % 6 : 15 * F + (q - 6 * F); };   // dense index -> index in S
+  auto cb = [&](int f) { return 15 * f + 6; };                                                    // first column of B_f in S
+  auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
+  auto slot = [&](int i, int j) -> double * {   // element (i, j), j <= i, of the dense part (dense indices)
+    const int I = i >> 3, r = i & 7;
+    return (j >> 3) == I ? Dg + 36 * I + r * (r + 1) / 2 + (j & 7) : A + 32 * I * (I - 1) + (j >> 2) * 4 * rows_of(I) + 4 * r + (j & 3);
+  };
+  auto lm = [&](int s) { const double sc = scale[s], h = sc * sc * colsq[s]; return clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; };
+  auto sup = [&](int i, int j) { return i <= j ? Sg + (size_t)i * d + j : Sg + (size_t)j * d + i; };   // S is stored as its upper triangle
+  // issue the copies of chain block fb (C lower, W) into buffer `buf`; with fx > 0 also X_fx (rows B_fx-1, columns B_fx)
+  auto load_block = [&](int fb, int buf, int fx) {
+    const int c0 = cb(fb);
+    for (int e = tid; e < 81; e += nthr) { const int r = e / 9, c = e - 9 * r; if (c <= r) cp_async8(Cb[buf] + e, sup(c0 + c, c0 + r)); }
+    for (int e = tid; e < nd * 9; e += nthr) { const int q = e / 9, c = e - 9 * q; cp_async8(Wb[buf] + e, sup(sidx(q), c0 + c)); }
+    if (fx > 0) for (int e = tid; e < 81; e += nthr) { const int r = e / 9, c = e - 9 * r; cp_async8(Xb + e, sup(cb(fx - 1) + r, cb(fx) + c)); }
+  };
+  auto scale_block = [&](int fb, int buf, int fx) {   // every thread scales what it copied
+    const int c0 = cb(fb);
+    for (int e = tid; e < 81; e += nthr) {
+      const int r = e / 9, c = e - 9 * r;
+      if (c <= r) { double v = Cb[buf][e] * scale[c0 + r] * scale[c0 + c]; if (c == r) v += lm(c0 + r); Cb[buf][e] = v; }
+    }
+    for (int e = tid; e < nd * 9; e += nthr) { const int q = e / 9, c = e - 9 * q; Wb[buf][e] *= scale[sidx(q)] * scale[c0 + c]; }
+    if (fx > 0) for (int e = tid; e < 81; e += nthr) { const int r = e / 9, c = e - 9 * r; Xb[e] *= scale[cb(fx - 1) + r] * scale[cb(fx) + c]; }
+  };
+
+  for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
+  // ---- load: dense part (fragment slots), first chain block, right-hand sides
+  for (int qj = warp; qj < nd; qj += nw) {
+    const int sj = sidx(qj);
+    for (int qi = qj + lane; qi < nd; qi += 32) cp_async8(slot(qi, qj), Sg + (size_t)sj * d + sidx(qi));
+  }
+  load_block(F - 1, (F - 1) & 1, 0);
+  for (int e = tid; e < K * 96; e += nthr) LwF[e] = 0.0;
+  for (int c = tid; c < K * NB; c += nthr) { bz[c] = c < nd ? -scale[sidx(c)] * gS[sidx(c)] : 0.0; invd_all[c] = 1.0; }
+  for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9, s = cb(f) + e - 9 * f; bb[e] = -scale[s] * gS[s]; }
+  cp_async_wait();
+  __syncthreads();
+  for (int qj = warp; qj < nd; qj += nw) {
+    const double sj = scale[sidx(qj)];
+    for (int qi = qj + lane; qi < nd; qi += 32) { double *a = slot(qi, qj); *a = scale[sidx(qi)] * sj * *a; }
+  }
+  scale_block(F - 1, (F - 1) & 1, 0);
+  __syncthreads();
+  for (int q = tid; q < nd; q += nthr) *slot(q, q) += lm(sidx(q));
+  __syncthreads();
+
+  // ---- chain elimination
+  for (int f = F - 1; f >= 0 && !s_flag; f--) {
+    const int cur = f & 1, nxt = cur ^ 1;
+    double *C = Cb[cur], *W = Wb[cur], *Li = LL + 164 * f, *Lx = Li + 81, *z = zb + 10 * f;
+    if (f > 0) load_block(f - 1, nxt, f);   // the next block and this block's coupling X_f land while warp 0 factors C
+    if (warp == 0) {
+      // 9x9 Cholesky in registers: lane r < 9 owns row r (same pivot chain as the 8x8 blocks)
+      const int r = lane < 9 ? lane : 8;
+      double a[9];
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = c <= r ? C[9 * r + c] : 0.0;
+      int bad = 0;
+      double myinv = 1.0;
+#pragma unroll
+      for (int p = 0; p < 9; p++) {
+        const double piv = __shfl_sync(0xffffffffu, a[p], p);
+        if (!(piv > 0.0) || !isfinite(piv)) bad = 1;
+        const double inv = rsqrt(piv);
+        a[p] = r == p ? piv * inv : a[p] * inv;
+        if (r == p) myinv = inv;
+#pragma unroll
+        for (int q = p + 1; q < 9; q++) {
+          const double lq = __shfl_sync(0xffffffffu, a[p], q);
+          a[q] -= a[p] * lq;
+        }
+      }
+      if (lane < 9) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) if (c <= r) C[9 * r + c] = a[c];   // L_c
+        z[lane] = myinv;                                              // parked: reciprocal diagonal
+      }
+      if (lane == 0 && bad) s_flag = 1;
+      __syncwarp();
+      // inverse of L_c, lane c: column c (forward substitution), then z = L_c^-1 b and, from the scaled X, L_x = X L_c^-T
+      {
+        const int c = r;
+        double m[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int q = 0; q < i; q++) sacc += C[9 * i + q] * m[q];
+          m[i] = i < c ? 0.0 : (i == c ? z[i] : -sacc * z[i]);
+        }
+        __syncwarp();
+        if (lane < 9) {
+#pragma unroll
+          for (int i = 0; i < 9; i++) Li[9 * i + c] = m[i];            // L_c^-1 (zeros above the diagonal)
+        }
+        __syncwarp();
+        double zz = 0.0;
+#pragma unroll
+        for (int q = 0; q < 9; q++) zz += Li[9 * r + q] * bb[9 * f + q];
+        __syncwarp();
+        if (lane < 9) z[lane] = zz;
+      }
+    }
+    if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt, f); }
+    __syncthreads();
+    if (s_flag) break;
+    if (f > 0 && tid < 81) {   // L_x = X L_c^-T
+      const int r = tid / 9, c = tid - 9 * r;
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) v += Xb[9 * r + k] * Li[9 * c + k];
+      Lx[tid] = v;
+    }
+    __syncthreads();
+    // L_w = W L_c^-T row by row; the same thread updates its row of the next block's W and the dense right-hand side
+    for (int q = tid; q < nd; q += nthr) {
+      double lw[9];
+#pragma unroll
+      for (int c = 0; c < 9; c++) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) if (k <= c) v += W[9 * q + k] * Li[9 * c + k];
+        lw[c] = v;
+      }
+      double *g = lwg + (size_t)f * CH_LWG + 9 * q;
+      double bq = bz[q];
+#pragma unroll
+      for (int c = 0; c < 9; c++) {
+        g[c] = lw[c];
+        LwF[((q >> 3) * 3 + (c >> 2)) * 32 + 4 * (q & 7) + (c & 3)] = lw[c];
+        bq -= lw[c] * z[c];
+      }
+      bz[q] = bq;
+      if (f > 0) {
+        double *Wn = Wb[nxt] + 9 * q;
+#pragma unroll
+        for (int c2 = 0; c2 < 9; c2++) {
+          double v = Wn[c2];
+#pragma unroll
+          for (int k = 0; k < 9; k++) v -= lw[k] * Lx[9 * c2 + k];
+          Wn[c2] = v;
+        }
+      }
+    }
+    if (f > 0 && tid >= nthr - 96 && tid < nthr - 96 + 81) {   // C_f-1 -= L_x L_x^T (lower), b_f-1 -= L_x z: another warp group
+      const int e = tid - (nthr - 96), r = e / 9, c = e - 9 * r;
+      if (c <= r) {
+        double v = Cb[nxt][e];
+#pragma unroll
+        for (int k = 0; k < 9; k++) v -= Lx[9 * r + k] * Lx[9 * c + k];
+        Cb[nxt][e] = v;
+      }
+      if (c == 0) {
+        double v = bb[9 * (f - 1) + r];
+#pragma unroll
+        for (int k = 0; k < 9; k++) v -= Lx[9 * r + k] * z[k];
+        bb[9 * (f - 1) + r] = v;
+      }
+    }
+    __syncthreads();
+    // dense part -= L_w L_w^T on the tensor cores (three k-steps of four columns; columns 9..11 are zero)
+    for (int blk = warp; blk < K * (K + 1) / 2; blk += nw) {
+      const int pr = s_pair[blk], I = pr >> 8, J = pr & 255;
+      double a[3], b[3];
+#pragma unroll
+      for (int s = 0; s < 3; s++) { a[s] = LwF[(I * 3 + s) * 32 + lane]; b[s] = LwF[(J * 3 + s) * 32 + lane]; }
+      frag_block_sub(A, Dg, K, Lo.vr, I, J, lane, a, b, 3);
+    }
+    __syncthreads();
+  }
+  if (s_flag) return false;
+
+  // ---- dense part
+  if (!blocked_chol_solve(A, Lo, nthr, s_pair, s_flag)) return false;
+
+  // ---- back-substitution of the chain: t_f = z_f - L_w^T y_D for all blocks at once, then y_f = L_c^-T (t_f - L_x^T y_f-1)
+  for (int e = tid; e < 9 * F; e += nthr) {
+    const int f = e / 9, c = e - 9 * f;
+    const double *g = lwg + (size_t)f * CH_LWG + c;
+    double t = zb[10 * f + c];
+    for (int q = 0; q < nd; q++) t -= g[9 * q] * bz[q];
+    tb[10 * f + c] = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int r = lane < 9 ? lane : 8;
+    for (int f = 0; f < F; f++) {
+      const double *Li = LL + 164 * f, *Lx = Li + 81;
+      double u = tb[10 * f + r];
+      if (f > 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) u -= Lx[9 * k + r] * zb[10 * (f - 1) + k];
+      }
+      __syncwarp();
+      if (lane < 9) tb[10 * f + lane] = u;
+      __syncwarp();
+      double y = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) if (k >= r) y += Li[9 * k + r] * tb[10 * f + k];
+      if (lane < 9) zb[10 * f + lane] = y;   // y_f replaces z_f
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int q = tid; q < nd; q += nthr) yout[sidx(q)] = bz[q];
+  for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9; yout[cb(f) + e - 9 * f] = zb[10 * f + e - 9 * f]; }
+  __syncthreads();
+  return true;
+}
+
 // developer aid: -DUVS_CHOL_TIMING prints the cycle count of every phase of window 0 (one line per launch)
 #ifdef UVS_CHOL_TIMING
 #define CHOL_TS(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) ts[i] = clock64(); } while (0)
@@ -113,14 +605,16 @@ __device__ __forceinline__ void unrank_lower(int t, int &I, int &J) {
 #define CHOL_TS(i) do { } while (0)
 #endif
 
-template <bool kPacked>
+// kMode: 0 = in place in global memory (large windows), 1 = dense blocked in shared memory, 2 = chain mode
+template <int kMode>
 __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, bool mc_identity) {
   __shared__ double red[CT / 32];   // CT = largest block size
   __shared__ int s_flag;
-  __shared__ unsigned short s_pair[kPacked ? 528 : 1];   // (I, J) of the t-th block of a lower triangle, K <= 32
+  constexpr bool kPacked = kMode == 1;
+  __shared__ unsigned short s_pair[kMode == 1 ? 528 : (kMode == 2 ? 64 : 1)];   // (I, J) of the t-th block of a lower triangle (K <= 32; chain mode K <= 10)
   const int nthr = blockDim.x;   // 256 when two windows fit one SM, else 512
 #ifdef UVS_CHOL_TIMING
-  long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_panel = 0, t_trail = 0, t_potrf = 0, t_bs_mma = 0, t_bs_rest = 0;
+  long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   CHOL_TS(0);
   int *s_cmap = reinterpret_cast<int *>(smem);   // aliases the factor: only used after the back-substitution
@@ -167,7 +661,18 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
   double *vec;   // solution vector y (d doubles)
   const double radius = ctl.radius;
   CHOL_TS(1);
-  if (kPacked) {
+  if (kMode == 2) {
+    vec = vec_y;   // the solution is written straight to its global home
+    CHOL_TS(2);
+    const bool ok = chain_solve(smem, nthr, s_pair, s_flag, P, Sg, d, F, scale, colsq, gS, radius, vec_y,
+                                D.chain_lw + (size_t)w * D.chain_lw_stride);
+    if (!ok) {
+      if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
+      return;
+    }
+    CHOL_TS(4);
+    CHOL_TS(5);
+  } else if (kPacked) {
     // ---- blocked path: the lower triangle in shared memory, 8x8 blocks, stored in FP64 tensor-core FRAGMENT order:
     //      block row I (rows 8I..8I+7), columns 0..8I-1, is a sequence of 8x4 fragments (32 consecutive doubles,
     //      element (r, c) at 4r + c = the lane that holds it in mma.sync m8n8k4), so every operand load of the
@@ -225,234 +730,12 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
 #endif
     }
     for (int c = tid; c < K * NB; c += nthr) { bz[c] = c < d ? -scale[c] * gS[c] : 0.0; invd_all[c] = 1.0; }
-    for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
-    __syncthreads();
-    // factor of a diagonal block with one warp, in registers: lane r < 8 owns row r; the pivot chain is
-    // rsqrt -> scale -> rank-1 update, operands exchanged with shuffles.  Missing rows act as identity rows.
-    auto potrf_block = [&](int k) {
-      double *invd = invd_all + k * NB;
-      double a[NB];
-      const int r = lane & 7;
-      const bool have = r < rows_of(k);
-      double *row = Dg + 36 * k + r * (r + 1) / 2;
-#pragma unroll
-      for (int c = 0; c < NB; c++) a[c] = have ? (c <= r ? row[c] : 0.0) : (c == r ? 1.0 : 0.0);
-      int bad = 0;
-#pragma unroll
-      for (int p = 0; p < NB; p++) {
-        const double piv = __shfl_sync(0xffffffffu, a[p], p);
-        if (!(piv > 0.0) || !isfinite(piv)) bad = 1;
-        const double inv = rsqrt(piv);
-        a[p] = r == p ? piv * inv : a[p] * inv;          // rows r < p are finished (their a[p] is unused)
-        if (r == p && lane < NB) invd[p] = inv;
-#pragma unroll
-        for (int q = p + 1; q < NB; q++) {
-          const double lq = __shfl_sync(0xffffffffu, a[p], q);
-          a[q] -= a[p] * lq;                             // only meaningful for r >= q
-        }
-      }
-      if (lane < NB && have) {
-#pragma unroll
-        for (int c = 0; c < NB; c++) if (c <= r) row[c] = a[c];
-      }
-      if (lane == 0 && bad) s_flag = 1;
-    };
-    // C -= L_I L_J^T for one 8x8 block on the tensor cores: lane l holds L[l>>2][l&3] of both operands (the B operand
-    // of m8n8k4 is column-major, i.e. L_J itself), and C[l>>2][2(l&3) + {0,1}]
-    const int fr = lane >> 2, fc = lane & 3;
-    auto block_update = [&](int I, int J, int k) {
-      const int ra = min(fr, rows_of(I) - 1), rb = min(fr, rows_of(J) - 1);   // rows that do not exist: any finite value
-      const double a0 = -frag(I, 2 * k)[4 * ra + fc], a1 = -frag(I, 2 * k + 1)[4 * ra + fc];
-      const double b0 = frag(J, 2 * k)[4 * rb + fc], b1 = frag(J, 2 * k + 1)[4 * rb + fc];
-      double c[2];
-      if (J < I) {
-        double2 *C = reinterpret_cast<double2 *>(frag(I, 2 * J + (fc >> 1)) + 4 * ra + 2 * (fc & 1));
-        const double2 c2 = *C;
-        c[0] = c2.x; c[1] = c2.y;
-        dmma884(c, a0, b0); dmma884(c, a1, b1);
-        if (fr < rows_of(I)) *C = make_double2(c[0], c[1]);
-      } else {
-        double *C = Dg + 36 * I + fr * (fr + 1) / 2 + 2 * fc;   // row fr, columns 2 fc, 2 fc + 1 (lower part only)
-        const bool h0 = 2 * fc <= fr && fr < rows_of(I), h1 = 2 * fc + 1 <= fr && fr < rows_of(I);
-        c[0] = h0 ? C[0] : 0.0; c[1] = h1 ? C[1] : 0.0;
-        dmma884(c, a0, b0); dmma884(c, a1, b1);
-        if (h0) C[0] = c[0];
-        if (h1) C[1] = c[1];
-      }
-    };
     CHOL_TS(2);
-    if (warp == 0) potrf_block(0);
-    __syncthreads();
-    CHOL_TS(3);
-    for (int k = 0; k < K && !s_flag; k++) {
-#ifdef UVS_CHOL_TIMING
-      const long long tk0 = clock64();
-#endif
-      const double *invd = invd_all + k * NB;
-      const int vr = rows_of(k);                         // rows of block k that exist
-      // panel: L_Ik = A_Ik L_kk^-T for the rows below, z_k = L_kk^-1 b_k
-      const int nrows = max(0, d - NB * (k + 1));
-      for (int t = tid; t <= nrows; t += nthr) {
-        double x[NB];
-        double2 *r0, *r1;   // columns 8k..8k+3 and 8k+4..8k+7 of the row
-        if (t < nrows) {
-          const int i = NB * (k + 1) + t, I = i >> 3, r = i & 7;
-          r0 = reinterpret_cast<double2 *>(frag(I, 2 * k) + 4 * r); r1 = reinterpret_cast<double2 *>(frag(I, 2 * k + 1) + 4 * r);
-        } else {
-          r0 = reinterpret_cast<double2 *>(bz + k * NB); r1 = r0 + 2;
-        }
-        { const double2 t0 = r0[0], t1 = r0[1], t2 = r1[0], t3 = r1[1];
-          x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; x[4] = t2.x; x[5] = t2.y; x[6] = t3.x; x[7] = t3.y; }
-#pragma unroll
-        for (int p = 0; p < NB; p++) {
-          if (p < vr) {
-            const double *akk = Dg + 36 * k + p * (p + 1) / 2;   // row p of L_kk (broadcast reads)
-            double v = x[p];
-#pragma unroll
-            for (int q = 0; q < p; q++) v -= x[q] * akk[q];
-            x[p] = v * invd[p];
-          }
-        }
-        r0[0] = make_double2(x[0], x[1]); r0[1] = make_double2(x[2], x[3]);
-        r1[0] = make_double2(x[4], x[5]); r1[1] = make_double2(x[6], x[7]);
-      }
-      __syncthreads();
-#ifdef UVS_CHOL_TIMING
-      const long long tk1 = clock64();
-      t_panel += tk1 - tk0;
-#endif
-      // trailing update A_IJ -= L_Ik L_Jk^T, one 8x8 block per warp and step (two DMMAs), b_I -= L_Ik z_k.
-      // Look-ahead: warp 0 updates the next diagonal block first and factors it while the other warps do the rest.
-      const int nt = K - 1 - k;
-      if (warp == 0) {
-        if (nt > 0) {
-#ifdef UVS_CHOL_TIMING
-          const long long tp0 = clock64();
-#endif
-          block_update(k + 1, k + 1, k);
-          __syncwarp();
-          potrf_block(k + 1);
-#ifdef UVS_CHOL_TIMING
-          t_potrf += clock64() - tp0;
-#endif
-        }
-      } else {
-        if (warp == 1) {
-          // L_kk is not read again before the back-substitution: replace it by its inverse (lane c: column c),
-          // which turns the 8-step dependent chain per block of the back-substitution into independent dot products
-          double *Dk = Dg + 36 * k;
-          double m[NB];
-          const int c = lane & 7;
-#pragma unroll
-          for (int r = 0; r < NB; r++) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int q = 0; q < r; q++) if (r < vr) sacc += Dk[r * (r + 1) / 2 + q] * m[q];
-            m[r] = r < c ? 0.0 : (r == c ? invd[r] : -sacc * invd[r]);
-          }
-          __syncwarp();
-          if (lane < NB) {
-#pragma unroll
-            for (int r = 0; r < NB; r++) if (r >= c && r < vr) Dk[r * (r + 1) / 2 + c] = m[r];
-          }
-        }
-        const int nblk = nt * (nt + 1) / 2;
-        for (int blk = warp; blk < nblk; blk += nthr / 32 - 1) {   // blk 0 = (k+1, k+1): warp 0
-          const int pr = s_pair[blk];
-          block_update(k + 1 + (pr >> 8), k + 1 + (pr & 255), k);
-        }
-        for (int t = tid - 32; t < nrows; t += nthr - 32) {
-          const int i = NB * (k + 1) + t, I = i >> 3, r = i & 7;
-          const double2 *r0 = reinterpret_cast<const double2 *>(frag(I, 2 * k) + 4 * r), *r1 = reinterpret_cast<const double2 *>(frag(I, 2 * k + 1) + 4 * r);
-          const double2 *z = reinterpret_cast<const double2 *>(bz + k * NB);
-          double v = bz[i];
-          v -= r0[0].x * z[0].x; v -= r0[0].y * z[0].y; v -= r0[1].x * z[1].x; v -= r0[1].y * z[1].y;
-          v -= r1[0].x * z[2].x; v -= r1[0].y * z[2].y; v -= r1[1].x * z[3].x; v -= r1[1].y * z[3].y;
-          bz[i] = v;
-        }
-      }
-      __syncthreads();
-#ifdef UVS_CHOL_TIMING
-      t_trail += clock64() - tk1;
-#endif
-    }
-    CHOL_TS(4);
-    if (s_flag) {
+    if (!blocked_chol_solve(A, Lo, nthr, s_pair, s_flag)) {
       if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
       return;
     }
-    // back-substitution L^T y = z by one warp, block by block from the bottom, "left-looking": for block k first
-    // s = sum_{I>k} L_Ik^T y_I on the tensor cores ((y_I^T in row 0 of A) x (block of L as B), four independent
-    // accumulator chains, nothing written back in between), then y_k = L_kk^-T (z_k - s) as eight independent dot
-    // products (the diagonal blocks hold their inverses by now).
-    if (warp == 0) {
-      for (int k = K - 1; k >= 0; k--) {
-        const int vr = rows_of(k);
-#ifdef UVS_CHOL_TIMING
-        const long long tb0 = clock64();
-#endif
-        double c[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; u++) c[u][0] = c[u][1] = 0.0;
-        // one warp issues this whole chain: keep the instruction count per block low (pointer increments instead of
-        // address arithmetic; the ragged last block row is peeled off)
-        const double ymask = fr == 0 ? 1.0 : 0.0;
-        {
-          const int I = K - 1;   // last block row: rI rows
-          if (I > k) {
-            const int rI = rows_of(I);
-            const double ya = fc < rI ? ymask * bz[I * NB + fc] : 0.0;
-            const double yb = 4 + fc < rI ? ymask * bz[I * NB + 4 + fc] : 0.0;
-            const double *f = frag(I, 2 * k + (fr >> 2)) + (fr & 3);
-            dmma884(c[3], ya, f[4 * min(fc, rI - 1)]);
-            dmma884(c[3], yb, f[4 * min(4 + fc, rI - 1)]);
-          }
-        }
-        {
-          // full block rows I = k+1 .. K-2: fragment (I, 2k + (fr >> 2)) sits at 32 I (I-1) + 32 (2k + (fr >> 2)), i.e. 64 I further per row
-          int I = k + 1;
-          const double *f = A + 32 * I * (I - 1) + 32 * (2 * k + (fr >> 2)) + (fr & 3) + 4 * fc;
-          const double *yv = bz + I * NB + fc;
-          for (; I + 4 <= K - 1; I += 4) {
-            const double *f1 = f + 64 * I, *f2 = f1 + 64 * (I + 1), *f3 = f2 + 64 * (I + 2);
-            // issue order: the two DMMAs of an accumulator are four apart, so none waits for its predecessor
-            dmma884(c[0], ymask * yv[0], f[0]);    dmma884(c[1], ymask * yv[8], f1[0]);
-            dmma884(c[2], ymask * yv[16], f2[0]);  dmma884(c[3], ymask * yv[24], f3[0]);
-            dmma884(c[0], ymask * yv[4], f[16]);   dmma884(c[1], ymask * yv[12], f1[16]);
-            dmma884(c[2], ymask * yv[20], f2[16]); dmma884(c[3], ymask * yv[28], f3[16]);
-            f = f3 + 64 * (I + 3); yv += 32;
-          }
-          for (; I < K - 1; I++) {
-            dmma884(c[0], ymask * yv[0], f[0]); dmma884(c[0], ymask * yv[4], f[16]);
-            f += 64 * I; yv += NB;
-          }
-        }
-#ifdef UVS_CHOL_TIMING
-        const long long tb1 = clock64();
-        t_bs_mma += tb1 - tb0;
-#endif
-        if (lane < 4) {   // row 0 of the accumulators: columns 2 lane, 2 lane + 1 of block k
-          double2 *zc = reinterpret_cast<double2 *>(bz + k * NB + 2 * lane);
-          double2 zz = *zc;
-          zz.x -= (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
-          zz.y -= (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
-          *zc = zz;
-        }
-        __syncwarp();
-        const double *Dk = Dg + 36 * k;
-        const int p = lane & 7;
-        double y = 0.0;
-#pragma unroll
-        for (int q = 0; q < NB; q++) if (q >= p && q < vr) y += Dk[q * (q + 1) / 2 + p] * bz[k * NB + q];
-        __syncwarp();
-        if (lane < NB) bz[k * NB + lane] = y;
-        __syncwarp();
-#ifdef UVS_CHOL_TIMING
-        t_bs_rest += clock64() - tb1;
-#endif
-      }
-    }
-    __syncthreads();
+    CHOL_TS(4);
     CHOL_TS(5);
   } else {
     // ---- large windows: in place in global memory (mirror the upper triangle into the lower one),
@@ -595,8 +878,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
 #ifdef UVS_CHOL_TIMING
   if (kPacked && threadIdx.x == 0 && blockIdx.x == 0) {
     const long long t6 = clock64();
-    printf("chol d=%d cycles: prologue %lld load %lld potrf0 %lld loop %lld (panel %lld trailing %lld of which diag update + potrf %lld) backsub %lld (mma %lld rest %lld) tail %lld total %lld\n", d,
-           ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], t_panel, t_trail, t_potrf, ts[5] - ts[4], t_bs_mma, t_bs_rest, t6 - ts[5], t6 - ts[0]);
+    printf("chol d=%d cycles: prologue %lld load %lld factor + substitutions %lld tail %lld total %lld\n", d, ts[1] - ts[0], ts[2] - ts[1], ts[4] - ts[2], t6 - ts[4], t6 - ts[0]);
   }
 #endif
   if (tid == 0) {
@@ -615,8 +897,20 @@ __global__ void __launch_bounds__(CT) k_chol(Dev D, Params P, int packed_limit, 
     return;
   }
   const int d = D.cam_off[w + 1] - D.cam_off[w];
-  if (d <= packed_limit) chol_window<true>(D, P, w, smem, mc_identity != 0);
-  else chol_window<false>(D, P, w, smem, mc_identity != 0);
+  if (d <= packed_limit) chol_window<1>(D, P, w, smem, mc_identity != 0);
+  else chol_window<0>(D, P, w, smem, mc_identity != 0);
+}
+
+// chain mode: 256 threads, <= 64 registers so that four windows share an SM
+__global__ void __launch_bounds__(256, 4) k_chol_chain(Dev D, Params P, int mc_identity) {
+  extern __shared__ double smem[];
+  const int w = blockIdx.x;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  if (D.acc[(size_t)w * ACC_STRIDE + ACC_FAIL] != 0.0) {   // a landmark block was not positive definite
+    if (threadIdx.x == 0) { D.ctl[w].state &= ~WS_STEP_OK; D.ctl[w].have_scale = 1; if (D.ctl[w].iter == 0) { D.ctl[w].cost = D.acc[(size_t)w * ACC_STRIDE + ACC_COST0]; D.ctl[w].iter = 1; D.summary[w].initial_cost = D.ctl[w].cost; D.summary[w].cost[0] = D.ctl[w].cost; } }
+    return;
+  }
+  chol_window<2>(D, P, w, smem, mc_identity != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -719,6 +1013,23 @@ int chol_packed_limit(size_t max_smem) {
 }
 
 int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st) { k_solve_init<<<D.B, CT, 0, st>>>(D, P); return 1; }
+
+size_t chol_chain_smem(int max_frames, bool any_ex) {
+  return (size_t)chain_layout(6 * max_frames + (any_ex ? 6 : 0), max_frames).total * sizeof(double);
+}
+int chol_chain_lw_doubles(int max_frames) { return max_frames * CH_LWG; }
+
+int launch_chol_chain(const Dev &D, const Params &P, int max_frames, bool any_ex, bool mc_identity, cudaStream_t st) {
+  const size_t smem = std::max(chol_chain_smem(max_frames, any_ex), (size_t)MAX_PRIOR_COLS * sizeof(int));
+  static size_t raised = 0;
+  if (smem > raised) {
+    cudaFuncSetAttribute(k_chol_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_chol_chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    raised = smem;
+  }
+  k_chol_chain<<<D.B, 256, smem, st>>>(D, P, mc_identity ? 1 : 0);
+  return 1;
+}
 
 int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool mc_identity, cudaStream_t st) {
   const int dd = max_d <= packed_limit ? max_d : packed_limit;
