@@ -413,6 +413,12 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     if (fx > 0) for (int e = tid; e < 81; e += nthr) { const int r = e / 9, c = e - 9 * r; Xb[e] *= scale[cb(fx - 1) + r] * scale[cb(fx) + c]; }
   };
 
+#ifdef UVS_CHOL_TIMING
+  long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq0 = clock64(), tq1;
+#define CH_T(i) do { tq1 = clock64(); tc[i] += tq1 - tq0; tq0 = tq1; } while (0)
+#else
+#define CH_T(i) do { } while (0)
+#endif
   for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
   // ---- load: dense part (fragment slots), first chain block, right-hand sides
   for (int qj = warp; qj < nd; qj += nw) {
@@ -434,6 +440,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   for (int q = tid; q < nd; q += nthr) *slot(q, q) += lm(sidx(q));
   __syncthreads();
 
+  CH_T(0);
   // ---- chain elimination
   for (int f = F - 1; f >= 0 && !s_flag; f--) {
     const int cur = f & 1, nxt = cur ^ 1;
@@ -493,6 +500,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     }
     if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt, f); }
     __syncthreads();
+    CH_T(1);
     if (s_flag) break;
     if (f > 0 && tid < 81) {   // L_x = X L_c^-T
       const int r = tid / 9, c = tid - 9 * r;
@@ -502,6 +510,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       Lx[tid] = v;
     }
     __syncthreads();
+    CH_T(2);
     // L_w = W L_c^-T row by row; the same thread updates its row of the next block's W and the dense right-hand side
     for (int q = tid; q < nd; q += nthr) {
       double lw[9];
@@ -548,6 +557,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       }
     }
     __syncthreads();
+    CH_T(3);
     // dense part -= L_w L_w^T on the tensor cores (three k-steps of four columns; columns 9..11 are zero)
     for (int blk = warp; blk < K * (K + 1) / 2; blk += nw) {
       const int pr = s_pair[blk], I = pr >> 8, J = pr & 255;
@@ -557,11 +567,13 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       frag_block_sub(A, Dg, K, Lo.vr, I, J, lane, a, b, 3);
     }
     __syncthreads();
+    CH_T(4);
   }
   if (s_flag) return false;
 
   // ---- dense part
   if (!blocked_chol_solve(A, Lo, nthr, s_pair, s_flag)) return false;
+  CH_T(5);
 
   // ---- back-substitution of the chain: t_f = z_f - L_w^T y_D for all blocks at once, then y_f = L_c^-T (t_f - L_x^T y_f-1)
   for (int e = tid; e < 9 * F; e += nthr) {
@@ -595,6 +607,12 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   for (int q = tid; q < nd; q += nthr) yout[sidx(q)] = bz[q];
   for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9; yout[cb(f) + e - 9 * f] = zb[10 * f + e - 9 * f]; }
   __syncthreads();
+  CH_T(6);
+#ifdef UVS_CHOL_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("chain nd=%d F=%d cycles: load %lld | per-block: factor+inverse+next-load %lld  Lx %lld  Lw+updates %lld  dense update %lld | dense solve %lld  chain back-sub %lld\n",
+           nd, F, tc[0], tc[1], tc[2], tc[3], tc[4], tc[5], tc[6]);
+#endif
   return true;
 }
 
