@@ -78,40 +78,89 @@ __device__ __forceinline__ double group_sum(unsigned gmask, double v) {
 constexpr int LPP = 4;   // lanes per point: one observation each (a C2 point has ~4), partial sums merged by shuffles
 constexpr int LPL = 8;   // lanes per line  (a C2 line has ~7 observations)
 
+// asynchronous global -> shared copies (LDGSTS): whole chunks of records are in flight at once without holding registers
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+// The records of a warp's eight points are one contiguous span of rec_proj (factors of a landmark are contiguous,
+// landmarks consecutive): the warp copies it 32 records at a time into shared memory with coalesced 16-byte
+// asynchronous copies (a lane reading its own 320-byte record with 8-byte loads costs 32 L1 wavefronts per
+// instruction), then every lane reads its record as 128-bit words (row stride 42 doubles: conflict-free).
+constexpr int PSTR = 42;
+
 __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
+  __shared__ __align__(16) double stage_all[4][32 * PSTR];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double *stage = stage_all[threadIdx.x >> 5];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int gp = t / LPP, sub = t - gp * LPP;
-  if (gp >= D.nP) return;   // every branch up to the shuffles is uniform over the lane group
-  const unsigned gmask = ((1u << LPP) - 1u) << ((threadIdx.x & 31) & ~(LPP - 1));
-  const int w = D.pt_win[gp];
-  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const unsigned gmask = ((1u << LPP) - 1u) << (lane & ~(LPP - 1));
+  bool act = gp < D.nP;   // uniform over the lane group
+  int w = 0, f0 = 0, n = 0;
+  if (act) { w = D.pt_win[gp]; act = (D.ctl[w].state & WS_ACTIVE) != 0; }
   const int mp = S.mp;
-  double *Y = S.Y + (colbase(D, w) + (gp - D.point_off[w])) * mp;
-  double *ph = S.ph + 4 * (size_t)gp;
-  const int f0 = D.pt_begin[gp], n = D.pt_end[gp] - f0;
-  const bool mine = D.nranks <= 1 || (gp % D.nranks) == D.rank;
-  // the column was zero-filled at upload and its sparsity pattern never changes: only the blocks are rewritten
-  if (n <= 0 || !mine) { if (sub == 0) ph[1] = 0.0; return; }
-  const bool ex = (D.win_flags[w] & WF_EXTRINSIC) != 0;
-  const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
-  const double *R = D.rec_proj + (size_t)f0 * REC_PROJ;
+  double *Y = nullptr, *ph = nullptr;
+  if (act) {
+    Y = S.Y + (colbase(D, w) + (gp - D.point_off[w])) * mp;
+    ph = S.ph + 4 * (size_t)gp;
+    f0 = D.pt_begin[gp]; n = D.pt_end[gp] - f0;
+    const bool mine = D.nranks <= 1 || (gp % D.nranks) == D.rank;
+    // the column was zero-filled at upload and its sparsity pattern never changes: only the blocks are rewritten
+    if (n <= 0 || !mine) { if (sub == 0) ph[1] = 0.0; act = false; }
+  }
+  const int lo = __reduce_min_sync(full, act ? f0 : 0x7fffffff), hi = __reduce_max_sync(full, act ? f0 + n : 0);
+  if (lo >= hi) return;   // uniform over the warp
+  const bool ex = act && (D.win_flags[w] & WF_EXTRINSIC) != 0;
+  const int fo = act ? D.frame_off[w] : 0, F = act ? D.frame_off[w + 1] - fo : 0;
   double colsq = 0.0, gk = 0.0;
   double wa[6] = {0, 0, 0, 0, 0, 0}, we[6] = {0, 0, 0, 0, 0, 0}, u0[6] = {0, 0, 0, 0, 0, 0};
-  for (int f = sub; f < n; f += LPP) {
-    const double *r = R + f * REC_PROJ;
-    const double j0 = r[38], j1 = r[39];
-    colsq += j0 * j0 + j1 * j1;
-    gk += j0 * r[0] + j1 * r[1];
-    const bool first = f < LPP;
-    double *yj = Y + 6 * (D.proj_idx[f0 + f].y - fo);
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      wa[c] += r[2 + c] * j0 + r[8 + c] * j1;
-      const double u = r[14 + c] * j0 + r[20 + c] * j1;
-      if (first) u0[c] = u; else yj[c] = u;   // later observations of this lane: parked unscaled, rescaled below
-      if (ex) we[c] += r[26 + c] * j0 + r[32 + c] * j1;
+  for (int c0 = lo; c0 < hi; c0 += 32) {
+    const int cnt = min(32, hi - c0);
+    const double *src = D.rec_proj + (size_t)c0 * REC_PROJ;
+    for (int p = lane; p < cnt * (REC_PROJ / 2); p += 32) {
+      const int r = p / (REC_PROJ / 2), q = p - (REC_PROJ / 2) * r;
+      cp_async16(stage + r * PSTR + 2 * q, src + 2 * p);
     }
+    cp_async_wait_all();
+    __syncwarp();
+    if (act) {
+      for (int f = sub; f < n; f += LPP) {
+        const int g = f0 + f - c0;
+        if (g < 0 || g >= 32) continue;
+        const double2 *r2 = reinterpret_cast<const double2 *>(stage + g * PSTR);
+        const double2 rr = r2[0], jl = r2[19];
+        const double j0 = jl.x, j1 = jl.y;
+        colsq += j0 * j0 + j1 * j1;
+        gk += j0 * rr.x + j1 * rr.y;
+        const bool first = f < LPP;
+        double *yj = Y + 6 * (D.proj_idx[f0 + f].y - fo);
+        double ji[12], jj[12];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { const double2 a = r2[1 + c], b2 = r2[7 + c]; ji[2 * c] = a.x; ji[2 * c + 1] = a.y; jj[2 * c] = b2.x; jj[2 * c + 1] = b2.y; }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          wa[c] += ji[c] * j0 + ji[6 + c] * j1;
+          const double u = jj[c] * j0 + jj[6 + c] * j1;
+          if (first) u0[c] = u; else yj[c] = u;   // later observations of this lane: parked unscaled, rescaled below
+        }
+        if (ex) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const double2 a = r2[13 + c], b2 = r2[16 + c];
+            we[2 * c] += a.x * j0 + b2.x * j1; we[2 * c + 1] += a.y * j0 + b2.y * j1;
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
+  if (!act) return;   // uniform over the lane group
   colsq = group_sum<LPP>(gmask, colsq);
   gk = group_sum<LPP>(gmask, gk);
 #pragma unroll
@@ -139,38 +188,73 @@ __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
 
 // One lane GROUP per line: the lanes split the line's observations (E = sum Jl^T Jl, g), merge by shuffles, every lane
 // factors the damped 4x4 block, then each lane writes  Y_f = (Jp^T Jl D_s) L^-T  of its own observations (+ VP factors).
+// The line records of a warp's four lines are one contiguous span of rec_line, their VP records one span of rec_vp
+// (k_prep_vp keeps the VP observations in line-observation order): both are copied into shared memory with coalesced
+// asynchronous copies and read from there by BOTH passes; spans that do not fit (never with <= 12 frames and dense
+// ranges) are read from global memory as before.
+constexpr int LCAP = 48;   // staged records per warp
+
 __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
+  __shared__ __align__(16) double lstage_all[4][LCAP * REC_LINE];
+  __shared__ __align__(16) double vstage_all[4][LCAP * REC_VP];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double *lstage = lstage_all[threadIdx.x >> 5], *vstage = vstage_all[threadIdx.x >> 5];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int gl = t / LPL, sub = t - gl * LPL;
-  if (gl >= D.nL) return;
-  const unsigned gmask = ((1u << LPL) - 1u) << ((threadIdx.x & 31) & ~(LPL - 1));
-  const int w = D.ln_win[gl];
-  if (!(D.ctl[w].state & WS_ACTIVE)) return;
-  const int f0 = D.ln_begin[gl], n = D.ln_end[gl] - f0;
+  const unsigned gmask = ((1u << LPL) - 1u) << (lane & ~(LPL - 1));
+  bool act = gl < D.nL;   // uniform over the lane group
+  int w = 0, f0 = 0, n = 0;
+  if (act) { w = D.ln_win[gl]; act = (D.ctl[w].state & WS_ACTIVE) != 0; }
   const int mp = S.mp;
-  double *Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp;   // 4 columns
-  double *hd = S.lh + 24 * (size_t)gl;
-  const bool mine = D.nranks <= 1 || (gl % D.nranks) == D.rank;
-  // Linv[0][0] = 0 marks "no step" for the back-substitution
-  if (n <= 0 || !mine) { if (sub == 0) hd[8] = 0.0; return; }
+  double *Y = nullptr, *hd = nullptr;
+  if (act) {
+    f0 = D.ln_begin[gl]; n = D.ln_end[gl] - f0;
+    Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * (gl - D.line_off[w])) * mp;   // 4 columns
+    hd = S.lh + 24 * (size_t)gl;
+    const bool mine = D.nranks <= 1 || (gl % D.nranks) == D.rank;
+    // Linv[0][0] = 0 marks "no step" for the back-substitution
+    if (n <= 0 || !mine) { if (sub == 0) hd[8] = 0.0; act = false; }
+  }
+  int myvlo = 0x7fffffff, myvhi = -1;
+  if (act) for (int f = sub; f < n; f += LPL) { const int vi = D.line_idx4[f0 + f].w; if (vi >= 0) { myvlo = min(myvlo, vi); myvhi = max(myvhi, vi); } }
+  const int lo = __reduce_min_sync(full, act ? f0 : 0x7fffffff), hi = __reduce_max_sync(full, act ? f0 + n : 0);
+  if (lo >= hi) return;   // uniform over the warp
+  const int vlo = __reduce_min_sync(full, myvlo), vhi = __reduce_max_sync(full, myvhi) + 1;
+  const bool staged_l = hi - lo <= LCAP, staged_v = vhi > vlo && vhi - vlo <= LCAP;
+  if (staged_l) {
+    const double *src = D.rec_line + (size_t)lo * REC_LINE;
+    for (int p = lane; p < (hi - lo) * (REC_LINE / 2); p += 32) cp_async16(lstage + 2 * p, src + 2 * p);
+  }
+  if (staged_v) {
+    const double *src = D.rec_vp + (size_t)vlo * REC_VP;
+    for (int p = lane; p < (vhi - vlo) * REC_VP; p += 32) cp_async8(vstage + p, src + p);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  if (!act) return;   // uniform over the lane group
+  auto line_rec = [&](int f) { return staged_l ? lstage + (f0 + f - lo) * REC_LINE : D.rec_line + (size_t)(f0 + f) * REC_LINE; };
+  auto vp_rec = [&](int vi) { return staged_v ? vstage + (vi - vlo) * REC_VP : D.rec_vp + (size_t)vi * REC_VP; };
   const int fo = D.frame_off[w];
   double E[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
   for (int f = sub; f < n; f += LPL) {
-    const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
+    const double2 *r2 = reinterpret_cast<const double2 *>(line_rec(f));
+    const double2 rr = r2[0];
 #pragma unroll
     for (int row = 0; row < 2; row++) {
-      const double a0 = r[14 + 4 * row], a1 = r[15 + 4 * row], a2 = r[16 + 4 * row], a3 = r[17 + 4 * row], rr = r[row];
+      const double2 a01 = r2[7 + 2 * row], a23 = r2[8 + 2 * row];
+      const double a0 = a01.x, a1 = a01.y, a2 = a23.x, a3 = a23.y, rw = row ? rr.y : rr.x;
       E[0] += a0 * a0; E[1] += a0 * a1; E[2] += a0 * a2; E[3] += a0 * a3; E[4] += a1 * a1; E[5] += a1 * a2; E[6] += a1 * a3;
       E[7] += a2 * a2; E[8] += a2 * a3; E[9] += a3 * a3;
-      g[0] += a0 * rr; g[1] += a1 * rr; g[2] += a2 * rr; g[3] += a3 * rr;
+      g[0] += a0 * rw; g[1] += a1 * rw; g[2] += a2 * rw; g[3] += a3 * rw;
     }
     const int vi = D.line_idx4[f0 + f].w;
     if (vi >= 0) {
-      const double *q = D.rec_vp + (size_t)vi * REC_VP;
-      const double a0 = q[7], a1 = q[8], a2 = q[9], a3 = q[10], rr = q[0];
+      const double *q = vp_rec(vi);
+      const double a0 = q[7], a1 = q[8], a2 = q[9], a3 = q[10], rw = q[0];
       E[0] += a0 * a0; E[1] += a0 * a1; E[2] += a0 * a2; E[3] += a0 * a3; E[4] += a1 * a1; E[5] += a1 * a2; E[6] += a1 * a3;
       E[7] += a2 * a2; E[8] += a2 * a3; E[9] += a3 * a3;
-      g[0] += a0 * rr; g[1] += a1 * rr; g[2] += a2 * rr; g[3] += a3 * rr;
+      g[0] += a0 * rw; g[1] += a1 * rw; g[2] += a2 * rw; g[3] += a3 * rw;
     }
   }
 #pragma unroll
@@ -242,16 +326,27 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
   }
   // Y blocks of this lane's observations
   for (int f = sub; f < n; f += LPL) {
-    const double *r = D.rec_line + (size_t)(f0 + f) * REC_LINE;
+    const double2 *r2 = reinterpret_cast<const double2 *>(line_rec(f));
     const int4 ix = D.line_idx4[f0 + f];
-    const double *q = ix.w >= 0 ? D.rec_vp + (size_t)ix.w * REC_VP : nullptr;
+    const double *q = ix.w >= 0 ? vp_rec(ix.w) : nullptr;
     double *Yf = Y + 6 * (ix.x - fo);
-    double jl[3][4];
+    double jl[3][4], jp[2][6];
 #pragma unroll
-    for (int c = 0; c < 4; c++) { jl[0][c] = r[14 + c] * s[c]; jl[1][c] = r[18 + c] * s[c]; jl[2][c] = q ? q[7 + c] * s[c] : 0.0; }
+    for (int c = 0; c < 2; c++) {
+      const double2 a = r2[7 + c], b2 = r2[9 + c];
+      jl[0][2 * c] = a.x * s[2 * c]; jl[0][2 * c + 1] = a.y * s[2 * c + 1];
+      jl[1][2 * c] = b2.x * s[2 * c]; jl[1][2 * c + 1] = b2.y * s[2 * c + 1];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) jl[2][c] = q ? q[7 + c] * s[c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const double2 a = r2[1 + c], b2 = r2[4 + c];
+      jp[0][2 * c] = a.x; jp[0][2 * c + 1] = a.y; jp[1][2 * c] = b2.x; jp[1][2 * c + 1] = b2.y;
+    }
 #pragma unroll
     for (int p = 0; p < 6; p++) {
-      const double a0 = r[2 + p], a1 = r[8 + p], a2 = q ? q[1 + p] : 0.0;
+      const double a0 = jp[0][p], a1 = jp[1][p], a2 = q ? q[1 + p] : 0.0;
       double W4[4];
 #pragma unroll
       for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
@@ -577,16 +672,11 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
 // (b,b) blocks (21 + 21) and of the gradient (6 + 6) - 90 outputs, three per lane; SEGS_D warps per diagonal block
 // take the line / VP factors.  The lists are read 32 items at a time (coalesced) and handed round by shuffles, so the
 // record loads of consecutive items are independent and stay in flight together.
+// FP64 tensor-core MMA  D(8x8) += A(8x4) B(4x8)  (mma.sync m8n8k4: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}])
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 constexpr int SEGS_D = 4;
-// asynchronous global -> shared copies (LDGSTS): the records of a whole list chunk are in flight at once without
-// holding registers
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 constexpr int DSTR = 26;   // doubles staged per item: [r | Ji | Jj] of a projection record; 14 of a line record, 7 of a VP record
 
 __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int nb_max) {
@@ -626,24 +716,17 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
     if (b >= nb) return;
     const int i0 = o0, i1 = o1;
     if (i0 >= i1) return;
-    // output o = lane + 32 t:  [0,36) block (a,b)   [36,57) (a,a)   [57,78) (b,b)   [78,84) g_a   [84,90) g_b
-    // operand offsets inside the record for a kind-2 item (a = anchor frame i: A = Ji at 2, B = Jj at 14) and a
-    // kind-3 item (a = observing frame j: A = Jj, B = Ji);  second row: +6 for a Jacobian operand, +1 for the residual
-    int x2[3], y2[3], x3[3], y3[3], yd[3];
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      const int o = lane + 32 * t;
-      int xs = 0, xp = 0, ys = 0, yq = 0;   // operand = block (0 = A, 1 = B, 2 = residual) + column
-      if (o < 36) { xs = 0; xp = o / 6; ys = 1; yq = o - 6 * xp; }
-      else if (o < 57) { xs = 0; xp = c_sym_p[o - 36]; ys = 0; yq = c_sym_q[o - 36]; }
-      else if (o < 78) { xs = 1; xp = c_sym_p[o - 57]; ys = 1; yq = c_sym_q[o - 57]; }
-      else if (o < 84) { xs = 0; xp = o - 78; ys = 2; }
-      else if (o < 90) { xs = 1; xp = o - 84; ys = 2; }
-      x2[t] = (xs == 0 ? 2 : 14) + xp; x3[t] = (xs == 0 ? 14 : 2) + xp;
-      y2[t] = ys == 2 ? 0 : (ys == 0 ? 2 : 14) + yq; y3[t] = ys == 2 ? 0 : (ys == 0 ? 14 : 2) + yq;
-      yd[t] = ys == 2 ? 1 : 6;
-    }
-    double acc[3] = {0.0, 0.0, 0.0};
+    // G = [J_a | J_b | r | 0 0 0] (two rows per factor, 16 columns): G^T G holds the (a,a), (a,b), (b,b) blocks and both
+    // gradients.  It is accumulated on the FP64 tensor cores, four rows (two factors) per step: the A fragment of a
+    // column block and its B fragment are the same value G[k = lane % 4][8 blk + lane / 4], so a step is two
+    // shared-memory reads and three DMMAs (blocks (0,0), (0,1), (1,1) of the upper triangle) per lane.
+    // Offsets inside a staged record for a kind-2 item (a = anchor frame i: J_a = Ji at 2, J_b = Jj at 14) and a
+    // kind-3 item (a = observing frame j: J_a = Jj, J_b = Ji); second row +6 (Jacobians) / +1 (residual).
+    const int fcol = lane >> 2, frow = lane & 1, fsub = (lane >> 1) & 1;
+    const int o0_k2 = (fcol < 6 ? 2 + fcol : 8 + fcol) + 6 * frow, o0_k3 = (fcol < 6 ? 14 + fcol : fcol - 4) + 6 * frow;
+    const int o1_k2 = fcol < 4 ? 16 + fcol + 6 * frow : (fcol == 4 ? frow : -1);
+    const int o1_k3 = fcol < 4 ? 4 + fcol + 6 * frow : (fcol == 4 ? frow : -1);
+    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
     for (int base = i0; base < i1; base += 32) {
       int kind = -1;
       if (base + lane < i1) {
@@ -660,36 +743,38 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
       cp_async_wait_all();
       __syncwarp();
       const int cnt = min(32, i1 - base);
-#pragma unroll 4
-      for (int k = 0; k < cnt; k++) {
-        const int kd = __shfl_sync(full, kind, k);
-        if (kd < 0) continue;
-        const double *rec = buf + k * DSTR;
-        const bool swap = kd == 3;
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-          const int xo = swap ? x3[t] : x2[t], yo = swap ? y3[t] : y2[t];
-          acc[t] += rec[xo] * rec[yo] + rec[xo + 6] * rec[yo + yd[t]];
+#pragma unroll 2
+      for (int s = 0; 2 * s < cnt; s++) {
+        const int it = 2 * s + fsub;
+        const int kd = __shfl_sync(full, kind, it);
+        double g0 = 0.0, g1 = 0.0;
+        if (kd >= 0) {
+          const double *rec = buf + it * DSTR;
+          const int o1 = kd == 3 ? o1_k3 : o1_k2;
+          g0 = rec[kd == 3 ? o0_k3 : o0_k2];
+          if (o1 >= 0) g1 = rec[o1];
         }
+        dmma884(c00, g0, g0);
+        dmma884(c01, g0, g1);
+        dmma884(c11, g1, g1);
       }
       __syncwarp();
     }
     const int ra = 15 * a, rb = 15 * b;
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      const int o = lane + 32 * t;
-      if (o < 36) { const int p = o / 6, q = o - 6 * p; atomicAdd(Sg + (size_t)(ra + p) * d + rb + q, acc[t]); }
-      else if (o < 78) {
-        const int e = o < 57 ? o - 36 : o - 57, r0 = o < 57 ? ra : rb;
-        const int p = c_sym_p[e], q = c_sym_q[e];
-        atomicAdd(Sg + (size_t)(r0 + p) * d + r0 + q, acc[t]);
-        if (p == q) atomicAdd(D.colsq_cam + co + r0 + p, acc[t]);
-      } else if (o < 90) {
-        const int r0 = (o < 84 ? ra : rb) + (o < 84 ? o - 78 : o - 84);
-        atomicAdd(D.gS + co + r0, acc[t]);
-        atomicAdd(D.gfull + co + r0, acc[t]);
-      }
-    }
+    // entry (p, q) of G^T G, p <= q: columns 0..5 -> block a, 6..11 -> block b, 12 -> gradient
+    auto put = [&](int p, int q, double v) {
+      if (p >= 12 || q > 12) return;
+      const int gp = p < 6 ? ra + p : rb + p - 6;
+      if (q == 12) { atomicAdd(D.gS + co + gp, v); atomicAdd(D.gfull + co + gp, v); return; }
+      if (p > q) return;
+      const int gq = q < 6 ? ra + q : rb + q - 6;
+      atomicAdd(Sg + (size_t)gp * d + gq, v);
+      if (p == q) atomicAdd(D.colsq_cam + co + gp, v);
+    };
+    const int pr = lane >> 2, pc = 2 * (lane & 3);
+    put(pr, pc, c00[0]); put(pr, pc + 1, c00[1]);
+    put(pr, 8 + pc, c01[0]); put(pr, 9 + pc, c01[1]);
+    put(8 + pr, 8 + pc, c11[0]); put(8 + pr, 9 + pc, c11[1]);
   } else {
     // line / VP factors of diagonal block a, one segment of the list
     if (a >= nb) return;
@@ -697,9 +782,11 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
     const int per = (i1 - i0 + SEGS_D - 1) / SEGS_D;
     i0 += seg * per; i1 = min(i1, i0 + per);
     if (i0 >= i1) return;
-    const bool isg = lane >= 21;
-    const int p = lane < 21 ? c_sym_p[lane] : min(lane - 21, 5), q = lane < 21 ? c_sym_q[lane] : 0;
-    double acc = 0.0;
+    // G = [J_pose (6) | r | 0], two rows per item (the second row of a VP item is zero): one DMMA per two items
+    const int fcol = lane >> 2, frow = lane & 1, fsub = (lane >> 1) & 1;
+    const int o_line = fcol < 6 ? 2 + 6 * frow + fcol : (fcol == 6 ? frow : -1);
+    const int o_vp = frow ? -1 : (fcol < 6 ? 1 + fcol : (fcol == 6 ? 0 : -1));
+    double cc[2] = {0.0, 0.0};
     for (int base = i0; base < i1; base += 32) {
       int mybase = -1;   // offset of the pose block inside the record (2: line, two rows; 1: VP, one row); -1 = skip
       if (base + lane < i1) {
@@ -724,32 +811,34 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
       cp_async_wait_all();
       __syncwarp();
       const int cnt = min(32, i1 - base);
-#pragma unroll 4
-      for (int k = 0; k < cnt; k++) {
-        const int bA = __shfl_sync(full, mybase, k);
-        if (bA < 0) continue;
-        const double *rec = buf + k * DSTR;
-        double t = rec[bA + p] * (isg ? rec[0] : rec[bA + q]);
-        if (bA == 2) t += rec[bA + 6 + p] * (isg ? rec[1] : rec[bA + 6 + q]);   // line factors have two residual rows
-        acc += t;
+#pragma unroll 2
+      for (int s = 0; 2 * s < cnt; s++) {
+        const int it = 2 * s + fsub;
+        const int bA = __shfl_sync(full, mybase, it);
+        double g = 0.0;
+        if (bA >= 0) {
+          const int o = bA == 2 ? o_line : o_vp;
+          if (o >= 0) g = buf[it * DSTR + o];
+        }
+        dmma884(cc, g, g);
       }
       __syncwarp();
     }
     const int ra = 15 * a;
-    if (lane < 21) {
-      atomicAdd(Sg + (size_t)(ra + p) * d + ra + q, acc);
-      if (p == q) atomicAdd(D.colsq_cam + co + ra + p, acc);
-    } else if (lane < 27) {
-      atomicAdd(D.gS + co + ra + p, acc);
-      atomicAdd(D.gfull + co + ra + p, acc);
+    const int pr = lane >> 2, pc = 2 * (lane & 3);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int p = pr, q = pc + e;
+      if (p >= 6 || q > 6) continue;
+      if (q == 6) { atomicAdd(D.gS + co + ra + p, cc[e]); atomicAdd(D.gfull + co + ra + p, cc[e]); }
+      else if (p <= q) {
+        atomicAdd(Sg + (size_t)(ra + p) * d + ra + q, cc[e]);
+        if (p == q) atomicAdd(D.colsq_cam + co + ra + p, cc[e]);
+      }
     }
   }
 }
 
-// FP64 tensor-core MMA  D(8x8) += A(8x4) B(4x8)  (mma.sync m8n8k4: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}])
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
 constexpr int SUP = 3;        // a warp owns a SUP x SUP block of 8x8 tiles of the rank update
 constexpr int SUP_SETS = 2;   // and at most this many of them (8 warps x 2 covers the 10 blocks of 12 camera blocks)
 
