@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
 // (k_prep_vp keeps the VP observations in line-observation order): both are copied into shared memory with coalesced
 // asynchronous copies and read from there by BOTH passes; spans that do not fit (never with <= 12 frames and dense
 // ranges) are read from global memory as before.
-constexpr int LCAP = 48;   // staged records per warp
+constexpr int LCAP = 44;   // staged records per warp (4 lines x 11 frames; 46 KB of static shared memory per CTA)
 
 __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
   __shared__ __align__(16) double lstage_all[4][LCAP * REC_LINE];

@@ -414,10 +414,14 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   };
 
 #ifdef UVS_CHOL_TIMING
-  long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq0 = clock64(), tq1;
+  long long tc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tq0 = clock64(), tq1, tp0, tp1;
+#define CH_P0() do { tp0 = clock64(); } while (0)
+#define CH_P(i) do { tp1 = clock64(); tc[i] += tp1 - tp0; tp0 = tp1; } while (0)
 #define CH_T(i) do { tq1 = clock64(); tc[i] += tq1 - tq0; tq0 = tq1; } while (0)
 #else
 #define CH_T(i) do { } while (0)
+#define CH_P0() do { } while (0)
+#define CH_P(i) do { } while (0)
 #endif
   for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
   // ---- load: dense part (fragment slots), first chain block, right-hand sides
@@ -445,7 +449,9 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   for (int f = F - 1; f >= 0 && !s_flag; f--) {
     const int cur = f & 1, nxt = cur ^ 1;
     double *C = Cb[cur], *W = Wb[cur], *Li = LL + 164 * f, *Lx = Li + 81, *z = zb + 10 * f;
+    CH_P0();
     if (f > 0) load_block(f - 1, nxt, f);   // the next block and this block's coupling X_f land while warp 0 factors C
+    CH_P(8);
     if (warp == 0) {
       // 9x9 Cholesky in registers: lane r < 9 owns row r (same pivot chain as the 8x8 blocks)
       const int r = lane < 9 ? lane : 8;
@@ -474,6 +480,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       }
       if (lane == 0 && bad) s_flag = 1;
       __syncwarp();
+      CH_P(9);
       // inverse of L_c, lane c: column c (forward substitution), then z = L_c^-1 b and, from the scaled X, L_x = X L_c^-T
       {
         const int c = r;
@@ -497,9 +504,11 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
         __syncwarp();
         if (lane < 9) z[lane] = zz;
       }
+      CH_P(10);
     }
-    if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt, f); }
+    if (f > 0) { cp_async_wait(); CH_P(11); scale_block(f - 1, nxt, f); CH_P(12); }
     __syncthreads();
+    CH_P(13);
     CH_T(1);
     if (s_flag) break;
     if (f > 0 && tid < 81) {   // L_x = X L_c^-T
@@ -612,6 +621,9 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   if (threadIdx.x == 0 && blockIdx.x == 0)
     printf("chain nd=%d F=%d cycles: load %lld | per-block: factor+inverse+next-load %lld  Lx %lld  Lw+updates %lld  dense update %lld | dense solve %lld  chain back-sub %lld\n",
            nd, F, tc[0], tc[1], tc[2], tc[3], tc[4], tc[5], tc[6]);
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("  phase 1 of warp 0: issue next-block copies %lld  9x9 Cholesky %lld  inverse + z %lld  copy wait %lld  scale %lld  barrier %lld\n",
+           tc[8], tc[9], tc[10], tc[11], tc[12], tc[13]);
 #endif
   return true;
 }
