@@ -363,20 +363,41 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
 
 // ------------------------------------------------------------------------------------------------
 // back-substitution, one thread per landmark
+// The columns of a warp's eight points are contiguous when they belong to one window: the warp copies them into shared
+// memory with coalesced 16-byte asynchronous copies and the lane groups (4 lanes per point) read their blocks from
+// there; warps that straddle windows read global memory.
+constexpr int MP_MAX = 84;   // largest column stride (12 camera blocks + z, padded to 4 mod 16)
+
 __global__ void __launch_bounds__(128) k_back_points(Dev D, Stash S) {
-  const int gp = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ __align__(16) double stage_all[4][(32 / LPP) * MP_MAX];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double *stage = stage_all[threadIdx.x >> 5];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gp = t / LPP, sub = t - gp * LPP;
+  const unsigned gmask = ((1u << LPP) - 1u) << (lane & ~(LPP - 1));
   bool valid = gp < D.nP && (D.nranks <= 1 || (gp % D.nranks) == D.rank);
   int w = 0;
   if (valid) {
     w = D.pt_win[gp];
     valid = (D.ctl[w].state & WS_ACTIVE) && D.acc[(size_t)w * ACC_STRIDE + ACC_FAIL] == 0.0;
   }
+  const int mp = S.mp;
+  const double *Y = valid ? S.Y + (colbase(D, w) + (gp - D.point_off[w])) * mp : nullptr;
+  // staged path: every group of the warp valid and in the window of lane 0 (columns contiguous from lane 0's on)
+  const int w0 = __shfl_sync(full, w, 0);
+  const bool staged = __all_sync(full, valid && w == w0) && mp <= MP_MAX;
+  if (staged) {
+    const double *src = reinterpret_cast<const double *>(__shfl_sync(full, (unsigned long long)Y, 0));
+    for (int p = lane; p < (32 / LPP) * mp / 2; p += 32) cp_async16(stage + 2 * p, src + 2 * p);
+    cp_async_wait_all();
+    __syncwarp();
+  }
   double mc = 0.0, s2 = 0.0, x2 = 0.0;
-  if (valid) {
-    const int mp = S.mp, cur = D.cur[w];
-    const double *Y = S.Y + (colbase(D, w) + (gp - D.point_off[w])) * mp;
+  if (valid) {   // uniform over the lane group
+    const int cur = D.cur[w];
+    const double *y = staged ? stage + (lane / LPP) * mp : Y;
     const double *ph = S.ph + 4 * (size_t)gp;
-    const double lam = D.inv_depth[cur][gp];
     const double sk = ph[0], sh = ph[1], D2 = ph[2];
     double dk = 0.0;
     if (sh != 0.0) {
@@ -384,23 +405,28 @@ __global__ void __launch_bounds__(128) k_back_points(Dev D, Stash S) {
       const int nb = F + ((D.win_flags[w] & WF_EXTRINSIC) ? 1 : 0);
       const double *dl = D.delta_cam + D.cam_off[w];
       double u = 0.0;
-      for (int b = 0; b < nb; b++) {
-        const double *y = Y + 6 * b, *d = dl + 15 * b;   // the extrinsic block (b == F) sits at 15 F as well
+      for (int b = sub; b < nb; b += LPP) {   // the lanes split the camera blocks; the extrinsic block (b == F) sits at 15 F as well
 #pragma unroll
-        for (int c = 0; c < 6; c++) u += y[c] * d[c];
+        for (int c = 0; c < 6; c++) u += y[6 * b + c] * dl[15 * b + c];
       }
-      const double z = Y[mp - 2];
+      u = group_sum<LPP>(gmask, u);
+      const double z = y[mp - 2];
       const double yk = -sh * (z + u);
       dk = sk * yk;
       mc = 0.5 * (D2 * yk * yk - (z / sh) * yk);
     }
-    D.delta_pt[gp] = dk;
-    D.inv_depth[cur ^ 1][gp] = lam + dk;
-    s2 = dk * dk; x2 = lam * lam;
+    if (sub == 0) {
+      const double lam = D.inv_depth[cur][gp];
+      D.delta_pt[gp] = dk;
+      D.inv_depth[cur ^ 1][gp] = lam + dk;
+      s2 = dk * dk; x2 = lam * lam;
+    }
   }
-  add_win3(D.acc, w, valid, mc, s2, x2);
+  add_win3(D.acc, w, valid && sub == 0, mc, s2, x2);
 }
 
+// back-substitution of the lines, one lane group per line (4 columns).  Staging the columns like k_back_points was
+// measured slower (43 KB of shared memory per CTA halves the resident warps of a latency-bound kernel: 76 -> 90 us).
 __global__ void __launch_bounds__(128) k_back_lines(Dev D, Stash S) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int gl = t / LPL, sub = t - gl * LPL;
@@ -1118,7 +1144,7 @@ int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t
   Build3Ctx c; make_ctx(base, lay, c);
   int n = 0;
   if (fk) fork_from(fk, st, 1);
-  if (D.nP) { k_back_points<<<cdiv3(D.nP, 128), 128, 0, st>>>(D, c.S); n++; }
+  if (D.nP) { k_back_points<<<cdiv3(D.nP, 128 / LPP), 128, 0, st>>>(D, c.S); n++; }
   if (D.nL) { k_back_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, fk ? fk->aux[0] : st>>>(D, c.S); n++; }
   if (fk) join_to(fk, st, 0);
   return n;

@@ -396,21 +396,32 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   };
   auto lm = [&](int s) { const double sc = scale[s], h = sc * sc * colsq[s]; return clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; };
   auto sup = [&](int i, int j) { return i <= j ? Sg + (size_t)i * d + j : Sg + (size_t)j * d + i; };   // S is stored as its upper triangle
+  // Copies and scaling of the chain blocks belong to warps 1.. (warp 0 runs the 9x9 factorisation meanwhile): thread
+  // lt = tid - 32 owns column cc = lt % 9 of rows q0, q0 + R, ... of W, element (q0, cc) of C (q0 < 9) and of X (9 <= q0 < 18)
+  const int lt = tid - 32, R = (nthr - 32) / 9;
+  const bool part = lt >= 0 && lt < 9 * R;
+  const int cc = part ? lt % 9 : 0, q0 = part ? lt / 9 : 0;
   // issue the copies of chain block fb (C lower, W) into buffer `buf`; with fx > 0 also X_fx (rows B_fx-1, columns B_fx)
   auto load_block = [&](int fb, int buf, int fx) {
-    const int c0 = cb(fb);
-    for (int e = tid; e < 81; e += nthr) { const int r = e / 9, c = e - 9 * r; if (c <= r) cp_async8(Cb[buf] + e, sup(c0 + c, c0 + r)); }
-    for (int e = tid; e < nd * 9; e += nthr) { const int q = e / 9, c = e - 9 * q; cp_async8(Wb[buf] + e, sup(sidx(q), c0 + c)); }
-    if (fx > 0) for (int e = tid; e < 81; e += nthr) { const int r = e / 9, c = e - 9 * r; cp_async8(Xb + e, sup(cb(fx - 1) + r, cb(fx) + c)); }
+    if (!part) return;
+    const int c0 = cb(fb), col = c0 + cc;
+#pragma unroll 4
+    for (int q = q0; q < nd; q += R) {
+      const int sq = sidx(q);
+      cp_async8(Wb[buf] + 9 * q + cc, sq <= col ? Sg + (size_t)sq * d + col : Sg + (size_t)col * d + sq);
+    }
+    if (q0 < 9) { if (cc <= q0) cp_async8(Cb[buf] + 9 * q0 + cc, Sg + (size_t)col * d + c0 + q0); }
+    else if (q0 < 18 && fx > 0) cp_async8(Xb + 9 * (q0 - 9) + cc, Sg + (size_t)(cb(fx - 1) + q0 - 9) * d + cb(fx) + cc);
   };
   auto scale_block = [&](int fb, int buf, int fx) {   // every thread scales what it copied
-    const int c0 = cb(fb);
-    for (int e = tid; e < 81; e += nthr) {
-      const int r = e / 9, c = e - 9 * r;
-      if (c <= r) { double v = Cb[buf][e] * scale[c0 + r] * scale[c0 + c]; if (c == r) v += lm(c0 + r); Cb[buf][e] = v; }
-    }
-    for (int e = tid; e < nd * 9; e += nthr) { const int q = e / 9, c = e - 9 * q; Wb[buf][e] *= scale[sidx(q)] * scale[c0 + c]; }
-    if (fx > 0) for (int e = tid; e < 81; e += nthr) { const int r = e / 9, c = e - 9 * r; Xb[e] *= scale[cb(fx - 1) + r] * scale[cb(fx) + c]; }
+    if (!part) return;
+    const int c0 = cb(fb), col = c0 + cc;
+    const double scol = scale[col];
+#pragma unroll 4
+    for (int q = q0; q < nd; q += R) Wb[buf][9 * q + cc] *= scale[sidx(q)] * scol;
+    if (q0 < 9) {
+      if (cc <= q0) { double v = Cb[buf][9 * q0 + cc] * scale[c0 + q0] * scol; if (cc == q0) v += lm(col); Cb[buf][9 * q0 + cc] = v; }
+    } else if (q0 < 18 && fx > 0) Xb[9 * (q0 - 9) + cc] *= scale[cb(fx - 1) + q0 - 9] * scale[cb(fx) + cc];
   };
 
 #ifdef UVS_CHOL_TIMING
@@ -506,7 +517,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       }
       CH_P(10);
     }
-    if (f > 0) { cp_async_wait(); CH_P(11); scale_block(f - 1, nxt, f); CH_P(12); }
+    else if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt, f); }
     __syncthreads();
     CH_P(13);
     CH_T(1);
