@@ -997,31 +997,57 @@ __global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
   for (int g0 = 0; g0 < nf; g0 += IMU_G) {
     const int ng = min(IMU_G, nf - g0);
     const double *R = D.rec_imu + (size_t)(f0 + g0) * REC_IMU;
-    for (int e = tid; e < ng * REC_IMU; e += TT) sm[e] = R[e];
+    for (int e = tid; e < ng * REC_IMU; e += TT) cp_async8(sm + e, R + e);
+    cp_async_wait_all();
     __syncthreads();
-    // J^T J: the 465 upper-triangle entries of every 30x30 block
-    for (int e = tid; e < ng * 465; e += TT) {
-      const int k = e / 465, t = e - 465 * k;
-      int p = (int)((61.0f - sqrtf(3721.0f - 8.0f * (float)t)) * 0.5f);   // t = p (61 - p) / 2 + (q - p)
-      while (p * (61 - p) / 2 > t) p--;
-      while ((p + 1) * (60 - p) / 2 <= t) p++;
-      const int q = p + t - p * (61 - p) / 2;
-      const double *J = sm + k * REC_IMU + 15;
-      double h = 0.0;
+    // G = [J (15 x 30) | r | 0], padded to 16 x 32: G^T G holds the upper triangle of the 30x30 block and, in column 30,
+    // the gradient J^T r.  A warp takes half of a factor's ten upper 8x8 blocks (block rows {0, 3} or {1, 2}, five
+    // blocks each) on the FP64 tensor cores: the A fragment of a column block and its B fragment are the same value
+    // G[4 ks + lane % 4][8 blk + lane / 4].
+    {
+      const int warp = tid >> 5, lane = tid & 31, fr = lane & 3, fc = lane >> 2;
+      for (int u = warp; u < 2 * ng; u += TT / 32) {
+        const int k = u >> 1, hsel = u & 1;
+        const double *r = sm + k * REC_IMU, *J = r + 15;
+        const int c0 = 15 * (D.imu_idx[f0 + g0 + k].x - fo);
+        auto frag = [&](int blk, int ks) {
+          const int row = 4 * ks + fr, col = 8 * blk + fc;
+          return row < 15 ? (col < 30 ? J[row * 30 + col] : (col == 30 ? r[row] : 0.0)) : 0.0;
+        };
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+          const int I = hsel == 0 ? (pass == 0 ? 0 : 3) : (pass == 0 ? 1 : 2);
+          double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-      for (int i = 0; i < 15; i++) h += J[i * 30 + p] * J[i * 30 + q];
-      const int c0 = 15 * (D.imu_idx[f0 + g0 + k].x - fo);
-      atomicAdd(Sg + (size_t)(c0 + p) * d + c0 + q, h);
-      if (p == q) atomicAdd(D.colsq_cam + co + c0 + p, h);
-    }
-    for (int e = tid; e < ng * 30; e += TT) {
-      const int k = e / 30, p = e - 30 * k;
-      const double *r = sm + k * REC_IMU, *J = r + 15;
-      double gg = 0.0;
+          for (int ks = 0; ks < 4; ks++) {
+            const double a = frag(I, ks);
 #pragma unroll
-      for (int i = 0; i < 15; i++) gg += J[i * 30 + p] * r[i];
-      const int c0 = 15 * (D.imu_idx[f0 + g0 + k].x - fo);
-      atomicAdd(D.gfull + co + c0 + p, gg); atomicAdd(D.gS + co + c0 + p, gg);
+            for (int Jb = 0; Jb < 4; Jb++) {
+              if (Jb < I) continue;   // uniform over the warp
+              const double bv = Jb == I ? a : frag(Jb, ks);
+              dmma884(acc[Jb], a, bv);
+            }
+          }
+          const int p = 8 * I + fc;   // row of G^T G held by this lane
+          if (p < 30) {
+#pragma unroll
+            for (int Jb = 0; Jb < 4; Jb++) {
+              if (Jb < I) continue;
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const int q = 8 * Jb + 2 * fr + e;
+                const double v = acc[Jb][e];
+                if (q < 30) {
+                  if (p <= q) {
+                    atomicAdd(Sg + (size_t)(c0 + p) * d + c0 + q, v);
+                    if (p == q) atomicAdd(D.colsq_cam + co + c0 + p, v);
+                  }
+                } else if (q == 30) { atomicAdd(D.gfull + co + c0 + p, v); atomicAdd(D.gS + co + c0 + p, v); }
+              }
+            }
+          }
+        }
+      }
     }
     __syncthreads();
   }
@@ -1038,25 +1064,40 @@ __global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
     }
     __syncthreads();
     const double *H = D.prior_H + D.priorJ_off[w], *J0 = D.prior_J + D.priorJ_off[w], *r = D.rec_prior + D.prior_off[w];
-#pragma unroll 4
-    for (int e = tid; e < n * n; e += TT) {
-      const int p = e / n, q = e - p * n;
-      const int cp = cmap[p], cq = cmap[q];
-      if (cp < 0 || cq < 0 || cp > cq) continue;
-      atomicAdd(Sg + (size_t)cp * d + cq, __ldg(H + e));
+    for (int e0 = tid; e0 < n * n; e0 += 4 * TT) {   // four loads in flight, then the four reductions
+      double hv[4];
+      int at[4];
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const int e = e0 + v * TT;
+        at[v] = -1;
+        hv[v] = 0.0;
+        if (e < n * n) {
+          const int p = e / n, q = e - p * n;
+          const int cp = cmap[p], cq = cmap[q];
+          if (cp >= 0 && cq >= 0 && cp <= cq) { at[v] = cp * d + cq; hv[v] = __ldg(H + e); }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 4; v++) if (at[v] >= 0) atomicAdd(Sg + at[v], hv[v]);
     }
-    // gradient: thread (p, part) sums every fourth row of column p (coalesced over p), eight loads in flight
-    for (int u = tid; u < 4 * n; u += TT) {
+    // gradient: thread (p, part) sums every NP-th row of column p (coalesced over p), eight loads in flight; NP is chosen
+    // so that NP n <= TT: one pass over the threads (4 n = 300 > 256 made a second, serial pass of 44 threads)
+    const int NP = max(1, min(4, TT / n));
+    for (int u = tid; u < NP * n; u += TT) {
       const int part = u / n, p = u - part * n;
       const int cp = cmap[p];
       if (cp < 0) continue;
       double g4[4] = {0, 0, 0, 0};
       int i = part;
-      for (; i + 12 < n; i += 16) {
+      for (; i + 7 * NP < n; i += 8 * NP) {
+        double v8[8];
 #pragma unroll
-        for (int v = 0; v < 4; v++) g4[v] += __ldg(J0 + (size_t)(i + 4 * v) * n + p) * r[i + 4 * v];
+        for (int v = 0; v < 8; v++) v8[v] = __ldg(J0 + (size_t)(i + v * NP) * n + p);
+#pragma unroll
+        for (int v = 0; v < 8; v++) g4[v & 3] += v8[v] * r[i + v * NP];
       }
-      for (; i < n; i += 4) g4[0] += __ldg(J0 + (size_t)i * n + p) * r[i];
+      for (; i < n; i += NP) g4[0] += __ldg(J0 + (size_t)i * n + p) * r[i];
       const double gg = (g4[0] + g4[1]) + (g4[2] + g4[3]);
       atomicAdd(D.gfull + co + cp, gg); atomicAdd(D.gS + co + cp, gg);
       if (part == 0) atomicAdd(D.colsq_cam + co + cp, __ldg(H + (size_t)p * n + p));

@@ -330,7 +330,7 @@ __device__ bool blocked_chol_solve(double *A, const CholLayout &Lo, int nthr, un
 // FLOPs.  L_w (nd x 9 per block) goes to a global scratch for the back-substitution; everything else stays on chip.
 constexpr int CH_LWG = 720;      // doubles of global scratch per chain block (L_w, nd x 9)
 
-struct ChainLayout { int o_C[2], o_W[2], o_X, o_bb, o_LL, o_z, o_LwF, o_t, total; };
+struct ChainLayout { int o_C[2], o_W[2], o_X[2], o_bb, o_LL, o_z, o_LwF, o_t, total; };
 __host__ __device__ __forceinline__ ChainLayout chain_layout(int nd, int F) {
   const CholLayout Lo = chol_layout(nd);
   ChainLayout c;
@@ -338,9 +338,9 @@ __host__ __device__ __forceinline__ ChainLayout chain_layout(int nd, int F) {
   c.o_C[0] = o; o += 82; c.o_C[1] = o; o += 82;
   const int wsz = (9 * nd + 1) & ~1;          // a W buffer: nd x 9
   c.o_W[0] = o; o += wsz; c.o_W[1] = o; o += wsz;
-  c.o_X = o; o += 82;
+  c.o_X[0] = o; o += 82; c.o_X[1] = o; o += 82;
   c.o_bb = o; o += 9 * F + (F & 1);          // rhs of every chain block
-  c.o_LL = o; o += 164 * F;                   // per block: L_c^-1 (81, lower) | L_x (81) | 2 pad
+  c.o_LL = o; o += 164 * F;                   // per block: L_c (81, lower, reciprocal diagonal) | L_x (81) | 2 pad
   c.o_z = o; o += 10 * F;                     // z_f, later y_f
   c.o_LwF = o; o += Lo.K * 96;                // L_w as tensor-core A fragments: [block row][k-step 0..2][32]
   c.o_t = o; o += 10 * F;
@@ -386,7 +386,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   const int K = Lo.K;
   double *A = smem, *Dg = smem + Lo.dbase, *bz = smem + Lo.vbase, *invd_all = bz + K * NB;
   double *Cb[2] = {smem + Ch.o_C[0], smem + Ch.o_C[1]}, *Wb[2] = {smem + Ch.o_W[0], smem + Ch.o_W[1]};
-  double *Xb = smem + Ch.o_X, *bb = smem + Ch.o_bb, *LL = smem + Ch.o_LL, *zb = smem + Ch.o_z, *LwF = smem + Ch.o_LwF, *tb = smem + Ch.o_t;
+  double *Xb[2] = {smem + Ch.o_X[0], smem + Ch.o_X[1]}, *bb = smem + Ch.o_bb, *LL = smem + Ch.o_LL, *zb = smem + Ch.o_z, *LwF = smem + Ch.o_LwF, *tb = smem + Ch.o_t;
   auto sidx = [&](int q) { return q < 6 * F ? 15 * (q / 6) + q % 6 : 15 * F + (q - 6 * F); };   // dense index -> index in S
   auto cb = [&](int f) { return 15 * f + 6; };                                                    // first column of B_f in S
   auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
@@ -401,8 +401,9 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   const int lt = tid - 32, R = (nthr - 32) / 9;
   const bool part = lt >= 0 && lt < 9 * R;
   const int cc = part ? lt % 9 : 0, q0 = part ? lt / 9 : 0;
-  // issue the copies of chain block fb (C lower, W) into buffer `buf`; with fx > 0 also X_fx (rows B_fx-1, columns B_fx)
-  auto load_block = [&](int fb, int buf, int fx) {
+  // issue the copies of chain block fb into buffer `buf`: C_fb (lower), W_fb and, for fb > 0, the coupling X_fb (rows
+  // B_fb-1, columns B_fb) - everything the factorisation of block fb needs
+  auto load_block = [&](int fb, int buf) {
     if (!part) return;
     const int c0 = cb(fb), col = c0 + cc;
 #pragma unroll 4
@@ -411,9 +412,9 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       cp_async8(Wb[buf] + 9 * q + cc, sq <= col ? Sg + (size_t)sq * d + col : Sg + (size_t)col * d + sq);
     }
     if (q0 < 9) { if (cc <= q0) cp_async8(Cb[buf] + 9 * q0 + cc, Sg + (size_t)col * d + c0 + q0); }
-    else if (q0 < 18 && fx > 0) cp_async8(Xb + 9 * (q0 - 9) + cc, Sg + (size_t)(cb(fx - 1) + q0 - 9) * d + cb(fx) + cc);
+    else if (q0 < 18 && fb > 0) cp_async8(Xb[buf] + 9 * (q0 - 9) + cc, Sg + (size_t)(cb(fb - 1) + q0 - 9) * d + col);
   };
-  auto scale_block = [&](int fb, int buf, int fx) {   // every thread scales what it copied
+  auto scale_block = [&](int fb, int buf) {   // every thread scales what it copied
     if (!part) return;
     const int c0 = cb(fb), col = c0 + cc;
     const double scol = scale[col];
@@ -421,7 +422,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     for (int q = q0; q < nd; q += R) Wb[buf][9 * q + cc] *= scale[sidx(q)] * scol;
     if (q0 < 9) {
       if (cc <= q0) { double v = Cb[buf][9 * q0 + cc] * scale[c0 + q0] * scol; if (cc == q0) v += lm(col); Cb[buf][9 * q0 + cc] = v; }
-    } else if (q0 < 18 && fx > 0) Xb[9 * (q0 - 9) + cc] *= scale[cb(fx - 1) + q0 - 9] * scale[cb(fx) + cc];
+    } else if (q0 < 18 && fb > 0) Xb[buf][9 * (q0 - 9) + cc] *= scale[cb(fb - 1) + q0 - 9] * scol;
   };
 
 #ifdef UVS_CHOL_TIMING
@@ -440,7 +441,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     const int sj = sidx(qj);
     for (int qi = qj + lane; qi < nd; qi += 32) cp_async8(slot(qi, qj), Sg + (size_t)sj * d + sidx(qi));
   }
-  load_block(F - 1, (F - 1) & 1, 0);
+  load_block(F - 1, (F - 1) & 1);
   for (int e = tid; e < K * 96; e += nthr) LwF[e] = 0.0;
   for (int c = tid; c < K * NB; c += nthr) { bz[c] = c < nd ? -scale[sidx(c)] * gS[sidx(c)] : 0.0; invd_all[c] = 1.0; }
   for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9, s = cb(f) + e - 9 * f; bb[e] = -scale[s] * gS[s]; }
@@ -450,7 +451,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     const double sj = scale[sidx(qj)];
     for (int qi = qj + lane; qi < nd; qi += 32) { double *a = slot(qi, qj); *a = scale[sidx(qi)] * sj * *a; }
   }
-  scale_block(F - 1, (F - 1) & 1, 0);
+  scale_block(F - 1, (F - 1) & 1);
   __syncthreads();
   for (int q = tid; q < nd; q += nthr) *slot(q, q) += lm(sidx(q));
   __syncthreads();
@@ -459,16 +460,25 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   // ---- chain elimination
   for (int f = F - 1; f >= 0 && !s_flag; f--) {
     const int cur = f & 1, nxt = cur ^ 1;
-    double *C = Cb[cur], *W = Wb[cur], *Li = LL + 164 * f, *Lx = Li + 81, *z = zb + 10 * f;
+    double *C = Cb[cur], *W = Wb[cur], *Lc = LL + 164 * f, *Lx = Lc + 81, *z = zb + 10 * f;
     CH_P0();
-    if (f > 0) load_block(f - 1, nxt, f);   // the next block and this block's coupling X_f land while warp 0 factors C
+    if (f > 0) load_block(f - 1, nxt);   // the next block lands while warp 0 factors this one
     CH_P(8);
     if (warp == 0) {
-      // 9x9 Cholesky in registers: lane r < 9 owns row r (same pivot chain as the 8x8 blocks)
-      const int r = lane < 9 ? lane : 8;
+      // Cholesky of the 9x9 block in registers, lane r < 9 owns row r (same pivot chain as the 8x8 blocks).  The
+      // right-hand side b_f (lane 9) and the rows of the coupling block X_f (lanes 10..18) ride along as extra rows of
+      // the factorisation: what the pivot loop leaves in them is z_f = L_c^-1 b_f and L_x = X_f L_c^-T - no explicit
+      // inverse, no separate pass.
+      const int r = lane;
       double a[9];
 #pragma unroll
-      for (int c = 0; c < 9; c++) a[c] = c <= r ? C[9 * r + c] : 0.0;
+      for (int c = 0; c < 9; c++) {
+        double v = 0.0;
+        if (lane < 9) { if (c <= lane) v = C[9 * lane + c]; }
+        else if (lane == 9) v = bb[9 * f + c];
+        else if (lane < 19 && f > 0) v = Xb[cur][9 * (lane - 10) + c];
+        a[c] = v;
+      }
       int bad = 0;
       double myinv = 1.0;
 #pragma unroll
@@ -486,60 +496,32 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       }
       if (lane < 9) {
 #pragma unroll
-        for (int c = 0; c < 9; c++) if (c <= r) C[9 * r + c] = a[c];   // L_c
-        z[lane] = myinv;                                              // parked: reciprocal diagonal
+        for (int c = 0; c < 9; c++) Lc[9 * r + c] = c < r ? a[c] : (c == r ? myinv : 0.0);   // L_c with the reciprocal diagonal
+      } else if (lane == 9) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) z[c] = a[c];
+      } else if (lane < 19) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) Lx[9 * (lane - 10) + c] = a[c];
       }
       if (lane == 0 && bad) s_flag = 1;
-      __syncwarp();
       CH_P(9);
-      // inverse of L_c, lane c: column c (forward substitution), then z = L_c^-1 b and, from the scaled X, L_x = X L_c^-T
-      {
-        const int c = r;
-        double m[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int q = 0; q < i; q++) sacc += C[9 * i + q] * m[q];
-          m[i] = i < c ? 0.0 : (i == c ? z[i] : -sacc * z[i]);
-        }
-        __syncwarp();
-        if (lane < 9) {
-#pragma unroll
-          for (int i = 0; i < 9; i++) Li[9 * i + c] = m[i];            // L_c^-1 (zeros above the diagonal)
-        }
-        __syncwarp();
-        double zz = 0.0;
-#pragma unroll
-        for (int q = 0; q < 9; q++) zz += Li[9 * r + q] * bb[9 * f + q];
-        __syncwarp();
-        if (lane < 9) z[lane] = zz;
-      }
-      CH_P(10);
     }
-    else if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt, f); }
+    else if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt); }
     __syncthreads();
     CH_P(13);
     CH_T(1);
     if (s_flag) break;
-    if (f > 0 && tid < 81) {   // L_x = X L_c^-T
-      const int r = tid / 9, c = tid - 9 * r;
-      double v = 0.0;
-#pragma unroll
-      for (int k = 0; k < 9; k++) v += Xb[9 * r + k] * Li[9 * c + k];
-      Lx[tid] = v;
-    }
-    __syncthreads();
     CH_T(2);
-    // L_w = W L_c^-T row by row; the same thread updates its row of the next block's W and the dense right-hand side
+    // L_w = W L_c^-T row by row (forward substitution); the same thread updates its row of the next block's W and the dense right-hand side
     for (int q = tid; q < nd; q += nthr) {
       double lw[9];
 #pragma unroll
-      for (int c = 0; c < 9; c++) {
-        double v = 0.0;
+      for (int c = 0; c < 9; c++) {   // forward substitution with L_c (reciprocal diagonal)
+        double v = W[9 * q + c];
 #pragma unroll
-        for (int k = 0; k < 9; k++) if (k <= c) v += W[9 * q + k] * Li[9 * c + k];
-        lw[c] = v;
+        for (int k = 0; k < 9; k++) if (k < c) v -= lw[k] * Lc[9 * c + k];
+        lw[c] = v * Lc[10 * c];
       }
       double *g = lwg + (size_t)f * CH_LWG + 9 * q;
       double bq = bz[q];
@@ -607,18 +589,23 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   if (warp == 0) {
     const int r = lane < 9 ? lane : 8;
     for (int f = 0; f < F; f++) {
-      const double *Li = LL + 164 * f, *Lx = Li + 81;
+      const double *Lc = LL + 164 * f, *Lx = Lc + 81;
       double u = tb[10 * f + r];
       if (f > 0) {
 #pragma unroll
         for (int k = 0; k < 9; k++) u -= Lx[9 * k + r] * zb[10 * (f - 1) + k];
       }
-      __syncwarp();
-      if (lane < 9) tb[10 * f + lane] = u;
-      __syncwarp();
+      // y = L_c^-T u by backward substitution, lane r owns y_r: column r of L_c in registers
+      double lcol[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) lcol[k] = Lc[9 * k + r];
       double y = 0.0;
 #pragma unroll
-      for (int k = 0; k < 9; k++) if (k >= r) y += Li[9 * k + r] * tb[10 * f + k];
+      for (int k = 8; k >= 0; k--) {
+        const double yk = __shfl_sync(0xffffffffu, u * lcol[k], k);   // lane k: u_k / L_kk
+        if (r == k) y = yk;
+        if (r < k) u -= lcol[k] * yk;
+      }
       if (lane < 9) zb[10 * f + lane] = y;   // y_f replaces z_f
       __syncwarp();
     }
