@@ -162,6 +162,74 @@ def test_full_solve_parity(solver, windows, opts, cfg):
     assert np.median(np.abs(w.ortho - ref.ortho)) < STEP_TOL
 
 
+def _quat_rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _reanchor_at_last_frame(w0, every=3):
+    """Every `every`-th point is re-anchored at its LAST observing frame, so its projection factors have
+    frame_i > frame_j (the reference never builds these - imu_i is the start frame - but the C ABI takes any pair;
+    the direct-term kernel keeps a separate fragment mapping for them).  The inverse depth is recomputed in the new
+    anchor's camera (projection_factor.cpp:44-49 run forward), so the window stays geometrically consistent."""
+    w = w0.copy()
+    Ric, tic = _quat_rot(w.ex_pose[3:]), w.ex_pose[:3]
+    for k in range(0, w.n_points, every):
+        idx = np.nonzero(w.proj_point == k)[0]
+        if idx.size < 2:
+            continue
+        last = idx[np.argmax(w.proj_frame_j[idx])]
+        a_new, a_old = int(w.proj_frame_j[last]), int(w.proj_frame_i[last])
+        obs_new, obs_old = w.proj_pts_j[last].copy(), w.proj_pts_i[last].copy()
+        Ro, po = _quat_rot(w.pose[a_old, 3:]), w.pose[a_old, :3]
+        Rn, pn = _quat_rot(w.pose[a_new, 3:]), w.pose[a_new, :3]
+        p_w = Ro @ (Ric @ (obs_old / w.inv_depth[k]) + tic) + po
+        p_c = Ric.T @ (Rn.T @ (p_w - pn) - tic)
+        w.inv_depth[k] = 1.0 / p_c[2]
+        w.proj_frame_i[idx] = a_new
+        w.proj_pts_i[idx] = obs_new
+        w.proj_frame_j[last] = a_old
+        w.proj_pts_j[last] = obs_old
+    assert (w.proj_frame_i > w.proj_frame_j).any()
+    return w
+
+
+def test_anchor_frame_after_observing_frame(solver, windows, opts):
+    """projection factors with frame_i > frame_j: sweep, first step and the full solve against the oracle"""
+    w0 = _reanchor_at_last_frame(windows["C1"])
+    solver.upload([w0.copy()], opts)
+    r, J = solver.eval("proj", local=True)
+    r0, J0, _ = orc.eval_factors(w0, opts, orc.F_PROJ, local=True)
+    assert rel_err_rows(r, r0) < RTOL and rel_err_rows(J, J0) < RTOL
+    w = w0.copy()
+    fs = orc.first_step(w, opts, radius=1e4)
+    o = uvs_b200.default_options(max_num_iterations=1, fixed_iterations=1)
+    solver.upload([w], o)
+    sm = solver.solve()[0]
+    assert abs(sm.initial_cost - fs["cost"]) <= 1e-9 * abs(fs["cost"])
+    rel = (sm.initial_cost - sm.cost[1]) / fs["model_change"]
+    assert abs(sm.relative_decrease[1] - rel) < 1e-6 * max(1.0, abs(rel))
+    if sm.step_accepted[1] == 1:
+        solver.download()
+        delta = fs["delta"]
+        for f in range(w.n_frames):
+            assert np.abs(w.pose[f] - orc.pose_plus(w0.pose[f], delta[15 * f:15 * f + 6])).max() < STEP_TOL
+    w, ref = w0.copy(), w0.copy()
+    sm0 = orc.solve(ref, opts)
+    solver.upload([w], opts)
+    sm = solver.solve()[0]
+    solver.download()
+    n = sm.num_iterations
+    assert n == sm0.num_iterations
+    assert [sm.step_accepted[i] for i in range(n)] == [sm0.step_accepted[i] for i in range(n)]
+    for i in range(n):
+        assert abs(sm.cost[i] - sm0.cost[i]) <= 1e-6 * abs(sm0.cost[i]) + 1e-9, (i, sm.cost[i], sm0.cost[i])
+    dp, dq = _tangent_delta(ref, w)
+    assert dp < STEP_TOL and dq < STEP_TOL
+
+
 def test_solve_with_extrinsic(solver, opts):
     w = gw.make_window("C1", estimate_extrinsic=1)
     ref = w.copy()

@@ -813,7 +813,9 @@ int uvs_batch_solve(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOptions *opt
 int uvs_batch_solve_pipelined(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOptions *opts, UvsSummary *summaries, int32_t n_groups) {
   if (!h || B <= 0 || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_batch_solve_pipelined: bad arguments");
   if (h->nranks > 1) return fail(h, UVS_ERR_UNSUPPORTED, "uvs_batch_solve_pipelined: not available in factor-parallel mode");
-  int G = n_groups > 0 ? n_groups : (B >= 512 ? 4 : (B >= 128 ? 2 : 1));
+  // every sub-batch pays the fixed latency of an LM solve (~20 dependent launches per iteration) again, so few groups:
+  // measured on B200, 1184 C2 windows: 1 group 27.8 ms, 2: 23.0, 3: 22.8, 4: 24.1, 6: 27.0, 8: 28.7 (tools/e2e_probe.py)
+  int G = n_groups > 0 ? n_groups : (B >= 768 ? 3 : (B >= 128 ? 2 : 1));
   G = std::min(G, B);
   if (G <= 1) return uvs_batch_solve(h, B, w, opts, summaries);
   while ((int)h->children.size() < G) {

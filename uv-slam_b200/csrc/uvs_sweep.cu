@@ -91,7 +91,7 @@ __device__ __forceinline__ void flush_tile(const double *tile, const unsigned ch
 
 // ------------------------------------------------------------------------------------------------
 template <bool kJac, bool kTd, bool kCeres>
-__global__ void __launch_bounds__(NT, 4) k_proj(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+__global__ void __launch_bounds__(NT, 5) k_proj(Dev D, Params P, int mode, int cand, double *__restrict__ out,
                                              double *__restrict__ res_out, double *cost, int cost_stride) {
   constexpr int REC = kCeres ? (kTd ? CREC_PROJ_TD : CREC_PROJ) : (kTd ? REC_PROJ_TD : REC_PROJ);
   constexpr int PW = kCeres ? 7 : 6;
@@ -247,7 +247,7 @@ struct LineVpSink {
 };
 
 template <bool kJac>
-__global__ void __launch_bounds__(NT, 3) k_line_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out_line,
+__global__ void __launch_bounds__(NT, 4) k_line_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out_line,
                                                 double *__restrict__ out_vp, double *cost, int cost_stride) {
   extern __shared__ double smem[];
   double *tile = smem;                                        // [NT][REC_LINE + 1]
