@@ -15,6 +15,8 @@
 // observations are read once; state blocks (a few KB per window) come through L1/L2; every CTA
 // stages its tile of records in shared memory and writes it back as one contiguous, fully
 // coalesced chunk.
+#include <cstdlib>
+
 #include "uvs_device.cuh"
 #include "uvs_factors.cuh"
 #include "uvs_imu.cuh"
@@ -90,8 +92,8 @@ __device__ __forceinline__ void flush_tile(const double *tile, const unsigned ch
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool kJac, bool kTd, bool kCeres>
-__global__ void __launch_bounds__(NT, 5) k_proj(Dev D, Params P, int mode, int cand, double *__restrict__ out,
+template <bool kJac, bool kTd, bool kCeres, int kOcc = 4>
+__global__ void __launch_bounds__(NT, kOcc) k_proj(Dev D, Params P, int mode, int cand, double *__restrict__ out,
                                              double *__restrict__ res_out, double *cost, int cost_stride) {
   constexpr int REC = kCeres ? (kTd ? CREC_PROJ_TD : CREC_PROJ) : (kTd ? REC_PROJ_TD : REC_PROJ);
   constexpr int PW = kCeres ? 7 : 6;
@@ -246,8 +248,8 @@ struct LineVpSink {
   __device__ __forceinline__ void partial(int k, d3 dn, d3 du) { ln.partial(k, dn, du); if (has_vp) vp.partial(k, dn, du); }
 };
 
-template <bool kJac>
-__global__ void __launch_bounds__(NT, 4) k_line_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out_line,
+template <bool kJac, int kOcc = 3>
+__global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out_line,
                                                 double *__restrict__ out_vp, double *cost, int cost_stride) {
   extern __shared__ double smem[];
   double *tile = smem;                                        // [NT][REC_LINE + 1]
@@ -489,6 +491,12 @@ template <int REC>
 static size_t tile_bytes() { return (size_t)NT * (REC + 1) * sizeof(double) + NT; }
 
 // tiles of the widest records exceed the 48 KB default of dynamic shared memory
+// developer switch: resident CTAs per SM the register allocation of a sweep kernel is bounded for (A/B runs)
+static int sweep_occ(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
 static void raise_smem_limits() {
   static bool done = false;
   if (done) return;
@@ -497,6 +505,7 @@ static void raise_smem_limits() {
   cudaFuncSetAttribute(k_proj<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<CREC_PROJ>());
   cudaFuncSetAttribute(k_proj<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<REC_PROJ_TD>());
   cudaFuncSetAttribute(k_proj<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<REC_PROJ>());
+  cudaFuncSetAttribute(k_proj<true, false, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<REC_PROJ>());
 }
 
 int launch_proj(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int cand, double *out, double *res_out,
@@ -515,6 +524,7 @@ int launch_proj(const Dev &D, const Params &P, bool jac, bool ceres, int mode, i
     else k_proj<true, false, true><<<grid, NT, tile_bytes<CREC_PROJ>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
   } else {
     if (td) k_proj<true, true, false><<<grid, NT, tile_bytes<REC_PROJ_TD>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
+    else if (sweep_occ("UVS_PROJ_OCC", 4) == 5) k_proj<true, false, false, 5><<<grid, NT, tile_bytes<REC_PROJ>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
     else k_proj<true, false, false><<<grid, NT, tile_bytes<REC_PROJ>(), st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
   }
   return 1;
@@ -545,7 +555,8 @@ int launch_line_vp(const Dev &D, const Params &P, bool jac, int mode, int cand, 
   if (D.nLobs == 0) return 0;
   const int grid = cdiv(D.nLobs, NT);
   const size_t smem = (size_t)NT * (REC_LINE + 1 + REC_VP + 1) * sizeof(double) + NT * sizeof(int) + NT;
-  if (jac) k_line_vp<true><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  if (jac && sweep_occ("UVS_LINE_OCC", 3) == 4) k_line_vp<true, 4><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  else if (jac) k_line_vp<true><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
   else k_line_vp<false><<<grid, NT, 0, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
   return 1;
 }
