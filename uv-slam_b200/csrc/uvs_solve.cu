@@ -470,15 +470,13 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       // the factorisation: what the pivot loop leaves in them is z_f = L_c^-1 b_f and L_x = X_f L_c^-T - no explicit
       // inverse, no separate pass.
       const int r = lane;
+      // one source / destination row per lane, no divergence: C row (entries c <= lane), b_f, X_f row, or nothing
+      const double *src = lane < 9 ? C + 9 * lane : (lane == 9 ? bb + 9 * f : Xb[cur] + 9 * (lane - 10));
+      const int cnt = lane < 9 ? lane + 1 : ((lane == 9 || (lane < 19 && f > 0)) ? 9 : 0);
+      double *dst = lane < 9 ? Lc + 9 * lane : (lane == 9 ? z : Lx + 9 * (lane - 10));
       double a[9];
 #pragma unroll
-      for (int c = 0; c < 9; c++) {
-        double v = 0.0;
-        if (lane < 9) { if (c <= lane) v = C[9 * lane + c]; }
-        else if (lane == 9) v = bb[9 * f + c];
-        else if (lane < 19 && f > 0) v = Xb[cur][9 * (lane - 10) + c];
-        a[c] = v;
-      }
+      for (int c = 0; c < 9; c++) a[c] = c < cnt ? src[c] : 0.0;
       int bad = 0;
       double myinv = 1.0;
 #pragma unroll
@@ -494,15 +492,9 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
           a[q] -= a[p] * lq;
         }
       }
-      if (lane < 9) {
+      if (lane < 19) {   // L_c with the reciprocal diagonal | z_f | L_x
 #pragma unroll
-        for (int c = 0; c < 9; c++) Lc[9 * r + c] = c < r ? a[c] : (c == r ? myinv : 0.0);   // L_c with the reciprocal diagonal
-      } else if (lane == 9) {
-#pragma unroll
-        for (int c = 0; c < 9; c++) z[c] = a[c];
-      } else if (lane < 19) {
-#pragma unroll
-        for (int c = 0; c < 9; c++) Lx[9 * (lane - 10) + c] = a[c];
+        for (int c = 0; c < 9; c++) dst[c] = lane < 9 ? (c < r ? a[c] : (c == r ? myinv : 0.0)) : a[c];
       }
       if (lane == 0 && bad) s_flag = 1;
       CH_P(9);
@@ -578,12 +570,17 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   CH_T(5);
 
   // ---- back-substitution of the chain: t_f = z_f - L_w^T y_D for all blocks at once, then y_f = L_c^-T (t_f - L_x^T y_f-1)
-  for (int e = tid; e < 9 * F; e += nthr) {
+  for (int base = 0; base < 9 * F; base += nthr / 2) {   // two threads per entry, each half of the dot product
+    const int e = base + (tid >> 1), half = tid & 1;
     const int f = e / 9, c = e - 9 * f;
-    const double *g = lwg + (size_t)f * CH_LWG + c;
-    double t = zb[10 * f + c];
-    for (int q = 0; q < nd; q++) t -= g[9 * q] * bz[q];
-    tb[10 * f + c] = t;
+    double t = 0.0;
+    if (e < 9 * F) {
+      const double *g = lwg + (size_t)f * CH_LWG + c;
+      const int qm = (nd + 1) >> 1;
+      for (int q = half ? qm : 0; q < (half ? nd : qm); q++) t -= g[9 * q] * bz[q];
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    if (e < 9 * F && half == 0) tb[10 * f + c] = zb[10 * f + c] + t;
   }
   __syncthreads();
   if (warp == 0) {
