@@ -457,6 +457,18 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   __syncthreads();
 
   CH_T(0);
+  // dense part -= L_w L_w^T on the tensor cores (three k-steps of four columns; columns 9..11 are zero), 8x8 blocks
+  // first, first + step, ... of the lower triangle for this warp.  The update of block f + 1 runs on warps 1.. while
+  // warp 0 factors block f (it only touches the dense part and the fragments written before the last barrier).
+  auto dense_update = [&](int first, int step) {
+    for (int blk = first; blk < K * (K + 1) / 2; blk += step) {
+      const int pr = s_pair[blk], I = pr >> 8, J = pr & 255;
+      double a[3], b[3];
+#pragma unroll
+      for (int s = 0; s < 3; s++) { a[s] = LwF[(I * 3 + s) * 32 + lane]; b[s] = LwF[(J * 3 + s) * 32 + lane]; }
+      frag_block_sub(A, Dg, K, Lo.vr, I, J, lane, a, b, 3);
+    }
+  };
   // ---- chain elimination
   for (int f = F - 1; f >= 0 && !s_flag; f--) {
     const int cur = f & 1, nxt = cur ^ 1;
@@ -499,7 +511,10 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       if (lane == 0 && bad) s_flag = 1;
       CH_P(9);
     }
-    else if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt); }
+    else {
+      if (f < F - 1) dense_update(warp - 1, nw - 1);
+      if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt); }
+    }
     __syncthreads();
     CH_P(13);
     CH_T(1);
@@ -552,18 +567,11 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     }
     __syncthreads();
     CH_T(3);
-    // dense part -= L_w L_w^T on the tensor cores (three k-steps of four columns; columns 9..11 are zero)
-    for (int blk = warp; blk < K * (K + 1) / 2; blk += nw) {
-      const int pr = s_pair[blk], I = pr >> 8, J = pr & 255;
-      double a[3], b[3];
-#pragma unroll
-      for (int s = 0; s < 3; s++) { a[s] = LwF[(I * 3 + s) * 32 + lane]; b[s] = LwF[(J * 3 + s) * 32 + lane]; }
-      frag_block_sub(A, Dg, K, Lo.vr, I, J, lane, a, b, 3);
-    }
-    __syncthreads();
-    CH_T(4);
   }
   if (s_flag) return false;
+  dense_update(warp, nw);   // the update of block 0 has no factorisation to hide behind: all warps
+  __syncthreads();
+  CH_T(4);
 
   // ---- dense part
   if (!blocked_chol_solve(A, Lo, nthr, s_pair, s_flag)) return false;
