@@ -24,6 +24,7 @@ KEYS = {
     "l1tex_throughput_pct": "l1tex__throughput.avg.pct_of_peak_sustained_active",
     "inst_executed": "smsp__inst_executed.sum",
     "tensor_inst": "sm__inst_executed_pipe_tensor.sum",
+    "tensor_pipe_dmma_pct": "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
 }
 UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
 

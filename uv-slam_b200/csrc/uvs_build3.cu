@@ -868,6 +868,13 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
 constexpr int SUP = 3;        // a warp owns a SUP x SUP block of 8x8 tiles of the rank update
 constexpr int SUP_SETS = 2;   // and at most this many of them (8 warps x 2 covers the 10 blocks of 12 camera blocks)
 
+// cover of the 45 upper 8x8 tiles of a 9 x 9 tile grid by eight units {first row tile, first column tile, 3x3 mask}:
+// 2x3 rectangles, the three diagonal triangles and one 1x3 strip - loads 12, 12, 12, 9 tiles on the four schedulers
+__constant__ unsigned short c_units9[8][3] = {
+    {0, 3, 0x03f}, {0, 6, 0x03f}, {2, 6, 0x03f}, {4, 6, 0x03f},   // rows 0-1 x cols 3-5 | rows 0-1 x 6-8 | rows 2-3 x 6-8 | rows 4-5 x 6-8
+    {0, 0, 0x137}, {3, 3, 0x137}, {6, 6, 0x137},                  // upper triangles of tiles 0-2, 3-5, 6-8
+    {2, 3, 0x007}};                                                // row 2 x cols 3-5
+
 // Schur terms of one window as a dense rank update over its landmark columns, then IMU blocks and the prior.
 //   [V | gsch] = Y [Y | z]^T  on the FP64 tensor cores: the columns (camera rows + the z row) are streamed chunk by
 //   chunk with TMA bulk copies (cp.async.bulk + mbarrier, NSTAGE in flight); warps own 24 x 24 blocks of the upper
@@ -904,14 +911,28 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
     const int zr = mp - 2;                           // the z row of a column (rows m .. zr-1 are zero padding)
     const int ntr = (zr + 1 + 7) / 8;                // 8-row tiles over the camera rows and the z row
     const int nsr = (ntr + SUP - 1) / SUP, nsuper = nsr * (nsr + 1) / 2;
-    int sa[SUP_SETS], sb[SUP_SETS];
-    bool has[SUP_SETS];
+    // work units: first row tile, first column tile and a 3 x 3 mask of 8x8 tiles (bit 3 u + v).  General shapes: SUP x SUP
+    // super-blocks of the upper triangle in rank order.  The reference's window (nine row tiles: 11 frames x 6 + z) gets a
+    // hand-balanced cover of the 45 upper tiles by EIGHT units (c_units9: seven of six tiles, one of three) - six
+    // super-blocks of 6 / 9 tiles left two of the eight warps idle and two of the four schedulers with twice the DMMAs.
+    int ta[SUP_SETS], tb[SUP_SETS];
+    unsigned msk[SUP_SETS];
 #pragma unroll
     for (int i = 0; i < SUP_SETS; i++) {
-      const int idx = warp + i * (WT / 32);
-      has[i] = idx < nsuper;
-      sa[i] = sb[i] = 0;
-      if (has[i]) unrank_key(idx, sa[i], sb[i]);
+      ta[i] = tb[i] = 0; msk[i] = 0;
+      if (ntr == 9 && WT == 256) {
+        if (i == 0) { ta[0] = c_units9[warp][0]; tb[0] = c_units9[warp][1]; msk[0] = c_units9[warp][2]; }
+      } else {
+        const int idx = warp + i * (WT / 32);
+        if (idx < nsuper) {
+          int sa, sb;
+          unrank_key(idx, sa, sb);
+          ta[i] = SUP * sa; tb[i] = SUP * sb;
+          for (int u = 0; u < SUP; u++)
+            for (int v = 0; v < SUP; v++)
+              if (!(sa == sb && v < u) && ta[i] + u < ntr && tb[i] + v < ntr) msk[i] |= 1u << (3 * u + v);
+        }
+      }
     }
     double acc[SUP_SETS][SUP][SUP][2];
 #pragma unroll
@@ -934,22 +955,23 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
       }
 #pragma unroll
       for (int i = 0; i < SUP_SETS; i++) {
-        if (!has[i]) continue;
-        const bool diag = sa[i] == sb[i];
-        const double *ya = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * SUP * sa[i];
-        const double *yb = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * SUP * sb[i];
+        const unsigned mk = msk[i];
+        if (!mk) continue;
+        const unsigned rowm = (mk & 7u ? 1u : 0u) | (mk & 0x38u ? 2u : 0u) | (mk & 0x1c0u ? 4u : 0u), colm = (mk | mk >> 3 | mk >> 6) & 7u;
+        const double *ya = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * ta[i];
+        const double *yb = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * tb[i];
         for (int k0 = 0; k0 < c1; k0 += 4) {
           double fa[SUP], fb[SUP];
 #pragma unroll
-          for (int u = 0; u < SUP; u++) { fa[u] = ya[(size_t)k0 * mp + 8 * u]; fb[u] = yb[(size_t)k0 * mp + 8 * u]; }
+          for (int u = 0; u < SUP; u++) {
+            fa[u] = (rowm >> u & 1u) ? ya[(size_t)k0 * mp + 8 * u] : 0.0;
+            fb[u] = (colm >> u & 1u) ? yb[(size_t)k0 * mp + 8 * u] : 0.0;
+          }
 #pragma unroll
           for (int u = 0; u < SUP; u++)
 #pragma unroll
-            for (int v = 0; v < SUP; v++) {
-              if (diag && v < u) continue;                                   // lower-triangle tile
-              if (SUP * sa[i] + u >= ntr || SUP * sb[i] + v >= ntr) continue;   // past the last row tile
-              dmma884(acc[i][u][v], fa[u], fb[v]);
-            }
+            for (int v = 0; v < SUP; v++)
+              if (mk >> (3 * u + v) & 1u) dmma884(acc[i][u][v], fa[u], fb[v]);   // uniform over the warp
         }
       }
       __syncthreads();
@@ -959,17 +981,17 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
     auto grow = [&](int e) { const int a = e / 6; return (a < F ? 15 * a : 15 * F) + (e - 6 * a); };
 #pragma unroll
     for (int i = 0; i < SUP_SETS; i++) {
-      if (!has[i]) continue;
+      if (!msk[i]) continue;
 #pragma unroll
       for (int u = 0; u < SUP; u++)
 #pragma unroll
         for (int v = 0; v < SUP; v++) {
-          if (sa[i] == sb[i] && v < u) continue;
-          const int row = 8 * (SUP * sa[i] + u) + (lane >> 2);
+          if (!(msk[i] >> (3 * u + v) & 1u)) continue;
+          const int row = 8 * (ta[i] + u) + (lane >> 2);
           if (row >= m) continue;
 #pragma unroll
           for (int e = 0; e < 2; e++) {
-            const int col = 8 * (SUP * sb[i] + v) + 2 * (lane & 3) + e;
+            const int col = 8 * (tb[i] + v) + 2 * (lane & 3) + e;
             if (col < m) { if (row <= col) atomicAdd(Sg + (size_t)grow(row) * d + grow(col), -acc[i][u][v][e]); }
             else if (col == zr) atomicAdd(D.gS + co + grow(row), -acc[i][u][v][e]);
           }
