@@ -825,6 +825,16 @@ int uvs_batch_solve_pipelined(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOp
     h->children.push_back(c);
   }
   h->have_window = false;   // one-shot service call: the parent keeps no batch
+  // sub-batch boundaries: the first group gets `first` times the share of the others (the GPU idles until its data has
+  // landed, so a smaller first group starts the device earlier; UVS_PIPE_FIRST overrides for experiments)
+  std::vector<int> bounds(G + 1, 0);
+  {
+    static const char *env = std::getenv("UVS_PIPE_FIRST");
+    const double first = env ? std::atof(env) : (G >= 3 ? 0.6 : 1.0);   // measured (tools/e2e_split.py): G = 3: 22.84 -> 22.44 ms, G = 2: no gain
+    const double unit = (double)B / (first + (G - 1));
+    for (int g = 1; g < G; g++) bounds[g] = std::min(B, std::max(g, (int)(unit * (first + (g - 1)) + 0.5)));
+    bounds[G] = B;
+  }
   std::vector<int> rcs(G, UVS_OK);
   std::vector<std::thread> workers;
   const UvsOptions o = opts ? *opts : h->opts;
@@ -833,7 +843,7 @@ int uvs_batch_solve_pipelined(UvsHandle *h, int32_t B, UvsWindow *w, const UvsOp
   auto since = [t_call] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
   for (int g = 0; g < G; g++) {
     UvsHandle *c = h->children[g];
-    const int lo = (int)((long long)B * g / G), hi = (int)((long long)B * (g + 1) / G);
+    const int lo = bounds[g], hi = bounds[g + 1];
     // uploads go one after another (they share the host cores and the PCIe link); each sub-batch starts its LM loop
     // on its own stream as soon as its data has landed, overlapping the next sub-batch's pack + H2D
     rcs[g] = upload_enqueue(c, hi - lo, w + lo, &o);
