@@ -868,6 +868,37 @@ __global__ void __launch_bounds__(128) k_direct_fused(Dev D, DirectLists L, int 
 constexpr int SUP = 3;        // a warp owns a SUP x SUP block of 8x8 tiles of the rank update
 constexpr int SUP_SETS = 2;   // and at most this many of them (8 warps x 2 covers the 10 blocks of 12 camera blocks)
 
+// one chunk of the rank update for a 3 x 3 unit of 8x8 tiles: acc[u][v] += Y_rows(u) Y_rows(v)^T over c1 columns
+template <unsigned MK>
+__device__ __forceinline__ void rank_chunk(double (&acc)[SUP][SUP][2], const double *ya, const double *yb, int c1, int mp) {
+  constexpr unsigned rowm = (MK & 7u ? 1u : 0u) | (MK & 0x38u ? 2u : 0u) | (MK & 0x1c0u ? 4u : 0u), colm = (MK | MK >> 3 | MK >> 6) & 7u;
+  for (int k0 = 0; k0 < c1; k0 += 4) {
+    double fa[SUP], fb[SUP];
+#pragma unroll
+    for (int u = 0; u < SUP; u++) {
+      if (rowm >> u & 1u) fa[u] = ya[(size_t)k0 * mp + 8 * u];
+      if (colm >> u & 1u) fb[u] = yb[(size_t)k0 * mp + 8 * u];
+    }
+#pragma unroll
+    for (int u = 0; u < SUP; u++)
+#pragma unroll
+      for (int v = 0; v < SUP; v++)
+        if (MK >> (3 * u + v) & 1u) dmma884(acc[u][v], fa[u], fb[v]);
+  }
+}
+__device__ __forceinline__ void rank_chunk_any(unsigned mk, double (&acc)[SUP][SUP][2], const double *ya, const double *yb, int c1, int mp) {
+  for (int k0 = 0; k0 < c1; k0 += 4) {
+    double fa[SUP], fb[SUP];
+#pragma unroll
+    for (int u = 0; u < SUP; u++) { fa[u] = ya[(size_t)k0 * mp + 8 * u]; fb[u] = yb[(size_t)k0 * mp + 8 * u]; }
+#pragma unroll
+    for (int u = 0; u < SUP; u++)
+#pragma unroll
+      for (int v = 0; v < SUP; v++)
+        if (mk >> (3 * u + v) & 1u) dmma884(acc[u][v], fa[u], fb[v]);
+  }
+}
+
 // cover of the 45 upper 8x8 tiles of a 9 x 9 tile grid by eight units {first row tile, first column tile, 3x3 mask}:
 // 2x3 rectangles, the three diagonal triangles and one 1x3 strip - loads 12, 12, 12, 9 tiles on the four schedulers
 __constant__ unsigned short c_units9[8][3] = {
@@ -957,21 +988,16 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
       for (int i = 0; i < SUP_SETS; i++) {
         const unsigned mk = msk[i];
         if (!mk) continue;
-        const unsigned rowm = (mk & 7u ? 1u : 0u) | (mk & 0x38u ? 2u : 0u) | (mk & 0x1c0u ? 4u : 0u), colm = (mk | mk >> 3 | mk >> 6) & 7u;
         const double *ya = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * ta[i];
         const double *yb = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * tb[i];
-        for (int k0 = 0; k0 < c1; k0 += 4) {
-          double fa[SUP], fb[SUP];
-#pragma unroll
-          for (int u = 0; u < SUP; u++) {
-            fa[u] = (rowm >> u & 1u) ? ya[(size_t)k0 * mp + 8 * u] : 0.0;
-            fb[u] = (colm >> u & 1u) ? yb[(size_t)k0 * mp + 8 * u] : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < SUP; u++)
-#pragma unroll
-            for (int v = 0; v < SUP; v++)
-              if (mk >> (3 * u + v) & 1u) dmma884(acc[i][u][v], fa[u], fb[v]);   // uniform over the warp
+        // the tile mask is uniform over the warp: the common masks get loops with exactly their loads and DMMAs compiled
+        // in (a predicated-off DMMA still takes its issue slot and tensor-pipe cycles)
+        switch (mk) {
+          case 0x03fu: rank_chunk<0x03fu>(acc[i], ya, yb, c1, mp); break;
+          case 0x137u: rank_chunk<0x137u>(acc[i], ya, yb, c1, mp); break;
+          case 0x007u: rank_chunk<0x007u>(acc[i], ya, yb, c1, mp); break;
+          case 0x1ffu: rank_chunk<0x1ffu>(acc[i], ya, yb, c1, mp); break;
+          default: rank_chunk_any(mk, acc[i], ya, yb, c1, mp); break;
         }
       }
       __syncthreads();
