@@ -143,11 +143,16 @@ __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
         double ji[12], jj[12];
 #pragma unroll
         for (int c = 0; c < 6; c++) { const double2 a = r2[1 + c], b2 = r2[7 + c]; ji[2 * c] = a.x; ji[2 * c + 1] = a.y; jj[2 * c] = b2.x; jj[2 * c + 1] = b2.y; }
+        double u[6];
 #pragma unroll
         for (int c = 0; c < 6; c++) {
           wa[c] += ji[c] * j0 + ji[6 + c] * j1;
-          const double u = jj[c] * j0 + jj[6 + c] * j1;
-          if (first) u0[c] = u; else yj[c] = u;   // later observations of this lane: parked unscaled, rescaled below
+          u[c] = jj[c] * j0 + jj[6 + c] * j1;
+          if (first) u0[c] = u[c];
+        }
+        if (!first) {   // later observations of this lane: parked unscaled, rescaled below (a block is 48 bytes, 16-byte aligned)
+          double2 *y2 = reinterpret_cast<double2 *>(yj);
+          y2[0] = make_double2(u[0], u[1]); y2[1] = make_double2(u[2], u[3]); y2[2] = make_double2(u[4], u[5]);
         }
         if (ex) {
 #pragma unroll
@@ -173,14 +178,24 @@ __global__ void __launch_bounds__(128) k_core_points(Dev D, Params P, Stash S) {
   const double sh = rsqrt(Et + D2);
   const double ysc = sk * sh;
   for (int f = sub; f < n; f += LPP) {
-    double *yj = Y + 6 * (D.proj_idx[f0 + f].y - fo);
+    double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * (D.proj_idx[f0 + f].y - fo));
+    if (f < LPP) {
+      y2[0] = make_double2(ysc * u0[0], ysc * u0[1]); y2[1] = make_double2(ysc * u0[2], ysc * u0[3]); y2[2] = make_double2(ysc * u0[4], ysc * u0[5]);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 6; c++) yj[c] = ysc * (f < LPP ? u0[c] : yj[c]);
+      for (int c = 0; c < 3; c++) { const double2 v = y2[c]; y2[c] = make_double2(ysc * v.x, ysc * v.y); }
+    }
   }
   if (sub != 0) return;
   const int bi = D.proj_idx[f0].x - fo;
+  {
+    double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * bi);
+    y2[0] = make_double2(ysc * wa[0], ysc * wa[1]); y2[1] = make_double2(ysc * wa[2], ysc * wa[3]); y2[2] = make_double2(ysc * wa[4], ysc * wa[5]);
+  }
+  if (ex) {
 #pragma unroll
-  for (int c = 0; c < 6; c++) { Y[6 * bi + c] = ysc * wa[c]; if (ex) Y[6 * F + c] = ysc * we[c]; }
+    for (int c = 0; c < 6; c++) Y[6 * F + c] = ysc * we[c];
+  }
   Y[mp - 2] = sk * gk * sh;
   ph[0] = sk; ph[1] = sh; ph[2] = D2;
   atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fabs(gk));
@@ -345,24 +360,30 @@ __global__ void __launch_bounds__(128) k_core_lines(Dev D, Params P, Stash S) {
       jp[0][2 * c] = a.x; jp[0][2 * c + 1] = a.y; jp[1][2 * c] = b2.x; jp[1][2 * c + 1] = b2.y;
     }
 #pragma unroll
-    for (int p = 0; p < 6; p++) {
-      const double a0 = jp[0][p], a1 = jp[1][p], a2 = q ? q[1 + p] : 0.0;
-      double W4[4];
+    for (int p = 0; p < 6; p += 2) {   // two rows at a time: the 48-byte block of a column is written as three 128-bit words
+      double tt[2][4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
+      for (int h = 0; h < 2; h++) {
+        const double a0 = jp[0][p + h], a1 = jp[1][p + h], a2 = q ? q[1 + p + h] : 0.0;
+        double W4[4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        double tt = 0.0;
+        for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
 #pragma unroll
-        for (int k = 0; k <= c; k++) tt += W4[k] * Li[c][k];
-        Yf[c * mp + p] = tt;
+        for (int c = 0; c < 4; c++) {
+          double t1 = 0.0;
+#pragma unroll
+          for (int k = 0; k <= c; k++) t1 += W4[k] * Li[c][k];
+          tt[h][c] = t1;
+        }
       }
+#pragma unroll
+      for (int c = 0; c < 4; c++) *reinterpret_cast<double2 *>(Yf + c * mp + p) = make_double2(tt[0][c], tt[1][c]);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// back-substitution, one thread per landmark
+// back-substitution
 // The columns of a warp's eight points are contiguous when they belong to one window: the warp copies them into shared
 // memory with coalesced 16-byte asynchronous copies and the lane groups (4 lanes per point) read their blocks from
 // there; warps that straddle windows read global memory.
@@ -447,17 +468,22 @@ __global__ void __launch_bounds__(128) k_back_lines(Dev D, Stash S) {
       const int F = D.frame_off[w + 1] - D.frame_off[w];
       const double *dl = D.delta_cam + D.cam_off[w];
       double tz[4], yk[4];
-      // the lanes split the camera blocks of  u = Y^T delta_c
+      // the lanes split the camera blocks of  u = Y^T delta_c: a block of a column is 48 bytes, 16-byte aligned -> three
+      // 128-bit loads; the deltas of the lane's blocks are loaded once for the four columns (the kernel sat at 86 % L1 throughput)
+      double u4[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int b = sub; b < F; b += LPL) {
+        double dv[6];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const double *y = Y + c * mp;
-        double u = 0.0;
-        for (int b = sub; b < F; b += LPL) {
+        for (int p = 0; p < 6; p++) dv[p] = dl[15 * b + p];
 #pragma unroll
-          for (int p = 0; p < 6; p++) u += y[6 * b + p] * dl[15 * b + p];
+        for (int c = 0; c < 4; c++) {
+          const double2 *y2 = reinterpret_cast<const double2 *>(Y + c * mp + 6 * b);
+          const double2 a0 = y2[0], a1 = y2[1], a2 = y2[2];
+          u4[c] += a0.x * dv[0] + a0.y * dv[1] + a1.x * dv[2] + a1.y * dv[3] + a2.x * dv[4] + a2.y * dv[5];
         }
-        tz[c] = y[mp - 2] + group_sum<LPL>(gmask, u);   // z + u
       }
+#pragma unroll
+      for (int c = 0; c < 4; c++) tz[c] = Y[c * mp + mp - 2] + group_sum<LPL>(gmask, u4[c]);   // z + u
       // y_k = -L^-T (z + u)
 #pragma unroll
       for (int c = 0; c < 4; c++) {
