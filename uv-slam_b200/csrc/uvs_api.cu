@@ -638,18 +638,6 @@ static int launch_resid_sweep(UvsHandle *h, int mode, int cand, int slot) {
   return post_launch(h, "residual sweep");
 }
 
-static int launch_jac_sweep(UvsHandle *h, int mode) {
-  const Dev &D = h->D;
-  double *cost = D.acc + ACC_COST0;
-  cudaStream_t st = h->stream;
-  h->launches += launch_proj(D, h->P, true, false, mode, 0, D.rec_proj, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_line(D, h->P, true, false, mode, 0, D.rec_line, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_vp(D, h->P, true, false, mode, 0, D.rec_vp, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_imu(D, h->P, true, mode, 0, D.rec_imu, nullptr, cost, ACC_STRIDE, st);
-  h->launches += launch_prior(D, h->max_prior_n, true, mode, 0, D.rec_prior, cost, ACC_STRIDE, st);
-  return post_launch(h, "Jacobian sweep");
-}
-
 int uvs_eval_cost(UvsHandle *h, double *cost) {
   if (!h || !cost) return fail(h, UVS_ERR_INVALID_ARG, "uvs_eval_cost: bad arguments");
   if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_eval_cost: no window uploaded");
