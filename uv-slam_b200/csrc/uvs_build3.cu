@@ -1,22 +1,23 @@
 // uvs_build3.cu — normal equations + Schur complement + back-substitution for the reference's window
 // size (<= 12 six-wide camera blocks: 11 poses + extrinsic, no td): the production path.
 //
-// Same algebra as uvs_build.cu (Ceres SPARSE_SCHUR restated), organised so that no lane is idle and no
-// atomics touch the Hessian:
+// Same algebra as uvs_build.cu (Ceres SPARSE_SCHUR restated), organised so that every record is read a fixed number of
+// times (elimination + direct terms) and the dense contractions run on the FP64 tensor cores:
 //
-//   k_core_points / k_core_lines   one lane GROUP (4 / 8 lanes) per landmark: the lanes split the observations,
-//        merge by shuffles, eliminate the landmark block and write the
-//        "stash": Y = W (E + D^2)^-1/2 (6 values per camera block of the landmark; 6x4 per line observation),
-//        z = (E + D^2)^-1/2 g, Jacobi scale, LM diagonal.   W (E+D^2)^-1 W^T = Y Y^T,  W (E+D^2)^-1 g = Y z.
-//   k_window_system                one CTA per window:
-//        (1) direct terms  sum_f J_a^T J_b  per camera-block pair from lists sorted by block pair at upload
-//            (k_prep_direct): a warp owns a pair, lanes own the 6x6 entries, the records are gathered from L2;
-//        (2) Schur terms as a dense rank update  V -= Y Y^T  over all landmark columns, 6x6 register tiles,
-//            Y columns expanded chunk by chunk into shared memory (double buffered);
-//        (3) IMU blocks and the prior, then ONE write of the window's reduced system.
-//   k_back_points / k_back_lines   one thread per point / one lane group per line: delta_k = -(E+D^2)^-1/2 (z + Y^T delta_c).
+//   k_core_points / k_core_lines   one lane GROUP (4 / 8 lanes) per landmark: the warp stages the contiguous record span of
+//        its landmarks in shared memory (cp.async), the lanes split the observations, merge by shuffles, eliminate the
+//        landmark block and write the "stash": Y = W (E + D^2)^-1/2 (6 values per camera block of the landmark; 6x4 per
+//        line observation), z = (E + D^2)^-1/2 g, Jacobi scale, LM diagonal.  W (E+D^2)^-1 W^T = Y Y^T,  W (E+D^2)^-1 g = Y z.
+//   k_direct_fused (k_direct when an extrinsic is free)   direct terms  sum_f J_a^T J_b, J^T r, column norms per camera-block
+//        pair from lists sorted by block pair at upload (k_prep_direct): a warp owns a pair, the records are gathered
+//        with cp.async and contracted on the FP64 tensor cores (G^T G with G = [J_a | J_b | r]).
+//   k_window_system                one CTA per window: Schur terms as ONE dense rank update  V -= Y Y^T  over all landmark
+//        columns, streamed with TMA bulk copies (4 stages), FP64 mma.sync, eight balanced tile units for the 66-row window.
+//   k_window_tail                  IMU blocks ([J r]^T [J r] on the tensor cores) and the prior.
+//   k_back_points / k_back_lines   one lane group per point / line: delta_k = -(E+D^2)^-1/2 (z + Y^T delta_c).
+// All of them add into the window's reduced system with FP64 reductions (they run side by side on auxiliary streams).
 // The model cost change uses  -(g^T y + y^T H y / 2) = (y^T D^2 y - g^T y) / 2  (y solves (H + D^2) y = -g),
-// which needs no Jacobians; k_chol adds the camera part.
+// which needs no Jacobians; k_chol / k_chol_chain add the camera part.
 #include <algorithm>
 
 #include "uvs_device.cuh"

@@ -8,6 +8,8 @@
 //                 reduced camera system, camera step, x+ = Plus(x, delta) for poses / speed-biases /
 //                 extrinsic / td (pose_local_parameterization.cpp:3-19), model cost change of the
 //                 camera-only factors
+//   k_chol_chain  the same for windows whose speed-bias blocks form a chain (the reference's shape): the 9-column blocks
+//                 are eliminated one by one, a 66-column dense system remains; four windows per SM
 //   k_step        step quality, accept / reject, radius update, termination tests, iteration log
 // One CTA per window; windows of a batch advance in lock-step but accept / reject independently.
 #include <algorithm>
