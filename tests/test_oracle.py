@@ -278,6 +278,68 @@ def test_schur_equals_dense_solve(opts):
         assert np.abs(a.inv_depth - b.inv_depth).max() < 1e-9
 
 
+def _chain_solve(S, g, F, nd_extra):
+    """numpy restatement of the structure-exploiting reduced solve of uvs_solve.cu (k_chol_chain): the speed-bias blocks
+    B_f (rows 15 f + 6 .. 15 f + 14) are eliminated one by one from the last frame to the first - a 9x9 Cholesky, the
+    coupling to B_f-1 and to the dense set D = {poses, extrinsic}, a rank-9 update of D - then D is solved densely and
+    the chain is back-substituted.  Solves S y = -g."""
+    d = S.shape[0]
+    didx = np.array([15 * f + k for f in range(F) for k in range(6)] + list(range(15 * F, 15 * F + nd_extra)))
+    bidx = [np.arange(15 * f + 6, 15 * f + 15) for f in range(F)]
+    assert len(didx) + 9 * F == d
+    D = S[np.ix_(didx, didx)].copy()
+    bD = -g[didx].copy()
+    C = [S[np.ix_(b, b)].copy() for b in bidx]
+    W = [S[np.ix_(didx, b)].copy() for b in bidx]
+    X = [None] + [S[np.ix_(bidx[f - 1], bidx[f])].copy() for f in range(1, F)]
+    bb = [-g[b].copy() for b in bidx]
+    Ls, Lxs, Lws, zs = [None] * F, [None] * F, [None] * F, [None] * F
+    for f in range(F - 1, -1, -1):
+        L = np.linalg.cholesky(C[f])
+        Li = np.linalg.inv(L)
+        zs[f] = Li @ bb[f]
+        Lws[f] = W[f] @ Li.T
+        Ls[f] = L
+        if f > 0:
+            Lxs[f] = X[f] @ Li.T
+            C[f - 1] -= Lxs[f] @ Lxs[f].T
+            bb[f - 1] -= Lxs[f] @ zs[f]
+            W[f - 1] -= Lws[f] @ Lxs[f].T
+        D -= Lws[f] @ Lws[f].T
+        bD -= Lws[f] @ zs[f]
+    yD = np.linalg.solve(D, bD)
+    y = np.zeros(d)
+    y[didx] = yD
+    prev = None
+    for f in range(F):
+        t = zs[f] - Lws[f].T @ yD
+        if f > 0:
+            t -= Lxs[f].T @ prev
+        prev = np.linalg.solve(Ls[f].T, t)
+        y[bidx[f]] = prev
+    return y
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "C1", "C2"])
+def test_reduced_system_is_a_chain_and_chain_elimination_solves_it(opts, cfg):
+    """What k_chol_chain relies on, checked on the oracle's own reduced camera system: speed-bias blocks of frames more
+    than one apart are not coupled (IMU factors tie neighbours, the prior only holds the first frame's block), and the
+    block elimination in chain order gives the step of the oracle's dense Cholesky."""
+    w = gw.make_window(cfg)
+    fs = orc.first_step(w.copy(), opts, radius=1e4)
+    S, g = fs["S"], fs["g"]
+    F, d = w.n_frames, w.cam_dim
+    assert np.abs(S - S.T).max() <= 1e-9 * np.abs(S).max()
+    for f in range(F):
+        for h in range(f + 2, F):
+            assert not S[15 * f + 6:15 * f + 15, 15 * h + 6:15 * h + 15].any(), (f, h)
+    y = _chain_solve(S, g, F, d - 15 * F)
+    ref = np.linalg.solve(S, -g)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(y - ref).max() / scale < 1e-8
+    assert np.abs(y - fs["delta"][:d]).max() / scale < 1e-7   # the oracle's own (dense Cholesky) camera step
+
+
 def test_converges_and_cost_monotone(opts):
     w, truth = gw.make_window("C1", with_prior=False, return_truth=True)
     sm = orc.solve(w, uvs_b200.default_options(max_num_iterations=30))
