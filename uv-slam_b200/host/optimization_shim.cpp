@@ -1,6 +1,7 @@
 // optimization_shim.cpp — see optimization_shim.h.  Host glue over the C ABI; no arithmetic of the
 // solve happens here.
 #include "optimization_shim.h"
+#include "window_io.h"
 
 #include <algorithm>
 #include <cstring>
@@ -82,6 +83,13 @@ int GpuWindowProblem::solve(UvsSummary *summary) {
   const int rc = uvs_batch_solve(h, 1, &w, &opts_, summary);
   if (rc != UVS_OK) err_ = uvs_last_error(h);
   uploaded_ = rc == UVS_OK;
+  return rc;
+}
+
+int GpuWindowProblem::save(const char *path) {
+  const UvsWindow w = view();
+  const int rc = save_window(w, path);
+  if (rc) err_ = "GpuWindowProblem::save: cannot write the window";
   return rc;
 }
 

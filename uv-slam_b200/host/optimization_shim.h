@@ -47,6 +47,9 @@ class GpuWindowProblem {
   // next prior from the solved state (flag = marginalization_flag); returns UvsStatus, out.n == 0 when the
   // reference would build nothing.
   int marginalize(int flag, PriorData &out);
+  // dump hook: the assembled window in the `uvs_window v1` format of tests/ and bench.py - call it
+  // before solve() to record what the reference would hand to ceres::Solve.  Returns the UvsStatus.
+  int save(const char *path);
   const std::string &lastError() const { return err_; }
 
  private:
