@@ -103,6 +103,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def sources_sha():
+    """sha256 over the kernel sources: ties a committed ncu profile to the source state it was taken at"""
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(glob.glob(os.path.join(ROOT, "uv-slam_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "uv-slam_b200", "csrc", "*.h"))):
+        h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,17 +233,10 @@ def main():
         step_ms = float(t.item())
     value = world * B * K_LM / (step_ms * 1e-3)
 
-    # per-kernel view: a few extra steps with the sweep kernels one after the other (profiling level 2; the timed steps
-    # above run them side by side on four streams, so their stage events see one interval)
-    s.set_profiling(2)
-    ser_tot, ser_it = {}, 0
-    for _ in range(3):
-        s.reset_state(); s.solve()
-        st, n_it = s.last_stage_ms()
-        ser_it += n_it
-        for k, v in st.items():
-            ser_tot[k] = ser_tot.get(k, 0.0) + v
-    s.set_profiling(1)
+    # ---- materialised Jacobian sweep (the roofline kernel group): the four factor-type kernels write every residual and
+    # tangent Jacobian block of the batch to HBM; CUDA events on the handle's stream (uvs_jacobian_sweep).  uvs_solve itself
+    # takes the fused path (factors evaluated inside the landmark elimination, no records), so this is timed on its own.
+    sweep_ms, sweep_each = s.jacobian_sweep(repeats=10)
 
     # ---- end to end through the reference-facing call: host buffers, H2D + solve + D2H per step
     host_sets = [[w.copy() for w in ws] for _ in range(2)]
@@ -285,19 +287,194 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (of fallback)"
-    sweep_ms = sum(stage_tot[k] for k in ("sweep_proj", "sweep_line", "sweep_vp", "sweep_imu", "sweep_prior")) / max(1, iters_tot)
     achieved = jac_bytes / (sweep_ms * 1e-3) / 1e9
     total_stage = sum(stage_tot.values())
-    shares = {k: round(v / total_stage, 4) for k, v in stage_tot.items()}
+    shares = {k: round(v / total_stage, 4) for k, v in stage_tot.items() if v > 0}
     nproj, nline, nvp = sum(w.n_proj for w in ws), sum(w.n_line_obs for w in ws), sum(w.n_vp_obs for w in ws)
+    nimu = sum(w.n_imu for w in ws)
     per_kernel = {}
-    ser_tot["sweep_line_vp"] = ser_tot["sweep_line"] + ser_tot["sweep_vp"]   # the VP factors ride in the line kernel (k_line_vp)
-    for k, nb in (("sweep_proj", 384 * nproj), ("sweep_line_vp", 232 * nline + 120 * nvp), ("sweep_imu", 6024 * 10 * B),
-                  ("sweep_prior", jac_bytes - 384 * nproj - 232 * nline - 120 * nvp - 6024 * 10 * B)):
-        ms = ser_tot[k] / max(1, ser_it)
+    kbytes = (("k_proj", 384 * nproj), ("k_line_vp", 232 * nline + 120 * nvp), ("k_imu_geom+k_imu_weight", 6024 * nimu),
+              ("k_prior", jac_bytes - 384 * nproj - 232 * nline - 120 * nvp - 6024 * nimu))
+    for (k, nb), ms in zip(kbytes, sweep_each):
         if ms > 0:
-            per_kernel[k] = {"ms_alone": round(ms, 4), "GB/s": round(nb / (ms * 1e-3) / 1e9, 1), "frac": round(nb / (ms * 1e-3) / 1e9 / peak, 4)}
-    sweep_serial_ms = sum(ser_tot[k] for k in ("sweep_proj", "sweep_line", "sweep_vp", "sweep_imu", "sweep_prior")) / max(1, ser_it)
+            per_kernel[k] = {"ms_alone": round(ms, 4), "bytes": int(nb), "GB/s": round(nb / (ms * 1e-3) / 1e9, 1),
+                             "frac": round(nb / (ms * 1e-3) / 1e9 / peak, 4)}
+    sweep_serial_ms = float(sum(sweep_each))
+    # fused linearisation stage of the solver (IMU + prior sweeps, point / line linearisation, tail, rank update): the same
+    # algorithmic sweep bytes against its time (it never writes the point / line / VP records, so this can exceed the
+    # materialised figure)
+    lin_ms = stage_tot.get("build", 0.0) / max(1, iters_tot)
+    iter_ms = total_stage / max(1, iters_tot)
+
+    cpu = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, reps, dt = run_cpu_sample(max(2 * threads, 16), threads, args.cpu_budget)
+        v1, reps1, dt1 = run_cpu_sample(4, 1, min(4.0, args.cpu_budget / 3))
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d C2 windows x %d LM iterations x %d repetitions in %.1f s, %d host threads (window-parallel oracle)" % (
+                   max(2 * threads, 16), K_LM, reps, dt, threads),
+               "single_thread_value": v1}
+
+    # DRAM traffic of the sweep launches from an ncu --set full capture of THIS source state: the profile names the git
+    # commit it was taken at; a stale file is refused
+    traffic, traffic_note = None, "no ncu capture at this commit"
+    tp = os.path.join(ROOT, "profiles", "r2_sweep_ncu.json")
+    if os.path.exists(tp):
+        prof = json.load(open(tp))
+        try:
+            head = subprocess.run(["git", "-C", ROOT, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
+        except Exception:
+            head = ""
+        if prof.get("windows") == B and (not head or prof.get("git_sha") == head or prof.get("kernel_sources_sha") == sources_sha()):
+            traffic = prof["jacobian_sweep_dram_bytes"]
+            traffic_note = "dram read+write of the sweep launches, " + prof.get("note", "")
+        else:
+            traffic_note = "profiles/r2_sweep_ncu.json was taken at another source state (%s)" % prof.get("git_sha", "?")[:10]
+
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 window (11 frames / 200 points / 80 lines / 3 VP), %d LM iterations per window" % K_LM,
+                   "windows_per_step": n, "note": "reference = CPU restatement of the Ceres path (oracle/); Ceres itself cannot be built here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d C2 windows x %d LM iterations per step, %d host threads (window-parallel)" % (n, K_LM, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--windows", type=int, default=1184, help="windows per GPU and step (1184 = 4 x 148 SMs x 2 resident window CTAs)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import uvs_b200
+    rank, world, local, dist = dist_setup(args.gpus)
+    B = args.windows
+    ws = load_workload(B, rank)
+    opts = uvs_b200.default_options(max_num_iterations=K_LM, fixed_iterations=1)
+    s = uvs_b200.Solver(local)
+    s.upload(ws, opts)
+    jac_bytes, res_bytes = s.sweep_bytes()
+    s.set_profiling(1)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing: inputs already in HBM, state rewound on the device between steps
+    for _ in range(max(3, args.warmup)):
+        s.reset_state(); s.solve()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = s.launch_count()
+    dev_ms, stage_tot, iters_tot = 0.0, {}, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.reset_state()
+        s.solve()
+        dev_ms += s.last_solve_ms()
+        st, n_it = s.last_stage_ms()
+        iters_tot += n_it
+        for k, v in st.items():
+            stage_tot[k] = stage_tot.get(k, 0.0) + v
+    wall = time.perf_counter() - t0
+    barrier()
+    launches = s.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = dev_ms / args.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    value = world * B * K_LM / (step_ms * 1e-3)
+
+    # ---- materialised Jacobian sweep (the roofline kernel group): the four factor-type kernels write every residual and
+    # tangent Jacobian block of the batch to HBM; CUDA events on the handle's stream (uvs_jacobian_sweep).  uvs_solve itself
+    # takes the fused path (factors evaluated inside the landmark elimination, no records), so this is timed on its own.
+    sweep_ms, sweep_each = s.jacobian_sweep(repeats=10)
+
+    # ---- end to end through the reference-facing call: host buffers, H2D + solve + D2H per step
+    host_sets = [[w.copy() for w in ws] for _ in range(2)]
+    for k in range(2):
+        s.batch_solve(host_sets[k % 2], opts, groups=0)
+    n_e2e = max(2, min(args.steps, 5))
+    fresh_sets = [[w.copy() for w in ws] for _ in range(n_e2e)]   # host copies made outside the timer
+    views = [uvs_b200.window_array(fs) for fs in fresh_sets]     # ctypes structs of pointers to those host arrays
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        # uvs_batch_solve_pipelined: pack into pinned staging + H2D + solve + D2H, sub-batch k+1 uploading while k iterates
+        s.batch_solve(fresh_sets[k], opts, prepared=views[k], groups=0)
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * K_LM / e2e_s
+    h2d = sum(len(w.to_bytes()) for w in ws[:4]) // 4 * B
+    d2h = sum(w.state_vector().nbytes for w in ws) + B * C.sizeof(uvs_b200.UvsSummaryStruct)
+
+    # ---- single-window latency (the reference's own use: one window per frame)
+    s1 = uvs_b200.Solver(local)
+    s1.upload([ws[0]], opts)
+    for _ in range(5):
+        s1.reset_state(); s1.solve()
+    lat = []
+    for _ in range(20):
+        s1.reset_state(); s1.solve(); lat.append(s1.last_solve_ms())
+    lat_ms = float(np.median(lat))
+    # the same with the LM iteration replayed from a CUDA graph (pays only when one upload is solved repeatedly, as here)
+    s1.set_graph_replay(True)
+    for _ in range(3):
+        s1.reset_state(); s1.solve()
+    lat = []
+    for _ in range(20):
+        s1.reset_state(); s1.solve(); lat.append(s1.last_solve_ms())
+    lat_graph_ms = float(np.median(lat))
+    s1.close()
+
+    if rank != 0:
+        return
+    # ---- roofline of the Jacobian sweep (SURVEY.md 8d bytes) against the measured HBM peak
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (of fallback)"
+    achieved = jac_bytes / (sweep_ms * 1e-3) / 1e9
+    total_stage = sum(stage_tot.values())
+    shares = {k: round(v / total_stage, 4) for k, v in stage_tot.items() if v > 0}
+    nproj, nline, nvp = sum(w.n_proj for w in ws), sum(w.n_line_obs for w in ws), sum(w.n_vp_obs for w in ws)
+    nimu = sum(w.n_imu for w in ws)
+    per_kernel = {}
+    kbytes = (("k_proj", 384 * nproj), ("k_line_vp", 232 * nline + 120 * nvp), ("k_imu_geom+k_imu_weight", 6024 * nimu),
+              ("k_prior", jac_bytes - 384 * nproj - 232 * nline - 120 * nvp - 6024 * nimu))
+    for (k, nb), ms in zip(kbytes, sweep_each):
+        if ms > 0:
+            per_kernel[k] = {"ms_alone": round(ms, 4), "bytes": int(nb), "GB/s": round(nb / (ms * 1e-3) / 1e9, 1),
+                             "frac": round(nb / (ms * 1e-3) / 1e9 / peak, 4)}
+    sweep_serial_ms = float(sum(sweep_each))
+    # fused linearisation stage of the solver (IMU + prior sweeps, point / line linearisation, tail, rank update): the same
+    # algorithmic sweep bytes against its time (it never writes the point / line / VP records, so this can exceed the
+    # materialised figure)
+    lin_ms = stage_tot.get("build", 0.0) / max(1, iters_tot)
+    iter_ms = total_stage / max(1, iters_tot)
 
     cpu = None
     if not args.no_cpu:
@@ -331,10 +508,16 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                     "kernel": "Jacobian sweep = k_proj | k_line_vp | k_imu_geom + k_imu_weight | k_prior (Jacobian mode), launched side by side "
-                               "on four streams; achieved = bytes of all four / CUDA-event time of the group",
+                     "kernel": "materialised Jacobian sweep = k_proj | k_line_vp | k_imu_geom + k_imu_weight | k_prior (Jacobian mode, "
+                               "records to HBM), launched side by side on four streams (uvs_jacobian_sweep); achieved = SURVEY 8d bytes "
+                               "of all four / CUDA-event time of the group",
                      "bytes_per_launch": int(jac_bytes), "ms_per_launch": sweep_ms, "ms_one_after_the_other": sweep_serial_ms,
-                     "peak_source": peak_src, "per_kernel": per_kernel},
+                     "peak_source": peak_src, "per_kernel": per_kernel,
+                     "fused_linearisation": {"ms_per_iteration": lin_ms, "GB/s_algorithmic": jac_bytes / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else None,
+                                             "frac": jac_bytes / (lin_ms * 1e-3) / 1e9 / peak if lin_ms > 0 else None,
+                                             "note": "solver path: factors evaluated inside the landmark elimination (no point / line / VP records); "
+                                                     "the time also covers elimination, direct terms, IMU / prior blocks and the Schur rank update"},
+                     "whole_iteration": {"ms": iter_ms, "bytes_algorithmic": int(jac_bytes + res_bytes), "frac": (jac_bytes + res_bytes) / (iter_ms * 1e-3) / 1e9 / peak if iter_ms > 0 else None}},
         "cpu_baseline": cpu,
         "stage_share": shares,
         "latency": {"single_window_ms_per_solve": lat_ms, "single_window_iterations_per_s": K_LM / (lat_ms * 1e-3),

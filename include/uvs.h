@@ -228,6 +228,13 @@ int uvs_upload_windows(UvsHandle *h, int32_t n_windows, const UvsWindow *windows
 /* Copy the current state of every window back into the caller's state arrays (D2H). */
 int uvs_download_state(UvsHandle *h, int32_t n_windows, UvsWindow *windows);
 
+/* Replace the STATE of the uploaded batch (pose, speed_bias, ex_pose, td, inv_depth, ortho and the line_ric / line_tic
+ * frozen into the line functors) by the caller's arrays; the factors stay as uploaded.  The reference re-packs its
+ * state between the solve and the marginalization - double2vector() applies the yaw / position gauge fix and
+ * vector2double() packs the fixed state again (estimator.cpp:1006, :596-711, :1168) - so the prior must be built at
+ * THAT state: call this between uvs_solve / uvs_batch_solve and uvs_marginalize.  Sizes must match the upload. */
+int uvs_upload_state(UvsHandle *h, int32_t n_windows, const UvsWindow *windows);
+
 /* Batched factor sweeps over the uploaded batch, factors concatenated in window order.
  * residuals: [n_total][nres]; jacobians (nullable): per factor, layout per flags. */
 int uvs_eval_proj(UvsHandle *h, double *residuals, double *jacobians, int32_t flags);
@@ -264,6 +271,14 @@ int64_t uvs_launch_count(const UvsHandle *h);
 int uvs_last_solve_ms(const UvsHandle *h, float *ms);
 /* Device time [ms] of the Jacobian-sweep kernels accumulated over the last uvs_solve. */
 int uvs_last_sweep_ms(const UvsHandle *h, float *ms, int32_t *n_sweeps);
+
+/* Materialised Jacobian sweep of the uploaded batch, for measurement: the four factor-type kernels (point, line + VP,
+ * IMU, prior) evaluate every residual and tangent-space Jacobian block of the batch into the device record arrays
+ * (the layout of UVS_EVAL_LOCAL_LAYOUT), `repeats` times.  ms_group = CUDA-event time per repetition with the four
+ * kernels side by side on the handle's streams; ms_each[4] (nullable) = proj, line + VP, IMU, prior each on its own.
+ * (uvs_solve itself evaluates point / line / VP factors inside the landmark elimination and never writes these records
+ * when the batch takes the fused path; bytes per repetition: uvs_sweep_bytes.) */
+int uvs_jacobian_sweep(UvsHandle *h, int32_t repeats, float *ms_group, float *ms_each);
 
 /* Put every window back to the state it was uploaded with (device-to-device; no host traffic), so
  * that the same batch can be solved again - used to time solves with the inputs resident in HBM. */

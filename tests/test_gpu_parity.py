@@ -469,6 +469,47 @@ def test_rejected_steps_keep_the_system_complete(solver, windows):
         assert np.abs(big[i].pose - r.pose).max() < STEP_TOL
 
 
+def test_fused_path_equals_record_path(windows, opts, monkeypatch):
+    """The fused linearisation (uvs_lin.cu: factors evaluated inside the landmark elimination, no Jacobian records in HBM)
+    against the record path (k_proj / k_line_vp -> k_core_* -> k_direct_fused) on the same mixed batch: same iteration
+    log, cost to 1e-9 (FP64 reductions are order-dependent), states to 1e-8.  UVS_NO_FUSE is read at every upload."""
+    s = uvs_b200.Solver(0)
+    try:
+        names = ("C2", "C1", "tiny")
+        a = [windows[names[i % 3]].copy() for i in range(9)]
+        b = [w.copy() for w in a]
+        monkeypatch.delenv("UVS_NO_FUSE", raising=False)
+        s.upload(a, opts)
+        l0 = s.launch_count()
+        sa = s.solve()
+        fused_launches = s.launch_count() - l0
+        s.download()
+        monkeypatch.setenv("UVS_NO_FUSE", "1")
+        s.upload(b, opts)
+        l0 = s.launch_count()
+        sb = s.solve()
+        record_launches = s.launch_count() - l0
+        s.download()
+        assert fused_launches < record_launches   # the Jacobian-mode k_proj / k_line_vp / k_core_* / k_direct launches are gone
+        for i, (x, y) in enumerate(zip(a, b)):
+            n = sa[i].num_iterations
+            assert n == sb[i].num_iterations, i
+            assert [sa[i].step_accepted[k] for k in range(n)] == [sb[i].step_accepted[k] for k in range(n)], i
+            for k in range(n):
+                assert abs(sa[i].cost[k] - sb[i].cost[k]) <= 1e-9 * abs(sb[i].cost[k]) + 1e-12, (i, k)
+            assert np.abs(x.pose - y.pose).max() < 1e-8 and np.abs(x.speed_bias - y.speed_bias).max() < 1e-8, i
+            assert np.abs(x.inv_depth - y.inv_depth).max() < 1e-7, i
+    finally:
+        s.close()
+
+
+def test_materialised_sweep_timer(solver, windows, opts):
+    """uvs_jacobian_sweep (the measurement entry point of bench.py) runs the four Jacobian kernels into the record arrays"""
+    solver.upload([windows["C2"].copy() for _ in range(4)], opts)
+    g, each = solver.jacobian_sweep(repeats=3)
+    assert g > 0 and all(e > 0 for e in each)
+
+
 def test_graph_replay_gives_the_same_solve(windows, opts):
     """uvs_set_graph_replay: the LM iteration replayed from a CUDA graph (captured at the first solve after an upload,
     reused by later solves of the same upload) must give what the plain launches give."""

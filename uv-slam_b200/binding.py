@@ -22,7 +22,7 @@ EXPORTS = (
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
     "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate", "uvs_batch_solve_pipelined",
-    "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_set_graph_replay",
+    "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_set_graph_replay", "uvs_upload_state", "uvs_jacobian_sweep",
 )
 
 N_STAGES = 10
@@ -62,6 +62,8 @@ def load_library():
     lib.uvs_last_error.argtypes = [H]
     lib.uvs_upload_windows.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct), C.POINTER(UvsOptionsStruct)]
     lib.uvs_download_state.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct)]
+    lib.uvs_upload_state.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct)]
+    lib.uvs_jacobian_sweep.argtypes = [H, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float * 4)]
     for n in ("uvs_eval_proj", "uvs_eval_line", "uvs_eval_vp", "uvs_eval_imu", "uvs_eval_prior"):
         getattr(lib, n).argtypes = [H, C.c_void_p, C.c_void_p, C.c_int32]
     lib.uvs_eval_cost.argtypes = [H, c_double_p]
@@ -134,6 +136,19 @@ class Solver:
         """Writes the device state back into the Window objects given to upload()."""
         self._check(self.lib.uvs_download_state(self.h, len(self.windows), self._arr), "uvs_download_state")
         return self.windows
+
+    def upload_state(self, windows=None):
+        """Replaces the device state of the uploaded batch by the state arrays of `windows` (default: the Window objects
+        given to upload(), e.g. after the caller changed them in place); factors stay as uploaded."""
+        arr = self._arr if windows is None else window_array(list(windows))
+        n = len(self.windows)
+        self._check(self.lib.uvs_upload_state(self.h, n, arr), "uvs_upload_state")
+
+    def jacobian_sweep(self, repeats=10, each=True):
+        """-> (ms per materialised Jacobian sweep with the four kernels side by side, [ms of proj, line+vp, imu, prior alone])"""
+        g, e = C.c_float(), (C.c_float * 4)()
+        self._check(self.lib.uvs_jacobian_sweep(self.h, int(repeats), C.byref(g), C.byref(e) if each else None), "uvs_jacobian_sweep")
+        return g.value, [e[k] for k in range(4)]
 
     # -- factor sweeps -------------------------------------------------------------------------
     def _count(self, kind):

@@ -177,7 +177,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   fill_params(h->opts, h->P);
   h->have_window = false;
   const int td = w[0].estimate_td ? 1 : 0;
-  int max_d = 0, max_prior_n = 0, max_frames = 0;
+  int max_d = 0, max_prior_n = 0, max_frames = 0, max_lines = 0, max_lobs = 0;
   bool any_ex = false;
   for (int i = 0; i < B; i++) {
     const UvsWindow &x = w[i];
@@ -203,12 +203,14 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
     const int d = 15 * x.n_frames + (x.estimate_extrinsic ? 6 : 0) + (td ? 1 : 0);
     max_d = std::max(max_d, d);
     max_frames = std::max(max_frames, (int)x.n_frames);
+    max_lines = std::max(max_lines, (int)x.n_lines);
+    max_lobs = std::max(max_lobs, (int)x.n_line_obs);
     any_ex = any_ex || x.estimate_extrinsic;
     max_prior_n = std::max(max_prior_n, (int)x.prior_n);
   }
   h->B = B; h->max_d = max_d; h->max_prior_n = max_prior_n;
   if (h->iter_exec) { cudaGraphExecDestroy(h->iter_exec); h->iter_exec = nullptr; }   // the graph holds the old batch's arguments
-  h->max_frames = max_frames; h->any_ex = any_ex;
+  h->max_frames = max_frames; h->any_ex = any_ex; h->max_lines = max_lines;
   // independent kernels of a stage run side by side on the auxiliary streams (fork / join events).  This pays for a single
   // window too: its kernels are latency-bound (2.45 -> 1.89 ms per 10-iteration solve); UVS_SERIAL=1 forces the plain
   // in-order sequence (profiling), UVS_CONCURRENT_MIN=<B> restores a batch-size threshold
@@ -278,6 +280,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
                w_iidx = wk.take(nImu * sizeof(int2));
   const size_t w_ptb = wk.take(nP * I), w_lnb = wk.take(nL * I);            // begin arrays (memset 0x7f together)
   const size_t w_pte = wk.take(nP * I), w_lne = wk.take(nL * I), w_ptw = wk.take(nP * I), w_lnw = wk.take(nL * I);
+  const size_t w_pto = wk.take(nP * I), w_ptk = wk.take(nP * I);
   const size_t w_icomp = wk.take((size_t)nImu * 108 * Dd);
   const size_t w_clw = wk.take(h->use_build3 ? (size_t)B * chol_chain_lw_doubles(max_frames) * Dd : 0);
   const size_t w_sqi = wk.take((size_t)nImu * 225 * Dd), w_prH = wk.take((size_t)nPJ * Dd), w_err = wk.take(I);
@@ -305,7 +308,8 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   std::memcpy(S + o_S_off, h->S_off.data(), (B + 1) * 8);
   std::memcpy(S + o_pJ_off, h->priorJ_off.data(), (B + 1) * 8);
   auto put = [&](size_t off, size_t elem_off, const void *src, size_t bytes) { if (bytes) std::memcpy(S + off + elem_off, src, bytes); };
-  std::atomic<int> pack_err(0), chain_bad(0);
+  std::atomic<int> pack_err(0), chain_bad(0), line_run_max(0);
+  const bool want_line_runs = h->use_build3 && !any_ex;
   auto pack_range = [&](int lo, int hi) {
   for (int i = lo; i < hi; i++) {
     const UvsWindow &x = w[i];
@@ -327,6 +331,12 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
     }
     put(o_lf, a0 * I, x.line_frame, x.n_line_obs * I); put(o_li, a0 * I, x.line_idx, x.n_line_obs * I);
     put(o_lsp, a0 * 2 * Dd, x.line_sp, x.n_line_obs * 2 * Dd); put(o_lep, a0 * 2 * Dd, x.line_ep, x.n_line_obs * 2 * Dd);
+    if (want_line_runs && x.n_line_obs > 0) {   // most observations of one line (they are contiguous): the fused path stages them per line
+      int run = 1, best = 1;
+      for (int k = 1; k < x.n_line_obs; k++) { run = x.line_idx[k] == x.line_idx[k - 1] ? run + 1 : 1; best = std::max(best, run); }
+      int seen = line_run_max.load();
+      while (best > seen && !line_run_max.compare_exchange_weak(seen, best)) {}
+    }
     put(o_vf, v0 * I, x.vp_frame, x.n_vp_obs * I); put(o_vl, v0 * I, x.vp_line, x.n_vp_obs * I);
     put(o_vd, v0 * 3 * Dd, x.vp_dir, x.n_vp_obs * 3 * Dd);
     if (x.line_ric) put(o_ric, (size_t)i * 9 * Dd, x.line_ric, 9 * Dd); else std::memset(S + o_ric + (size_t)i * 9 * Dd, 0, 9 * Dd);
@@ -381,6 +391,10 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
       bool small = false;
       for (int i = 0; i < B; i++) small = small || w[i].n_frames < 2;
       h->chain_ok = h->use_build3 && !chain_bad && !small && !no_chain;
+      // fused linearisation (no point / line Jacobian records): the reference's configuration - constant extrinsic, no td
+      const bool no_fuse = std::getenv("UVS_NO_FUSE") != nullptr;   // read at every upload: tests switch paths
+      h->fused = h->use_build3 && !any_ex && !no_fuse && line_run_max.load() <= lin_max_line_obs() &&
+                 lin_lines_smem(max_frames) + 1024 <= h->smem_optin;
     }
     if (pack_err == 1) return fail(h, UVS_ERR_INVALID_ARG, "bad prior block kind");
     if (pack_err == 2) return fail(h, UVS_ERR_INVALID_ARG, "prior block id out of range");
@@ -403,6 +417,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   std::memset(&D, 0, sizeof(D));
   D.B = B; D.nF = nF; D.nP = nP; D.nL = nL; D.nProj = nProj; D.nLobs = nLobs; D.nVobs = nVobs; D.nImu = nImu; D.nCam = nCam;
   D.nPriorR = nPriorR; D.nPriorBlk = nBlk; D.estimate_td = td; D.rank = h->rank; D.nranks = h->nranks;
+  D.max_frames = max_frames; D.max_lines = max_lines; D.max_lobs = max_lobs;
 #define PI(o) ((const int *)(Dv + (o)))
 #define PD(o) ((const double *)(Dv + (o)))
 #define WD(o) ((double *)(Dv + (o)))
@@ -425,6 +440,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   D.pblk_col = WI(o_bcol); D.pblk_cam = WI(o_bcam); D.pblk_row = WI(o_brow);
   D.proj_idx = (int4 *)(Dv + w_pidx); D.line_idx4 = (int4 *)(Dv + w_lidx); D.vp_idx4 = (int4 *)(Dv + w_vidx); D.imu_idx = (int2 *)(Dv + w_iidx);
   D.pt_begin = WI(w_ptb); D.ln_begin = WI(w_lnb); D.pt_end = WI(w_pte); D.ln_end = WI(w_lne); D.pt_win = WI(w_ptw); D.ln_win = WI(w_lnw);
+  D.pt_order = WI(w_pto);
   D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.chain_lw = WD(w_clw); D.chain_lw_stride = chol_chain_lw_doubles(max_frames); D.prior_H = WD(w_prH); D.err = WI(w_err);
   D.rec_proj = WD(w_rp); D.rec_line = WD(w_rl); D.rec_vp = WD(w_rv); D.rec_imu = WD(w_ri); D.rec_prior = WD(w_rpr);
   D.scale_cam = WD(w_scc); D.scale_pt = WD(w_scp); D.scale_ln = WD(w_scl);
@@ -436,6 +452,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
 #undef WD
 #undef WI
   h->o_pose0 = o_pose; h->o_state_bytes = o_state_end - o_pose;
+  h->in_sb = o_sb; h->in_ex = o_ex; h->in_td = o_td; h->in_inv = o_inv; h->in_ortho = o_ortho; h->in_ric = o_ric; h->in_tic = o_tic;
   h->o_pristine = w_pristine; h->o_cur = w_cur; h->cur_bytes = B * I;
   h->o_reduce = w_S; h->reduce_doubles = (w_reduce_end - w_S) / Dd;
   h->o_b3 = w_b3;
@@ -444,7 +461,8 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   h->launches += launch_prep(D, h->stream);
   if (h->use_build3) {
     CK(cudaMemsetAsync(Dv + w_b3 + h->b3.o_Y, 0, h->b3.o_ph - h->b3.o_Y, h->stream));   // dense landmark columns start as zeros
-    h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->any_ex, h->stream);
+    if (h->fused) h->launches += launch_prep_point_order(D, (int *)(Dv + w_ptk), h->stream);
+    else h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->any_ex, h->stream);
   }
   int rc = post_launch(h, "prep kernels");
   if (rc) return rc;
@@ -535,6 +553,40 @@ int uvs_download_state(UvsHandle *h, int32_t B, UvsWindow *w) {
   return UVS_OK;
 }
 
+int uvs_upload_state(UvsHandle *h, int32_t B, const UvsWindow *w) {
+  if (!h || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_state: bad arguments");
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_upload_state: no window uploaded");
+  if (B != h->B) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_state: batch size differs from the upload");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));   // the staging buffer may still feed an earlier copy
+  const size_t Dd = sizeof(double);
+  char *S = h->stage.base, *Dv = h->dev.base;
+  for (int i = 0; i < B; i++) {
+    const UvsWindow &x = w[i];
+    if (x.n_frames != h->frame_off[i + 1] - h->frame_off[i] || x.n_points != h->point_off[i + 1] - h->point_off[i] ||
+        x.n_lines != h->line_off[i + 1] - h->line_off[i])
+      return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_state: window sizes differ from the upload");
+    if (!x.pose || !x.speed_bias || !x.ex_pose || (x.n_points && !x.inv_depth) || (x.n_lines && !x.ortho))
+      return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_state: null state pointer");
+    std::memcpy(S + h->o_pose0 + (size_t)h->frame_off[i] * 7 * Dd, x.pose, x.n_frames * 7 * Dd);
+    std::memcpy(S + h->in_sb + (size_t)h->frame_off[i] * 9 * Dd, x.speed_bias, x.n_frames * 9 * Dd);
+    std::memcpy(S + h->in_ex + (size_t)i * 7 * Dd, x.ex_pose, 7 * Dd);
+    if (x.td) std::memcpy(S + h->in_td + (size_t)i * Dd, x.td, Dd);
+    if (x.n_points) std::memcpy(S + h->in_inv + (size_t)h->point_off[i] * Dd, x.inv_depth, x.n_points * Dd);
+    if (x.n_lines) std::memcpy(S + h->in_ortho + (size_t)h->line_off[i] * 4 * Dd, x.ortho, x.n_lines * 4 * Dd);
+    if (x.line_ric) std::memcpy(S + h->in_ric + (size_t)i * 9 * Dd, x.line_ric, 9 * Dd);
+    if (x.line_tic) std::memcpy(S + h->in_tic + (size_t)i * 3 * Dd, x.line_tic, 3 * Dd);
+  }
+  // buffer 0 becomes the current iterate of every window again; the pristine copy follows (uvs_reset_state)
+  CK(cudaMemcpyAsync(Dv + h->o_pose0, S + h->o_pose0, h->o_state_bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(Dv + h->in_ric, S + h->in_ric, (size_t)B * 9 * Dd, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(Dv + h->in_tic, S + h->in_tic, (size_t)B * 3 * Dd, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(Dv + h->o_pristine, Dv + h->o_pose0, h->o_state_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemsetAsync(Dv + h->o_cur, 0, h->cur_bytes, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return UVS_OK;
+}
+
 // ---- factor sweeps through the ABI ---------------------------------------------------------------
 static int eval_common(UvsHandle *h, int type, double *residuals, double *jacobians, int32_t flags) {
   if (!h) return UVS_ERR_INVALID_ARG;
@@ -551,9 +603,14 @@ static int eval_common(UvsHandle *h, int type, double *residuals, double *jacobi
     case 0: n = D.nProj; NR = 2; REC = ceres ? (td ? CREC_PROJ_TD : CREC_PROJ) : (td ? REC_PROJ_TD : REC_PROJ); rec = D.rec_proj;
       h->launches += launch_proj(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st); break;
     case 1: n = D.nLobs; NR = 2; REC = ceres ? CREC_LINE : REC_LINE; rec = D.rec_line;
-      h->launches += launch_line(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st); break;
+      // tangent layout: the table-based line + VP kernel the solver and the marginalization use; Ceres layout (raw qw column): k_line
+      if (ceres) h->launches += launch_line(D, h->P, true, true, 0, 0, rec, nullptr, nullptr, 0, st);
+      else h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st);
+      break;
     case 2: n = D.nVobs; NR = 1; REC = ceres ? CREC_VP : REC_VP; rec = D.rec_vp;
-      h->launches += launch_vp(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st); break;
+      if (ceres || D.nLobs == 0) h->launches += launch_vp(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st);
+      else h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st);
+      break;
     case 3: n = D.nImu; NR = 15; REC = 15 + 15 * (2 * (ceres ? 7 : 6) + 18); rec = D.rec_imu;
       h->launches += launch_imu(D, h->P, true, 0, 0, rec, nullptr, nullptr, 0, st); break;
     default: return UVS_ERR_INVALID_ARG;
@@ -681,7 +738,13 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
   // than a single 10-iteration solve saves (0.3 ms) - it pays when one upload is solved repeatedly.
   auto enqueue_iteration = [&](int it) -> int {
     STAGE(0);
-    if (fk && h->profiling < 2) {
+    if (h->fused) {
+      // fused path: the point / line / VP factors are evaluated inside the landmark elimination (uvs_lin.cu); only the
+      // IMU and prior sweeps still write records.  The whole linearisation is accounted to the build stage.
+      STAGE(1); STAGE(2); STAGE(3); STAGE(4); STAGE(5);
+      h->launches += launch_build3_fused(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->max_lines, h->max_prior_n, st,
+                                         h->profiling < 2 ? fk : nullptr);
+    } else if (fk && h->profiling < 2) {
       // the four factor-type kernels side by side; the stage events then see the sweep as one interval
       fork_from(fk, st, 3);
       h->launches += launch_proj(D, P, true, false, 1, 0, D.rec_proj, nullptr, cost0, ACC_STRIDE, st);
@@ -698,7 +761,8 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
       h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, st); STAGE(5);
     }
     rc = post_launch(h, "Jacobian sweep"); if (rc) return rc;
-    if (h->use_build3) {
+    if (h->fused) {
+    } else if (h->use_build3) {
       h->launches += launch_build3(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->any_ex, h->max_prior_n, st, fk);
     } else {
       h->launches += launch_build(D, P, h->max_prior_n, st);
@@ -880,6 +944,44 @@ int uvs_sweep_bytes(UvsHandle *h, int64_t *jac, int64_t *res) {
   if (jac) *jac = 384LL * D.nProj + 232LL * D.nLobs + 120LL * D.nVobs + 6024LL * D.nImu + pr + state;
   if (res) *res = 80LL * D.nProj + 72LL * D.nLobs + 40LL * D.nVobs + 2424LL * D.nImu + pr + state;
   return UVS_OK;
+}
+
+int uvs_jacobian_sweep(UvsHandle *h, int32_t repeats, float *ms_group, float *ms_each) {
+  if (!h || repeats <= 0) return fail(h, UVS_ERR_INVALID_ARG, "uvs_jacobian_sweep: bad arguments");
+  if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_jacobian_sweep: no window uploaded");
+  CK(cudaSetDevice(h->device));
+  const Dev &D = h->D;
+  const Params &P = h->P;
+  cudaStream_t st = h->stream;
+  const Fork *fk = &h->fork;
+  auto one = [&](int k, cudaStream_t s) {
+    if (k == 0) h->launches += launch_proj(D, P, true, false, 0, 0, D.rec_proj, nullptr, nullptr, 0, s);
+    else if (k == 1) h->launches += launch_line_vp(D, P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, s);
+    else if (k == 2) h->launches += launch_imu(D, P, true, 0, 0, D.rec_imu, nullptr, nullptr, 0, s);
+    else h->launches += launch_prior(D, h->max_prior_n, true, 0, 0, D.rec_prior, nullptr, 0, s);
+  };
+  for (int k = 0; k < 4; k++) one(k, st);   // warm-up (shared-memory attributes, instruction cache)
+  CK(cudaEventRecord(h->ev_c, st));
+  for (int r = 0; r < repeats; r++) {
+    fork_from(fk, st, 3);
+    one(0, st); one(1, fk->aux[0]); one(2, fk->aux[1]); one(3, fk->aux[2]);
+    for (int k = 0; k < 3; k++) join_to(fk, st, k);
+  }
+  CK(cudaEventRecord(h->ev_d, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev_c, h->ev_d);
+  if (ms_group) *ms_group = ms / repeats;
+  if (ms_each)
+    for (int k = 0; k < 4; k++) {
+      CK(cudaEventRecord(h->ev_c, st));
+      for (int r = 0; r < repeats; r++) one(k, st);
+      CK(cudaEventRecord(h->ev_d, st));
+      CK(cudaStreamSynchronize(st));
+      cudaEventElapsedTime(&ms, h->ev_c, h->ev_d);
+      ms_each[k] = ms / repeats;
+    }
+  return post_launch(h, "uvs_jacobian_sweep");
 }
 
 int uvs_reset_state(UvsHandle *h) {

@@ -22,71 +22,9 @@
 
 #include "uvs_device.cuh"
 #include "uvs_kernels.h"
+#include "uvs_stash.cuh"
 
 namespace uvs {
-
-__device__ __forceinline__ double clamp4(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
-__device__ __forceinline__ void atomic_max_nn3(double *addr, double v) {
-  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
-}
-__device__ __forceinline__ int pair_key(int a, int b) { return a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b; }
-__device__ __forceinline__ void unrank_key(int t, int &a, int &b) {
-  int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-  while (i * (i + 1) / 2 > t) i--;
-  while ((i + 1) * (i + 2) / 2 <= t) i++;
-  b = i; a = t - i * (i + 1) / 2;
-}
-
-// warp-aggregated per-window accumulation (threads of a warp usually share the window)
-__device__ __forceinline__ void add_win3(double *acc, int win, bool valid, double v0, double v1, double v2) {
-  const unsigned full = 0xffffffffu;
-  const int w0 = __shfl_sync(full, win, 0);
-  const bool v00 = __shfl_sync(full, (int)valid, 0) != 0;
-  const bool uniform = __all_sync(full, !valid || win == w0) && v00;
-  if (uniform) {
-    double a = valid ? v0 : 0.0, b = valid ? v1 : 0.0, c = valid ? v2 : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(full, a, o); b += __shfl_down_sync(full, b, o); c += __shfl_down_sync(full, c, o); }
-    if ((threadIdx.x & 31) == 0) {
-      double *p = acc + (size_t)w0 * ACC_STRIDE;
-      atomicAdd(p + ACC_MODEL, a); atomicAdd(p + ACC_STEP2, b); atomicAdd(p + ACC_XNORM2, c);
-    }
-  } else if (valid) {
-    double *p = acc + (size_t)win * ACC_STRIDE;
-    atomicAdd(p + ACC_MODEL, v0); atomicAdd(p + ACC_STEP2, v1); atomicAdd(p + ACC_XNORM2, v2);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// stash (B3): dense landmark columns  Y[col][mp]:  entries [6 blk + k] = Y of camera block blk, [mp-2] = z,
-//             col = colbase(w) + point  |  colbase(w) + np_w + 4 line + sub, colbase(w) = point_off[w] + 4 line_off[w]
-//             (the window kernel streams whole chunks of columns with TMA bulk copies);
-//             headers for the back-substitution: points ph[4] = sk, sh, D2, -;  lines lh[24] = s(4) D2(4) Linv(16)
-struct Stash {
-  double *Y, *ph, *lh;
-  int mp;
-};
-__device__ __forceinline__ long long colbase(const Dev &D, int w) { return (long long)D.point_off[w] + 4LL * D.line_off[w]; }
-
-// sum over the 2^k lanes of a landmark's lane group (all lanes end with the same bits)
-template <int kLanes>
-__device__ __forceinline__ double group_sum(unsigned gmask, double v) {
-#pragma unroll
-  for (int o = 1; o < kLanes; o <<= 1) v += __shfl_xor_sync(gmask, v, o);
-  return v;
-}
-
-constexpr int LPP = 4;   // lanes per point: one observation each (a C2 point has ~4), partial sums merged by shuffles
-constexpr int LPL = 8;   // lanes per line  (a C2 line has ~7 observations)
-
-// asynchronous global -> shared copies (LDGSTS): whole chunks of records are in flight at once without holding registers
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 // The records of a warp's eight points are one contiguous span of rec_proj (factors of a landmark are contiguous,
 // landmarks consecutive): the warp copies it 32 records at a time into shared memory with coalesced 16-byte
@@ -725,10 +663,6 @@ __global__ void __launch_bounds__(128) k_direct(Dev D, DirectLists L, int nb_max
 // (b,b) blocks (21 + 21) and of the gradient (6 + 6) - 90 outputs, three per lane; SEGS_D warps per diagonal block
 // take the line / VP factors.  The lists are read 32 items at a time (coalesced) and handed round by shuffles, so the
 // record loads of consecutive items are independent and stay in flight together.
-// FP64 tensor-core MMA  D(8x8) += A(8x4) B(4x8)  (mma.sync m8n8k4: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}])
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
 constexpr int SEGS_D = 4;
 constexpr int DSTR = 26;   // doubles staged per item: [r | Ji | Jj] of a projection record; 14 of a line record, 7 of a VP record
 
@@ -1253,6 +1187,35 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
   k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
   n++;
   if (fk) { join_to(fk, st, 1); join_to(fk, st, 2); }
+  return n;
+}
+
+// Linearisation stage of the fused path: IMU + prior sweeps (the only factor records that still exist), point and line
+// linearisation with the factors evaluated in registers (uvs_lin.cu), IMU / prior tail, rank update.  Three strands:
+// main = points -> rank update, aux 0 = lines, aux 1 = IMU sweep -> prior sweep -> tail.
+int launch_build3_fused(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, int max_lines, int max_prior_n,
+                        cudaStream_t st, const Fork *fk) {
+  Build3Ctx c; make_ctx(base, lay, c);
+  int n = 0;
+  cudaStream_t s_lines = fk ? fk->aux[0] : st, s_tail = fk ? fk->aux[1] : st;
+  double *cost0 = D.acc + ACC_COST0;
+  if (fk) fork_from(fk, st, 2);
+  n += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, s_tail);
+  n += launch_prior(D, max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, s_tail);
+  n += launch_lin_points(D, P, base, lay, st);
+  n += launch_lin_lines(D, P, base, lay, max_frames, max_lines, s_lines);
+  if (D.nranks <= 1 || D.rank == 0) {   // factor-parallel mode: IMU factors and the prior belong to rank 0
+    const size_t tsm = std::max((size_t)IMU_G * REC_IMU * sizeof(double), (size_t)(max_prior_n + 2) * sizeof(int));
+    k_window_tail<<<dim3(D.B, 2), TT, tsm, s_tail>>>(D, max_prior_n);
+    n++;
+  }
+  if (fk) join_to(fk, st, 0);
+  const size_t smem = build3_smem(max_frames, false, max_prior_n);
+  static size_t raised = 0;
+  if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
+  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
+  n++;
+  if (fk) join_to(fk, st, 1);
   return n;
 }
 

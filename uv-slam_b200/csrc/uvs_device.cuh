@@ -65,6 +65,7 @@ struct Dev {
   int nF, nP, nL, nProj, nLobs, nVobs, nImu, nCam, nPriorR, nPriorBlk;
   int estimate_td;          // uniform over the batch
   int rank, nranks;         // factor-parallel multi-GPU: landmark k is owned by rank k % nranks
+  int max_frames, max_lines, max_lobs;   // largest per-window counts of the batch (grids of the window-chunk kernels)
   // per-window tables [B+1]
   const int *frame_off, *point_off, *line_off, *proj_off, *lobs_off, *vobs_off, *imu_off, *cam_off, *prior_off,
       *pblk_off;
@@ -98,6 +99,7 @@ struct Dev {
   int *pt_begin, *pt_end;   // [nP] proj factor range of a point
   int *ln_begin, *ln_end;   // [nL] line obs range of a line
   int *pt_win, *ln_win;     // [nP], [nL]
+  int *pt_order;            // [nP] processing order of the fused point kernel: per window sorted by (anchor frame, track length)
   int *pblk_col, *pblk_cam, *pblk_row;   // column in J0, tangent offset in the window (-1 const), state row
   double *imu_sqrt_info;    // [nImu][225]
   double *chain_lw;         // [B][chain_lw_stride] L_w blocks of the chain-mode reduced solve (k_chol_chain)

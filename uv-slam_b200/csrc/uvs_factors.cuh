@@ -80,8 +80,10 @@ __device__ __forceinline__ void proj_eval(const double *__restrict__ pose_i, con
   red(mtmul(Ric, skew(pbj)), Jj + 3, 1.0);
   const m33 T = mmul(B, Ric);  // tmp_r
   if (!want_ex) {
+    if (Jex) {   // callers that never use the extrinsic block pass no storage for it
 #pragma unroll
-    for (int k = 0; k < 6; k++) { Jex[k] = 0.0; Jex[ld + k] = 0.0; }
+      for (int k = 0; k < 6; k++) { Jex[k] = 0.0; Jex[ld + k] = 0.0; }
+    }
   } else {
     m33 L = B;  // ric^T (Rj^T Ri - I) = B - ric^T
 #pragma unroll

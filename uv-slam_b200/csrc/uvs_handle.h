@@ -65,6 +65,7 @@ struct UvsHandle {
   std::vector<int> win_flags;
   // offsets of the state sections inside the device arena (buffer 0) for download
   size_t o_pose0 = 0, o_state_bytes = 0;
+  size_t in_sb = 0, in_ex = 0, in_td = 0, in_inv = 0, in_ortho = 0, in_ric = 0, in_tic = 0;   // input-region offsets (uvs_upload_state)
   size_t o_reduce = 0, reduce_doubles = 0;   // [Smat | gS | gfull | colsq] block for the multi-GPU exchange
   int64_t launches = 0;
   float last_solve_ms = 0.f, last_sweep_ms = 0.f;
@@ -79,6 +80,8 @@ struct UvsHandle {
   int profiling = 0;
   int max_frames = 0; bool any_ex = false;
   bool use_build3 = false;                    // atomics-free landmark path (uvs_build3.cu)
+  bool fused = false;                         // factors evaluated inside the landmark elimination (uvs_lin.cu): no point / line records
+  int max_lines = 0;                          // most lines in one window (grid of k_lin_lines)
   bool chain_ok = false;                      // speed-bias blocks form a chain in every window: k_chol_chain
   uvs::Build3Layout b3{};
   size_t o_b3 = 0;

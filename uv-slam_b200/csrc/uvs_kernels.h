@@ -59,6 +59,17 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
                   cudaStream_t st, const Fork *fk);
 int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st, const Fork *fk);
 int launch_build_cam(const Dev &D, int max_prior_n, cudaStream_t st);
+// fused linearisation (uvs_lin.cu): factors evaluated in registers, no Jacobian records in HBM; launch_build3_fused is the
+// build stage of that path (point + line linearisation, IMU / prior tail, rank update)
+int launch_build3_fused(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, int max_lines, int max_prior_n,
+                        cudaStream_t st, const Fork *fk);
+
+// uvs_lin.cu
+int launch_prep_point_order(const Dev &D, int *key_scratch, cudaStream_t st);
+size_t lin_lines_smem(int max_frames);
+int lin_max_line_obs();
+int launch_lin_points(const Dev &D, const Params &P, char *base, const Build3Layout &lay, cudaStream_t st);
+int launch_lin_lines(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, int max_lines, cudaStream_t st);
 
 // uvs_solve.cu
 int chol_packed_limit(size_t max_smem);

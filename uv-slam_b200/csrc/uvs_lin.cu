@@ -1,0 +1,514 @@
+// uvs_lin.cu — fused linearisation of the landmark factors: Jacobian evaluation + landmark elimination + direct
+// terms in ONE pass per landmark type, so that no point / line / VP Jacobian record is ever written to HBM
+// ("fully fused (never write J to HBM) for the iteration-rate config").
+//
+// What Ceres does per residual block behind ceres::Solve (vins_estimator/src/estimator.cpp:982-994): Evaluate
+// (ProjectionFactor projection_factor.cpp:22-175, LineProjectionFactor / VPProjectionFactor via AutoDiff,
+// line_projection_factor.h:16-60, vp_projection_factor.h:19-66), loss correction (marginalization_factor.cpp:37-68
+// restates it), J^T J accumulation and the SPARSE_SCHUR elimination of the landmark blocks.
+//
+//   k_lin_points   a LANE owns a point, step k of the loop evaluates the k-th factor of every lane's point.  Points are
+//                  processed in an order sorted by (anchor frame, track length) (k_prep_point_order, once per upload), so
+//                  the 32 factors of a step mostly share their camera-block pair (i, j): their [r | Ji | Jj] rows sit in a
+//                  shared-memory stage and G^T G (G = [J_i | J_j | r]) of the whole group is ONE chain of FP64 tensor-core
+//                  MMAs, flushed with ~3 reductions per factor into the window's system.  The lane keeps the point's
+//                  sums (E, g, W_i), parks the unscaled W_j blocks in the Y stash and rescales them at the end.
+//   k_lin_lines    a lane GROUP (8 lanes) owns a line, one observation (+ its VP factor) per lane, evaluated through the
+//                  per-frame tables of uvs_linefast.cuh into a shared-memory stage; the elimination of the 4x4 block
+//                  then reads the stage instead of HBM records, and the diagonal direct terms are grouped by frame on
+//                  the tensor cores.
+// Both write the same stash (uvs_stash.cuh) as k_core_points / k_core_lines of uvs_build3.cu; the rank update
+// (k_window_system), the IMU / prior tail and the back-substitution are shared with that path.
+#include <algorithm>
+
+#include "uvs_device.cuh"
+#include "uvs_factors.cuh"
+#include "uvs_kernels.h"
+#include "uvs_linefast.cuh"
+#include "uvs_stash.cuh"
+
+namespace uvs {
+
+// ------------------------------------------------------------------------------------------------
+// processing order of the points of every window: sorted by (anchor frame, track length descending); points without
+// factors last.  One CTA per window; keys in `key` (scratch, [nP]).
+__global__ void __launch_bounds__(256) k_prep_point_order(Dev D, int *__restrict__ key) {
+  const int w = blockIdx.x;
+  const int p0 = D.point_off[w], np = D.point_off[w + 1] - p0, fo = D.frame_off[w];
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    const int gp = p0 + p, n = D.pt_end[gp] - D.pt_begin[gp];
+    key[gp] = n <= 0 ? 0x7fffffff : ((D.proj_idx[D.pt_begin[gp]].x - fo) << 8 | (255 - min(n, 255)));
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    const int kp = key[p0 + p];
+    int rank = 0;
+    for (int q = 0; q < np; q++) { const int kq = key[p0 + q]; rank += (kq < kp || (kq == kp && q < p)) ? 1 : 0; }
+    D.pt_order[p0 + rank] = p0 + p;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int LP_NT = 128;   // threads (= points) per CTA of k_lin_points
+constexpr int PST = 27;      // stage row: [r(2) | Ji 2x6 | Jj 2x6] + 1 (odd stride: conflict-free stores)
+
+__global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash S) {
+  __shared__ double stage_all[LP_NT * PST];
+  __shared__ unsigned char mlist_all[LP_NT / 32][32];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *stage = stage_all + warp * 32 * PST;
+  double *row = stage + lane * PST;
+  unsigned char *mlist = mlist_all[warp];
+  const int t = blockIdx.x * LP_NT + threadIdx.x;
+  bool act = t < D.nP;
+  int gp = 0, w = 0, f0 = 0, n = 0;
+  if (act) { gp = D.pt_order[t]; w = D.pt_win[gp]; act = (D.ctl[w].state & WS_ACTIVE) != 0; }
+  const int mp = S.mp;
+  double *Y = nullptr, *ph = nullptr;
+  if (act) {
+    Y = S.Y + (colbase(D, w) + (gp - D.point_off[w])) * mp;
+    ph = S.ph + 4 * (size_t)gp;
+    f0 = D.pt_begin[gp]; n = D.pt_end[gp] - f0;
+    const bool mine = D.nranks <= 1 || (gp % D.nranks) == D.rank;
+    // the column was zero-filled at upload and its sparsity pattern never changes: only the blocks are rewritten
+    if (n <= 0 || !mine) { ph[1] = 0.0; act = false; }
+  }
+  if (!act) n = 0;
+  const int nmax = __reduce_max_sync(full, n);
+  if (nmax == 0) return;   // uniform over the warp
+  int fo = 0, co = 0, d = 0, cur = 0;
+  long long s_off = 0;
+  if (act) { fo = D.frame_off[w]; co = D.cam_off[w]; d = D.cam_off[w + 1] - co; s_off = D.S_off[w]; cur = D.cur[w]; }
+  const double *ex = D.ex[cur] + 7 * (size_t)w;
+  const double lam = act ? D.inv_depth[cur][gp] : 1.0;
+  double colsq = 0.0, gk = 0.0, half = 0.0;
+  double wa[6] = {0, 0, 0, 0, 0, 0};
+  int row_i = 0;
+  // fragment offsets inside a staged row (see k_direct_fused): kind 2 = anchor frame before the observing frame
+  const int fcol = lane >> 2, frow = lane & 1, fsub = (lane >> 1) & 1;
+  const int o0_k2 = (fcol < 6 ? 2 + fcol : 8 + fcol) + 6 * frow, o0_k3 = (fcol < 6 ? 14 + fcol : fcol - 4) + 6 * frow;
+  const int o1_k2 = fcol < 4 ? 16 + fcol + 6 * frow : (fcol == 4 ? frow : -1);
+  const int o1_k3 = fcol < 4 ? 4 + fcol + 6 * frow : (fcol == 4 ? frow : -1);
+  for (int k = 0; k < nmax; k++) {
+    const bool has = k < n;
+    int ri = -1, rj = -1;
+    if (has) {
+      const int f = f0 + k;
+      const int4 ix = D.proj_idx[f];
+      ri = ix.x; rj = ix.y; row_i = ri;
+      const double *oi = D.proj_pts_i + 3 * (size_t)f, *oj = D.proj_pts_j + 3 * (size_t)f;
+      const d3 pts_i = mk3(__ldg(oi), __ldg(oi + 1), __ldg(oi + 2)), pts_j = mk3(__ldg(oj), __ldg(oj + 1), __ldg(oj + 2));
+      double jl[2], hr;
+      proj_eval<true, false>(D.pose[cur] + 7 * (size_t)ri, D.pose[cur] + 7 * (size_t)rj, ex, lam, pts_i, pts_j, P.S, nullptr, false,
+                             P.cauchy_point, true, 6, row, row + 2, row + 14, nullptr, jl, nullptr, &hr);
+      half += hr;
+      const double j0 = jl[0], j1 = jl[1];
+      colsq += j0 * j0 + j1 * j1;
+      gk += j0 * row[0] + j1 * row[1];
+      double u[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        wa[c] += row[2 + c] * j0 + row[8 + c] * j1;
+        u[c] = row[14 + c] * j0 + row[20 + c] * j1;
+      }
+      // parked unscaled, rescaled below (a block is 48 bytes, 16-byte aligned)
+      double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * (rj - fo));
+      y2[0] = make_double2(u[0], u[1]); y2[1] = make_double2(u[2], u[3]); y2[2] = make_double2(u[4], u[5]);
+    }
+    __syncwarp();
+    // ---- direct terms of this step's factors, grouped by camera-block pair
+    unsigned todo = __ballot_sync(full, has);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int li = __shfl_sync(full, ri, leader), lj = __shfl_sync(full, rj, leader);
+      const unsigned grp = __ballot_sync(full, has && ri == li && rj == lj);
+      todo &= ~grp;
+      const int m = __popc(grp);
+      if (grp >> lane & 1u) mlist[__popc(grp & ((1u << lane) - 1u))] = (unsigned char)lane;
+      __syncwarp();
+      const bool swp = li > lj;   // block a = the earlier frame
+      const int o0 = swp ? o0_k3 : o0_k2, o1 = swp ? o1_k3 : o1_k2;
+      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+      for (int s = 0; 2 * s < m; s++) {
+        const int it = 2 * s + fsub;
+        double g0 = 0.0, g1 = 0.0;
+        if (it < m) {
+          const double *rec = stage + (int)mlist[it] * PST;
+          g0 = rec[o0];
+          if (o1 >= 0) g1 = rec[o1];
+        }
+        dmma884(c00, g0, g0);
+        dmma884(c01, g0, g1);
+        dmma884(c11, g1, g1);
+      }
+      const int lfo = __shfl_sync(full, fo, leader), lco = __shfl_sync(full, co, leader), ld = __shfl_sync(full, d, leader);
+      const long long lso = __shfl_sync(full, s_off, leader);
+      double *Sg = D.Smat + lso;
+      const int ra = 15 * ((swp ? lj : li) - lfo), rb = 15 * ((swp ? li : lj) - lfo);
+      // entry (p, q) of G^T G, p <= q: columns 0..5 -> block a, 6..11 -> block b, 12 -> gradient
+      auto put = [&](int p, int q, double v) {
+        if (p >= 12 || q > 12) return;
+        const int gpp = p < 6 ? ra + p : rb + p - 6;
+        if (q == 12) { atomicAdd(D.gS + lco + gpp, v); atomicAdd(D.gfull + lco + gpp, v); return; }
+        if (p > q) return;
+        const int gq = q < 6 ? ra + q : rb + q - 6;
+        atomicAdd(Sg + (size_t)gpp * ld + gq, v);
+        if (p == q) atomicAdd(D.colsq_cam + lco + gpp, v);
+      };
+      const int pr = lane >> 2, pc = 2 * (lane & 3);
+      put(pr, pc, c00[0]); put(pr, pc + 1, c00[1]);
+      put(pr, 8 + pc, c01[0]); put(pr, 9 + pc, c01[1]);
+      put(8 + pr, 8 + pc, c11[0]); put(8 + pr, 9 + pc, c11[1]);
+      __syncwarp();
+    }
+  }
+  add_window_scalar(D.acc + ACC_COST0, ACC_STRIDE, w, half, act);
+  if (!act) return;
+  // ---- elimination of the 1x1 landmark block (same arithmetic as k_core_points)
+  double sk;
+  if (!D.ctl[w].have_scale) { sk = 1.0 / (1.0 + sqrt(colsq)); D.scale_pt[gp] = sk; }
+  else sk = D.scale_pt[gp];
+  const double Et = sk * sk * colsq;
+  const double D2 = clamp4(Et, P.min_lm_diag, P.max_lm_diag) / D.ctl[w].radius;
+  const double sh = rsqrt(Et + D2);
+  const double ysc = sk * sh;
+  for (int k = 0; k < n; k++) {
+    double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * (D.proj_idx[f0 + k].y - fo));
+#pragma unroll
+    for (int c = 0; c < 3; c++) { const double2 v = y2[c]; y2[c] = make_double2(ysc * v.x, ysc * v.y); }
+  }
+  {
+    double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * (row_i - fo));
+    y2[0] = make_double2(ysc * wa[0], ysc * wa[1]); y2[1] = make_double2(ysc * wa[2], ysc * wa[3]); y2[2] = make_double2(ysc * wa[4], ysc * wa[5]);
+  }
+  Y[mp - 2] = sk * gk * sh;
+  ph[0] = sk; ph[1] = sh; ph[2] = D2;
+  atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fabs(gk));
+}
+
+// ------------------------------------------------------------------------------------------------
+// lines
+constexpr int LL_NT = 128;                 // threads per CTA: 16 lines x 8 lanes
+constexpr int LSLOT = 12;                  // observations staged per line (<= frames of a window on this path)
+constexpr int WSLOTS = (32 / LPL) * LSLOT; // staged observations per warp
+// doubles of shared memory per warp: line + VP stage, frame / VP flag of every slot (ints), row list of a frame group (ints)
+constexpr int LL_WARP_DOUBLES = WSLOTS * (REC_LINE + REC_VP) + WSLOTS + (3 * WSLOTS + 1) / 2;
+
+template <bool kJac>
+struct LineVpSinkF {
+  LineSink<kJac, false> ln;
+  VpSink<kJac, false> vp;
+  bool has_vp;
+  __device__ __forceinline__ void base(d3 n, d3 dd) { ln.base(n, dd); if (has_vp) vp.base(n, dd); }
+  __device__ __forceinline__ void partial(int k, d3 dn, d3 du) { ln.partial(k, dn, du); if (has_vp) vp.partial(k, dn, du); }
+};
+
+// grid (ceil(max lines per window / 16), B): a CTA works on 16 lines of ONE window, so the frame tables are per CTA
+__global__ void __launch_bounds__(LL_NT, 3) k_lin_lines(Dev D, Params P, Stash S, int max_frames) {
+  extern __shared__ __align__(16) double lsm[];
+  const unsigned full = 0xffffffffu;
+  const int w = blockIdx.y;
+  const int nl = D.line_off[w + 1] - D.line_off[w];
+  const int l0 = blockIdx.x * (LL_NT / LPL);
+  if (l0 >= nl) return;
+  if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // shared: frame tables [max_frames][FT_STRIDE] | per warp: line stage [WSLOTS][REC_LINE], VP stage [WSLOTS][REC_VP],
+  //         frame of a slot (-1 = empty), VP flag, row list of the direct-term grouping
+  double *ftab = lsm;
+  double *wbase = lsm + ((max_frames * FT_STRIDE + 1) & ~1) + warp * LL_WARP_DOUBLES;
+  double *lstage = wbase, *vstage = wbase + WSLOTS * REC_LINE;
+  int *sframe = reinterpret_cast<int *>(vstage + WSLOTS * REC_VP);        // [WSLOTS]
+  int *svp = sframe + WSLOTS;                                              // [WSLOTS]
+  int *rowlist = svp + WSLOTS;                                             // [3 * WSLOTS] rows of one frame group
+  const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
+  const int cur = D.cur[w];
+  for (int e = threadIdx.x; e < 3 * F; e += LL_NT) {
+    const int f = e / 3, m = e - 3 * f;
+    line_frame_table(D.pose[cur] + 7 * (size_t)(fo + f), D.ric + 9 * (size_t)w, D.tic + 3 * (size_t)w, m, ftab + f * FT_STRIDE);
+  }
+  for (int e = lane; e < WSLOTS; e += 32) { sframe[e] = -1; svp[e] = 0; }
+  __syncthreads();
+
+  const int grp = lane / LPL, sub = lane - grp * LPL;
+  const int li = l0 + threadIdx.x / LPL;
+  const unsigned gmask = ((1u << LPL) - 1u) << (lane & ~(LPL - 1));
+  bool act = li < nl;   // uniform over the lane group
+  const int gl = D.line_off[w] + li;
+  const int mp = S.mp;
+  int f0 = 0, n = 0;
+  double *Y = nullptr, *hd = nullptr;
+  if (act) {
+    f0 = D.ln_begin[gl]; n = D.ln_end[gl] - f0;
+    Y = S.Y + (colbase(D, w) + (D.point_off[w + 1] - D.point_off[w]) + 4LL * li) * mp;   // 4 columns
+    hd = S.lh + 24 * (size_t)gl;
+    const bool mine = D.nranks <= 1 || (gl % D.nranks) == D.rank;
+    // Linv[0][0] = 0 marks "no step" for the back-substitution
+    if (n <= 0 || !mine) { if (sub == 0) hd[8] = 0.0; act = false; }
+  }
+  if (!act) n = 0;
+  if (n > LSLOT) n = LSLOT;   // excluded at upload (the batch takes the record path instead)
+  // ---- per-line table: lane c < 4 of the group takes sin / cos of parameter c
+  LineTab LT;
+  {
+    double sv = 0.0, cv = 1.0;
+    if (act && sub < 4) sincos(D.ortho[cur][4 * (size_t)gl + sub], &sv, &cv);
+    const int gb = lane & ~(LPL - 1);
+    const double sa = __shfl_sync(full, sv, gb), ca = __shfl_sync(full, cv, gb), sb = __shfl_sync(full, sv, gb + 1), cb = __shfl_sync(full, cv, gb + 1);
+    const double sc = __shfl_sync(full, sv, gb + 2), cc = __shfl_sync(full, cv, gb + 2), sp = __shfl_sync(full, sv, gb + 3), cp = __shfl_sync(full, cv, gb + 3);
+    line_table(sa, ca, sb, cb, sc, cc, sp, cp, LT);
+  }
+  // ---- evaluation: observation f of the line -> slot grp * LSLOT + f of the warp's stage
+  double half = 0.0;
+  for (int f = sub; f < n; f += LPL) {
+    const int slot = grp * LSLOT + f;
+    const int4 ix = D.line_idx4[f0 + f];
+    const double *sp = D.line_sp + 2 * (size_t)(f0 + f), *ep = D.line_ep + 2 * (size_t)(f0 + f);
+    LineVpSinkF<true> sink;
+    sink.ln.spx = __ldg(sp); sink.ln.spy = __ldg(sp + 1); sink.ln.epx = __ldg(ep); sink.ln.epy = __ldg(ep + 1);
+    sink.ln.lf = P.line_factor; sink.ln.loss_a = P.cauchy_line; sink.ln.correct = true; sink.ln.PW = 6;
+    sink.has_vp = ix.w >= 0;
+    sink.vp.half_rho = 0.0;
+    if (ix.w >= 0) {
+      const double *vp = D.vp_dir + 3 * (size_t)ix.w;
+      sink.vp.vp = mk3(__ldg(vp), __ldg(vp + 1), __ldg(vp + 2));
+      sink.vp.vf = P.vp_factor; sink.vp.loss_a = P.cauchy_vp; sink.vp.correct = true;
+    }
+    double *tl = lstage + slot * REC_LINE, *tv = vstage + slot * REC_VP;
+    sink.ln.out_r = tl; sink.ln.out_jp = tl + 2; sink.ln.out_jl = tl + 14;
+    sink.vp.out_r = tv; sink.vp.out_jp = tv + 1; sink.vp.out_jl = tv + 7;
+    line_obs_eval<true, true>(ftab + (ix.x - fo) * FT_STRIDE, LT, sink);
+    half += sink.ln.half_rho + sink.vp.half_rho;
+    sframe[slot] = ix.x - fo;
+    svp[slot] = ix.w >= 0 ? 1 : 0;
+  }
+  add_window_scalar(D.acc + ACC_COST0, ACC_STRIDE, w, half, act);
+  __syncwarp();
+
+  // ---- diagonal direct terms of the warp's observations, grouped by frame: G = [J_pose (6) | r | 0], one row per
+  //      residual row (two per line observation, one per VP factor), G^T G on the FP64 tensor cores
+  {
+    const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+    double *Sg = D.Smat + D.S_off[w];
+    // slots of this lane: lane and lane + 32 (WSLOTS = 48)
+    const int s0 = lane, s1 = lane + 32;
+    const int fr0 = sframe[s0], fr1 = s1 < WSLOTS ? sframe[s1] : -1;
+    const int vp0 = svp[s0], vp1 = s1 < WSLOTS ? svp[s1] : 0;
+    unsigned present = 0;   // frames that occur in this warp
+    {
+      unsigned mine = (fr0 >= 0 ? 1u << fr0 : 0u) | (fr1 >= 0 ? 1u << fr1 : 0u);
+      present = __reduce_or_sync(full, mine);
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    while (present) {
+      const int jj = __ffs(present) - 1;
+      present &= present - 1;
+      const unsigned b0 = __ballot_sync(full, fr0 == jj), b1 = __ballot_sync(full, fr1 == jj);
+      const unsigned v0 = __ballot_sync(full, fr0 == jj && vp0), v1 = __ballot_sync(full, fr1 == jj && vp1);
+      const int base_l1 = 2 * __popc(b0), base_v0 = base_l1 + 2 * __popc(b1), base_v1 = base_v0 + __popc(v0);
+      const int total = base_v1 + __popc(v1);
+      // row descriptor: offset of the six pose-Jacobian entries | offset of the residual << 16 (doubles from lstage)
+      if (fr0 == jj) {
+        const int o = s0 * REC_LINE, p = 2 * __popc(b0 & lt);
+        rowlist[p] = (o + 2) | (o << 16); rowlist[p + 1] = (o + 8) | ((o + 1) << 16);
+        if (vp0) { const int ov = WSLOTS * REC_LINE + s0 * REC_VP; rowlist[base_v0 + __popc(v0 & lt)] = (ov + 1) | (ov << 16); }
+      }
+      if (fr1 == jj) {
+        const int o = s1 * REC_LINE, p = base_l1 + 2 * __popc(b1 & lt);
+        rowlist[p] = (o + 2) | (o << 16); rowlist[p + 1] = (o + 8) | ((o + 1) << 16);
+        if (vp1) { const int ov = WSLOTS * REC_LINE + s1 * REC_VP; rowlist[base_v1 + __popc(v1 & lt)] = (ov + 1) | (ov << 16); }
+      }
+      __syncwarp();
+      double cc[2] = {0.0, 0.0};
+      const int fcol = lane >> 2, krow = lane & 3;
+      for (int r0 = 0; r0 < total; r0 += 4) {
+        double g = 0.0;
+        if (r0 + krow < total && fcol < 7) {
+          const int ds = rowlist[r0 + krow];
+          g = fcol < 6 ? lstage[(ds & 0xffff) + fcol] : lstage[ds >> 16];
+        }
+        dmma884(cc, g, g);
+      }
+      const int ra = 15 * jj;
+      const int pr = lane >> 2, pc = 2 * (lane & 3);
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int p = pr, q = pc + e;
+        if (p >= 6 || q > 6) continue;
+        if (q == 6) { atomicAdd(D.gS + co + ra + p, cc[e]); atomicAdd(D.gfull + co + ra + p, cc[e]); }
+        else if (p <= q) {
+          atomicAdd(Sg + (size_t)(ra + p) * d + ra + q, cc[e]);
+          if (p == q) atomicAdd(D.colsq_cam + co + ra + p, cc[e]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (!act) return;   // uniform over the lane group
+
+  // ---- elimination of the 4x4 landmark block (same arithmetic as k_core_lines; records come from the stage)
+  auto line_rec = [&](int f) { return lstage + (grp * LSLOT + f) * REC_LINE; };
+  auto vp_rec = [&](int f) { return vstage + (grp * LSLOT + f) * REC_VP; };
+  auto has_vp = [&](int f) { return svp[grp * LSLOT + f] != 0; };
+  double E[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
+  for (int f = sub; f < n; f += LPL) {
+    const double2 *r2 = reinterpret_cast<const double2 *>(line_rec(f));
+    const double2 rr = r2[0];
+#pragma unroll
+    for (int rw_ = 0; rw_ < 2; rw_++) {
+      const double2 a01 = r2[7 + 2 * rw_], a23 = r2[8 + 2 * rw_];
+      const double a0 = a01.x, a1 = a01.y, a2 = a23.x, a3 = a23.y, rw = rw_ ? rr.y : rr.x;
+      E[0] += a0 * a0; E[1] += a0 * a1; E[2] += a0 * a2; E[3] += a0 * a3; E[4] += a1 * a1; E[5] += a1 * a2; E[6] += a1 * a3;
+      E[7] += a2 * a2; E[8] += a2 * a3; E[9] += a3 * a3;
+      g[0] += a0 * rw; g[1] += a1 * rw; g[2] += a2 * rw; g[3] += a3 * rw;
+    }
+    if (has_vp(f)) {
+      const double *q = vp_rec(f);
+      const double a0 = q[7], a1 = q[8], a2 = q[9], a3 = q[10], rw = q[0];
+      E[0] += a0 * a0; E[1] += a0 * a1; E[2] += a0 * a2; E[3] += a0 * a3; E[4] += a1 * a1; E[5] += a1 * a2; E[6] += a1 * a3;
+      E[7] += a2 * a2; E[8] += a2 * a3; E[9] += a3 * a3;
+      g[0] += a0 * rw; g[1] += a1 * rw; g[2] += a2 * rw; g[3] += a3 * rw;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 10; k++) E[k] = group_sum<LPL>(gmask, E[k]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) g[k] = group_sum<LPL>(gmask, g[k]);
+  double s[4];
+  const double Ed[4] = {E[0], E[4], E[7], E[9]};
+  if (!D.ctl[w].have_scale) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) { s[c] = 1.0 / (1.0 + sqrt(Ed[c])); if (sub == 0) D.scale_ln[4 * (size_t)gl + c] = s[c]; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; c++) s[c] = D.scale_ln[4 * (size_t)gl + c];
+  }
+  // M = D_s E D_s + D^2 (lower), Cholesky, inverse of the factor
+  const double radius = D.ctl[w].radius;
+  double M[4][4], D2[4];
+  M[0][0] = s[0] * s[0] * E[0]; M[1][0] = s[1] * s[0] * E[1]; M[2][0] = s[2] * s[0] * E[2]; M[3][0] = s[3] * s[0] * E[3];
+  M[1][1] = s[1] * s[1] * E[4]; M[2][1] = s[2] * s[1] * E[5]; M[3][1] = s[3] * s[1] * E[6];
+  M[2][2] = s[2] * s[2] * E[7]; M[3][2] = s[3] * s[2] * E[8]; M[3][3] = s[3] * s[3] * E[9];
+#pragma unroll
+  for (int c = 0; c < 4; c++) { D2[c] = clamp4(M[c][c], P.min_lm_diag, P.max_lm_diag) / radius; M[c][c] += D2[c]; }
+  double L[4][4], Li[4][4];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    double dj = M[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) dj -= L[j][k] * L[j][k];
+    if (!(dj > 0.0)) ok = false;
+    const double id = rsqrt(dj);
+    L[j][j] = dj * id;
+#pragma unroll
+    for (int i = j + 1; i < 4; i++) {
+      double tt = M[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) tt -= L[i][k] * L[j][k];
+      L[i][j] = tt * id;
+    }
+  }
+  if (!ok) {
+    if (sub == 0) { hd[8] = 0.0; atomicAdd(D.acc + (size_t)w * ACC_STRIDE + ACC_FAIL, 1.0); }
+    return;
+  }
+#pragma unroll
+  for (int col = 0; col < 4; col++)
+#pragma unroll
+    for (int i = col; i < 4; i++) {
+      double tt = (i == col) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = col; k < i; k++) tt -= L[i][k] * Li[k][col];
+      Li[i][col] = tt / L[i][i];
+    }
+  if (sub == 0) {
+    // z = L^-1 (D_s g)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      double tt = 0.0;
+#pragma unroll
+      for (int k = 0; k <= c; k++) tt += Li[c][k] * s[k] * g[k];
+      Y[c * mp + mp - 2] = tt; hd[c] = s[c]; hd[4 + c] = D2[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) hd[8 + 4 * i + k] = k <= i ? Li[i][k] : 0.0;
+    atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fmax(fmax(fabs(g[0]), fabs(g[1])), fmax(fabs(g[2]), fabs(g[3]))));
+  }
+  // Y blocks of this lane's observations
+  for (int f = sub; f < n; f += LPL) {
+    const double2 *r2 = reinterpret_cast<const double2 *>(line_rec(f));
+    const double *q = has_vp(f) ? vp_rec(f) : nullptr;
+    double *Yf = Y + 6 * sframe[grp * LSLOT + f];
+    double jl[3][4], jp[2][6];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const double2 a = r2[7 + c], b2 = r2[9 + c];
+      jl[0][2 * c] = a.x * s[2 * c]; jl[0][2 * c + 1] = a.y * s[2 * c + 1];
+      jl[1][2 * c] = b2.x * s[2 * c]; jl[1][2 * c + 1] = b2.y * s[2 * c + 1];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) jl[2][c] = q ? q[7 + c] * s[c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const double2 a = r2[1 + c], b2 = r2[4 + c];
+      jp[0][2 * c] = a.x; jp[0][2 * c + 1] = a.y; jp[1][2 * c] = b2.x; jp[1][2 * c + 1] = b2.y;
+    }
+#pragma unroll
+    for (int p = 0; p < 6; p += 2) {   // two rows at a time: the 48-byte block of a column is written as three 128-bit words
+      double tt[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double a0 = jp[0][p + h], a1 = jp[1][p + h], a2 = q ? q[1 + p + h] : 0.0;
+        double W4[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) W4[c] = a0 * jl[0][c] + a1 * jl[1][c] + a2 * jl[2][c];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          double t1 = 0.0;
+#pragma unroll
+          for (int k = 0; k <= c; k++) t1 += W4[k] * Li[c][k];
+          tt[h][c] = t1;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) *reinterpret_cast<double2 *>(Yf + c * mp + p) = make_double2(tt[0][c], tt[1][c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int cdivl(int a, int b) { return (a + b - 1) / b; }
+
+int launch_prep_point_order(const Dev &D, int *key_scratch, cudaStream_t st) {
+  if (D.nP == 0) return 0;
+  k_prep_point_order<<<D.B, 256, 0, st>>>(D, key_scratch);
+  return 1;
+}
+
+size_t lin_lines_smem(int max_frames) {
+  return ((size_t)((max_frames * FT_STRIDE + 1) & ~1) + (size_t)(LL_NT / 32) * LL_WARP_DOUBLES) * sizeof(double);
+}
+int lin_max_line_obs() { return LSLOT; }
+
+int launch_lin_points(const Dev &D, const Params &P, char *base, const Build3Layout &lay, cudaStream_t st) {
+  if (D.nP == 0) return 0;
+  Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp;
+  k_lin_points<<<cdivl(D.nP, LP_NT), LP_NT, 0, st>>>(D, P, S);
+  return 1;
+}
+
+int launch_lin_lines(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, int max_lines, cudaStream_t st) {
+  if (D.nL == 0 || max_lines == 0) return 0;
+  Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp;
+  const size_t smem = lin_lines_smem(max_frames);
+  static size_t raised = 0;
+  if (smem > raised) { cudaFuncSetAttribute(k_lin_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
+  k_lin_lines<<<dim3(cdivl(max_lines, LL_NT / LPL), D.B), LL_NT, smem, st>>>(D, P, S, max_frames);
+  return 1;
+}
+
+}  // namespace uvs

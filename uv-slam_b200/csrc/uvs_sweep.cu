@@ -21,6 +21,7 @@
 #include "uvs_factors.cuh"
 #include "uvs_imu.cuh"
 #include "uvs_kernels.h"
+#include "uvs_linefast.cuh"
 
 namespace uvs {
 
@@ -234,11 +235,13 @@ __global__ void __launch_bounds__(NT, 4) k_vp(Dev D, Params P, int mode, int can
 }
 
 // ------------------------------------------------------------------------------------------------
-// Solver path: line factor and the VP factor of the same (frame, line) observation in ONE pass - both are functions of
-// (n_c, d_c) and their ten partials, which cost ~10x more than either residual's own arithmetic.  A thread owns a line
-// observation; line_idx4[f].w names the paired VP observation (k_prep_vp) or -1.  The VP records of a tile are staged
-// in shared memory and written back record by record (the VP observations follow the order of the line observations,
-// so neighbouring records are adjacent in memory).
+// Line factor and the VP factor of the same (frame, line) observation in ONE pass, through per-frame and per-line
+// tables (uvs_linefast.cuh): a CTA works on up to NT consecutive line observations of ONE window (grid: chunks x
+// windows), first builds the window's frame tables (thread per (frame, quaternion coordinate)) and the sines / cosines
+// of its lines (one parameter per thread) in shared memory, then a thread owns an observation: ~500 FP64
+// instructions instead of the ~1500 of line_to_camera.  line_idx4[f].w names the paired VP observation (k_prep_vp) or
+// -1.  Records of a tile are staged in shared memory and written back as contiguous chunks (the VP observations follow
+// the order of the line observations, so neighbouring VP records are adjacent in memory).
 template <bool kJac>
 struct LineVpSink {
   LineSink<kJac, false> ln;
@@ -251,23 +254,48 @@ struct LineVpSink {
 template <bool kJac, int kOcc = 3>
 __global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode, int cand, double *__restrict__ out_line,
                                                 double *__restrict__ out_vp, double *cost, int cost_stride) {
-  extern __shared__ double smem[];
-  double *tile = smem;                                        // [NT][REC_LINE + 1]
-  double *vtile = smem + NT * (REC_LINE + 1);                 // [NT][REC_VP + 1]
+  extern __shared__ __align__(16) double smem[];
+  const int w = blockIdx.y;
+  const int a0 = D.lobs_off[w], a1 = D.lobs_off[w + 1];
+  const int first = a0 + blockIdx.x * NT;
+  if (first >= a1) return;
+  if (!wants<kJac>(D.ctl[w].state, mode)) return;
+  const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
+  double *ftab = smem;                                        // [F][FT_STRIDE]
+  double *lsc = ftab + ((D.max_frames * FT_STRIDE + 1) & ~1); // [NT][8] sin / cos of the four parameters, row of the line's first thread
+  double *tile = lsc + NT * 8;                                // [NT][REC_LINE + 1]   (Jacobian mode only)
+  double *vtile = tile + NT * (REC_LINE + 1);                 // [NT][REC_VP + 1]
   int *vslot = reinterpret_cast<int *>(vtile + NT * (REC_VP + 1));   // [NT] VP observation of the slot or -1
   unsigned char *ok = reinterpret_cast<unsigned char *>(vslot + NT);
-  const int first = blockIdx.x * NT;
+  const int buf = D.cur[w] ^ cand;
+  for (int e = threadIdx.x; e < 3 * F; e += NT) {
+    const int f = e / 3, m = e - 3 * f;
+    line_frame_table(D.pose[buf] + 7 * (size_t)(fo + f), D.ric + 9 * (size_t)w, D.tic + 3 * (size_t)w, m, ftab + f * FT_STRIDE);
+  }
   const int f = first + threadIdx.x;
-  bool valid = f < D.nLobs;
-  int4 ix = make_int4(0, 0, 0, -1);
+  bool valid = f < a1;
+  int4 ix = make_int4(0, 0, w, -1);
+  int lead = 0;   // thread of this CTA that holds the first observation of my line
   if (valid) {
     ix = D.line_idx4[f];
-    valid = wants<kJac>(D.ctl[ix.z].state, mode) && (D.nranks <= 1 || mode == 0 || (ix.y % D.nranks) == D.rank);
+    lead = max(D.ln_begin[ix.y], first) - first;
+    // thread lead + c takes parameter c; a line with fewer than four observations in this CTA: its last thread the rest
+    const int k = threadIdx.x - lead;
+    const int last = min(D.ln_end[ix.y], min(a1, first + NT)) - first - 1;
+    const double *lp = D.ortho[buf] + 4 * (size_t)ix.y;
+    for (int c = k; c < 4; c += (threadIdx.x == last ? 1 : 4)) {
+      double sv, cv;
+      sincos(__ldg(lp + c), &sv, &cv);
+      lsc[lead * 8 + 2 * c] = sv; lsc[lead * 8 + 2 * c + 1] = cv;
+    }
+    valid = D.nranks <= 1 || mode == 0 || (ix.y % D.nranks) == D.rank;
   }
+  __syncthreads();
   double half_rho = 0.0;
   int vi = -1;
   if (valid) {
-    const int buf = D.cur[ix.z] ^ cand;
+    LineTab LT;
+    { const double *q = lsc + lead * 8; line_table(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], LT); }
     const double *sp = D.line_sp + 2 * (size_t)f, *ep = D.line_ep + 2 * (size_t)f;
     LineVpSink<kJac> sink;
     sink.ln.spx = __ldg(sp); sink.ln.spy = __ldg(sp + 1); sink.ln.epx = __ldg(ep); sink.ln.epy = __ldg(ep + 1);
@@ -289,16 +317,15 @@ __global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode,
       sink.ln.out_r = rloc; sink.ln.out_jp = nullptr; sink.ln.out_jl = nullptr;
       sink.vp.out_r = rloc + 2; sink.vp.out_jp = nullptr; sink.vp.out_jl = nullptr;
     }
-    line_to_camera<kJac, true, false>(D.pose[buf] + 7 * (size_t)ix.x, D.ortho[buf] + 4 * (size_t)ix.y, D.ric + 9 * (size_t)ix.z,
-                                      D.tic + 3 * (size_t)ix.z, sink);
+    line_obs_eval<kJac, true>(ftab + (ix.x - fo) * FT_STRIDE, LT, sink);
     half_rho = sink.ln.half_rho + sink.vp.half_rho;
   }
-  if (cost) add_window_scalar(cost, cost_stride, ix.z, half_rho, valid);
+  if (cost) add_window_scalar(cost, cost_stride, w, half_rho, valid);
   if (kJac) {
     ok[threadIdx.x] = valid;
     vslot[threadIdx.x] = valid ? vi : -1;
-    const bool all_ok = __syncthreads_and(valid || f >= D.nLobs) != 0;
-    flush_tile<REC_LINE>(tile, ok, out_line, first, min(NT, D.nLobs - first), all_ok);
+    const bool all_ok = __syncthreads_and(valid || f >= a1) != 0;
+    flush_tile<REC_LINE>(tile, ok, out_line, first, min(NT, a1 - first), all_ok);
     {
       constexpr int DF = NT / REC_VP, DC = NT % REC_VP;
       int e = threadIdx.x;
@@ -550,14 +577,26 @@ int launch_vp(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int
   return 1;
 }
 
+static size_t line_vp_smem(int max_frames, bool jac) {
+  size_t dbl = (size_t)((max_frames * FT_STRIDE + 1) & ~1) + NT * 8;
+  if (jac) return (dbl + (size_t)NT * (REC_LINE + 1 + REC_VP + 1)) * sizeof(double) + NT * sizeof(int) + NT;
+  return dbl * sizeof(double);
+}
+
 int launch_line_vp(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out_line, double *out_vp, double *cost,
                    int cost_stride, cudaStream_t st) {
-  if (D.nLobs == 0) return 0;
-  const int grid = cdiv(D.nLobs, NT);
-  const size_t smem = (size_t)NT * (REC_LINE + 1 + REC_VP + 1) * sizeof(double) + NT * sizeof(int) + NT;
+  if (D.nLobs == 0 || D.max_lobs == 0) return 0;
+  const dim3 grid(cdiv(D.max_lobs, NT), D.B);
+  const size_t smem = line_vp_smem(D.max_frames, jac);
+  static size_t raised = 0;
+  if (jac && smem > raised) {
+    cudaFuncSetAttribute(k_line_vp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_line_vp<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    raised = smem;
+  }
   if (jac && sweep_occ("UVS_LINE_OCC", 3) == 4) k_line_vp<true, 4><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
   else if (jac) k_line_vp<true><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
-  else k_line_vp<false><<<grid, NT, 0, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  else k_line_vp<false, 4><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
   return 1;
 }
 
