@@ -336,6 +336,18 @@ int uvs_triangulate_lines(UvsHandle *h, int32_t n_frames, const double *Rs, cons
 typedef int (*UvsAllReduceFn)(void *user, void *device_buf, int64_t count, void *cuda_stream);
 int uvs_comm_init(UvsHandle *h, int32_t rank, int32_t nranks, UvsAllReduceFn reduce, void *user);
 
+/* The same mode with the library's own NCCL communicator (uvs_comm_init(h, ncclUniqueId, rank, nranks)):
+ * one rank calls uvs_comm_unique_id (ncclGetUniqueId; the 128 bytes of a ncclUniqueId), the caller hands the bytes to
+ * every rank by whatever means it has (MPI, a file, torch.distributed), every rank calls uvs_comm_init_nccl
+ * (ncclCommInitRank, collective).  Per LM iteration the library then issues ONE ncclAllReduce (sum, double) of
+ * [S | gS | g | column norms | per-window accumulators] on the handle's stream, plus one of 16 doubles per window for
+ * the candidate cost.  libnccl.so.2 is bound at run time (dlopen); nranks == 1 leaves the mode. */
+#define UVS_NCCL_UNIQUE_ID_BYTES 128
+int uvs_comm_unique_id(unsigned char *id /* [UVS_NCCL_UNIQUE_ID_BYTES] */);
+int uvs_comm_init_nccl(UvsHandle *h, const unsigned char *id, int32_t rank, int32_t nranks);
+/* number of all-reduces issued through this handle since creation */
+int64_t uvs_collective_count(const UvsHandle *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ EXPORTS = (
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
     "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate", "uvs_batch_solve_pipelined",
-    "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_set_graph_replay", "uvs_upload_state", "uvs_jacobian_sweep",
+    "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_set_graph_replay", "uvs_upload_state", "uvs_jacobian_sweep", "uvs_comm_unique_id", "uvs_comm_init_nccl", "uvs_collective_count",
 )
 
 N_STAGES = 10
@@ -80,6 +80,10 @@ def load_library():
     lib.uvs_last_sweep_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.uvs_comm_init.argtypes = [H, C.c_int32, C.c_int32, ALLREDUCE_FN, C.c_void_p]
     lib.uvs_reset_state.argtypes = [H]
+    lib.uvs_comm_unique_id.argtypes = [C.c_char_p]
+    lib.uvs_comm_init_nccl.argtypes = [H, C.c_char_p, C.c_int32, C.c_int32]
+    lib.uvs_collective_count.restype = C.c_int64
+    lib.uvs_collective_count.argtypes = [H]
     lib.uvs_preintegrate.argtypes = [H, C.c_int32, c_int32_p] + [c_double_p] * 14
     lib.uvs_triangulate_points.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p, c_double_p, C.c_double, c_double_p]
     lib.uvs_triangulate_lines.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p] + [c_double_p] * 5
@@ -309,6 +313,24 @@ class Solver:
                                                    frame_last.ctypes.data_as(c_int32_p), p(sp_first), p(ep_first), p(sp_last), p(ep_last),
                                                    p(out)), "uvs_triangulate_lines")
         return out
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId through the library (call on one rank, hand the 128 bytes to all)"""
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.uvs_comm_unique_id(buf)
+        if rc != 0:
+            raise UvsError(rc, "uvs_comm_unique_id", lib.uvs_status_string(rc).decode())
+        return buf.raw
+
+    def comm_init_nccl(self, unique_id: bytes, rank: int, nranks: int):
+        """factor-parallel mode over the library's own NCCL communicator (collective call)"""
+        assert len(unique_id) == 128
+        self._check(self.lib.uvs_comm_init_nccl(self.h, unique_id, rank, nranks), "uvs_comm_init_nccl")
+
+    def collective_count(self):
+        return int(self.lib.uvs_collective_count(self.h))
 
     def comm_init(self, rank, nranks, reduce_fn):
         """reduce_fn(device_ptr:int, count:int, stream:int) -> int, summing in place over ranks."""

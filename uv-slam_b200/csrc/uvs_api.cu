@@ -147,6 +147,7 @@ int uvs_destroy(UvsHandle *h) {
   if (h->h_active) cudaFreeHost(h->h_active);
   cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b); cudaEventDestroy(h->ev_c); cudaEventDestroy(h->ev_d);
   if (h->iter_exec) cudaGraphExecDestroy(h->iter_exec);
+  if (h->nccl_comm) uvs::nccl_destroy(h->nccl_comm);
   for (int k = 0; k < 3; k++) { cudaStreamDestroy(h->fork.aux[k]); cudaEventDestroy(h->fork.join[k]); }
   cudaEventDestroy(h->fork.fork);
   for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
@@ -248,7 +249,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
                o_proj_off = in.take((B + 1) * I), o_lobs_off = in.take((B + 1) * I), o_vobs_off = in.take((B + 1) * I),
                o_imu_off = in.take((B + 1) * I), o_cam_off = in.take((B + 1) * I), o_prior_off = in.take((B + 1) * I),
                o_pblk_off = in.take((B + 1) * I), o_S_off = in.take((B + 1) * 8), o_pJ_off = in.take((B + 1) * 8),
-               o_flags = in.take(B * I);
+               o_flags = in.take(B * I), o_frwin = in.take(nF * I);
   const size_t o_pose = in.take(nF * 7 * Dd), o_sb = in.take(nF * 9 * Dd), o_ex = in.take(B * 7 * Dd), o_td = in.take(B * Dd),
                o_inv = in.take(nP * Dd), o_ortho = in.take(nL * 4 * Dd);
   const size_t o_state_end = in.total;
@@ -274,20 +275,22 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   const size_t w_pose = wk.take(nF * 7 * Dd), w_sb = wk.take(nF * 9 * Dd), w_ex = wk.take(B * 7 * Dd), w_td = wk.take(B * Dd),
                w_inv = wk.take(nP * Dd), w_ortho = wk.take(nL * 4 * Dd);
   const size_t w_pristine = wk.take(o_state_end - o_pose);
-  const size_t w_cur = wk.take(B * I), w_ctl = wk.take(B * sizeof(WinCtl)), w_acc = wk.take((size_t)B * ACC_STRIDE * Dd),
-               w_sum = wk.take((size_t)B * sizeof(UvsSummary));
+  const size_t w_cur = wk.take(B * I), w_ctl = wk.take(B * sizeof(WinCtl)), w_sum = wk.take((size_t)B * sizeof(UvsSummary));
   const size_t w_pidx = wk.take(nProj * sizeof(int4)), w_lidx = wk.take(nLobs * sizeof(int4)), w_vidx = wk.take(nVobs * sizeof(int4)),
                w_iidx = wk.take(nImu * sizeof(int2));
   const size_t w_ptb = wk.take(nP * I), w_lnb = wk.take(nL * I);            // begin arrays (memset 0x7f together)
   const size_t w_pte = wk.take(nP * I), w_lne = wk.take(nL * I), w_ptw = wk.take(nP * I), w_lnw = wk.take(nL * I);
   const size_t w_pto = wk.take(nP * I), w_ptk = wk.take(nP * I);
+  const size_t w_ft0 = wk.take((size_t)nF * 48 * Dd), w_ft1 = wk.take((size_t)nF * 48 * Dd), w_ls0 = wk.take((size_t)nL * 8 * Dd), w_ls1 = wk.take((size_t)nL * 8 * Dd);
   const size_t w_icomp = wk.take((size_t)nImu * 108 * Dd);
   const size_t w_clw = wk.take(h->use_build3 ? (size_t)B * chol_chain_lw_doubles(max_frames) * Dd : 0);
   const size_t w_sqi = wk.take((size_t)nImu * 225 * Dd), w_prH = wk.take((size_t)nPJ * Dd), w_err = wk.take(I);
   const size_t w_rp = wk.take((size_t)nProj * 48 * Dd), w_rl = wk.take((size_t)nLobs * 24 * Dd), w_rv = wk.take((size_t)nVobs * 12 * Dd),
                w_ri = wk.take((size_t)nImu * REC_IMU * Dd), w_rpr = wk.take(nPriorR * Dd);
   const size_t w_scc = wk.take(nCam * Dd), w_scp = wk.take(nP * Dd), w_scl = wk.take(nL * 4 * Dd);
+  // [S | gS | gfull | colsq | acc]: ONE contiguous block = one all-reduce per iteration in the factor-parallel mode
   const size_t w_S = wk.take((size_t)nS * Dd), w_gS = wk.take(nCam * Dd), w_gf = wk.take(nCam * Dd), w_csq = wk.take(nCam * Dd);
+  const size_t w_acc = wk.take((size_t)B * ACC_STRIDE * Dd);
   const size_t w_reduce_end = wk.total;
   const size_t w_dc = wk.take(nCam * Dd), w_dp = wk.take(nP * Dd), w_dl = wk.take(nL * 4 * Dd);
   size_t w_b3 = 0;
@@ -315,6 +318,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
     const UvsWindow &x = w[i];
     const size_t f0 = h->frame_off[i], p0 = h->point_off[i], l0 = h->line_off[i], j0 = h->proj_off[i], a0 = h->lobs_off[i],
                  v0 = h->vobs_off[i], m0 = h->imu_off[i], b0 = h->pblk_off[i];
+    { int *fw = (int *)(S + o_frwin) + f0; for (int k = 0; k < x.n_frames; k++) fw[k] = i; }
     put(o_pose, f0 * 7 * Dd, x.pose, x.n_frames * 7 * Dd);
     put(o_sb, f0 * 9 * Dd, x.speed_bias, x.n_frames * 9 * Dd);
     put(o_ex, (size_t)i * 7 * Dd, x.ex_pose, 7 * Dd);
@@ -440,7 +444,8 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   D.pblk_col = WI(o_bcol); D.pblk_cam = WI(o_bcam); D.pblk_row = WI(o_brow);
   D.proj_idx = (int4 *)(Dv + w_pidx); D.line_idx4 = (int4 *)(Dv + w_lidx); D.vp_idx4 = (int4 *)(Dv + w_vidx); D.imu_idx = (int2 *)(Dv + w_iidx);
   D.pt_begin = WI(w_ptb); D.ln_begin = WI(w_lnb); D.pt_end = WI(w_pte); D.ln_end = WI(w_lne); D.pt_win = WI(w_ptw); D.ln_win = WI(w_lnw);
-  D.pt_order = WI(w_pto);
+  D.pt_order = WI(w_pto); D.fr_win = PI(o_frwin);
+  D.ftab[0] = WD(w_ft0); D.ftab[1] = WD(w_ft1); D.lsc[0] = WD(w_ls0); D.lsc[1] = WD(w_ls1);
   D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.chain_lw = WD(w_clw); D.chain_lw_stride = chol_chain_lw_doubles(max_frames); D.prior_H = WD(w_prH); D.err = WI(w_err);
   D.rec_proj = WD(w_rp); D.rec_line = WD(w_rl); D.rec_vp = WD(w_rv); D.rec_imu = WD(w_ri); D.rec_prior = WD(w_rpr);
   D.scale_cam = WD(w_scc); D.scale_pt = WD(w_scp); D.scale_ln = WD(w_scl);
@@ -461,6 +466,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   h->launches += launch_prep(D, h->stream);
   if (h->use_build3) {
     CK(cudaMemsetAsync(Dv + w_b3 + h->b3.o_Y, 0, h->b3.o_ph - h->b3.o_Y, h->stream));   // dense landmark columns start as zeros
+    h->launches += launch_stash_init(D, Dv + w_b3, h->b3, h->stream);
     if (h->fused) h->launches += launch_prep_point_order(D, (int *)(Dv + w_ptk), h->stream);
     else h->launches += launch_build3_prep(D, Dv + w_b3, h->b3, h->any_ex, h->stream);
   }
@@ -507,9 +513,16 @@ int ensure_scratch(UvsHandle *h, size_t bytes) { return handle_ensure_scratch(h,
 int ensure_hscratch(UvsHandle *h, size_t bytes) { return handle_ensure_hscratch(h, bytes); }
 int all_reduce(UvsHandle *h, double *buf, size_t count) {
   if (h->nranks <= 1) return UVS_OK;
-  if (!h->reduce) return fail(h, UVS_ERR_COMM, "multi-rank mode without a reduce callback");
+  if (h->nccl_comm) {
+    const int rc = uvs::nccl_all_reduce_sum(h->nccl_comm, buf, count, h->stream);
+    if (rc != 0) return fail(h, UVS_ERR_COMM, std::string("ncclAllReduce: ") + uvs::nccl_error_string(rc));
+    h->collectives++;
+    return UVS_OK;
+  }
+  if (!h->reduce) return fail(h, UVS_ERR_COMM, "multi-rank mode without a communicator");
   const int rc = h->reduce(h->reduce_user, buf, (int64_t)count, (void *)h->stream);
   if (rc != 0) return fail(h, UVS_ERR_COMM, "reduce callback failed with " + std::to_string(rc));
+  h->collectives++;
   return UVS_OK;
 }
 }  // namespace
@@ -605,11 +618,11 @@ static int eval_common(UvsHandle *h, int type, double *residuals, double *jacobi
     case 1: n = D.nLobs; NR = 2; REC = ceres ? CREC_LINE : REC_LINE; rec = D.rec_line;
       // tangent layout: the table-based line + VP kernel the solver and the marginalization use; Ceres layout (raw qw column): k_line
       if (ceres) h->launches += launch_line(D, h->P, true, true, 0, 0, rec, nullptr, nullptr, 0, st);
-      else h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st);
+      else { h->launches += launch_line_tables(D, 0, st); h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st); }
       break;
     case 2: n = D.nVobs; NR = 1; REC = ceres ? CREC_VP : REC_VP; rec = D.rec_vp;
       if (ceres || D.nLobs == 0) h->launches += launch_vp(D, h->P, true, ceres, 0, 0, rec, nullptr, nullptr, 0, st);
-      else h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st);
+      else { h->launches += launch_line_tables(D, 0, st); h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st); }
       break;
     case 3: n = D.nImu; NR = 15; REC = 15 + 15 * (2 * (ceres ? 7 : 6) + 18); rec = D.rec_imu;
       h->launches += launch_imu(D, h->P, true, 0, 0, rec, nullptr, nullptr, 0, st); break;
@@ -687,6 +700,7 @@ static int launch_resid_sweep(UvsHandle *h, int mode, int cand, int slot) {
   const Fork *fk = h->concurrent ? &h->fork : nullptr;
   if (fk) fork_from(fk, st, 3);
   h->launches += launch_proj(D, h->P, false, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, st);
+  h->launches += launch_line_tables(D, cand, fk ? fk->aux[0] : st);   // tables of the candidate's state buffer (current ones after an accepted step)
   h->launches += launch_line_vp(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, fk ? fk->aux[0] : st);
   h->launches += launch_imu(D, h->P, false, mode, cand, nullptr, nullptr, cost, ACC_STRIDE, fk ? fk->aux[1] : st);
   // residual-only: the prior residual of the CURRENT iterate (rec_prior) must survive a rejected step
@@ -720,6 +734,7 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
   const auto t0 = std::chrono::steady_clock::now();
   CK(cudaEventRecord(h->ev_a, st));
   h->launches += launch_solve_init(D, P, st);
+  h->launches += launch_line_tables(D, 0, st);   // line / VP tables of the starting state
   const bool prof = h->profiling > 0;
   const int NE = UVS_N_STAGES + 1;
   if (prof) {
@@ -768,9 +783,8 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
       h->launches += launch_build(D, P, h->max_prior_n, st);
     }
     rc = post_launch(h, "build"); if (rc) return rc;
-    if (h->nranks > 1) {
+    if (h->nranks > 1) {   // partial reduced systems + per-window accumulators of all ranks: one collective
       rc = all_reduce(h, (double *)(h->dev.base + h->o_reduce), h->reduce_doubles); if (rc) return rc;
-      rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc;
     }
     STAGE(6);
     if (h->chain_ok) h->launches += launch_chol_chain(D, P, h->max_frames, h->any_ex, h->use_build3, st);
@@ -960,6 +974,7 @@ int uvs_jacobian_sweep(UvsHandle *h, int32_t repeats, float *ms_group, float *ms
     else if (k == 2) h->launches += launch_imu(D, P, true, 0, 0, D.rec_imu, nullptr, nullptr, 0, s);
     else h->launches += launch_prior(D, h->max_prior_n, true, 0, 0, D.rec_prior, nullptr, 0, s);
   };
+  h->launches += launch_line_tables(D, 0, st);
   for (int k = 0; k < 4; k++) one(k, st);   // warm-up (shared-memory attributes, instruction cache)
   CK(cudaEventRecord(h->ev_c, st));
   for (int r = 0; r < repeats; r++) {
@@ -1028,6 +1043,27 @@ int uvs_last_sweep_ms(const UvsHandle *h, float *ms, int32_t *n) {
   if (n) *n = h->n_sweeps;
   return UVS_OK;
 }
+
+int uvs_comm_unique_id(unsigned char *id) {
+  if (!id) return UVS_ERR_INVALID_ARG;
+  return uvs::nccl_unique_id(id) == 0 ? UVS_OK : UVS_ERR_COMM;
+}
+
+int uvs_comm_init_nccl(UvsHandle *h, const unsigned char *id, int32_t rank, int32_t nranks) {
+  if (!h || !id || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(h, UVS_ERR_INVALID_ARG, "uvs_comm_init_nccl: bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (h->iter_exec) { cudaGraphExecDestroy(h->iter_exec); h->iter_exec = nullptr; }
+  if (h->nccl_comm) { uvs::nccl_destroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  if (nranks > 1) {
+    const int rc = uvs::nccl_init_rank(&h->nccl_comm, id, rank, nranks);
+    if (rc != 0) return fail(h, UVS_ERR_COMM, std::string("ncclCommInitRank: ") + uvs::nccl_error_string(rc));
+  }
+  h->rank = rank; h->nranks = nranks; h->reduce = nullptr; h->reduce_user = nullptr;
+  h->D.rank = rank; h->D.nranks = nranks;
+  return UVS_OK;
+}
+
+int64_t uvs_collective_count(const UvsHandle *h) { return h ? h->collectives : 0; }
 
 int uvs_comm_init(UvsHandle *h, int32_t rank, int32_t nranks, UvsAllReduceFn reduce, void *user) {
   if (!h || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(h, UVS_ERR_INVALID_ARG, "uvs_comm_init: bad arguments");

@@ -371,9 +371,10 @@ __global__ void __launch_bounds__(128) k_back_points(Dev D, Stash S) {
       }
       u = group_sum<LPP>(gmask, u);
       const double z = y[mp - 2];
-      const double yk = -sh * (z + u);
+      // scaled column: z = sk sh g, entries sk sh W;  unscaled column (fused path): z = g, entries W
+      const double yk = S.unscaled_pts ? -sh * sk * sh * (z + u) : -sh * (z + u);
       dk = sk * yk;
-      mc = 0.5 * (D2 * yk * yk - (z / sh) * yk);
+      mc = 0.5 * (D2 * yk * yk - (S.unscaled_pts ? sk * z : z / sh) * yk);
     }
     if (sub == 0) {
       const double lam = D.inv_depth[cur][gp];
@@ -831,13 +832,14 @@ constexpr int SUP_SETS = 2;   // and at most this many of them (8 warps x 2 cove
 
 // one chunk of the rank update for a 3 x 3 unit of 8x8 tiles: acc[u][v] += Y_rows(u) Y_rows(v)^T over c1 columns
 template <unsigned MK>
-__device__ __forceinline__ void rank_chunk(double (&acc)[SUP][SUP][2], const double *ya, const double *yb, int c1, int mp) {
+__device__ __forceinline__ void rank_chunk(double (&acc)[SUP][SUP][2], const double *ya, const double *yb, const double *ysc, int c1, int mp) {
   constexpr unsigned rowm = (MK & 7u ? 1u : 0u) | (MK & 0x38u ? 2u : 0u) | (MK & 0x1c0u ? 4u : 0u), colm = (MK | MK >> 3 | MK >> 6) & 7u;
   for (int k0 = 0; k0 < c1; k0 += 4) {
     double fa[SUP], fb[SUP];
+    const double cs = ysc[(size_t)k0 * mp];   // scale of this lane's column (entry mp - 1)
 #pragma unroll
     for (int u = 0; u < SUP; u++) {
-      if (rowm >> u & 1u) fa[u] = ya[(size_t)k0 * mp + 8 * u];
+      if (rowm >> u & 1u) fa[u] = cs * ya[(size_t)k0 * mp + 8 * u];
       if (colm >> u & 1u) fb[u] = yb[(size_t)k0 * mp + 8 * u];
     }
 #pragma unroll
@@ -847,11 +849,12 @@ __device__ __forceinline__ void rank_chunk(double (&acc)[SUP][SUP][2], const dou
         if (MK >> (3 * u + v) & 1u) dmma884(acc[u][v], fa[u], fb[v]);
   }
 }
-__device__ __forceinline__ void rank_chunk_any(unsigned mk, double (&acc)[SUP][SUP][2], const double *ya, const double *yb, int c1, int mp) {
+__device__ __forceinline__ void rank_chunk_any(unsigned mk, double (&acc)[SUP][SUP][2], const double *ya, const double *yb, const double *ysc, int c1, int mp) {
   for (int k0 = 0; k0 < c1; k0 += 4) {
     double fa[SUP], fb[SUP];
+    const double cs = ysc[(size_t)k0 * mp];
 #pragma unroll
-    for (int u = 0; u < SUP; u++) { fa[u] = ya[(size_t)k0 * mp + 8 * u]; fb[u] = yb[(size_t)k0 * mp + 8 * u]; }
+    for (int u = 0; u < SUP; u++) { fa[u] = cs * ya[(size_t)k0 * mp + 8 * u]; fb[u] = yb[(size_t)k0 * mp + 8 * u]; }
 #pragma unroll
     for (int u = 0; u < SUP; u++)
 #pragma unroll
@@ -951,14 +954,15 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
         if (!mk) continue;
         const double *ya = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * ta[i];
         const double *yb = Yb + (size_t)(lane & 3) * mp + (lane >> 2) + 8 * tb[i];
+        const double *ysc = Yb + (size_t)(lane & 3) * mp + mp - 1;   // column scale (uvs_stash.cuh)
         // the tile mask is uniform over the warp: the common masks get loops with exactly their loads and DMMAs compiled
         // in (a predicated-off DMMA still takes its issue slot and tensor-pipe cycles)
         switch (mk) {
-          case 0x03fu: rank_chunk<0x03fu>(acc[i], ya, yb, c1, mp); break;
-          case 0x137u: rank_chunk<0x137u>(acc[i], ya, yb, c1, mp); break;
-          case 0x007u: rank_chunk<0x007u>(acc[i], ya, yb, c1, mp); break;
-          case 0x1ffu: rank_chunk<0x1ffu>(acc[i], ya, yb, c1, mp); break;
-          default: rank_chunk_any(mk, acc[i], ya, yb, c1, mp); break;
+          case 0x03fu: rank_chunk<0x03fu>(acc[i], ya, yb, ysc, c1, mp); break;
+          case 0x137u: rank_chunk<0x137u>(acc[i], ya, yb, ysc, c1, mp); break;
+          case 0x007u: rank_chunk<0x007u>(acc[i], ya, yb, ysc, c1, mp); break;
+          case 0x1ffu: rank_chunk<0x1ffu>(acc[i], ya, yb, ysc, c1, mp); break;
+          default: rank_chunk_any(mk, acc[i], ya, yb, ysc, c1, mp); break;
         }
       }
       __syncthreads();
@@ -1136,11 +1140,24 @@ size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay
 
 static void make_ctx(char *base, const Build3Layout &lay, Build3Ctx &c) {
   c.S.Y = (double *)(base + lay.o_Y); c.S.ph = (double *)(base + lay.o_ph); c.S.lh = (double *)(base + lay.o_lh);
-  c.S.mp = lay.mp;
+  c.S.mp = lay.mp; c.S.unscaled_pts = 0;
   c.L.items = (int2 *)(base + lay.o_items); c.L.off = (int *)(base + lay.o_off);
 }
 
 static inline int cdiv3(int a, int b) { return (a + b - 1) / b; }
+
+// column scales of the stash start as 1 (the columns themselves as zeros: cudaMemset at upload)
+__global__ void k_stash_init(double *Y, long long ncols, int mp) {
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c < ncols) Y[c * mp + mp - 1] = 1.0;
+}
+
+int launch_stash_init(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st) {
+  const long long ncols = (long long)D.nP + 4LL * D.nL;
+  if (ncols == 0) return 0;
+  k_stash_init<<<(unsigned)((ncols + 255) / 256), 256, 0, st>>>((double *)(base + lay.o_Y), ncols, lay.mp);
+  return 1;
+}
 
 int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, bool any_ex, cudaStream_t st) {
   Build3Ctx c; make_ctx(base, lay, c);

@@ -99,6 +99,9 @@ struct Dev {
   int *pt_begin, *pt_end;   // [nP] proj factor range of a point
   int *ln_begin, *ln_end;   // [nL] line obs range of a line
   int *pt_win, *ln_win;     // [nP], [nL]
+  const int *fr_win;        // [nF] window of a frame (host-built)
+  double *ftab[2];          // [nF][48] per-frame tables of the line / VP factors for state buffer 0 / 1 (uvs_linefast.cuh)
+  double *lsc[2];           // [nL][8] sin, cos of the four orthonormal line parameters, per state buffer
   int *pt_order;            // [nP] processing order of the fused point kernel: per window sorted by (anchor frame, track length)
   int *pblk_col, *pblk_cam, *pblk_row;   // column in J0, tangent offset in the window (-1 const), state row
   double *imu_sqrt_info;    // [nImu][225]

@@ -71,6 +71,8 @@ struct UvsHandle {
   float last_solve_ms = 0.f, last_sweep_ms = 0.f;
   int n_sweeps = 0;
   int rank = 0, nranks = 1;
+  void *nccl_comm = nullptr;                  // ncclComm_t of uvs_comm_init_nccl (uvs_comm.cpp); takes precedence over the callback
+  int64_t collectives = 0;                    // all-reduces issued since creation
   UvsAllReduceFn reduce = nullptr;
   void *reduce_user = nullptr;
   int *d_active = nullptr;
@@ -97,4 +99,10 @@ namespace uvs {
 int handle_fail(UvsHandle *h, int status, const std::string &msg);
 int handle_ensure_scratch(UvsHandle *h, size_t bytes);
 int handle_ensure_hscratch(UvsHandle *h, size_t bytes);
+// uvs_comm.cpp: NCCL bound at run time (dlopen of libnccl.so.2; the library has no link-time dependency on it)
+int nccl_unique_id(unsigned char id[128]);
+int nccl_init_rank(void **comm, const unsigned char id[128], int rank, int nranks);
+int nccl_all_reduce_sum(void *comm, double *buf, size_t count, cudaStream_t st);
+void nccl_destroy(void *comm);
+const char *nccl_error_string(int rc);
 }  // namespace uvs

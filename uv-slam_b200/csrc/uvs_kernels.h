@@ -23,6 +23,8 @@ int launch_vp(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int
 // solver path: line + VP factors of one observation in one pass (every VP factor is paired with a line factor at upload)
 int launch_line_vp(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out_line, double *out_vp, double *cost,
                    int cost_stride, cudaStream_t st);
+// tables of the line / VP factors for state buffer cur ^ cand (must precede launch_line_vp / the fused line kernel at that state)
+int launch_line_tables(const Dev &D, int cand, cudaStream_t st);
 int launch_imu(const Dev &D, const Params &P, bool jac, int mode, int cand, double *out, double *res_out, double *cost,
                int cost_stride, cudaStream_t st);
 int launch_prior(const Dev &D, int max_prior_n, bool jac_phase, int mode, int cand, double *res_out, double *cost,
@@ -54,6 +56,7 @@ inline void join_to(const Fork *fk, cudaStream_t main, int k) {
 
 size_t build3_bytes(const Dev &D, int max_frames, bool any_ex, Build3Layout *lay);
 size_t build3_smem(int max_frames, bool any_ex, int max_prior_n);
+int launch_stash_init(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st);
 int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, bool any_ex, cudaStream_t st);
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
                   cudaStream_t st, const Fork *fk);

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
         wa[c] += row[2 + c] * j0 + row[8 + c] * j1;
         u[c] = row[14 + c] * j0 + row[20 + c] * j1;
       }
-      // parked unscaled, rescaled below (a block is 48 bytes, 16-byte aligned)
+      // W_j = Jj^T Jl goes to the stash unscaled: the column carries its scale (uvs_stash.cuh), nothing is rewritten later
       double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * (rj - fo));
       y2[0] = make_double2(u[0], u[1]); y2[1] = make_double2(u[2], u[3]); y2[2] = make_double2(u[4], u[5]);
     }
@@ -148,13 +148,14 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
       const int ra = 15 * ((swp ? lj : li) - lfo), rb = 15 * ((swp ? li : lj) - lfo);
       // entry (p, q) of G^T G, p <= q: columns 0..5 -> block a, 6..11 -> block b, 12 -> gradient
       auto put = [&](int p, int q, double v) {
-        if (p >= 12 || q > 12) return;
-        const int gpp = p < 6 ? ra + p : rb + p - 6;
-        if (q == 12) { atomicAdd(D.gS + lco + gpp, v); atomicAdd(D.gfull + lco + gpp, v); return; }
-        if (p > q) return;
-        const int gq = q < 6 ? ra + q : rb + q - 6;
-        atomicAdd(Sg + (size_t)gpp * ld + gq, v);
-        if (p == q) atomicAdd(D.colsq_cam + lco + gpp, v);
+        const bool isg = q == 12;
+        const bool ok = p < 12 && (isg || (q < 12 && p <= q));
+        const int gpp = (p < 6 ? ra : rb - 6) + p, gq = (q < 6 ? ra : rb - 6) + q;
+        if (ok) {
+          atomicAdd(isg ? D.gS + lco + gpp : Sg + (size_t)gpp * ld + gq, v);
+          if (isg) atomicAdd(D.gfull + lco + gpp, v);
+          else if (p == q) atomicAdd(D.colsq_cam + lco + gpp, v);
+        }
       };
       const int pr = lane >> 2, pc = 2 * (lane & 3);
       put(pr, pc, c00[0]); put(pr, pc + 1, c00[1]);
@@ -173,17 +174,12 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
   const double D2 = clamp4(Et, P.min_lm_diag, P.max_lm_diag) / D.ctl[w].radius;
   const double sh = rsqrt(Et + D2);
   const double ysc = sk * sh;
-  for (int k = 0; k < n; k++) {
-    double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * (D.proj_idx[f0 + k].y - fo));
-#pragma unroll
-    for (int c = 0; c < 3; c++) { const double2 v = y2[c]; y2[c] = make_double2(ysc * v.x, ysc * v.y); }
-  }
   {
     double2 *y2 = reinterpret_cast<double2 *>(Y + 6 * (row_i - fo));
-    y2[0] = make_double2(ysc * wa[0], ysc * wa[1]); y2[1] = make_double2(ysc * wa[2], ysc * wa[3]); y2[2] = make_double2(ysc * wa[4], ysc * wa[5]);
+    y2[0] = make_double2(wa[0], wa[1]); y2[1] = make_double2(wa[2], wa[3]); y2[2] = make_double2(wa[4], wa[5]);
   }
-  Y[mp - 2] = sk * gk * sh;
-  ph[0] = sk; ph[1] = sh; ph[2] = D2;
+  *reinterpret_cast<double2 *>(Y + mp - 2) = make_double2(gk, ysc * ysc);   // z row and column scale (unscaled column: uvs_stash.cuh)
+  ph[0] = sk; ph[1] = sh; ph[2] = D2; ph[3] = gk;
   atomic_max_nn3(D.acc + (size_t)w * ACC_STRIDE + ACC_GMAX + D.rank, fabs(gk));
 }
 
@@ -224,10 +220,7 @@ __global__ void __launch_bounds__(LL_NT, 3) k_lin_lines(Dev D, Params P, Stash S
   int *rowlist = svp + WSLOTS;                                             // [3 * WSLOTS] rows of one frame group
   const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
   const int cur = D.cur[w];
-  for (int e = threadIdx.x; e < 3 * F; e += LL_NT) {
-    const int f = e / 3, m = e - 3 * f;
-    line_frame_table(D.pose[cur] + 7 * (size_t)(fo + f), D.ric + 9 * (size_t)w, D.tic + 3 * (size_t)w, m, ftab + f * FT_STRIDE);
-  }
+  load_frame_tables(D.ftab[cur] + (size_t)fo * FT_DOUBLES, F, ftab, LL_NT);
   for (int e = lane; e < WSLOTS; e += 32) { sframe[e] = -1; svp[e] = 0; }
   __syncthreads();
 
@@ -249,15 +242,11 @@ __global__ void __launch_bounds__(LL_NT, 3) k_lin_lines(Dev D, Params P, Stash S
   }
   if (!act) n = 0;
   if (n > LSLOT) n = LSLOT;   // excluded at upload (the batch takes the record path instead)
-  // ---- per-line table: lane c < 4 of the group takes sin / cos of parameter c
+  // ---- per-line table from the sines / cosines k_line_tables left for this state buffer
   LineTab LT;
   {
-    double sv = 0.0, cv = 1.0;
-    if (act && sub < 4) sincos(D.ortho[cur][4 * (size_t)gl + sub], &sv, &cv);
-    const int gb = lane & ~(LPL - 1);
-    const double sa = __shfl_sync(full, sv, gb), ca = __shfl_sync(full, cv, gb), sb = __shfl_sync(full, sv, gb + 1), cb = __shfl_sync(full, cv, gb + 1);
-    const double sc = __shfl_sync(full, sv, gb + 2), cc = __shfl_sync(full, cv, gb + 2), sp = __shfl_sync(full, sv, gb + 3), cp = __shfl_sync(full, cv, gb + 3);
-    line_table(sa, ca, sb, cb, sc, cc, sp, cp, LT);
+    const double *q = D.lsc[cur] + 8 * (size_t)(act ? gl : D.line_off[w]);
+    line_table(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), __ldg(q + 4), __ldg(q + 5), __ldg(q + 6), __ldg(q + 7), LT);
   }
   // ---- evaluation: observation f of the line -> slot grp * LSLOT + f of the warp's stage
   double half = 0.0;
@@ -496,14 +485,14 @@ int lin_max_line_obs() { return LSLOT; }
 
 int launch_lin_points(const Dev &D, const Params &P, char *base, const Build3Layout &lay, cudaStream_t st) {
   if (D.nP == 0) return 0;
-  Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp;
+  Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp; S.unscaled_pts = 1;
   k_lin_points<<<cdivl(D.nP, LP_NT), LP_NT, 0, st>>>(D, P, S);
   return 1;
 }
 
 int launch_lin_lines(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, int max_lines, cudaStream_t st) {
   if (D.nL == 0 || max_lines == 0) return 0;
-  Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp;
+  Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp; S.unscaled_pts = 1;
   const size_t smem = lin_lines_smem(max_frames);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_lin_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }

@@ -62,6 +62,15 @@ __device__ __forceinline__ void line_frame_table(const double *__restrict__ pose
   Mo[9] = da.x; Mo[10] = da.y; Mo[11] = da.z;
 }
 
+// copy of one window's frame tables (contiguous in global memory, FT_DOUBLES per frame) into shared memory with the
+// padded row stride; call with all threads of the CTA, then __syncthreads()
+__device__ __forceinline__ void load_frame_tables(const double *__restrict__ src, int F, double *ftab, int nthreads) {
+  for (int e = threadIdx.x; e < F * FT_DOUBLES; e += nthreads) {
+    const int f = e / FT_DOUBLES;
+    ftab[e + f * (FT_STRIDE - FT_DOUBLES)] = __ldg(src + e);
+  }
+}
+
 struct LineTab {
   d3 u0, u1, du0a, du1a, du0b, du1b;
   double sp, cp;

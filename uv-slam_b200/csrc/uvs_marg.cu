@@ -361,6 +361,7 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
 
   // ---- 1. evaluate every factor at the current iterate (tangent columns, loss-corrected)
   h->launches += launch_proj(D, h->P, true, false, 0, 0, D.rec_proj, nullptr, nullptr, 0, st);
+  h->launches += launch_line_tables(D, 0, st);
   h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st);
   h->launches += launch_imu(D, h->P, true, 0, 0, D.rec_imu, nullptr, nullptr, 0, st);
   h->launches += launch_prior(D, h->max_prior_n, false, 0, 0, D.rec_prior, nullptr, 0, st);

@@ -57,9 +57,14 @@ __device__ __forceinline__ void add_window_scalar(double *arr, int stride_double
 //             col = colbase(w) + point  |  colbase(w) + np_w + 4 line + sub, colbase(w) = point_off[w] + 4 line_off[w]
 //             (the window kernel streams whole chunks of columns with TMA bulk copies);
 //             headers for the back-substitution: points ph[4] = sk, sh, D2, -;  lines lh[24] = s(4) D2(4) Linv(16)
+//             entry [mp-1] of a column = its scale c: the rank update adds  -c y y^T.  Line columns and the point columns of
+//             the record path hold scaled entries and c = 1 (set once at upload); the fused point kernel leaves the
+//             entries unscaled (W_j = Jj^T Jl, W_i, g) and stores c = (sk sh)^2, so nothing is rewritten once the
+//             landmark's sums are known (`unscaled_pts`).
 struct Stash {
   double *Y, *ph, *lh;
   int mp;
+  int unscaled_pts;
 };
 __device__ __forceinline__ long long colbase(const Dev &D, int w) { return (long long)D.point_off[w] + 4LL * D.line_off[w]; }
 

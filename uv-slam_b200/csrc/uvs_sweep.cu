@@ -236,10 +236,9 @@ __global__ void __launch_bounds__(NT, 4) k_vp(Dev D, Params P, int mode, int can
 
 // ------------------------------------------------------------------------------------------------
 // Line factor and the VP factor of the same (frame, line) observation in ONE pass, through per-frame and per-line
-// tables (uvs_linefast.cuh): a CTA works on up to NT consecutive line observations of ONE window (grid: chunks x
-// windows), first builds the window's frame tables (thread per (frame, quaternion coordinate)) and the sines / cosines
-// of its lines (one parameter per thread) in shared memory, then a thread owns an observation: ~500 FP64
-// instructions instead of the ~1500 of line_to_camera.  line_idx4[f].w names the paired VP observation (k_prep_vp) or
+// tables (uvs_linefast.cuh, written by k_line_tables for the state buffer in question): a CTA works on up to NT
+// consecutive line observations of ONE window (grid: chunks x windows), copies the window's frame tables into shared
+// memory, then a thread owns an observation: ~500 FP64 instructions instead of the ~1500 of line_to_camera.  line_idx4[f].w names the paired VP observation (k_prep_vp) or
 // -1.  Records of a tile are staged in shared memory and written back as contiguous chunks (the VP observations follow
 // the order of the line observations, so neighbouring VP records are adjacent in memory).
 template <bool kJac>
@@ -262,32 +261,17 @@ __global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode,
   if (!wants<kJac>(D.ctl[w].state, mode)) return;
   const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
   double *ftab = smem;                                        // [F][FT_STRIDE]
-  double *lsc = ftab + ((D.max_frames * FT_STRIDE + 1) & ~1); // [NT][8] sin / cos of the four parameters, row of the line's first thread
-  double *tile = lsc + NT * 8;                                // [NT][REC_LINE + 1]   (Jacobian mode only)
+  double *tile = ftab + ((D.max_frames * FT_STRIDE + 1) & ~1); // [NT][REC_LINE + 1]   (Jacobian mode only)
   double *vtile = tile + NT * (REC_LINE + 1);                 // [NT][REC_VP + 1]
   int *vslot = reinterpret_cast<int *>(vtile + NT * (REC_VP + 1));   // [NT] VP observation of the slot or -1
   unsigned char *ok = reinterpret_cast<unsigned char *>(vslot + NT);
   const int buf = D.cur[w] ^ cand;
-  for (int e = threadIdx.x; e < 3 * F; e += NT) {
-    const int f = e / 3, m = e - 3 * f;
-    line_frame_table(D.pose[buf] + 7 * (size_t)(fo + f), D.ric + 9 * (size_t)w, D.tic + 3 * (size_t)w, m, ftab + f * FT_STRIDE);
-  }
+  load_frame_tables(D.ftab[buf] + (size_t)fo * FT_DOUBLES, F, ftab, NT);
   const int f = first + threadIdx.x;
   bool valid = f < a1;
   int4 ix = make_int4(0, 0, w, -1);
-  int lead = 0;   // thread of this CTA that holds the first observation of my line
   if (valid) {
     ix = D.line_idx4[f];
-    lead = max(D.ln_begin[ix.y], first) - first;
-    // thread lead + c takes parameter c; a line with fewer than four observations in this CTA: its last thread the rest
-    const int k = threadIdx.x - lead;
-    const int last = min(D.ln_end[ix.y], min(a1, first + NT)) - first - 1;
-    const double *lp = D.ortho[buf] + 4 * (size_t)ix.y;
-    for (int c = k; c < 4; c += (threadIdx.x == last ? 1 : 4)) {
-      double sv, cv;
-      sincos(__ldg(lp + c), &sv, &cv);
-      lsc[lead * 8 + 2 * c] = sv; lsc[lead * 8 + 2 * c + 1] = cv;
-    }
     valid = D.nranks <= 1 || mode == 0 || (ix.y % D.nranks) == D.rank;
   }
   __syncthreads();
@@ -295,7 +279,7 @@ __global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode,
   int vi = -1;
   if (valid) {
     LineTab LT;
-    { const double *q = lsc + lead * 8; line_table(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], LT); }
+    { const double *q = D.lsc[buf] + 8 * (size_t)ix.y; line_table(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), __ldg(q + 4), __ldg(q + 5), __ldg(q + 6), __ldg(q + 7), LT); }
     const double *sp = D.line_sp + 2 * (size_t)f, *ep = D.line_ep + 2 * (size_t)f;
     LineVpSink<kJac> sink;
     sink.ln.spx = __ldg(sp); sink.ln.spy = __ldg(sp + 1); sink.ln.epx = __ldg(ep); sink.ln.epy = __ldg(ep + 1);
@@ -338,6 +322,24 @@ __global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode,
         if (c >= REC_VP) { c -= REC_VP; slot++; }
       }
     }
+  }
+}
+
+// Per-frame and per-line tables of the line / VP factors for the state buffer cur ^ cand of every window: thread per
+// (frame, quaternion coordinate) and per (line, parameter).  The tables live per STATE BUFFER, so an accepted step needs
+// no new ones (the candidate's tables become the current ones with the buffer flip): one launch per LM iteration.
+__global__ void __launch_bounds__(128) k_line_tables(Dev D, int cand) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 3 * D.nF) {
+    const int f = t / 3, m = t - 3 * f;
+    const int w = D.fr_win[f], buf = D.cur[w] ^ cand;
+    line_frame_table(D.pose[buf] + 7 * (size_t)f, D.ric + 9 * (size_t)w, D.tic + 3 * (size_t)w, m, D.ftab[buf] + (size_t)f * FT_DOUBLES);
+  } else if (t < 3 * D.nF + 4 * D.nL) {
+    const int e = t - 3 * D.nF, l = e >> 2, c = e & 3;
+    const int buf = D.cur[D.ln_win[l]] ^ cand;
+    double sv, cv;
+    sincos(D.ortho[buf][4 * (size_t)l + c], &sv, &cv);
+    D.lsc[buf][8 * (size_t)l + 2 * c] = sv; D.lsc[buf][8 * (size_t)l + 2 * c + 1] = cv;
   }
 }
 
@@ -577,8 +579,15 @@ int launch_vp(const Dev &D, const Params &P, bool jac, bool ceres, int mode, int
   return 1;
 }
 
+int launch_line_tables(const Dev &D, int cand, cudaStream_t st) {
+  const int n = 3 * D.nF + 4 * D.nL;
+  if (D.nLobs == 0 || n == 0) return 0;
+  k_line_tables<<<cdiv(n, 128), 128, 0, st>>>(D, cand);
+  return 1;
+}
+
 static size_t line_vp_smem(int max_frames, bool jac) {
-  size_t dbl = (size_t)((max_frames * FT_STRIDE + 1) & ~1) + NT * 8;
+  size_t dbl = (size_t)((max_frames * FT_STRIDE + 1) & ~1);
   if (jac) return (dbl + (size_t)NT * (REC_LINE + 1 + REC_VP + 1)) * sizeof(double) + NT * sizeof(int) + NT;
   return dbl * sizeof(double);
 }
