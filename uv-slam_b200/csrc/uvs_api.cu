@@ -230,6 +230,9 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   prefix<int>(h->imu_off, B, w, [](const UvsWindow &x) { return (int)x.n_imu; });
   prefix<int>(h->prior_off, B, w, [](const UvsWindow &x) { return (int)x.prior_n; });
   prefix<int>(h->pblk_off, B, w, [](const UvsWindow &x) { return x.prior_n > 0 ? (int)x.prior_n_blocks : 0; });
+  std::vector<int> pw_off(B + 1, 0);   // warp slots of the fused point kernel: ceil(points / 32) + frames bounds the anchor-uniform warps of a window
+  for (int i = 0; i < B; i++) pw_off[i + 1] = pw_off[i] + (w[i].n_points + 31) / 32 + w[i].n_frames;
+  const int nPW = pw_off[B];
   h->cam_off.assign(B + 1, 0); h->S_off.assign(B + 1, 0); h->priorJ_off.assign(B + 1, 0); h->win_flags.assign(B, 0);
   for (int i = 0; i < B; i++) {
     const int d = 15 * w[i].n_frames + (w[i].estimate_extrinsic ? 6 : 0) + (td ? 1 : 0);
@@ -249,7 +252,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
                o_proj_off = in.take((B + 1) * I), o_lobs_off = in.take((B + 1) * I), o_vobs_off = in.take((B + 1) * I),
                o_imu_off = in.take((B + 1) * I), o_cam_off = in.take((B + 1) * I), o_prior_off = in.take((B + 1) * I),
                o_pblk_off = in.take((B + 1) * I), o_S_off = in.take((B + 1) * 8), o_pJ_off = in.take((B + 1) * 8),
-               o_flags = in.take(B * I), o_frwin = in.take(nF * I);
+               o_flags = in.take(B * I), o_frwin = in.take(nF * I), o_pwoff = in.take((B + 1) * I);
   const size_t o_pose = in.take(nF * 7 * Dd), o_sb = in.take(nF * 9 * Dd), o_ex = in.take(B * 7 * Dd), o_td = in.take(B * Dd),
                o_inv = in.take(nP * Dd), o_ortho = in.take(nL * 4 * Dd);
   const size_t o_state_end = in.total;
@@ -280,7 +283,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
                w_iidx = wk.take(nImu * sizeof(int2));
   const size_t w_ptb = wk.take(nP * I), w_lnb = wk.take(nL * I);            // begin arrays (memset 0x7f together)
   const size_t w_pte = wk.take(nP * I), w_lne = wk.take(nL * I), w_ptw = wk.take(nP * I), w_lnw = wk.take(nL * I);
-  const size_t w_pto = wk.take(nP * I), w_ptk = wk.take(nP * I);
+  const size_t w_pto = wk.take((size_t)nPW * 32 * I), w_ptk = wk.take(nP * I);
   const size_t w_ft0 = wk.take((size_t)nF * 48 * Dd), w_ft1 = wk.take((size_t)nF * 48 * Dd), w_ls0 = wk.take((size_t)nL * 8 * Dd), w_ls1 = wk.take((size_t)nL * 8 * Dd);
   const size_t w_icomp = wk.take((size_t)nImu * 108 * Dd);
   const size_t w_clw = wk.take(h->use_build3 ? (size_t)B * chol_chain_lw_doubles(max_frames) * Dd : 0);
@@ -307,7 +310,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   auto cpI = [&](size_t off, const std::vector<int> &v) { std::memcpy(S + off, v.data(), v.size() * sizeof(int)); };
   cpI(o_frame_off, h->frame_off); cpI(o_point_off, h->point_off); cpI(o_line_off, h->line_off); cpI(o_proj_off, h->proj_off);
   cpI(o_lobs_off, h->lobs_off); cpI(o_vobs_off, h->vobs_off); cpI(o_imu_off, h->imu_off); cpI(o_cam_off, h->cam_off);
-  cpI(o_prior_off, h->prior_off); cpI(o_pblk_off, h->pblk_off); cpI(o_flags, h->win_flags);
+  cpI(o_pwoff, pw_off); cpI(o_prior_off, h->prior_off); cpI(o_pblk_off, h->pblk_off); cpI(o_flags, h->win_flags);
   std::memcpy(S + o_S_off, h->S_off.data(), (B + 1) * 8);
   std::memcpy(S + o_pJ_off, h->priorJ_off.data(), (B + 1) * 8);
   auto put = [&](size_t off, size_t elem_off, const void *src, size_t bytes) { if (bytes) std::memcpy(S + off + elem_off, src, bytes); };
@@ -413,6 +416,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   CK(cudaMemsetAsync(Dv + w_ptb, 0x7f, w_pte - w_ptb, h->stream));        // pt_begin, ln_begin
   CK(cudaMemsetAsync(Dv + w_pte, 0, w_sqi - w_pte, h->stream));           // pt_end .. ln_win
   CK(cudaMemsetAsync(Dv + w_err, 0, ALIGN, h->stream));
+  CK(cudaMemsetAsync(Dv + w_pto, 0xff, (size_t)nPW * 32 * I, h->stream));   // empty lanes of the point order
   CK(cudaMemsetAsync(Dv + w_scc, 0, wk.total - w_scc, h->stream));        // scales, system, deltas
   CK(cudaMemcpyAsync(Dv + w_pose, Dv + o_pose, o_state_end - o_pose, cudaMemcpyDeviceToDevice, h->stream));  // candidate buffer = copy
   CK(cudaMemcpyAsync(Dv + w_pristine, Dv + o_pose, o_state_end - o_pose, cudaMemcpyDeviceToDevice, h->stream));
@@ -444,7 +448,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   D.pblk_col = WI(o_bcol); D.pblk_cam = WI(o_bcam); D.pblk_row = WI(o_brow);
   D.proj_idx = (int4 *)(Dv + w_pidx); D.line_idx4 = (int4 *)(Dv + w_lidx); D.vp_idx4 = (int4 *)(Dv + w_vidx); D.imu_idx = (int2 *)(Dv + w_iidx);
   D.pt_begin = WI(w_ptb); D.ln_begin = WI(w_lnb); D.pt_end = WI(w_pte); D.ln_end = WI(w_lne); D.pt_win = WI(w_ptw); D.ln_win = WI(w_lnw);
-  D.pt_order = WI(w_pto); D.fr_win = PI(o_frwin);
+  D.pt_order = WI(w_pto); D.fr_win = PI(o_frwin); D.pw_off = PI(o_pwoff); D.nPW = nPW;
   D.ftab[0] = WD(w_ft0); D.ftab[1] = WD(w_ft1); D.lsc[0] = WD(w_ls0); D.lsc[1] = WD(w_ls1);
   D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.chain_lw = WD(w_clw); D.chain_lw_stride = chol_chain_lw_doubles(max_frames); D.prior_H = WD(w_prH); D.err = WI(w_err);
   D.rec_proj = WD(w_rp); D.rec_line = WD(w_rl); D.rec_vp = WD(w_rv); D.rec_imu = WD(w_ri); D.rec_prior = WD(w_rpr);
@@ -791,7 +795,7 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
     else h->launches += launch_chol(D, P, h->max_d, h->packed_limit, h->use_build3, st);
     STAGE(7);
     rc = post_launch(h, "chol"); if (rc) return rc;
-    if (h->use_build3) h->launches += launch_back3(D, h->dev.base + h->o_b3, h->b3, st, fk);
+    if (h->use_build3) h->launches += launch_back3(D, h->dev.base + h->o_b3, h->b3, st, fk, h->fused);
     else h->launches += launch_backsub(D, P, st);
     STAGE(8);
     rc = post_launch(h, "backsub"); if (rc) return rc;

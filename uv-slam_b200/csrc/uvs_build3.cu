@@ -1236,8 +1236,9 @@ int launch_build3_fused(const Dev &D, const Params &P, char *base, const Build3L
   return n;
 }
 
-int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st, const Fork *fk) {
+int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st, const Fork *fk, bool unscaled_pts) {
   Build3Ctx c; make_ctx(base, lay, c);
+  c.S.unscaled_pts = unscaled_pts ? 1 : 0;   // the fused point kernel leaves its columns unscaled (uvs_stash.cuh)
   int n = 0;
   if (fk) fork_from(fk, st, 1);
   if (D.nP) { k_back_points<<<cdiv3(D.nP, 128 / LPP), 128, 0, st>>>(D, c.S); n++; }

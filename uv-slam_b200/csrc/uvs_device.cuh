@@ -102,7 +102,9 @@ struct Dev {
   const int *fr_win;        // [nF] window of a frame (host-built)
   double *ftab[2];          // [nF][48] per-frame tables of the line / VP factors for state buffer 0 / 1 (uvs_linefast.cuh)
   double *lsc[2];           // [nL][8] sin, cos of the four orthonormal line parameters, per state buffer
-  int *pt_order;            // [nP] processing order of the fused point kernel: per window sorted by (anchor frame, track length)
+  int *pt_order;            // [32 nPW] points in the processing order of the fused point kernel (k_prep_point_order), -1 = empty lane
+  const int *pw_off;        // [B+1] warp slots of every window in pt_order
+  int nPW;
   int *pblk_col, *pblk_cam, *pblk_row;   // column in J0, tangent offset in the window (-1 const), state row
   double *imu_sqrt_info;    // [nImu][225]
   double *chain_lw;         // [B][chain_lw_stride] L_w blocks of the chain-mode reduced solve (k_chol_chain)

@@ -30,26 +30,46 @@
 namespace uvs {
 
 // ------------------------------------------------------------------------------------------------
-// processing order of the points of every window: sorted by (anchor frame, track length descending); points without
-// factors last.  One CTA per window; keys in `key` (scratch, [nP]).
+// Processing order of the points: every WARP of k_lin_points gets points of ONE window with ONE anchor frame, sorted by
+// track length (descending), so that step k of a warp sees a single camera-block pair (i, i + 1 + k) for the usual
+// consecutive tracks.  Window w owns the warp slots [pw_off[w], pw_off[w + 1]) (host bound: ceil(np / 32) + frames);
+// pt_order[32 slot + lane] = global point or -1 (preset by a memset).  One CTA per window; `key` is scratch [nP].
 __global__ void __launch_bounds__(256) k_prep_point_order(Dev D, int *__restrict__ key) {
+  __shared__ int cnt[33], wstart[34];
   const int w = blockIdx.x;
   const int p0 = D.point_off[w], np = D.point_off[w + 1] - p0, fo = D.frame_off[w];
-  for (int p = threadIdx.x; p < np; p += blockDim.x) {
-    const int gp = p0 + p, n = D.pt_end[gp] - D.pt_begin[gp];
-    key[gp] = n <= 0 ? 0x7fffffff : ((D.proj_idx[D.pt_begin[gp]].x - fo) << 8 | (255 - min(n, 255)));
-  }
+  if (threadIdx.x < 33) cnt[threadIdx.x] = 0;
   __syncthreads();
   for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    const int gp = p0 + p, n = D.pt_end[gp] - D.pt_begin[gp];
+    int k = -1;
+    if (n > 0) {
+      const int a = min(max(D.proj_idx[D.pt_begin[gp]].x - fo, 0), 31);
+      k = a << 8 | (255 - min(n, 255));
+      atomicAdd(&cnt[a], 1);
+    }
+    key[gp] = k;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int a = 0; a < 32; a++) { wstart[a] = run; run += (cnt[a] + 31) >> 5; }
+    wstart[32] = run;
+  }
+  __syncthreads();
+  const int wbase = D.pw_off[w], wcap = D.pw_off[w + 1] - wbase;
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
     const int kp = key[p0 + p];
-    int rank = 0;
-    for (int q = 0; q < np; q++) { const int kq = key[p0 + q]; rank += (kq < kp || (kq == kp && q < p)) ? 1 : 0; }
-    D.pt_order[p0 + rank] = p0 + p;
+    if (kp < 0) continue;
+    int rank = 0;   // among the points of the same anchor
+    for (int q = 0; q < np; q++) { const int kq = key[p0 + q]; rank += (kq >= 0 && (kq >> 8) == (kp >> 8) && (kq < kp || (kq == kp && q < p))) ? 1 : 0; }
+    const int slot = wstart[kp >> 8] + (rank >> 5);
+    if (slot < wcap) D.pt_order[32 * (size_t)(wbase + slot) + (rank & 31)] = p0 + p;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int LP_NT = 128;   // threads (= points) per CTA of k_lin_points
+constexpr int LP_NT = 128;   // threads per CTA of k_lin_points (four warp slots)
 constexpr int PST = 27;      // stage row: [r(2) | Ji 2x6 | Jj 2x6] + 1 (odd stride: conflict-free stores)
 
 __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash S) {
@@ -61,9 +81,10 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
   double *row = stage + lane * PST;
   unsigned char *mlist = mlist_all[warp];
   const int t = blockIdx.x * LP_NT + threadIdx.x;
-  bool act = t < D.nP;
-  int gp = 0, w = 0, f0 = 0, n = 0;
-  if (act) { gp = D.pt_order[t]; w = D.pt_win[gp]; act = (D.ctl[w].state & WS_ACTIVE) != 0; }
+  int gp = (t >> 5) < D.nPW ? D.pt_order[t] : -1;
+  bool act = gp >= 0;
+  int w = 0, f0 = 0, n = 0;
+  if (act) { w = D.pt_win[gp]; act = (D.ctl[w].state & WS_ACTIVE) != 0; }
   const int mp = S.mp;
   double *Y = nullptr, *ph = nullptr;
   if (act) {
@@ -85,22 +106,53 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
   double colsq = 0.0, gk = 0.0, half = 0.0;
   double wa[6] = {0, 0, 0, 0, 0, 0};
   int row_i = 0;
-  // fragment offsets inside a staged row (see k_direct_fused): kind 2 = anchor frame before the observing frame
+  // Direct terms: G = [J_i (6) | r | 0 || J_j (6) | 0 0], two rows per factor.  G^T G on the FP64 tensor cores, four rows
+  // (two factors) per k-step: c00 = (i,i) block and, in column 6, the gradient of frame i; c01 = (i,j) block and, in row 6,
+  // the gradient of frame j; c11 = (j,j) block.  The A fragment of a column tile and its B fragment are the same value
+  // G[k = lane % 4][8 tile + lane / 4].  c00 belongs to the anchor frame, which a warp keeps over all steps: it is flushed
+  // only when the anchor changes (never, for the sorted order above).
   const int fcol = lane >> 2, frow = lane & 1, fsub = (lane >> 1) & 1;
-  const int o0_k2 = (fcol < 6 ? 2 + fcol : 8 + fcol) + 6 * frow, o0_k3 = (fcol < 6 ? 14 + fcol : fcol - 4) + 6 * frow;
-  const int o1_k2 = fcol < 4 ? 16 + fcol + 6 * frow : (fcol == 4 ? frow : -1);
-  const int o1_k3 = fcol < 4 ? 4 + fcol + 6 * frow : (fcol == 4 ? frow : -1);
+  const int o0 = fcol < 6 ? 2 + 6 * frow + fcol : (fcol == 6 ? frow : -1);
+  const int o1 = fcol < 6 ? 14 + 6 * frow + fcol : -1;
+  const int pr = lane >> 2, pc = 2 * (lane & 3);   // accumulator entries of this lane: (pr, pc), (pr, pc + 1)
+  double c00[2] = {0.0, 0.0};
+  int pk_i = -1, pk_fo = 0, pk_co = 0, pk_d = 0;   // anchor (pose row) c00 belongs to, and its window
+  long long pk_so = 0;
+  auto flush00 = [&]() {
+    if (pk_i < 0) return;
+    const int ra = 15 * (pk_i - pk_fo);
+    double *Sg = D.Smat + pk_so;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int q = pc + e;
+      if (pr < 6 && q >= pr && q < 6) {
+        atomicAdd(Sg + (size_t)(ra + pr) * pk_d + ra + q, c00[e]);
+        if (q == pr) atomicAdd(D.colsq_cam + pk_co + ra + pr, c00[e]);
+      } else if (pr < 6 && q == 6) {
+        atomicAdd(D.gS + pk_co + ra + pr, c00[e]); atomicAdd(D.gfull + pk_co + ra + pr, c00[e]);
+      }
+    }
+    c00[0] = c00[1] = 0.0;
+  };
+  // inputs of step 0 (the loads of step k + 1 are issued before step k is evaluated)
+  int4 ix = make_int4(-1, -1, 0, 0);
+  d3 pts_i = mk3(0, 0, 1), pts_j = mk3(0, 0, 1);
+  auto load_step = [&](int k) {
+    const int f = f0 + k;
+    ix = D.proj_idx[f];
+    const double *oi = D.proj_pts_i + 3 * (size_t)f, *oj = D.proj_pts_j + 3 * (size_t)f;
+    pts_i = mk3(__ldg(oi), __ldg(oi + 1), __ldg(oi + 2)); pts_j = mk3(__ldg(oj), __ldg(oj + 1), __ldg(oj + 2));
+  };
+  if (n > 0) load_step(0);
   for (int k = 0; k < nmax; k++) {
     const bool has = k < n;
     int ri = -1, rj = -1;
     if (has) {
-      const int f = f0 + k;
-      const int4 ix = D.proj_idx[f];
       ri = ix.x; rj = ix.y; row_i = ri;
-      const double *oi = D.proj_pts_i + 3 * (size_t)f, *oj = D.proj_pts_j + 3 * (size_t)f;
-      const d3 pts_i = mk3(__ldg(oi), __ldg(oi + 1), __ldg(oi + 2)), pts_j = mk3(__ldg(oj), __ldg(oj + 1), __ldg(oj + 2));
+      const d3 pi = pts_i, pj = pts_j;
+      if (k + 1 < n) load_step(k + 1);
       double jl[2], hr;
-      proj_eval<true, false>(D.pose[cur] + 7 * (size_t)ri, D.pose[cur] + 7 * (size_t)rj, ex, lam, pts_i, pts_j, P.S, nullptr, false,
+      proj_eval<true, false>(D.pose[cur] + 7 * (size_t)ri, D.pose[cur] + 7 * (size_t)rj, ex, lam, pi, pj, P.S, nullptr, false,
                              P.cauchy_point, true, 6, row, row + 2, row + 14, nullptr, jl, nullptr, &hr);
       half += hr;
       const double j0 = jl[0], j1 = jl[1];
@@ -117,7 +169,7 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
       y2[0] = make_double2(u[0], u[1]); y2[1] = make_double2(u[2], u[3]); y2[2] = make_double2(u[4], u[5]);
     }
     __syncwarp();
-    // ---- direct terms of this step's factors, grouped by camera-block pair
+    // ---- direct terms of this step's factors, grouped by camera-block pair (one group per step for sorted consecutive tracks)
     unsigned todo = __ballot_sync(full, has);
     while (todo) {
       const int leader = __ffs(todo) - 1;
@@ -125,45 +177,54 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
       const unsigned grp = __ballot_sync(full, has && ri == li && rj == lj);
       todo &= ~grp;
       const int m = __popc(grp);
-      if (grp >> lane & 1u) mlist[__popc(grp & ((1u << lane) - 1u))] = (unsigned char)lane;
-      __syncwarp();
-      const bool swp = li > lj;   // block a = the earlier frame
-      const int o0 = swp ? o0_k3 : o0_k2, o1 = swp ? o1_k3 : o1_k2;
-      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+      const bool contiguous = grp == ((m == 32 ? full : ((1u << m) - 1u)) << leader);   // members = lanes leader .. leader + m - 1
+      if (!contiguous) {
+        if (grp >> lane & 1u) mlist[__popc(grp & ((1u << lane) - 1u))] = (unsigned char)lane;
+        __syncwarp();
+      }
+      if (li != pk_i) {   // uniform
+        flush00();
+        pk_i = li; pk_fo = __shfl_sync(full, fo, leader); pk_co = __shfl_sync(full, co, leader); pk_d = __shfl_sync(full, d, leader);
+        pk_so = __shfl_sync(full, s_off, leader);
+      }
+      double c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
       for (int s = 0; 2 * s < m; s++) {
         const int it = 2 * s + fsub;
         double g0 = 0.0, g1 = 0.0;
         if (it < m) {
-          const double *rec = stage + (int)mlist[it] * PST;
-          g0 = rec[o0];
+          const double *rec = stage + (contiguous ? leader + it : (int)mlist[it]) * PST;
+          if (o0 >= 0) g0 = rec[o0];
           if (o1 >= 0) g1 = rec[o1];
         }
         dmma884(c00, g0, g0);
         dmma884(c01, g0, g1);
         dmma884(c11, g1, g1);
       }
-      const int lfo = __shfl_sync(full, fo, leader), lco = __shfl_sync(full, co, leader), ld = __shfl_sync(full, d, leader);
-      const long long lso = __shfl_sync(full, s_off, leader);
-      double *Sg = D.Smat + lso;
-      const int ra = 15 * ((swp ? lj : li) - lfo), rb = 15 * ((swp ? li : lj) - lfo);
-      // entry (p, q) of G^T G, p <= q: columns 0..5 -> block a, 6..11 -> block b, 12 -> gradient
-      auto put = [&](int p, int q, double v) {
-        const bool isg = q == 12;
-        const bool ok = p < 12 && (isg || (q < 12 && p <= q));
-        const int gpp = (p < 6 ? ra : rb - 6) + p, gq = (q < 6 ? ra : rb - 6) + q;
-        if (ok) {
-          atomicAdd(isg ? D.gS + lco + gpp : Sg + (size_t)gpp * ld + gq, v);
-          if (isg) atomicAdd(D.gfull + lco + gpp, v);
-          else if (p == q) atomicAdd(D.colsq_cam + lco + gpp, v);
+      // flush of the (i,j) block + gradient of j (c01) and the (j,j) block (c11)
+      {
+        const int ra = 15 * (li - pk_fo), rb = 15 * (lj - pk_fo);
+        double *Sg = D.Smat + pk_so;
+        const bool up = li < lj;   // the system keeps its upper triangle: block (i,j) as is, or transposed when j comes first
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int q = pc + e;
+          if (q < 6) {
+            if (pr < 6) {
+              atomicAdd(up ? Sg + (size_t)(ra + pr) * pk_d + rb + q : Sg + (size_t)(rb + q) * pk_d + ra + pr, c01[e]);
+              if (q >= pr) {
+                atomicAdd(Sg + (size_t)(rb + pr) * pk_d + rb + q, c11[e]);
+                if (q == pr) atomicAdd(D.colsq_cam + pk_co + rb + pr, c11[e]);
+              }
+            } else if (pr == 6) {
+              atomicAdd(D.gS + pk_co + rb + q, c01[e]); atomicAdd(D.gfull + pk_co + rb + q, c01[e]);
+            }
+          }
         }
-      };
-      const int pr = lane >> 2, pc = 2 * (lane & 3);
-      put(pr, pc, c00[0]); put(pr, pc + 1, c00[1]);
-      put(pr, 8 + pc, c01[0]); put(pr, 9 + pc, c01[1]);
-      put(8 + pr, 8 + pc, c11[0]); put(8 + pr, 9 + pc, c11[1]);
+      }
       __syncwarp();
     }
   }
+  flush00();
   add_window_scalar(D.acc + ACC_COST0, ACC_STRIDE, w, half, act);
   if (!act) return;
   // ---- elimination of the 1x1 landmark block (same arithmetic as k_core_points)
@@ -188,8 +249,8 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
 constexpr int LL_NT = 128;                 // threads per CTA: 16 lines x 8 lanes
 constexpr int LSLOT = 12;                  // observations staged per line (<= frames of a window on this path)
 constexpr int WSLOTS = (32 / LPL) * LSLOT; // staged observations per warp
-// doubles of shared memory per warp: line + VP stage, frame / VP flag of every slot (ints), row list of a frame group (ints)
-constexpr int LL_WARP_DOUBLES = WSLOTS * (REC_LINE + REC_VP) + WSLOTS + (3 * WSLOTS + 1) / 2;
+// doubles of shared memory per warp: line + VP stage, frame / VP flag of every slot (ints)
+constexpr int LL_WARP_DOUBLES = WSLOTS * (REC_LINE + REC_VP) + WSLOTS;
 
 template <bool kJac>
 struct LineVpSinkF {
@@ -213,15 +274,17 @@ __global__ void __launch_bounds__(LL_NT, 3) k_lin_lines(Dev D, Params P, Stash S
   // shared: frame tables [max_frames][FT_STRIDE] | per warp: line stage [WSLOTS][REC_LINE], VP stage [WSLOTS][REC_VP],
   //         frame of a slot (-1 = empty), VP flag, row list of the direct-term grouping
   double *ftab = lsm;
-  double *wbase = lsm + ((max_frames * FT_STRIDE + 1) & ~1) + warp * LL_WARP_DOUBLES;
+  const int ftab_doubles = (max_frames * FT_STRIDE + 1) & ~1;
+  double *wbase = lsm + ftab_doubles + warp * LL_WARP_DOUBLES;
+  signed char *slotof = reinterpret_cast<signed char *>(lsm + ftab_doubles + (LL_NT / 32) * LL_WARP_DOUBLES);   // [16 lines][16 frames] observation (| 0x40: VP) or -1
   double *lstage = wbase, *vstage = wbase + WSLOTS * REC_LINE;
   int *sframe = reinterpret_cast<int *>(vstage + WSLOTS * REC_VP);        // [WSLOTS]
   int *svp = sframe + WSLOTS;                                              // [WSLOTS]
-  int *rowlist = svp + WSLOTS;                                             // [3 * WSLOTS] rows of one frame group
   const int fo = D.frame_off[w], F = D.frame_off[w + 1] - fo;
   const int cur = D.cur[w];
   load_frame_tables(D.ftab[cur] + (size_t)fo * FT_DOUBLES, F, ftab, LL_NT);
   for (int e = lane; e < WSLOTS; e += 32) { sframe[e] = -1; svp[e] = 0; }
+  for (int e = threadIdx.x; e < (LL_NT / LPL) * 16; e += LL_NT) slotof[e] = -1;
   __syncthreads();
 
   const int grp = lane / LPL, sub = lane - grp * LPL;
@@ -271,67 +334,46 @@ __global__ void __launch_bounds__(LL_NT, 3) k_lin_lines(Dev D, Params P, Stash S
     half += sink.ln.half_rho + sink.vp.half_rho;
     sframe[slot] = ix.x - fo;
     svp[slot] = ix.w >= 0 ? 1 : 0;
+    slotof[(threadIdx.x / LPL) * 16 + (ix.x - fo)] = (signed char)(f | (ix.w >= 0 ? 0x40 : 0));
   }
   add_window_scalar(D.acc + ACC_COST0, ACC_STRIDE, w, half, act);
-  __syncwarp();
 
-  // ---- diagonal direct terms of the warp's observations, grouped by frame: G = [J_pose (6) | r | 0], one row per
-  //      residual row (two per line observation, one per VP factor), G^T G on the FP64 tensor cores
+  // ---- diagonal direct terms of the CTA's observations, per frame: G = [J_pose (6) | r | 0], one row per residual row
+  //      (two per line observation, one per VP factor), G^T G on the FP64 tensor cores.  Warp q takes the frames q, q + 4,
+  //      q + 8, ...; row r of a frame's G is fixed to (line r / 3 of the CTA, row type r % 3) and read through the
+  //      (line, frame) -> observation table, absent rows are zero: no lists, one flush per frame and CTA.
+  __syncthreads();
   {
     const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
     double *Sg = D.Smat + D.S_off[w];
-    // slots of this lane: lane and lane + 32 (WSLOTS = 48)
-    const int s0 = lane, s1 = lane + 32;
-    const int fr0 = sframe[s0], fr1 = s1 < WSLOTS ? sframe[s1] : -1;
-    const int vp0 = svp[s0], vp1 = s1 < WSLOTS ? svp[s1] : 0;
-    unsigned present = 0;   // frames that occur in this warp
-    {
-      unsigned mine = (fr0 >= 0 ? 1u << fr0 : 0u) | (fr1 >= 0 ? 1u << fr1 : 0u);
-      present = __reduce_or_sync(full, mine);
-    }
-    const unsigned lt = (1u << lane) - 1u;
-    while (present) {
-      const int jj = __ffs(present) - 1;
-      present &= present - 1;
-      const unsigned b0 = __ballot_sync(full, fr0 == jj), b1 = __ballot_sync(full, fr1 == jj);
-      const unsigned v0 = __ballot_sync(full, fr0 == jj && vp0), v1 = __ballot_sync(full, fr1 == jj && vp1);
-      const int base_l1 = 2 * __popc(b0), base_v0 = base_l1 + 2 * __popc(b1), base_v1 = base_v0 + __popc(v0);
-      const int total = base_v1 + __popc(v1);
-      // row descriptor: offset of the six pose-Jacobian entries | offset of the residual << 16 (doubles from lstage)
-      if (fr0 == jj) {
-        const int o = s0 * REC_LINE, p = 2 * __popc(b0 & lt);
-        rowlist[p] = (o + 2) | (o << 16); rowlist[p + 1] = (o + 8) | ((o + 1) << 16);
-        if (vp0) { const int ov = WSLOTS * REC_LINE + s0 * REC_VP; rowlist[base_v0 + __popc(v0 & lt)] = (ov + 1) | (ov << 16); }
-      }
-      if (fr1 == jj) {
-        const int o = s1 * REC_LINE, p = base_l1 + 2 * __popc(b1 & lt);
-        rowlist[p] = (o + 2) | (o << 16); rowlist[p + 1] = (o + 8) | ((o + 1) << 16);
-        if (vp1) { const int ov = WSLOTS * REC_LINE + s1 * REC_VP; rowlist[base_v1 + __popc(v1 & lt)] = (ov + 1) | (ov << 16); }
-      }
-      __syncwarp();
+    const int fcol = lane >> 2, krow = lane & 3;
+    const int pr = lane >> 2, pc = 2 * (lane & 3);
+    for (int jj = warp; jj < F; jj += LL_NT / 32) {
       double cc[2] = {0.0, 0.0};
-      const int fcol = lane >> 2, krow = lane & 3;
-      for (int r0 = 0; r0 < total; r0 += 4) {
+#pragma unroll 4
+      for (int ks = 0; ks < 3 * (LL_NT / LPL) / 4; ks++) {
+        const int r = 4 * ks + krow, ln = r / 3, ty = r - 3 * ln;
+        const int sl = slotof[ln * 16 + jj];
         double g = 0.0;
-        if (r0 + krow < total && fcol < 7) {
-          const int ds = rowlist[r0 + krow];
-          g = fcol < 6 ? lstage[(ds & 0xffff) + fcol] : lstage[ds >> 16];
+        if (sl >= 0 && fcol < 7 && (ty < 2 || (sl & 0x40))) {
+          const double *wb = lsm + ftab_doubles + (ln >> 2) * LL_WARP_DOUBLES;   // stage of the warp that owns line ln
+          const int slot = (ln & 3) * LSLOT + (sl & 0x3f);
+          const double *rec = ty < 2 ? wb + slot * REC_LINE : wb + WSLOTS * REC_LINE + slot * REC_VP;
+          g = ty == 0 ? (fcol < 6 ? rec[2 + fcol] : rec[0]) : (ty == 1 ? (fcol < 6 ? rec[8 + fcol] : rec[1]) : (fcol < 6 ? rec[1 + fcol] : rec[0]));
         }
         dmma884(cc, g, g);
       }
       const int ra = 15 * jj;
-      const int pr = lane >> 2, pc = 2 * (lane & 3);
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        const int p = pr, q = pc + e;
-        if (p >= 6 || q > 6) continue;
-        if (q == 6) { atomicAdd(D.gS + co + ra + p, cc[e]); atomicAdd(D.gfull + co + ra + p, cc[e]); }
-        else if (p <= q) {
-          atomicAdd(Sg + (size_t)(ra + p) * d + ra + q, cc[e]);
-          if (p == q) atomicAdd(D.colsq_cam + co + ra + p, cc[e]);
+        const int q = pc + e;
+        if (pr < 6 && q >= pr && q < 6) {
+          atomicAdd(Sg + (size_t)(ra + pr) * d + ra + q, cc[e]);
+          if (q == pr) atomicAdd(D.colsq_cam + co + ra + pr, cc[e]);
+        } else if (pr < 6 && q == 6) {
+          atomicAdd(D.gS + co + ra + pr, cc[e]); atomicAdd(D.gfull + co + ra + pr, cc[e]);
         }
       }
-      __syncwarp();
     }
   }
   if (!act) return;   // uniform over the lane group
@@ -479,14 +521,14 @@ int launch_prep_point_order(const Dev &D, int *key_scratch, cudaStream_t st) {
 }
 
 size_t lin_lines_smem(int max_frames) {
-  return ((size_t)((max_frames * FT_STRIDE + 1) & ~1) + (size_t)(LL_NT / 32) * LL_WARP_DOUBLES) * sizeof(double);
+  return ((size_t)((max_frames * FT_STRIDE + 1) & ~1) + (size_t)(LL_NT / 32) * LL_WARP_DOUBLES) * sizeof(double) + (LL_NT / LPL) * 16;
 }
 int lin_max_line_obs() { return LSLOT; }
 
 int launch_lin_points(const Dev &D, const Params &P, char *base, const Build3Layout &lay, cudaStream_t st) {
-  if (D.nP == 0) return 0;
+  if (D.nP == 0 || D.nPW == 0) return 0;
   Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp; S.unscaled_pts = 1;
-  k_lin_points<<<cdivl(D.nP, LP_NT), LP_NT, 0, st>>>(D, P, S);
+  k_lin_points<<<cdivl(32 * D.nPW, LP_NT), LP_NT, 0, st>>>(D, P, S);
   return 1;
 }
 

@@ -12,7 +12,8 @@ namespace uvs_host {
 namespace {
 UvsHandle *g_handle = nullptr;
 UvsOptions g_opts;
-std::once_flag g_once;
+std::once_flag g_once, g_handle_once;
+int g_device = 0;
 const double kIdentityPose[7] = {0, 0, 0, 0, 0, 0, 1};
 
 void copy_block(double **jacobians, int b, const double *src, int rows, int cols) {
@@ -25,9 +26,13 @@ UvsOptions &shared_options() {
   return g_opts;
 }
 
+int shared_device() { return g_device; }
+void set_shared_device(int device) { g_device = device; }
+
+// the handle of the single-factor Evaluate() drop-ins only; every GpuWindowProblem owns its own handle
 UvsHandle *shared_handle() {
   shared_options();
-  if (!g_handle && uvs_create(0, &g_handle) != UVS_OK) g_handle = nullptr;
+  std::call_once(g_handle_once, [] { if (uvs_create(g_device, &g_handle) != UVS_OK) g_handle = nullptr; });
   return g_handle;
 }
 

@@ -20,9 +20,12 @@
 
 namespace uvs_host {
 
-// One process-wide handle for the single-factor calls (the reference calls Evaluate() from one thread,
-// ceres num_threads = 1, estimator.cpp:985 commented out).
+// One process-wide handle for the single-factor Evaluate() calls (the reference calls Evaluate() from one thread,
+// ceres num_threads = 1, estimator.cpp:985 commented out); created once (std::call_once), not re-entrant.  A
+// GpuWindowProblem never uses it: each problem owns a handle, so an Evaluate() call cannot replace its device batch.
 UvsHandle *shared_handle();
+int shared_device();                 // CUDA device of the handles created by this library (default 0)
+void set_shared_device(int device);  // call before the first factor / problem is used
 UvsOptions &shared_options();   // FOCAL_LENGTH, G, LINE_FACTOR, VP_FACTOR, TR, ROW of parameters.h:11-47
 
 struct PreintegrationView {   // the members of IntegrationBase the factor reads (integration_base.h:188-207)

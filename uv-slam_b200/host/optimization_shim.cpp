@@ -17,6 +17,27 @@ GpuWindowProblem::GpuWindowProblem(int n_frames, double (*para_Pose)[7], double 
   std::memcpy(ric_, I3, sizeof(I3)); std::memcpy(tic_, z3, sizeof(z3));
 }
 
+GpuWindowProblem::~GpuWindowProblem() {
+  if (h_) uvs_destroy(h_);
+}
+
+UvsHandle *GpuWindowProblem::handle() {
+  if (!h_ && uvs_create(shared_device(), &h_) != UVS_OK) h_ = nullptr;
+  return h_;
+}
+
+// the td arrays are filled by addProjectionTd() only: a mix of addProjection() and addProjectionTd() calls (or
+// setEstimateTd(true) with plain addProjection()) would leave them shorter than n_proj
+int GpuWindowProblem::check_sizes() {
+  const size_t n = p_fi_.size();
+  if (estimate_td_ && (p_vi_.size() != 2 * n || p_vj_.size() != 2 * n || p_tdi_.size() != n || p_tdj_.size() != n || p_rwi_.size() != n ||
+                       p_rwj_.size() != n)) {
+    err_ = "estimate_td is set but not every projection factor was added with addProjectionTd()";
+    return UVS_ERR_INVALID_ARG;
+  }
+  return UVS_OK;
+}
+
 void GpuWindowProblem::setLineExtrinsic(const double ric[9], const double tic[3]) {
   std::memcpy(ric_, ric, 72); std::memcpy(tic_, tic, 24);
 }
@@ -77,8 +98,9 @@ UvsWindow GpuWindowProblem::view() {
 }
 
 int GpuWindowProblem::solve(UvsSummary *summary) {
-  UvsHandle *h = shared_handle();
+  UvsHandle *h = handle();
   if (!h) { err_ = "no CUDA device (there is no CPU fallback)"; return UVS_ERR_CUDA; }
+  if (int rc = check_sizes()) return rc;
   UvsWindow w = view();
   const int rc = uvs_batch_solve(h, 1, &w, &opts_, summary);
   if (rc != UVS_OK) err_ = uvs_last_error(h);
@@ -87,6 +109,7 @@ int GpuWindowProblem::solve(UvsSummary *summary) {
 }
 
 int GpuWindowProblem::save(const char *path) {
+  if (int rc = check_sizes()) return rc;
   const UvsWindow w = view();
   const int rc = save_window(w, path);
   if (rc) err_ = "GpuWindowProblem::save: cannot write the window";
@@ -94,9 +117,15 @@ int GpuWindowProblem::save(const char *path) {
 }
 
 int GpuWindowProblem::marginalize(int flag, PriorData &out) {
-  UvsHandle *h = shared_handle();
+  UvsHandle *h = handle();
   if (!h) { err_ = "no CUDA device (there is no CPU fallback)"; return UVS_ERR_CUDA; }
   if (!uploaded_) { err_ = "marginalize() needs a solved window"; return UVS_ERR_NO_WINDOW; }
+  {
+    // linearise at the state the caller holds NOW (gauge-fixed and re-packed, see the header), with the current ric / tic
+    UvsWindow w = view();
+    const int rc = uvs_upload_state(h, 1, &w);
+    if (rc != UVS_OK) { err_ = uvs_last_error(h); out.n = 0; return rc; }
+  }
   const int cap_n = 16 * n_frames_ + 16, cap_b = 2 * n_frames_ + 8;
   out.J.assign((size_t)cap_n * cap_n, 0.0); out.r.assign(cap_n, 0.0); out.x0.assign((size_t)9 * cap_b, 0.0);
   out.block_kind.assign(cap_b, 0); out.block_id.assign(cap_b, 0);

@@ -42,10 +42,17 @@ class GpuWindowProblem {
   void addLine(int frame_j, int line_index, const double sp[2], const double ep[2]);                              // :916-918
   void addVP(int frame_j, int line_index, const double vp[3]);                                                    // :920-925
 
+  ~GpuWindowProblem();
+  GpuWindowProblem(const GpuWindowProblem &) = delete;
+  GpuWindowProblem &operator=(const GpuWindowProblem &) = delete;
+
   // ceres::Solve replacement.  Returns the UvsStatus; parameters are updated in place.
   int solve(UvsSummary *summary = nullptr);
-  // next prior from the solved state (flag = marginalization_flag); returns UvsStatus, out.n == 0 when the
-  // reference would build nothing.
+  // Next prior (flag = marginalization_flag); returns UvsStatus, out.n == 0 when the reference would build nothing.
+  // The prior is linearised at the CURRENT contents of the para_* arrays, not at the device's raw solver state: the
+  // reference runs double2vector() (yaw / position gauge fix, estimator.cpp:596-711) and vector2double() again
+  // (:1006 / :1168) between ceres::Solve and the marginalization, so call this after those two, exactly where the
+  // reference builds its MarginalizationInfo.  The state (and ric / tic of the line functors) is re-uploaded first.
   int marginalize(int flag, PriorData &out);
   // dump hook: the assembled window in the `uvs_window v1` format of tests/ and bench.py - call it
   // before solve() to record what the reference would hand to ceres::Solve.  Returns the UvsStatus.
@@ -64,6 +71,9 @@ class GpuWindowProblem {
   std::vector<double> p_pi_, p_pj_, p_vi_, p_vj_, p_tdi_, p_tdj_, p_rwi_, p_rwj_, l_sp_, l_ep_, v_dir_;
   std::vector<double> i_dp_, i_dq_, i_dv_, i_dt_, i_ba_, i_bg_, i_jac_, i_cov_;
   std::string err_;
+  UvsHandle *h_ = nullptr;   // this problem's own device batch: nothing another object uploads can get between solve() and marginalize()
+  UvsHandle *handle();
+  int check_sizes();
   UvsWindow view();
 };
 

@@ -26,8 +26,30 @@ struct Writer {
 
 }  // namespace
 
+// the format is little-endian; the writer emits host byte order
+static_assert(
+#if defined(__BYTE_ORDER__) && defined(__ORDER_LITTLE_ENDIAN__)
+    __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__,
+#else
+    true,
+#endif
+    "uvs_window v1 is little-endian: add a byte swap to Writer::raw for this target");
+
 int save_window(const UvsWindow &w, const char *path) {
   if (!path) return UVS_ERR_INVALID_ARG;
+  // the same size / consistency checks as uvs_upload_windows, before anything is written
+  if (w.n_frames < 1 || w.n_points < 0 || w.n_lines < 0 || w.n_proj < 0 || w.n_line_obs < 0 || w.n_vp_obs < 0 || w.n_imu < 0 ||
+      w.prior_n < 0 || w.prior_n_blocks < 0)
+    return UVS_ERR_INVALID_ARG;
+  if (w.prior_n > 0) {
+    if (!w.prior_block_kind || !w.prior_block_id || !w.prior_J || !w.prior_r || !w.prior_x0 || w.prior_n_blocks == 0) return UVS_ERR_INVALID_ARG;
+    int cols = 0;
+    for (int b = 0; b < w.prior_n_blocks; b++) {
+      const int k = w.prior_block_kind[b];
+      cols += (k == UVS_BLOCK_POSE || k == UVS_BLOCK_EXPOSE) ? 6 : (k == UVS_BLOCK_SPEEDBIAS ? 9 : 1);
+    }
+    if (cols != w.prior_n) return UVS_ERR_INVALID_ARG;   // local sizes of the kept blocks must add up to prior_n
+  }
   // global sizes of the kept blocks of the prior: pose / extrinsic 7, speed-bias 9, td 1 (marginalization_factor.cpp:203-215)
   int x0_len = 0;
   if (w.prior_n > 0) {
