@@ -11,7 +11,7 @@ from uvs_b200.window import (UvsOptionsStruct, UvsPriorStruct, UvsSummaryStruct,
                              c_double_p, c_int32_p, window_array)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "oracle", "liborc.so")
+LIB = os.environ.get("UVS_ORC_LIB") or os.path.join(ROOT, "oracle", "liborc.so")   # bench.py points this at its -march=native build
 F_PRIOR, F_IMU, F_PROJ, F_LINE, F_VP = 0, 1, 2, 3, 4
 _lib = None
 

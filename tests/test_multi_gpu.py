@@ -10,15 +10,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-def test_factor_parallel_two_gpus_match_single_gpu():
+@pytest.mark.parametrize("window,how", [("window_C2_s1002.uvsw", "nccl"), ("window_10k.uvsw", "nccl"), ("window_C2_s1002.uvsw", "callback")])
+def test_factor_parallel_two_gpus_match_single_gpu(window, how):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29581", os.path.join(ROOT, "tools", "run_factor_parallel.py"), "window_C2_s1002.uvsw", "2"],
+                        "--master-port", "29581", os.path.join(ROOT, "tools", "run_factor_parallel.py"), window, "2", how],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert abs(out["final_cost"] - out["final_cost_1gpu"]) <= 1e-6 * abs(out["final_cost_1gpu"])
     assert out["pose_diff"] < 1e-4 and out["inv_depth_diff"] < 1e-4
+    assert out["collectives_per_solve"] == 20   # ten LM iterations: one all-reduce of the reduced system + accumulators, one of the accumulators each

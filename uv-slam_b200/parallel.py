@@ -4,10 +4,11 @@ Two ways the path shards:
   * window-parallel - independent windows are split over the ranks, no data-path collective;
   * factor-parallel - ONE window's landmarks are split over the ranks (landmark k -> rank k % N, IMU factors
     and the prior on rank 0); every LM iteration the ranks sum their partial reduced camera systems
-    (one all-reduce of d^2 + 3d doubles) and a 16-double accumulator per window.  The C library takes the
-    reduction as a callback (`uvs_comm_init`), implemented here with `torch.distributed.all_reduce` on the
-    library's own CUDA stream (NCCL over NVLink on GPUs; the same code path runs over gloo on host buffers
-    in the CPU tests).
+    (ONE all-reduce of d^2 + 3d doubles + the 16-double accumulators per window) and, for the candidate cost, the
+    accumulators once more.  The C library holds its own NCCL communicator (`uvs_comm_init_nccl`, libnccl bound at run
+    time) or takes the reduction as a callback (`uvs_comm_init`), implemented here with
+    `torch.distributed.all_reduce` on the library's own CUDA stream (the same callback runs over gloo on host buffers in
+    the CPU tests).
 """
 from __future__ import annotations
 
@@ -26,6 +27,18 @@ def shard_windows(windows, rank: int, world: int):
 def landmark_owner(index, world: int):
     """rank that owns global landmark `index` in the factor-parallel mode (mirrors the device code)"""
     return np.asarray(index) % world
+
+
+def init_factor_parallel(solver, dist, rank: int, world: int, how: str = "nccl"):
+    """Puts `solver` into the factor-parallel mode.  how = "nccl": the library's own NCCL communicator - rank 0 creates the
+    ncclUniqueId (uvs_comm_unique_id), torch.distributed only carries its 128 bytes to the other ranks, every rank calls
+    uvs_comm_init_nccl; how = "callback": the all-reduce as a callback into torch.distributed (uvs_comm_init)."""
+    if how == "callback":
+        solver.comm_init(rank, world, make_allreduce(dist, "cuda"))
+        return
+    box = [solver.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    solver.comm_init_nccl(box[0], rank, world)
 
 
 def make_allreduce(dist, device: str = "cuda"):
