@@ -140,6 +140,7 @@ struct MargResult {
   std::vector<double> J, r;     // linearized_jacobians (n x n), linearized_residuals
   std::vector<int> block_kind, block_id;   // kept blocks, ids after the window shift
   std::vector<double> x0;       // global-size data of kept blocks
+  std::vector<double> A_full, b_full;   // the system before the Schur complement, (m + n) x (m + n), dropped blocks first (tests only)
 };
 
 // Build the next prior from the window's state `s`.  flag: UVS_MARGIN_OLD / UVS_MARGIN_SECOND_NEW.
@@ -249,6 +250,7 @@ inline bool marginalize(const Problem &P, const State &s, int flag, MargResult &
       for (int p = 0; p < size_i; p++) { double g = 0.0; for (int t = 0; t < f.nr; t++) g += f.J[i][(size_t)t * gi + p] * f.r[t]; b[idx_i + p] += g; }
     }
   }
+  out.A_full = A; out.b_full = b;
   // Amm^-1 by eigendecomposition with eigenvalues <= eps zeroed          marginalization_factor.cpp:266-272
   std::vector<double> Amm((size_t)m * m), ev, V;
   for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Amm[(size_t)i * m + j] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]);

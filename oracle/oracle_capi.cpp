@@ -160,6 +160,22 @@ int orc_marginalize(const UvsWindow *w, const UvsOptions *o, int flag, UvsPrior 
   return 0;
 }
 
+// the (m + n)-dimensional system A, b the prior is built from (before the Schur complement), for the high-precision
+// reference of tests/margref.py.  A_full: [cap x cap] row-major, first (m + n)^2 entries used.
+int orc_marginalize_system(const UvsWindow *w, const UvsOptions *o, int flag, double *A_full, double *b_full, int cap, int *m, int *n) {
+  Problem P(*w, *o);
+  State s = P.initial_state();
+  MargResult R;
+  *m = 0; *n = 0;
+  if (!marginalize(P, s, flag, R)) return 0;
+  const int pos = R.m + R.n;
+  if (pos > cap) return UVS_ERR_CAPACITY;
+  std::memcpy(A_full, R.A_full.data(), sizeof(double) * pos * pos);
+  std::memcpy(b_full, R.b_full.data(), sizeof(double) * pos);
+  *m = R.m; *n = R.n;
+  return 0;
+}
+
 // a4: preintegrate n IMU samples (integration_base.h:30-36, 130-158).  noise = {acc_n, gyr_n, acc_w, gyr_w}.
 int orc_preintegrate(int n, const double *dt, const double *acc, const double *gyr, const double *acc0, const double *gyr0,
                      const double *ba, const double *bg, const double *noise, double *delta_p, double *delta_q_xyzw,

@@ -125,6 +125,23 @@ def marginalize(w: Window, opts, flag=0):
                 x0=x0[:gs.sum()].copy())
 
 
+def marginalize_system(w: Window, opts, flag=0):
+    """-> (A [(m+n) x (m+n)], b, m, n): the system MarginalizationInfo::marginalize builds before its Schur complement
+    (dropped blocks first), or None"""
+    s = w.as_struct()
+    cap = 16 * w.n_frames + 16 + w.n_points + 4 * w.n_lines
+    A = np.zeros(cap * cap); b = np.zeros(cap)
+    m, n = C.c_int(), C.c_int()
+    fn = lib().orc_marginalize_system
+    fn.argtypes = [C.POINTER(UvsWindowStruct), C.POINTER(UvsOptionsStruct), C.c_int, c_double_p, c_double_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = fn(C.byref(s), C.byref(opts), flag, _p(A), _p(b), cap, C.byref(m), C.byref(n))
+    assert rc == 0, rc
+    if m.value + n.value == 0:
+        return None
+    pos = m.value + n.value
+    return A[:pos * pos].reshape(pos, pos).copy(), b[:pos].copy(), m.value, n.value
+
+
 def preintegrate(dt, acc, gyr, acc0, gyr0, ba, bg, noise):
     n = len(dt)
     f = lambda a: np.ascontiguousarray(a, dtype=np.float64)

@@ -52,7 +52,7 @@ def sass_lines(so_path, kernel, n_inst=None):
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 30
-    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "uv-slam_b200", "csrc", "libuvs_b200.so")
+    so = os.environ.get("UVS_SO", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "uv-slam_b200", "csrc", "libuvs_b200.so"))
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     # the report may hold several launches / instantiations of the kernel: --nth N picks the N-th block (default 0)

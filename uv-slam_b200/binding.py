@@ -38,7 +38,8 @@ class UvsError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "csrc", _LIB_NAME)
+    # UVS_LIB: developer override (e.g. a -DUVS_CHOL_TIMING build); the product library lives next to this package
+    return os.environ.get("UVS_LIB") or os.path.join(_HERE, "csrc", _LIB_NAME)
 
 
 def load_library():

@@ -803,7 +803,7 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
     (void)costc;
     if (h->nranks > 1) { rc = all_reduce(h, D.acc, (size_t)D.B * ACC_STRIDE); if (rc) return rc; }
     STAGE(9);
-    h->launches += launch_step(D, P, st); STAGE(10);
+    h->launches += launch_step(D, P, !h->chain_ok, st); STAGE(10);
     rc = post_launch(h, "step"); if (rc) return rc;
     return UVS_OK;
   };

@@ -83,7 +83,7 @@ int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool
 size_t chol_chain_smem(int max_frames, bool any_ex);
 int chol_chain_lw_doubles(int max_frames);
 int launch_chol_chain(const Dev &D, const Params &P, int max_frames, bool any_ex, bool mc_identity, cudaStream_t st);
-int launch_step(const Dev &D, const Params &P, cudaStream_t st);
+int launch_step(const Dev &D, const Params &P, bool clear_system, cudaStream_t st);
 int launch_finish(const Dev &D, cudaStream_t st);
 int launch_count_active(const Dev &D, int *out, cudaStream_t st);
 int launch_copy_acc(const Dev &D, int slot, double *out, int zero, cudaStream_t st);

@@ -20,6 +20,7 @@
 // Both write the same stash (uvs_stash.cuh) as k_core_points / k_core_lines of uvs_build3.cu; the rank update
 // (k_window_system), the IMU / prior tail and the back-substitution are shared with that path.
 #include <algorithm>
+#include <cstdlib>
 
 #include "uvs_device.cuh"
 #include "uvs_factors.cuh"
@@ -34,7 +35,7 @@ namespace uvs {
 // track length (descending), so that step k of a warp sees a single camera-block pair (i, i + 1 + k) for the usual
 // consecutive tracks.  Window w owns the warp slots [pw_off[w], pw_off[w + 1]) (host bound: ceil(np / 32) + frames);
 // pt_order[32 slot + lane] = global point or -1 (preset by a memset).  One CTA per window; `key` is scratch [nP].
-__global__ void __launch_bounds__(256) k_prep_point_order(Dev D, int *__restrict__ key) {
+__global__ void __launch_bounds__(256) k_prep_point_order(Dev D, int *__restrict__ key, int dense) {
   __shared__ int cnt[33], wstart[34];
   const int w = blockIdx.x;
   const int p0 = D.point_off[w], np = D.point_off[w + 1] - p0, fo = D.frame_off[w];
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(256) k_prep_point_order(Dev D, int *__restrict
   __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0;
-    for (int a = 0; a < 32; a++) { wstart[a] = run; run += (cnt[a] + 31) >> 5; }
+    // dense: the anchors share warps (fewer, fuller warps; a warp that straddles two anchors sees two block pairs per step)
+    for (int a = 0; a < 32; a++) { wstart[a] = run; run += dense ? cnt[a] : ((cnt[a] + 31) >> 5); }
     wstart[32] = run;
   }
   __syncthreads();
@@ -63,16 +65,23 @@ __global__ void __launch_bounds__(256) k_prep_point_order(Dev D, int *__restrict
     if (kp < 0) continue;
     int rank = 0;   // among the points of the same anchor
     for (int q = 0; q < np; q++) { const int kq = key[p0 + q]; rank += (kq >= 0 && (kq >> 8) == (kp >> 8) && (kq < kp || (kq == kp && q < p))) ? 1 : 0; }
-    const int slot = wstart[kp >> 8] + (rank >> 5);
-    if (slot < wcap) D.pt_order[32 * (size_t)(wbase + slot) + (rank & 31)] = p0 + p;
+    if (dense) {
+      const int pos = wstart[kp >> 8] + rank;   // position in the window's sorted list
+      D.pt_order[32 * (size_t)wbase + pos] = p0 + p;
+    } else {
+      const int slot = wstart[kp >> 8] + (rank >> 5);
+      if (slot < wcap) D.pt_order[32 * (size_t)(wbase + slot) + (rank & 31)] = p0 + p;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int LP_NT = 128;   // threads per CTA of k_lin_points (four warp slots)
 constexpr int PST = 27;      // stage row: [r(2) | Ji 2x6 | Jj 2x6] + 1 (odd stride: conflict-free stores)
 
-__global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash S) {
+// LP_NT threads per CTA (32: one warp slot per CTA - a finished warp frees its registers at once, whatever the track
+// lengths of its neighbours; 128: four), kPrefetch: the inputs of step k + 1 are loaded before step k is evaluated
+template <int LP_NT, bool kPrefetch, int kThreadsPerSM = 512>
+__global__ void __launch_bounds__(LP_NT, kThreadsPerSM / LP_NT) k_lin_points(Dev D, Params P, Stash S) {
   __shared__ double stage_all[LP_NT * PST];
   __shared__ unsigned char mlist_all[LP_NT / 32][32];
   const unsigned full = 0xffffffffu;
@@ -143,14 +152,15 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
     const double *oi = D.proj_pts_i + 3 * (size_t)f, *oj = D.proj_pts_j + 3 * (size_t)f;
     pts_i = mk3(__ldg(oi), __ldg(oi + 1), __ldg(oi + 2)); pts_j = mk3(__ldg(oj), __ldg(oj + 1), __ldg(oj + 2));
   };
-  if (n > 0) load_step(0);
+  if (kPrefetch && n > 0) load_step(0);
   for (int k = 0; k < nmax; k++) {
     const bool has = k < n;
     int ri = -1, rj = -1;
     if (has) {
+      if (!kPrefetch) load_step(k);
       ri = ix.x; rj = ix.y; row_i = ri;
       const d3 pi = pts_i, pj = pts_j;
-      if (k + 1 < n) load_step(k + 1);
+      if (kPrefetch && k + 1 < n) load_step(k + 1);
       double jl[2], hr;
       proj_eval<true, false>(D.pose[cur] + 7 * (size_t)ri, D.pose[cur] + 7 * (size_t)rj, ex, lam, pi, pj, P.S, nullptr, false,
                              P.cauchy_point, true, 6, row, row + 2, row + 14, nullptr, jl, nullptr, &hr);
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(LP_NT, 4) k_lin_points(Dev D, Params P, Stash 
 // ------------------------------------------------------------------------------------------------
 // lines
 constexpr int LL_NT = 128;                 // threads per CTA: 16 lines x 8 lanes
-constexpr int LSLOT = 12;                  // observations staged per line (<= frames of a window on this path)
+constexpr int LSLOT = 11;                  // observations staged per line (the reference's window has 11 frames; longer tracks -> record path)
 constexpr int WSLOTS = (32 / LPL) * LSLOT; // staged observations per warp
 // doubles of shared memory per warp: line + VP stage, frame / VP flag of every slot (ints)
 constexpr int LL_WARP_DOUBLES = WSLOTS * (REC_LINE + REC_VP) + WSLOTS;
@@ -262,7 +272,8 @@ struct LineVpSinkF {
 };
 
 // grid (ceil(max lines per window / 16), B): a CTA works on 16 lines of ONE window, so the frame tables are per CTA
-__global__ void __launch_bounds__(LL_NT, 3) k_lin_lines(Dev D, Params P, Stash S, int max_frames) {
+template <int kOcc>
+__global__ void __launch_bounds__(LL_NT, kOcc) k_lin_lines(Dev D, Params P, Stash S, int max_frames) {
   extern __shared__ __align__(16) double lsm[];
   const unsigned full = 0xffffffffu;
   const int w = blockIdx.y;
@@ -514,9 +525,14 @@ __global__ void __launch_bounds__(LL_NT, 3) k_lin_lines(Dev D, Params P, Stash S
 // ------------------------------------------------------------------------------------------------
 static inline int cdivl(int a, int b) { return (a + b - 1) / b; }
 
+static int env_int(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
 int launch_prep_point_order(const Dev &D, int *key_scratch, cudaStream_t st) {
   if (D.nP == 0) return 0;
-  k_prep_point_order<<<D.B, 256, 0, st>>>(D, key_scratch);
+  k_prep_point_order<<<D.B, 256, 0, st>>>(D, key_scratch, env_int("UVS_PT_DENSE", 1));
   return 1;
 }
 
@@ -528,7 +544,17 @@ int lin_max_line_obs() { return LSLOT; }
 int launch_lin_points(const Dev &D, const Params &P, char *base, const Build3Layout &lay, cudaStream_t st) {
   if (D.nP == 0 || D.nPW == 0) return 0;
   Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp; S.unscaled_pts = 1;
-  k_lin_points<<<cdivl(32 * D.nPW, LP_NT), LP_NT, 0, st>>>(D, P, S);
+  // developer switches (A/B runs): UVS_PT_CTA = threads per CTA (32 | 128), UVS_PT_PREFETCH = 0 | 1
+  const int cta = env_int("UVS_PT_CTA", 32), pre = env_int("UVS_PT_PREFETCH", 0), occ = env_int("UVS_PT_OCC", 512);
+  if (cta == 32 && occ == 640) k_lin_points<32, false, 640><<<D.nPW, 32, 0, st>>>(D, P, S);
+  else if (cta == 32 && occ == 768) k_lin_points<32, false, 768><<<D.nPW, 32, 0, st>>>(D, P, S);
+  else if (cta == 128) {
+    if (pre) k_lin_points<128, true><<<cdivl(32 * D.nPW, 128), 128, 0, st>>>(D, P, S);
+    else k_lin_points<128, false><<<cdivl(32 * D.nPW, 128), 128, 0, st>>>(D, P, S);
+  } else {
+    if (pre) k_lin_points<32, true><<<D.nPW, 32, 0, st>>>(D, P, S);
+    else k_lin_points<32, false><<<D.nPW, 32, 0, st>>>(D, P, S);
+  }
   return 1;
 }
 
@@ -537,8 +563,14 @@ int launch_lin_lines(const Dev &D, const Params &P, char *base, const Build3Layo
   Stash S; S.Y = (double *)(base + lay.o_Y); S.ph = (double *)(base + lay.o_ph); S.lh = (double *)(base + lay.o_lh); S.mp = lay.mp; S.unscaled_pts = 1;
   const size_t smem = lin_lines_smem(max_frames);
   static size_t raised = 0;
-  if (smem > raised) { cudaFuncSetAttribute(k_lin_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
-  k_lin_lines<<<dim3(cdivl(max_lines, LL_NT / LPL), D.B), LL_NT, smem, st>>>(D, P, S, max_frames);
+  if (smem > raised) {
+    cudaFuncSetAttribute(k_lin_lines<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_lin_lines<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    raised = smem;
+  }
+  const dim3 grid(cdivl(max_lines, LL_NT / LPL), D.B);
+  if (env_int("UVS_LL_OCC", 4) == 3) k_lin_lines<3><<<grid, LL_NT, smem, st>>>(D, P, S, max_frames);
+  else k_lin_lines<4><<<grid, LL_NT, smem, st>>>(D, P, S, max_frames);
   return 1;
 }
 

@@ -379,7 +379,7 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 // Solves (D_s S D_s + D^2) y = -D_s g for one window; y (in the order of S) -> yout (global).  All threads of the CTA.
-__device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int &s_flag, const Params &P, const double *Sg, int d, int F,
+__device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int &s_flag, const Params &P, double *Sg, int d, int F,
                             const double *scale, const double *colsq, const double *gS, double radius, double *yout, double *lwg) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
   const int nd = d - 9 * F;
@@ -416,15 +416,27 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     if (q0 < 9) { if (cc <= q0) cp_async8(Cb[buf] + 9 * q0 + cc, Sg + (size_t)col * d + c0 + q0); }
     else if (q0 < 18 && fb > 0) cp_async8(Xb[buf] + 9 * (q0 - 9) + cc, Sg + (size_t)(cb(fb - 1) + q0 - 9) * d + col);
   };
-  auto scale_block = [&](int fb, int buf) {   // every thread scales what it copied
+  // every thread scales what it copied - and clears the copied entries of S: the system is consumed here, so the next
+  // linearisation finds it zeroed without a clearing pass of its own (k_step keeps that pass for the other solvers)
+  auto scale_block = [&](int fb, int buf) {
     if (!part) return;
     const int c0 = cb(fb), col = c0 + cc;
     const double scol = scale[col];
 #pragma unroll 4
-    for (int q = q0; q < nd; q += R) Wb[buf][9 * q + cc] *= scale[sidx(q)] * scol;
+    for (int q = q0; q < nd; q += R) {
+      const int sq = sidx(q);
+      Wb[buf][9 * q + cc] *= scale[sq] * scol;
+      if (sq <= col) Sg[(size_t)sq * d + col] = 0.0; else Sg[(size_t)col * d + sq] = 0.0;
+    }
     if (q0 < 9) {
-      if (cc <= q0) { double v = Cb[buf][9 * q0 + cc] * scale[c0 + q0] * scol; if (cc == q0) v += lm(col); Cb[buf][9 * q0 + cc] = v; }
-    } else if (q0 < 18 && fb > 0) Xb[buf][9 * (q0 - 9) + cc] *= scale[cb(fb - 1) + q0 - 9] * scol;
+      if (cc <= q0) {
+        double v = Cb[buf][9 * q0 + cc] * scale[c0 + q0] * scol; if (cc == q0) v += lm(col); Cb[buf][9 * q0 + cc] = v;
+        Sg[(size_t)col * d + c0 + q0] = 0.0;
+      }
+    } else if (q0 < 18 && fb > 0) {
+      Xb[buf][9 * (q0 - 9) + cc] *= scale[cb(fb - 1) + q0 - 9] * scol;
+      Sg[(size_t)(cb(fb - 1) + q0 - 9) * d + col] = 0.0;
+    }
   };
 
 #ifdef UVS_CHOL_TIMING
@@ -450,8 +462,9 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   cp_async_wait();
   __syncthreads();
   for (int qj = warp; qj < nd; qj += nw) {
-    const double sj = scale[sidx(qj)];
-    for (int qi = qj + lane; qi < nd; qi += 32) { double *a = slot(qi, qj); *a = scale[sidx(qi)] * sj * *a; }
+    const int sjj = sidx(qj);
+    const double sj = scale[sjj];
+    for (int qi = qj + lane; qi < nd; qi += 32) { double *a = slot(qi, qj); *a = scale[sidx(qi)] * sj * *a; Sg[(size_t)sjj * d + sidx(qi)] = 0.0; }
   }
   scale_block(F - 1, (F - 1) & 1);
   __syncthreads();
@@ -703,6 +716,7 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
                                 D.chain_lw + (size_t)w * D.chain_lw_stride);
     if (!ok) {
       if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
+      zero_window_system(D, w);   // the failed solve consumed (and cleared) only part of the system
       return;
     }
     CHOL_TS(4);
@@ -943,13 +957,14 @@ __global__ void __launch_bounds__(256, 4) k_chol_chain(Dev D, Params P, int mc_i
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
   if (D.acc[(size_t)w * ACC_STRIDE + ACC_FAIL] != 0.0) {   // a landmark block was not positive definite
     if (threadIdx.x == 0) { D.ctl[w].state &= ~WS_STEP_OK; D.ctl[w].have_scale = 1; if (D.ctl[w].iter == 0) { D.ctl[w].cost = D.acc[(size_t)w * ACC_STRIDE + ACC_COST0]; D.ctl[w].iter = 1; D.summary[w].initial_cost = D.ctl[w].cost; D.summary[w].cost[0] = D.ctl[w].cost; } }
+    zero_window_system(D, w);   // nobody consumes this system: clear it for the rebuild (k_step leaves the matrix to this kernel)
     return;
   }
   chol_window<2>(D, P, w, smem, mc_identity != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CT) k_step(Dev D, Params P) {
+__global__ void __launch_bounds__(CT) k_step(Dev D, Params P, int clear_system) {
   const int w = blockIdx.x;
   WinCtl &c = D.ctl[w];
   if (!(c.state & WS_ACTIVE)) return;
@@ -1006,7 +1021,12 @@ __global__ void __launch_bounds__(CT) k_step(Dev D, Params P) {
     if (done) c.state &= ~WS_ACTIVE;
     for (int e = 0; e < ACC_STRIDE; e++) acc[e] = 0.0;
   }
-  zero_window_system(D, w);
+  // chain mode: k_chol_chain has cleared the matrix while consuming it; only the three vectors are left
+  if (clear_system) zero_window_system(D, w);
+  else {
+    const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) { D.gS[co + e] = 0.0; D.gfull[co + e] = 0.0; D.colsq_cam[co + e] = 0.0; }
+  }
 }
 
 // final bookkeeping: summaries (device copy), number of active windows
@@ -1095,7 +1115,11 @@ size_t chol_max_dynamic_smem(size_t optin_bytes) {
   return dyn;
 }
 
-int launch_step(const Dev &D, const Params &P, cudaStream_t st) { k_step<<<D.B, CT, 0, st>>>(D, P); return 1; }
+int launch_step(const Dev &D, const Params &P, bool clear_system, cudaStream_t st) {
+  if (clear_system) k_step<<<D.B, CT, 0, st>>>(D, P, 1);
+  else k_step<<<D.B, 192, 0, st>>>(D, P, 0);
+  return 1;
+}
 int launch_finish(const Dev &D, cudaStream_t st) { k_finish<<<(D.B + 127) / 128, 128, 0, st>>>(D); return 1; }
 int launch_count_active(const Dev &D, int *out, cudaStream_t st) {
   cudaMemsetAsync(out, 0, sizeof(int), st);
