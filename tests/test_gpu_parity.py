@@ -399,6 +399,26 @@ def test_marginalization_parity(solver, opts, cfg, flag):
             assert np.abs(w2.pose - w3.pose).max() < STEP_TOL, np.abs(w2.pose - w3.pose).max()
 
 
+@pytest.mark.parametrize("cfg,flag", [("tiny", 0), ("tiny", 1), ("C1", 0), ("C2", 0)])
+def test_marginalization_against_exact_rule(solver, opts, cfg, flag):
+    """GPU A', b' at the fixture's solved state against the reference's rule evaluated with mpmath at 40 digits
+    (tests/golden/marg_*.npz): the device result (cyclic Jacobi eigensolver) must be as close to the exact value as the
+    CPU oracle (Householder + QL, like Eigen) is - within a factor 4 of the oracle's own distance, which the explicit
+    eigen-inverse of Amm puts at 1e-5 .. 2e-4 of max|A'| for MARGIN_OLD (tests/test_oracle.py explains why), and 1e-12 for
+    the prior-only case."""
+    from tests.test_oracle import _marg_fixture
+    w, z = _marg_fixture(cfg, flag)
+    solver.upload([w], opts)
+    g = solver.marginalize(0, flag)
+    sA, sb = np.abs(z["A_exact"]).max(), max(1.0, np.abs(z["b_exact"]).max())
+    As = np.tril(g["A"]) + np.tril(g["A"], -1).T
+    eg, eo = np.abs(As - z["A_exact"]).max() / sA, np.abs(z["A_oracle"] - z["A_exact"]).max() / sA
+    bg, bo = np.abs(g["b"] - z["b_exact"]).max() / sb, np.abs(z["b_oracle"] - z["b_exact"]).max() / sb
+    print("marg %s flag %d: GPU vs exact A %.2e b %.2e | oracle vs exact A %.2e b %.2e" % (cfg, flag, eg, bg, eo, bo))
+    assert eg <= max(4 * eo, 1e-9), (eg, eo)
+    assert bg <= max(4 * bo, 1e-9), (bg, bo)
+
+
 def test_preintegration_on_device(solver):
     """IntegrationBase mid-point preintegration (integration_base.h:30-158) for many intervals in one launch,
     against the oracle's restatement and the independent numpy one of the generator"""
