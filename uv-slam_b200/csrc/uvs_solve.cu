@@ -331,21 +331,19 @@ __device__ bool blocked_chol_solve(double *A, const CholLayout &Lo, int nthr, un
 // but 35..50 KB of shared memory per window instead of 112 KB (four windows per SM instead of two) and ~2.3x fewer
 // FLOPs.  L_w (nd x 9 per block) goes to a global scratch for the back-substitution; everything else stays on chip.
 constexpr int CH_LWG = 720;      // doubles of global scratch per chain block (L_w, nd x 9)
+constexpr int LLS = 190;         // shared memory per chain block: L_c 9 x 10 (reciprocal diagonal) | L_x 9 x 10 | z_f 10
+constexpr int CH_ROWS = 96;      // row threads (warps 1..3): one per row of the dense part, nd <= 96
 
-struct ChainLayout { int o_C[2], o_W[2], o_X[2], o_bb, o_LL, o_z, o_LwF, o_t, total; };
+struct ChainLayout { int o_LL, o_z, o_t, o_LwF, o_sc, total; };
 __host__ __device__ __forceinline__ ChainLayout chain_layout(int nd, int F) {
   const CholLayout Lo = chol_layout(nd);
   ChainLayout c;
   int o = (Lo.total + 1) & ~1;
-  c.o_C[0] = o; o += 82; c.o_C[1] = o; o += 82;
-  const int wsz = (9 * nd + 1) & ~1;          // a W buffer: nd x 9
-  c.o_W[0] = o; o += wsz; c.o_W[1] = o; o += wsz;
-  c.o_X[0] = o; o += 82; c.o_X[1] = o; o += 82;
-  c.o_bb = o; o += 9 * F + (F & 1);          // rhs of every chain block
-  c.o_LL = o; o += 164 * F;                   // per block: L_c (81, lower, reciprocal diagonal) | L_x (81) | 2 pad
+  c.o_LL = o; o += LLS * F;                   // per block: C_f -> L_c | X_f -> L_x | b_f -> z_f, factored in place
   c.o_z = o; o += 10 * F;                     // z_f, later y_f
-  c.o_LwF = o; o += Lo.K * 96;                // L_w as tensor-core A fragments: [block row][k-step 0..2][32]
   c.o_t = o; o += 10 * F;
+  c.o_LwF = o; o += 2 * Lo.K * 96;            // L_w of a block as tensor-core A fragments [block row][k-step 0..2][32], two buffers
+  c.o_sc = o; o += (nd + 9 * F + 1) & ~1;     // Jacobi scale of every column
   c.total = o;
   return c;
 }
@@ -378,13 +376,43 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
-// Solves (D_s S D_s + D^2) y = -D_s g for one window; y (in the order of S) -> yout (global).  All threads of the CTA.
-__device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int &s_flag, const Params &P, double *Sg, int d, int F,
+// Named barriers of the chain pipeline (bar.arrive / bar.sync: waiting warps sleep in hardware, nothing polls).  A barrier id
+// serves every second block, and the producer of a phase only arrives once the consumers have left the previous phase of
+// the same id (the back / empty barriers), so at most one phase per id is ever open.
+constexpr int NB_READY = 1, NB_BACK = 3, NB_FULL = 5, NB_EMPTY = 7;   // + (block & 1)
+__device__ __forceinline__ void nbar_arrive(int id, int count) {   // st.shared ; bar.arrive | bar.sync ; ld.shared is the documented producer / consumer pattern
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+struct ChainLayoutV1 { int o_C[2], o_W[2], o_X[2], o_bb, o_LL, o_z, o_LwF, o_t, total; };
+__host__ __device__ __forceinline__ ChainLayoutV1 chain_layout_v1(int nd, int F) {
+  const CholLayout Lo = chol_layout(nd);
+  ChainLayoutV1 c;
+  int o = (Lo.total + 1) & ~1;
+  c.o_C[0] = o; o += 82; c.o_C[1] = o; o += 82;
+  const int wsz = (9 * nd + 1) & ~1;          // a W buffer: nd x 9
+  c.o_W[0] = o; o += wsz; c.o_W[1] = o; o += wsz;
+  c.o_X[0] = o; o += 82; c.o_X[1] = o; o += 82;
+  c.o_bb = o; o += 9 * F + (F & 1);          // rhs of every chain block
+  c.o_LL = o; o += 164 * F;                   // per block: L_c (81, lower, reciprocal diagonal) | L_x (81) | 2 pad
+  c.o_z = o; o += 10 * F;                     // z_f, later y_f
+  c.o_LwF = o; o += Lo.K * 96;                // L_w as tensor-core A fragments: [block row][k-step 0..2][32]
+  c.o_t = o; o += 10 * F;
+  c.total = o;
+  return c;
+}
+
+
+// Barrier-phased variant of the chain solve (every warp takes part in every phase, two CTA barriers per block): slower for a
+// single window than the pipeline below, faster when four windows share an SM - its waiting warps sleep at CTA barriers and
+// leave the load / store unit to the one warp that runs the pivot chain.  Used for large batches (launch_chol_chain).
+__device__ bool chain_solve_v1(double *smem, int nthr, unsigned short *s_pair, int &s_flag, const Params &P, double *Sg, int d, int F,
                             const double *scale, const double *colsq, const double *gS, double radius, double *yout, double *lwg) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
   const int nd = d - 9 * F;
   const CholLayout Lo = chol_layout(nd);
-  const ChainLayout Ch = chain_layout(nd, F);
+  const ChainLayoutV1 Ch = chain_layout_v1(nd, F);
   const int K = Lo.K;
   double *A = smem, *Dg = smem + Lo.dbase, *bz = smem + Lo.vbase, *invd_all = bz + K * NB;
   double *Cb[2] = {smem + Ch.o_C[0], smem + Ch.o_C[1]}, *Wb[2] = {smem + Ch.o_W[0], smem + Ch.o_W[1]};
@@ -439,16 +467,6 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     }
   };
 
-#ifdef UVS_CHOL_TIMING
-  long long tc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tq0 = clock64(), tq1, tp0, tp1;
-#define CH_P0() do { tp0 = clock64(); } while (0)
-#define CH_P(i) do { tp1 = clock64(); tc[i] += tp1 - tp0; tp0 = tp1; } while (0)
-#define CH_T(i) do { tq1 = clock64(); tc[i] += tq1 - tq0; tq0 = tq1; } while (0)
-#else
-#define CH_T(i) do { } while (0)
-#define CH_P0() do { } while (0)
-#define CH_P(i) do { } while (0)
-#endif
   for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
   // ---- load: dense part (fragment slots), first chain block, right-hand sides
   for (int qj = warp; qj < nd; qj += nw) {
@@ -470,8 +488,6 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   __syncthreads();
   for (int q = tid; q < nd; q += nthr) *slot(q, q) += lm(sidx(q));
   __syncthreads();
-
-  CH_T(0);
   // dense part -= L_w L_w^T on the tensor cores (three k-steps of four columns; columns 9..11 are zero), 8x8 blocks
   // first, first + step, ... of the lower triangle for this warp.  The update of block f + 1 runs on warps 1.. while
   // warp 0 factors block f (it only touches the dense part and the fragments written before the last barrier).
@@ -488,9 +504,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   for (int f = F - 1; f >= 0 && !s_flag; f--) {
     const int cur = f & 1, nxt = cur ^ 1;
     double *C = Cb[cur], *W = Wb[cur], *Lc = LL + 164 * f, *Lx = Lc + 81, *z = zb + 10 * f;
-    CH_P0();
     if (f > 0) load_block(f - 1, nxt);   // the next block lands while warp 0 factors this one
-    CH_P(8);
     if (warp == 0) {
       // Cholesky of the 9x9 block in registers, lane r < 9 owns row r (same pivot chain as the 8x8 blocks).  The
       // right-hand side b_f (lane 9) and the rows of the coupling block X_f (lanes 10..18) ride along as extra rows of
@@ -524,17 +538,13 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
         for (int c = 0; c < 9; c++) dst[c] = lane < 9 ? (c < r ? a[c] : (c == r ? myinv : 0.0)) : a[c];
       }
       if (lane == 0 && bad) s_flag = 1;
-      CH_P(9);
     }
     else {
       if (f < F - 1) dense_update(warp - 1, nw - 1);
       if (f > 0) { cp_async_wait(); scale_block(f - 1, nxt); }
     }
     __syncthreads();
-    CH_P(13);
-    CH_T(1);
     if (s_flag) break;
-    CH_T(2);
     // L_w = W L_c^-T row by row (forward substitution); the same thread updates its row of the next block's W and the dense right-hand side
     for (int q = tid; q < nd; q += nthr) {
       double lw[9];
@@ -581,16 +591,13 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       }
     }
     __syncthreads();
-    CH_T(3);
   }
   if (s_flag) return false;
   dense_update(warp, nw);   // the update of block 0 has no factorisation to hide behind: all warps
   __syncthreads();
-  CH_T(4);
 
   // ---- dense part
   if (!blocked_chol_solve(A, Lo, nthr, s_pair, s_flag)) return false;
-  CH_T(5);
 
   // ---- back-substitution of the chain: t_f = z_f - L_w^T y_D for all blocks at once, then y_f = L_c^-T (t_f - L_x^T y_f-1)
   for (int base = 0; base < 9 * F; base += nthr / 2) {   // two threads per entry, each half of the dot product
@@ -634,14 +641,320 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   for (int q = tid; q < nd; q += nthr) yout[sidx(q)] = bz[q];
   for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9; yout[cb(f) + e - 9 * f] = zb[10 * f + e - 9 * f]; }
   __syncthreads();
-  CH_T(6);
+  return true;
+}
+
+
+// Solves (D_s S D_s + D^2) y = -D_s g for one window; y (in the order of S) -> yout (global).  All 256 threads of the CTA.
+//
+// The chain elimination is a three-stage pipeline of specialised warps that meet at named barriers only (no CTA barrier inside
+// the loop over the blocks):
+//   warp 0       factors block f: C_f minus the rank-9 term of block f+1, with b_f and the rows of X_f riding through the
+//                9-pivot loop as extra rows (-> z_f, L_x); nothing it needs comes from the other warps, so it runs ahead
+//   warps 1..3   one thread per row q of the dense part: L_w[q] = W_f[q] L_c^-T (W read straight from S, one block ahead),
+//                W_f-1[q] -= L_w[q] L_x^T and the dense right-hand side, all in registers; L_w goes to the fragment buffer
+//                of the block (two buffers) and to the global scratch of the back-substitution
+//   warps 4..7   dense part -= L_w L_w^T on the FP64 tensor cores, as soon as a block's fragments are complete
+__device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int &s_flag, const Params &P, double *Sg, int d, int F,
+                            const double *scale, const double *colsq, const double *gS, double radius, double *yout, double *lwg) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+  const int nd = d - 9 * F;
+  const CholLayout Lo = chol_layout(nd);
+  const ChainLayout Ch = chain_layout(nd, F);
+  const int K = Lo.K;
+  double *A = smem, *Dg = smem + Lo.dbase, *bz = smem + Lo.vbase, *invd_all = bz + K * NB;
+  double *LL = smem + Ch.o_LL, *zb = smem + Ch.o_z, *tb = smem + Ch.o_t, *LwF = smem + Ch.o_LwF, *sc = smem + Ch.o_sc;
+  auto sidx = [&](int q) { return q < 6 * F ? 15 * (q / 6) + q % 6 : 15 * F + (q - 6 * F); };   // dense index -> index in S
+  auto cb = [&](int f) { return 15 * f + 6; };                                                    // first column of B_f in S
+  auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
+  auto slot = [&](int i, int j) -> double * {   // element (i, j), j <= i, of the dense part (dense indices)
+    const int I = i >> 3, r = i & 7;
+    return (j >> 3) == I ? Dg + 36 * I + r * (r + 1) / 2 + (j & 7) : A + 32 * I * (I - 1) + (j >> 2) * 4 * rows_of(I) + 4 * r + (j & 3);
+  };
+  auto lm = [&](int s) { const double v = sc[s], h = v * v * colsq[s]; return clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; };
+  // entry e of the chain blocks' inputs: C_f (lower, 45) and, for f > 0, X_f (rows B_f-1, columns B_f, 81) -> slot in LL, the
+  // two S indices (s1 <= s2: S is stored as its upper triangle)
+  auto chain_entry = [&](int e, double *&dst, int &s1, int &s2) -> bool {
+    const int f = e / 126, k = e - 126 * f;
+    double *blk = LL + LLS * f;
+    if (k < 45) { int r, c; unrank_lower(k, r, c); dst = blk + 10 * r + c; s1 = cb(f) + c; s2 = cb(f) + r; return true; }
+    if (f == 0) return false;
+    const int r = (k - 45) / 9, c = (k - 45) - 9 * r;
+    dst = blk + 90 + 10 * r + c; s1 = cb(f - 1) + r; s2 = cb(f) + c;
+    return true;
+  };
+#ifdef UVS_CHOL_TIMING
+  long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq0 = clock64(), tq1;
+#define CH_T(i) do { tq1 = clock64(); tc[i] += tq1 - tq0; tq0 = tq1; } while (0)
+  long long rt[6] = {0, 0, 0, 0, 0, 0}, r0 = 0;
+#define CH_R0() do { r0 = clock64(); } while (0)
+#define CH_R(i) do { const long long r1 = clock64(); rt[i] += r1 - r0; r0 = r1; } while (0)
+#else
+#define CH_R0() do { } while (0)
+#define CH_R(i) do { } while (0)
+#define CH_T(i) do { } while (0)
+#endif
+
+  // ---- load: everything the solve reads from S goes to shared memory (or, for W, to registers later) in one round trip
+  for (int t = tid; t < K * (K + 1) / 2; t += nthr) { int I, J; unrank_lower(t, I, J); s_pair[t] = (unsigned short)(I << 8 | J); }
+  for (int qj = warp; qj < nd; qj += nw) {
+    const int sj = sidx(qj);
+    for (int qi = qj + lane; qi < nd; qi += 32) cp_async8(slot(qi, qj), Sg + (size_t)sj * d + sidx(qi));
+  }
+  for (int e = tid; e < 126 * F; e += nthr) {
+    double *dst; int s1, s2;
+    if (chain_entry(e, dst, s1, s2)) cp_async8(dst, Sg + (size_t)s1 * d + s2);
+  }
+  for (int c = tid; c < d; c += nthr) sc[c] = scale[c];
+  for (int e = tid; e < 2 * K * 96; e += nthr) LwF[e] = 0.0;
+  cp_async_wait();
+  __syncthreads();
+  // scaling, LM diagonal - and the copied entries of S are cleared: the system is consumed here, so the next
+  // linearisation finds it zeroed without a clearing pass of its own (k_step keeps that pass for the other solvers)
+  for (int qj = warp; qj < nd; qj += nw) {
+    const int sjj = sidx(qj);
+    const double sj = sc[sjj];
+    for (int qi = qj + lane; qi < nd; qi += 32) {
+      double *a = slot(qi, qj);
+      double v = sc[sidx(qi)] * sj * *a;
+      if (qi == qj) v += lm(sjj);
+      *a = v;
+      Sg[(size_t)sjj * d + sidx(qi)] = 0.0;
+    }
+  }
+  for (int e = tid; e < 126 * F; e += nthr) {
+    double *dst; int s1, s2;
+    if (chain_entry(e, dst, s1, s2)) {
+      double v = *dst * sc[s1] * sc[s2];
+      if (s1 == s2) v += lm(s1);
+      *dst = v;
+      Sg[(size_t)s1 * d + s2] = 0.0;
+    }
+  }
+  for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9, c = e - 9 * f, s = cb(f) + c; LL[LLS * f + 180 + c] = -sc[s] * gS[s]; }
+  for (int c = tid; c < K * NB; c += nthr) { bz[c] = 0.0; invd_all[c] = 1.0; }
+  // row threads: row q of W_F-1 (scaled) and the dense right-hand side, in registers
+  const int q = tid - 32;
+  const bool rowthr = q >= 0 && q < CH_ROWS, rowact = rowthr && q < nd;
+  const int sq = rowact ? sidx(q) : 0;
+  const double ssq = rowact ? sc[sq] : 0.0;
+  double wn[9], bzq = 0.0;
+  // raw row q of W_fb out of S (upper triangle: the row of S when q's column comes first, else the column), cleared behind
+  auto load_w = [&](int fb, double (&dst)[9]) {
+    const int c0 = cb(fb);
+    if (sq <= c0) {
+      double *src = Sg + (size_t)sq * d + c0;
+#pragma unroll
+      for (int c = 0; c < 9; c++) { dst[c] = src[c]; src[c] = 0.0; }
+    } else {
+      double *src = Sg + (size_t)c0 * d + sq;
+#pragma unroll
+      for (int c = 0; c < 9; c++) { dst[c] = src[(size_t)c * d]; src[(size_t)c * d] = 0.0; }
+    }
+  };
+  if (rowact) {
+    load_w(F - 1, wn);
+#pragma unroll
+    for (int c = 0; c < 9; c++) wn[c] *= ssq * sc[cb(F - 1) + c];
+    bzq = -ssq * gS[sq];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 9; c++) wn[c] = 0.0;
+  }
+  __syncthreads();
+  CH_T(0);
+
+  // ---- chain elimination
+  if (warp == 0) {
+    for (int f = F - 1; f >= 0; f--) {
+      double *Lc = LL + LLS * f, *Lx = Lc + 90;
+      // one row per lane, no divergence: C row (entries c <= lane), b_f (lane 9), X_f row (lanes 10..18), or nothing
+      double *row = lane < 9 ? Lc + 10 * lane : (lane == 9 ? Lx + 90 : Lx + 10 * (lane - 10));
+      const int cnt = lane < 9 ? lane + 1 : ((lane == 9 || (lane < 19 && f > 0)) ? 9 : 0);
+      const int r = lane;
+      double a[9];
+      CH_R0();
+#pragma unroll
+      for (int c = 0; c < 9; c++) a[c] = c < cnt ? row[c] : 0.0;
+      if (f < F - 1) {
+        // what the elimination of block f + 1 left for this one: C_f -= L_x L_x^T, b_f -= L_x z (rows 0..8 of U: L_x, row 9: z)
+        const double *U = LL + LLS * (f + 1) + 90;
+        const double *ur = U + 10 * min(lane, 9);
+        double u[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) u[k] = lane <= 9 ? ur[k] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+          const double *lx = U + 10 * c;
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 9; k++) s += u[k] * lx[k];
+          a[c] -= c < cnt ? s : 0.0;
+        }
+      }
+      CH_R(0);
+      // Cholesky of the 9x9 block in registers, lane r < 9 owns row r.  The right-hand side and the rows of the coupling block
+      // ride along as extra rows: what the pivot loop leaves in them is z_f = L_c^-1 b_f and L_x = X_f L_c^-T
+      int bad = 0;
+      double myinv = 1.0;
+#pragma unroll
+      for (int p = 0; p < 9; p++) {
+        const double piv = __shfl_sync(0xffffffffu, a[p], p);
+        if (!(piv > 0.0) || !isfinite(piv)) bad = 1;
+        const double inv = rsqrt(piv);
+        a[p] = r == p ? piv * inv : a[p] * inv;
+        if (r == p) myinv = inv;
+#pragma unroll
+        for (int qq = p + 1; qq < 9; qq++) {
+          const double lq = __shfl_sync(0xffffffffu, a[p], qq);
+          a[qq] -= a[p] * lq;
+        }
+      }
+      CH_R(1);
+      if (lane < 19) {   // L_c with the reciprocal diagonal | z_f | L_x, in place
+#pragma unroll
+        for (int c = 0; c < 9; c++) row[c] = lane < 9 ? (c < r ? a[c] : (c == r ? myinv : 0.0)) : a[c];
+      }
+      if (lane == 9) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) zb[10 * f + c] = a[c];
+      }
+      if (lane == 0 && bad) s_flag = 1;
+      CH_R(2);
+      if (f <= F - 3) nbar_sync(NB_BACK + (f & 1), 32 + CH_ROWS);   // the row threads have left block f + 2 (same barrier id)
+      nbar_arrive(NB_READY + (f & 1), 32 + CH_ROWS);
+      CH_R(3);
+    }
+#ifdef UVS_CHOL_TIMING
+    if (lane == 0 && blockIdx.x == 0) printf("  warp 0: update %lld pivots %lld stores %lld barriers %lld\n", rt[0], rt[1], rt[2], rt[3]);
+#endif
+  } else if (rowthr) {
+    for (int f = F - 1; f >= 0; f--) {
+      const double *Lc = LL + LLS * f, *Lx = Lc + 90, *z = Lx + 90;
+      double nx[9];
+      CH_R0();
+      if (f > 0 && rowact) load_w(f - 1, nx);   // in flight while this block is processed
+      CH_R(0);
+      nbar_sync(NB_READY + (f & 1), 32 + CH_ROWS);
+      CH_R(1);
+      // L_w[q] = W_f[q] L_c^-T by forward substitution, in place
+#pragma unroll
+      for (int c = 0; c < 9; c++) {
+        double v = wn[c];
+#pragma unroll
+        for (int k = 0; k < 9; k++) if (k < c) v -= wn[k] * Lc[10 * c + k];
+        wn[c] = v * Lc[11 * c];
+      }
+      CH_R(2);
+      if (f <= F - 3) nbar_sync(NB_EMPTY + (f & 1), CH_ROWS + 128);   // the fragment buffer of this block was last used two blocks ago
+      CH_R(3);
+      if (rowact) {
+        double *g = lwg + (size_t)f * CH_LWG + 9 * q;
+        double *fb = LwF + (f & 1) * K * 96 + (q >> 3) * 96 + 4 * (q & 7);
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+          g[c] = wn[c];
+          fb[(c >> 2) * 32 + (c & 3)] = wn[c];
+          bzq -= wn[c] * z[c];
+        }
+      }
+      nbar_arrive(NB_FULL + (f & 1), CH_ROWS + 128);
+      CH_R(4);
+      if (f > 0) {
+        const int c1 = cb(f - 1);
+#pragma unroll
+        for (int c2 = 0; c2 < 9; c2++) {
+          double v = rowact ? nx[c2] * ssq * sc[c1 + c2] : 0.0;
+#pragma unroll
+          for (int k = 0; k < 9; k++) v -= wn[k] * Lx[10 * c2 + k];
+          nx[c2] = v;
+        }
+#pragma unroll
+        for (int c = 0; c < 9; c++) wn[c] = nx[c];
+      }
+      if (f >= 2) nbar_arrive(NB_BACK + (f & 1), 32 + CH_ROWS);
+      CH_R(5);
+    }
+#ifdef UVS_CHOL_TIMING
+    if (q == 0 && blockIdx.x == 0) printf("  rows: issue loads %lld wait ready %lld forward %lld wait empty %lld write+arrive %lld next-W %lld\n", rt[0], rt[1], rt[2], rt[3], rt[4], rt[5]);
+#endif
+    if (rowact) bz[q] = bzq;
+  } else {
+    // dense part -= L_w L_w^T (three k-steps of four columns; columns 9..11 are zero), 8x8 blocks u, u + 4, ... of the lower triangle
+    const int u = warp - 4;
+    for (int f = F - 1; f >= 0; f--) {
+      const double *buf = LwF + (f & 1) * K * 96;
+      CH_R0();
+      nbar_sync(NB_FULL + (f & 1), CH_ROWS + 128);
+      CH_R(0);
+      for (int blk = u; blk < K * (K + 1) / 2; blk += 4) {
+        const int pr = s_pair[blk], I = pr >> 8, J = pr & 255;
+        double a[3], b[3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) { a[s] = buf[(I * 3 + s) * 32 + lane]; b[s] = buf[(J * 3 + s) * 32 + lane]; }
+        frag_block_sub(A, Dg, K, Lo.vr, I, J, lane, a, b, 3);
+      }
+      if (f >= 2) nbar_arrive(NB_EMPTY + (f & 1), CH_ROWS + 128);
+      CH_R(1);
+    }
+#ifdef UVS_CHOL_TIMING
+    if (tid == 128 && blockIdx.x == 0) printf("  update: wait full %lld tiles %lld\n", rt[0], rt[1]);
+#endif
+  }
+  __syncthreads();
+  CH_T(1);
+  if (s_flag) return false;
+
+  // ---- dense part
+  if (!blocked_chol_solve(A, Lo, nthr, s_pair, s_flag)) return false;
+  CH_T(2);
+
+  // ---- back-substitution of the chain: t_f = z_f - L_w^T y_D for all blocks at once, then y_f = L_c^-T (t_f - L_x^T y_f-1)
+  for (int base = 0; base < 9 * F; base += nthr / 2) {   // two threads per entry, each half of the dot product
+    const int e = base + (tid >> 1), half = tid & 1;
+    const int f = e / 9, c = e - 9 * f;
+    double t = 0.0;
+    if (e < 9 * F) {
+      const double *g = lwg + (size_t)f * CH_LWG + c;
+      const int qm = (nd + 1) >> 1;
+      for (int qq = half ? qm : 0; qq < (half ? nd : qm); qq++) t -= g[9 * qq] * bz[qq];
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    if (e < 9 * F && half == 0) tb[10 * f + c] = zb[10 * f + c] + t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int r = lane < 9 ? lane : 8;
+    for (int f = 0; f < F; f++) {
+      const double *Lc = LL + LLS * f, *Lx = Lc + 90;
+      double u = tb[10 * f + r];
+      if (f > 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) u -= Lx[10 * k + r] * zb[10 * (f - 1) + k];
+      }
+      // y = L_c^-T u by backward substitution, lane r owns y_r: column r of L_c in registers
+      double lcol[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) lcol[k] = Lc[10 * k + r];
+      double y = 0.0;
+#pragma unroll
+      for (int k = 8; k >= 0; k--) {
+        const double yk = __shfl_sync(0xffffffffu, u * lcol[k], k);   // lane k: u_k / L_kk
+        if (r == k) y = yk;
+        if (r < k) u -= lcol[k] * yk;
+      }
+      if (lane < 9) zb[10 * f + lane] = y;   // y_f replaces z_f
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int qq = tid; qq < nd; qq += nthr) yout[sidx(qq)] = bz[qq];
+  for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9; yout[cb(f) + e - 9 * f] = zb[10 * f + e - 9 * f]; }
+  __syncthreads();
+  CH_T(3);
 #ifdef UVS_CHOL_TIMING
   if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("chain nd=%d F=%d cycles: load %lld | per-block: factor+inverse+next-load %lld  Lx %lld  Lw+updates %lld  dense update %lld | dense solve %lld  chain back-sub %lld\n",
-           nd, F, tc[0], tc[1], tc[2], tc[3], tc[4], tc[5], tc[6]);
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("  phase 1 of warp 0: issue next-block copies %lld  9x9 Cholesky %lld  inverse + z %lld  copy wait %lld  scale %lld  barrier %lld\n",
-           tc[8], tc[9], tc[10], tc[11], tc[12], tc[13]);
+    printf("chain nd=%d F=%d cycles: load %lld | chain pipeline %lld | dense solve %lld | chain back-sub %lld\n", nd, F, tc[0], tc[1], tc[2], tc[3]);
 #endif
   return true;
 }
@@ -653,13 +966,14 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
 #define CHOL_TS(i) do { } while (0)
 #endif
 
-// kMode: 0 = in place in global memory (large windows), 1 = dense blocked in shared memory, 2 = chain mode
+// kMode: 0 = in place in global memory (large windows), 1 = dense blocked in shared memory, 2 = chain mode (barrier-phased),
+//        3 = chain mode (warp-specialised pipeline)
 template <int kMode>
 __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, bool mc_identity) {
   __shared__ double red[CT / 32];   // CT = largest block size
   __shared__ int s_flag;
   constexpr bool kPacked = kMode == 1;
-  __shared__ unsigned short s_pair[kMode == 1 ? 528 : (kMode == 2 ? 64 : 1)];   // (I, J) of the t-th block of a lower triangle (K <= 32; chain mode K <= 10)
+  __shared__ unsigned short s_pair[kMode == 1 ? 528 : (kMode >= 2 ? 64 : 1)];   // (I, J) of the t-th block of a lower triangle (K <= 32; chain mode K <= 10)
   const int nthr = blockDim.x;   // 256 when two windows fit one SM, else 512
 #ifdef UVS_CHOL_TIMING
   long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -709,11 +1023,12 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
   double *vec;   // solution vector y (d doubles)
   const double radius = ctl.radius;
   CHOL_TS(1);
-  if (kMode == 2) {
+  if (kMode >= 2) {
     vec = vec_y;   // the solution is written straight to its global home
     CHOL_TS(2);
-    const bool ok = chain_solve(smem, nthr, s_pair, s_flag, P, Sg, d, F, scale, colsq, gS, radius, vec_y,
-                                D.chain_lw + (size_t)w * D.chain_lw_stride);
+    double *lwg = D.chain_lw + (size_t)w * D.chain_lw_stride;
+    const bool ok = kMode == 3 ? chain_solve(smem, nthr, s_pair, s_flag, P, Sg, d, F, scale, colsq, gS, radius, vec_y, lwg)
+                               : chain_solve_v1(smem, nthr, s_pair, s_flag, P, Sg, d, F, scale, colsq, gS, radius, vec_y, lwg);
     if (!ok) {
       if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
       zero_window_system(D, w);   // the failed solve consumed (and cleared) only part of the system
@@ -951,6 +1266,7 @@ __global__ void __launch_bounds__(CT) k_chol(Dev D, Params P, int packed_limit, 
 }
 
 // chain mode: 256 threads, <= 64 registers so that four windows share an SM
+template <int kMode>
 __global__ void __launch_bounds__(256, 4) k_chol_chain(Dev D, Params P, int mc_identity) {
   extern __shared__ double smem[];
   const int w = blockIdx.x;
@@ -960,7 +1276,7 @@ __global__ void __launch_bounds__(256, 4) k_chol_chain(Dev D, Params P, int mc_i
     zero_window_system(D, w);   // nobody consumes this system: clear it for the rebuild (k_step leaves the matrix to this kernel)
     return;
   }
-  chol_window<2>(D, P, w, smem, mc_identity != 0);
+  chol_window<kMode>(D, P, w, smem, mc_identity != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1070,19 +1386,30 @@ int chol_packed_limit(size_t max_smem) {
 int launch_solve_init(const Dev &D, const Params &P, cudaStream_t st) { k_solve_init<<<D.B, CT, 0, st>>>(D, P); return 1; }
 
 size_t chol_chain_smem(int max_frames, bool any_ex) {
-  return (size_t)chain_layout(6 * max_frames + (any_ex ? 6 : 0), max_frames).total * sizeof(double);
+  const int nd = 6 * max_frames + (any_ex ? 6 : 0);
+  return (size_t)std::max(chain_layout(nd, max_frames).total, chain_layout_v1(nd, max_frames).total) * sizeof(double);
 }
 int chol_chain_lw_doubles(int max_frames) { return max_frames * CH_LWG; }
 
+// Two variants of the chain solve.  Measured (us per LM iteration, B windows; gpurun_out/c*_scan): pipeline 92 / 95 / 107 /
+// 178 / 392 against barrier-phased 107 / 109 / 108 / 119 / 161 at B = 1 / 16 / 64 / 148 / 592.  The pipeline has the shorter
+// critical path, but its row threads read W and write L_w / the cleared entries of S with plain 8-byte global accesses
+// between named barriers (a barrier waits for the warp's outstanding global accesses), so it degrades as soon as many
+// windows share the memory system - even on different SMs; the barrier-phased variant prefetches with cp.async.
 int launch_chol_chain(const Dev &D, const Params &P, int max_frames, bool any_ex, bool mc_identity, cudaStream_t st) {
-  const size_t smem = std::max(chol_chain_smem(max_frames, any_ex), (size_t)MAX_PRIOR_COLS * sizeof(int));
+  static const size_t pad = std::getenv("UVS_CHAIN_PAD_SMEM") ? (size_t)std::atoi(std::getenv("UVS_CHAIN_PAD_SMEM")) : 0;   // developer knob: fewer windows per SM
+  static const int pipe_max = std::getenv("UVS_CHAIN_PIPE_MAX") ? std::atoi(std::getenv("UVS_CHAIN_PIPE_MAX")) : 32;    // largest batch that takes the pipeline
+  const size_t smem = std::max(chol_chain_smem(max_frames, any_ex), (size_t)MAX_PRIOR_COLS * sizeof(int)) + pad;
   static size_t raised = 0;
   if (smem > raised) {
-    cudaFuncSetAttribute(k_chol_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_chol_chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_chol_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_chol_chain<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_chol_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_chol_chain<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     raised = smem;
   }
-  k_chol_chain<<<D.B, 256, smem, st>>>(D, P, mc_identity ? 1 : 0);
+  if (D.B <= pipe_max) k_chol_chain<3><<<D.B, 256, smem, st>>>(D, P, mc_identity ? 1 : 0);
+  else k_chol_chain<2><<<D.B, 256, smem, st>>>(D, P, mc_identity ? 1 : 0);
   return 1;
 }
 
