@@ -329,6 +329,68 @@ int uvs_triangulate_lines(UvsHandle *h, int32_t n_frames, const double *Rs, cons
                           int32_t n_lines, const int32_t *frame_first, const int32_t *frame_last, const double *sp_first,
                           const double *ep_first, const double *sp_last, const double *ep_last, double *ortho_out);
 
+/* ---- Device-resident sliding window --------------------------------------------------------------
+ * The reference rebuilds its Ceres problem from FeatureManager every frame (estimator.cpp:823-934) although only one frame
+ * of observations, one IMU interval and the state are new.  With a resident window the observation tracks, the IMU records
+ * and the marginalization prior stay on the device; per frame the caller sends the new frame (uvs_window_push_frame), the
+ * packed state (the para_* arrays of vector2double, through uvs_window_upload) and nothing else:
+ *
+ *   uvs_window_create(h, WINDOW_SIZE, LINE_WINDOW, max tracks)           once
+ *   per frame:  uvs_window_push_frame                                    FeatureManager::addFeatureCheckParallax (bookkeeping part)
+ *               uvs_window_counts -> sizes of para_Feature / para_Ortho_plucker
+ *               uvs_window_upload(state)                                 problem assembly of estimator.cpp:823-934, on the device
+ *               uvs_solve, uvs_download_state, [double2vector / vector2double], uvs_upload_state
+ *               uvs_window_marginalize(flag)                             estimator.cpp:1003-1228, prior kept on the device
+ *               uvs_window_slide(flag)                                   Estimator::slideWindow, estimator.cpp:1235-1359
+ *               uvs_window_remove_tracks                                 FeatureManager::removeFailures / removeOutlier / removeLineFailures
+ * After uvs_window_upload the handle holds the window exactly as after uvs_upload_windows of the same window packed on the
+ * host (same factor order: list order of the tracks, eligibility filters of estimator.cpp:826 and :873, running feature
+ * indices), so every other entry point works on it.  One window per handle; estimate_td is not supported in this mode. */
+typedef struct UvsImuRecord {      /* constants of one IntegrationBase (integration_base.h:188-207) */
+  const double *delta_p;     /* [3] */
+  const double *delta_q;     /* [4] x,y,z,w */
+  const double *delta_v;     /* [3] */
+  const double *sum_dt;      /* [1] */
+  const double *lin_ba;      /* [3] */
+  const double *lin_bg;      /* [3] */
+  const double *jacobian;    /* [225] row-major */
+  const double *covariance;  /* [225] row-major */
+} UvsImuRecord;
+
+typedef struct UvsFrameInput {     /* what one image frame adds (feature_manager.cpp:73-133; the tracker's ids) */
+  const UvsImuRecord *imu;   /* preintegration from the previous frame to this one; NULL for the first frame only */
+  int32_t n_points;
+  int32_t n_lines;
+  const int32_t *point_id;   /* [n_points] feature_id */
+  const double *point_xyz;   /* [n_points][3] FeaturePerFrame::point */
+  const int32_t *line_id;    /* [n_lines] */
+  const double *line_sp;     /* [n_lines][2] LineFeaturePerFrame::start_point */
+  const double *line_ep;     /* [n_lines][2] end_point */
+  const double *line_vp;     /* [n_lines][3] vp; a VP factor exists where vp[2] == 1 (estimator.cpp:920) */
+} UvsFrameInput;
+
+int uvs_window_create(UvsHandle *h, int32_t window_size, int32_t line_window, int32_t max_points, int32_t max_lines);
+int uvs_window_push_frame(UvsHandle *h, const UvsFrameInput *frame);
+/* counts[8] = n_frames, eligible points, eligible lines, point factors, line factors, VP factors, IMU factors, prior_n */
+int uvs_window_counts(UvsHandle *h, int32_t counts[8]);
+/* `state`: n_frames / n_points / n_lines as uvs_window_counts reports them, the state arrays, line_ric / line_tic,
+ * estimate_extrinsic; every factor / IMU / prior field is ignored (they come from the device-resident store). */
+int uvs_window_upload(UvsHandle *h, const UvsWindow *state, const UvsOptions *opts);
+/* uvs_marginalize of the resident window; the result also becomes the resident prior of the next uvs_window_upload
+ * (block ids already shifted).  `out` may be NULL. */
+int uvs_window_marginalize(UvsHandle *h, int32_t flag, UvsPrior *out);
+/* UVS_MARGIN_OLD: frame 0 leaves (removeBackShiftDepth / removeBack / removeLineBack; the re-anchored depth is caller
+ * state).  UVS_MARGIN_SECOND_NEW: the second newest frame leaves (removeFront / removeLineFront); `merged_imu` = the
+ * preintegration over the last two intervals (estimator.cpp:1301-1312), required when the window has >= 2 IMU factors. */
+int uvs_window_slide(UvsHandle *h, int32_t flag, const UvsImuRecord *merged_imu);
+int uvs_window_remove_tracks(UvsHandle *h, int32_t n_points, const int32_t *point_id, int32_t n_lines, const int32_t *line_id);
+
+/* Copy the factor arrays of an uploaded window back into the caller's arrays (w's counts must match; NULL pointers are
+ * skipped; IMU / prior arrays only when n_imu / prior_n match): the dump hook of the device-resident window, and its test. */
+int uvs_download_factors(UvsHandle *h, int32_t window_index, UvsWindow *w);
+/* host-to-device bytes copied by the upload paths of this handle since creation */
+int64_t uvs_h2d_bytes(const UvsHandle *h);
+
 /* Factor-parallel multi-GPU mode: this rank owns the landmarks with (index % nranks == rank);
  * IMU factors and the prior belong to rank 0.  `reduce` is called once per LM iteration with the
  * device buffer holding the rank's partial reduced camera system (count doubles) and must sum it

@@ -402,10 +402,8 @@ def test_marginalization_parity(solver, opts, cfg, flag):
 @pytest.mark.parametrize("cfg,flag", [("tiny", 0), ("tiny", 1), ("C1", 0), ("C2", 0)])
 def test_marginalization_against_exact_rule(solver, opts, cfg, flag):
     """GPU A', b' at the fixture's solved state against the reference's rule evaluated with mpmath at 40 digits
-    (tests/golden/marg_*.npz): the device result (cyclic Jacobi eigensolver) must be as close to the exact value as the
-    CPU oracle (Householder + QL, like Eigen) is - within a factor 4 of the oracle's own distance, which the explicit
-    eigen-inverse of Amm puts at 1e-5 .. 2e-4 of max|A'| for MARGIN_OLD (tests/test_oracle.py explains why), and 1e-12 for
-    the prior-only case."""
+    (tests/golden/marg_*.npz).  This settles the loosened MARGIN_OLD tolerance of test_marginalization_parity (2e-3 between
+    GPU and CPU oracle): the difference is the CPU restatement's, not the device's."""
     from tests.test_oracle import _marg_fixture
     w, z = _marg_fixture(cfg, flag)
     solver.upload([w], opts)
@@ -415,8 +413,11 @@ def test_marginalization_against_exact_rule(solver, opts, cfg, flag):
     eg, eo = np.abs(As - z["A_exact"]).max() / sA, np.abs(z["A_oracle"] - z["A_exact"]).max() / sA
     bg, bo = np.abs(g["b"] - z["b_exact"]).max() / sb, np.abs(z["b_oracle"] - z["b_exact"]).max() / sb
     print("marg %s flag %d: GPU vs exact A %.2e b %.2e | oracle vs exact A %.2e b %.2e" % (cfg, flag, eg, bg, eo, bo))
-    assert eg <= max(4 * eo, 1e-9), (eg, eo)
-    assert bg <= max(4 * bo, 1e-9), (bg, bo)
+    # measured on B200: the device's cyclic Jacobi rotations resolve the small eigenvalues of Amm to full relative accuracy -
+    # 3e-7 of max|A'| at worst against the exact rule, where the QL-based CPU restatement is at 2e-5 .. 2e-4.  So the GPU is
+    # held to the north_star's 1e-6 against the EXACT value, and never behind the CPU restatement
+    assert eg <= 1e-6 and bg <= 2e-6, (eg, bg)
+    assert eg <= max(4 * eo, 1e-9) and bg <= max(4 * bo, 1e-9), (eg, eo, bg, bo)
 
 
 def test_preintegration_on_device(solver):

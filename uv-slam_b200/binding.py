@@ -23,12 +23,33 @@ EXPORTS = (
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
     "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate", "uvs_batch_solve_pipelined",
     "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_set_graph_replay", "uvs_upload_state", "uvs_jacobian_sweep", "uvs_comm_unique_id", "uvs_comm_init_nccl", "uvs_collective_count",
+    "uvs_window_create", "uvs_window_push_frame", "uvs_window_counts", "uvs_window_upload", "uvs_window_marginalize", "uvs_window_slide",
+    "uvs_window_remove_tracks", "uvs_download_factors", "uvs_h2d_bytes",
 )
 
 N_STAGES = 10
 STAGE_NAMES = ("sweep_proj", "sweep_line", "sweep_vp", "sweep_imu", "sweep_prior", "build", "chol", "backsub",
                "resid_sweep", "step")
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+class UvsImuRecordStruct(C.Structure):
+    _fields_ = [(n, c_double_p) for n in ("delta_p", "delta_q", "delta_v", "sum_dt", "lin_ba", "lin_bg", "jacobian", "covariance")]
+
+
+class UvsFrameInputStruct(C.Structure):
+    _fields_ = [("imu", C.POINTER(UvsImuRecordStruct)), ("n_points", C.c_int32), ("n_lines", C.c_int32), ("point_id", c_int32_p),
+                ("point_xyz", c_double_p), ("line_id", c_int32_p), ("line_sp", c_double_p), ("line_ep", c_double_p), ("line_vp", c_double_p)]
+
+
+def _imu_record(rec):
+    """dict with the keys of tools/gen_window.preintegrate (+ lin_ba / lin_bg) -> (struct, keep-alive arrays)"""
+    keep = {k: np.ascontiguousarray(np.atleast_1d(rec[k]), dtype=np.float64) for k in
+            ("delta_p", "delta_q", "delta_v", "sum_dt", "lin_ba", "lin_bg", "jacobian", "covariance")}
+    st = UvsImuRecordStruct()
+    for k, a in keep.items():
+        setattr(st, k, a.ctypes.data_as(c_double_p))
+    return st, keep
 
 
 class UvsError(RuntimeError):
@@ -91,6 +112,16 @@ def load_library():
     lib.uvs_set_profiling.argtypes = [H, C.c_int32]
     lib.uvs_set_graph_replay.argtypes = [H, C.c_int32]
     lib.uvs_last_stage_ms.argtypes = [H, C.POINTER(C.c_float * N_STAGES), C.POINTER(C.c_int32)]
+    lib.uvs_window_create.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.uvs_window_push_frame.argtypes = [H, C.POINTER(UvsFrameInputStruct)]
+    lib.uvs_window_counts.argtypes = [H, C.POINTER(C.c_int32 * 8)]
+    lib.uvs_window_upload.argtypes = [H, C.POINTER(UvsWindowStruct), C.POINTER(UvsOptionsStruct)]
+    lib.uvs_window_marginalize.argtypes = [H, C.c_int32, C.POINTER(UvsPriorStruct)]
+    lib.uvs_window_slide.argtypes = [H, C.c_int32, C.POINTER(UvsImuRecordStruct)]
+    lib.uvs_window_remove_tracks.argtypes = [H, C.c_int32, c_int32_p, C.c_int32, c_int32_p]
+    lib.uvs_download_factors.argtypes = [H, C.c_int32, C.POINTER(UvsWindowStruct)]
+    lib.uvs_h2d_bytes.restype = C.c_int64
+    lib.uvs_h2d_bytes.argtypes = [H]
     _lib = lib
     return lib
 
@@ -218,6 +249,88 @@ class Solver:
             self._check(self.lib.uvs_batch_solve_pipelined(self.h, len(self.windows), self._arr, C.byref(self.opts), sums, int(groups)),
                         "uvs_batch_solve_pipelined")
         return sums
+
+    # -- device-resident sliding window (include/uvs.h, uvs_window_*) --------------------------------
+    def window_create(self, window_size=10, line_window=5, max_points=1024, max_lines=512):
+        self._check(self.lib.uvs_window_create(self.h, window_size, line_window, max_points, max_lines), "uvs_window_create")
+
+    def window_push_frame(self, point_id, point_xyz, line_id, line_sp, line_ep, line_vp, imu=None):
+        f64 = lambda a, sh: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(sh))
+        pid, lid = np.ascontiguousarray(point_id, dtype=np.int32), np.ascontiguousarray(line_id, dtype=np.int32)
+        xyz, sp, ep, vp = f64(point_xyz, (-1, 3)), f64(line_sp, (-1, 2)), f64(line_ep, (-1, 2)), f64(line_vp, (-1, 3))
+        fr = UvsFrameInputStruct()
+        keep = None
+        if imu is not None:
+            st, keep = _imu_record(imu)
+            fr.imu = C.pointer(st)
+        fr.n_points, fr.n_lines = len(pid), len(lid)
+        fr.point_id, fr.point_xyz = pid.ctypes.data_as(c_int32_p), xyz.ctypes.data_as(c_double_p)
+        fr.line_id, fr.line_sp, fr.line_ep, fr.line_vp = (lid.ctypes.data_as(c_int32_p), sp.ctypes.data_as(c_double_p),
+                                                          ep.ctypes.data_as(c_double_p), vp.ctypes.data_as(c_double_p))
+        self._check(self.lib.uvs_window_push_frame(self.h, C.byref(fr)), "uvs_window_push_frame")
+        del keep
+
+    def window_counts(self):
+        c = (C.c_int32 * 8)()
+        self._check(self.lib.uvs_window_counts(self.h, C.byref(c)), "uvs_window_counts")
+        return dict(zip(("n_frames", "n_points", "n_lines", "n_proj", "n_line_obs", "n_vp_obs", "n_imu", "prior_n"), list(c)))
+
+    def window_upload(self, state: Window, opts: UvsOptionsStruct | None = None):
+        """assemble the resident window on the device around the caller's state; `state` then plays the role of the uploaded
+        window for solve() / download() / upload_state()"""
+        self.windows = [state]
+        self.opts = opts if opts is not None else default_options()
+        self._arr = window_array(self.windows)
+        self._check(self.lib.uvs_window_upload(self.h, self._arr, C.byref(self.opts)), "uvs_window_upload")
+
+    def window_marginalize(self, flag=0):
+        cap_n, cap_b = 16 * 32 + 16, 2 * 32 + 8
+        J = np.zeros((cap_n, cap_n)); r = np.zeros(cap_n); A = np.zeros((cap_n, cap_n)); b = np.zeros(cap_n)
+        kind = np.zeros(cap_b, np.int32); bid = np.zeros(cap_b, np.int32); x0 = np.zeros(9 * cap_b)
+        p = UvsPriorStruct()
+        p.J, p.r, p.A, p.b, p.x0 = (a.ctypes.data_as(c_double_p) for a in (J, r, A, b, x0))
+        p.block_kind, p.block_id = kind.ctypes.data_as(c_int32_p), bid.ctypes.data_as(c_int32_p)
+        p.cap_n, p.cap_blocks = cap_n, cap_b
+        self._check(self.lib.uvs_window_marginalize(self.h, flag, C.byref(p)), "uvs_window_marginalize")
+        n, nb = p.n, p.n_blocks
+        if n == 0:
+            return None
+        kinds = kind[:nb].copy(); ids = bid[:nb].copy()
+        gs = np.array([7 if k in (0, 2) else (9 if k == 1 else 1) for k in kinds])
+        return dict(n=n, m=p.m, J=J.ravel()[:n * n].reshape(n, n).copy(), r=r[:n].copy(), A=A.ravel()[:n * n].reshape(n, n).copy(),
+                    b=b[:n].copy(), kinds=kinds, ids=ids, x0=x0[:gs.sum()].copy())
+
+    def window_slide(self, flag=0, merged_imu=None):
+        if merged_imu is None:
+            self._check(self.lib.uvs_window_slide(self.h, flag, None), "uvs_window_slide")
+        else:
+            st, keep = _imu_record(merged_imu)
+            self._check(self.lib.uvs_window_slide(self.h, flag, C.byref(st)), "uvs_window_slide")
+            del keep
+
+    def window_remove_tracks(self, point_ids=(), line_ids=()):
+        p, l = np.ascontiguousarray(point_ids, dtype=np.int32), np.ascontiguousarray(line_ids, dtype=np.int32)
+        self._check(self.lib.uvs_window_remove_tracks(self.h, len(p), p.ctypes.data_as(c_int32_p), len(l), l.ctypes.data_as(c_int32_p)),
+                    "uvs_window_remove_tracks")
+
+    def download_factors(self, counts, window_index=0) -> Window:
+        """the factor arrays of an uploaded window as the device holds them -> a Window sized by `counts` (window_counts() or
+        a host-packed Window's sizes); state arrays are zeros"""
+        g = lambda k: int(counts[k]) if isinstance(counts, dict) else int(getattr(counts, k))
+        F, npnt, nl, npj, nlo, nvo, nim, pn = (g(k) for k in ("n_frames", "n_points", "n_lines", "n_proj", "n_line_obs", "n_vp_obs", "n_imu", "prior_n"))
+        z, zi = (lambda *sh: np.zeros(sh)), (lambda n: np.zeros(n, np.int32))
+        w = Window(pose=z(F, 7), speed_bias=z(F, 9), ex_pose=z(7), inv_depth=z(npnt), ortho=z(nl, 4),
+                   proj_frame_i=zi(npj), proj_frame_j=zi(npj), proj_point=zi(npj), proj_pts_i=z(npj, 3), proj_pts_j=z(npj, 3),
+                   line_frame=zi(nlo), line_idx=zi(nlo), line_sp=z(nlo, 2), line_ep=z(nlo, 2), vp_frame=zi(nvo), vp_line=zi(nvo), vp_dir=z(nvo, 3),
+                   imu_frame_i=zi(nim), imu_delta_p=z(nim, 3), imu_delta_q=z(nim, 4), imu_delta_v=z(nim, 3), imu_sum_dt=z(nim),
+                   imu_lin_ba=z(nim, 3), imu_lin_bg=z(nim, 3), imu_jacobian=z(nim, 225), imu_covariance=z(nim, 225),
+                   prior_J=z(pn, pn), prior_r=z(pn))
+        arr = window_array([w])
+        self._check(self.lib.uvs_download_factors(self.h, window_index, arr), "uvs_download_factors")
+        return w
+
+    def h2d_bytes(self):
+        return int(self.lib.uvs_h2d_bytes(self.h))
 
     def marginalize(self, window_index=0, flag=0):
         w = self.windows[window_index]

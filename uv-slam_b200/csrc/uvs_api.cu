@@ -141,6 +141,7 @@ int uvs_destroy(UvsHandle *h) {
   for (UvsHandle *c : h->children) uvs_destroy(c);
   h->children.clear();
   cudaSetDevice(h->device);
+  uvs::resident_destroy(h);
   cudaStreamSynchronize(h->stream);
   h->dev.release(); h->stage.release(); h->scratch.release(); h->hscratch.release();
   if (h->d_active) cudaFree(h->d_active);
@@ -158,7 +159,7 @@ int uvs_destroy(UvsHandle *h) {
 
 const char *uvs_last_error(const UvsHandle *h) { return h ? h->err.c_str() : "null handle"; }
 
-static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts);
+static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts, const ResidentHook *hook = nullptr);
 static int upload_finish(UvsHandle *h);
 
 int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts) {
@@ -166,8 +167,10 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
   return rc ? rc : upload_finish(h);
 }
 
-// host packing + every device operation of an upload, enqueued on the handle's stream without waiting
-static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts) {
+// host packing + every device operation of an upload, enqueued on the handle's stream without waiting.  With a resident
+// hook (uvs_window.cu) the factor / IMU / prior-matrix sections are not copied from the caller (their pointers are null)
+// but written on the device by hook->fill.
+static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts, const ResidentHook *hook) {
   if (!h || B <= 0 || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_windows: bad arguments");
   CK(cudaSetDevice(h->device));
   static const bool trace = std::getenv("UVS_TRACE") != nullptr;   // host-side phase timings on stderr (adds syncs)
@@ -188,17 +191,18 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
     if ((x.estimate_td ? 1 : 0) != td) return fail(h, UVS_ERR_UNSUPPORTED, "estimate_td must be uniform over the batch");
     if (!x.pose || !x.speed_bias || !x.ex_pose || (x.n_points && !x.inv_depth) || (x.n_lines && !x.ortho))
       return fail(h, UVS_ERR_INVALID_ARG, "null state pointer in window " + std::to_string(i));
-    if (x.n_proj && (!x.proj_frame_i || !x.proj_frame_j || !x.proj_point || !x.proj_pts_i || !x.proj_pts_j))
+    if (hook && (B != 1 || td)) return fail(h, UVS_ERR_UNSUPPORTED, "device-resident window: one window, no td");
+    if (x.n_proj && !hook && (!x.proj_frame_i || !x.proj_frame_j || !x.proj_point || !x.proj_pts_i || !x.proj_pts_j))
       return fail(h, UVS_ERR_INVALID_ARG, "null projection-factor array");
     if (td && x.n_proj && (!x.proj_vel_i || !x.proj_vel_j || !x.proj_td_i || !x.proj_td_j || !x.proj_row_i || !x.proj_row_j || !x.td))
       return fail(h, UVS_ERR_INVALID_ARG, "estimate_td needs the td arrays");
-    if (x.n_line_obs && (!x.line_frame || !x.line_idx || !x.line_sp || !x.line_ep)) return fail(h, UVS_ERR_INVALID_ARG, "null line-factor array");
-    if (x.n_vp_obs && (!x.vp_frame || !x.vp_line || !x.vp_dir)) return fail(h, UVS_ERR_INVALID_ARG, "null VP-factor array");
+    if (x.n_line_obs && !hook && (!x.line_frame || !x.line_idx || !x.line_sp || !x.line_ep)) return fail(h, UVS_ERR_INVALID_ARG, "null line-factor array");
+    if (x.n_vp_obs && !hook && (!x.vp_frame || !x.vp_line || !x.vp_dir)) return fail(h, UVS_ERR_INVALID_ARG, "null VP-factor array");
     if ((x.n_line_obs || x.n_vp_obs) && (!x.line_ric || !x.line_tic)) return fail(h, UVS_ERR_INVALID_ARG, "line_ric / line_tic missing");
-    if (x.n_imu && (!x.imu_frame_i || !x.imu_delta_p || !x.imu_delta_q || !x.imu_delta_v || !x.imu_sum_dt || !x.imu_lin_ba ||
+    if (x.n_imu && !hook && (!x.imu_frame_i || !x.imu_delta_p || !x.imu_delta_q || !x.imu_delta_v || !x.imu_sum_dt || !x.imu_lin_ba ||
                     !x.imu_lin_bg || !x.imu_jacobian || !x.imu_covariance))
       return fail(h, UVS_ERR_INVALID_ARG, "null IMU array");
-    if (x.prior_n && (!x.prior_J || !x.prior_r || !x.prior_block_kind || !x.prior_block_id || !x.prior_x0 || !x.prior_n_blocks))
+    if (x.prior_n && ((!hook && (!x.prior_J || !x.prior_r)) || !x.prior_block_kind || !x.prior_block_id || !x.prior_x0 || !x.prior_n_blocks))
       return fail(h, UVS_ERR_INVALID_ARG, "null prior array");
     if (x.n_frames > 32) return fail(h, UVS_ERR_CAPACITY, "more than 32 frames per window (a landmark's factors must fit one warp)");
     const int d = 15 * x.n_frames + (x.estimate_extrinsic ? 6 : 0) + (td ? 1 : 0);
@@ -248,13 +252,13 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   // ---- input region: identical offsets in the pinned staging buffer and in the device arena
   Layout in;
   const size_t I = sizeof(int), Dd = sizeof(double);
-  const size_t o_frame_off = in.take((B + 1) * I), o_point_off = in.take((B + 1) * I), o_line_off = in.take((B + 1) * I),
-               o_proj_off = in.take((B + 1) * I), o_lobs_off = in.take((B + 1) * I), o_vobs_off = in.take((B + 1) * I),
-               o_imu_off = in.take((B + 1) * I), o_cam_off = in.take((B + 1) * I), o_prior_off = in.take((B + 1) * I),
-               o_pblk_off = in.take((B + 1) * I), o_S_off = in.take((B + 1) * 8), o_pJ_off = in.take((B + 1) * 8),
-               o_flags = in.take(B * I), o_frwin = in.take(nF * I), o_pwoff = in.take((B + 1) * I);
-  const size_t o_pose = in.take(nF * 7 * Dd), o_sb = in.take(nF * 9 * Dd), o_ex = in.take(B * 7 * Dd), o_td = in.take(B * Dd),
-               o_inv = in.take(nP * Dd), o_ortho = in.take(nL * 4 * Dd);
+  const size_t o_frame_off = in.take((B + 1) * I, 16), o_point_off = in.take((B + 1) * I, 16), o_line_off = in.take((B + 1) * I, 16),
+               o_proj_off = in.take((B + 1) * I, 16), o_lobs_off = in.take((B + 1) * I, 16), o_vobs_off = in.take((B + 1) * I, 16),
+               o_imu_off = in.take((B + 1) * I, 16), o_cam_off = in.take((B + 1) * I, 16), o_prior_off = in.take((B + 1) * I, 16),
+               o_pblk_off = in.take((B + 1) * I, 16), o_S_off = in.take((B + 1) * 8, 16), o_pJ_off = in.take((B + 1) * 8, 16),
+               o_flags = in.take(B * I, 16), o_frwin = in.take(nF * I, 16), o_pwoff = in.take((B + 1) * I, 16);
+  const size_t o_pose = in.take(nF * 7 * Dd), o_sb = in.take(nF * 9 * Dd, 16), o_ex = in.take(B * 7 * Dd, 16), o_td = in.take(B * Dd, 16),
+               o_inv = in.take(nP * Dd, 16), o_ortho = in.take(nL * 4 * Dd, 16);
   const size_t o_state_end = in.total;
   const size_t o_pfi = in.take(nProj * I), o_pfj = in.take(nProj * I), o_ppt = in.take(nProj * I),
                o_ppi = in.take(nProj * 3 * Dd), o_ppj = in.take(nProj * 3 * Dd);
@@ -268,15 +272,17 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
                o_idt = in.take(nImu * Dd), o_iba = in.take(nImu * 3 * Dd), o_ibg = in.take(nImu * 3 * Dd),
                o_ijac = in.take((size_t)nImu * 225 * Dd), o_icov = in.take((size_t)nImu * 225 * Dd);
   const size_t o_prJ = in.take((size_t)nPJ * Dd), o_prr = in.take(nPriorR * Dd), o_prx = in.take((size_t)nBlk * 9 * Dd),
-               o_bk = in.take(nBlk * I), o_bi = in.take(nBlk * I), o_bcol = in.take(nBlk * I), o_bcam = in.take(nBlk * I),
-               o_brow = in.take(nBlk * I);
+               o_bk = in.take(nBlk * I, 16), o_bi = in.take(nBlk * I, 16), o_bcol = in.take(nBlk * I, 16), o_bcam = in.take(nBlk * I, 16),
+               o_brow = in.take(nBlk * I, 16);
+  in.take(0);   // the region ends aligned
   h->input_bytes = in.total;
 
   // ---- work region
   Layout wk;
   wk.total = in.total;
-  const size_t w_pose = wk.take(nF * 7 * Dd), w_sb = wk.take(nF * 9 * Dd), w_ex = wk.take(B * 7 * Dd), w_td = wk.take(B * Dd),
-               w_inv = wk.take(nP * Dd), w_ortho = wk.take(nL * 4 * Dd);
+  // candidate state buffer: the same relative layout as the input state sections (filled by ONE device copy of that range)
+  const size_t w_pose = wk.take(nF * 7 * Dd), w_sb = wk.take(nF * 9 * Dd, 16), w_ex = wk.take(B * 7 * Dd, 16), w_td = wk.take(B * Dd, 16),
+               w_inv = wk.take(nP * Dd, 16), w_ortho = wk.take(nL * 4 * Dd, 16);
   const size_t w_pristine = wk.take(o_state_end - o_pose);
   const size_t w_cur = wk.take(B * I), w_ctl = wk.take(B * sizeof(WinCtl)), w_sum = wk.take((size_t)B * sizeof(UvsSummary));
   const size_t w_pidx = wk.take(nProj * sizeof(int4)), w_lidx = wk.take(nLobs * sizeof(int4)), w_vidx = wk.take(nVobs * sizeof(int4)),
@@ -313,7 +319,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   cpI(o_pwoff, pw_off); cpI(o_prior_off, h->prior_off); cpI(o_pblk_off, h->pblk_off); cpI(o_flags, h->win_flags);
   std::memcpy(S + o_S_off, h->S_off.data(), (B + 1) * 8);
   std::memcpy(S + o_pJ_off, h->priorJ_off.data(), (B + 1) * 8);
-  auto put = [&](size_t off, size_t elem_off, const void *src, size_t bytes) { if (bytes) std::memcpy(S + off + elem_off, src, bytes); };
+  auto put = [&](size_t off, size_t elem_off, const void *src, size_t bytes) { if (bytes && src) std::memcpy(S + off + elem_off, src, bytes); };
   std::atomic<int> pack_err(0), chain_bad(0), line_run_max(0);
   const bool want_line_runs = h->use_build3 && !any_ex;
   auto pack_range = [&](int lo, int hi) {
@@ -338,7 +344,10 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
     }
     put(o_lf, a0 * I, x.line_frame, x.n_line_obs * I); put(o_li, a0 * I, x.line_idx, x.n_line_obs * I);
     put(o_lsp, a0 * 2 * Dd, x.line_sp, x.n_line_obs * 2 * Dd); put(o_lep, a0 * 2 * Dd, x.line_ep, x.n_line_obs * 2 * Dd);
-    if (want_line_runs && x.n_line_obs > 0) {   // most observations of one line (they are contiguous): the fused path stages them per line
+    if (hook) {
+      int seen = line_run_max.load();
+      while (hook->line_run_max > seen && !line_run_max.compare_exchange_weak(seen, hook->line_run_max)) {}
+    } else if (want_line_runs && x.n_line_obs > 0) {   // most observations of one line (they are contiguous): the fused path stages them per line
       int run = 1, best = 1;
       for (int k = 1; k < x.n_line_obs; k++) { run = x.line_idx[k] == x.line_idx[k - 1] ? run + 1 : 1; best = std::max(best, run); }
       int seen = line_run_max.load();
@@ -355,7 +364,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
     put(o_ijac, m0 * 225 * Dd, x.imu_jacobian, (size_t)x.n_imu * 225 * Dd);
     put(o_icov, m0 * 225 * Dd, x.imu_covariance, (size_t)x.n_imu * 225 * Dd);
     if (x.prior_n > 0) {
-      put(o_prJ, (size_t)h->priorJ_off[i] * Dd, x.prior_J, (size_t)x.prior_n * x.prior_n * Dd);
+      if (x.prior_J) put(o_prJ, (size_t)h->priorJ_off[i] * Dd, x.prior_J, (size_t)x.prior_n * x.prior_n * Dd);
       put(o_prr, (size_t)h->prior_off[i] * Dd, x.prior_r, x.prior_n * Dd);
       int col = 0; size_t xo = 0;
       int sb_lo = 1 << 30, sb_hi = -1;   // frames whose speed-bias block the prior couples
@@ -409,7 +418,21 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   }
   char *Dv = h->dev.base;
   if (trace) { std::fprintf(stderr, "[uvs] upload: pack %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
-  CK(cudaMemcpyAsync(Dv, S, in.total, cudaMemcpyHostToDevice, h->stream));
+  if (!hook) {
+    CK(cudaMemcpyAsync(Dv, S, in.total, cudaMemcpyHostToDevice, h->stream));
+    h->h2d_bytes += (int64_t)in.total;
+  } else {
+    // host-provided sections only: tables + state, the extrinsic frozen into the line functors, the prior's block tables;
+    // the factor / IMU / prior-matrix sections are written on the device from the resident store
+    InputOffsets io{o_state_end, o_pfi, o_pfj, o_ppt, o_ppi, o_ppj, o_lf, o_li, o_lsp, o_lep, o_vf, o_vl, o_vd, o_ric, o_if, o_idp, o_idq, o_idv,
+                    o_idt, o_iba, o_ibg, o_ijac, o_icov, o_prJ, o_prr, o_prx, in.total};
+    CK(cudaMemcpyAsync(Dv, S, o_state_end, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(Dv + o_ric, S + o_ric, o_if - o_ric, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(Dv + o_prx, S + o_prx, in.total - o_prx, cudaMemcpyHostToDevice, h->stream));
+    h->h2d_bytes += (int64_t)(o_state_end + (o_if - o_ric) + (in.total - o_prx));
+    const int frc = hook->fill(hook->user, h, Dv, S, io);
+    if (frc) return frc;
+  }
   if (trace) { cudaStreamSynchronize(h->stream); std::fprintf(stderr, "[uvs] upload: H2D %.3f ms\n", ms_since(t_phase)); t_phase = now(); }
   // zero / preset the derived region that needs it
   CK(cudaMemsetAsync(Dv + w_cur, 0, w_pidx - w_cur, h->stream));          // cur, ctl, acc, summary
@@ -502,6 +525,10 @@ static int upload_finish(UvsHandle *h) {
 }  // extern "C"
 
 namespace uvs {
+int handle_upload(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts, const ResidentHook *hook) {
+  const int rc = upload_enqueue(h, B, w, opts, hook);
+  return rc ? rc : upload_finish(h);
+}
 int handle_fail(UvsHandle *h, int status, const std::string &msg) { return fail(h, status, msg); }
 int handle_ensure_scratch(UvsHandle *h, size_t bytes) {
   if (h->scratch.reserve(bytes) != cudaSuccess) return fail(h, UVS_ERR_CUDA, "scratch allocation failed");

@@ -37,7 +37,22 @@ struct Arena {
 
 struct Layout {   // byte offsets of one section list; computed twice (input region, work region)
   size_t total = 0;
-  size_t take(size_t bytes) { const size_t o = total; total = align_up(total + std::max<size_t>(bytes, 8)); return o; }
+  // every section STARTS aligned (256 bytes by default; the small per-window tables pack at 16 so that the host-provided
+  // part of a single window's upload stays a few KB - uvs_window_upload); the end is not padded
+  size_t take(size_t bytes, size_t a = ALIGN) { total = (total + a - 1) / a * a; const size_t o = total; total += std::max<size_t>(bytes, 8); return o; }
+};
+
+// byte offsets of the caller-array sections inside the input region (device arena and pinned staging alike)
+struct InputOffsets {
+  size_t state_end, pfi, pfj, ppt, ppi, ppj, lf, li, lsp, lep, vf, vl, vd, ric, imu_f, idp, idq, idv, idt, iba, ibg, ijac, icov, prJ, prr, prx, total;
+};
+// Device-resident window (uvs_window.cu): the factor / IMU / prior sections of the input region are written on the device
+// from the resident track store instead of being copied from the caller; `fill` is called with the upload's stream
+// after the host-provided sections have been enqueued.
+struct ResidentHook {
+  void *user;
+  int line_run_max;   // most observations of one eligible line
+  int (*fill)(void *user, UvsHandle *h, char *dev_base, char *stage_base, const InputOffsets &o);
 };
 
 }  // namespace uvs
@@ -92,6 +107,10 @@ struct UvsHandle {
   int stage_iters = 0;
   size_t smem_optin = 0;                      // cudaDeviceProp::sharedMemPerBlockOptin (queried once)
   std::vector<UvsHandle *> children;          // sub-batch handles of uvs_batch_solve_pipelined (own stream + arenas)
+  void *resident = nullptr;                   // uvs::ResidentWindow of uvs_window_create (uvs_window.cu)
+  const double *last_marg_J = nullptr, *last_marg_r = nullptr;   // device result of the last uvs_marginalize (in `scratch`), n x n and n
+  int last_marg_n = 0;
+  int64_t h2d_bytes = 0;                      // host-to-device bytes copied through this handle's upload paths since creation
 };
 
 
@@ -99,6 +118,10 @@ namespace uvs {
 int handle_fail(UvsHandle *h, int status, const std::string &msg);
 int handle_ensure_scratch(UvsHandle *h, size_t bytes);
 int handle_ensure_hscratch(UvsHandle *h, size_t bytes);
+// uvs_api.cu: upload of one window whose factor sections come from the device-resident store (hook != nullptr)
+int handle_upload(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts, const ResidentHook *hook);
+// uvs_window.cu
+void resident_destroy(UvsHandle *h);
 // uvs_comm.cpp: NCCL bound at run time (dlopen of libnccl.so.2; the library has no link-time dependency on it)
 int nccl_unique_id(unsigned char id[128]);
 int nccl_init_rank(void **comm, const unsigned char id[128], int rank, int nranks);

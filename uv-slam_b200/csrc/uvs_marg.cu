@@ -225,6 +225,7 @@ using namespace uvs;
   } while (0)
 
 int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
+  h->last_marg_J = h->last_marg_r = nullptr; h->last_marg_n = 0;
   if (wi < 0 || wi >= h->B) return handle_fail(h, UVS_ERR_INVALID_ARG, "uvs_marginalize: window index out of range");
   if (flag != UVS_MARGIN_OLD && flag != UVS_MARGIN_SECOND_NEW) return handle_fail(h, UVS_ERR_INVALID_ARG, "uvs_marginalize: bad flag");
   if (h->nranks > 1) return handle_fail(h, UVS_ERR_UNSUPPORTED, "uvs_marginalize: not available in the factor-parallel multi-GPU mode");
@@ -381,6 +382,7 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
   CKM(cudaMemcpyAsync(hs + oAo, ds + oAo, ocam + al((size_t)(16 * F + 8) * Dd) - oAo, cudaMemcpyDeviceToHost, st));
   CKM(cudaStreamSynchronize(st));
 
+  h->last_marg_J = (const double *)(ds + oJ); h->last_marg_r = (const double *)(ds + orr); h->last_marg_n = n;   // stays valid until the scratch arena is used again
   // ---- outputs (getParameterBlocks with the window shift, estimator.cpp:1139-1153 / 1199-1222)
   out->n = n; out->m = m; out->n_blocks = nkept;
   std::memcpy(out->J, hs + oJ, (size_t)n * n * Dd);
