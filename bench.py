@@ -289,6 +289,65 @@ def factor_arm(args):
     s.close()
 
 
+def frame_path(local, k_lm=K_LM, n_slides=12):
+    """The reference's own use - ONE window per image frame - end to end, two ways: (a) every window packed on the host and
+    uploaded from scratch (uvs_upload_windows), (b) the device-resident window (uvs_window_*: only the new frame, the packed
+    state and a plan cross the bus).  Host wall-clock of upload + solve + state download per frame, median over the slides."""
+    import uvs_b200
+    from tools import fm_ref, gen_sequence as gs
+    W = 10
+    seq = gs.Sequence(n_frames=W + 1 + n_slides, n_points=150, n_lines=50, seed=3)
+    opts = uvs_b200.default_options(max_num_iterations=k_lm, fixed_iterations=1)
+    dev, ref = uvs_b200.Solver(local), uvs_b200.Solver(local)
+    dev.window_create(W, 5, 1024, 512)
+    host = fm_ref.HostWindow(W, 5)
+    nrng = np.random.default_rng(5)
+    prior, t_res, t_scr, b_res, b_scr, slides = None, [], [], [], [], 0
+    for k, fr in enumerate(seq.frames):
+        host.push(k, fr)
+        h0 = dev.h2d_bytes()
+        t0 = time.perf_counter()
+        dev.window_push_frame(fr.point_id, fr.point_xyz, fr.line_id, fr.line_sp, fr.line_ep, fr.line_vp, imu=fr.imu)
+        t_push = time.perf_counter() - t0
+        if len(host.frame_ids) < W + 1:
+            continue
+        pose, sb = seq.noisy_pose_sb(host.frame_ids, nrng)
+        ep, el = host.eligible_points(), host.eligible_lines()
+        inv = np.array([seq.inv_depth_of(t.id, host.frame_ids[t.start]) for t in ep]) * (1 + nrng.normal(0, 0.05, len(ep)))
+        ortho = np.array([seq.ortho_of(t.id) for t in el]).reshape(-1, 4) + nrng.normal(0, 0.01, (len(el), 4))
+        w_host = host.pack(pose, sb, seq.ex_pose(), inv, ortho, seq.ric, seq.tic, prior)
+        w_dev = uvs_b200.Window(pose=pose.copy(), speed_bias=sb.copy(), ex_pose=seq.ex_pose(), inv_depth=inv.copy(), ortho=ortho.copy(),
+                                line_ric=seq.ric.copy(), line_tic=seq.tic.copy())
+        t0 = time.perf_counter()
+        dev.window_upload(w_dev, opts); dev.solve(); dev.download()
+        t_res.append(t_push + time.perf_counter() - t0)
+        b_res.append(dev.h2d_bytes() - h0)
+        h0 = ref.h2d_bytes()
+        t0 = time.perf_counter()
+        ref.upload([w_host], opts); ref.solve(); ref.download()
+        t_scr.append(time.perf_counter() - t0)
+        b_scr.append(ref.h2d_bytes() - h0)
+        flag = 1 if slides % 3 == 2 else 0
+        pd = dev.window_marginalize(flag)
+        if pd is not None:
+            prior = pd
+        elif flag == 0:
+            prior = None
+        merged = ms = None
+        if flag == 1 and len(host.imu) >= 2:
+            ms = gs.merge_samples(host.imu_samples[-2], host.imu_samples[-1])
+            merged = gs.imu_record(ms)
+        host.slide(flag, merged, ms)
+        dev.window_slide(flag, merged)
+        slides += 1
+    dev.close(); ref.close()
+    med = lambda a: float(np.median(a[2:]))   # the first frames pay allocations
+    return {"workload": "one 11-frame window per image frame, ~150 tracked points + ~50 lines per frame, %d LM iterations, %d frames" % (k_lm, slides),
+            "from_scratch": {"ms_per_frame": 1e3 * med(t_scr), "h2d_bytes_per_frame": int(med(b_scr)), "call": "uvs_upload_windows + uvs_solve + uvs_download_state"},
+            "device_resident": {"ms_per_frame": 1e3 * med(t_res), "h2d_bytes_per_frame": int(med(b_res)),
+                                "call": "uvs_window_push_frame + uvs_window_upload + uvs_solve + uvs_download_state"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -412,6 +471,7 @@ def main():
         s1.reset_state(); s1.solve(); lat.append(s1.last_solve_ms())
     lat_graph_ms = float(np.median(lat))
     s1.close()
+    frames = frame_path(local) if rank == 0 and args.config == "C2" else None
 
     if rank != 0:
         if dist is not None:
@@ -495,6 +555,8 @@ def main():
                     "single_window_ms_per_solve_graph_replay": lat_graph_ms},
         "wall_ms_per_step": 1e3 * wall / args.steps,
     }
+    if frames is not None:
+        line["e2e"]["single_window_per_frame"] = frames
     if check is not None:
         line["parity_check"] = check
     print(json.dumps(line))

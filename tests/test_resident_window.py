@@ -1,5 +1,5 @@
 """Device-resident sliding window (include/uvs.h uvs_window_*) against the host-side restatement of the
-reference's per-frame bookkeeping (tests/fm_ref.py): a seeded frame stream is fed frame by frame to
+reference's per-frame bookkeeping (tools/fm_ref.py): a seeded frame stream is fed frame by frame to
   (a) the resident window: uvs_window_push_frame / _upload / uvs_solve / _marginalize / _slide - observations, IMU records
       and the prior never leave the device again, and
   (b) a second handle that gets every window packed from scratch on the host (uvs_upload_windows),
@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import uvs_b200
-from tests import fm_ref
+from tools import fm_ref
 from tools import gen_sequence as gs
 
 pytestmark = pytest.mark.gpu
