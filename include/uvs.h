@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UVS_ABI_VERSION 1
+#define UVS_ABI_VERSION 2
 
 typedef enum UvsStatus {
   UVS_OK = 0,
@@ -132,6 +132,18 @@ typedef struct UvsWindow {
   const int32_t *prior_block_kind; /* [prior_n_blocks] UvsBlockKind, in column order */
   const int32_t *prior_block_id;   /* [prior_n_blocks] */
   const double *prior_x0;          /* global-size linearisation points, concatenated */
+
+  /* ---- relocalisation factors (estimator.cpp:944-978; ABI version 2) ----
+   * With relocalization_info set, optimization() adds the parameter block relo_Pose (7, PoseLocalParameterization) and,
+   * for every eligible feature matched in the loop-closure frame, one ProjectionFactor(pts_i, pts_j) on the blocks
+   * {para_Pose[start_frame], relo_Pose, para_Ex_Pose[0], para_Feature[k]} with the point loss; pts_i is the feature's
+   * first observation (as in its other factors), pts_j = (match.x, match.y, 1).  The marginalization does not see them
+   * (estimator.cpp:1003-1228 builds its own list).  n_relo = 0: none.  Not combinable with estimate_td. */
+  int32_t n_relo;
+  int32_t reserved1;
+  double *relo_pose;               /* [7] in: initial value (the loop frame's pose), out: uvs_download_state */
+  const int32_t *relo_point;       /* [n_relo] index into inv_depth; the point must own at least one proj factor; ascending */
+  const double *relo_pts_j;        /* [n_relo][3] */
 } UvsWindow;
 
 /* Globals of parameters.h:11-47 that the hot path reads, plus Ceres' trust-region defaults. */

@@ -15,14 +15,15 @@
 
 namespace orc {
 
-enum FactorType { F_PRIOR = 0, F_IMU = 1, F_PROJ = 2, F_LINE = 3, F_VP = 4 };
+enum FactorType { F_PRIOR = 0, F_IMU = 1, F_PROJ = 2, F_LINE = 3, F_VP = 4, F_RELO = 5 };   // F_RELO: estimator.cpp:944-978
+constexpr int F_LAST = F_RELO;
 
 // Tangent-space layout used by the oracle's linear algebra:
-//   camera set:   pose f -> 15f, speed-bias f -> 15f+6, [ex-pose -> 15F], [td -> 15F(+6)]
+//   camera set:   pose f -> 15f, speed-bias f -> 15f+6, [ex-pose -> 15F], [td -> 15F(+6)], [relo_Pose -> after those]
 //   landmark set: point k -> d + k, line k -> d + Np + 4k
 struct Layout {
   int F = 0, Np = 0, Nl = 0;
-  int ex_off = -1, td_off = -1;
+  int ex_off = -1, td_off = -1, relo_off = -1;
   int d = 0;      // camera dims
   int total = 0;  // camera + landmark dims
   int pose(int f) const { return 15 * f; }
@@ -32,7 +33,7 @@ struct Layout {
 };
 
 struct State {
-  std::vector<double> pose, sb, ex, td, inv_depth, ortho;
+  std::vector<double> pose, sb, ex, td, inv_depth, ortho, relo;
 };
 
 // One evaluated (non-prior) residual block.  Jacobians are row-major nr x gs[b] ("Ceres layout")
@@ -55,12 +56,21 @@ class Problem {
   Layout lay;
   std::vector<double> imu_sqrt_info_;  // [n_imu][225]
   std::vector<int> prior_gs_, prior_off_, prior_col_;  // global size, tangent offset, column in J0
+  std::vector<int> relo_anchor_;                       // first projection factor of every matched point (its start frame / pts_i)
 
   Problem(const UvsWindow &win, const UvsOptions &opt) : w(win), o(opt) {
     lay.F = w.n_frames; lay.Np = w.n_points; lay.Nl = w.n_lines;
     lay.d = 15 * lay.F;
     if (w.estimate_extrinsic) { lay.ex_off = lay.d; lay.d += 6; }
     if (w.estimate_td) { lay.td_off = lay.d; lay.d += 1; }
+    if (w.n_relo > 0) {   // problem.AddParameterBlock(relo_Pose, SIZE_POSE, local_parameterization), estimator.cpp:947-948
+      lay.relo_off = lay.d; lay.d += 6;
+      for (int r = 0; r < w.n_relo; r++) {
+        int a = -1;
+        for (int k = 0; k < w.n_proj && a < 0; k++) if (w.proj_point[k] == w.relo_point[r]) a = k;
+        relo_anchor_.push_back(a);
+      }
+    }
     lay.total = lay.d + lay.Np + 4 * lay.Nl;
     imu_sqrt_info_.resize((size_t)w.n_imu * 225);
     for (int k = 0; k < w.n_imu; k++) imu_sqrt_info(w.imu_covariance + (size_t)k * 225, &imu_sqrt_info_[(size_t)k * 225]);
@@ -85,6 +95,7 @@ class Problem {
     s.td.assign(1, w.td ? w.td[0] : 0.0);
     s.inv_depth.assign(w.inv_depth, w.inv_depth + w.n_points);
     s.ortho.assign(w.ortho, w.ortho + 4 * w.n_lines);
+    if (w.n_relo > 0) s.relo.assign(w.relo_pose, w.relo_pose + 7);
     return s;
   }
   void store_state(const State &s, UvsWindow &dst) const {
@@ -94,6 +105,7 @@ class Problem {
     if (dst.td) dst.td[0] = s.td[0];
     std::copy(s.inv_depth.begin(), s.inv_depth.end(), dst.inv_depth);
     std::copy(s.ortho.begin(), s.ortho.end(), dst.ortho);
+    if (lay.relo_off >= 0 && dst.relo_pose) std::copy(s.relo.begin(), s.relo.end(), dst.relo_pose);
   }
 
   int num_factors(int type) const {
@@ -102,6 +114,7 @@ class Problem {
       case F_IMU: return w.n_imu;
       case F_PROJ: return w.n_proj;
       case F_LINE: return w.n_line_obs;
+      case F_RELO: return w.n_relo;
       default: return w.n_vp_obs;
     }
   }
@@ -115,6 +128,7 @@ class Problem {
     }
     if (lay.ex_off >= 0) pose_plus(s.ex.data(), &delta[lay.ex_off], t.ex.data());
     if (lay.td_off >= 0) t.td[0] = s.td[0] + delta[lay.td_off];
+    if (lay.relo_off >= 0) pose_plus(s.relo.data(), &delta[lay.relo_off], t.relo.data());
     for (int k = 0; k < lay.Np; k++) t.inv_depth[k] = s.inv_depth[k] + delta[lay.point(k)];
     for (int k = 0; k < 4 * lay.Nl; k++) t.ortho[k] = s.ortho[k] + delta[lay.d + lay.Np + k];
   }
@@ -126,6 +140,7 @@ class Problem {
     for (double v : s.sb) n += v * v;
     if (lay.ex_off >= 0) for (double v : s.ex) n += v * v;
     if (lay.td_off >= 0) n += s.td[0] * s.td[0];
+    for (double v : s.relo) n += v * v;
     for (double v : s.inv_depth) n += v * v;
     for (double v : s.ortho) n += v * v;
     return n;
@@ -136,6 +151,7 @@ class Problem {
     acc(a.pose, b.pose); acc(a.sb, b.sb);
     if (lay.ex_off >= 0) acc(a.ex, b.ex);
     if (lay.td_off >= 0) acc(a.td, b.td);
+    acc(a.relo, b.relo);
     acc(a.inv_depth, b.inv_depth); acc(a.ortho, b.ortho);
     return n;
   }
@@ -164,6 +180,17 @@ class Problem {
       eval_projection(pose_ptr(fi), pose_ptr(fj), s.ex.data(), s.inv_depth[pk], vec_from(w.proj_pts_i + 3 * idx),
                       vec_from(w.proj_pts_j + 3 * idx), o.focal_length / 1.6, tp, e.r, jp(0), jp(1), jp(2), jp(3),
                       e.nb == 5 ? jp(4) : nullptr);
+    } else if (type == F_RELO) {
+      // ProjectionFactor(pts_i, pts_j) on {para_Pose[start], relo_Pose, para_Ex_Pose[0], para_Feature[k]} (estimator.cpp:964-970):
+      // pts_i = the feature's first observation, pts_j = (match.x, match.y, 1)
+      const int a = relo_anchor_[idx], fi = w.proj_frame_i[a], pk = w.relo_point[idx];
+      e.nr = 2; e.nb = 4;
+      e.gs[0] = 7; e.off[0] = lay.pose(fi);
+      e.gs[1] = 7; e.off[1] = lay.relo_off;
+      e.gs[2] = 7; e.off[2] = lay.ex_off;
+      e.gs[3] = 1; e.off[3] = lay.point(pk);
+      eval_projection(pose_ptr(fi), s.relo.data(), s.ex.data(), s.inv_depth[pk], vec_from(w.proj_pts_i + 3 * a),
+                      vec_from(w.relo_pts_j + 3 * idx), o.focal_length / 1.6, nullptr, e.r, jp(0), jp(1), jp(2), jp(3), nullptr);
     } else if (type == F_LINE || type == F_VP) {
       const bool is_line = type == F_LINE;
       const int fj = is_line ? w.line_frame[idx] : w.vp_frame[idx];
@@ -203,7 +230,7 @@ class Problem {
   }
 
   double loss_scale(int type) const {
-    return type == F_PROJ ? o.cauchy_point : (type == F_LINE ? o.cauchy_line : (type == F_VP ? o.cauchy_vp : -1.0));
+    return (type == F_PROJ || type == F_RELO) ? o.cauchy_point : (type == F_LINE ? o.cauchy_line : (type == F_VP ? o.cauchy_vp : -1.0));
   }
 
   // Ceres' ResidualBlock::Evaluate: raw -> tangent columns -> corrector.  J[b] becomes nr x ls[b].
@@ -233,7 +260,7 @@ class Problem {
   double total_cost(const State &s) const {
     double c = 0.0;
     BlockEval e;
-    for (int t = F_IMU; t <= F_VP; t++) for (int i = 0; i < num_factors(t); i++) { evaluate_block(t, i, s, e, false); c += e.cost; }
+    for (int t = F_IMU; t <= F_LAST; t++) for (int i = 0; i < num_factors(t); i++) { evaluate_block(t, i, s, e, false); c += e.cost; }
     if (w.prior_n > 0) {
       std::vector<double> r(w.prior_n);
       evaluate_prior(s, r.data());

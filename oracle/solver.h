@@ -91,10 +91,10 @@ class Solver {
     double cost = 0.0;
     std::vector<BlockEval> &ev = evals_;
     size_t nf = 0;
-    for (int t = F_IMU; t <= F_VP; t++) nf += P.num_factors(t);
+    for (int t = F_IMU; t <= F_LAST; t++) nf += P.num_factors(t);
     ev.resize(nf);
     size_t k = 0;
-    for (int t = F_IMU; t <= F_VP; t++)
+    for (int t = F_IMU; t <= F_LAST; t++)
       for (int i = 0; i < P.num_factors(t); i++) { P.evaluate_block(t, i, s, ev[k], true); cost += ev[k].cost; k++; }
     const int n = P.w.prior_n;
     if (n > 0) {

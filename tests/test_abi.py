@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.uvs_abi_version() == 1
+    assert lib.uvs_abi_version() == 2   # version 2: relocalisation fields of UvsWindow
     assert set(uvs_b200.binding.EXPORTS) == set(names)
 
 
@@ -42,7 +42,7 @@ def test_struct_layouts_match_the_header():
         else:
             assert a == b, f
     assert C.sizeof(uvs_b200.UvsSummaryStruct) == 16 + 16 + 5 * 8 * 64 + 4 * 64
-    assert C.sizeof(uvs_b200.UvsWindowStruct) == 12 * 4 + 40 * 8
+    assert C.sizeof(uvs_b200.UvsWindowStruct) == 12 * 4 + 40 * 8 + 2 * 4 + 3 * 8   # + the relocalisation fields (ABI version 2)
 
 
 def test_no_cpu_fallback_without_gpu():

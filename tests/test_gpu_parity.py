@@ -599,3 +599,44 @@ def test_graph_replay_gives_the_same_solve(windows, opts):
                 assert abs(a.final_cost - b.final_cost) <= 1e-7 * abs(a.final_cost)   # FP64 reductions are order-dependent
     finally:
         s.close()
+
+
+def test_relocalisation_factors(solver, opts):
+    """Relocalisation factors and the relo_Pose block (estimator.cpp:944-978; UvsWindow.n_relo / relo_*) against the oracle:
+    same accept sequence, per-iteration cost to 1e-6, poses and relo_Pose to 1e-4; the marginalization built afterwards
+    ignores them, exactly like the reference's (estimator.cpp:1003-1228)."""
+    w0, truth = gw.make_window("C1", return_truth=True)
+    w0 = gw.add_relocalisation(w0, truth, frame=3, n_match=15)
+    ref, w = w0.copy(), w0.copy()
+    sm0 = orc.solve(ref, opts)
+    solver.upload([w], opts)
+    assert abs(solver.cost()[0] - orc.total_cost(w0, opts)) <= 1e-9 * orc.total_cost(w0, opts)
+    r, _ = solver.eval("proj", local=True)
+    assert r.shape[0] == w0.n_proj + w0.n_relo           # the relocalisation factors are evaluated with their points' groups
+    sm = solver.solve()[0]
+    solver.download()
+    n = sm.num_iterations
+    assert n == sm0.num_iterations
+    assert [sm.step_accepted[i] for i in range(n)] == [sm0.step_accepted[i] for i in range(n)]
+    for i in range(n):
+        assert abs(sm.cost[i] - sm0.cost[i]) <= 1e-6 * abs(sm0.cost[i]), (i, sm.cost[i], sm0.cost[i])
+    dp, dq = _tangent_delta(ref, w)
+    assert dp < STEP_TOL and dq < STEP_TOL
+    assert np.abs(w.relo_pose - ref.relo_pose).max() < STEP_TOL
+    assert np.abs(w.relo_pose - w0.relo_pose).max() > 1e-3        # and it moved
+    assert np.abs(w.speed_bias - ref.speed_bias).max() < STEP_TOL and np.abs(w.inv_depth - ref.inv_depth).max() < STEP_TOL
+    # marginalization: neither the block nor its factors take part
+    g = solver.marginalize(0, 0)
+    m = orc.marginalize(w, opts, 0)
+    assert g["n"] == m["n"] and np.array_equal(g["kinds"], m["kinds"]) and np.array_equal(g["ids"], m["ids"])
+    assert np.abs(g["A"] - m["A"]).max() < 2e-3 * np.abs(m["A"]).max()
+    # a batch mixing windows with and without relocalisation
+    a, b = w0.copy(), gw.make_window("C1")
+    sums = solver.batch_solve([a, b], opts)
+    assert abs(sums[0].final_cost - sm0.final_cost) <= 1e-6 * abs(sm0.final_cost)
+    assert np.abs(a.relo_pose - ref.relo_pose).max() < STEP_TOL
+    # argument checks: a matched point needs a projection factor; no td
+    bad = w0.copy()
+    bad.relo_point = np.array([w0.n_points - 1, w0.n_points], np.int32); bad.relo_pts_j = np.zeros((2, 3))
+    with pytest.raises(uvs_b200.UvsError):
+        solver.upload([bad], opts)

@@ -419,3 +419,32 @@ def test_marginalization_against_exact_rule(opts, cfg, flag):
     else:
         assert errA < 1e-3 and errb < 1e-3, (errA, errb)
         assert errA > 10 * float(z["cond"])   # the loss is the method's (explicit inverse), not the problem's conditioning
+
+
+# ---- relocalisation factors (estimator.cpp:944-978) ----------------------------------------------------------------
+def test_relocalisation_block_equals_an_extra_frame(opts):
+    """The oracle's relo_Pose block + F_RELO factors (restated from estimator.cpp:944-978) against the SAME problem written as
+    one more frame whose pose observes the matched points (tools/gen_window.expand_relocalisation): equal cost at the start,
+    equal iteration log, equal solution - the extra frame's speed-bias block has no factor and must not move."""
+    w, truth = gw.make_window("C1", return_truth=True)
+    w = gw.add_relocalisation(w, truth, frame=3, n_match=15)
+    assert w.n_relo >= 8
+    x = gw.expand_relocalisation(w)
+    assert x.n_frames == w.n_frames + 1 and x.n_proj == w.n_proj + w.n_relo
+    assert abs(orc.total_cost(w, opts) - orc.total_cost(x, opts)) <= 1e-12 * orc.total_cost(w, opts)
+    assert orc.total_cost(w, opts) > orc.total_cost(gw.make_window("C1"), opts)          # the factors are really there
+    a, b = w.copy(), x.copy()
+    sa, sb = orc.solve(a, opts), orc.solve(b, opts)
+    n = sa.num_iterations
+    assert n == sb.num_iterations and [sa.step_accepted[i] for i in range(n)] == [sb.step_accepted[i] for i in range(n)]
+    for i in range(n):
+        assert abs(sa.cost[i] - sb.cost[i]) <= 1e-9 * abs(sb.cost[i]), i
+    assert np.abs(a.pose - b.pose[:-1]).max() < 1e-8 and np.abs(a.relo_pose - b.pose[-1]).max() < 1e-8
+    assert np.abs(b.speed_bias[-1]).max() == 0.0
+    # the loop frame's pose is recovered from the matches (it started 0.1 m / 2 deg away)
+    d0 = np.linalg.norm(w.relo_pose[:3] - truth["relo_pose"][:3]); d1 = np.linalg.norm(a.relo_pose[:3] - truth["relo_pose"][:3])
+    assert d1 < 0.5 * d0, (d0, d1)
+    # file format: the optional relocalisation section round-trips, windows without it keep their bytes
+    r = Window.from_bytes(w.to_bytes())
+    assert np.array_equal(r.relo_point, w.relo_point) and np.array_equal(r.relo_pts_j, w.relo_pts_j) and np.array_equal(r.relo_pose, w.relo_pose)
+    assert len(gw.make_window("C1").to_bytes()) < len(w.to_bytes())

@@ -523,3 +523,64 @@ if __name__ == "__main__":
         win.n_frames, win.n_points, win.n_lines, win.n_proj, win.n_line_obs, win.n_vp_obs, win.n_imu, win.prior_n))
     if a.out:
         win.save(a.out)
+
+
+def add_relocalisation(w: Window, truth, frame=3, n_match=15, seed=0) -> Window:
+    """Relocalisation factors (estimator.cpp:944-978, :1366-1378) for window `w`: a loop-closure frame that saw the same place
+    as window frame `frame` from a slightly different pose; `n_match` eligible features whose track starts at or before that
+    frame are matched in it (match_points), relo_Pose starts at the window's estimate of that frame (estimator.cpp:1376).
+    -> a copy of `w` with relo_pose / relo_point / relo_pts_j set; truth["relo_pose"] = the loop frame's true pose."""
+    rng = np.random.default_rng(seed + 31)
+    ric = ric_normalized()
+    dth = rng.normal(0, np.deg2rad(2.0), 3)
+    q_loop = q_mul(R_to_q(truth["Rs"][frame]), np.array([dth[0] / 2, dth[1] / 2, dth[2] / 2, 1.0]))
+    q_loop /= np.linalg.norm(q_loop)
+    R_loop, P_loop = q_to_R(q_loop), truth["Ps"][frame] + rng.normal(0, 0.1, 3)
+    Rwc, twc = R_loop @ ric, R_loop @ TIC + P_loop
+    first = {}
+    for k in range(w.n_proj):
+        first.setdefault(int(w.proj_point[k]), k)
+    pts, pj = [], []
+    for p in sorted(first):
+        a = first[p]
+        fi = int(w.proj_frame_i[a])
+        if fi > frame:
+            continue
+        Xc = w.proj_pts_i[a] / truth["inv_depth"][p]
+        Xw = truth["Rwc"][fi] @ Xc + truth["twc"][fi]
+        pc = (Xw - twc) @ Rwc
+        if pc[2] < 0.5 or abs(pc[0] / pc[2]) > 1.5 or abs(pc[1] / pc[2]) > 1.5:
+            continue
+        pts.append(p)
+        pj.append(np.array([pc[0] / pc[2], pc[1] / pc[2], 1.0]) + np.append(rng.normal(0, 1.0 / FOCAL, 2), 0.0))
+        if len(pts) == n_match:
+            break
+    out = w.copy()
+    out.relo_pose = w.pose[frame].copy()
+    out.relo_point = np.array(pts, np.int32)
+    out.relo_pts_j = np.array(pj).reshape(-1, 3)
+    out.normalize()
+    truth["relo_pose"] = np.concatenate([P_loop, q_loop])
+    return out
+
+
+def expand_relocalisation(w: Window) -> Window:
+    """The same problem written without the relocalisation fields: relo_Pose as one more frame at the end of the window
+    (no IMU factor, a speed-bias block no factor touches), its factors as ordinary point factors observing from that frame -
+    what the library does internally (uvs_api.cu) and what the oracle's F_RELO evaluation is checked against."""
+    F = w.n_frames
+    out = w.copy()
+    out.pose = np.vstack([w.pose, w.relo_pose.reshape(1, 7)])
+    out.speed_bias = np.vstack([w.speed_bias, np.zeros((1, 9))])
+    fi, fj, pt, pi, pj = [], [], [], [], []
+    relo_of = {int(p): r for r, p in enumerate(w.relo_point)}
+    for k in range(w.n_proj):
+        fi.append(w.proj_frame_i[k]); fj.append(w.proj_frame_j[k]); pt.append(w.proj_point[k]); pi.append(w.proj_pts_i[k]); pj.append(w.proj_pts_j[k])
+        p = int(w.proj_point[k])
+        if (k + 1 == w.n_proj or int(w.proj_point[k + 1]) != p) and p in relo_of:
+            fi.append(w.proj_frame_i[k]); fj.append(F); pt.append(p); pi.append(w.proj_pts_i[k]); pj.append(w.relo_pts_j[relo_of[p]])
+    out.proj_frame_i, out.proj_frame_j, out.proj_point = (np.array(a, np.int32) for a in (fi, fj, pt))
+    out.proj_pts_i, out.proj_pts_j = np.array(pi).reshape(-1, 3), np.array(pj).reshape(-1, 3)
+    out.relo_pose, out.relo_point, out.relo_pts_j = np.zeros(0), np.zeros(0, np.int32), np.zeros((0, 3))
+    out.normalize()
+    return out

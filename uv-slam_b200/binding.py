@@ -188,7 +188,8 @@ class Solver:
 
     # -- factor sweeps -------------------------------------------------------------------------
     def _count(self, kind):
-        return sum({"proj": w.n_proj, "line": w.n_line_obs, "vp": w.n_vp_obs, "imu": w.n_imu}[kind] for w in self.windows)
+        # relocalisation factors are point factors inside the library (each one follows its point's own factors)
+        return sum({"proj": w.n_proj + w.n_relo, "line": w.n_line_obs, "vp": w.n_vp_obs, "imu": w.n_imu}[kind] for w in self.windows)
 
     def eval(self, kind: str, local: bool = False, want_jac: bool = True):
         """-> (residuals [n, nr], jacobians [n, jd] or None) on the host."""

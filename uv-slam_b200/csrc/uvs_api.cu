@@ -63,6 +63,50 @@ void prefix(std::vector<T> &off, int B, const UvsWindow *w, T (*get)(const UvsWi
 int prior_local(int kind) { return (kind == UVS_BLOCK_POSE || kind == UVS_BLOCK_EXPOSE) ? 6 : (kind == UVS_BLOCK_SPEEDBIAS ? 9 : 1); }
 int prior_global(int kind) { return (kind == UVS_BLOCK_POSE || kind == UVS_BLOCK_EXPOSE) ? 7 : (kind == UVS_BLOCK_SPEEDBIAS ? 9 : 1); }
 
+// owned arrays of a window expanded by its relocalisation pose (see upload_enqueue)
+struct RelocExpansion {
+  std::vector<double> pose, sb, pts_i, pts_j;
+  std::vector<int> fi, fj, pt;
+};
+int expand_relocalisation(const UvsWindow &x, RelocExpansion &E, UvsWindow &out) {
+  if (!x.relo_pose || !x.relo_point || !x.relo_pts_j || !x.pose || !x.speed_bias) return 1;
+  if (x.estimate_td) return 3;
+  if (x.n_proj > 0 && (!x.proj_frame_i || !x.proj_frame_j || !x.proj_point || !x.proj_pts_i || !x.proj_pts_j)) return 1;
+  const int F = x.n_frames, np = x.n_proj, nr = x.n_relo;
+  for (int r = 0; r < nr; r++) {
+    if (x.relo_point[r] < 0 || x.relo_point[r] >= x.n_points) return 1;
+    if (r > 0 && x.relo_point[r] <= x.relo_point[r - 1]) return 1;
+  }
+  E.pose.assign(x.pose, x.pose + 7 * (size_t)F); E.pose.insert(E.pose.end(), x.relo_pose, x.relo_pose + 7);
+  E.sb.assign(x.speed_bias, x.speed_bias + 9 * (size_t)F); E.sb.insert(E.sb.end(), 9, 0.0);
+  std::vector<int> relo_of(x.n_points, -1);
+  for (int r = 0; r < nr; r++) relo_of[x.relo_point[r]] = r;
+  int placed = 0;
+  for (int k = 0; k < np; k++) {
+    E.fi.push_back(x.proj_frame_i[k]); E.fj.push_back(x.proj_frame_j[k]); E.pt.push_back(x.proj_point[k]);
+    E.pts_i.insert(E.pts_i.end(), x.proj_pts_i + 3 * (size_t)k, x.proj_pts_i + 3 * (size_t)k + 3);
+    E.pts_j.insert(E.pts_j.end(), x.proj_pts_j + 3 * (size_t)k, x.proj_pts_j + 3 * (size_t)k + 3);
+    const int p = x.proj_point[k];
+    if (p < 0 || p >= x.n_points) return 1;
+    const bool last_of_point = k + 1 == np || x.proj_point[k + 1] != p;
+    if (last_of_point && relo_of[p] >= 0) {   // the point's factor group ends here: its relocalisation factor joins it
+      const int r = relo_of[p];
+      E.fi.push_back(x.proj_frame_i[k]); E.fj.push_back(F); E.pt.push_back(p);
+      E.pts_i.insert(E.pts_i.end(), x.proj_pts_i + 3 * (size_t)k, x.proj_pts_i + 3 * (size_t)k + 3);
+      E.pts_j.insert(E.pts_j.end(), x.relo_pts_j + 3 * (size_t)r, x.relo_pts_j + 3 * (size_t)r + 3);
+      relo_of[p] = -2;
+      placed++;
+    }
+  }
+  if (placed != nr) return 2;
+  out = x;
+  out.n_frames = F + 1; out.n_proj = np + nr; out.n_relo = 0;
+  out.pose = E.pose.data(); out.speed_bias = E.sb.data();
+  out.proj_frame_i = E.fi.data(); out.proj_frame_j = E.fj.data(); out.proj_point = E.pt.data();
+  out.proj_pts_i = E.pts_i.data(); out.proj_pts_j = E.pts_j.data();
+  return 0;
+}
+
 int post_launch(UvsHandle *h, const char *where) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, where);
@@ -173,6 +217,31 @@ int uvs_upload_windows(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOpt
 static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const UvsOptions *opts, const ResidentHook *hook) {
   if (!h || B <= 0 || !w) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_windows: bad arguments");
   CK(cudaSetDevice(h->device));
+  // Relocalisation factors (estimator.cpp:944-978): relo_Pose is a pose block without IMU factors, its factors are point
+  // factors whose observing pose is that block.  Inside the library it is one more FRAME at the end of the window whose
+  // speed-bias block has no factor (zero Hessian rows: the LM diagonal keeps them at a zero step, the rest of the system
+  // is what Ceres sees), and every relocalisation factor joins the factor group of its point.
+  std::vector<UvsWindow> expanded;
+  std::vector<RelocExpansion> reloc_store;
+  h->relo.assign(B, 0);
+  {
+    bool any = false;
+    for (int i = 0; i < B; i++) any = any || w[i].n_relo > 0;
+    if (any) {
+      if (hook) return fail(h, UVS_ERR_UNSUPPORTED, "device-resident window: relocalisation factors are not supported");
+      expanded.assign(w, w + B);
+      reloc_store.resize(B);
+      for (int i = 0; i < B; i++) {
+        if (w[i].n_relo <= 0) continue;
+        const int rc = expand_relocalisation(w[i], reloc_store[i], expanded[i]);
+        if (rc == 1) return fail(h, UVS_ERR_INVALID_ARG, "relocalisation: null array / index out of range / not ascending in window " + std::to_string(i));
+        if (rc == 2) return fail(h, UVS_ERR_INVALID_ARG, "relocalisation: a matched point owns no projection factor in window " + std::to_string(i));
+        if (rc == 3) return fail(h, UVS_ERR_UNSUPPORTED, "relocalisation factors cannot be combined with estimate_td");
+        h->relo[i] = 1;
+      }
+      w = expanded.data();
+    }
+  }
   static const bool trace = std::getenv("UVS_TRACE") != nullptr;   // host-side phase timings on stderr (adds syncs)
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
@@ -584,9 +653,11 @@ int uvs_download_state(UvsHandle *h, int32_t B, UvsWindow *w) {
   const char *S = h->hscratch.base;
   for (int i = 0; i < B; i++) {
     UvsWindow &x = w[i];
-    if (x.n_frames != h->frame_off[i + 1] - h->frame_off[i] || x.n_points != h->point_off[i + 1] - h->point_off[i] ||
-        x.n_lines != h->line_off[i + 1] - h->line_off[i])
+    const int relo = (int)h->relo.size() > i ? h->relo[i] : 0;
+    if (x.n_frames + relo != h->frame_off[i + 1] - h->frame_off[i] || x.n_points != h->point_off[i + 1] - h->point_off[i] ||
+        x.n_lines != h->line_off[i + 1] - h->line_off[i] || (relo && !x.relo_pose))
       return fail(h, UVS_ERR_INVALID_ARG, "uvs_download_state: window sizes differ from the upload");
+    if (relo) std::memcpy(x.relo_pose, S + o_pose + (size_t)(h->frame_off[i] + x.n_frames) * 7 * Dd, 7 * Dd);
     std::memcpy(x.pose, S + o_pose + (size_t)h->frame_off[i] * 7 * Dd, x.n_frames * 7 * Dd);
     std::memcpy(x.speed_bias, S + o_sb + (size_t)h->frame_off[i] * 9 * Dd, x.n_frames * 9 * Dd);
     std::memcpy(x.ex_pose, S + o_ex + (size_t)i * 7 * Dd, 7 * Dd);
@@ -607,13 +678,18 @@ int uvs_upload_state(UvsHandle *h, int32_t B, const UvsWindow *w) {
   char *S = h->stage.base, *Dv = h->dev.base;
   for (int i = 0; i < B; i++) {
     const UvsWindow &x = w[i];
-    if (x.n_frames != h->frame_off[i + 1] - h->frame_off[i] || x.n_points != h->point_off[i + 1] - h->point_off[i] ||
+    const int relo = (int)h->relo.size() > i ? h->relo[i] : 0;
+    if (x.n_frames + relo != h->frame_off[i + 1] - h->frame_off[i] || x.n_points != h->point_off[i + 1] - h->point_off[i] ||
         x.n_lines != h->line_off[i + 1] - h->line_off[i])
       return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_state: window sizes differ from the upload");
-    if (!x.pose || !x.speed_bias || !x.ex_pose || (x.n_points && !x.inv_depth) || (x.n_lines && !x.ortho))
+    if (!x.pose || !x.speed_bias || !x.ex_pose || (x.n_points && !x.inv_depth) || (x.n_lines && !x.ortho) || (relo && !x.relo_pose))
       return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_state: null state pointer");
     std::memcpy(S + h->o_pose0 + (size_t)h->frame_off[i] * 7 * Dd, x.pose, x.n_frames * 7 * Dd);
     std::memcpy(S + h->in_sb + (size_t)h->frame_off[i] * 9 * Dd, x.speed_bias, x.n_frames * 9 * Dd);
+    if (relo) {
+      std::memcpy(S + h->o_pose0 + (size_t)(h->frame_off[i] + x.n_frames) * 7 * Dd, x.relo_pose, 7 * Dd);
+      std::memset(S + h->in_sb + (size_t)(h->frame_off[i] + x.n_frames) * 9 * Dd, 0, 9 * Dd);
+    }
     std::memcpy(S + h->in_ex + (size_t)i * 7 * Dd, x.ex_pose, 7 * Dd);
     if (x.td) std::memcpy(S + h->in_td + (size_t)i * Dd, x.td, Dd);
     if (x.n_points) std::memcpy(S + h->in_inv + (size_t)h->point_off[i] * Dd, x.inv_depth, x.n_points * Dd);

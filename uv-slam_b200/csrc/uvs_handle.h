@@ -78,6 +78,7 @@ struct UvsHandle {
   std::vector<int> frame_off, point_off, line_off, proj_off, lobs_off, vobs_off, imu_off, cam_off, prior_off, pblk_off;
   std::vector<long long> S_off, priorJ_off;
   std::vector<int> win_flags;
+  std::vector<int> relo;                      // per window: 1 = the last internal frame is the relocalisation pose (uvs.h, n_relo > 0)
   // offsets of the state sections inside the device arena (buffer 0) for download
   size_t o_pose0 = 0, o_state_bytes = 0;
   size_t in_sb = 0, in_ex = 0, in_td = 0, in_inv = 0, in_ortho = 0, in_ric = 0, in_tic = 0;   // input-region offsets (uvs_upload_state)

@@ -234,7 +234,10 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
   cudaStream_t st = h->stream;
   // host views of the caller's index arrays (the pinned staging buffer mirrors the device input region)
   auto host = [&](const void *devp) -> const char * { return h->stage.base + ((const char *)devp - h->dev.base); };
-  const int F = h->frame_off[wi + 1] - h->frame_off[wi];
+  // a relocalisation pose (uvs.h, n_relo > 0) is the last internal frame: the reference's marginalization knows neither the
+  // block nor its factors (estimator.cpp:1003-1228), so the plan runs over the window's own frames and skips those factors
+  const int Fint = h->frame_off[wi + 1] - h->frame_off[wi];
+  const int F = Fint - ((int)h->relo.size() > wi ? h->relo[wi] : 0);
   const int j0 = h->proj_off[wi], nproj = h->proj_off[wi + 1] - j0;
   const int a0 = h->lobs_off[wi], nlobs = h->lobs_off[wi + 1] - a0;
   const int v0 = h->vobs_off[wi], nvobs = h->vobs_off[wi + 1] - v0;
@@ -261,7 +264,7 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
     drop_pose = 0; drop_sb = 0;
     if (prior_n > 0) use_prior = true;
     for (int k = 0; k < nimu; k++) if (imf[k] == 0 && imdt[k] < 10.0) { sel_imu.push_back(k); has_pose[0] = has_sb[0] = 1; if (F > 1) has_pose[1] = has_sb[1] = 1; }
-    for (int k = 0; k < nproj; k++) if (pfi[k] == 0) { sel_proj.push_back(k); has_pose[0] = 1; has_pose[pfj[k]] = 1; has_ex = true; has_pt[ppt[k]] = 1; if (td) has_td = true; }
+    for (int k = 0; k < nproj; k++) if (pfi[k] == 0 && pfj[k] < F) { sel_proj.push_back(k); has_pose[0] = 1; has_pose[pfj[k]] = 1; has_ex = true; has_pt[ppt[k]] = 1; if (td) has_td = true; }
     std::vector<int> start(nl, 1 << 30);
     for (int k = 0; k < nlobs; k++) start[li[k]] = std::min(start[li[k]], lf[k]);
     for (int k = 0; k < nlobs; k++) if (start[li[k]] == 0 && lf[k] != 0) { sel_line.push_back(k); has_pose[lf[k]] = 1; has_ln[li[k]] = 1; }
@@ -349,7 +352,7 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
   const size_t obo = o; o += al((size_t)n * Dd);
   const size_t oJ = o; o += al((size_t)n * n * Dd);
   const size_t orr = o; o += al((size_t)n * Dd);
-  const size_t ocam = o; o += al((size_t)(16 * F + 8) * Dd);
+  const size_t ocam = o; o += al((size_t)(16 * Fint + 8) * Dd);
   const size_t ofac = o; o += al(std::max<size_t>(facs.size(), 1) * sizeof(MargFactor));
   const size_t ocm = o; o += al(prior_colmap.size() * sizeof(int));
   int rc = handle_ensure_scratch(h, o); if (rc) return rc;
@@ -379,7 +382,7 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return handle_fail(h, UVS_ERR_CUDA, std::string("uvs_marginalize kernels: ") + cudaGetErrorString(e));
-  CKM(cudaMemcpyAsync(hs + oAo, ds + oAo, ocam + al((size_t)(16 * F + 8) * Dd) - oAo, cudaMemcpyDeviceToHost, st));
+  CKM(cudaMemcpyAsync(hs + oAo, ds + oAo, ocam + al((size_t)(16 * Fint + 8) * Dd) - oAo, cudaMemcpyDeviceToHost, st));
   CKM(cudaStreamSynchronize(st));
 
   h->last_marg_J = (const double *)(ds + oJ); h->last_marg_r = (const double *)(ds + orr); h->last_marg_n = n;   // stays valid until the scratch arena is used again
@@ -396,9 +399,9 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
     int id = kept_id[k];
     const double *src; int gs;
     if (kind == UVS_BLOCK_POSE) { src = cam + 7 * id; gs = 7; }
-    else if (kind == UVS_BLOCK_SPEEDBIAS) { src = cam + 7 * F + 9 * id; gs = 9; }
-    else if (kind == UVS_BLOCK_EXPOSE) { src = cam + 16 * F; gs = 7; }
-    else { src = cam + 16 * F + 7; gs = 1; }
+    else if (kind == UVS_BLOCK_SPEEDBIAS) { src = cam + 7 * Fint + 9 * id; gs = 9; }
+    else if (kind == UVS_BLOCK_EXPOSE) { src = cam + 16 * Fint; gs = 7; }
+    else { src = cam + 16 * Fint + 7; gs = 1; }
     if (kind <= UVS_BLOCK_SPEEDBIAS) {
       if (flag == UVS_MARGIN_OLD) id -= 1;
       else if (id == F - 1) id -= 1;

@@ -75,6 +75,11 @@ void GpuWindowProblem::addVP(int fj, int k, const double vp[3]) {
   n_lines_ = std::max(n_lines_, k + 1);
 }
 
+void GpuWindowProblem::addRelocalization(int k, const double pts_j[3]) {
+  r_pt_.push_back(k);
+  r_pj_.insert(r_pj_.end(), pts_j, pts_j + 3);
+}
+
 UvsWindow GpuWindowProblem::view() {
   UvsWindow w{};
   w.n_frames = n_frames_; w.n_points = n_points_; w.n_lines = n_lines_;
@@ -93,6 +98,9 @@ UvsWindow GpuWindowProblem::view() {
     w.prior_n = prior_.n; w.prior_n_blocks = (int32_t)prior_.block_kind.size();
     w.prior_J = prior_.J.data(); w.prior_r = prior_.r.data(); w.prior_block_kind = prior_.block_kind.data();
     w.prior_block_id = prior_.block_id.data(); w.prior_x0 = prior_.x0.data();
+  }
+  if (relo_pose_ && !r_pt_.empty()) {
+    w.n_relo = (int32_t)r_pt_.size(); w.relo_pose = relo_pose_; w.relo_point = r_pt_.data(); w.relo_pts_j = r_pj_.data();
   }
   return w;
 }

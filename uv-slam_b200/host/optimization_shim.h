@@ -41,6 +41,11 @@ class GpuWindowProblem {
                        const double vel_j[2], double td_i, double td_j, double row_i, double row_j);              // :846-855
   void addLine(int frame_j, int line_index, const double sp[2], const double ep[2]);                              // :916-918
   void addVP(int frame_j, int line_index, const double vp[3]);                                                    // :920-925
+  // relocalisation (estimator.cpp:944-978): relo_Pose becomes a parameter block of this solve (updated in place), one factor
+  // per matched feature on {para_Pose[start], relo_Pose, para_Ex_Pose[0], para_Feature[feature_index]}; pts_i is taken from
+  // the feature's own factors.  Add the matches in ascending feature_index (the order of the reference's loop).
+  void setRelocalization(double relo_Pose[7]) { relo_pose_ = relo_Pose; }
+  void addRelocalization(int feature_index, const double pts_j[3]);
 
   ~GpuWindowProblem();
   GpuWindowProblem(const GpuWindowProblem &) = delete;
@@ -70,6 +75,9 @@ class GpuWindowProblem {
   std::vector<int32_t> p_fi_, p_fj_, p_pt_, l_fr_, l_idx_, v_fr_, v_idx_, i_fr_;
   std::vector<double> p_pi_, p_pj_, p_vi_, p_vj_, p_tdi_, p_tdj_, p_rwi_, p_rwj_, l_sp_, l_ep_, v_dir_;
   std::vector<double> i_dp_, i_dq_, i_dv_, i_dt_, i_ba_, i_bg_, i_jac_, i_cov_;
+  double *relo_pose_ = nullptr;
+  std::vector<int32_t> r_pt_;
+  std::vector<double> r_pj_;
   std::string err_;
   UvsHandle *h_ = nullptr;   // this problem's own device batch: nothing another object uploads can get between solve() and marginalize()
   UvsHandle *handle();

@@ -38,6 +38,7 @@ static_assert(
 int save_window(const UvsWindow &w, const char *path) {
   if (!path) return UVS_ERR_INVALID_ARG;
   // the same size / consistency checks as uvs_upload_windows, before anything is written
+  if (w.n_relo < 0 || (w.n_relo > 0 && (!w.relo_pose || !w.relo_point || !w.relo_pts_j))) return UVS_ERR_INVALID_ARG;
   if (w.n_frames < 1 || w.n_points < 0 || w.n_lines < 0 || w.n_proj < 0 || w.n_line_obs < 0 || w.n_vp_obs < 0 || w.n_imu < 0 ||
       w.prior_n < 0 || w.prior_n_blocks < 0)
     return UVS_ERR_INVALID_ARG;
@@ -85,6 +86,9 @@ int save_window(const UvsWindow &w, const char *path) {
   o.array(w.proj_frame_i, {np}); o.array(w.proj_frame_j, {np}); o.array(w.proj_point, {np});
   o.array(w.line_frame, {nl}); o.array(w.line_idx, {nl}); o.array(w.vp_frame, {nv}); o.array(w.vp_line, {nv});
   o.array(w.imu_frame_i, {ni}); o.array(w.prior_block_kind, {pb}); o.array(w.prior_block_id, {pb});
+  if (w.n_relo > 0) {   // optional relocalisation section (window.py:_RELO_F64 / _RELO_I32)
+    o.array(w.relo_pose, {7}); o.array(w.relo_pts_j, {w.n_relo, 3}); o.array(w.relo_point, {w.n_relo});
+  }
   const bool closed = std::fclose(f) == 0;
   return (o.ok && closed) ? UVS_OK : UVS_ERR_UNSUPPORTED;
 }

@@ -42,6 +42,8 @@ class UvsWindowStruct(C.Structure):
                                      "imu_lin_bg", "imu_jacobian", "imu_covariance")]
         + [("prior_J", c_double_p), ("prior_r", c_double_p), ("prior_block_kind", c_int32_p),
            ("prior_block_id", c_int32_p), ("prior_x0", c_double_p)]
+        + [("n_relo", C.c_int32), ("reserved1", C.c_int32), ("relo_pose", c_double_p), ("relo_point", c_int32_p),
+           ("relo_pts_j", c_double_p)]
     )
 
 
@@ -103,6 +105,9 @@ _F64 = ("pose", "speed_bias", "ex_pose", "td", "inv_depth", "ortho", "proj_pts_i
         "imu_lin_bg", "imu_jacobian", "imu_covariance", "prior_J", "prior_r", "prior_x0")
 _I32 = ("proj_frame_i", "proj_frame_j", "proj_point", "line_frame", "line_idx", "vp_frame", "vp_line",
         "imu_frame_i", "prior_block_kind", "prior_block_id")
+# optional relocalisation section (estimator.cpp:944-978), written after the arrays above only when n_relo > 0
+_RELO_F64 = ("relo_pose", "relo_pts_j")
+_RELO_I32 = ("relo_point",)
 _MAGIC = b"UVSWIN01"
 
 
@@ -153,6 +158,9 @@ class Window:
     prior_block_kind: np.ndarray = field(default_factory=lambda: _z(0, np.int32))
     prior_block_id: np.ndarray = field(default_factory=lambda: _z(0, np.int32))
     prior_x0: np.ndarray = field(default_factory=lambda: _z(0))
+    relo_pose: np.ndarray = field(default_factory=lambda: _z(0))          # [7] with relocalisation factors, else empty
+    relo_pts_j: np.ndarray = field(default_factory=lambda: _z((0, 3)))
+    relo_point: np.ndarray = field(default_factory=lambda: _z(0, np.int32))
     estimate_extrinsic: int = 0
     estimate_td: int = 0
 
@@ -160,9 +168,9 @@ class Window:
         self.normalize()
 
     def normalize(self):
-        for n in _F64:
+        for n in _F64 + _RELO_F64:
             setattr(self, n, np.ascontiguousarray(getattr(self, n), dtype=np.float64))
-        for n in _I32:
+        for n in _I32 + _RELO_I32:
             setattr(self, n, np.ascontiguousarray(getattr(self, n), dtype=np.int32))
         return self
 
@@ -186,12 +194,14 @@ class Window:
     @property
     def prior_n_blocks(self): return int(self.prior_block_kind.shape[0])
     @property
+    def n_relo(self): return int(self.relo_point.shape[0])
+    @property
     def cam_dim(self): return 15 * self.n_frames + (6 if self.estimate_extrinsic else 0) + (1 if self.estimate_td else 0)
     @property
     def tangent_dim(self): return self.cam_dim + self.n_points + 4 * self.n_lines
 
     def copy(self) -> "Window":
-        kw = {n: getattr(self, n).copy() for n in _F64 + _I32}
+        kw = {n: getattr(self, n).copy() for n in _F64 + _I32 + _RELO_F64 + _RELO_I32}
         return Window(estimate_extrinsic=self.estimate_extrinsic, estimate_td=self.estimate_td, **kw)
 
     def state_vector(self) -> np.ndarray:
@@ -204,12 +214,14 @@ class Window:
         self.normalize()
         s = UvsWindowStruct()
         for n in ("n_frames", "n_points", "n_lines", "n_proj", "n_line_obs", "n_vp_obs", "n_imu", "prior_n",
-                  "prior_n_blocks", "estimate_extrinsic", "estimate_td"):
+                  "prior_n_blocks", "estimate_extrinsic", "estimate_td", "n_relo"):
             setattr(s, n, int(getattr(self, n)))
-        for n in _F64:
+        if self.n_relo and self.relo_pose.size != 7:
+            raise ValueError("relocalisation factors need relo_pose[7]")
+        for n in _F64 + _RELO_F64:
             a = getattr(self, n)
             setattr(s, n, a.ctypes.data_as(c_double_p) if a.size else C.cast(None, c_double_p))
-        for n in _I32:
+        for n in _I32 + _RELO_I32:
             a = getattr(self, n)
             setattr(s, n, a.ctypes.data_as(c_int32_p) if a.size else C.cast(None, c_int32_p))
         if self.estimate_td and self.proj_vel_i.shape[0] != self.n_proj:
@@ -227,6 +239,12 @@ class Window:
             out.write(struct.pack("<i", a.ndim))
             out.write(struct.pack("<%di" % a.ndim, *a.shape))
             out.write(a.astype("<f8" if n in _F64 else "<i4").tobytes())
+        if self.n_relo:
+            for n in _RELO_F64 + _RELO_I32:
+                a = getattr(self, n)
+                out.write(struct.pack("<i", a.ndim))
+                out.write(struct.pack("<%di" % a.ndim, *a.shape))
+                out.write(a.astype("<f8" if n in _RELO_F64 else "<i4").tobytes())
         return out.getvalue()
 
     @staticmethod
@@ -236,13 +254,15 @@ class Window:
         off = 8
         ee, et = struct.unpack_from("<2i", buf, off); off += 8
         kw = {}
-        for n in _F64 + _I32:
+        for n in _F64 + _I32 + _RELO_F64 + _RELO_I32:
+            if off >= len(buf):
+                break           # no relocalisation section
             (nd,) = struct.unpack_from("<i", buf, off); off += 4
             shape = struct.unpack_from("<%di" % nd, buf, off); off += 4 * nd
             cnt = int(np.prod(shape)) if nd else 1
-            dt = "<f8" if n in _F64 else "<i4"
-            kw[n] = np.frombuffer(buf, dtype=dt, count=cnt, offset=off).reshape(shape).copy()
-            off += cnt * (8 if n in _F64 else 4)
+            f64 = n in _F64 or n in _RELO_F64
+            kw[n] = np.frombuffer(buf, dtype="<f8" if f64 else "<i4", count=cnt, offset=off).reshape(shape).copy()
+            off += cnt * (8 if f64 else 4)
         return Window(estimate_extrinsic=ee, estimate_td=et, **kw)
 
     def save(self, path):
