@@ -362,6 +362,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   const size_t w_ft0 = wk.take((size_t)nF * 48 * Dd), w_ft1 = wk.take((size_t)nF * 48 * Dd), w_ls0 = wk.take((size_t)nL * 8 * Dd), w_ls1 = wk.take((size_t)nL * 8 * Dd);
   const size_t w_icomp = wk.take((size_t)nImu * 108 * Dd);
   const size_t w_clw = wk.take(h->use_build3 ? (size_t)B * chol_chain_lw_doubles(max_frames) * Dd : 0);
+  const size_t w_cfrag = wk.take(max_d > h->packed_limit ? (size_t)B * chol_frag_doubles(max_d) * Dd : 0);
   const size_t w_sqi = wk.take((size_t)nImu * 225 * Dd), w_prH = wk.take((size_t)nPJ * Dd), w_err = wk.take(I);
   const size_t w_rp = wk.take((size_t)nProj * 48 * Dd), w_rl = wk.take((size_t)nLobs * 24 * Dd), w_rv = wk.take((size_t)nVobs * 12 * Dd),
                w_ri = wk.take((size_t)nImu * REC_IMU * Dd), w_rpr = wk.take(nPriorR * Dd);
@@ -555,7 +556,8 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   D.pt_begin = WI(w_ptb); D.ln_begin = WI(w_lnb); D.pt_end = WI(w_pte); D.ln_end = WI(w_lne); D.pt_win = WI(w_ptw); D.ln_win = WI(w_lnw);
   D.pt_order = WI(w_pto); D.fr_win = PI(o_frwin); D.pw_off = PI(o_pwoff); D.nPW = nPW;
   D.ftab[0] = WD(w_ft0); D.ftab[1] = WD(w_ft1); D.lsc[0] = WD(w_ls0); D.lsc[1] = WD(w_ls1);
-  D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.chain_lw = WD(w_clw); D.chain_lw_stride = chol_chain_lw_doubles(max_frames); D.prior_H = WD(w_prH); D.err = WI(w_err);
+  D.imu_sqrt_info = WD(w_sqi); D.imu_comp = WD(w_icomp); D.chain_lw = WD(w_clw); D.chain_lw_stride = chol_chain_lw_doubles(max_frames);
+  D.chol_frag = WD(w_cfrag); D.chol_frag_stride = chol_frag_doubles(max_d); D.prior_H = WD(w_prH); D.err = WI(w_err);
   D.rec_proj = WD(w_rp); D.rec_line = WD(w_rl); D.rec_vp = WD(w_rv); D.rec_imu = WD(w_ri); D.rec_prior = WD(w_rpr);
   D.scale_cam = WD(w_scc); D.scale_pt = WD(w_scp); D.scale_ln = WD(w_scl);
   D.Smat = WD(w_S); D.gS = WD(w_gS); D.gfull = WD(w_gf); D.colsq_cam = WD(w_csq);

@@ -82,6 +82,7 @@ int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool
 // chain mode (uvs_solve.cu): speed-bias blocks eliminated one by one, dense tensor-core Cholesky of the rest
 size_t chol_chain_smem(int max_frames, bool any_ex);
 int chol_chain_lw_doubles(int max_frames);
+long long chol_frag_doubles(int d);   // doubles of global scratch per window of the large-window reduced solve
 int launch_chol_chain(const Dev &D, const Params &P, int max_frames, bool any_ex, bool mc_identity, cudaStream_t st);
 int launch_step(const Dev &D, const Params &P, bool clear_system, cudaStream_t st);
 int launch_finish(const Dev &D, cudaStream_t st);

@@ -1102,50 +1102,39 @@ __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, 
     CHOL_TS(4);
     CHOL_TS(5);
   } else {
-    // ---- large windows: in place in global memory (mirror the upper triangle into the lower one),
-    //      unblocked right-looking Cholesky
-    vec = D.delta_cam + co;
-    for (int e = tid; e < d * d; e += nthr) {
-      const int i = e / d, j = e - i * d;   // lower entry (i, j), j <= i
-      if (j > i) continue;
-      double v = scale[i] * scale[j] * Sg[(size_t)j * d + i];
-      if (i == j) { const double h = scale[i] * scale[i] * colsq[i]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
-      Sg[e] = v;
-    }
-    for (int c = tid; c < d; c += nthr) vec[c] = -scale[c] * gS[c];
-    __syncthreads();
-    const int ti = tid >> 4, tk = tid & 15;
-    bool fail = false;
-    for (int j = 0; j < d; j++) {
-      const double piv = Sg[(size_t)j * d + j];
-      if (!(piv > 0.0) || !isfinite(piv)) { fail = true; break; }
-      const double inv = 1.0 / sqrt(piv);
-      __syncthreads();
-      for (int i = j + 1 + tid; i < d; i += nthr) Sg[(size_t)i * d + j] *= inv;
-      if (tid == 0) { vec[j] *= inv; Sg[(size_t)j * d + j] = piv * inv; }
-      __syncthreads();
-      const double zj = vec[j];
-      for (int i = j + 1 + tid; i < d; i += nthr) vec[i] -= Sg[(size_t)i * d + j] * zj;
-      for (int i = j + 1 + ti; i < d; i += nthr / 16) {
-        const double lij = Sg[(size_t)i * d + j];
-        for (int k = j + 1 + tk; k <= i; k += 16) Sg[(size_t)i * d + k] -= lij * Sg[(size_t)k * d + j];
+    // ---- large windows (d > packed limit, e.g. the 31-frame stress window, d = 465): the same blocked tensor-core
+    //      Cholesky, with the fragment-order factor in a per-window GLOBAL scratch (D.chol_frag) instead of shared memory.
+    //      Every operand of the trailing update is still one contiguous 256-byte read per warp (now a coalesced global
+    //      load; the current panel - d x 8 doubles - stays in L1), the C tiles are read-modify-written in L2 / HBM:
+    //      ~d^3 / 24 x 16 bytes per factorisation.  Visibility between the phases is the CTA barrier (global accesses of a
+    //      CTA are ordered by __syncthreads).  The pair table lives in dynamic shared memory behind the prior column map.
+    const CholLayout Lo = chol_layout(d);
+    const int K = Lo.K;
+    double *A = D.chol_frag + (size_t)w * D.chol_frag_stride;
+    double *Dg = A + Lo.dbase, *bz = A + Lo.vbase, *invd_all = bz + (size_t)K * NB;
+    unsigned short *pairs = reinterpret_cast<unsigned short *>(smem) + MAX_PRIOR_COLS * 2;   // after the 2 KB column map
+    vec = bz;
+    const int warp = tid >> 5, lane = tid & 31;
+    auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
+    auto slot = [&](int i, int j) -> double * {   // element (i, j), j <= i, of the lower matrix
+      const int I = i >> 3, r = i & 7;
+      return (j >> 3) == I ? Dg + 36 * I + r * (r + 1) / 2 + (j & 7) : A + (size_t)32 * I * (I - 1) + (j >> 2) * 4 * rows_of(I) + 4 * r + (j & 3);
+    };
+    for (int j = warp; j < d; j += nthr / 32) {
+      const double *src = Sg + (size_t)j * d;
+      const double sj = scale[j];
+      for (int i = j + lane; i < d; i += 32) {
+        double v = scale[i] * sj * src[i];
+        if (i == j) { const double h = sj * sj * colsq[j]; v += clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; }
+        *slot(i, j) = v;
       }
-      __syncthreads();
     }
-    if (fail) {
+    for (int c = tid; c < K * NB; c += nthr) { bz[c] = c < d ? -scale[c] * gS[c] : 0.0; invd_all[c] = 1.0; }
+    __syncthreads();
+    if (!blocked_chol_solve(A, Lo, nthr, pairs, s_flag)) {
       if (tid == 0) { acc[ACC_FAIL] += 1.0; ctl.state &= ~WS_STEP_OK; ctl.have_scale = 1; }
       return;
     }
-    if (tid < 32) {
-      for (int j = d - 1; j >= 0; j--) {
-        const double yj = vec[j] / Sg[(size_t)j * d + j];
-        __syncwarp();
-        for (int i = tid; i < j; i += 32) vec[i] -= Sg[(size_t)j * d + i] * yj;
-        if (tid == 0) vec[j] = yj;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
   }
 
   // ---- delta = s .* y, candidate camera state, step / state norms
@@ -1390,6 +1379,9 @@ size_t chol_chain_smem(int max_frames, bool any_ex) {
   return (size_t)std::max(chain_layout(nd, max_frames).total, chain_layout_v1(nd, max_frames).total) * sizeof(double);
 }
 int chol_chain_lw_doubles(int max_frames) { return max_frames * CH_LWG; }
+long long chol_frag_doubles(int d) { return ((long long)chol_layout(d).total + 1) & ~1LL; }
+// dynamic shared memory of the large-window mode: prior column map + pair table of the K (K + 1) / 2 lower blocks
+static size_t chol_large_smem(int d) { const size_t K = (d + NB - 1) / NB; return (size_t)MAX_PRIOR_COLS * sizeof(int) + K * (K + 1) / 2 * sizeof(unsigned short) + 16; }
 
 // Two variants of the chain solve.  Measured (us per LM iteration, B windows; gpurun_out/c*_scan): pipeline 92 / 95 / 107 /
 // 178 / 392 against barrier-phased 107 / 109 / 108 / 119 / 161 at B = 1 / 16 / 64 / 148 / 592.  The pipeline has the shorter
@@ -1414,7 +1406,13 @@ int launch_chol_chain(const Dev &D, const Params &P, int max_frames, bool any_ex
 }
 
 int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool mc_identity, cudaStream_t st) {
-  const int dd = max_d <= packed_limit ? max_d : packed_limit;
+  if (max_d > packed_limit) {
+    // a batch with a window too large for shared memory: every window takes the global-scratch mode (little shared memory,
+    // several windows per SM)
+    k_chol<<<D.B, CT, chol_large_smem(max_d), st>>>(D, P, 0, mc_identity ? 1 : 0);
+    return 1;
+  }
+  const int dd = max_d;
   const size_t smem = chol_smem_bytes(dd);
   // two windows per SM when two factors fit its shared memory (d <= 165): 256 threads each, else one window with 512
   static int sm_smem = 0, static_smem = 0;
@@ -1425,7 +1423,7 @@ int launch_chol(const Dev &D, const Params &P, int max_d, int packed_limit, bool
     cudaFuncAttributes attr;
     if (cudaFuncGetAttributes(&attr, k_chol) == cudaSuccess) static_smem = (int)attr.sharedSizeBytes;
   }
-  const bool two = 2 * (smem + static_smem + 1024) <= (size_t)sm_smem && max_d <= packed_limit;
+  const bool two = 2 * (smem + static_smem + 1024) <= (size_t)sm_smem;
   static const int t2 = std::getenv("UVS_CHOL_T2") ? std::atoi(std::getenv("UVS_CHOL_T2")) : CT;   // tuning knob (64 registers per thread: two 512-thread CTAs fit)
   k_chol<<<D.B, two ? t2 : CT, smem, st>>>(D, P, packed_limit, mc_identity ? 1 : 0);
   return 1;
