@@ -115,12 +115,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+SWEEP_SOURCES = ("uvs_sweep.cu", "uvs_factors.cuh", "uvs_imu.cuh", "uvs_linefast.cuh", "uvs_math.cuh", "uvs_device.cuh")
+
+
 def sources_sha():
-    """sha256 over the kernel sources: ties a committed ncu profile to the source state it was taken at"""
+    """sha256 over the sources of the materialised sweep kernels: ties the committed ncu profile (profiles/r2_sweep_ncu.json,
+    written by tools/ncu_summary.py --sweep) to the source state it was taken at"""
     import hashlib
     h = hashlib.sha256()
-    for p in sorted(glob.glob(os.path.join(ROOT, "uv-slam_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "uv-slam_b200", "csrc", "*.h"))):
-        h.update(open(p, "rb").read())
+    for name in SWEEP_SOURCES:
+        h.update(open(os.path.join(ROOT, "uv-slam_b200", "csrc", name), "rb").read())
     return h.hexdigest()[:16]
 
 

@@ -66,7 +66,11 @@ def main():
            "note": "per launch; dram write bytes under-count what a kernel produces because dirty lines still sit in the 126 MB L2 when it ends",
            "kernels": kernels}
     if "--sweep" in sys.argv:
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
         doc["jacobian_sweep_dram_bytes"] = sweep
+        doc["kernel_sources_sha"] = bench.sources_sha()   # bench.py refuses the file when the sweep sources have changed since
     json.dump(doc, open(out, "w"), indent=1)
     print("wrote %s: %d kernels" % (out, len(kernels)))
 

@@ -360,7 +360,7 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
   const size_t w_pte = wk.take(nP * I), w_lne = wk.take(nL * I), w_ptw = wk.take(nP * I), w_lnw = wk.take(nL * I);
   const size_t w_pto = wk.take((size_t)nPW * 32 * I), w_ptk = wk.take(nP * I);
   const size_t w_ft0 = wk.take((size_t)nF * 48 * Dd), w_ft1 = wk.take((size_t)nF * 48 * Dd), w_ls0 = wk.take((size_t)nL * 8 * Dd), w_ls1 = wk.take((size_t)nL * 8 * Dd);
-  const size_t w_icomp = wk.take((size_t)nImu * 108 * Dd);
+  const size_t w_icomp = wk.take((size_t)nImu * (108 + 16) * Dd);   // compact Jacobian blocks + unweighted residual (uvs_sweep.cu IMU_CS)
   const size_t w_clw = wk.take(h->use_build3 ? (size_t)B * chol_chain_lw_doubles(max_frames) * Dd : 0);
   const size_t w_cfrag = wk.take(max_d > h->packed_limit ? (size_t)B * chol_frag_doubles(max_d) * Dd : 0);
   const size_t w_sqi = wk.take((size_t)nImu * 225 * Dd), w_prH = wk.take((size_t)nPJ * Dd), w_err = wk.take(I);

@@ -893,8 +893,12 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
 
   {
     const int np = D.point_off[w + 1] - D.point_off[w], nl = D.line_off[w + 1] - D.line_off[w];
-    const int ncols = np + 4 * nl, nchunks = (ncols + CH - 1) / CH;
-    const double *Yw = S.Y + colbase(D, w) * mp;
+    // small batches split a window's columns over gridDim.y CTAs (every CTA adds its partial update with reductions anyway)
+    const int ncols_all = np + 4 * nl, nchunks_all = (ncols_all + CH - 1) / CH;
+    const int cper = (nchunks_all + (int)gridDim.y - 1) / (int)gridDim.y, cbeg = (int)blockIdx.y * cper;
+    if (cbeg >= nchunks_all) return;
+    const int ncols = min(ncols_all - cbeg * CH, cper * CH), nchunks = (ncols + CH - 1) / CH;
+    const double *Yw = S.Y + (colbase(D, w) + (size_t)cbeg * CH) * mp;
     auto issue = [&](int c) {   // one elected thread: arm the barrier with the byte count, start the bulk copy
       const int c0 = c * CH, c1 = min(ncols, c0 + CH);
       const unsigned bytes = (unsigned)((c1 - c0) * mp * sizeof(double));
@@ -998,7 +1002,7 @@ __global__ void __launch_bounds__(WT) k_window_system(Dev D, Stash S, int max_pr
 constexpr int TT = 256;       // threads of k_window_tail
 constexpr int IMU_G = 4;      // IMU records staged per pass (15 KB: ten or more CTAs per SM)
 
-__global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
+__global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n, int ni) {
   extern __shared__ __align__(16) double sm[];
   const int w = blockIdx.x;
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
@@ -1006,8 +1010,11 @@ __global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
   const int fo = D.frame_off[w];
   const int co = D.cam_off[w], d = D.cam_off[w + 1] - co;
   double *Sg = D.Smat + D.S_off[w];
-  const int f0 = D.imu_off[w], nf = blockIdx.y == 0 ? D.imu_off[w + 1] - f0 : 0;   // blockIdx.y: 0 = IMU factors, 1 = prior
-  for (int g0 = 0; g0 < nf; g0 += IMU_G) {
+  // blockIdx.y: parts 0 .. ni-1 take the IMU factors (groups of IMU_G, round robin), the remaining np parts slices of the prior
+  // (large batches: ni = np = 1; a handful of windows: several CTAs per window)
+  const int part = blockIdx.y, np = (int)gridDim.y - ni;
+  const int f0 = D.imu_off[w], nf = part < ni ? D.imu_off[w + 1] - f0 : 0;
+  for (int g0 = part * IMU_G; g0 < nf; g0 += ni * IMU_G) {
     const int ng = min(IMU_G, nf - g0);
     const double *R = D.rec_imu + (size_t)(f0 + g0) * REC_IMU;
     for (int e = tid; e < ng * REC_IMU; e += TT) cp_async8(sm + e, R + e);
@@ -1065,8 +1072,9 @@ __global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
     __syncthreads();
   }
   // prior: H += J0^T J0 (precomputed at upload), g += J0^T r
-  const int n = blockIdx.y == 1 ? D.prior_off[w + 1] - D.prior_off[w] : 0;
+  const int n = part >= ni ? D.prior_off[w + 1] - D.prior_off[w] : 0;
   if (n > 0) {
+    const int sl = part - ni;   // slice of the prior
     int *cmap = reinterpret_cast<int *>(sm);
     for (int c = tid; c < n; c += TT) cmap[c] = -1;
     __syncthreads();
@@ -1077,7 +1085,7 @@ __global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
     }
     __syncthreads();
     const double *H = D.prior_H + D.priorJ_off[w], *J0 = D.prior_J + D.priorJ_off[w], *r = D.rec_prior + D.prior_off[w];
-    for (int e0 = tid; e0 < n * n; e0 += 4 * TT) {   // four loads in flight, then the four reductions
+    for (int e0 = sl * 4 * TT + tid; e0 < n * n; e0 += np * 4 * TT) {   // four loads in flight, then the four reductions
       double hv[4];
       int at[4];
 #pragma unroll
@@ -1102,18 +1110,19 @@ __global__ void __launch_bounds__(TT) k_window_tail(Dev D, int max_prior_n) {
       const int cp = cmap[p];
       if (cp < 0) continue;
       double g4[4] = {0, 0, 0, 0};
-      int i = part;
-      for (; i + 7 * NP < n; i += 8 * NP) {
+      const int RS = NP * np;   // row stride: NP parts in this CTA x np slices
+      int i = sl * NP + part;
+      for (; i + 7 * RS < n; i += 8 * RS) {
         double v8[8];
 #pragma unroll
-        for (int v = 0; v < 8; v++) v8[v] = __ldg(J0 + (size_t)(i + v * NP) * n + p);
+        for (int v = 0; v < 8; v++) v8[v] = __ldg(J0 + (size_t)(i + v * RS) * n + p);
 #pragma unroll
-        for (int v = 0; v < 8; v++) g4[v & 3] += v8[v] * r[i + v * NP];
+        for (int v = 0; v < 8; v++) g4[v & 3] += v8[v] * r[i + v * RS];
       }
-      for (; i < n; i += NP) g4[0] += __ldg(J0 + (size_t)i * n + p) * r[i];
+      for (; i < n; i += RS) g4[0] += __ldg(J0 + (size_t)i * n + p) * r[i];
       const double gg = (g4[0] + g4[1]) + (g4[2] + g4[3]);
       atomicAdd(D.gfull + co + cp, gg); atomicAdd(D.gS + co + cp, gg);
-      if (part == 0) atomicAdd(D.colsq_cam + co + cp, __ldg(H + (size_t)p * n + p));
+      if (part == 0 && sl == 0) atomicAdd(D.colsq_cam + co + cp, __ldg(H + (size_t)p * n + p));
     }
   }
 }
@@ -1173,6 +1182,10 @@ size_t build3_smem(int max_frames, bool any_ex, int max_prior_n) {
   return ((size_t)NSTAGE * CH * mp + YSLACK) * sizeof(double) + (size_t)(max_prior_n + 2) * sizeof(int);
 }
 
+// CTAs per window of the per-window kernels: one for batches that fill the GPU, several for a handful of windows (the
+// reference's use is ONE window per frame: a single CTA would stream all its landmark columns on one SM)
+static int window_split(int B) { return B >= 74 ? 1 : std::min(8, cdiv3(148, 2 * B)); }
+
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
                   cudaStream_t st, const Fork *fk) {
   Build3Ctx c; make_ctx(base, lay, c);
@@ -1194,14 +1207,14 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
   n++;
   if (D.nranks <= 1 || D.rank == 0) {   // factor-parallel mode: IMU factors and the prior belong to rank 0
     const size_t tsm = std::max((size_t)IMU_G * REC_IMU * sizeof(double), (size_t)(max_prior_n + 2) * sizeof(int));
-    k_window_tail<<<dim3(D.B, 2), TT, tsm, s_tail>>>(D, max_prior_n);
+    { const int ws = window_split(D.B), ni = ws > 1 ? 3 : 1, np = ws > 1 ? 4 : 1; k_window_tail<<<dim3(D.B, ni + np), TT, tsm, s_tail>>>(D, max_prior_n, ni); }
     n++;
   }
   if (fk) join_to(fk, st, 0);
   const size_t smem = build3_smem(max_frames, any_ex, max_prior_n);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
-  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
+  k_window_system<<<dim3(D.B, window_split(D.B)), WT, smem, st>>>(D, c.S, max_prior_n);
   n++;
   if (fk) { join_to(fk, st, 1); join_to(fk, st, 2); }
   return n;
@@ -1223,14 +1236,14 @@ int launch_build3_fused(const Dev &D, const Params &P, char *base, const Build3L
   n += launch_lin_lines(D, P, base, lay, max_frames, max_lines, s_lines);
   if (D.nranks <= 1 || D.rank == 0) {   // factor-parallel mode: IMU factors and the prior belong to rank 0
     const size_t tsm = std::max((size_t)IMU_G * REC_IMU * sizeof(double), (size_t)(max_prior_n + 2) * sizeof(int));
-    k_window_tail<<<dim3(D.B, 2), TT, tsm, s_tail>>>(D, max_prior_n);
+    { const int ws = window_split(D.B), ni = ws > 1 ? 3 : 1, np = ws > 1 ? 4 : 1; k_window_tail<<<dim3(D.B, ni + np), TT, tsm, s_tail>>>(D, max_prior_n, ni); }
     n++;
   }
   if (fk) join_to(fk, st, 0);
   const size_t smem = build3_smem(max_frames, false, max_prior_n);
   static size_t raised = 0;
   if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
-  k_window_system<<<D.B, WT, smem, st>>>(D, c.S, max_prior_n);
+  k_window_system<<<dim3(D.B, window_split(D.B)), WT, smem, st>>>(D, c.S, max_prior_n);
   n++;
   if (fk) join_to(fk, st, 1);
   return n;

@@ -111,7 +111,7 @@ struct Dev {
   long long chain_lw_stride;
   double *chol_frag;        // [B][chol_frag_stride] fragment-order factor of the large-window reduced solve (d > packed limit, k_chol mode 0)
   long long chol_frag_stride;
-  double *imu_comp;         // [IMU_COMP = 108][nImu] compact blocks of the unweighted IMU Jacobians (k_imu_geom -> k_imu_weight)
+  double *imu_comp;         // [IMU_COMP + 15 = 123][nImu] compact blocks of the unweighted IMU Jacobians + unweighted residual (k_imu_geom -> k_imu_weight)
   double *prior_H;          // [sum n^2]  J0^T J0 (constant during a solve)
   int *err;                 // [1] validation flag
   // records

@@ -15,6 +15,7 @@
 // observations are read once; state blocks (a few KB per window) come through L1/L2; every CTA
 // stages its tile of records in shared memory and writes it back as one contiguous, fully
 // coalesced chunk.
+#include <algorithm>
 #include <cstdlib>
 
 #include "uvs_device.cuh"
@@ -381,76 +382,123 @@ __global__ void __launch_bounds__(GT_IMU) k_imu_geom(Dev D, Params P, int mode, 
     in.sqrt_info = D.imu_sqrt_info + 225 * (size_t)f;
     double raw[15];
     imu_geometry<kJac>(in, P.g, raw, D.imu_comp + f, D.nImu);
-    const double *SI = in.sqrt_info;
-    double *rdst = kJac ? out + (size_t)f * REC_IMU : (res_out ? res_out + 15 * (size_t)f : nullptr);
-    double s = 0.0;
+    if (kJac) {
+      // Jacobian mode: the unweighted residual rides to k_imu_weight as a 31st column of the unweighted Jacobian, so the
+      // sqrt_info product of residual and Jacobian is ONE tensor-core product there (and this thread never reads sqrt_info)
 #pragma unroll
-    for (int i = 0; i < 15; i++) {
-      double r = 0.0;
+      for (int i = 0; i < 15; i++) D.imu_comp[(size_t)(IMU_COMP + i) * D.nImu + f] = raw[i];
+    } else {
+      const double *SI = in.sqrt_info;
+      double *rdst = res_out ? res_out + 15 * (size_t)f : nullptr;
+      double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < 15; k++) if (k >= i) r += __ldg(SI + i * 15 + k) * raw[k];
-      if (rdst) rdst[i] = r;
-      s += r * r;
+      for (int i = 0; i < 15; i++) {
+        double r = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; k++) if (k >= i) r += __ldg(SI + i * 15 + k) * raw[k];
+        if (rdst) rdst[i] = r;
+        s += r * r;
+      }
+      half = 0.5 * s;
     }
-    half = 0.5 * s;
   }
-  if (cost) add_window_scalar(cost, cost_stride, ix.y, half, valid);
+  if (!kJac && cost) add_window_scalar(cost, cost_stride, ix.y, half, valid);
 }
 
-__global__ void __launch_bounds__(32 * IMU_WPC) k_imu_weight(Dev D, int mode, double *__restrict__ out) {
+// [r | J] = sqrt_info x [raw | J_raw]: a CTA takes IMU_WPC consecutive factors at a time (their compact blocks are
+// IMU_WPC consecutive doubles of every row of imu_comp = one 32-byte sector, loaded cooperatively), a warp per factor.
+// The zero pattern of J_raw is the same for every factor, so the staging tile is cleared once per CTA.
+constexpr int IMU_CS = IMU_COMP + 15;   // rows of imu_comp: compact Jacobian blocks + unweighted residual
+constexpr int IMU_CSP = IMU_CS + 1;     // padded row of the staged copy
+__global__ void __launch_bounds__(32 * IMU_WPC) k_imu_weight(Dev D, int mode, double *__restrict__ out, double *cost, int cost_stride) {
   __shared__ __align__(16) double Jraw_all[IMU_WPC][16 * JS];
+  __shared__ __align__(16) double prod_all[IMU_WPC][15 * JS];   // row stride 40 = 8 mod 16 doubles: conflict-free double2 stores of the accumulator fragments
+  __shared__ double comp_s[IMU_WPC][IMU_CSP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * IMU_WPC + warp;
-  if (f >= D.nImu) return;
-  const int2 ix = D.imu_idx[f];
-  if (!wants<true>(D.ctl[ix.y].state, mode) || (D.nranks > 1 && mode != 0 && D.rank != 0)) return;   // uniform over the warp
-  double *Jraw = Jraw_all[warp];
-  const int fr = lane >> 2, fc = lane & 3;
-  // A fragments: sqrt_info[8 mt + fr][4 ks + fc] (upper triangular, row / column 15 = padding)
-  const double *SI = D.imu_sqrt_info + 225 * (size_t)f;
-  double a[2][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-    for (int ks = 0; ks < 4; ks++) {
-      const int row = 8 * mt + fr, col = 4 * ks + fc;
-      a[mt][ks] = (row < 15 && col < 15 && col >= row) ? __ldg(SI + row * 15 + col) : 0.0;
-    }
+  double *Jraw = Jraw_all[warp], *prod = prod_all[warp];
   for (int e = lane; e < 16 * JS; e += 32) Jraw[e] = 0.0;
-  __syncwarp();
-  const double *comp = D.imu_comp + f;
-  for (int e = lane; e < 18 * 9; e += 32) {
-    const int b = e / 9, k = e - 9 * b;
-    const ImuPut p = c_imu_puts[b];
-    Jraw[(p.r0 + k / 3) * JS + p.c0 + k % 3] = (double)p.sgn * __ldg(comp + (size_t)(9 * p.blk + k) * D.nImu);
-  }
-  __syncwarp();
-  double acc[2][4][2];
+  const int fr = lane >> 2, fc = lane & 3;
+  const int ce = threadIdx.x / IMU_WPC, ck = threadIdx.x % IMU_WPC;   // this thread's share of a group's compact blocks
+  // both inputs of a group are fetched one group ahead (registers), so a group costs one memory round trip that overlaps
+  // the previous group's product
+  double cv[4], a[2][4];
+  auto fetch_comp = [&](int f0) {
 #pragma unroll
-  for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-#pragma unroll
-  for (int ks = 0; ks < 4; ks++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-      const double b = Jraw[(4 * ks + fc) * JS + 8 * nt + fr];   // B[k][n] = J[k][n]
-      dmma884(acc[0][nt], a[0][ks], b);
-      if (ks >= 2) dmma884(acc[1][nt], a[1][ks], b);               // rows 8..14 of sqrt_info start at column 8
+    for (int i = 0; i < 4; i++) {
+      const int e = ce + 32 * i;
+      cv[i] = (e < IMU_CS && f0 + ck < D.nImu) ? __ldg(D.imu_comp + (size_t)e * D.nImu + f0 + ck) : 0.0;
     }
-  __syncwarp();
+  };
+  auto fetch_info = [&](int f) {   // A fragments: sqrt_info[8 mt + fr][4 ks + fc] (upper triangular, row / column 15 = padding)
+    const double *SI = D.imu_sqrt_info + 225 * (size_t)min(f, D.nImu - 1);
 #pragma unroll
-  for (int mt = 0; mt < 2; mt++)
+    for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int row = 8 * mt + fr, col = 8 * nt + 2 * fc + e;
-        if (row < 15 && col < 30) Jraw[row * 30 + col] = acc[mt][nt][e];
+      for (int ks = 0; ks < 4; ks++) {
+        const int row = 8 * mt + fr, col = 4 * ks + fc;
+        a[mt][ks] = (row < 15 && col < 15 && col >= row) ? __ldg(SI + row * 15 + col) : 0.0;
       }
-  __syncwarp();
-  double *rec = out + (size_t)f * REC_IMU + 15;
-  for (int e = lane; e < 450; e += 32) rec[e] = Jraw[e];
+  };
+  int f0 = blockIdx.x * IMU_WPC;
+  if (f0 < D.nImu) { fetch_comp(f0); fetch_info(f0 + warp); }
+  for (; f0 < D.nImu; f0 += gridDim.x * IMU_WPC) {
+    __syncthreads();   // comp_s of the previous group is consumed
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (ce + 32 * i < IMU_CS) comp_s[ck][ce + 32 * i] = cv[i];
+    double a0[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) a0[mt][ks] = a[mt][ks];
+    __syncthreads();
+    const int fn = f0 + gridDim.x * IMU_WPC;
+    if (fn < D.nImu) { fetch_comp(fn); fetch_info(fn + warp); }
+    const int f = f0 + warp;
+    if (f >= D.nImu) continue;
+    const int2 ix = D.imu_idx[f];
+    if (!wants<true>(D.ctl[ix.y].state, mode) || (D.nranks > 1 && mode != 0 && D.rank != 0)) continue;   // uniform over the warp
+    const double *cs = comp_s[warp];
+    for (int e = lane; e < 18 * 9; e += 32) {
+      const int b = e / 9, k = e - 9 * b;
+      const ImuPut p = c_imu_puts[b];
+      Jraw[(p.r0 + k / 3) * JS + p.c0 + k % 3] = (double)p.sgn * cs[9 * p.blk + k];
+    }
+    if (lane < 15) Jraw[lane * JS + 30] = cs[IMU_COMP + lane];
+    __syncwarp();
+    double acc[2][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const double b = Jraw[(4 * ks + fc) * JS + 8 * nt + fr];   // B[k][n] = J[k][n]
+        dmma884(acc[0][nt], a0[0][ks], b);
+        if (ks >= 2) dmma884(acc[1][nt], a0[1][ks], b);              // rows 8..14 of sqrt_info start at column 8
+      }
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const int row = 8 * mt + fr;
+        if (row < 15) *reinterpret_cast<double2 *>(prod + row * JS + 8 * nt + 2 * fc) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      }
+    __syncwarp();
+    // record = [r (15) | J (15 x 30 row-major)]: consecutive lanes write consecutive doubles
+    double *rec = out + (size_t)f * REC_IMU;
+    double rr = 0.0;
+    if (lane < 15) { rr = prod[lane * JS + 30]; rec[lane] = rr; }
+    for (int e = lane; e < 450; e += 32) { const int row = e / 30, col = e - 30 * row; rec[15 + e] = prod[row * JS + col]; }
+    if (cost) {
+      double s = rr * rr;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) atomicAdd(cost + (size_t)ix.y * cost_stride, 0.5 * s);
+    }
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -599,12 +647,19 @@ int launch_line_vp(const Dev &D, const Params &P, bool jac, int mode, int cand, 
   const size_t smem = line_vp_smem(D.max_frames, jac);
   static size_t raised = 0;
   if (jac && smem > raised) {
-    cudaFuncSetAttribute(k_line_vp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_line_vp<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_line_vp<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_line_vp<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_line_vp<true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_line_vp<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_line_vp<true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     raised = smem;
   }
-  if (jac && sweep_occ("UVS_LINE_OCC", 3) == 4) k_line_vp<true, 4><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
-  else if (jac) k_line_vp<true><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  // resident CTAs per SM the registers are bounded for: 4 measured best (99 -> 85 us on the C2 x 1184 batch; 3 = 134 registers)
+  const int occ = jac ? sweep_occ("UVS_LINE_OCC", 4) : 0;
+  if (jac && occ == 3) k_line_vp<true, 3><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  else if (jac && occ == 5) k_line_vp<true, 5><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
+  else if (jac) k_line_vp<true, 4><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
   else k_line_vp<false, 4><<<grid, NT, smem, st>>>(D, P, mode, cand, out_line, out_vp, cost, cost_stride);
   return 1;
 }
@@ -615,7 +670,7 @@ int launch_imu(const Dev &D, const Params &P, bool jac, int mode, int cand, doub
   const int grid = cdiv(D.nImu, GT_IMU);
   if (!jac) { k_imu_geom<false><<<grid, GT_IMU, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride); return 1; }
   k_imu_geom<true><<<grid, GT_IMU, 0, st>>>(D, P, mode, cand, out, res_out, cost, cost_stride);
-  k_imu_weight<<<cdiv(D.nImu, IMU_WPC), 32 * IMU_WPC, 0, st>>>(D, mode, out);
+  k_imu_weight<<<std::min(cdiv(D.nImu, IMU_WPC), 148 * 5), 32 * IMU_WPC, 0, st>>>(D, mode, out, cost, cost_stride);
   return 2;
 }
 
