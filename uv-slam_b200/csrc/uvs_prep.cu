@@ -88,72 +88,131 @@ __global__ void k_prep_fix_ranges(Dev D) {
 
 // IMU index records + sqrt_info.  The inverse (LU, partial pivoting) and the Cholesky factor use
 // un-fused multiplies/adds so that the result does not depend on FMA contraction.
-__global__ void k_imu_info(Dev D) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int II_WPC = 4;   // warps (= IMU factors) per CTA of k_imu_info
+// One WARP per factor, the 15 x 15 matrices in shared memory (row stride 15: odd, conflict-free): lane i owns row i of the
+// LU elimination and of the Cholesky factor, lane c column c of the inverse.  Every matrix entry sees exactly the
+// operations, in the order, of the plain sequential algorithm (un-fused multiplies / subtractions), so the result is the
+// one the single-thread version produced - that one kept two 225-double arrays in local memory and took 159 us for the ten
+// factors of one window (299 us for a batch of 11 840).
+__global__ void __launch_bounds__(32 * II_WPC) k_imu_info(Dev D) {
+  __shared__ double s_lu[II_WPC][232], s_inv[II_WPC][232];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * II_WPC + warp;
   if (f >= D.nImu) return;
   const int w = find_window(D.imu_off, D.B, f);
   const int F = D.frame_off[w + 1] - D.frame_off[w];
   const int fi = D.imu_frame[f];
-  if (fi < 0 || fi + 1 >= F) { flag_error(D, 9); return; }
-  D.imu_idx[f] = make_int2(D.frame_off[w] + fi, w);
+  if (fi < 0 || fi + 1 >= F) { if (lane == 0) flag_error(D, 9); return; }
+  if (lane == 0) D.imu_idx[f] = make_int2(D.frame_off[w] + fi, w);
   const double *cov = D.imu_cov + 225 * (size_t)f;
-  double lu[225], inv[225];
+  double *lu = s_lu[warp], *inv = s_inv[warp];
+  for (int e = lane; e < 225; e += 32) lu[e] = cov[e];
+  __syncwarp();
+  const unsigned full = 0xffffffffu;
+  const bool row = lane < 15;
   int piv[15];
-  for (int k = 0; k < 225; k++) lu[k] = cov[k];
   bool ok = true;
+#pragma unroll
   for (int k = 0; k < 15; k++) {
-    int p = k;
-    double best = fabs(lu[k * 15 + k]);
-    for (int i = k + 1; i < 15; i++) { const double v = fabs(lu[i * 15 + k]); if (v > best) { best = v; p = i; } }
-    piv[k] = p;
-    if (best == 0.0) { ok = false; break; }
-    if (p != k) for (int j = 0; j < 15; j++) { const double t = lu[k * 15 + j]; lu[k * 15 + j] = lu[p * 15 + j]; lu[p * 15 + j] = t; }
-    for (int i = k + 1; i < 15; i++) {
-      const double l = lu[i * 15 + k] / lu[k * 15 + k];
-      lu[i * 15 + k] = l;
-      for (int j = k + 1; j < 15; j++) lu[i * 15 + j] = __dsub_rn(lu[i * 15 + j], __dmul_rn(l, lu[k * 15 + j]));
+    // partial pivoting: first row i >= k with the largest |lu[i][k]|
+    double v = (row && lane >= k) ? fabs(lu[lane * 15 + k]) : -1.0;
+    int idx = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double v2 = __shfl_xor_sync(full, v, o);
+      const int i2 = __shfl_xor_sync(full, idx, o);
+      if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
     }
+    piv[k] = idx;
+    if (v == 0.0) { ok = false; break; }
+    if (idx != k && row) { const double t = lu[k * 15 + lane]; lu[k * 15 + lane] = lu[idx * 15 + lane]; lu[idx * 15 + lane] = t; }
+    __syncwarp();
+    if (row && lane > k) {
+      const double l = lu[lane * 15 + k] / lu[k * 15 + k];
+      lu[lane * 15 + k] = l;
+      for (int j = k + 1; j < 15; j++) lu[lane * 15 + j] = __dsub_rn(lu[lane * 15 + j], __dmul_rn(l, lu[k * 15 + j]));
+    }
+    __syncwarp();
   }
-  for (int c = 0; c < 15 && ok; c++) {
+  if (ok && row) {   // column `lane` of the inverse
     double x[15];
-    for (int i = 0; i < 15; i++) x[i] = i == c ? 1.0 : 0.0;
-    for (int k = 0; k < 15; k++) if (piv[k] != k) { const double t = x[k]; x[k] = x[piv[k]]; x[piv[k]] = t; }
-    for (int i = 0; i < 15; i++) { double s = x[i]; for (int j = 0; j < i; j++) s = __dsub_rn(s, __dmul_rn(lu[i * 15 + j], x[j])); x[i] = s; }
-    for (int i = 14; i >= 0; i--) { double s = x[i]; for (int j = i + 1; j < 15; j++) s = __dsub_rn(s, __dmul_rn(lu[i * 15 + j], x[j])); x[i] = s / lu[i * 15 + i]; }
-    for (int i = 0; i < 15; i++) inv[i * 15 + c] = x[i];
+#pragma unroll
+    for (int i = 0; i < 15; i++) x[i] = i == lane ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+      const int p = piv[k];
+      if (p != k) {   // x[k] <-> x[p], p > k (register array: resolved by selects)
+        const double xk = x[k];
+        double xp = 0.0;
+#pragma unroll
+        for (int i = 0; i < 15; i++) if (i == p) xp = x[i];
+        x[k] = xp;
+#pragma unroll
+        for (int i = 0; i < 15; i++) if (i == p) x[i] = xk;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 15; i++) { double sacc = x[i]; for (int j = 0; j < i; j++) sacc = __dsub_rn(sacc, __dmul_rn(lu[i * 15 + j], x[j])); x[i] = sacc; }
+#pragma unroll
+    for (int i = 14; i >= 0; i--) { double sacc = x[i]; for (int j = i + 1; j < 15; j++) sacc = __dsub_rn(sacc, __dmul_rn(lu[i * 15 + j], x[j])); x[i] = sacc / lu[i * 15 + i]; }
+#pragma unroll
+    for (int i = 0; i < 15; i++) inv[i * 15 + lane] = x[i];
   }
+  __syncwarp();
   // lower Cholesky of inv (reads the lower triangle), stored transposed -> upper sqrt_info
   double *L = lu;
-  for (int k = 0; k < 225; k++) L[k] = 0.0;
+  for (int e = lane; e < 225; e += 32) L[e] = 0.0;
+  __syncwarp();
   for (int j = 0; j < 15 && ok; j++) {
     double d = inv[j * 15 + j];
     for (int k = 0; k < j; k++) d = __dsub_rn(d, __dmul_rn(L[j * 15 + k], L[j * 15 + k]));
     if (!(d > 0.0)) { ok = false; break; }
     d = sqrt(d);
-    L[j * 15 + j] = d;
-    for (int i = j + 1; i < 15; i++) {
-      double s = inv[i * 15 + j];
-      for (int k = 0; k < j; k++) s = __dsub_rn(s, __dmul_rn(L[i * 15 + k], L[j * 15 + k]));
-      L[i * 15 + j] = s / d;
+    __syncwarp();
+    if (lane == j) L[j * 15 + j] = d;
+    if (row && lane > j) {
+      double sacc = inv[lane * 15 + j];
+      for (int k = 0; k < j; k++) sacc = __dsub_rn(sacc, __dmul_rn(L[lane * 15 + k], L[j * 15 + k]));
+      L[lane * 15 + j] = sacc / d;
     }
+    __syncwarp();
   }
-  if (!ok) { flag_error(D, 10); return; }
+  if (!ok) { if (lane == 0) flag_error(D, 10); return; }
   double *out = D.imu_sqrt_info + 225 * (size_t)f;
-  for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) out[i * 15 + j] = L[j * 15 + i];
+  for (int e = lane; e < 225; e += 32) { const int i = e / 15, j = e - 15 * i; out[e] = L[j * 15 + i]; }
 }
 
 // prior_H = J0^T J0, one CTA per window
-__global__ void k_prior_H(Dev D) {
+// J0^T J0 of a window's prior: a thread owns a 4 x 4 tile (eight loads per sixteen multiply-adds, J0 through L1), the
+// tiles of a window are spread over gridDim.y CTAs (a handful of windows: several CTAs per window)
+__global__ void __launch_bounds__(256) k_prior_H(Dev D) {
   const int w = blockIdx.x;
   const int n = D.prior_off[w + 1] - D.prior_off[w];
   if (n <= 0) return;
   const double *J0 = D.prior_J + D.priorJ_off[w];
   double *H = D.prior_H + D.priorJ_off[w];
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int p = e / n, q = e - p * n;
-    double acc = 0.0;
-    for (int i = 0; i < n; i++) acc += J0[(size_t)i * n + p] * J0[(size_t)i * n + q];
-    H[e] = acc;
+  const int nt = (n + 3) / 4;
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < nt * nt; t += gridDim.y * blockDim.x) {
+    const int p0 = 4 * (t / nt), q0 = 4 * (t % nt);
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+    for (int i = 0; i < n; i++) {
+      const double *r = J0 + (size_t)i * n;
+      double pa[4], qa[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) { pa[a] = p0 + a < n ? __ldg(r + p0 + a) : 0.0; qa[a] = q0 + a < n ? __ldg(r + q0 + a) : 0.0; }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[a][c] += pa[a] * qa[c];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) if (p0 + a < n && q0 + c < n) H[(size_t)(p0 + a) * n + q0 + c] = acc[a][c];
   }
 }
 
@@ -250,8 +309,8 @@ int launch_prep(const Dev &D, cudaStream_t st) {
   if (D.nVobs) { k_prep_vp<<<cdiv(D.nVobs, 256), 256, 0, st>>>(D); n++; }
   const int m = D.nP > D.nL ? D.nP : D.nL;
   if (m) { k_prep_fix_ranges<<<cdiv(m, 256), 256, 0, st>>>(D); n++; }
-  if (D.nImu) { k_imu_info<<<cdiv(D.nImu, 64), 64, 0, st>>>(D); n++; }
-  if (D.nPriorR) { k_prior_H<<<D.B, 256, 0, st>>>(D); n++; }
+  if (D.nImu) { k_imu_info<<<cdiv(D.nImu, II_WPC), 32 * II_WPC, 0, st>>>(D); n++; }
+  if (D.nPriorR) { k_prior_H<<<dim3(D.B, D.B >= 74 ? 1 : 8), 256, 0, st>>>(D); n++; }
   return n;
 }
 

@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(32 * IMU_WPC) k_imu_weight(Dev D, int mode, do
 
 // ------------------------------------------------------------------------------------------------
 // Prior residual r = r0 + J0 dx (its Jacobian is J0 itself).  One CTA per window, a warp per row.
-__global__ void __launch_bounds__(NT) k_prior(Dev D, int jac_phase, int mode, int cand, double *__restrict__ res_out,
+__global__ void __launch_bounds__(1024) k_prior(Dev D, int jac_phase, int mode, int cand, double *__restrict__ res_out,
                                               double *cost, int cost_stride) {
   extern __shared__ double dx[];
   const int w = blockIdx.x;
@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(NT) k_prior(Dev D, int jac_phase, int mode, in
   if (D.nranks > 1 && D.rank != 0) return;
   const int buf = D.cur[w] ^ cand;
   const int b0 = D.pblk_off[w], b1 = D.pblk_off[w + 1];
-  for (int b = b0 + threadIdx.x; b < b1; b += NT) {
+  const int nthr = blockDim.x;   // 128 for batches that fill the GPU, 1024 for a handful of windows (one round of rows instead of six)
+  for (int b = b0 + threadIdx.x; b < b1; b += nthr) {
     const int kind = D.pblk_kind[b], row = D.pblk_row[b], col = D.pblk_col[b];
     const double *x0 = D.prior_x0 + 9 * (size_t)b;
     if (kind == 0 || kind == 2) {   // pose / ex-pose: [dp ; 2 vec(q0^-1 q)] with sign fix
@@ -536,7 +537,8 @@ __global__ void __launch_bounds__(NT) k_prior(Dev D, int jac_phase, int mode, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double csum = 0.0;
   // a warp per row, four rows in flight per warp (independent accumulators keep the loads overlapped)
-  constexpr int NW = NT / 32, RB = 4;
+  constexpr int RB = 4;
+  const int NW = nthr / 32;
   for (int i0 = warp * RB; i0 < n; i0 += NW * RB) {
     double acc[RB];
 #pragma unroll
@@ -677,7 +679,7 @@ int launch_imu(const Dev &D, const Params &P, bool jac, int mode, int cand, doub
 int launch_prior(const Dev &D, int max_prior_n, bool jac_phase, int mode, int cand, double *res_out, double *cost,
                  int cost_stride, cudaStream_t st) {
   if (D.nPriorR == 0) return 0;
-  k_prior<<<D.B, NT, (size_t)max_prior_n * sizeof(double), st>>>(D, jac_phase ? 1 : 0, mode, cand, res_out, cost, cost_stride);
+  k_prior<<<D.B, D.B >= 74 ? NT : 1024, (size_t)max_prior_n * sizeof(double), st>>>(D, jac_phase ? 1 : 0, mode, cand, res_out, cost, cost_stride);
   return 1;
 }
 
