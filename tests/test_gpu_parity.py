@@ -329,7 +329,7 @@ def test_edge_cases(solver, opts):
 
 
 def test_stress_window_global_cholesky(solver, opts):
-    """C5 (31 frames, d = 465): reduced system too large for shared memory -> in-place global path"""
+    """C5 (31 frames, d = 465): reduced system too large for shared memory -> blocked Cholesky in a global scratch"""
     w = gw.make_window("C5")
     ref = w.copy()
     sm0 = orc.solve(ref, opts)
@@ -338,6 +338,41 @@ def test_stress_window_global_cholesky(solver, opts):
     solver.download()
     assert abs(sm.final_cost - sm0.final_cost) <= 1e-6 * abs(sm0.final_cost)
     assert np.abs(w.pose - ref.pose).max() < STEP_TOL
+
+
+def test_large_window_first_step_and_batch(solver, opts):
+    """the blocked global-scratch Cholesky of the large windows (chol_window<0>): one LM step of C5 against the oracle's
+    camera step, and a batch of three such windows (every window has its own fragment scratch) against one-by-one solves"""
+    w0 = gw.make_window("C5")
+    w = w0.copy()
+    fs = orc.first_step(w, opts, radius=1e4)
+    o = uvs_b200.default_options(max_num_iterations=1, fixed_iterations=1)
+    solver.upload([w], o)
+    sm = solver.solve()[0]
+    solver.download()
+    assert abs(sm.initial_cost - fs["cost"]) <= 1e-9 * abs(fs["cost"])
+    assert sm.step_accepted[1] == 1
+    delta = fs["delta"]
+    for f in range(w.n_frames):
+        assert np.abs(w.pose[f] - orc.pose_plus(w0.pose[f], delta[15 * f:15 * f + 6])).max() < STEP_TOL
+        assert np.abs(w.speed_bias[f] - (w0.speed_bias[f] + delta[15 * f + 6:15 * f + 15])).max() < STEP_TOL
+    rng = np.random.default_rng(5)
+    batch = [w0.copy() for _ in range(3)]
+    for b in batch[1:]:
+        b.pose[:, :3] += rng.normal(0, 0.01, b.pose[:, :3].shape)
+        b.inv_depth *= 1.0 + rng.normal(0, 0.02, b.n_points)
+    single = []
+    for b in batch:
+        c = b.copy()
+        solver.upload([c], opts)
+        single.append((solver.solve()[0].final_cost, c))
+        solver.download()
+    solver.upload(batch, opts)
+    sms = solver.solve()
+    solver.download()
+    for k in range(3):
+        assert abs(sms[k].final_cost - single[k][0]) <= 1e-7 * abs(single[k][0])
+        assert np.abs(batch[k].pose - single[k][1].pose).max() < 1e-6
 
 
 @pytest.mark.parametrize("cfg,flag", [("C1", 0), ("C2", 0), ("tiny", 0), ("tiny", 1)])
