@@ -434,6 +434,38 @@ def test_marginalization_parity(solver, opts, cfg, flag):
             assert np.abs(w2.pose - w3.pose).max() < STEP_TOL, np.abs(w2.pose - w3.pose).max()
 
 
+def test_marginalization_on_the_repacked_state(solver, opts):
+    """The reference marginalizes on the state AFTER double2vector() / vector2double() (yaw / position gauge fix,
+    estimator.cpp:999-1006 and :1168), not on the raw solver output.  Shift the gauge on the host between solve and
+    marginalize, hand the state back with uvs_upload_state (what GpuWindowProblem::marginalize does): linearisation
+    points, A' and b' follow the shifted state (oracle on the same state) and differ from the un-shifted ones."""
+    w = gw.make_window("C1")
+    solver.upload([w], opts)
+    solver.solve()
+    solver.download()
+    g_raw = solver.marginalize(0, 0)
+    yaw, t = 0.02, np.array([0.3, -0.2, 0.05])
+    Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0.0], [np.sin(yaw), np.cos(yaw), 0.0], [0.0, 0.0, 1.0]])
+    w.pose[:, :3] = w.pose[:, :3] @ Rz.T + t
+    x, y, z, s_ = (w.pose[:, 3 + k].copy() for k in range(4))
+    a, b = np.sin(yaw / 2), np.cos(yaw / 2)          # q' = (0, 0, a, b) * q   (x, y, z, w)
+    w.pose[:, 3] = b * x - a * y
+    w.pose[:, 4] = b * y + a * x
+    w.pose[:, 5] = b * z + a * s_
+    w.pose[:, 6] = b * s_ - a * z
+    w.speed_bias[:, :3] = w.speed_bias[:, :3] @ Rz.T
+    solver.upload_state()
+    g = solver.marginalize(0, 0)
+    m = orc.marginalize(w, opts, 0)
+    assert g is not None and m is not None and g["n"] == m["n"]
+    assert np.array_equal(g["kinds"], m["kinds"]) and np.array_equal(g["ids"], m["ids"])
+    assert np.allclose(g["x0"], m["x0"], atol=1e-12)
+    assert np.abs(g["x0"] - g_raw["x0"]).max() > 1e-2          # the prior really moved with the state
+    sA, sb = np.abs(m["A"]).max(), max(1.0, np.abs(m["b"]).max())
+    assert np.abs(g["A"] - m["A"]).max() < 2e-3 * sA            # same bar as test_marginalization_parity (MARGIN_OLD vs the oracle)
+    assert np.abs(g["b"] - m["b"]).max() < 2e-3 * sb
+
+
 @pytest.mark.parametrize("cfg,flag", [("tiny", 0), ("tiny", 1), ("C1", 0), ("C2", 0)])
 def test_marginalization_against_exact_rule(solver, opts, cfg, flag):
     """GPU A', b' at the fixture's solved state against the reference's rule evaluated with mpmath at 40 digits
