@@ -108,8 +108,20 @@ def _tangent_delta(w0, w1):
     return dp, dq
 
 
+@pytest.fixture(params=["fused", "record", "default"])
+def landmark_path(request, monkeypatch):
+    """fused linearisation (uvs_lin.cu) | record path (k_proj / k_line_vp -> k_core_* -> k_direct_fused) | the library's own
+    choice by batch size (record path for a single window); read at every upload"""
+    monkeypatch.delenv("UVS_NO_FUSE", raising=False)
+    if request.param == "record":
+        monkeypatch.setenv("UVS_NO_FUSE", "1")
+    elif request.param == "default":
+        monkeypatch.delenv("UVS_FUSE_MIN", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("cfg", ["tiny", "C1", "C2"])
-def test_first_step_parity(solver, windows, opts, cfg):
+def test_first_step_parity(solver, windows, opts, cfg, landmark_path):
     """one LM iteration (fixed radius 1e4): the GPU candidate equals Plus(x, oracle delta)"""
     w = windows[cfg].copy()
     fs = orc.first_step(w, opts, radius=1e4)
@@ -155,7 +167,7 @@ def _well_conditioned_lines(w, opts, bound=1e8, min_information=1e-3):
 
 
 @pytest.mark.parametrize("cfg", ["tiny", "C1", "C2"])
-def test_full_solve_parity(solver, windows, opts, cfg):
+def test_full_solve_parity(solver, windows, opts, cfg, landmark_path):
     w = windows[cfg].copy()
     ref = windows[cfg].copy()
     sm0 = orc.solve(ref, opts)

@@ -492,7 +492,12 @@ static int upload_enqueue(UvsHandle *h, int32_t B, const UvsWindow *w, const Uvs
       h->chain_ok = h->use_build3 && !chain_bad && !small && !no_chain;
       // fused linearisation (no point / line Jacobian records): the reference's configuration - constant extrinsic, no td
       const bool no_fuse = std::getenv("UVS_NO_FUSE") != nullptr;   // read at every upload: tests switch paths
-      h->fused = h->use_build3 && !any_ex && !no_fuse && line_run_max.load() <= lin_max_line_obs() &&
+      // The fused kernels trade parallelism for traffic: a lane walks its point's whole track (ten factors = ten dependent
+      // evaluations), which is what a batch that fills the GPU wants and what a handful of windows does not - there the
+      // record path (a thread per factor, then 4 / 8 lanes per landmark) has the shorter critical path.  Measured per
+      // 10-iteration solve, fused / record: B = 1 1.650 / 1.604, 4 1.713 / 1.637, 16 1.779 / 1.753, 64 2.259 / 2.362 ms.
+      const int fuse_min = std::getenv("UVS_FUSE_MIN") ? std::atoi(std::getenv("UVS_FUSE_MIN")) : 32;
+      h->fused = h->use_build3 && !any_ex && !no_fuse && B >= fuse_min && line_run_max.load() <= lin_max_line_obs() &&
                  lin_lines_smem(max_frames) + 1024 <= h->smem_optin;
     }
     if (pack_err == 1) return fail(h, UVS_ERR_INVALID_ARG, "bad prior block kind");

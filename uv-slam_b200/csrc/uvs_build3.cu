@@ -1227,11 +1227,12 @@ int launch_build3_fused(const Dev &D, const Params &P, char *base, const Build3L
                         cudaStream_t st, const Fork *fk) {
   Build3Ctx c; make_ctx(base, lay, c);
   int n = 0;
-  cudaStream_t s_lines = fk ? fk->aux[0] : st, s_tail = fk ? fk->aux[1] : st;
+  cudaStream_t s_lines = fk ? fk->aux[0] : st, s_tail = fk ? fk->aux[1] : st, s_prior = fk ? fk->aux[2] : st;
   double *cost0 = D.acc + ACC_COST0;
-  if (fk) fork_from(fk, st, 2);
+  if (fk) fork_from(fk, st, 3);
   n += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, s_tail);
-  n += launch_prior(D, max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, s_tail);
+  n += launch_prior(D, max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, s_prior);   // beside the IMU sweep; the tail needs both
+  if (fk) { cudaEventRecord(fk->join[2], s_prior); cudaStreamWaitEvent(s_tail, fk->join[2], 0); }
   n += launch_lin_points(D, P, base, lay, st);
   n += launch_lin_lines(D, P, base, lay, max_frames, max_lines, s_lines);
   if (D.nranks <= 1 || D.rank == 0) {   // factor-parallel mode: IMU factors and the prior belong to rank 0
