@@ -446,6 +446,38 @@ def test_marginalization_parity(solver, opts, cfg, flag):
             assert np.abs(w2.pose - w3.pose).max() < STEP_TOL, np.abs(w2.pose - w3.pose).max()
 
 
+def test_marginalization_of_every_window_of_a_batch(solver, windows, opts):
+    """uvs_marginalize per window of a solved batch: the factor sweep (whole batch) runs once, the later calls reuse its
+    records; every prior equals the one of the same window marginalized on its own."""
+    batch = [windows["C1"].copy(), windows["tiny"].copy(), windows["C1"].copy()]
+    batch[2].pose[:, :3] += np.random.default_rng(3).normal(0, 0.01, batch[2].pose[:, :3].shape)
+    solver.upload(batch, opts)
+    solver.solve()
+    solver.download()
+    counts, priors = [], []
+    for i in range(3):
+        l0 = solver.launch_count()
+        priors.append(solver.marginalize(i, 0))
+        counts.append(solver.launch_count() - l0)
+    assert counts[1] < counts[0] and counts[2] < counts[0]      # no second sweep
+    s2 = uvs_b200.Solver(0)
+    try:
+        for i in range(3):
+            s2.upload([batch[i].copy()], opts)                   # the solved state, alone
+            m = s2.marginalize(0, 0)
+            g = priors[i]
+            assert g["n"] == m["n"] and np.array_equal(g["kinds"], m["kinds"]) and np.array_equal(g["ids"], m["ids"])
+            assert np.allclose(g["x0"], m["x0"], atol=1e-12)
+            sA, sb = np.abs(m["A"]).max(), max(1.0, np.abs(m["b"]).max())
+            assert np.abs(g["A"] - m["A"]).max() < 5e-6 * sA and np.abs(g["b"] - m["b"]).max() < 5e-6 * sb   # both within 1e-6 of the exact rule
+    finally:
+        s2.close()
+    solver.solve()                                               # anything that moves the state invalidates the records
+    l0 = solver.launch_count()
+    solver.marginalize(0, 0)
+    assert solver.launch_count() - l0 == counts[0]
+
+
 def test_marginalization_on_the_repacked_state(solver, opts):
     """The reference marginalizes on the state AFTER double2vector() / vector2double() (yaw / position gauge fix,
     estimator.cpp:999-1006 and :1168), not on the raw solver output.  Shift the gauge on the host between solve and

@@ -608,6 +608,7 @@ static int upload_finish(UvsHandle *h) {
                 std::string("uvs_upload_windows: ") + msg[err < 11 ? err : 0]);
   }
   h->have_window = true;
+  h->records_epoch++;
   return UVS_OK;
 }
 
@@ -693,6 +694,7 @@ int uvs_upload_state(UvsHandle *h, int32_t B, const UvsWindow *w) {
   if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_upload_state: no window uploaded");
   if (B != h->B) return fail(h, UVS_ERR_INVALID_ARG, "uvs_upload_state: batch size differs from the upload");
   CK(cudaSetDevice(h->device));
+  h->records_epoch++;
   CK(cudaStreamSynchronize(h->stream));   // the staging buffer may still feed an earlier copy
   const size_t Dd = sizeof(double);
   char *S = h->stage.base, *Dv = h->dev.base;
@@ -731,6 +733,7 @@ int uvs_upload_state(UvsHandle *h, int32_t B, const UvsWindow *w) {
 static int eval_common(UvsHandle *h, int type, double *residuals, double *jacobians, int32_t flags) {
   if (!h) return UVS_ERR_INVALID_ARG;
   if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_eval_*: no window uploaded");
+  h->records_epoch++;
   CK(cudaSetDevice(h->device));
   const Dev &D = h->D;
   const bool local = (flags & UVS_EVAL_LOCAL_LAYOUT) != 0, dev_out = (flags & UVS_EVAL_DEVICE_OUT) != 0;
@@ -783,6 +786,7 @@ int uvs_eval_imu(UvsHandle *h, double *r, double *J, int32_t flags) { return eva
 int uvs_eval_prior(UvsHandle *h, double *residuals, double *jacobians, int32_t flags) {
   if (!h) return UVS_ERR_INVALID_ARG;
   if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_eval_prior: no window uploaded");
+  h->records_epoch++;
   CK(cudaSetDevice(h->device));
   const Dev &D = h->D;
   if (D.nPriorR == 0) return UVS_OK;
@@ -854,6 +858,7 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
   if (!h) return UVS_ERR_INVALID_ARG;
   if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_solve: no window uploaded");
   CK(cudaSetDevice(h->device));
+  h->records_epoch++;
   const Dev &D = h->D;
   const Params &P = h->P;
   cudaStream_t st = h->stream;
@@ -1091,6 +1096,7 @@ int uvs_jacobian_sweep(UvsHandle *h, int32_t repeats, float *ms_group, float *ms
   if (!h || repeats <= 0) return fail(h, UVS_ERR_INVALID_ARG, "uvs_jacobian_sweep: bad arguments");
   if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_jacobian_sweep: no window uploaded");
   CK(cudaSetDevice(h->device));
+  h->records_epoch++;
   const Dev &D = h->D;
   const Params &P = h->P;
   cudaStream_t st = h->stream;
@@ -1130,6 +1136,7 @@ int uvs_reset_state(UvsHandle *h) {
   if (!h) return UVS_ERR_INVALID_ARG;
   if (!h->have_window) return fail(h, UVS_ERR_NO_WINDOW, "uvs_reset_state: no window uploaded");
   CK(cudaSetDevice(h->device));
+  h->records_epoch++;
   char *Dv = h->dev.base;
   CK(cudaMemcpyAsync(Dv + h->o_pose0, Dv + h->o_pristine, h->o_state_bytes, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(Dv + h->o_cur, 0, h->cur_bytes, h->stream));

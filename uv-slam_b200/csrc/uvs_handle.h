@@ -100,6 +100,9 @@ struct UvsHandle {
   bool use_build3 = false;                    // atomics-free landmark path (uvs_build3.cu)
   bool fused = false;                         // factors evaluated inside the landmark elimination (uvs_lin.cu): no point / line records
   int max_lines = 0;                          // most lines in one window (grid of k_lin_lines)
+  // bumped by everything that changes the device state or overwrites the factor records (upload, solve, state upload /
+  // reset, the evaluation entry points); uvs_marginalize re-evaluates the factors only when its records are older
+  int64_t records_epoch = 0, marg_epoch = -1;
   bool chain_ok = false;                      // speed-bias blocks form a chain in every window: k_chol_chain
   uvs::Build3Layout b3{};
   size_t o_b3 = 0;

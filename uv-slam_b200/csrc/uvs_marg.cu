@@ -363,12 +363,17 @@ int uvs_marginalize_impl(UvsHandle *h, int wi, int flag, UvsPrior *out) {
   std::memcpy(hs + ocm, prior_colmap.data(), prior_colmap.size() * sizeof(int));
   CKM(cudaMemcpyAsync(ds + ocm, hs + ocm, prior_colmap.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 
-  // ---- 1. evaluate every factor at the current iterate (tangent columns, loss-corrected)
-  h->launches += launch_proj(D, h->P, true, false, 0, 0, D.rec_proj, nullptr, nullptr, 0, st);
-  h->launches += launch_line_tables(D, 0, st);
-  h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st);
-  h->launches += launch_imu(D, h->P, true, 0, 0, D.rec_imu, nullptr, nullptr, 0, st);
-  h->launches += launch_prior(D, h->max_prior_n, false, 0, 0, D.rec_prior, nullptr, 0, st);
+  // ---- 1. evaluate every factor at the current iterate (tangent columns, loss-corrected).  The sweeps cover the whole
+  //         batch, so the records stay valid for the other windows of the batch: marginalizing B windows costs one sweep,
+  //         not B (the epoch moves with every upload, solve, state change or evaluation call)
+  if (h->marg_epoch != h->records_epoch) {
+    h->launches += launch_proj(D, h->P, true, false, 0, 0, D.rec_proj, nullptr, nullptr, 0, st);
+    h->launches += launch_line_tables(D, 0, st);
+    h->launches += launch_line_vp(D, h->P, true, 0, 0, D.rec_line, D.rec_vp, nullptr, 0, st);
+    h->launches += launch_imu(D, h->P, true, 0, 0, D.rec_imu, nullptr, nullptr, 0, st);
+    h->launches += launch_prior(D, h->max_prior_n, false, 0, 0, D.rec_prior, nullptr, 0, st);
+    h->marg_epoch = h->records_epoch;
+  }
   // ---- 2. A, b
   double *A = (double *)(ds + oA), *b = (double *)(ds + ob);
   if (!facs.empty()) { k_marg_accum<<<(int)facs.size(), 128, 0, st>>>(D, (const MargFactor *)(ds + ofac), pos, A, b); h->launches++; }
