@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Join the per-instruction stall samples of an ncu report with the source lines of the kernel.
 
-  python tools/ncu_lines.py REPORT.ncu-rep KERNEL_SUBSTRING [CUBIN_GLOB] [--top N]
+  python tools/ncu_lines.py REPORT.ncu-rep KERNEL_SUBSTRING [--top N] [--nth N] [--by-inst]
 
 ncu's CSV source page is SASS-only; nvdisasm -g prints the same instructions with `//## File ..., line N`
 markers.  Both list the kernel's instructions in address order, so they are matched by position.
@@ -52,6 +52,7 @@ def sass_lines(so_path, kernel, n_inst=None):
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 30
+    by_inst = "--by-inst" in sys.argv   # rank the source lines by executed warp instructions instead of stall samples
     so = os.environ.get("UVS_SO", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "uv-slam_b200", "csrc", "libuvs_b200.so"))
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
@@ -73,6 +74,7 @@ def main():
     per, ops = {}, {}
     for k, (s, src, n) in enumerate(inst):
         key = lines[k] if k < len(lines) else None
+        s = n if by_inst else s
         per[key] = per.get(key, 0) + s
         ops.setdefault(key, {})
         op = src.split()[0] if src else "?"
@@ -81,7 +83,7 @@ def main():
         ops[key][op] = ops[key].get(op, 0) + s
     tot = sum(per.values()) or 1
     srcs = {}
-    print("total samples %d over %d instructions" % (tot, len(inst)))
+    print("total %s %d over %d instructions" % ("warp instructions executed" if by_inst else "samples", tot, len(inst)))
     for key, s in sorted(per.items(), key=lambda kv: -kv[1])[:top]:
         text = ""
         if key:
