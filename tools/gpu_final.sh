@@ -4,8 +4,11 @@
 # top solver kernels.  Results under gpurun_out/<tag>_*.
 TAG=${1:-fin}
 mkdir -p gpurun_out
+python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.txt 2>&1; tail -1 gpurun_out/${TAG}_smoke.txt
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_C2_reference.json 2> gpurun_out/${TAG}_ref.err
-timeout 900 python bench.py --check 8 > gpurun_out/${TAG}_bench_C2.json 2> gpurun_out/${TAG}_bench_C2.err
+timeout 900 python bench.py > gpurun_out/${TAG}_bench_C2.json 2> gpurun_out/${TAG}_bench_C2.err
+timeout 900 python bench.py --check 8 --no-cpu --steps 5 > gpurun_out/${TAG}_bench_C2_check.json 2> gpurun_out/${TAG}_bench_C2.err
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches_C2.csv python bench.py --steps 1 --warmup 1 --no-cpu > /dev/null 2>&1
 for c in C1 C5 10k; do
   timeout 900 python bench.py --config $c --steps 5 --cpu-budget 6 > gpurun_out/${TAG}_bench_$c.json 2> gpurun_out/${TAG}_bench_$c.err
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 250 --csv --log-file gpurun_out/${TAG}_launches_$c.csv python bench.py --config $c --steps 1 --warmup 1 --no-cpu > /dev/null 2>&1

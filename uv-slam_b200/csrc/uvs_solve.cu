@@ -147,6 +147,7 @@ __device__ bool blocked_chol_solve(double *A, const CholLayout &Lo, int nthr, un
           a[q] -= a[p] * lq;                             // only meaningful for r >= q
         }
       }
+      __syncwarp();   // lanes 8..31 mirror rows 0..7 (r = lane & 7): their reads above come before the owners' write-back
       if (lane < NB && have) {
 #pragma unroll
         for (int c = 0; c < NB; c++) if (c <= r) row[c] = a[c];
@@ -163,7 +164,7 @@ __device__ bool blocked_chol_solve(double *A, const CholLayout &Lo, int nthr, un
       double c[2];
       if (J < I) {
         double2 *C = reinterpret_cast<double2 *>(frag(I, 2 * J + (fc >> 1)) + 4 * ra + 2 * (fc & 1));
-        const double2 c2 = *C;
+        const double2 c2 = fr < rows_of(I) ? *C : make_double2(0.0, 0.0);   // rows that do not exist: their lanes own nothing
         c[0] = c2.x; c[1] = c2.y;
         dmma884(c, a0, b0); dmma884(c, a1, b1);
         if (fr < rows_of(I)) *C = make_double2(c[0], c[1]);
@@ -357,7 +358,7 @@ __device__ __forceinline__ void frag_block_sub(double *A, double *Dg, int K, int
   if (J < I) {
     const int ra = min(fr, rows - 1);
     double2 *C = reinterpret_cast<double2 *>(A + 32 * I * (I - 1) + (2 * J + (fc >> 1)) * 4 * rows + 4 * ra + 2 * (fc & 1));
-    const double2 c2 = *C;
+    const double2 c2 = fr < rows ? *C : make_double2(0.0, 0.0);   // rows that do not exist: their lanes own nothing
     c[0] = c2.x; c[1] = c2.y;
     for (int s = 0; s < nk; s++) dmma884(c, -a[s], b[s]);
     if (fr < rows) *C = make_double2(c[0], c[1]);
