@@ -229,7 +229,17 @@ void uvs_default_options(UvsOptions *opts);
 const char *uvs_status_string(int status);
 
 /* Create a solver bound to CUDA device `device` with its own stream.  Fails (UVS_ERR_CUDA) when no
- * GPU is present: there is no CPU fallback. */
+ * GPU is present: there is no CPU fallback.
+ *
+ * Threading and lifetime.  A handle is NOT thread-safe: all calls on one handle must come from one thread at a time (the
+ * reference calls optimization() under its m_estimator lock, estimator_node.cpp:352).  Different handles are independent
+ * (own stream, own device and pinned arenas) and may be used from different threads concurrently; one process may hold
+ * handles on several devices.  A handle owns ONE device batch: every upload replaces it, and uvs_marginalize / uvs_eval_* /
+ * uvs_download_* always refer to the batch uploaded last through THAT handle - give every independent problem its own
+ * handle (uvs_host::GpuWindowProblem does).  uvs_batch_solve_pipelined runs its sub-batches on child handles that the
+ * parent creates once and keeps; it starts one short-lived host thread per sub-batch and joins them before it returns, so
+ * the call itself is synchronous.  Every entry point returns only after its results are in the caller's buffers
+ * (the library synchronises its stream); caller-owned arrays are never referenced after the call returns. */
 int uvs_create(int device, UvsHandle **out);
 int uvs_destroy(UvsHandle *h);
 const char *uvs_last_error(const UvsHandle *h);
