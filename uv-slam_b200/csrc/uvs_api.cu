@@ -884,6 +884,7 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
   // driver call per iteration instead of ~45.  Opt-in: instantiating the graph costs ~1.7 ms per upload (measured), more
   // than a single 10-iteration solve saves (0.3 ms) - it pays when one upload is solved repeatedly.
   auto enqueue_iteration = [&](int it) -> int {
+    bool merged = false;
     STAGE(0);
     if (h->fused) {
       // fused path: the point / line / VP factors are evaluated inside the landmark elimination (uvs_lin.cu); only the
@@ -891,6 +892,10 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
       STAGE(1); STAGE(2); STAGE(3); STAGE(4); STAGE(5);
       h->launches += launch_build3_fused(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->max_lines, h->max_prior_n, st,
                                          h->profiling < 2 ? fk : nullptr);
+    } else if (fk && h->profiling == 0 && h->use_build3 && !h->any_ex && D.B < 74 && !std::getenv("UVS_TWO_STAGE")) {
+      // a handful of windows: sweep and build stage as one dependency graph over the streams (uvs_build3.cu)
+      h->launches += launch_record_linearisation(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->max_prior_n, st, fk);
+      merged = true;
     } else if (fk && h->profiling < 2) {
       // the four factor-type kernels side by side; the stage events then see the sweep as one interval
       fork_from(fk, st, 3);
@@ -908,7 +913,7 @@ int uvs_solve(UvsHandle *h, UvsSummary *summaries) {
       h->launches += launch_prior(D, h->max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, st); STAGE(5);
     }
     rc = post_launch(h, "Jacobian sweep"); if (rc) return rc;
-    if (h->fused) {
+    if (h->fused || merged) {
     } else if (h->use_build3) {
       h->launches += launch_build3(D, P, h->dev.base + h->o_b3, h->b3, h->max_frames, h->any_ex, h->max_prior_n, st, fk);
     } else {

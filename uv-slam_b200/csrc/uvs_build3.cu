@@ -1220,6 +1220,56 @@ int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout 
   return n;
 }
 
+// Record path, sweep and build stage as ONE dependency graph over the four streams (no join / fork between the two stages):
+//   main   k_proj<1> -> k_core_points -> [lines] -> k_window_system
+//   aux 0  k_line_vp<1> -> k_core_lines
+//   aux 1  IMU sweep -> [prior] -> k_window_tail
+//   aux 2  prior sweep -> [proj, lines] -> k_direct_fused
+// For a handful of windows the kernels are ~10 us each and the stage barrier cost as much as a kernel: one window 1.61 ->
+// 1.54 ms per solve, sixteen 1.75 -> 1.69 ms (constant extrinsic only; the caller keeps the two-stage form for profiling).
+// Merging the back-substitution and candidate-cost stages the same way was measured too and bought nothing.
+int launch_record_linearisation(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, int max_prior_n,
+                                cudaStream_t st, const Fork *fk) {
+  Build3Ctx c; make_ctx(base, lay, c);
+  int n = 0;
+  double *cost0 = D.acc + ACC_COST0;
+  cudaStream_t s0 = fk->aux[0], s1 = fk->aux[1], s2 = fk->aux[2];
+  fork_from(fk, st, 3);
+  n += launch_proj(D, P, true, false, 1, 0, D.rec_proj, nullptr, cost0, ACC_STRIDE, st);
+  n += launch_line_vp(D, P, true, 1, 0, D.rec_line, D.rec_vp, cost0, ACC_STRIDE, s0);
+  n += launch_imu(D, P, true, 1, 0, D.rec_imu, nullptr, cost0, ACC_STRIDE, s1);
+  n += launch_prior(D, max_prior_n, true, 1, 0, D.rec_prior, cost0, ACC_STRIDE, s2);
+  // a wait refers to the recording of an event that precedes it: the auxiliary streams have already been told to wait for
+  // the first recording of `fork`, so the event can be recorded again
+  cudaEventRecord(fk->fork, st);        // projection records written
+  cudaEventRecord(fk->join[0], s0);     // line / VP records written
+  cudaEventRecord(fk->join[2], s2);     // prior residual written
+  cudaStreamWaitEvent(s1, fk->join[2], 0);
+  cudaStreamWaitEvent(s2, fk->fork, 0);
+  cudaStreamWaitEvent(s2, fk->join[0], 0);
+  if (D.nP) { k_core_points<<<cdiv3(D.nP, 128 / LPP), 128, 0, st>>>(D, P, c.S); n++; }
+  if (D.nL) { k_core_lines<<<cdiv3(D.nL, 128 / LPL), 128, 0, s0>>>(D, P, c.S); n++; }
+  {
+    const long long units = (long long)D.B * (max_frames * SEGS_D + max_frames * (max_frames - 1) / 2);
+    k_direct_fused<<<(unsigned)((units + 3) / 4), 128, 0, s2>>>(D, c.L, max_frames);
+    n++;
+  }
+  if (D.nranks <= 1 || D.rank == 0) {
+    const size_t tsm = std::max((size_t)IMU_G * REC_IMU * sizeof(double), (size_t)(max_prior_n + 2) * sizeof(int));
+    const int ws = window_split(D.B), ni = ws > 1 ? 3 : 1, np = ws > 1 ? 4 : 1;
+    k_window_tail<<<dim3(D.B, ni + np), TT, tsm, s1>>>(D, max_prior_n, ni);
+    n++;
+  }
+  join_to(fk, st, 0);
+  const size_t smem = build3_smem(max_frames, false, max_prior_n);
+  static size_t raised = 0;
+  if (smem > raised) { cudaFuncSetAttribute(k_window_system, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); raised = smem; }
+  k_window_system<<<dim3(D.B, window_split(D.B)), WT, smem, st>>>(D, c.S, max_prior_n);
+  n++;
+  join_to(fk, st, 1); join_to(fk, st, 2);
+  return n;
+}
+
 // Linearisation stage of the fused path: IMU + prior sweeps (the only factor records that still exist), point and line
 // linearisation with the factors evaluated in registers (uvs_lin.cu), IMU / prior tail, rank update.  Three strands:
 // main = points -> rank update, aux 0 = lines, aux 1 = IMU sweep -> prior sweep -> tail.

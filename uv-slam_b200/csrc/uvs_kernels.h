@@ -61,6 +61,9 @@ int launch_build3_prep(const Dev &D, char *base, const Build3Layout &lay, bool a
 int launch_build3(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, bool any_ex, int max_prior_n,
                   cudaStream_t st, const Fork *fk);
 int launch_back3(const Dev &D, char *base, const Build3Layout &lay, cudaStream_t st, const Fork *fk, bool unscaled_pts);
+// record path: Jacobian sweep + build stage as one dependency graph over the handle's streams (small batches, constant extrinsic)
+int launch_record_linearisation(const Dev &D, const Params &P, char *base, const Build3Layout &lay, int max_frames, int max_prior_n,
+                                cudaStream_t st, const Fork *fk);
 int launch_build_cam(const Dev &D, int max_prior_n, cudaStream_t st);
 // fused linearisation (uvs_lin.cu): factors evaluated in registers, no Jacobian records in HBM; launch_build3_fused is the
 // build stage of that path (point + line linearisation, IMU / prior tail, rank update)
