@@ -335,7 +335,7 @@ constexpr int CH_LWG = 720;      // doubles of global scratch per chain block (L
 constexpr int LLS = 190;         // shared memory per chain block: L_c 9 x 10 (reciprocal diagonal) | L_x 9 x 10 | z_f 10
 constexpr int CH_ROWS = 96;      // row threads (warps 1..3): one per row of the dense part, nd <= 96
 
-struct ChainLayout { int o_LL, o_z, o_t, o_LwF, o_sc, total; };
+struct ChainLayout { int o_LL, o_z, o_t, o_LwF, o_sc, o_lm, o_g, total; };
 __host__ __device__ __forceinline__ ChainLayout chain_layout(int nd, int F) {
   const CholLayout Lo = chol_layout(nd);
   ChainLayout c;
@@ -345,6 +345,8 @@ __host__ __device__ __forceinline__ ChainLayout chain_layout(int nd, int F) {
   c.o_t = o; o += 10 * F;
   c.o_LwF = o; o += 2 * Lo.K * 96;            // L_w of a block as tensor-core A fragments [block row][k-step 0..2][32], two buffers
   c.o_sc = o; o += (nd + 9 * F + 1) & ~1;     // Jacobi scale of every column
+  c.o_lm = o; o += (nd + 9 * F + 1) & ~1;     // LM diagonal of every column
+  c.o_g = o; o += (nd + 9 * F + 1) & ~1;      // scaled negative gradient (right-hand side) of every column
   c.total = o;
   return c;
 }
@@ -665,6 +667,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
   const int K = Lo.K;
   double *A = smem, *Dg = smem + Lo.dbase, *bz = smem + Lo.vbase, *invd_all = bz + K * NB;
   double *LL = smem + Ch.o_LL, *zb = smem + Ch.o_z, *tb = smem + Ch.o_t, *LwF = smem + Ch.o_LwF, *sc = smem + Ch.o_sc;
+  double *lmd = smem + Ch.o_lm, *rhs = smem + Ch.o_g;
   auto sidx = [&](int q) { return q < 6 * F ? 15 * (q / 6) + q % 6 : 15 * F + (q - 6 * F); };   // dense index -> index in S
   auto cb = [&](int f) { return 15 * f + 6; };                                                    // first column of B_f in S
   auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
@@ -672,7 +675,9 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     const int I = i >> 3, r = i & 7;
     return (j >> 3) == I ? Dg + 36 * I + r * (r + 1) / 2 + (j & 7) : A + 32 * I * (I - 1) + (j >> 2) * 4 * rows_of(I) + 4 * r + (j & 3);
   };
-  auto lm = [&](int s) { const double v = sc[s], h = v * v * colsq[s]; return clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; };
+  // LM diagonal and right-hand side of every column are staged with the scale (one round trip for all three vectors):
+  // read where they are needed, a global load per diagonal entry stalled its warp once per column
+  auto lm = [&](int s) { return lmd[s]; };
   // entry e of the chain blocks' inputs: C_f (lower, 45) and, for f > 0, X_f (rows B_f-1, columns B_f, 81) -> slot in LL, the
   // two S indices (s1 <= s2: S is stored as its upper triangle)
   auto chain_entry = [&](int e, double *&dst, int &s1, int &s2) -> bool {
@@ -706,7 +711,10 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     double *dst; int s1, s2;
     if (chain_entry(e, dst, s1, s2)) cp_async8(dst, Sg + (size_t)s1 * d + s2);
   }
-  for (int c = tid; c < d; c += nthr) sc[c] = scale[c];
+  for (int c = tid; c < d; c += nthr) {
+    const double v = scale[c], h = v * v * colsq[c];
+    sc[c] = v; lmd[c] = clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; rhs[c] = -v * gS[c];
+  }
   for (int e = tid; e < 2 * K * 96; e += nthr) LwF[e] = 0.0;
   cp_async_wait();
   __syncthreads();
@@ -732,7 +740,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
       Sg[(size_t)s1 * d + s2] = 0.0;
     }
   }
-  for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9, c = e - 9 * f, s = cb(f) + c; LL[LLS * f + 180 + c] = -sc[s] * gS[s]; }
+  for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9, c = e - 9 * f; LL[LLS * f + 180 + c] = rhs[cb(f) + c]; }
   for (int c = tid; c < K * NB; c += nthr) { bz[c] = 0.0; invd_all[c] = 1.0; }
   // row threads: row q of W_F-1 (scaled) and the dense right-hand side, in registers
   const int q = tid - 32;
@@ -757,7 +765,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
     load_w(F - 1, wn);
 #pragma unroll
     for (int c = 0; c < 9; c++) wn[c] *= ssq * sc[cb(F - 1) + c];
-    bzq = -ssq * gS[sq];
+    bzq = rhs[sq];
   } else {
 #pragma unroll
     for (int c = 0; c < 9; c++) wn[c] = 0.0;
@@ -1401,8 +1409,11 @@ int launch_chol_chain(const Dev &D, const Params &P, int max_frames, bool any_ex
     cudaFuncSetAttribute(k_chol_chain<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     raised = smem;
   }
+  // each variant is launched with its own layout's size: four windows of the barrier-phased one must keep fitting an SM
+  const int nd = 6 * max_frames + (any_ex ? 6 : 0);
+  const size_t smem_v1 = std::max((size_t)chain_layout_v1(nd, max_frames).total * sizeof(double), (size_t)MAX_PRIOR_COLS * sizeof(int)) + pad;
   if (D.B <= pipe_max) k_chol_chain<3><<<D.B, 256, smem, st>>>(D, P, mc_identity ? 1 : 0);
-  else k_chol_chain<2><<<D.B, 256, smem, st>>>(D, P, mc_identity ? 1 : 0);
+  else k_chol_chain<2><<<D.B, 256, smem_v1, st>>>(D, P, mc_identity ? 1 : 0);
   return 1;
 }
 
