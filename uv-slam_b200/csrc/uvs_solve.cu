@@ -388,7 +388,7 @@ __device__ __forceinline__ void nbar_arrive(int id, int count) {   // st.shared 
 }
 __device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-struct ChainLayoutV1 { int o_C[2], o_W[2], o_X[2], o_bb, o_LL, o_z, o_LwF, o_t, total; };
+struct ChainLayoutV1 { int o_C[2], o_W[2], o_X[2], o_bb, o_LL, o_z, o_LwF, o_t, o_sc, total; };
 __host__ __device__ __forceinline__ ChainLayoutV1 chain_layout_v1(int nd, int F) {
   const CholLayout Lo = chol_layout(nd);
   ChainLayoutV1 c;
@@ -402,6 +402,7 @@ __host__ __device__ __forceinline__ ChainLayoutV1 chain_layout_v1(int nd, int F)
   c.o_z = o; o += 10 * F;                     // z_f, later y_f
   c.o_LwF = o; o += Lo.K * 96;                // L_w as tensor-core A fragments: [block row][k-step 0..2][32]
   c.o_t = o; o += 10 * F;
+  c.o_sc = o; o += (nd + 9 * F + 1) & ~1;     // Jacobi scale of every column (four windows per SM leave room for this, not for more)
   c.total = o;
   return c;
 }
@@ -420,6 +421,7 @@ __device__ bool chain_solve_v1(double *smem, int nthr, unsigned short *s_pair, i
   double *A = smem, *Dg = smem + Lo.dbase, *bz = smem + Lo.vbase, *invd_all = bz + K * NB;
   double *Cb[2] = {smem + Ch.o_C[0], smem + Ch.o_C[1]}, *Wb[2] = {smem + Ch.o_W[0], smem + Ch.o_W[1]};
   double *Xb[2] = {smem + Ch.o_X[0], smem + Ch.o_X[1]}, *bb = smem + Ch.o_bb, *LL = smem + Ch.o_LL, *zb = smem + Ch.o_z, *LwF = smem + Ch.o_LwF, *tb = smem + Ch.o_t;
+  double *sc = smem + Ch.o_sc;   // the Jacobi scale, staged: it is read for every entry that is scaled
   auto sidx = [&](int q) { return q < 6 * F ? 15 * (q / 6) + q % 6 : 15 * F + (q - 6 * F); };   // dense index -> index in S
   auto cb = [&](int f) { return 15 * f + 6; };                                                    // first column of B_f in S
   auto rows_of = [&](int I) { return I == K - 1 ? Lo.vr : NB; };
@@ -427,7 +429,7 @@ __device__ bool chain_solve_v1(double *smem, int nthr, unsigned short *s_pair, i
     const int I = i >> 3, r = i & 7;
     return (j >> 3) == I ? Dg + 36 * I + r * (r + 1) / 2 + (j & 7) : A + 32 * I * (I - 1) + (j >> 2) * 4 * rows_of(I) + 4 * r + (j & 3);
   };
-  auto lm = [&](int s) { const double sc = scale[s], h = sc * sc * colsq[s]; return clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; };
+  auto lm = [&](int s) { const double v = sc[s], h = v * v * colsq[s]; return clampd2(h, P.min_lm_diag, P.max_lm_diag) / radius; };
   auto sup = [&](int i, int j) { return i <= j ? Sg + (size_t)i * d + j : Sg + (size_t)j * d + i; };   // S is stored as its upper triangle
   // Copies and scaling of the chain blocks belong to warps 1.. (warp 0 runs the 9x9 factorisation meanwhile): thread
   // lt = tid - 32 owns column cc = lt % 9 of rows q0, q0 + R, ... of W, element (q0, cc) of C (q0 < 9) and of X (9 <= q0 < 18)
@@ -452,20 +454,20 @@ __device__ bool chain_solve_v1(double *smem, int nthr, unsigned short *s_pair, i
   auto scale_block = [&](int fb, int buf) {
     if (!part) return;
     const int c0 = cb(fb), col = c0 + cc;
-    const double scol = scale[col];
+    const double scol = sc[col];
 #pragma unroll 4
     for (int q = q0; q < nd; q += R) {
       const int sq = sidx(q);
-      Wb[buf][9 * q + cc] *= scale[sq] * scol;
+      Wb[buf][9 * q + cc] *= sc[sq] * scol;
       if (sq <= col) Sg[(size_t)sq * d + col] = 0.0; else Sg[(size_t)col * d + sq] = 0.0;
     }
     if (q0 < 9) {
       if (cc <= q0) {
-        double v = Cb[buf][9 * q0 + cc] * scale[c0 + q0] * scol; if (cc == q0) v += lm(col); Cb[buf][9 * q0 + cc] = v;
+        double v = Cb[buf][9 * q0 + cc] * sc[c0 + q0] * scol; if (cc == q0) v += lm(col); Cb[buf][9 * q0 + cc] = v;
         Sg[(size_t)col * d + c0 + q0] = 0.0;
       }
     } else if (q0 < 18 && fb > 0) {
-      Xb[buf][9 * (q0 - 9) + cc] *= scale[cb(fb - 1) + q0 - 9] * scol;
+      Xb[buf][9 * (q0 - 9) + cc] *= sc[cb(fb - 1) + q0 - 9] * scol;
       Sg[(size_t)(cb(fb - 1) + q0 - 9) * d + col] = 0.0;
     }
   };
@@ -478,14 +480,15 @@ __device__ bool chain_solve_v1(double *smem, int nthr, unsigned short *s_pair, i
   }
   load_block(F - 1, (F - 1) & 1);
   for (int e = tid; e < K * 96; e += nthr) LwF[e] = 0.0;
+  for (int c = tid; c < d; c += nthr) sc[c] = scale[c];
   for (int c = tid; c < K * NB; c += nthr) { bz[c] = c < nd ? -scale[sidx(c)] * gS[sidx(c)] : 0.0; invd_all[c] = 1.0; }
   for (int e = tid; e < 9 * F; e += nthr) { const int f = e / 9, s = cb(f) + e - 9 * f; bb[e] = -scale[s] * gS[s]; }
   cp_async_wait();
   __syncthreads();
   for (int qj = warp; qj < nd; qj += nw) {
     const int sjj = sidx(qj);
-    const double sj = scale[sjj];
-    for (int qi = qj + lane; qi < nd; qi += 32) { double *a = slot(qi, qj); *a = scale[sidx(qi)] * sj * *a; Sg[(size_t)sjj * d + sidx(qi)] = 0.0; }
+    const double sj = sc[sjj];
+    for (int qi = qj + lane; qi < nd; qi += 32) { double *a = slot(qi, qj); *a = sc[sidx(qi)] * sj * *a; Sg[(size_t)sjj * d + sidx(qi)] = 0.0; }
   }
   scale_block(F - 1, (F - 1) & 1);
   __syncthreads();
