@@ -350,6 +350,15 @@ int uvs_triangulate_points(UvsHandle *h, int32_t n_frames, const double *Rs, con
 int uvs_triangulate_lines(UvsHandle *h, int32_t n_frames, const double *Rs, const double *Ps, const double *ric, const double *tic,
                           int32_t n_lines, const int32_t *frame_first, const int32_t *frame_last, const double *sp_first,
                           const double *ep_first, const double *sp_last, const double *ep_last, double *ortho_out);
+/* uvs_validate_lines = the validity test of FeatureManager::setLineOrtho (feature_manager.cpp:333-423), run after the solve
+ * (double2vector, estimator.cpp:706): line t, given by the orthonormal parameters the FEATURE holds (ortho[t][4]: the test
+ * uses the stored ones, the solved ones are written back only for valid lines), is taken into the camera of its first frame
+ * start_frame[t] and intersected with the planes through the end points sp_first / ep_first ([n_lines][3], z = 1) of its first
+ * observation; solve_flag[t] = 2 when either 3-D end point lies behind that camera, else 1.  end_points (nullable,
+ * [n_lines][6]) receives the world end points D_s_w, D_e_w the reference computes on the way.  Rs / Ps: the solved poses. */
+int uvs_validate_lines(UvsHandle *h, int32_t n_frames, const double *Rs, const double *Ps, const double *ric, const double *tic,
+                       int32_t n_lines, const int32_t *start_frame, const double *ortho, const double *sp_first,
+                       const double *ep_first, int32_t *solve_flag, double *end_points);
 
 /* ---- Device-resident sliding window --------------------------------------------------------------
  * The reference rebuilds its Ceres problem from FeatureManager every frame (estimator.cpp:823-934) although only one frame

@@ -5,6 +5,7 @@ Follows, line by line:
   FeatureManager::triangulate      /root/reference/vins_estimator/src/feature_manager.cpp:427-481
   FeatureManager::triangulateLine  /root/reference/vins_estimator/src/feature_manager.cpp:504-589
   FeatureManager::calcPluckerLine  /root/reference/vins_estimator/src/feature_manager.cpp:827-902
+  FeatureManager::setLineOrtho     /root/reference/vins_estimator/src/feature_manager.cpp:333-423 (validity test)
 Eigen pieces restated from their published algorithms (Eigen is not in this image, version unpinned by the reference):
 JacobiSVD(...).matrixV().rightCols<1>() = right singular vector of the smallest singular value (numpy.linalg.svd);
 Matrix3d::eulerAngles(0, 1, 2) as implemented in Eigen 3.3 (Geometry/EulerAngles.h).  PARITY UNPINNED in the same sense
@@ -87,3 +88,37 @@ def triangulate_line(Rs, Ps, ric, tic, frame_first, frame_last, sp_first, ep_fir
     out[:3] = euler_angles_012(psi)
     out[3] = np.arctan2(np.linalg.norm(d_w), np.linalg.norm(n_w))
     return out
+
+
+def line_solve_flag(Rs, Ps, ric, tic, start_frame, ortho, sp, ep):
+    """feature_manager.cpp:346-415 for one line -> (solve_flag, D_s_w, D_e_w); ortho = the feature's stored
+    orthonormal_vec, sp / ep = start_point / end_point of its first observation (z = 1)"""
+    a, b, c, phi = ortho
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    psi = Rx @ Ry @ Rz                                   # roll * pitch * yaw
+    n_w = np.cos(phi) * psi[:, 0]
+    d_w = np.sin(phi) * psi[:, 1]
+    R_wc = Rs[start_frame] @ ric
+    t_wc = Rs[start_frame] @ tic + Ps[start_frame]
+    T_cw = np.zeros((6, 6))
+    T_cw[:3, :3] = R_wc.T
+    T_cw[:3, 3:] = skew(-R_wc.T @ t_wc) @ R_wc.T
+    T_cw[3:, 3:] = R_wc.T
+    l_c = T_cw @ np.concatenate([n_w, d_w])
+    n_c, d_c = l_c[:3], l_c[3:]
+    L_c = np.zeros((4, 4))
+    L_c[:3, :3] = skew(n_c)
+    L_c[:3, 3] = d_c
+    L_c[3, :3] = -d_c
+    with np.errstate(divide="ignore", invalid="ignore"):
+        slope = -1.0 * (ep[0] - sp[0]) / (ep[1] - sp[1])
+        sp_p = np.array([sp[0] + 1.0, slope + sp[1], 1.0])
+        ep_p = np.array([ep[0] + 1.0, slope + ep[1], 1.0])
+        pi_s = np.append(np.cross(sp, sp_p), 0.0)
+        pi_e = np.append(np.cross(ep, ep_p), 0.0)
+        D_s, D_e = L_c @ pi_s, L_c @ pi_e
+        D_s3, D_e3 = D_s[:3] / D_s[3], D_e[:3] / D_e[3]
+    flag = 2 if (D_s3[2] < 0 or D_e3[2] < 0) else 1
+    return flag, R_wc @ D_s3 + t_wc, R_wc @ D_e3 + t_wc

@@ -1,6 +1,6 @@
 """Triangulation: the numpy oracle (oracle/triangulate.py, a restatement of
 feature_manager.cpp:427-589, 827-902) against exact synthetic geometry on the CPU, and the CUDA kernels
-(uvs_triangulate_points / uvs_triangulate_lines) against the oracle on the GPU."""
+(uvs_triangulate_points / uvs_triangulate_lines / uvs_validate_lines) against the oracle on the GPU."""
 import os
 import sys
 
@@ -49,7 +49,7 @@ def make_scene(seed, n_frames=11, n_tracks=200, n_lines=80, noise=0.0):
             p[:2] += rng.normal(0, noise, 2)
             pts.append(p)
         start.append(s); off.append(off[-1] + n); depth.append(d)
-    lines = dict(first=[], last=[], sp0=[], ep0=[], sp1=[], ep1=[], nw=[], dw=[])
+    lines = dict(first=[], last=[], sp0=[], ep0=[], sp1=[], ep1=[], nw=[], dw=[], a=[], b=[])
     for _ in range(n_lines):
         s = int(rng.integers(0, n_frames - 5))
         e = int(rng.integers(s + 2, n_frames))
@@ -63,6 +63,7 @@ def make_scene(seed, n_frames=11, n_tracks=200, n_lines=80, noise=0.0):
         lines["sp0"].append(project(s, a)); lines["ep0"].append(project(s, b))
         lines["sp1"].append(project(e, a1)); lines["ep1"].append(project(e, b1))
         lines["nw"].append(np.cross(a, b)); lines["dw"].append(b - a)
+        lines["a"].append(a); lines["b"].append(b)
     return dict(Rs=Rs, Ps=Ps, ric=ric, tic=tic, start=np.array(start, np.int32), off=np.array(off, np.int32), pts=np.array(pts),
                 depth=np.array(depth), **{k: np.array(v) for k, v in lines.items()})
 
@@ -126,6 +127,43 @@ def test_oracle_line_recovers_the_world_pluecker_line():
 
 
 # ---- GPU: kernels against the oracle -----------------------------------------------------------------------------
+def behind_camera_copy(sc):
+    """the same scene seen by cameras turned by 180 degrees about their y axis (R_wc' = R_wc diag(-1, 1, -1)): every line
+    lies behind its first camera; the 'observations' are the central projections x / z of the end points (z < 0)"""
+    flip = sc["ric"] @ np.diag([-1.0, 1.0, -1.0]) @ sc["ric"].T
+    out = dict(sc)
+    out["Rs"] = np.array([R @ flip for R in sc["Rs"]])
+    out["Ps"] = np.array([P + R @ sc["tic"] - R2 @ sc["tic"] for P, R, R2 in zip(sc["Ps"], sc["Rs"], out["Rs"])])   # same camera centres
+    sp0, ep0 = [], []
+    for t in range(len(sc["first"])):
+        f = int(sc["first"][t])
+        R, c = out["Rs"][f] @ sc["ric"], out["Ps"][f] + out["Rs"][f] @ sc["tic"]
+        xa, xb = R.T @ (sc["a"][t] - c), R.T @ (sc["b"][t] - c)
+        sp0.append(xa / xa[2]); ep0.append(xb / xb[2])
+    out["sp0"], out["ep0"] = np.array(sp0), np.array(ep0)
+    return out
+
+
+def oracle_flags(sc, ortho):
+    res = [tri.line_solve_flag(sc["Rs"], sc["Ps"], sc["ric"], sc["tic"], int(sc["first"][t]), ortho[t], sc["sp0"][t], sc["ep0"][t])
+           for t in range(len(sc["first"]))]
+    return np.array([r[0] for r in res], np.int32), np.array([np.concatenate([r[1], r[2]]) for r in res])
+
+
+def test_oracle_line_validity_recovers_the_end_points():
+    """setLineOrtho's test (feature_manager.cpp:333-423): with the exact line the 3-D end points it computes are the world
+    points that project onto the first observation's end points - in front of the camera flag 1, behind it flag 2"""
+    sc = make_scene(31, n_lines=40)
+    ortho = oracle_lines(sc)
+    flag, ends = oracle_flags(sc, ortho)
+    assert (flag == 1).all()
+    assert np.abs(ends[:, :3] - sc["a"]).max() < 1e-6 and np.abs(ends[:, 3:] - sc["b"]).max() < 1e-6
+    back = behind_camera_copy(sc)
+    flag, ends = oracle_flags(back, ortho)      # the world line is the same
+    assert (flag == 2).all()
+    assert np.abs(ends[:, :3] - sc["a"]).max() < 1e-6 and np.abs(ends[:, 3:] - sc["b"]).max() < 1e-6
+
+
 @pytest.fixture(scope="module")
 def solver():
     import uvs_b200
@@ -172,3 +210,31 @@ def test_gpu_lines_match_oracle(solver, seed):
         n1, d1 = ortho_to_plucker(got[t])
         assert np.linalg.norm(n0 - n1) < 1e-9 and np.linalg.norm(d0 - d1) < 1e-9
     assert np.max(np.abs(got - ref)) < 1e-8
+
+
+@pytest.mark.gpu
+def test_gpu_line_validity_matches_oracle(solver):
+    """uvs_validate_lines against the oracle: lines in front of their first camera, the same lines behind it, and random
+    orthonormal parameters (both outcomes); flags equal, world end points to 1e-9 relative"""
+    sc = make_scene(41, n_lines=120)
+    ortho = oracle_lines(sc)
+    cases = [(sc, ortho), (behind_camera_copy(sc), ortho)]
+    rng = np.random.default_rng(7)
+    cases.append((sc, np.column_stack([rng.uniform(-np.pi, np.pi, (120, 3)), rng.uniform(0.05, 1.5, 120)])))
+    seen = set()
+    for scn, o in cases:
+        f0, e0 = oracle_flags(scn, o)
+        f1, e1 = solver.validate_lines(scn["Rs"], scn["Ps"], scn["ric"], scn["tic"], scn["first"], o, scn["sp0"], scn["ep0"], want_end_points=True)
+        # camera-frame depths of the two end points: leave out lines whose depth is zero to rounding (the sign is then noise)
+        R = np.array([scn["Rs"][int(f)] @ scn["ric"] for f in scn["first"]])
+        c = np.array([scn["Ps"][int(f)] + scn["Rs"][int(f)] @ scn["tic"] for f in scn["first"]])
+        zs = np.einsum("nij,ni->nj", R, e0[:, :3] - c)[:, 2]
+        ze = np.einsum("nij,ni->nj", R, e0[:, 3:] - c)[:, 2]
+        clear = (np.abs(zs) > 1e-9) & (np.abs(ze) > 1e-9) & np.isfinite(e0).all(axis=1)
+        assert clear.sum() > 100
+        assert np.array_equal(f0[clear], f1[clear])
+        assert (np.abs(e1[clear] - e0[clear]) <= 1e-9 * np.maximum(1.0, np.abs(e0[clear]))).all()
+        seen |= set(f0[clear].tolist())
+    assert seen == {1, 2}
+    f = solver.validate_lines(sc["Rs"], sc["Ps"], sc["ric"], sc["tic"], sc["first"], ortho, sc["sp0"], sc["ep0"])
+    assert (f == 1).all()

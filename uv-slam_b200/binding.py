@@ -22,7 +22,7 @@ EXPORTS = (
     "uvs_eval_prior", "uvs_eval_cost", "uvs_solve", "uvs_batch_solve", "uvs_marginalize", "uvs_sweep_bytes",
     "uvs_launch_count", "uvs_last_solve_ms", "uvs_last_sweep_ms", "uvs_comm_init", "uvs_reset_state",
     "uvs_set_profiling", "uvs_last_stage_ms", "uvs_preintegrate", "uvs_batch_solve_pipelined",
-    "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_set_graph_replay", "uvs_upload_state", "uvs_jacobian_sweep", "uvs_comm_unique_id", "uvs_comm_init_nccl", "uvs_collective_count",
+    "uvs_triangulate_points", "uvs_triangulate_lines", "uvs_validate_lines", "uvs_set_graph_replay", "uvs_upload_state", "uvs_jacobian_sweep", "uvs_comm_unique_id", "uvs_comm_init_nccl", "uvs_collective_count",
     "uvs_window_create", "uvs_window_push_frame", "uvs_window_counts", "uvs_window_upload", "uvs_window_marginalize", "uvs_window_slide",
     "uvs_window_remove_tracks", "uvs_download_factors", "uvs_h2d_bytes",
 )
@@ -109,6 +109,7 @@ def load_library():
     lib.uvs_preintegrate.argtypes = [H, C.c_int32, c_int32_p] + [c_double_p] * 14
     lib.uvs_triangulate_points.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p, c_double_p, C.c_double, c_double_p]
     lib.uvs_triangulate_lines.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p, c_int32_p] + [c_double_p] * 5
+    lib.uvs_validate_lines.argtypes = [H, C.c_int32] + [c_double_p] * 4 + [C.c_int32, c_int32_p] + [c_double_p] * 3 + [c_int32_p, c_double_p]
     lib.uvs_set_profiling.argtypes = [H, C.c_int32]
     lib.uvs_set_graph_replay.argtypes = [H, C.c_int32]
     lib.uvs_last_stage_ms.argtypes = [H, C.POINTER(C.c_float * N_STAGES), C.POINTER(C.c_int32)]
@@ -413,6 +414,21 @@ class Solver:
                                                     obs_off.ctypes.data_as(c_int32_p), p(obs_pts), float(init_depth), p(out)),
                     "uvs_triangulate_points")
         return out
+
+    def validate_lines(self, Rs, Ps, ric, tic, start_frame, ortho, sp_first, ep_first, want_end_points=False):
+        """validity test of FeatureManager::setLineOrtho on the device: solve_flag [n] (1 valid, 2 behind the camera)
+        and, on request, the world end points [n][6] (see include/uvs.h)."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        Rs, Ps, ric, tic, ortho, sp_first, ep_first = (f64(a) for a in (Rs, Ps, ric, tic, ortho, sp_first, ep_first))
+        start_frame = np.ascontiguousarray(start_frame, dtype=np.int32)
+        n = len(start_frame)
+        flag = np.zeros(n, np.int32)
+        ends = np.zeros((n, 6)) if want_end_points else None
+        p = lambda a: a.ctypes.data_as(c_double_p)
+        self._check(self.lib.uvs_validate_lines(self.h, len(Ps), p(Rs), p(Ps), p(ric), p(tic), n, start_frame.ctypes.data_as(c_int32_p),
+                                                p(ortho), p(sp_first), p(ep_first), flag.ctypes.data_as(c_int32_p),
+                                                p(ends) if want_end_points else None), "uvs_validate_lines")
+        return (flag, ends) if want_end_points else flag
 
     def triangulate_lines(self, Rs, Ps, ric, tic, frame_first, frame_last, sp_first, ep_first, sp_last, ep_last):
         """FeatureManager::triangulateLine on the device: orthonormal parameters [n][4] (see include/uvs.h)."""

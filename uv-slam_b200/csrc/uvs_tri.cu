@@ -178,6 +178,59 @@ __global__ void __launch_bounds__(128) k_triangulate_lines(TriLineArgs A) {
   out[3] = atan2(dn, nn);
 }
 
+// FeatureManager::setLineOrtho, the validity test (feature_manager.cpp:333-423): the line - from the orthonormal
+// parameters the FEATURE holds, i.e. before the solved ones are written back - is taken into the camera of its first
+// frame (Pluecker transform T_cw), intersected with the two planes through the viewing rays of the first observation's
+// end points, and is invalid (solve_flag 2) when either 3-D end point lies behind that camera.
+struct LineFlagArgs {
+  int n_frames, n_lines;
+  const double *Rs, *Ps;
+  double ric[9], tic[3];
+  const int *start_frame;
+  const double *ortho;             // [n_lines][4] psi_x, psi_y, psi_z, phi
+  const double *sp, *ep;           // [n_lines][3] end points of the first observation (z = 1)
+  int *flag;                       // [n_lines] 1 valid, 2 behind the camera
+  double *ends;                    // [n_lines][6] D_s_w, D_e_w (world end points, as the reference computes them) or null
+};
+
+__global__ void __launch_bounds__(128) k_line_flags(LineFlagArgs A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_lines) return;
+  const int i = A.start_frame[t];
+  if (i < 0 || i >= A.n_frames) { A.flag[t] = 2; return; }
+  const double *o = A.ortho + 4 * (size_t)t;
+  double sa, ca, sb, cb, sc, cc, sp, cp;
+  sincos(o[0], &sa, &ca); sincos(o[1], &sb, &cb); sincos(o[2], &sc, &cc); sincos(o[3], &sp, &cp);
+  // Rx(a) Ry(b) Rz(c): column 0 and column 1
+  const d3 u0 = mk3(cb * cc, ca * sc + sa * sb * cc, sa * sc - ca * sb * cc);
+  const d3 u1 = mk3(-cb * sc, ca * cc - sa * sb * sc, sa * cc + ca * sb * sc);
+  const d3 nw = cp * u0, dw = sp * u1;
+  const m33 ric = ldm(A.ric);
+  const d3 tic = mk3(A.tic[0], A.tic[1], A.tic[2]);
+  const m33 Ri = ldm(A.Rs + 9 * (size_t)i);
+  const m33 Rwc = mmul(Ri, ric);
+  const d3 twc = mvec(Ri, tic) + mk3(A.Ps[3 * i], A.Ps[3 * i + 1], A.Ps[3 * i + 2]);
+  // l_c = T_cw l_w:  n_c = R^T n_w + [-R^T t]x R^T d_w,  d_c = R^T d_w
+  const d3 dc = mtvec(Rwc, dw);
+  const d3 mt = mtvec(Rwc, twc);
+  const d3 nc = mtvec(Rwc, nw) - cross(mt, dc);
+  const double *ps = A.sp + 3 * (size_t)t, *pe = A.ep + 3 * (size_t)t;
+  const d3 s2 = mk3(ps[0], ps[1], ps[2]), e2 = mk3(pe[0], pe[1], pe[2]);
+  const double slope = -(e2.x - s2.x) / (e2.y - s2.y);     // scale = 1 (a horizontal segment divides by zero, as in the reference)
+  const d3 s2p = mk3(s2.x + 1.0, slope + s2.y, 1.0), e2p = mk3(e2.x + 1.0, slope + e2.y, 1.0);
+  const d3 pis = cross(s2, s2p), pie = cross(e2, e2p);
+  // D = L_c [pi; 0] with L_c = [[n_c]x d_c; -d_c^T 0]:  D.xyz = n_c x pi, D.w = -d_c . pi
+  const d3 ds = cross(nc, pis), de = cross(nc, pie);
+  const double ws = -dot(dc, pis), we = -dot(dc, pie);
+  const d3 Ds = mk3(ds.x / ws, ds.y / ws, ds.z / ws), De = mk3(de.x / we, de.y / we, de.z / we);
+  A.flag[t] = (Ds.z < 0.0 || De.z < 0.0) ? 2 : 1;
+  if (A.ends) {
+    const d3 a = mvec(Rwc, Ds) + twc, b = mvec(Rwc, De) + twc;
+    double *q = A.ends + 6 * (size_t)t;
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = b.x; q[4] = b.y; q[5] = b.z;
+  }
+}
+
 }  // namespace uvs
 
 using namespace uvs;
@@ -270,5 +323,49 @@ extern "C" int uvs_triangulate_lines(UvsHandle *h, int32_t n_frames, const doubl
     return handle_fail(h, UVS_ERR_CUDA, "uvs_triangulate_lines: D2H");
   if (cudaStreamSynchronize(st) != cudaSuccess) return handle_fail(h, UVS_ERR_CUDA, "uvs_triangulate_lines: sync");
   std::memcpy(ortho_out, hs + o_out, (size_t)n_lines * 4 * Dd);
+  return UVS_OK;
+}
+
+extern "C" int uvs_validate_lines(UvsHandle *h, int32_t n_frames, const double *Rs, const double *Ps, const double *ric, const double *tic,
+                                  int32_t n_lines, const int32_t *start_frame, const double *ortho, const double *sp_first,
+                                  const double *ep_first, int32_t *solve_flag, double *end_points) {
+  if (!h || n_frames <= 0 || n_lines <= 0 || !Rs || !Ps || !ric || !tic || !start_frame || !ortho || !sp_first || !ep_first || !solve_flag)
+    return handle_fail(h, UVS_ERR_INVALID_ARG, "uvs_validate_lines: bad arguments");
+  if (cudaSetDevice(h->device) != cudaSuccess) return handle_fail(h, UVS_ERR_CUDA, "cudaSetDevice");
+  const size_t Dd = sizeof(double), L3 = (size_t)n_lines * 3 * Dd;
+  size_t o = 0;
+  const size_t o_R = o; o += al256((size_t)n_frames * 9 * Dd);
+  const size_t o_P = o; o += al256((size_t)n_frames * 3 * Dd);
+  const size_t o_sf = o; o += al256((size_t)n_lines * sizeof(int));
+  const size_t o_or = o; o += al256((size_t)n_lines * 4 * Dd);
+  const size_t o_a = o; o += al256(L3);
+  const size_t o_b = o; o += al256(L3);
+  const size_t in_end = o;
+  const size_t o_fl = o; o += al256((size_t)n_lines * sizeof(int));
+  const size_t o_en = o; o += al256((size_t)n_lines * 6 * Dd);
+  int rc = handle_ensure_scratch(h, o); if (rc) return rc;
+  rc = handle_ensure_hscratch(h, o); if (rc) return rc;
+  char *hs = h->hscratch.base, *ds = h->scratch.base;
+  std::memcpy(hs + o_R, Rs, (size_t)n_frames * 9 * Dd); std::memcpy(hs + o_P, Ps, (size_t)n_frames * 3 * Dd);
+  std::memcpy(hs + o_sf, start_frame, (size_t)n_lines * sizeof(int)); std::memcpy(hs + o_or, ortho, (size_t)n_lines * 4 * Dd);
+  std::memcpy(hs + o_a, sp_first, L3); std::memcpy(hs + o_b, ep_first, L3);
+  cudaStream_t st = h->stream;
+  if (cudaMemcpyAsync(ds, hs, in_end, cudaMemcpyHostToDevice, st) != cudaSuccess) return handle_fail(h, UVS_ERR_CUDA, "uvs_validate_lines: H2D");
+  LineFlagArgs A;
+  A.n_frames = n_frames; A.n_lines = n_lines;
+  A.Rs = (const double *)(ds + o_R); A.Ps = (const double *)(ds + o_P);
+  for (int k = 0; k < 9; k++) A.ric[k] = ric[k];
+  for (int k = 0; k < 3; k++) A.tic[k] = tic[k];
+  A.start_frame = (const int *)(ds + o_sf); A.ortho = (const double *)(ds + o_or);
+  A.sp = (const double *)(ds + o_a); A.ep = (const double *)(ds + o_b);
+  A.flag = (int *)(ds + o_fl); A.ends = end_points ? (double *)(ds + o_en) : nullptr;
+  k_line_flags<<<(n_lines + 127) / 128, 128, 0, st>>>(A);
+  h->launches++;
+  if (cudaGetLastError() != cudaSuccess) return handle_fail(h, UVS_ERR_CUDA, "uvs_validate_lines: launch");
+  if (cudaMemcpyAsync(hs + o_fl, ds + o_fl, o - o_fl, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    return handle_fail(h, UVS_ERR_CUDA, "uvs_validate_lines: D2H");
+  if (cudaStreamSynchronize(st) != cudaSuccess) return handle_fail(h, UVS_ERR_CUDA, "uvs_validate_lines: sync");
+  std::memcpy(solve_flag, hs + o_fl, (size_t)n_lines * sizeof(int));
+  if (end_points) std::memcpy(end_points, hs + o_en, (size_t)n_lines * 6 * Dd);
   return UVS_OK;
 }
