@@ -50,12 +50,17 @@ __device__ __forceinline__ void proj_eval(const double *__restrict__ pose_i, con
   double r0 = S * (pcj.x * iz - pts_j.x), r1 = S * (pcj.y * iz - pts_j.y);
   const double s = r0 * r0 + r1 * r1;
   double sq = 1.0;
+  // half_rho == nullptr: the caller does not need the cost (see cauchy_rho1)
   if (correct && loss_a > 0.0) {
-    double rho0, rho1;
-    cauchy(loss_a, s, rho0, rho1);
-    *half_rho = 0.5 * rho0;
-    sq = sqrt(rho1);
-  } else {
+    if (half_rho) {
+      double rho0, rho1;
+      cauchy(loss_a, s, rho0, rho1);
+      *half_rho = 0.5 * rho0;
+      sq = sqrt(rho1);
+    } else {
+      sq = sqrt(cauchy_rho1(loss_a, s));
+    }
+  } else if (half_rho) {
     *half_rho = 0.5 * s;
   }
   r[0] = sq * r0; r[1] = sq * r1;
@@ -194,6 +199,7 @@ template <bool kJac, bool kQw>
 struct LineSink {
   double spx, spy, epx, epy, lf, loss_a;
   bool correct;
+  bool want_cost = true;   // false: rho' only, half_rho stays 0 (linearisation after iteration 0, cost-free sweeps)
   int PW;
   double *out_r, *out_jp, *out_jl;
   double half_rho;
@@ -209,8 +215,10 @@ struct LineSink {
     const double r0 = lf * ds * irho, r1 = lf * de * irho;
     const double s = r0 * r0 + r1 * r1;
     sq = 1.0;
-    if (correct && loss_a > 0.0) { double rho0, rho1; cauchy(loss_a, s, rho0, rho1); half_rho = 0.5 * rho0; sq = sqrt(rho1); }
-    else half_rho = 0.5 * s;
+    if (correct && loss_a > 0.0) {
+      if (want_cost) { double rho0, rho1; cauchy(loss_a, s, rho0, rho1); half_rho = 0.5 * rho0; sq = sqrt(rho1); }
+      else { half_rho = 0.0; sq = sqrt(cauchy_rho1(loss_a, s)); }
+    } else half_rho = 0.5 * s;
     out_r[0] = sq * r0; out_r[1] = sq * r1;
   }
   __device__ __forceinline__ void partial(int k, d3 dn, d3) {
@@ -229,6 +237,7 @@ struct VpSink {
   d3 vp;
   double vf, loss_a;
   bool correct;
+  bool want_cost = true;
   double *out_r, *out_jp, *out_jl;
   double half_rho;
   d3 dvec;
@@ -243,8 +252,10 @@ struct VpSink {
     const double r0 = vf * acos(ac);
     const double s = r0 * r0;
     double sq = 1.0;
-    if (correct && loss_a > 0.0) { double rho0, rho1; cauchy(loss_a, s, rho0, rho1); half_rho = 0.5 * rho0; sq = sqrt(rho1); }
-    else half_rho = 0.5 * s;
+    if (correct && loss_a > 0.0) {
+      if (want_cost) { double rho0, rho1; cauchy(loss_a, s, rho0, rho1); half_rho = 0.5 * rho0; sq = sqrt(rho1); }
+      else { half_rho = 0.0; sq = sqrt(cauchy_rho1(loss_a, s)); }
+    } else half_rho = 0.5 * s;
     out_r[0] = sq * r0;
     if (kJac) {
       g = sq * vf * (c < 0.0 ? 1.0 : -1.0) * rsqrt(1.0 - ac * ac);

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(LP_NT, kThreadsPerSM / LP_NT) k_lin_points(Dev
   if (nmax == 0) return;   // uniform over the warp
   int fo = 0, co = 0, d = 0, cur = 0;
   long long s_off = 0;
-  if (act) { fo = D.frame_off[w]; co = D.cam_off[w]; d = D.cam_off[w + 1] - co; s_off = D.S_off[w]; cur = D.cur[w]; }
+  bool need_cost = false;   // the cost of the linearisation point is only used at iteration 0 (uvs_math.cuh cauchy_rho1)
+  if (act) { fo = D.frame_off[w]; co = D.cam_off[w]; d = D.cam_off[w + 1] - co; s_off = D.S_off[w]; cur = D.cur[w]; need_cost = D.ctl[w].iter == 0; }
   const double *ex = D.ex[cur] + 7 * (size_t)w;
   const double lam = act ? D.inv_depth[cur][gp] : 1.0;
   double colsq = 0.0, gk = 0.0, half = 0.0;
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(LP_NT, kThreadsPerSM / LP_NT) k_lin_points(Dev
       ri = ix.x; rj = ix.y; row_i = ri;
       const d3 pi = pts_i, pj = pts_j;
       if (kPrefetch && k + 1 < n) load_step(k + 1);
-      double jl[2], hr;
+      double jl[2], hr = 0.0;
       proj_eval<true, false>(D.pose[cur] + 7 * (size_t)ri, D.pose[cur] + 7 * (size_t)rj, ex, lam, pi, pj, P.S, nullptr, false,
-                             P.cauchy_point, true, 6, row, row + 2, row + 14, nullptr, jl, nullptr, &hr);
+                             P.cauchy_point, true, 6, row, row + 2, row + 14, nullptr, jl, nullptr, need_cost ? &hr : nullptr);
       half += hr;
       const double j0 = jl[0], j1 = jl[1];
       colsq += j0 * j0 + j1 * j1;
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(LL_NT, kOcc) k_lin_lines(Dev D, Params P, Stas
   const int l0 = blockIdx.x * (LL_NT / LPL);
   if (l0 >= nl) return;
   if (!(D.ctl[w].state & WS_ACTIVE)) return;
+  const bool need_cost = D.ctl[w].iter == 0;   // the cost of the linearisation point is only used at iteration 0
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // shared: frame tables [max_frames][FT_STRIDE] | per warp: line stage [WSLOTS][REC_LINE], VP stage [WSLOTS][REC_VP],
   //         frame of a slot (-1 = empty), VP flag, row list of the direct-term grouping
@@ -331,6 +333,7 @@ __global__ void __launch_bounds__(LL_NT, kOcc) k_lin_lines(Dev D, Params P, Stas
     LineVpSinkF<true> sink;
     sink.ln.spx = __ldg(sp); sink.ln.spy = __ldg(sp + 1); sink.ln.epx = __ldg(ep); sink.ln.epy = __ldg(ep + 1);
     sink.ln.lf = P.line_factor; sink.ln.loss_a = P.cauchy_line; sink.ln.correct = true; sink.ln.PW = 6;
+    sink.ln.want_cost = sink.vp.want_cost = need_cost;
     sink.has_vp = ix.w >= 0;
     sink.vp.half_rho = 0.0;
     if (ix.w >= 0) {

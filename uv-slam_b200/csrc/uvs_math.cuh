@@ -110,5 +110,11 @@ __device__ __forceinline__ void cauchy(double a, double s, double &rho0, double 
   rho0 = b * log(sum);
   rho1 = fmax(inv, 2.2250738585072014e-308);
 }
+// rho' alone: what the loss correction of a Jacobian needs.  The cost rho (one FP64 log per factor, ~45 instructions) is only
+// used from a linearisation at iteration 0 (afterwards the cost of an iterate is the candidate cost that accepted it)
+__device__ __forceinline__ double cauchy_rho1(double a, double s) {
+  const double c = 1.0 / (a * a);
+  return fmax(1.0 / (1.0 + s * c), 2.2250738585072014e-308);
+}
 
 }  // namespace uvs

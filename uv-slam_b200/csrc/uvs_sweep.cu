@@ -130,10 +130,12 @@ __global__ void __launch_bounds__(NT, kOcc) k_proj(Dev D, Params P, int mode, in
       tdp.tr_over_row = P.tr_over_row; tdp.half_row = P.half_row;
     }
     const bool want_ex = mode == 0 || (wflags & WF_EXTRINSIC);
+    // the cost of a Jacobian-mode sweep is only used at iteration 0 of a solve (and by nobody when no accumulator is given)
+    const bool want_cost = cost != nullptr && (!kJac || mode == 0 || D.ctl[ix.w].iter == 0);
     if (kJac) {
       double *t = tile + threadIdx.x * (REC + 1);
       proj_eval<true, kTd>(pi, pj, ex, lam, pts_i, pts_j, P.S, &tdp, want_ex, P.cauchy_point, !kCeres, PW, t, t + 2, t + 2 + 2 * PW,
-                           t + 2 + 4 * PW, t + 2 + 6 * PW, t + 2 + 6 * PW + 2, &half_rho);
+                           t + 2 + 4 * PW, t + 2 + 6 * PW, t + 2 + 6 * PW + 2, want_cost ? &half_rho : nullptr);
       if (kCeres) {
 #pragma unroll
         for (int row = 0; row < 2; row++) { t[2 + row * 7 + 6] = 0.0; t[2 + 14 + row * 7 + 6] = 0.0; t[2 + 28 + row * 7 + 6] = 0.0; }
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(NT, kOcc) k_proj(Dev D, Params P, int mode, in
     } else {
       double r[2];
       proj_eval<false, kTd>(pi, pj, ex, lam, pts_i, pts_j, P.S, &tdp, want_ex, P.cauchy_point, true, 6, r, nullptr, nullptr, nullptr,
-                            nullptr, nullptr, &half_rho);
+                            nullptr, nullptr, want_cost ? &half_rho : nullptr);
       if (res_out) { res_out[2 * (size_t)f] = r[0]; res_out[2 * (size_t)f + 1] = r[1]; }
     }
   }
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode,
     LineVpSink<kJac> sink;
     sink.ln.spx = __ldg(sp); sink.ln.spy = __ldg(sp + 1); sink.ln.epx = __ldg(ep); sink.ln.epy = __ldg(ep + 1);
     sink.ln.lf = P.line_factor; sink.ln.loss_a = P.cauchy_line; sink.ln.correct = true; sink.ln.PW = 6;
+    sink.ln.want_cost = sink.vp.want_cost = cost != nullptr && (!kJac || mode == 0 || D.ctl[w].iter == 0);
     vi = ix.w;
     sink.has_vp = vi >= 0;
     sink.vp.half_rho = 0.0;
