@@ -5,6 +5,9 @@
 TAG=${1:-fin}
 mkdir -p gpurun_out
 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.txt 2>&1; tail -1 gpurun_out/${TAG}_smoke.txt
+# ncu --set full of the materialised sweep kernels first: the bench lines below report its DRAM bytes as roofline.traffic
+bash tools/gpu_sweep_ncu.sh ${TAG} > /dev/null 2>&1
+python tools/ncu_summary.py gpurun_out/${TAG}_sweep.ncu-rep gpurun_out/${TAG}_sweep_ncu.json --windows 1184 --sweep --command "ncu --set full --clock-control none --import-source on -k regex:k_line_vp|k_imu_geom|k_imu_weight|k_proj|k_prior\$ --launch-skip 10 -c 5 python tools/sweep_probe.py 3" && cp gpurun_out/${TAG}_sweep_ncu.json profiles/r2_sweep_ncu.json
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_C2_reference.json 2> gpurun_out/${TAG}_ref.err
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_C2.json 2> gpurun_out/${TAG}_bench_C2.err
 timeout 900 python bench.py --check 8 --no-cpu --steps 5 > gpurun_out/${TAG}_bench_C2_check.json 2> gpurun_out/${TAG}_bench_C2.err
