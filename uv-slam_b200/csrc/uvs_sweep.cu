@@ -76,8 +76,16 @@ __device__ __forceinline__ void flush_tile(const double *tile, const unsigned ch
   constexpr int DF = NT / REC, DC = NT % REC;   // element e + NT lies DF records and DC columns further
   int e = threadIdx.x;
   int f = e / REC, c = e - f * REC;
-  if (all_ok) {
-    // element (f, c) sits at tile[f (REC + 1) + c] = tile[e + f]
+  if (all_ok && count == NT) {
+    // full tile: element e = (f, c) sits at tile[f (REC + 1) + c] = tile[e + f]; the trip count and the divisor are compile-time
+    // constants, so an element costs a multiply-high, an add, the load and the store (the carried (f, c) update cost twice that:
+    // the write-back loops were a third of the instructions of k_line_vp<1>)
+#pragma unroll 4
+    for (int i = 0; i < REC; i++) {
+      const int x = threadIdx.x + NT * i;
+      dst[x] = tile[x + x / REC];
+    }
+  } else if (all_ok) {
 #pragma unroll 4
     for (; e < total; e += NT) {
       dst[e] = tile[e + f];
@@ -315,15 +323,11 @@ __global__ void __launch_bounds__(NT, kOcc) k_line_vp(Dev D, Params P, int mode,
     const bool all_ok = __syncthreads_and(valid || f >= a1) != 0;
     flush_tile<REC_LINE>(tile, ok, out_line, first, min(NT, a1 - first), all_ok);
     {
-      constexpr int DF = NT / REC_VP, DC = NT % REC_VP;
-      int e = threadIdx.x;
-      int slot = e / REC_VP, c = e - slot * REC_VP;
-#pragma unroll 4
-      for (; e < NT * REC_VP; e += NT) {
+#pragma unroll
+      for (int i = 0; i < REC_VP; i++) {
+        const int e = threadIdx.x + NT * i, slot = e / REC_VP, c = e - slot * REC_VP;
         const int v = vslot[slot];
         if (v >= 0) out_vp[(size_t)v * REC_VP + c] = vtile[e + slot];
-        slot += DF; c += DC;
-        if (c >= REC_VP) { c -= REC_VP; slot++; }
       }
     }
   }
