@@ -978,7 +978,7 @@ __device__ bool chain_solve(double *smem, int nthr, unsigned short *s_pair, int 
 #define CHOL_TS(i) do { } while (0)
 #endif
 
-// kMode: 0 = in place in global memory (large windows), 1 = dense blocked in shared memory, 2 = chain mode (barrier-phased),
+// kMode: 0 = dense blocked, factor in a per-window global scratch (large windows), 1 = dense blocked in shared memory, 2 = chain mode (barrier-phased),
 //        3 = chain mode (warp-specialised pipeline)
 template <int kMode>
 __device__ void chol_window(const Dev &D, const Params &P, int w, double *smem, bool mc_identity) {
